@@ -1,0 +1,186 @@
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/* by running the UNMODIFIED reference.
+
+Run in the build container (where /root/reference exists):
+
+    PYTHONDONTWRITEBYTECODE=1 python -m oracle.make_golden
+
+The reference itself is the source of every number written here; the restatement in
+`oracle/xdeepfm_oracle.py` is only used for its deterministic parameter/input builders
+(`make_params`, `make_inputs`) so that tests can regenerate identical inputs on the GPU box.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+
+from oracle.ref_loader import load_reference  # noqa: E402
+from oracle.xdeepfm_oracle import ModelSpec, make_inputs, make_params  # noqa: E402
+
+load_reference()
+from deepctr.inputs import DenseFeat, SparseFeat  # noqa: E402
+from deepctr.layers.interaction import CIN  # noqa: E402
+from deepctr.models import xDeepFM, xDeepFMAttention, xDeepFMAttentionV2  # noqa: E402
+
+
+def spec_to_json(spec: ModelSpec):
+    d = dict(spec.__dict__)
+    d["cin_layer_size"] = list(d["cin_layer_size"])
+    d["dnn_hidden_units"] = list(d["dnn_hidden_units"])
+    return d
+
+
+def build_reference_model(spec: ModelSpec, **extra):
+    cols = [SparseFeat(n, v, spec.embedding_dim) for n, v in zip(spec.sparse_names, spec.vocab_sizes)] + \
+           [DenseFeat(n, 1) for n in spec.dense_names]
+    common = dict(dnn_hidden_units=spec.dnn_hidden_units, cin_layer_size=spec.cin_layer_size,
+                  cin_split_half=spec.cin_split_half, cin_activation=spec.cin_activation,
+                  l2_reg_linear=spec.l2_reg_linear, l2_reg_embedding=spec.l2_reg_embedding,
+                  l2_reg_dnn=spec.l2_reg_dnn, l2_reg_cin=spec.l2_reg_cin, device="cpu")
+    common.update(extra)
+    if spec.variant == "xdeepfm":
+        return xDeepFM(cols, cols, **common)
+    if spec.variant == "attn":
+        return xDeepFMAttention(cols, cols, cin_num_heads=spec.num_heads, cin_use_layer_norm=spec.use_layer_norm,
+                                cin_use_residual=spec.use_residual, **common)
+    return xDeepFMAttentionV2(cols, cols, cin_num_heads=spec.num_heads, cin_use_layer_norm=spec.use_layer_norm,
+                              cin_use_residual=spec.use_residual, cin_num_attn_layers=spec.num_attn_layers, **common)
+
+
+def cin_kat():
+    """RNG-free known-answer test of the reference CIN (recipe from SURVEY.md 8c)."""
+    cin = CIN(3, (4, 2), "relu", True)
+    K = [9, 6]
+    with torch.no_grad():
+        for l, conv in enumerate(cin.conv1ds):
+            H = conv.weight.shape[0]
+            W = torch.tensor([[(((h * K[l] + k) * 3) % 7 - 2) / 10 for k in range(K[l])] for h in range(H)])
+            conv.weight.copy_(W.unsqueeze(-1))
+            conv.bias.copy_(torch.tensor([(h + 1) / 10 for h in range(H)]))
+    x = torch.tensor([((2 * i) % 5 - 1) / 2 for i in range(12)], dtype=torch.float32).reshape(2, 3, 2).requires_grad_(True)
+    out = cin(x)
+    out.sum().backward()
+    kat = {
+        "recipe": "W_l[h,k,0]=(((h*K_l+k)*3)%7-2)/10 (K_0=9,K_1=6); b_l[h]=(h+1)/10; x.flat[i]=((2*i)%5-1)/2; x:[2,3,2]; L=out.sum()",
+        "x": x.detach().flatten().tolist(),
+        "out": out.detach().tolist(),
+        "dx": x.grad.flatten().tolist(),
+        "dW0": cin.conv1ds[0].weight.grad.flatten().tolist(),
+        "dW1": cin.conv1ds[1].weight.grad.flatten().tolist(),
+        "db0": cin.conv1ds[0].bias.grad.tolist(),
+        "db1": cin.conv1ds[1].bias.grad.tolist(),
+    }
+    with open(os.path.join(GOLD, "cin_kat.json"), "w") as f:
+        json.dump(kat, f, indent=1)
+    print("cin_kat out", kat["out"])
+
+
+def forward_backward_case(name, spec: ModelSpec, B, seed, store_params=True, grad_keys=None, zipf=False):
+    """y_pred / BCE-sum / total loss / parameter gradients of one reference train-step (no optimizer)."""
+    params = make_params(spec, seed=seed)
+    X, y = make_inputs(spec, B, seed=seed, zipf=zipf)
+    model = build_reference_model(spec)
+    missing = model.load_state_dict(params, strict=True)
+    model.train()
+    y_pred = model(X).squeeze()
+    loss = torch.nn.functional.binary_cross_entropy(y_pred, y, reduction="sum")   # basemodel.py:254
+    reg = model.get_regularization_loss()                                          # basemodel.py:255
+    total = loss + reg + model.aux_loss
+    model.zero_grad()
+    total.backward()
+    out = {"X": X.numpy(), "y": y.numpy(), "y_pred": y_pred.detach().numpy(),
+           "loss": loss.detach().numpy(), "reg_loss": reg.detach().numpy(), "total": total.detach().numpy()}
+    named = dict(model.named_parameters())
+    for k, p in named.items():
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        if grad_keys is None or k in grad_keys:
+            out["grad::" + k] = g.numpy()
+        out["gradnorm::" + k] = np.float64(g.double().norm().item())
+    model.eval()
+    with torch.no_grad():
+        out["y_pred_eval"] = model(X).numpy()
+    if store_params:
+        for k, v in params.items():
+            out["param::" + k] = v.numpy()
+    else:
+        out["param_checksum"] = np.float64(sum(v.double().sum().item() for v in params.values()))
+    out["spec_json"] = np.array(json.dumps(spec_to_json(spec)))
+    out["seed"] = np.int64(seed)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(name, "loss", float(loss), "total", float(total), "y_pred[:3]", y_pred[:3].tolist())
+
+
+def fit_case(name, spec: ModelSpec, N, batch_size, epochs, optimizer, seed, lr=None):
+    """Trajectory of the reference's own fit(): History['loss'] per epoch + final weights + predictions."""
+    params = make_params(spec, seed=seed)
+    X, y = make_inputs(spec, N, seed=seed)
+    model = build_reference_model(spec)
+    model.load_state_dict(params, strict=True)
+    model.compile(optimizer, "binary_crossentropy", metrics=["binary_crossentropy", "auc"])
+    if lr is not None:
+        for gparam in model.optim.param_groups:       # xdftrain.py:282-284
+            gparam["lr"] = lr
+    names = list(model.feature_index.keys())
+    xdict = {n: X[:, i].numpy().copy() for i, n in enumerate(names)}
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        hist = model.fit(xdict, y.numpy().reshape(-1, 1), batch_size=batch_size, epochs=epochs, verbose=0,
+                         shuffle=False, validation_data=(dict(xdict), y.numpy().reshape(-1, 1)))
+        pred = model.predict(dict(xdict), batch_size=batch_size)
+    out = {"X": X.numpy(), "y": y.numpy(), "pred": pred,
+           "history_loss": np.array(hist.history["loss"], dtype=np.float64),
+           "history_val_auc": np.array(hist.history["val_auc"], dtype=np.float64),
+           "history_val_bce": np.array(hist.history["val_binary_crossentropy"], dtype=np.float64),
+           "spec_json": np.array(json.dumps(spec_to_json(spec))), "seed": np.int64(seed),
+           "batch_size": np.int64(batch_size), "epochs": np.int64(epochs), "optimizer": np.array(optimizer),
+           "lr": np.float64(-1.0 if lr is None else lr)}
+    for k, v in params.items():
+        out["param::" + k] = v.numpy()
+    for k, v in model.state_dict().items():
+        out["final::" + k] = v.numpy()
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(name, "history loss", hist.history["loss"], "val_auc", hist.history["val_auc"])
+
+
+def small_spec(**kw):
+    base = dict(sparse_names=["C%d" % i for i in range(1, 6)], vocab_sizes=[7, 13, 50, 3, 29], embedding_dim=8,
+                dense_names=["I1", "I2", "I3"], cin_layer_size=(16, 8), dnn_hidden_units=(32, 16),
+                l2_reg_linear=1e-3, l2_reg_embedding=1e-3, l2_reg_dnn=1e-3, l2_reg_cin=1e-3)
+    base.update(kw)
+    return ModelSpec(**base)
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(4)
+    cin_kat()
+    forward_backward_case("xdeepfm_small", small_spec(), B=32, seed=1)
+    forward_backward_case("xdeepfm_small_nosplit", small_spec(cin_split_half=False, cin_layer_size=(6, 5, 4)), B=17, seed=2)
+    forward_backward_case("xdeepfm_small_linearact", small_spec(cin_activation="linear", cin_layer_size=(8, 6, 3)), B=9, seed=3)
+    forward_backward_case("xdeepfm_small_nodense", small_spec(dense_names=[], embedding_dim=4), B=16, seed=4)
+    forward_backward_case("xdeepfm_small_zipf", small_spec(vocab_sizes=[1000, 13, 5000, 3, 29]), B=64, seed=5, zipf=True)
+    forward_backward_case("attn_small", small_spec(variant="attn", num_heads=4), B=12, seed=6)
+    forward_backward_case("attn_small_3heads", small_spec(variant="attn", num_heads=3, embedding_dim=10), B=8, seed=7)
+    forward_backward_case("attn_v2_small", small_spec(variant="attn_v2", num_heads=2, num_attn_layers=2), B=12, seed=8)
+    # BASELINE.json config 1 shape (26 sparse + 13 dense, D=8, CIN (256,128), DNN (256,256)); vocab 100/field
+    cfg1 = ModelSpec(sparse_names=["C%d" % i for i in range(1, 27)], vocab_sizes=[100] * 26, embedding_dim=8,
+                     dense_names=["I%d" % i for i in range(1, 14)])
+    keep = {"embedding_dict.C1.weight", "embedding_dict.C26.weight", "linear_model.embedding_dict.C3.weight",
+            "linear_model.weight", "out.bias", "cin.conv1ds.0.bias", "cin.conv1ds.1.bias", "cin_linear.weight",
+            "dnn.linears.1.bias", "dnn_linear.weight"}
+    forward_backward_case("xdeepfm_cfg1", cfg1, B=64, seed=9, store_params=False, grad_keys=keep)
+    fit_case("fit_small_adam", small_spec(), N=96, batch_size=32, epochs=3, optimizer="adam", seed=11, lr=1e-2)
+    fit_case("fit_small_sgd", small_spec(), N=96, batch_size=32, epochs=2, optimizer="sgd", seed=12)
+    fit_case("fit_small_adagrad", small_spec(), N=80, batch_size=32, epochs=2, optimizer="adagrad", seed=13)
+    fit_case("fit_small_rmsprop", small_spec(), N=80, batch_size=32, epochs=2, optimizer="rmsprop", seed=14, lr=1e-3)
+
+
+if __name__ == "__main__":
+    main()
