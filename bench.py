@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""Benchmark of the xDeepFM training hot path (BASELINE.json metric: train samples/sec, Criteo-shape xDeepFM).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload cfg2]
+
+One "step" = one full training step (fused gather -> CIN -> DNN -> head -> BCE -> backward -> sorted scatter-add ->
+fused Adam incl. the reference's dense-table L2/Adam semantics) over one batch of synthetic Criteo-shaped input.
+Prints ONE JSON line on rank 0 (see the task contract): `value` = device-resident throughput, `e2e` = the same step
+through the public `train_on_batch` API with pinned-host inputs (H2D + D2H inside the timed region), `roofline` for the
+dominant kernel (timed live with CUDA events), `cpu_baseline` = the CPU oracle port on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "xdeepfm-pytorch_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+# Kaggle Display-Advertising-Challenge cardinalities of C1..C26 (assumption stated in SURVEY.md 8d; the reference ships no data)
+CRITEO_VOCAB = [1460, 583, 10131227, 2202608, 305, 24, 12517, 633, 3, 93145, 5683, 8351593, 3194, 27, 14992, 5461306, 10,
+                5652, 2173, 4, 7046547, 18, 15, 286181, 105, 142572]
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on
+    "cfg2": dict(m=26, nd=13, D=16, cin=(200, 200, 200), dnn=(400, 400), batch=8192, vocab=CRITEO_VOCAB),
+    # BASELINE.json configs[0] (reference's CPU-runnable case) -- parity-test shape, selectable for quick runs
+    "cfg1": dict(m=26, nd=13, D=8, cin=(256, 128), dnn=(256, 256), batch=256, vocab=[min(v, 100000) for v in CRITEO_VOCAB]),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d.get("hbm_gbs", 6650.0), tf_burst=d.get("bf16_tflops", 1590.0),
+                    tf_sust=d.get("bf16_tflops_sustained", 1400.0), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+def make_spec(w, vocab_cap=None):
+    from oracle.xdeepfm_oracle import ModelSpec
+    vocab = [min(v, vocab_cap) if vocab_cap else v for v in w["vocab"]]
+    return ModelSpec(sparse_names=["C%d" % i for i in range(1, w["m"] + 1)], vocab_sizes=vocab, embedding_dim=w["D"],
+                     dense_names=["I%d" % i for i in range(1, w["nd"] + 1)], cin_layer_size=tuple(w["cin"]),
+                     dnn_hidden_units=tuple(w["dnn"]))
+
+
+def synth_batches(spec, batch, n_batches, seed):
+    """Seeded synthetic Criteo-shaped batches: ids log-uniform (Zipf-like) per field, dense U[0,1), labels Bernoulli(0.25)."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n_batches):
+        cols = []
+        for V in spec.vocab_sizes:
+            u = torch.rand(batch, generator=g)
+            cols.append(torch.clamp((float(V) ** u).long() - 1, 0, V - 1).to(torch.int32))
+        ids = torch.stack(cols, 1).contiguous()
+        dense = torch.rand(batch, spec.nd, generator=g)
+        y = (torch.rand(batch, generator=g) < 0.25).float()
+        out.append((ids, dense, y))
+    return out
+
+
+def cin_flops_per_sample(spec):
+    """Algorithmic CIN FLOPs per sample, forward: 2*D*sum_k H_k*K_k; training = 3x."""
+    m, D = spec.m, spec.embedding_dim
+    prev, tot = m, 0
+    for k, H in enumerate(spec.cin_layer_size):
+        tot += H * prev * m
+        prev = H // 2 if spec.cin_split_half else H
+    return 2.0 * D * tot
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.sm_max = index, [], set(), False, None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5)
+                f = [x.strip() for x in r.stdout.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.sm_max = float(f[1])
+                for nme, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nme)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the reference's own algorithm on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_steps(spec, batch, steps, warmup, seed=2025):
+    """Time `steps` training steps (forward, BCE-sum + L2, backward, dense Adam) on the CPU.
+    Uses the unmodified reference when /root/reference exists (kind 'reference'), else the oracle port ('port')."""
+    from oracle import xdeepfm_oracle as O
+    from oracle.ref_loader import reference_available
+    torch.set_num_threads(os.cpu_count() or 1)
+    batches = synth_batches(spec, batch, 2, seed)
+    kind = "port"
+    if reference_available():
+        try:
+            from oracle.ref_loader import load_reference
+            load_reference_ok = True
+            # the product package is also called `deepctr`; the reference arm runs in its own process (see main)
+            load_reference()
+            from oracle.make_golden import build_reference_model
+            model = build_reference_model(spec)
+            model.compile("adam", "binary_crossentropy")
+            kind = "reference"
+        except Exception as e:  # pragma: no cover
+            print("reference import failed (%s); using the oracle port" % e, file=sys.stderr)
+            kind = "port"
+    if kind == "port":
+        params = {k: v.requires_grad_(True) for k, v in O.make_params(spec, seed=1).items()}
+        opt = torch.optim.Adam(list(params.values()))
+
+    def one_step(i):
+        ids, dense, y = batches[i % len(batches)]
+        X = torch.cat([ids.float(), dense], 1)
+        if kind == "reference":
+            y_pred = model(X).squeeze()
+            model.optim.zero_grad()
+            loss = torch.nn.functional.binary_cross_entropy(y_pred, y, reduction="sum")
+            total = loss + model.get_regularization_loss() + model.aux_loss
+            total.backward()
+            model.optim.step()
+        else:
+            opt.zero_grad()
+            loss, total = O.train_loss(params, spec, X, y)
+            total.backward()
+            opt.step()
+        return float(loss)
+
+    for i in range(warmup):
+        one_step(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one_step(warmup + i)
+    dt = time.perf_counter() - t0
+    return dict(samples_per_s=batch * steps / dt, ms_per_step=1e3 * dt / steps, kind=kind, cores=torch.get_num_threads())
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference_arm(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    spec = make_spec(w, args.ref_vocab_cap)
+    sample_batch = args.ref_batch
+    r = cpu_reference_steps(spec, sample_batch, max(1, args.steps), max(1, min(args.warmup, 1)))
+    sample = "%d-sample batches (of the %d-sample workload batch), vocab capped at %s rows/field, Adam, %d timed steps" % (
+        sample_batch, w["batch"], args.ref_vocab_cap, max(1, args.steps))
+    line = {"impl": "reference", "metric": "train samples/sec (Criteo-shape xDeepFM)", "value": r["samples_per_s"],
+            "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, w),
+            "cpu_baseline": {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"], "sample": sample},
+            "e2e": {"value": r["samples_per_s"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, w):
+    return {"workload": "%s: xDeepFM Criteo-shape, %d sparse + %d dense, emb_dim %d, CIN %s, DNN %s, batch %d/GPU, Adam, "
+                        "Criteo cardinalities (%.1fM rows), reference dense-table L2+Adam semantics" % (
+                            args.workload, w["m"], w["nd"], w["D"], tuple(w["cin"]), tuple(w["dnn"]), w["batch"], sum(w["vocab"]) / 1e6),
+            "batch_per_gpu": w["batch"], "optimizer": "adam", "cin_precision": args.cin_impl,
+            "l2_flush": "not needed: every step streams all tables + Adam state (%.1f GB) >> 126 MB L2" % (
+                sum(w["vocab"]) * (w["D"] + 1) * 4 * 3 / 1e9)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cin-impl", default="fp32")
+    ap.add_argument("--ref-batch", type=int, default=1024)
+    ap.add_argument("--ref-vocab-cap", type=int, default=100000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference_arm(args, w)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = "cuda:%d" % local_rank
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    from deepctr import _native, ops
+    from tests.helpers import build_product_model
+    peaks = load_peaks()
+    spec = make_spec(w)
+    B = w["batch"]
+    model = build_product_model(spec, dev)
+    # reference initialisation (init_std=1e-4 embeddings, default-init CIN) is what a user trains from
+    model.compile("adam", "binary_crossentropy")
+    if world > 1:
+        raise NotImplementedError("multi-GPU bench arm lands with deepctr.distributed")
+    n_pool = 4
+    host = [(i.pin_memory(), d.pin_memory(), y.pin_memory()) for i, d, y in synth_batches(spec, B, n_pool, seed=2025 + rank)]
+    devb = [(i.to(dev), d.to(dev), y.to(dev)) for i, d, y in host]
+    accum = torch.zeros(1, dtype=torch.float64, device=dev)
+    model.train()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up
+    for i in range(max(args.warmup, 3)):
+        model.train_step(*devb[i % n_pool], accum)
+    sync_all()
+    # ---- timed: device-resident inputs
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.TIMERS = {}
+    l0 = _native.lib().xdfm_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for i in range(args.steps):
+        model.train_step(*devb[i % n_pool], accum)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = _native.lib().xdfm_launch_count() - l0
+    timers = ops.timer_totals()
+    ops.TIMERS = None
+    # ---- timed: end-to-end through the public API with pinned host inputs
+    for i in range(2):
+        model.train_on_batch(*host[i % n_pool])
+    sync_all()
+    t0 = time.perf_counter()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(args.steps):
+        model.train_on_batch(*host[i % n_pool])
+    e3.record()
+    sync_all()
+    ms_e2e = max(e2.elapsed_time(e3), 1e3 * (time.perf_counter() - t0))
+    sampler.stop_flag = True
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+    if rank != 0:
+        return
+    value = B * world * args.steps / (ms / 1e3)
+    e2e = B * world * args.steps / (ms_e2e / 1e3)
+    # ---- roofline of the dominant kernel group: the CIN contraction (fwd + bwd)
+    cin_ms = sum(timers.get(k, (0.0, 0))[0] for k in ("cin_fwd", "cin_bwd"))
+    cin_calls = sum(timers.get(k, (0.0, 0))[1] for k in ("cin_fwd", "cin_bwd"))
+    flops_step = 3.0 * cin_flops_per_sample(spec) * B
+    achieved = flops_step * args.steps / (cin_ms / 1e3) / 1e12 if cin_ms > 0 else None
+    peak = peaks["tf_sust"]
+    roofline = {"bound": "tensor", "kernel": "CIN contraction (cin_fwd + cin_bwd launches, %d per step)" % (cin_calls // max(args.steps, 1)),
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
+                "traffic": None, "peak_source": "%s MEASURED_PEAKS.json bf16 sustained (kernel timed inside a long step)" % peaks["src"],
+                "share_of_step": cin_ms / ms if ms > 0 else None,
+                "other_ms_per_step": {k: v[0] / args.steps for k, v in timers.items()}}
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    line = {"metric": "train samples/sec (Criteo-shape xDeepFM)", "value": value, "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.cin_impl == "fp32" else "bf16", "data": "synthetic",
+            "config": workload_config(args, w), "clocks": sampler.summary(),
+            "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "roofline": roofline}
+    if not args.no_cpu_baseline and world == 1:
+        # bounded CPU sample in a separate process (the reference package shares the name `deepctr` with the product)
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1",
+                                "--workload", args.workload, "--ref-batch", str(args.ref_batch),
+                                "--ref-vocab-cap", str(args.ref_vocab_cap)], capture_output=True, text=True, timeout=600)
+            ref = json.loads(r.stdout.strip().splitlines()[-1])
+            line["cpu_baseline"] = ref["cpu_baseline"]
+        except Exception as e:  # pragma: no cover
+            line["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": "failed: %s" % e}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

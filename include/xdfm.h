@@ -1,0 +1,141 @@
+/* libxdfm_sm100a.so -- C ABI of the B200-native xDeepFM hot path.
+ *
+ * The reference (Syclus123/xDeepFM-pytorch) is pure Python/PyTorch and has NO FFI boundary of its own; its
+ * "operator API" is the deepctr Python class surface.  This header is therefore a NEW boundary: every entry point
+ * names the reference code (file:line under /root/reference) whose arithmetic it replaces.  The Python host side
+ * (xdeepfm-pytorch_b200/deepctr) binds these symbols with ctypes and keeps the reference's
+ * class/ctor/state_dict surface.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers unless marked "host".
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on that stream (no sync, no
+ *     allocation; workspaces are caller-provided, sized by the matching *_workspace_bytes()).
+ *   - return value 0 = ok; non-zero = error, message via xdfm_last_error().
+ *   - row-major fp32 unless stated.  B = batch, m = sparse fields, D = embedding dim, nd = dense features.
+ */
+#ifndef XDFM_H_
+#define XDFM_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XDFM_MAX_FIELDS 64
+#define XDFM_MAX_DENSE 256
+
+#define XDFM_ACT_NONE 0
+#define XDFM_ACT_RELU 1
+#define XDFM_ACT_TANH 2
+#define XDFM_ACT_SIGMOID 3
+
+#define XDFM_OPT_SGD 0
+#define XDFM_OPT_ADAM 1
+#define XDFM_OPT_ADAGRAD 2
+#define XDFM_OPT_RMSPROP 3
+
+/* optimizer hyper-parameters (torch.optim defaults are applied by the Python side: basemodel.py:447-461) */
+typedef struct {
+  int32_t kind;     /* XDFM_OPT_* */
+  float lr;
+  float beta1;      /* adam */
+  float beta2;      /* adam */
+  float eps;
+  float alpha;      /* rmsprop */
+  float lr_decay;   /* adagrad */
+  float l2;         /* L2 regulariser strength of the parameter group: loss term l2*sum(w^2) -> grad 2*l2*w */
+} xdfm_opt_cfg;
+
+const char* xdfm_last_error(void);
+int xdfm_version(void);
+/* compute capability of the current device * 10 (100 on B200); <0 on error */
+int xdfm_device_cc(void);
+/* kernels of this library launched so far by this process */
+long long xdfm_launch_count(void);
+
+/* ---- input split: replaces X[:, i:i+1].long() / X[:, a:b] column slicing (deepctr/models/basemodel.py:368-370, 377-378).
+ * X [B, ncol] fp32 (ids stored as floats); sparse_cols/dense_cols are HOST arrays of column indices.
+ * ids [B, m] int32 (truncation toward zero == .long()), dense [B, nd] fp32. */
+int xdfm_split_input(const float* X, int64_t B, int ncol, const int32_t* sparse_cols, int m, const int32_t* dense_cols, int nd,
+                     int32_t* ids, float* dense, void* stream);
+
+/* ---- fused multi-table embedding gather + first-order term.
+ * replaces input_from_feature_columns (basemodel.py:354-380), torch.cat(.., dim=1) (xdeepfm.py:86) and
+ * Linear.forward (basemodel.py:63-92).
+ * tables / lin_tables: HOST arrays (length m, one entry per FEATURE) of device pointers to [V_f, D] / [V_f, 1] fp32.
+ * vocab: HOST array of V_f (ids are clamped into range).  out_emb [B, m, D]; out_lin [B] = sum_f lin_f[id] + dense.dense_w.
+ * out_emb or out_lin may be NULL to skip that half. */
+int xdfm_embed_gather(const float* const* tables, const float* const* lin_tables, const int32_t* vocab, const int32_t* ids, int64_t B,
+                      int m, int D, float* out_emb, const float* dense, int nd, const float* dense_w, float* out_lin, void* stream);
+
+/* ---- deterministic sorted segmented scatter-add (backward of the gather; replaces aten::embedding_dense_backward).
+ * step 1: keys = row_offset[f] + ids[b,f] -> radix sort -> run-length segments.
+ *   row_offset: HOST array (length m) = first global row of feature f's table (features sharing a table share it).
+ *   outputs: uniq_keys [n_keys] (first *num_segments valid), seg_offsets [n_keys+1], sorted_pos [n_keys] (index b*m+f),
+ *   num_segments [1] (device). n_keys = B*m. */
+int64_t xdfm_embed_bwd_workspace_bytes(int64_t n_keys);
+int xdfm_embed_bwd_segments(const int32_t* ids, int64_t B, int m, const int64_t* row_offset, const int32_t* vocab, int64_t total_rows,
+                            void* workspace, int64_t workspace_bytes, uint32_t* uniq_keys, int32_t* seg_offsets, int32_t* sorted_pos,
+                            int32_t* num_segments, void* stream);
+/* step 2: gsum[s, :] = sum over the segment's entries of demb[pos, :] ([B*m, D] view of d(out_emb)); gsum_lin[s] = sum of
+ * dlin[pos / m].  Summation order is a fixed function of the segment length -> bit-reproducible. demb or dlin may be NULL. */
+int xdfm_embed_bwd_reduce(const float* demb, const float* dlin, const int32_t* sorted_pos, const int32_t* seg_offsets,
+                          const int32_t* num_segments, int64_t n_keys, int m, int D, float* gsum, float* gsum_lin, void* stream);
+/* optional: scatter the segment sums into dense per-table gradients (what nn.Embedding(sparse=False) would produce).
+ * grad_tables: HOST array (length T) of device pointers [rows_t, width]; table_row_offset: HOST array length T+1. */
+int xdfm_embed_bwd_scatter_dense(float* const* grad_tables, const int64_t* table_row_offset, int T, int width, const uint32_t* uniq_keys,
+                                 const float* gsum, const int32_t* num_segments, int64_t max_segments, void* stream);
+
+/* ---- CIN layer, fp32 CUDA-core path (deepctr/layers/interaction.py:207-248).
+ * x0 [B,m,D]; xk = layer input: element (b,i,d) at xk[b*xk_bstride + i*D + d], i < Hp; W [H, Hp*m]; bias [H].
+ * y [B,H,D] = act(W . (xk (x) x0) + bias).  Channels [direct_begin, H) are "direct": their sum over D goes to
+ * pooled[b, col_off + h - direct_begin] (pooled is [B, fm_total]) and/or the un-pooled values to maps [B, fm_total, D]. */
+int xdfm_cin_fwd_f32(const float* x0, const float* xk, int64_t xk_bstride, const float* W, const float* bias, int64_t B, int m, int Hp,
+                     int H, int D, int act, float* y, int direct_begin, float* pooled, float* maps, int fm_total, int col_off,
+                     void* stream);
+/* dy = act'(y) * (dpooled / dmaps on direct channels + dnext [B, n_next, D] on channels [0, n_next)) */
+int xdfm_cin_dy(const float* y, int64_t B, int H, int D, int act, int direct_begin, const float* dpooled, const float* dmaps,
+                int fm_total, int col_off, const float* dnext, int n_next, float* dy, void* stream);
+/* dW [H, Hp*m], db [H] (overwritten); dxk [B,Hp,D] (overwritten); dx0 [B,m,D] (accumulated +=). */
+int64_t xdfm_cin_bwd_f32_workspace_bytes(int64_t B, int m, int Hp, int H, int D);
+int xdfm_cin_bwd_f32(const float* x0, const float* xk, int64_t xk_bstride, const float* W, const float* dy, int64_t B, int m, int Hp,
+                     int H, int D, float* dW, float* db, float* dxk, float* dx0, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- dense helpers (DNN: deepctr/layers/core.py:120-134; heads: xdeepfm.py:56,73,88-105; core.py:154-160) */
+int64_t xdfm_gemm_workspace_bytes(int M, int N, int K);
+/* C[M,N] = act(op(A)[M,K] op(B)[K,N] + bias[N]) (+= C if accumulate) */
+int xdfm_gemm_f32(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                  const float* bias, int act, int accumulate, void* workspace, int64_t workspace_bytes, void* stream);
+int xdfm_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int act, void* stream);
+int64_t xdfm_wcolsum_workspace_bytes(int K);
+/* out[k] (+)= sum_b s[b] * X[b*ld + k]; s may be NULL (plain column sum); deterministic */
+int xdfm_wcolsum(const float* X, int64_t B, int K, int ld, const float* s, float* out, int accumulate, void* workspace,
+                 int64_t workspace_bytes, void* stream);
+/* y_pred[b] = sigmoid(lin[b] + dnn_out[b,:].w_dnn + cin_out[b,:].w_cin + bias) (binary) or the raw logit */
+int xdfm_head_fwd(const float* lin, const float* cin_out, const float* w_cin, int fm, const float* dnn_out, const float* w_dnn, int hd,
+                  const float* bias, int64_t B, int binary, float* y_pred, void* stream);
+int xdfm_head_bwd(const float* dy_pred, const float* y_pred, int64_t B, int binary, const float* w_cin, int fm, const float* w_dnn,
+                  int hd, float* dlogit, float* d_cin_out, float* d_dnn_out, void* stream);
+/* F.binary_cross_entropy(y_pred, y, reduction='sum') (basemodel.py:254): *loss_sum += loss; dy_pred = scale * dL/dy_pred */
+int xdfm_bce_sum(const float* y_pred, const float* labels, int64_t B, float scale, float* per_sample, float* dy_pred,
+                 double* loss_sum, void* stream);
+
+/* ---- fused optimizer + L2 regulariser (basemodel.py:262, 412-428, 447-461).
+ * opt_dev: 8 floats of device state per optimizer instance (zero-initialised); xdfm_opt_tick advances the step counter
+ * and recomputes the bias corrections ON DEVICE (CUDA-graph friendly). */
+int xdfm_opt_tick(float* opt_dev, const xdfm_opt_cfg* cfg, void* stream);
+/* all dense parameters as one flat buffer; l2vec = per-element L2 strength (may be NULL); *reg_out += sum(l2*w^2) */
+int xdfm_flat_opt(const xdfm_opt_cfg* cfg, const float* opt_dev, int64_t n, float* w, const float* g, float* s1, float* s2,
+                  const float* l2vec, float grad_scale, double* reg_out, void* stream);
+/* embedding tables: w/s1/s2 HOST arrays (length T) of device pointers [rows_t, width]; rows present in (uniq_keys, gsum)
+ * get g = gsum*grad_scale + 2*l2*w; if dense_pass != 0 every other row gets g = 2*l2*w (the reference's dense semantics;
+ * touched_bitmap = ceil(total_rows/32) uint32 scratch); *reg_out += sum(l2*w^2) over the rows visited. */
+int xdfm_rows_opt(const xdfm_opt_cfg* cfg, const float* opt_dev, float* const* w, float* const* s1, float* const* s2,
+                  const int64_t* table_row_offset, int T, int width, const uint32_t* uniq_keys, const float* gsum,
+                  const int32_t* num_segments, int64_t max_segments, float grad_scale, uint32_t* touched_bitmap, int dense_pass,
+                  double* reg_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XDFM_H_ */

@@ -34,3 +34,35 @@ def golden_grads(z):
 
 def golden_gradnorms(z):
     return {k[len("gradnorm::"):]: float(z[k]) for k in z.files if k.startswith("gradnorm::")}
+
+
+def build_product_model(spec, device="cuda:0", **extra):
+    """The product model (xdeepfm-pytorch_b200/deepctr) for a ModelSpec."""
+    from deepctr.inputs import DenseFeat, SparseFeat
+    from deepctr import models as M
+    cols = [SparseFeat(n, v, spec.embedding_dim) for n, v in zip(spec.sparse_names, spec.vocab_sizes)] + \
+           [DenseFeat(n, 1) for n in spec.dense_names]
+    common = dict(dnn_hidden_units=spec.dnn_hidden_units, cin_layer_size=spec.cin_layer_size,
+                  cin_split_half=spec.cin_split_half, cin_activation=spec.cin_activation,
+                  l2_reg_linear=spec.l2_reg_linear, l2_reg_embedding=spec.l2_reg_embedding,
+                  l2_reg_dnn=spec.l2_reg_dnn, l2_reg_cin=spec.l2_reg_cin, device=device)
+    common.update(extra)
+    if spec.variant == "xdeepfm":
+        return M.xDeepFM(cols, cols, **common)
+    if spec.variant == "attn":
+        return M.xDeepFMAttention(cols, cols, cin_num_heads=spec.num_heads, cin_use_layer_norm=spec.use_layer_norm,
+                                  cin_use_residual=spec.use_residual, **common)
+    return M.xDeepFMAttentionV2(cols, cols, cin_num_heads=spec.num_heads, cin_use_layer_norm=spec.use_layer_norm,
+                                cin_use_residual=spec.use_residual, cin_num_attn_layers=spec.num_attn_layers, **common)
+
+
+def assert_close(a, b, rtol, atol, what=""):
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
+    assert a.shape == b.shape, "%s: shape %s vs %s" % (what, tuple(a.shape), tuple(b.shape))
+    err = (a - b).abs()
+    tol = atol + rtol * b.abs()
+    if not bool((err <= tol).all()):
+        i = int(torch.argmax(err - tol))
+        raise AssertionError("%s: max |err| %.3e (ref %.3e) at flat index %d; rtol %.1e atol %.1e; frac bad %.4f" % (
+            what, err.flatten()[i].item(), b.flatten()[i].item(), i, rtol, atol, float((err > tol).double().mean())))

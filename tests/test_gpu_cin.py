@@ -1,0 +1,104 @@
+"""GPU parity of the CIN operator (forward + backward) against the CPU oracle and the reference's known answers."""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import xdeepfm_oracle as O
+from tests.helpers import GOLDEN, assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _run_product(x0, Ws, bs, split_half, act, pool, gout):
+    from deepctr import ops
+    m = x0.shape[1]
+    cfg = ops.CINConfig(m, [W.shape[0] for W in Ws], split_half, act, pool=pool)
+    x = x0.to(DEV).requires_grad_(True)
+    wb = []
+    for W, b in zip(Ws, bs):
+        wb += [W.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)]
+    out = ops.CINFunction.apply(cfg, x, *wb)
+    out.backward(gout.to(DEV))
+    return out.detach(), x.grad, [t.grad for t in wb]
+
+
+def _run_oracle(x0, Ws, bs, split_half, act, pool, gout):
+    x = x0.double().requires_grad_(True)
+    Wd = [W.double().requires_grad_(True) for W in Ws]
+    bd = [b.double().requires_grad_(True) for b in bs]
+    out = O.cin_forward(x, Wd, bd, split_half, act, pool=pool)
+    out.backward(gout.double())
+    g = []
+    for W, b in zip(Wd, bd):
+        g += [W.grad, b.grad]
+    return out.detach(), x.grad, g
+
+
+def _rand_case(B, m, D, layers, split_half, seed):
+    g = torch.Generator().manual_seed(seed)
+    x0 = torch.randn(B, m, D, generator=g) * 0.5
+    Ws, bs = [], []
+    prev = m
+    for H in layers:
+        K = prev * m
+        Ws.append(torch.randn(H, K, 1, generator=g) / K ** 0.5)
+        bs.append(torch.randn(H, generator=g) * 0.1)
+        prev = H // 2 if split_half else H
+    return x0, Ws, bs, g
+
+
+CASES = [
+    # B, m, D, layers, split_half, act, pool
+    (5, 3, 2, (4, 2), True, "relu", True),
+    (33, 5, 8, (16, 8), True, "relu", True),
+    (17, 5, 8, (6, 5, 4), False, "relu", True),
+    (9, 4, 10, (8, 6, 3), True, "linear", True),      # D not a power of two, odd last layer
+    (12, 5, 8, (16, 8), True, "relu", False),         # un-pooled maps (attention variant input)
+    (64, 26, 8, (256, 128), True, "relu", True),      # BASELINE config 1 shape
+    (40, 26, 16, (200, 200, 200), True, "relu", True),  # BASELINE config 2 shape
+    (16, 22, 32, (256, 256), True, "relu", True),     # config 4 shape (2 of 4 layers)
+    (6, 26, 64, (256, 128), True, "relu", True),      # config 5 shape
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(c[:5]) for c in CASES])
+def test_cin_fp32_matches_oracle(case):
+    B, m, D, layers, split_half, act, pool = case
+    x0, Ws, bs, g = _rand_case(B, m, D, layers, split_half, seed=B + m + D)
+    fm = (sum(layers[:-1]) // 2 + layers[-1]) if split_half else sum(layers)
+    gout = torch.randn((B, fm) if pool else (B, fm, D), generator=g)
+    out, dx, dwb = _run_product(x0, Ws, bs, split_half, act, pool, gout)
+    ro, rdx, rdwb = _run_oracle(x0, Ws, bs, split_half, act, pool, gout)
+    # fp32 CUDA-core path vs fp64 oracle: 1e-4 relative to the tensor's scale (K up to 3328 fp32 accumulations)
+    assert_close(out, ro, 1e-4, 1e-5 * max(ro.abs().max().item(), 1.0), "cin out")
+    assert_close(dx, rdx, 1e-4, 1e-4 * rdx.abs().max().item(), "cin dx0")
+    for i, (a, b) in enumerate(zip(dwb, rdwb)):
+        assert_close(a, b.reshape(a.shape), 1e-4, 1e-4 * b.abs().max().item(), "cin grad %d" % i)
+
+
+def test_cin_known_answer_forward():
+    """Reference-recorded KAT (tests/golden/cin_kat.json).  Only the forward is pinned here: one layer-0 pre-activation
+    is exactly 0 in decimal arithmetic, so the ReLU gradient of the KAT depends on summation order (see test_oracle)."""
+    kat = json.load(open(os.path.join(GOLDEN, "cin_kat.json")))
+    K = [9, 6]
+    Ws = [torch.tensor([[(((h * K[l] + k) * 3) % 7 - 2) / 10 for k in range(K[l])] for h in range(H)], dtype=torch.float32).unsqueeze(-1)
+          for l, H in enumerate((4, 2))]
+    bs = [torch.tensor([(h + 1) / 10 for h in range(H)], dtype=torch.float32) for H in (4, 2)]
+    x = torch.tensor(kat["x"], dtype=torch.float32).reshape(2, 3, 2)
+    out, dx, dwb = _run_product(x, Ws, bs, True, "relu", True, torch.ones(2, 4))
+    assert_close(out, torch.tensor(kat["out"]), 1e-6, 1e-6, "KAT out")
+    assert_close(dwb[3], torch.tensor(kat["db1"]), 1e-6, 1e-6, "KAT db1")
+    assert_close(dwb[2].flatten(), torch.tensor(kat["dW1"]), 1e-5, 1e-6, "KAT dW1")
+
+
+def test_cin_rejects_bad_rank():
+    from deepctr.layers import CIN
+    with pytest.raises(ValueError):
+        CIN(3, (4, 2), device=DEV)(torch.zeros(2, 6, device=DEV))
+    with pytest.raises(ValueError):
+        CIN(3, (3, 2), split_half=True)
+    with pytest.raises(ValueError):
+        CIN(3, ())

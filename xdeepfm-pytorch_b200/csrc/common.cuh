@@ -1,0 +1,66 @@
+// Shared helpers for libxdfm_sm100a.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <algorithm>
+
+#define XDFM_OK 0
+#define XDFM_ERR_ARG 1
+#define XDFM_ERR_CUDA 2
+#define XDFM_ERR_UNSUPPORTED 3
+
+void xdfm_set_error(const char* fmt, ...);
+
+#define XDFM_CHECK_ARG(cond, ...)              \
+  do {                                         \
+    if (!(cond)) {                             \
+      xdfm_set_error(__VA_ARGS__);             \
+      return XDFM_ERR_ARG;                     \
+    }                                          \
+  } while (0)
+
+#define XDFM_CUDA(call)                                                                   \
+  do {                                                                                    \
+    cudaError_t e__ = (call);                                                             \
+    if (e__ != cudaSuccess) {                                                             \
+      xdfm_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return XDFM_ERR_CUDA;                                                               \
+    }                                                                                     \
+  } while (0)
+
+extern long long g_xdfm_launches;
+#define XDFM_LAUNCH_CHECK()                                                                 \
+  do {                                                                                      \
+    ++g_xdfm_launches;                                                                      \
+    cudaError_t e__ = cudaGetLastError();                                                   \
+    if (e__ != cudaSuccess) {                                                               \
+      xdfm_set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return XDFM_ERR_CUDA;                                                                 \
+    }                                                                                       \
+  } while (0)
+
+static inline int xdfm_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// 128-bit streaming loads/stores (read-only path, do not pollute L1)
+__device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}

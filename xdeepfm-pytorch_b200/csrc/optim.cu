@@ -1,0 +1,277 @@
+// Fused optimizer + L2-regulariser kernels.
+//
+// Replaces (reference, file:line):
+//   get_regularization_loss  deepctr/models/basemodel.py:412-428  (sum(l2 * p^2) over every registered tensor,
+//                                                                 including WHOLE embedding tables, every step)
+//   optim.step()             deepctr/models/basemodel.py:262, 447-461 (torch.optim.SGD/Adam/Adagrad/RMSprop, torch
+//                                                                 defaults, dense over every table row)
+// Semantics are the reference's: every row of every table is updated every step with
+// g = scatter_add(row grads) + 2*l2*w, so the pass is a pure HBM stream: 4 B read + 4 B write per state
+// element (Adam: w, m, v -> 24 B/element).  Rows touched by the batch are updated by the sparse kernel
+// (which also marks them in a bitmap); the dense kernel streams all tables and skips marked rows.
+#include "common.cuh"
+#include "../../include/xdfm.h"
+
+// device-side per-step scalars written by opt_tick_kernel (keeps the step CUDA-graph capturable)
+// d[0] = step (int32 bits), d[1] = adam step_size, d[2] = adam sqrt(bias_correction2), d[3] = adagrad clr
+__global__ void opt_tick_kernel(float* d, xdfm_opt_cfg cfg) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int step = __float_as_int(d[0]) + 1;
+  d[0] = __int_as_float(step);
+  double bc1 = 1.0 - pow((double)cfg.beta1, (double)step);
+  double bc2 = 1.0 - pow((double)cfg.beta2, (double)step);
+  d[1] = (float)((double)cfg.lr / bc1);
+  d[2] = (float)sqrt(bc2);
+  d[3] = (float)((double)cfg.lr / (1.0 + (double)(step - 1) * (double)cfg.lr_decay));
+}
+
+extern "C" int xdfm_opt_tick(float* opt_dev, const xdfm_opt_cfg* cfg, void* stream) {
+  opt_tick_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(opt_dev, *cfg);
+  XDFM_LAUNCH_CHECK();
+  return XDFM_OK;
+}
+
+struct OptScalars {
+  int kind;
+  float lr, one_minus_b1, b2, one_minus_b2, eps, alpha, one_minus_alpha, step_size, bc2_sqrt, clr;
+};
+
+__device__ __forceinline__ OptScalars load_scalars(const xdfm_opt_cfg& c, const float* __restrict__ d) {
+  OptScalars s;
+  s.kind = c.kind;
+  s.lr = c.lr;
+  s.one_minus_b1 = (float)(1.0 - (double)c.beta1);
+  s.b2 = c.beta2;
+  s.one_minus_b2 = (float)(1.0 - (double)c.beta2);
+  s.eps = c.eps;
+  s.alpha = c.alpha;
+  s.one_minus_alpha = (float)(1.0 - (double)c.alpha);
+  s.step_size = d[1];
+  s.bc2_sqrt = d[2];
+  s.clr = d[3];
+  return s;
+}
+
+// one element; mirrors torch's single-tensor optimizer arithmetic (torch/optim/{sgd,adam,adagrad,rmsprop}.py)
+__device__ __forceinline__ void opt_apply(const OptScalars& h, float& w, float g, float& s1, float& s2) {
+  switch (h.kind) {
+    case XDFM_OPT_SGD:
+      w = w - h.lr * g;
+      break;
+    case XDFM_OPT_ADAM: {
+      s1 = s1 + h.one_minus_b1 * (g - s1);                 // exp_avg.lerp_(grad, 1-beta1)
+      s2 = s2 * h.b2 + h.one_minus_b2 * (g * g);           // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1-beta2)
+      float denom = sqrtf(s2) / h.bc2_sqrt + h.eps;
+      w = w - h.step_size * (s1 / denom);                  // param.addcdiv_(exp_avg, denom, value=-step_size)
+      break;
+    }
+    case XDFM_OPT_ADAGRAD: {
+      s1 = s1 + g * g;                                     // state_sum.addcmul_(grad, grad, value=1)
+      float stdv = sqrtf(s1) + h.eps;
+      w = w - h.clr * (g / stdv);
+      break;
+    }
+    case XDFM_OPT_RMSPROP: {
+      s1 = s1 * h.alpha + h.one_minus_alpha * (g * g);     // square_avg.mul_(alpha).addcmul_(g, g, 1-alpha)
+      float avg = sqrtf(s1) + h.eps;
+      w = w - h.lr * (g / avg);
+      break;
+    }
+  }
+}
+
+__device__ __forceinline__ void block_accumulate_double(float local, double* out) {
+  __shared__ float red[32];
+  float v = warp_sum(local);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    float t = lane < (int)((blockDim.x + 31) >> 5) ? red[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0 && out != nullptr) atomicAdd(out, (double)t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// flat dense-parameter step: w, g, s1, s2 are flat fp32 buffers over ALL dense parameters
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) flat_opt_kernel(xdfm_opt_cfg cfg, const float* __restrict__ d, int64_t n, float* __restrict__ w,
+                                                       const float* __restrict__ g, float* __restrict__ s1, float* __restrict__ s2,
+                                                       const float* __restrict__ l2vec, float grad_scale, double* reg_out) {
+  OptScalars h = load_scalars(cfg, d);
+  float reg = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float wi = w[i];
+    float l2 = l2vec ? l2vec[i] : 0.f;
+    reg += l2 * (wi * wi);
+    float gi = g[i] * grad_scale + 2.f * l2 * wi;
+    float a = s1 ? s1[i] : 0.f, b = s2 ? s2[i] : 0.f;
+    opt_apply(h, wi, gi, a, b);
+    w[i] = wi;
+    if (s1) s1[i] = a;
+    if (s2) s2[i] = b;
+  }
+  block_accumulate_double(reg, reg_out);
+}
+
+extern "C" int xdfm_flat_opt(const xdfm_opt_cfg* cfg, const float* opt_dev, int64_t n, float* w, const float* g, float* s1,
+                             float* s2, const float* l2vec, float grad_scale, double* reg_out, void* stream) {
+  XDFM_CHECK_ARG(cfg->kind >= 0 && cfg->kind <= 3, "flat_opt: unknown optimizer kind %d", cfg->kind);
+  if (n == 0) return XDFM_OK;
+  int blocks = (int)min((int64_t)xdfm_num_sms() * 8, ceil_div64(n, 256));
+  flat_opt_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*cfg, opt_dev, n, w, g, s1, s2, l2vec, grad_scale, reg_out);
+  XDFM_LAUNCH_CHECK();
+  return XDFM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// embedding tables: sparse (touched rows) + dense (all other rows)
+// ------------------------------------------------------------------------------------------------
+struct TableSet {
+  float* w[XDFM_MAX_FIELDS];
+  float* s1[XDFM_MAX_FIELDS];
+  float* s2[XDFM_MAX_FIELDS];
+  int64_t row_off[XDFM_MAX_FIELDS + 1];   // global row offsets (key space of the scatter-add)
+  int64_t vec_off[XDFM_MAX_FIELDS + 1];   // offsets in units of 4 elements, each table padded to a multiple of 4
+};
+
+__device__ __forceinline__ int find_tab(const int64_t* off, int T, int64_t key) {
+  int lo = 0, hi = T - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (key >= off[mid]) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) rows_opt_sparse_kernel(xdfm_opt_cfg cfg, const float* __restrict__ d, TableSet ts, int T, int width,
+                                                              const uint32_t* __restrict__ uniq_keys, const float* __restrict__ gsum,
+                                                              const int32_t* __restrict__ num_segments, float grad_scale,
+                                                              uint32_t* __restrict__ touched, double* reg_out) {
+  OptScalars h = load_scalars(cfg, d);
+  const int nseg = *num_segments;
+  const int64_t total = (int64_t)nseg * width;
+  float reg = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t s = i / width;
+    int c = (int)(i - s * width);
+    int64_t key = uniq_keys[s];
+    int t = find_tab(ts.row_off, T, key);
+    int64_t e = (key - ts.row_off[t]) * width + c;
+    float wi = ts.w[t][e];
+    reg += cfg.l2 * (wi * wi);
+    float gi = gsum[i] * grad_scale + 2.f * cfg.l2 * wi;
+    float a = ts.s1[t] ? ts.s1[t][e] : 0.f, b = ts.s2[t] ? ts.s2[t][e] : 0.f;
+    opt_apply(h, wi, gi, a, b);
+    ts.w[t][e] = wi;
+    if (ts.s1[t]) ts.s1[t][e] = a;
+    if (ts.s2[t]) ts.s2[t][e] = b;
+    if (c == 0 && touched != nullptr) atomicOr(touched + (key >> 5), 1u << (key & 31));
+  }
+  block_accumulate_double(reg, reg_out);
+}
+
+// dense pass over every row NOT marked in `touched`: g = 2*l2*w.  One thread = 4 consecutive elements of one table.
+__global__ void __launch_bounds__(256) rows_opt_dense_kernel(xdfm_opt_cfg cfg, const float* __restrict__ d, TableSet ts, int T, int width,
+                                                             const uint32_t* __restrict__ touched, double* reg_out) {
+  OptScalars h = load_scalars(cfg, d);
+  const int64_t nvec = ts.vec_off[T];
+  float reg = 0.f;
+  const bool has1 = ts.s1[0] != nullptr, has2 = ts.s2[0] != nullptr;
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+    int t = find_tab(ts.vec_off, T, v);
+    int64_t e0 = (v - ts.vec_off[t]) * 4;
+    int64_t nelem = (ts.row_off[t + 1] - ts.row_off[t]) * width;
+    float wv[4], av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
+    bool full = e0 + 4 <= nelem;
+    if (full) {
+      *reinterpret_cast<float4*>(wv) = *reinterpret_cast<const float4*>(ts.w[t] + e0);
+      if (has1) *reinterpret_cast<float4*>(av) = *reinterpret_cast<const float4*>(ts.s1[t] + e0);
+      if (has2) *reinterpret_cast<float4*>(bv) = *reinterpret_cast<const float4*>(ts.s2[t] + e0);
+    } else {
+      for (int i = 0; i < 4; ++i) {
+        if (e0 + i < nelem) {
+          wv[i] = ts.w[t][e0 + i];
+          if (has1) av[i] = ts.s1[t][e0 + i];
+          if (has2) bv[i] = ts.s2[t][e0 + i];
+        }
+      }
+    }
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int64_t e = e0 + i;
+      if (e < nelem) {
+        int64_t key = ts.row_off[t] + e / width;
+        bool tch = touched != nullptr && ((touched[key >> 5] >> (key & 31)) & 1u);
+        if (!tch) {
+          float wi = wv[i];
+          reg += cfg.l2 * (wi * wi);
+          opt_apply(h, wv[i], 2.f * cfg.l2 * wi, av[i], bv[i]);
+          any = true;
+        }
+      }
+    }
+    if (!any) continue;
+    if (full) {
+      *reinterpret_cast<float4*>(ts.w[t] + e0) = *reinterpret_cast<float4*>(wv);
+      if (has1) *reinterpret_cast<float4*>(ts.s1[t] + e0) = *reinterpret_cast<float4*>(av);
+      if (has2) *reinterpret_cast<float4*>(ts.s2[t] + e0) = *reinterpret_cast<float4*>(bv);
+    } else {
+      for (int i = 0; i < 4; ++i) {
+        if (e0 + i < nelem) {
+          ts.w[t][e0 + i] = wv[i];
+          if (has1) ts.s1[t][e0 + i] = av[i];
+          if (has2) ts.s2[t][e0 + i] = bv[i];
+        }
+      }
+    }
+  }
+  block_accumulate_double(reg, reg_out);
+}
+
+static int fill_table_set(TableSet& ts, float* const* w, float* const* s1, float* const* s2, const int64_t* row_off, int T, int width) {
+  int64_t voff = 0;
+  for (int t = 0; t < T; ++t) {
+    ts.w[t] = w[t];
+    ts.s1[t] = s1 ? s1[t] : nullptr;
+    ts.s2[t] = s2 ? s2[t] : nullptr;
+    ts.row_off[t] = row_off[t];
+    ts.vec_off[t] = voff;
+    voff += ((row_off[t + 1] - row_off[t]) * width + 3) / 4;
+    if ((uintptr_t)w[t] % 16 != 0) return 1;
+  }
+  ts.row_off[T] = row_off[T];
+  ts.vec_off[T] = voff;
+  return 0;
+}
+
+extern "C" int xdfm_rows_opt(const xdfm_opt_cfg* cfg, const float* opt_dev, float* const* w, float* const* s1, float* const* s2,
+                             const int64_t* table_row_offset, int T, int width, const uint32_t* uniq_keys, const float* gsum,
+                             const int32_t* num_segments, int64_t max_segments, float grad_scale, uint32_t* touched_bitmap,
+                             int dense_pass, double* reg_out, void* stream) {
+  XDFM_CHECK_ARG(cfg->kind >= 0 && cfg->kind <= 3, "rows_opt: unknown optimizer kind %d", cfg->kind);
+  XDFM_CHECK_ARG(T >= 1 && T <= XDFM_MAX_FIELDS, "rows_opt: T=%d", T);
+  TableSet ts;
+  XDFM_CHECK_ARG(fill_table_set(ts, w, s1, s2, table_row_offset, T, width) == 0, "rows_opt: tables must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t total_rows = table_row_offset[T];
+  if (dense_pass && touched_bitmap != nullptr)
+    XDFM_CUDA(cudaMemsetAsync(touched_bitmap, 0, (size_t)((total_rows + 31) / 32) * 4, st));
+  if (max_segments > 0 && uniq_keys != nullptr) {
+    int blocks = (int)min((int64_t)xdfm_num_sms() * 8, ceil_div64(max_segments * width, 256));
+    rows_opt_sparse_kernel<<<max(blocks, 1), 256, 0, st>>>(*cfg, opt_dev, ts, T, width, uniq_keys, gsum, num_segments, grad_scale,
+                                                           dense_pass ? touched_bitmap : nullptr, reg_out);
+    XDFM_LAUNCH_CHECK();
+  }
+  if (dense_pass) {
+    int64_t nvec = ts.vec_off[T];
+    if (nvec > 0) {
+      int blocks = (int)min((int64_t)xdfm_num_sms() * 16, ceil_div64(nvec, 256));
+      rows_opt_dense_kernel<<<max(blocks, 1), 256, 0, st>>>(*cfg, opt_dev, ts, T, width, touched_bitmap, reg_out);
+      XDFM_LAUNCH_CHECK();
+    }
+  }
+  return XDFM_OK;
+}

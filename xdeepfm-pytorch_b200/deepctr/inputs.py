@@ -1,0 +1,127 @@
+"""Feature-column API (drop-in for the reference's deepctr/inputs.py:20-245).
+
+Same names, fields, defaults and column-layout rule as the reference so that `xdftrain*.py` and user code keep
+working; the lookups themselves are done by the fused CUDA gather in `ops.py`, not by per-field nn.Embedding calls.
+"""
+from collections import OrderedDict, namedtuple
+
+import torch
+import torch.nn as nn
+
+DEFAULT_GROUP_NAME = "default_group"
+
+
+class SparseFeat(namedtuple("SparseFeat", ["name", "vocabulary_size", "embedding_dim", "use_hash", "dtype",
+                                           "embedding_name", "group_name"])):
+    """Categorical feature column (reference: inputs.py:20-38)."""
+    __slots__ = ()
+
+    def __new__(cls, name, vocabulary_size, embedding_dim=4, use_hash=False, dtype="int32", embedding_name=None,
+                group_name=DEFAULT_GROUP_NAME):
+        if embedding_dim == "auto":
+            embedding_dim = 6 * int(pow(vocabulary_size, 0.25))
+        if use_hash:
+            print("Notice! Feature Hashing on the fly currently is not supported in torch version,"
+                  "you can use tensorflow version!")
+        return super().__new__(cls, name, vocabulary_size, embedding_dim, use_hash, dtype,
+                               name if embedding_name is None else embedding_name, group_name)
+
+    def __hash__(self):
+        return hash(self.name)
+
+
+class VarLenSparseFeat(namedtuple("VarLenSparseFeat", ["sparsefeat", "maxlen", "combiner", "length_name"])):
+    """Variable-length categorical column (reference: inputs.py:41-77).  Kept for API compatibility; the xDeepFM
+    hot path of this build does not pool sequences (out of scope)."""
+    __slots__ = ()
+
+    def __new__(cls, sparsefeat, maxlen, combiner="mean", length_name=None):
+        return super().__new__(cls, sparsefeat, maxlen, combiner, length_name)
+
+    name = property(lambda self: self.sparsefeat.name)
+    vocabulary_size = property(lambda self: self.sparsefeat.vocabulary_size)
+    embedding_dim = property(lambda self: self.sparsefeat.embedding_dim)
+    use_hash = property(lambda self: self.sparsefeat.use_hash)
+    dtype = property(lambda self: self.sparsefeat.dtype)
+    embedding_name = property(lambda self: self.sparsefeat.embedding_name)
+    group_name = property(lambda self: self.sparsefeat.group_name)
+
+    def __hash__(self):
+        return hash(self.name)
+
+
+class DenseFeat(namedtuple("DenseFeat", ["name", "dimension", "dtype"])):
+    """Numeric feature column (reference: inputs.py:80-87)."""
+    __slots__ = ()
+
+    def __new__(cls, name, dimension=1, dtype="float32"):
+        return super().__new__(cls, name, dimension, dtype)
+
+    def __hash__(self):
+        return hash(self.name)
+
+
+def build_input_features(feature_columns):
+    """OrderedDict name -> (start, end) column range of the flat input matrix, first occurrence wins
+    (reference: inputs.py:99-123)."""
+    index = OrderedDict()
+    cursor = 0
+    for fc in feature_columns:
+        if fc.name in index:
+            continue
+        if isinstance(fc, SparseFeat):
+            width = 1
+        elif isinstance(fc, DenseFeat):
+            width = fc.dimension
+        elif isinstance(fc, VarLenSparseFeat):
+            width = fc.maxlen
+        else:
+            raise TypeError("Invalid feature column type,got", type(fc))
+        index[fc.name] = (cursor, cursor + width)
+        cursor += width
+        if isinstance(fc, VarLenSparseFeat) and fc.length_name is not None and fc.length_name not in index:
+            index[fc.length_name] = (cursor, cursor + 1)
+            cursor += 1
+    return index
+
+
+def get_feature_names(feature_columns):
+    return list(build_input_features(feature_columns).keys())
+
+
+def sparse_columns(feature_columns):
+    return [fc for fc in feature_columns if isinstance(fc, SparseFeat)] if feature_columns else []
+
+
+def dense_columns(feature_columns):
+    return [fc for fc in feature_columns if isinstance(fc, DenseFeat)] if feature_columns else []
+
+
+def varlen_columns(feature_columns):
+    return [fc for fc in feature_columns if isinstance(fc, VarLenSparseFeat)] if feature_columns else []
+
+
+def create_embedding_matrix(feature_columns, init_std=0.0001, linear=False, sparse=False, device="cpu"):
+    """nn.ModuleDict {embedding_name: nn.Embedding(vocab, D or 1)} initialised N(0, init_std)
+    (reference: inputs.py:158-180).  The modules are parameter containers: the CUDA gather reads `.weight` directly."""
+    if varlen_columns(feature_columns):
+        raise NotImplementedError("VarLenSparseFeat pooling is outside the xDeepFM hot path of this build")
+    tables = nn.ModuleDict()
+    for fc in sparse_columns(feature_columns):
+        if fc.embedding_name not in tables:
+            tables[fc.embedding_name] = nn.Embedding(fc.vocabulary_size, 1 if linear else fc.embedding_dim, sparse=sparse)
+    for emb in tables.values():
+        nn.init.normal_(emb.weight, mean=0, std=init_std)
+    return tables.to(device)
+
+
+def combined_dnn_input(sparse_embedding_list, dense_value_list):
+    """Flatten + concat: all sparse embeddings (field order) then the dense values (reference: inputs.py:126-138)."""
+    parts = []
+    if len(sparse_embedding_list) > 0:
+        parts.append(torch.flatten(torch.cat(sparse_embedding_list, dim=-1), start_dim=1))
+    if len(dense_value_list) > 0:
+        parts.append(torch.flatten(torch.cat(dense_value_list, dim=-1), start_dim=1))
+    if not parts:
+        raise NotImplementedError
+    return parts[0] if len(parts) == 1 else torch.cat(parts, dim=-1)

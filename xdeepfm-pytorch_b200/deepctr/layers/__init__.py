@@ -1,0 +1,4 @@
+from .activation import activation_layer, Identity
+from .core import DNN, PredictionLayer
+from .interaction import CIN
+from .utils import concat_fun, slice_arrays

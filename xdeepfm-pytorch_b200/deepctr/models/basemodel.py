@@ -1,0 +1,593 @@
+"""BaseModel: the reference's training/inference API (deepctr/models/basemodel.py:96-527) on the B200 kernels.
+
+Same public surface -- ctor arguments, compile / fit / evaluate / predict, input_from_feature_columns,
+compute_input_dim, add_regularization_weight, get_regularization_loss, add_auxiliary_loss, state_dict keys, History --
+with a different engine underneath:
+
+  * ids travel as an int32 [B, m] matrix next to the float32 dense [B, nd] matrix (the reference pushes ids through one
+    float32 matrix and corrupts ids >= 2^24: basemodel.py:195-198, 242, 368-370); `forward(X_float)` is still accepted.
+  * one fused multi-table gather instead of 2*m nn.Embedding calls; CIN / DNN / head are fused CUDA ops (ops.py).
+  * fit() is sync-free inside an epoch: loss and regulariser are accumulated on the device, per-step train metrics are
+    computed from a device-side prediction log at epoch end; batches are staged through pinned memory on a copy stream.
+  * named optimizers map to fused kernels (optim.py) that keep the reference's dense-table semantics.
+"""
+from __future__ import print_function
+
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..callbacks import CallbackList, History
+from ..inputs import (DenseFeat, SparseFeat, VarLenSparseFeat, build_input_features, create_embedding_matrix,
+                      dense_columns, sparse_columns, varlen_columns)
+from ..layers import PredictionLayer
+from ..layers.utils import slice_arrays
+from ..optim import FusedOptimizer, TableSet
+
+
+def _expand_cols(feature_index, columns):
+    cols = []
+    for fc in columns:
+        a, b = feature_index[fc.name]
+        cols.extend(range(a, b))
+    return cols
+
+
+def _make_plan(columns, embedding_dict, width):
+    names = list(embedding_dict.keys())
+    table_of = [names.index(fc.embedding_name) for fc in columns]
+    rows = [embedding_dict[n].weight.shape[0] for n in names]
+    return ops.SparsePlan(table_of, rows, width)
+
+
+class Linear(nn.Module):
+    """First-order term: sum_f w_f[id_f] + dense @ weight -> [B, 1] (reference: basemodel.py:34-92)."""
+
+    def __init__(self, feature_columns, feature_index, init_std=0.0001, device="cpu"):
+        super().__init__()
+        self.feature_index = feature_index
+        self.device = device
+        self.sparse_feature_columns = sparse_columns(feature_columns)
+        self.dense_feature_columns = dense_columns(feature_columns)
+        self.varlen_sparse_feature_columns = varlen_columns(feature_columns)
+        self.embedding_dict = create_embedding_matrix(feature_columns, init_std, linear=True, sparse=False, device=device)
+        if len(self.dense_feature_columns) > 0:
+            self.weight = nn.Parameter(torch.empty(sum(fc.dimension for fc in self.dense_feature_columns), 1, device=device))
+            nn.init.normal_(self.weight, mean=0, std=init_std)
+        self._sparse_cols = _expand_cols(feature_index, self.sparse_feature_columns)
+        self._dense_cols = _expand_cols(feature_index, self.dense_feature_columns)
+        self._plan = _make_plan(self.sparse_feature_columns, self.embedding_dict, 1)
+        self._cache = ops.SegmentCache()
+
+    def _tables(self):
+        return [emb.weight for emb in self.embedding_dict.values()]
+
+    def forward_ids(self, ids, dense, cache=None):
+        w = self.weight if len(self.dense_feature_columns) > 0 else None
+        return ops.LinearTerm.apply(self._plan, cache or self._cache, ids, dense if w is not None else None, w, *self._tables())
+
+    def forward(self, X, sparse_feat_refine_weight=None):
+        if sparse_feat_refine_weight is not None:
+            raise NotImplementedError("sparse_feat_refine_weight (IFM/DIFM) is outside the xDeepFM hot path")
+        ids, dense = ops.split_input(X, self._sparse_cols, self._dense_cols)
+        return self.forward_ids(ids, dense)
+
+
+class BaseModel(nn.Module):
+    def __init__(self, linear_feature_columns, dnn_feature_columns, l2_reg_linear=1e-5, l2_reg_embedding=1e-5,
+                 init_std=0.0001, seed=1024, task="binary", device="cpu", gpus=None):
+        super().__init__()
+        torch.manual_seed(seed)
+        self.dnn_feature_columns = dnn_feature_columns
+        self.linear_feature_columns = linear_feature_columns
+        self.reg_loss = torch.zeros((1,), device=device)
+        self.aux_loss = torch.zeros((1,), device=device)
+        self.device = device
+        self.gpus = gpus
+        if gpus and str(self.gpus[0]) not in self.device:
+            raise ValueError("`gpus[0]` should be the same gpu with `device`")
+        if varlen_columns(list(linear_feature_columns) + list(dnn_feature_columns)):
+            raise NotImplementedError("VarLenSparseFeat is outside the xDeepFM hot path of this build")
+
+        self.feature_index = build_input_features(list(linear_feature_columns) + list(dnn_feature_columns))
+        self.embedding_dict = create_embedding_matrix(dnn_feature_columns, init_std, sparse=False, device=device)
+        self.linear_model = Linear(linear_feature_columns, self.feature_index, device=device)
+
+        self.regularization_weight = []
+        self.add_regularization_weight(self.embedding_dict.parameters(), l2=l2_reg_embedding)
+        self.add_regularization_weight(self.linear_model.parameters(), l2=l2_reg_linear)
+        self._l2_reg_embedding, self._l2_reg_linear = l2_reg_embedding, l2_reg_linear
+
+        self.out = PredictionLayer(task, )
+        self.task = task
+
+        # fused-lookup plans: the sparse / dense columns of the deep part and of the linear part
+        self._dnn_sparse = sparse_columns(dnn_feature_columns)
+        self._dnn_dense = dense_columns(dnn_feature_columns)
+        dims = set(fc.embedding_dim for fc in self._dnn_sparse)
+        if len(dims) > 1:
+            raise ValueError("embedding_dim of SparseFeat and VarlenSparseFeat must be same in this model!")
+        self._emb_dim = dims.pop() if dims else 0
+        self._emb_plan = _make_plan(self._dnn_sparse, self.embedding_dict, self._emb_dim) if self._dnn_sparse else None
+        self._seg_cache = ops.SegmentCache()
+        # union column layout used by the int32/float32 feed
+        all_cols = []
+        seen = set()
+        for fc in list(linear_feature_columns) + list(dnn_feature_columns):
+            if fc.name not in seen:
+                seen.add(fc.name)
+                all_cols.append(fc)
+        self._all_sparse = sparse_columns(all_cols)
+        self._all_dense = dense_columns(all_cols)
+        self._all_sparse_cols = _expand_cols(self.feature_index, self._all_sparse)
+        self._all_dense_cols = _expand_cols(self.feature_index, self._all_dense)
+        sp_names = [fc.name for fc in self._all_sparse]
+        self._dnn_sparse_sel = self._selector([sp_names.index(fc.name) for fc in self._dnn_sparse], len(sp_names))
+        self._lin_sparse_sel = self._selector([sp_names.index(fc.name) for fc in self.linear_model.sparse_feature_columns],
+                                              len(sp_names))
+        dcol_pos = {c: i for i, c in enumerate(self._all_dense_cols)}
+        self._dnn_dense_sel = self._selector([dcol_pos[c] for c in _expand_cols(self.feature_index, self._dnn_dense)],
+                                             len(self._all_dense_cols))
+        self._lin_dense_sel = self._selector([dcol_pos[c] for c in self.linear_model._dense_cols], len(self._all_dense_cols))
+
+        self.to(device)
+        self._is_graph_network = True
+        self._ckpt_saved_epoch = False
+        self.history = History()
+        self.stop_training = False
+        self.sparse_embedding_update = False   # True: update only rows touched by the batch (NOT reference semantics)
+
+    @staticmethod
+    def _selector(idx, n):
+        return None if idx == list(range(n)) else idx
+
+    @staticmethod
+    def _select(t, sel):
+        if sel is None:
+            return t
+        return t[:, sel].contiguous()
+
+    # ------------------------------------------------------------------------------------------
+    # inputs
+    # ------------------------------------------------------------------------------------------
+    def split_input(self, X):
+        """X float [B, n_columns] -> (ids int32 [B, m_all], dense float32 [B, nd_all]) on the device."""
+        return ops.split_input(X, self._all_sparse_cols, self._all_dense_cols)
+
+    def embed(self, ids_all):
+        """Fused multi-table gather -> [B, m, D] for the deep part's sparse features."""
+        ids = self._select(ids_all, self._dnn_sparse_sel)
+        tables = [emb.weight for emb in self.embedding_dict.values()]
+        return ops.SparseGather.apply(self._emb_plan, self._seg_cache, ids, *tables)
+
+    def linear_logit(self, ids_all, dense_all):
+        ids = self._select(ids_all, self._lin_sparse_sel)
+        dense = self._select(dense_all, self._lin_dense_sel)
+        return self.linear_model.forward_ids(ids, dense, cache=self._seg_cache)
+
+    def dnn_dense(self, dense_all):
+        return self._select(dense_all, self._dnn_dense_sel)
+
+    def input_from_feature_columns(self, X, feature_columns, embedding_dict, support_dense=True):
+        """Reference-shaped helper (basemodel.py:354-380): ([B,1,D] per sparse feature, [B,w] per dense feature)."""
+        sp, de = sparse_columns(feature_columns), dense_columns(feature_columns)
+        if not support_dense and len(de) > 0:
+            raise ValueError("DenseFeat is not supported in dnn_feature_columns")
+        ids, _ = ops.split_input(X, _expand_cols(self.feature_index, sp), [])
+        plan = _make_plan(sp, embedding_dict, sp[0].embedding_dim) if sp else None
+        emb_list = []
+        if sp:
+            emb = ops.SparseGather.apply(plan, ops.SegmentCache(), ids, *[e.weight for e in embedding_dict.values()])
+            emb_list = list(torch.split(emb, 1, dim=1))
+        dense_list = [X[:, self.feature_index[fc.name][0]:self.feature_index[fc.name][1]] for fc in de]
+        return emb_list, dense_list
+
+    def compute_input_dim(self, feature_columns, include_sparse=True, include_dense=True, feature_group=False):
+        sp = [fc for fc in feature_columns if isinstance(fc, (SparseFeat, VarLenSparseFeat))] if len(feature_columns) else []
+        de = dense_columns(feature_columns)
+        dense_dim = sum(fc.dimension for fc in de)
+        sparse_dim = len(sp) if feature_group else sum(fc.embedding_dim for fc in sp)
+        return (sparse_dim if include_sparse else 0) + (dense_dim if include_dense else 0)
+
+    @property
+    def embedding_size(self):
+        sp = [fc for fc in self.dnn_feature_columns if isinstance(fc, (SparseFeat, VarLenSparseFeat))]
+        sizes = set(fc.embedding_dim for fc in sp)
+        if len(sizes) > 1:
+            raise ValueError("embedding_dim of SparseFeat and VarlenSparseFeat must be same in this model!")
+        return list(sizes)[0]
+
+    def forward(self, X):
+        X = X.to(self.device) if not X.is_cuda else X
+        ids, dense = self.split_input(X)
+        return self.forward_ids(ids, dense)
+
+    def forward_ids(self, ids, dense):
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------------------------------
+    # regularisation
+    # ------------------------------------------------------------------------------------------
+    def add_regularization_weight(self, weight_list, l1=0.0, l2=0.0):
+        if isinstance(weight_list, torch.nn.parameter.Parameter):
+            weight_list = [weight_list]
+        else:
+            weight_list = list(weight_list)
+        self.regularization_weight.append((weight_list, l1, l2))
+
+    def get_regularization_loss(self):
+        """sum(l1*|p|) + sum(l2*p^2) over the registered tensors (reference: basemodel.py:412-428); autograd-visible.
+        The fused fit path does not call this: the optimizer kernels add 2*l2*w and accumulate the loss value."""
+        dev = next(self.parameters()).device
+        total = torch.zeros((1,), device=dev)
+        for weight_list, l1, l2 in self.regularization_weight:
+            for w in weight_list:
+                p = w[1] if isinstance(w, tuple) else w
+                if l1 > 0:
+                    total = total + torch.sum(l1 * torch.abs(p))
+                if l2 > 0:
+                    total = total + torch.sum(l2 * torch.square(p))
+        return total
+
+    def add_auxiliary_loss(self, aux_loss, alpha):
+        self.aux_loss = aux_loss * alpha
+
+    def _l2_map(self):
+        m = {}
+        has_l1 = False
+        for weight_list, l1, l2 in self.regularization_weight:
+            has_l1 = has_l1 or l1 > 0
+            for w in weight_list:
+                p = w[1] if isinstance(w, tuple) else w
+                m[id(p)] = m.get(id(p), 0.0) + float(l2)
+        return m, has_l1
+
+    # ------------------------------------------------------------------------------------------
+    # compile
+    # ------------------------------------------------------------------------------------------
+    def compile(self, optimizer, loss=None, metrics=None):
+        self.metrics_names = ["loss"]
+        self.optim = self._get_optim(optimizer)
+        self.loss_func = self._get_loss_func(loss)
+        self._loss_name = loss if isinstance(loss, str) else None
+        self.metrics = self._get_metrics(metrics)
+
+    def _table_sets(self):
+        l2map, _ = self._l2_map()
+        sets = []
+        emb_params = [e.weight for e in self.embedding_dict.values()]
+        if self._emb_plan is not None:
+            sets.append(TableSet(self._emb_plan, emb_params, l2map.get(id(emb_params[0]), 0.0)))
+        lin_params = [e.weight for e in self.linear_model.embedding_dict.values()]
+        if lin_params:
+            sets.append(TableSet(self.linear_model._plan, lin_params, l2map.get(id(lin_params[0]), 0.0)))
+        return sets
+
+    def _get_optim(self, optimizer):
+        if not isinstance(optimizer, str):
+            return optimizer
+        if optimizer not in ("sgd", "adam", "adagrad", "rmsprop"):
+            raise NotImplementedError
+        sets = self._table_sets()
+        table_ids = set(id(p) for ts in sets for p in ts.params)
+        dense_named = [(n, p) for n, p in self.named_parameters() if id(p) not in table_ids]
+        l2map, _ = self._l2_map()
+        return FusedOptimizer(optimizer, dense_named, sets, l2map)
+
+    def _get_loss_func(self, loss):
+        if isinstance(loss, str):
+            return self._get_loss_func_single(loss)
+        if isinstance(loss, list):
+            return [self._get_loss_func_single(l) for l in loss]
+        return loss
+
+    def _get_loss_func_single(self, loss):
+        if loss == "binary_crossentropy":
+            return F.binary_cross_entropy
+        if loss == "mse":
+            return F.mse_loss
+        if loss == "mae":
+            return F.l1_loss
+        raise NotImplementedError
+
+    def _log_loss(self, y_true, y_pred, eps=1e-7, normalize=True, sample_weight=None, labels=None):
+        from sklearn.metrics import log_loss
+        return log_loss(y_true, y_pred, eps, normalize, sample_weight, labels)
+
+    @staticmethod
+    def _accuracy_score(y_true, y_pred):
+        from sklearn.metrics import accuracy_score
+        return accuracy_score(y_true, np.where(y_pred > 0.5, 1, 0))
+
+    def _get_metrics(self, metrics, set_eps=False):
+        from sklearn.metrics import log_loss, mean_squared_error, roc_auc_score
+        out = {}
+        for metric in metrics or []:
+            if metric in ("binary_crossentropy", "logloss"):
+                out[metric] = self._log_loss if set_eps else log_loss
+            if metric == "auc":
+                out[metric] = roc_auc_score
+            if metric == "mse":
+                out[metric] = mean_squared_error
+            if metric in ("accuracy", "acc"):
+                out[metric] = self._accuracy_score
+            self.metrics_names.append(metric)
+        return out
+
+    def _in_multi_worker_mode(self):
+        return None
+
+    # ------------------------------------------------------------------------------------------
+    # host-side data plumbing
+    # ------------------------------------------------------------------------------------------
+    def _as_list(self, x):
+        if isinstance(x, dict):
+            x = [x[name] for name in self.feature_index]
+        x = list(x)
+        for i in range(len(x)):
+            if len(x[i].shape) == 1:
+                x[i] = np.expand_dims(x[i], axis=1)
+        return x
+
+    def _host_arrays(self, x):
+        """list of per-feature arrays (feature_index order) -> pinned (ids int32 [N, m_all], dense float32 [N, nd_all])."""
+        x = self._as_list(x)
+        names = list(self.feature_index.keys())
+        by_name = dict(zip(names, x))
+        n = x[0].shape[0] if x else 0
+        ids = np.empty((n, len(self._all_sparse)), dtype=np.int32)
+        for j, fc in enumerate(self._all_sparse):
+            col = np.asarray(by_name[fc.name]).reshape(n, -1)[:, 0]
+            ids[:, j] = col.astype(np.int64) if col.dtype.kind in "fc" else col   # truncation == .long()
+        dense = np.empty((n, len(self._all_dense_cols)), dtype=np.float32)
+        j = 0
+        for fc in self._all_dense:
+            a = np.asarray(by_name[fc.name]).reshape(n, -1)
+            dense[:, j:j + a.shape[1]] = a
+            j += a.shape[1]
+        for fc, j in zip(self._all_sparse, range(ids.shape[1])):
+            if n and (ids[:, j].min() < 0 or ids[:, j].max() >= fc.vocabulary_size):
+                raise IndexError("feature '%s': id out of range [0, %d)" % (fc.name, fc.vocabulary_size))
+        ids_t, dense_t = torch.from_numpy(ids), torch.from_numpy(dense)
+        if torch.cuda.is_available():
+            ids_t, dense_t = ids_t.pin_memory(), dense_t.pin_memory()
+        return ids_t, dense_t
+
+    def _batches(self, ids, dense, y, batch_size, order=None):
+        """Yield device batches (ids, dense, y or None); H2D copies run one batch ahead on a side stream."""
+        dev = torch.device(self.device)
+        n = ids.shape[0]
+        steps = (n - 1) // batch_size + 1 if n > 0 else 0
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        stage = [None, None]
+
+        def launch(i):
+            lo, hi = i * batch_size, min(n, (i + 1) * batch_size)
+            slot = i & 1
+            if order is None:
+                h = (ids[lo:hi], dense[lo:hi], None if y is None else y[lo:hi])
+            else:
+                idx = order[lo:hi]
+                if stage[slot] is None:
+                    stage[slot] = (torch.empty((batch_size, ids.shape[1]), dtype=ids.dtype).pin_memory(),
+                                   torch.empty((batch_size, dense.shape[1]), dtype=dense.dtype).pin_memory(),
+                                   None if y is None else torch.empty((batch_size,) + tuple(y.shape[1:]), dtype=y.dtype).pin_memory(),
+                                   [None])
+                si, sd, sy, ev = stage[slot]
+                if ev[0] is not None:
+                    ev[0].synchronize()
+                k = hi - lo
+                torch.index_select(ids, 0, idx, out=si[:k])
+                torch.index_select(dense, 0, idx, out=sd[:k])
+                if y is not None:
+                    torch.index_select(y, 0, idx, out=sy[:k])
+                h = (si[:k], sd[:k], None if y is None else sy[:k])
+            with torch.cuda.stream(copy_stream):
+                d = tuple(None if t is None else t.to(dev, non_blocking=True) for t in h)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            if order is not None:
+                stage[slot][3][0] = ev
+            return d, ev
+
+        nxt = launch(0) if steps > 0 else None
+        for i in range(steps):
+            cur, ev = nxt
+            nxt = launch(i + 1) if i + 1 < steps else None
+            main.wait_event(ev)
+            for t in cur:
+                if t is not None:
+                    t.record_stream(main)
+            yield cur
+
+    # ------------------------------------------------------------------------------------------
+    # fit / evaluate / predict
+    # ------------------------------------------------------------------------------------------
+    def _fused_ok(self):
+        _, has_l1 = self._l2_map()
+        aux_zero = (not torch.is_tensor(self.aux_loss)) or (not self.aux_loss.requires_grad and float(self.aux_loss.abs().sum()) == 0.0)
+        return isinstance(self.optim, FusedOptimizer) and not has_l1 and aux_zero and not isinstance(self.loss_func, list)
+
+    def train_step(self, ids, dense, y, loss_accum, pred_log=None, pred_off=0):
+        """One fused training step on device tensors: forward, loss, backward, optimizer (+L2).  No host sync."""
+        opt = self.optim
+        opt.zero_grad()
+        for ts in opt.table_sets:
+            ts.plan.sparse_grad = True      # backward leaves (unique rows, segment sums) for the fused optimizer
+        try:
+            return self._train_step_inner(opt, ids, dense, y, loss_accum, pred_log, pred_off)
+        finally:
+            for ts in opt.table_sets:
+                ts.plan.sparse_grad = False
+
+    def _train_step_inner(self, opt, ids, dense, y, loss_accum, pred_log, pred_off):
+        y_pred = self.forward_ids(ids, dense)
+        yv = y.reshape(-1)
+        if self._loss_name == "binary_crossentropy":
+            _, dy = ops.bce_sum(y_pred, yv, loss_accum)
+            y_pred.backward(dy.view_as(y_pred))
+        else:
+            loss = self.loss_func(y_pred.reshape(-1), yv, reduction="sum")
+            loss_accum += loss.detach().double()
+            loss.backward()
+        opt.step(apply_l2=True)
+        if pred_log is not None:
+            pred_log[pred_off:pred_off + yv.shape[0]] = y_pred.detach().reshape(-1)
+        return y_pred
+
+    def train_on_batch(self, ids, dense, y):
+        """Public single-step API: HOST tensors (ids int32 [B, m_all], dense float32 [B, nd_all], y float32 [B]; pinned
+        memory makes the copies asynchronous) -> python float BCE-sum of the batch.  H2D copy, fused step, D2H of the loss."""
+        dev = torch.device(self.device)
+        ids_d = ids.to(dev, non_blocking=True)
+        dense_d = dense.to(dev, non_blocking=True)
+        y_d = y.to(dev, non_blocking=True)
+        if not hasattr(self, "_tob_accum") or self._tob_accum.device != dev:
+            self._tob_accum = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._tob_accum.zero_()
+        self.train_step(ids_d, dense_d, y_d, self._tob_accum)
+        return float(self._tob_accum.item())
+
+    def fit(self, x=None, y=None, batch_size=None, epochs=1, verbose=1, initial_epoch=0, validation_split=0.,
+            validation_data=None, shuffle=True, callbacks=None):
+        x = self._as_list(x)
+        do_validation = False
+        val_x, val_y = [], []
+        if validation_data:
+            do_validation = True
+            if len(validation_data) == 2:
+                val_x, val_y = validation_data
+            elif len(validation_data) == 3:
+                val_x, val_y, _ = validation_data
+            else:
+                raise ValueError("When passing a `validation_data` argument, it must contain either 2 items (x_val, y_val), "
+                                 "or 3 items (x_val, y_val, val_sample_weights)")
+            val_x = self._as_list(val_x)
+        elif validation_split and 0. < validation_split < 1.:
+            do_validation = True
+            split_at = int(x[0].shape[0] * (1. - validation_split))
+            x, val_x = slice_arrays(x, 0, split_at), slice_arrays(x, split_at)
+            y, val_y = slice_arrays(y, 0, split_at), slice_arrays(y, split_at)
+            if not isinstance(x, list):
+                x, val_x = [x], [val_x]
+        if batch_size is None:
+            batch_size = 256
+        if self.gpus and len(self.gpus) > 1:
+            raise NotImplementedError(
+                "single-process DataParallel (`gpus=[...]`) is replaced by one process per GPU: launch with torchrun and "
+                "use deepctr.distributed (see INTEGRATION.md)")
+        if torch.device(self.device).type != "cuda":
+            raise RuntimeError("fit(): the xdeepfm-b200 path needs device='cuda:N' (sm_100a); no CPU fallback")
+
+        ids, dense = self._host_arrays(x)
+        y_t = torch.from_numpy(np.ascontiguousarray(np.asarray(y, dtype=np.float32)).reshape(ids.shape[0], -1))
+        if y_t.shape[1] == 1:
+            y_t = y_t.reshape(-1)
+        y_t = y_t.pin_memory()
+        sample_num = ids.shape[0]
+        steps_per_epoch = (sample_num - 1) // batch_size + 1
+        dev = torch.device(self.device)
+        self.train()
+        fused = self._fused_ok()
+
+        callbacks = CallbackList((callbacks or []) + [self.history])
+        callbacks.set_model(self)
+        callbacks.on_train_begin()
+        callbacks.set_model(self)
+        self.stop_training = False
+
+        print("Train on {0} samples, validate on {1} samples, {2} steps per epoch".format(sample_num, len(val_y), steps_per_epoch))
+        loss_accum = torch.zeros(1, dtype=torch.float64, device=dev)
+        total_accum = torch.zeros(1, dtype=torch.float64, device=dev)
+        for epoch in range(initial_epoch, epochs):
+            callbacks.on_epoch_begin(epoch)
+            epoch_logs = {}
+            start_time = time.time()
+            loss_accum.zero_()
+            total_accum.zero_()
+            if fused:
+                self.optim.prepare()
+                self.optim.reg_accum.zero_()
+            order = torch.randperm(sample_num) if shuffle else None
+            want_metrics = verbose > 0 and len(self.metrics) > 0
+            pred_log = torch.empty(sample_num, dtype=torch.float32, device=dev) if want_metrics else None
+            off = 0
+            self.train()
+            for ids_b, dense_b, y_b in self._batches(ids, dense, y_t, batch_size, order):
+                nb = ids_b.shape[0]
+                if fused:
+                    self.train_step(ids_b, dense_b, y_b, loss_accum, pred_log, off)
+                else:
+                    # generic path (user-supplied optimizer / loss list / l1 / aux loss): mirrors basemodel.py:245-262
+                    y_pred = self.forward_ids(ids_b, dense_b).squeeze()
+                    self.optim.zero_grad()
+                    if isinstance(self.loss_func, list):
+                        loss = sum(self.loss_func[i](y_pred[:, i], y_b[:, i], reduction="sum") for i in range(len(self.loss_func)))
+                    else:
+                        loss = self.loss_func(y_pred, y_b.squeeze(), reduction="sum")
+                    total = loss + self.get_regularization_loss() + self.aux_loss
+                    loss_accum += loss.detach().double()
+                    total_accum += total.detach().double().reshape(-1)
+                    total.backward()
+                    self.optim.step()
+                    if pred_log is not None:
+                        pred_log[off:off + nb] = y_pred.detach().reshape(-1)
+                off += nb
+            # ---- one host sync per epoch
+            if fused:
+                total_loss_epoch = float(loss_accum.item()) + self.optim.pop_reg_loss()
+            else:
+                total_loss_epoch = float(total_accum.item())
+            epoch_logs["loss"] = total_loss_epoch / sample_num
+            if want_metrics:
+                pred_host = pred_log.cpu().numpy().astype("float64")
+                y_host = y_t.numpy() if order is None else y_t[order].numpy()
+                for name, fn in self.metrics.items():
+                    vals = []
+                    for s in range(steps_per_epoch):
+                        lo, hi = s * batch_size, min(sample_num, (s + 1) * batch_size)
+                        vals.append(fn(y_host[lo:hi], pred_host[lo:hi]))
+                    epoch_logs[name] = np.sum(vals) / steps_per_epoch
+            if do_validation:
+                for name, result in self.evaluate(val_x, val_y, batch_size).items():
+                    epoch_logs["val_" + name] = result
+            if verbose > 0:
+                epoch_time = int(time.time() - start_time)
+                print("Epoch {0}/{1}".format(epoch + 1, epochs))
+                msg = "{0}s - loss: {1: .4f}".format(epoch_time, epoch_logs["loss"])
+                for name in self.metrics:
+                    msg += " - " + name + ": {0: .4f}".format(epoch_logs[name])
+                if do_validation:
+                    for name in self.metrics:
+                        msg += " - val_" + name + ": {0: .4f}".format(epoch_logs["val_" + name])
+                print(msg)
+            callbacks.on_epoch_end(epoch, epoch_logs)
+            if self.stop_training:
+                break
+        callbacks.on_train_end()
+        return self.history
+
+    def evaluate(self, x, y, batch_size=256):
+        pred = self.predict(x, batch_size)
+        return {name: fn(y, pred) for name, fn in self.metrics.items()}
+
+    def predict(self, x, batch_size=256):
+        """Batched no-grad forward; float64 [N, 1] numpy like the reference (basemodel.py:325-352), one D2H at the end."""
+        if torch.device(self.device).type != "cuda":
+            raise RuntimeError("predict(): the xdeepfm-b200 path needs device='cuda:N' (sm_100a); no CPU fallback")
+        self.eval()
+        ids, dense = self._host_arrays(x)
+        n = ids.shape[0]
+        out = torch.empty((n, 1), dtype=torch.float32, device=torch.device(self.device))
+        off = 0
+        with torch.no_grad():
+            for ids_b, dense_b, _ in self._batches(ids, dense, None, batch_size, None):
+                yb = self.forward_ids(ids_b, dense_b)
+                out[off:off + yb.shape[0]] = yb.reshape(-1, 1)
+                off += yb.shape[0]
+        return out.cpu().numpy().astype("float64")

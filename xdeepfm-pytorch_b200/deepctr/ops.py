@@ -1,0 +1,455 @@
+"""Autograd-visible operators of the B200 hot path.  Every op enqueues hand-written sm_100a kernels from
+libxdfm_sm100a.so on torch's current stream; torch only owns memory and the autograd tape.
+
+Operators (reference code they replace):
+  split_input      X[:, i:i+1].long() / dense column views      deepctr/models/basemodel.py:368-370, 377-378
+  SparseGather     26x nn.Embedding + cat(dim=1)                deepctr/models/basemodel.py:354-380, xdeepfm.py:86
+  LinearTerm       Linear.forward                               deepctr/models/basemodel.py:63-92
+  CINFunction      CIN.forward                                  deepctr/layers/interaction.py:207-248
+  LinearAct        nn.Linear -> activation                      deepctr/layers/core.py:120-134
+  LogitHead        dnn_linear/cin_linear + sum + PredictionLayer deepctr/models/xdeepfm.py:88-105, layers/core.py:154-160
+"""
+import torch
+
+from . import _native as N
+
+_WS = {}
+
+# optional per-operator device timing (bench.py / profiling): name -> [(start_event, end_event), ...]
+TIMERS = None
+
+
+class timed:
+    """`with timed("cin_fwd"):` brackets the enclosed kernel launches with CUDA events on the current stream
+    when TIMERS is a dict; otherwise it costs one attribute check."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if TIMERS is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if TIMERS is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            TIMERS.setdefault(self.name, []).append((self.e0, e1))
+        return False
+
+
+def timer_totals():
+    """ms per operator name (call after torch.cuda.synchronize())."""
+    return {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in (TIMERS or {}).items()}
+
+
+def workspace(name, nbytes, device):
+    """Cached scratch buffer (uint8) per (name, device); grows monotonically."""
+    key = (name, device.index if device.index is not None else torch.cuda.current_device())
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError("%s: the xdeepfm-b200 path runs on CUDA (sm_100a) only; got a %s tensor. "
+                           "There is no CPU fallback -- construct the model with device='cuda:0'." % (what, t.device))
+
+
+# ------------------------------------------------------------------------------------------------
+# input split
+# ------------------------------------------------------------------------------------------------
+def split_input(X, sparse_cols, dense_cols):
+    """X float32 [B, ncol] -> (ids int32 [B, m], dense float32 [B, nd])."""
+    require_cuda(X, "split_input")
+    X = _f32c(X)
+    B, ncol = X.shape
+    m, nd = len(sparse_cols), len(dense_cols)
+    ids = torch.empty((B, m), dtype=torch.int32, device=X.device)
+    dense = torch.empty((B, nd), dtype=torch.float32, device=X.device)
+    N.check(N.lib().xdfm_split_input(N.ptr(X), B, ncol, N.i32_array(sparse_cols), m, N.i32_array(dense_cols), nd,
+                                     N.ptr(ids), N.ptr(dense), N.stream_ptr()))
+    return ids, dense
+
+
+# ------------------------------------------------------------------------------------------------
+# sparse plan + segment cache shared by the embedding and linear-term lookups of one step
+# ------------------------------------------------------------------------------------------------
+class SparsePlan:
+    """Static description of a set of sparse features looked up together.
+
+    feature f -> table index table_of[f]; tables have `rows[t]` rows; the scatter-add key space is the
+    concatenation of the tables (row_off).  `sparse_grad` = True routes the backward result to `self.stash`
+    (unique rows + summed gradients, consumed by the fused optimizer) instead of dense autograd gradients.
+    """
+
+    def __init__(self, table_of, rows, width):
+        self.table_of = list(table_of)
+        self.rows = list(rows)
+        self.width = int(width)
+        self.m = len(self.table_of)
+        self.T = len(self.rows)
+        if self.m > N.MAX_FIELDS:
+            raise ValueError("at most %d sparse features are supported" % N.MAX_FIELDS)
+        self.row_off = [0]
+        for r in self.rows:
+            self.row_off.append(self.row_off[-1] + int(r))
+        self.vocab = [self.rows[t] for t in self.table_of]
+        self.feat_row_off = [self.row_off[t] for t in self.table_of]
+        self.sparse_grad = False
+        self.stash = None
+        self._c_vocab = N.i32_array(self.vocab)
+        self._c_feat_off = N.i64_array(self.feat_row_off)
+        self._c_row_off = N.i64_array(self.row_off)
+
+    def signature(self):
+        return (tuple(self.table_of), tuple(self.rows))
+
+
+class SegmentCache:
+    """Sort + run-length segments of one ids tensor, reused by every lookup that shares the key space."""
+
+    def __init__(self):
+        self.key = None
+        self.val = None
+
+    def get(self, plan, ids):
+        key = (ids.data_ptr(), ids._version, tuple(ids.shape), plan.signature())
+        if self.key == key:
+            return self.val
+        B, m = ids.shape
+        n = B * m
+        dev = ids.device
+        uniq = torch.empty(max(n, 1), dtype=torch.int32, device=dev)       # uint32 bit pattern
+        seg_off = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        pos = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        nseg = torch.zeros(1, dtype=torch.int32, device=dev)
+        nb = N.lib().xdfm_embed_bwd_workspace_bytes(n)
+        ws = workspace("embed_bwd", nb, dev)
+        N.check(N.lib().xdfm_embed_bwd_segments(N.ptr(ids), B, m, plan._c_feat_off, plan._c_vocab, plan.row_off[-1],
+                                                N.ptr(ws), ws.numel(), N.ptr(uniq), N.ptr(seg_off), N.ptr(pos), N.ptr(nseg),
+                                                N.stream_ptr()))
+        self.key, self.val = key, (uniq, seg_off, pos, nseg, n)
+        return self.val
+
+    def clear(self):
+        self.key = self.val = None
+
+
+def segment_reduce(plan, seg, demb, dlin, width):
+    """(gsum [n, width] or None, gsum_lin [n] or None) for the segments `seg`."""
+    uniq, seg_off, pos, nseg, n = seg
+    dev = uniq.device
+    gsum = torch.empty((max(n, 1), width), dtype=torch.float32, device=dev) if demb is not None else None
+    gsum_lin = torch.empty(max(n, 1), dtype=torch.float32, device=dev) if dlin is not None else None
+    with timed("embed_scatter"):
+        N.check(N.lib().xdfm_embed_bwd_reduce(N.ptr(demb), N.ptr(dlin), N.ptr(pos), N.ptr(seg_off), N.ptr(nseg), n, plan.m,
+                                              width, N.ptr(gsum), N.ptr(gsum_lin), N.stream_ptr()))
+    return gsum, gsum_lin
+
+
+def scatter_dense(plan, seg, gsum, width, tables):
+    """Dense per-table gradients (zeros + scatter of the segment sums)."""
+    uniq, seg_off, pos, nseg, n = seg
+    grads = [torch.zeros_like(t) for t in tables]
+    N.check(N.lib().xdfm_embed_bwd_scatter_dense(N.ptr_array(grads), plan._c_row_off, plan.T, width, N.ptr(uniq), N.ptr(gsum),
+                                                 N.ptr(nseg), n, N.stream_ptr()))
+    return grads
+
+
+class SparseGather(torch.autograd.Function):
+    """out[b, f, :] = tables[table_of[f]][ids[b, f], :]  ->  [B, m, D]"""
+
+    @staticmethod
+    def forward(ctx, plan, cache, ids, *tables):
+        require_cuda(ids, "SparseGather")
+        B, m = ids.shape
+        D = plan.width
+        out = torch.empty((B, m, D), dtype=torch.float32, device=ids.device)
+        per_feat = [tables[t] for t in plan.table_of]
+        with timed("embed_gather"):
+            N.check(N.lib().xdfm_embed_gather(N.ptr_array(per_feat), None, plan._c_vocab, N.ptr(ids), B, m, D, N.ptr(out),
+                                              None, 0, None, None, N.stream_ptr()))
+        ctx.plan, ctx.cache, ctx.ids, ctx.tables = plan, cache, ids, tables
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        plan = ctx.plan
+        dout = _f32c(dout)
+        seg = ctx.cache.get(plan, ctx.ids)
+        gsum, _ = segment_reduce(plan, seg, dout, None, plan.width)
+        if plan.sparse_grad:
+            plan.stash = (seg, gsum)
+            return (None, None, None) + tuple(None for _ in ctx.tables)
+        grads = scatter_dense(plan, seg, gsum, plan.width, ctx.tables)
+        return (None, None, None) + tuple(grads)
+
+
+class LinearTerm(torch.autograd.Function):
+    """lin[b] = sum_f lin_tables[table_of[f]][ids[b, f]] + dense[b, :] @ dense_w   ->  [B, 1]"""
+
+    @staticmethod
+    def forward(ctx, plan, cache, ids, dense, dense_w, *lin_tables):
+        require_cuda(ids, "LinearTerm")
+        B, m = ids.shape
+        nd = 0 if dense is None or dense_w is None else dense.shape[1]
+        out = torch.empty((B,), dtype=torch.float32, device=ids.device)
+        per_feat = [lin_tables[t] for t in plan.table_of]
+        N.check(N.lib().xdfm_embed_gather(None, N.ptr_array(per_feat) if m > 0 else None, plan._c_vocab, N.ptr(ids), B, m, 1, None,
+                                          N.ptr(dense) if nd > 0 else None, nd, N.ptr(dense_w) if nd > 0 else None,
+                                          N.ptr(out), N.stream_ptr()))
+        ctx.plan, ctx.cache, ctx.ids, ctx.lin_tables = plan, cache, ids, lin_tables
+        ctx.dense, ctx.nd = dense, nd
+        ctx.dense_w_shape = None if dense_w is None else dense_w.shape
+        return out.view(B, 1)
+
+    @staticmethod
+    def backward(ctx, dout):
+        plan = ctx.plan
+        dlin = _f32c(dout).reshape(-1)
+        B = dlin.shape[0]
+        d_dense_w = None
+        if ctx.nd > 0:
+            d_dense_w = torch.empty(ctx.nd, dtype=torch.float32, device=dlin.device)
+            ws = workspace("wcolsum", N.lib().xdfm_wcolsum_workspace_bytes(ctx.nd), dlin.device)
+            N.check(N.lib().xdfm_wcolsum(N.ptr(ctx.dense), B, ctx.nd, ctx.nd, N.ptr(dlin), N.ptr(d_dense_w), 0, N.ptr(ws),
+                                         ws.numel(), N.stream_ptr()))
+            d_dense_w = d_dense_w.view(ctx.dense_w_shape)
+        table_grads = tuple(None for _ in ctx.lin_tables)
+        if plan.m > 0:
+            seg = ctx.cache.get(plan, ctx.ids)
+            _, gsum_lin = segment_reduce(plan, seg, None, dlin, 1)
+            if plan.sparse_grad:
+                plan.stash = (seg, gsum_lin)
+            else:
+                table_grads = tuple(scatter_dense(plan, seg, gsum_lin, 1, ctx.lin_tables))
+        return (None, None, None, None, d_dense_w) + table_grads
+
+
+# ------------------------------------------------------------------------------------------------
+# CIN
+# ------------------------------------------------------------------------------------------------
+class CINConfig:
+    def __init__(self, field_size, layer_size, split_half, activation, pool=True, impl="fp32"):
+        self.m = int(field_size)
+        self.layer_size = tuple(int(s) for s in layer_size)
+        self.split_half = bool(split_half)
+        self.act = N.ACT[activation]
+        self.pool = bool(pool)
+        self.impl = impl
+        n = len(self.layer_size)
+        self.Hp, self.direct_begin, self.n_next, self.col_off = [], [], [], []
+        prev, col = self.m, 0
+        for k, H in enumerate(self.layer_size):
+            self.Hp.append(prev)
+            last = k == n - 1
+            if self.split_half:
+                db = 0 if last else H // 2
+                nxt = 0 if last else H // 2
+            else:
+                db = 0
+                nxt = 0 if last else H
+            self.direct_begin.append(db)
+            self.n_next.append(nxt)
+            self.col_off.append(col)
+            col += H - db
+            prev = H // 2 if self.split_half else H
+        self.fm = col
+
+
+class CINFunction(torch.autograd.Function):
+    """CIN forward/backward; args: cfg, x0 [B,m,D], then W_0, b_0, W_1, b_1, ..."""
+
+    @staticmethod
+    def forward(ctx, cfg, x0, *wb):
+        require_cuda(x0, "CIN")
+        x0 = _f32c(x0)
+        B, m, D = x0.shape
+        dev = x0.device
+        L = N.lib()
+        out = torch.empty((B, cfg.fm) if cfg.pool else (B, cfg.fm, D), dtype=torch.float32, device=dev)
+        ys = []
+        xk, xk_stride = x0, m * D
+        for k, H in enumerate(cfg.layer_size):
+            W = _f32c(wb[2 * k]).view(H, -1)
+            b = _f32c(wb[2 * k + 1])
+            y = torch.empty((B, H, D), dtype=torch.float32, device=dev)
+            with timed("cin_fwd"):
+                N.check(L.xdfm_cin_fwd_f32(N.ptr(x0), N.ptr(xk), xk_stride, N.ptr(W), N.ptr(b), B, m, cfg.Hp[k], H, D, cfg.act,
+                                           N.ptr(y), cfg.direct_begin[k], N.ptr(out) if cfg.pool else None,
+                                           None if cfg.pool else N.ptr(out), cfg.fm, cfg.col_off[k], N.stream_ptr()))
+            ys.append(y)
+            xk, xk_stride = y, H * D
+        ctx.cfg, ctx.x0, ctx.ys, ctx.wb = cfg, x0, ys, wb
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        cfg, x0, ys, wb = ctx.cfg, ctx.x0, ctx.ys, ctx.wb
+        dout = _f32c(dout)
+        B, m, D = x0.shape
+        dev = x0.device
+        L = N.lib()
+        dx0 = torch.zeros_like(x0)
+        grads = [None] * len(wb)
+        dnext = None
+        for k in range(len(cfg.layer_size) - 1, -1, -1):
+            H, Hp = cfg.layer_size[k], cfg.Hp[k]
+            y = ys[k]
+            dy = torch.empty_like(y)
+            N.check(L.xdfm_cin_dy(N.ptr(y), B, H, D, cfg.act, cfg.direct_begin[k], N.ptr(dout) if cfg.pool else None,
+                                  None if cfg.pool else N.ptr(dout), cfg.fm, cfg.col_off[k], N.ptr(dnext), cfg.n_next[k],
+                                  N.ptr(dy), N.stream_ptr()))
+            xk, xk_stride = (x0, m * D) if k == 0 else (ys[k - 1], cfg.layer_size[k - 1] * D)
+            W = _f32c(wb[2 * k]).view(H, -1)
+            dW = torch.empty_like(W)
+            db = torch.empty(H, dtype=torch.float32, device=dev)
+            dxk = torch.empty((B, Hp, D), dtype=torch.float32, device=dev)
+            nb = L.xdfm_cin_bwd_f32_workspace_bytes(B, m, Hp, H, D)
+            ws = workspace("cin_bwd", nb, dev)
+            with timed("cin_bwd"):
+                N.check(L.xdfm_cin_bwd_f32(N.ptr(x0), N.ptr(xk), xk_stride, N.ptr(W), N.ptr(dy), B, m, Hp, H, D, N.ptr(dW), N.ptr(db),
+                                           N.ptr(dxk), N.ptr(dx0), N.ptr(ws), ws.numel(), N.stream_ptr()))
+            grads[2 * k] = dW.view(wb[2 * k].shape)
+            grads[2 * k + 1] = db
+            dnext = dxk
+        dx0.add_(dnext)   # layer 0: X^{k-1} is X^0 itself
+        return (None, dx0) + tuple(grads)
+
+
+# ------------------------------------------------------------------------------------------------
+# dense layers
+# ------------------------------------------------------------------------------------------------
+def gemm(transA, transB, M, Nn, K, A, lda, Bm, ldb, C, ldc, bias=None, act=0, accumulate=False):
+    L = N.lib()
+    nb = L.xdfm_gemm_workspace_bytes(M, Nn, K)
+    ws = workspace("gemm", nb, C.device) if nb > 0 else None
+    N.check(L.xdfm_gemm_f32(int(transA), int(transB), M, Nn, K, N.ptr(A), lda, N.ptr(Bm), ldb, N.ptr(C), ldc, N.ptr(bias), act,
+                            int(accumulate), N.ptr(ws), 0 if ws is None else ws.numel(), N.stream_ptr()))
+
+
+class LinearAct(torch.autograd.Function):
+    """y = act(x @ W.T + b);  x [..., K], W [N, K], b [N] or None."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, act):
+        require_cuda(x, "LinearAct")
+        shp = x.shape
+        x2 = _f32c(x).reshape(-1, shp[-1])
+        W = _f32c(W)
+        Bn, K = x2.shape
+        Nn = W.shape[0]
+        y = torch.empty((Bn, Nn), dtype=torch.float32, device=x.device)
+        gemm(0, 1, Bn, Nn, K, x2, K, W, K, y, Nn, bias=None if b is None else _f32c(b), act=act)
+        ctx.save_for_backward(x2, W, y)
+        ctx.act, ctx.has_bias, ctx.shp = act, b is not None, shp
+        return y.view(*shp[:-1], Nn)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, W, y = ctx.saved_tensors
+        Bn, K = x2.shape
+        Nn = W.shape[0]
+        dy = _f32c(dy).reshape(Bn, Nn)
+        L = N.lib()
+        if ctx.act != 0:
+            dym = torch.empty_like(dy)
+            N.check(L.xdfm_act_bwd(N.ptr(dy), N.ptr(y), N.ptr(dym), dy.numel(), ctx.act, N.stream_ptr()))
+        else:
+            dym = dy
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x2)
+            gemm(0, 0, Bn, K, Nn, dym, Nn, W, K, dx, K)
+            dx = dx.view(ctx.shp)
+        if ctx.needs_input_grad[1]:
+            dW = torch.empty_like(W)
+            gemm(1, 0, Nn, K, Bn, dym, Nn, x2, K, dW, K)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.empty(Nn, dtype=torch.float32, device=dy.device)
+            ws = workspace("wcolsum", L.xdfm_wcolsum_workspace_bytes(Nn), dy.device)
+            N.check(L.xdfm_wcolsum(N.ptr(dym), Bn, Nn, Nn, None, N.ptr(db), 0, N.ptr(ws), ws.numel(), N.stream_ptr()))
+        return dx, dW, db, None
+
+
+def linear_act(x, W, b=None, activation=None):
+    return LinearAct.apply(x, W, b, N.ACT[activation])
+
+
+class LogitHead(torch.autograd.Function):
+    """y_pred [B,1] = sigmoid(lin + dnn_out @ w_dnn.T + cin_out @ w_cin.T + bias)  (binary) or the raw sum."""
+
+    @staticmethod
+    def forward(ctx, lin, cin_out, w_cin, dnn_out, w_dnn, bias, binary):
+        ref = lin if lin is not None else (cin_out if cin_out is not None else dnn_out)
+        require_cuda(ref, "LogitHead")
+        B = ref.shape[0]
+        lin_c = None if lin is None else _f32c(lin).reshape(-1)
+        cin_c = None if cin_out is None else _f32c(cin_out)
+        dnn_c = None if dnn_out is None else _f32c(dnn_out)
+        wc = None if w_cin is None else _f32c(w_cin).reshape(-1)
+        wd = None if w_dnn is None else _f32c(w_dnn).reshape(-1)
+        bs = None if bias is None else _f32c(bias)
+        fm = 0 if cin_c is None else cin_c.shape[1]
+        hd = 0 if dnn_c is None else dnn_c.shape[1]
+        y = torch.empty(B, dtype=torch.float32, device=ref.device)
+        N.check(N.lib().xdfm_head_fwd(N.ptr(lin_c), N.ptr(cin_c), N.ptr(wc), fm, N.ptr(dnn_c), N.ptr(wd), hd, N.ptr(bs), B,
+                                      int(binary), N.ptr(y), N.stream_ptr()))
+        ctx.saved = (cin_c, wc, dnn_c, wd, y)
+        ctx.meta = (B, fm, hd, int(binary), None if lin is None else lin.shape, None if w_cin is None else w_cin.shape,
+                    None if w_dnn is None else w_dnn.shape, bias is not None)
+        return y.view(B, 1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        cin_c, wc, dnn_c, wd, y = ctx.saved
+        B, fm, hd, binary, lin_shape, wc_shape, wd_shape, has_bias = ctx.meta
+        dev = y.device
+        L = N.lib()
+        dy = _f32c(dy).reshape(-1)
+        dlogit = torch.empty(B, dtype=torch.float32, device=dev)
+        d_cin = torch.empty_like(cin_c) if cin_c is not None else None
+        d_dnn = torch.empty_like(dnn_c) if dnn_c is not None else None
+        N.check(L.xdfm_head_bwd(N.ptr(dy), N.ptr(y), B, binary, N.ptr(wc), fm, N.ptr(wd), hd, N.ptr(dlogit), N.ptr(d_cin),
+                                N.ptr(d_dnn), N.stream_ptr()))
+        ws = workspace("wcolsum", L.xdfm_wcolsum_workspace_bytes(max(fm, hd, 1)), dev)
+        d_wc = d_wd = d_bias = None
+        if cin_c is not None:
+            d_wc = torch.empty(fm, dtype=torch.float32, device=dev)
+            N.check(L.xdfm_wcolsum(N.ptr(cin_c), B, fm, fm, N.ptr(dlogit), N.ptr(d_wc), 0, N.ptr(ws), ws.numel(), N.stream_ptr()))
+            d_wc = d_wc.view(wc_shape)
+        if dnn_c is not None:
+            d_wd = torch.empty(hd, dtype=torch.float32, device=dev)
+            N.check(L.xdfm_wcolsum(N.ptr(dnn_c), B, hd, hd, N.ptr(dlogit), N.ptr(d_wd), 0, N.ptr(ws), ws.numel(), N.stream_ptr()))
+            d_wd = d_wd.view(wd_shape)
+        if has_bias:
+            d_bias = torch.empty(1, dtype=torch.float32, device=dev)
+            N.check(L.xdfm_wcolsum(N.ptr(dlogit), B, 1, 1, None, N.ptr(d_bias), 0, N.ptr(ws), ws.numel(), N.stream_ptr()))
+        d_lin = dlogit.view(lin_shape) if lin_shape is not None else None
+        return d_lin, d_cin, d_wc, d_dnn, d_wd, d_bias, None
+
+
+def bce_sum(y_pred, labels, loss_accum=None, scale=1.0, want_grad=True):
+    """Fused F.binary_cross_entropy(y_pred, y, reduction='sum').
+    Adds the loss into `loss_accum` (float64 [1] device tensor) and returns dL/dy_pred (or None)."""
+    require_cuda(y_pred, "bce_sum")
+    p = _f32c(y_pred).reshape(-1)
+    y = _f32c(labels).reshape(-1)
+    B = p.shape[0]
+    if loss_accum is None:
+        loss_accum = torch.zeros(1, dtype=torch.float64, device=p.device)
+    g = torch.empty_like(p) if want_grad else None
+    N.check(N.lib().xdfm_bce_sum(N.ptr(p), N.ptr(y), B, float(scale), None, N.ptr(g), N.ptr(loss_accum), N.stream_ptr()))
+    return loss_accum, g

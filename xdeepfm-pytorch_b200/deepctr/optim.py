@@ -1,0 +1,178 @@
+"""Fused optimizers (replace torch.optim.{SGD,Adam,Adagrad,RMSprop} chosen by name in the reference:
+deepctr/models/basemodel.py:447-461) and the L2 regulariser (basemodel.py:412-428).
+
+One flat fp32 buffer holds every dense parameter (CIN, DNN, heads, attention ...): a single kernel updates all of them.
+Embedding tables (and the [V,1] first-order tables) are updated in place by two kernels per table set: the rows the batch
+touched (unique rows + deterministic segment sums from ops.SparseGather/LinearTerm) and -- to keep the reference's dense
+semantics, where EVERY row moves every step because of L2 and optimizer momentum -- a streaming pass over all other rows.
+"""
+import torch
+
+from . import _native as N
+from . import ops
+
+_TORCH_DEFAULTS = {
+    "sgd": dict(lr=0.01),
+    "adam": dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8),
+    "adagrad": dict(lr=0.01, lr_decay=0.0, eps=1e-10),
+    "rmsprop": dict(lr=0.01, alpha=0.99, eps=1e-8),
+}
+_N_STATES = {"sgd": 0, "adam": 2, "adagrad": 1, "rmsprop": 1}
+
+
+class TableSet:
+    """One group of tables sharing a SparsePlan (embedding tables of width D, or first-order tables of width 1)."""
+
+    def __init__(self, plan, params, l2):
+        self.plan, self.params, self.l2 = plan, list(params), float(l2)
+        self.s1 = self.s2 = None
+        self.bitmap = None
+
+
+class FusedOptimizer(torch.optim.Optimizer):
+    """torch.optim.Optimizer-compatible (param_groups / state_dict) front end of the fused kernels."""
+
+    def __init__(self, kind, dense_named_params, table_sets, l2_of_param, **overrides):
+        if kind not in _TORCH_DEFAULTS:
+            raise NotImplementedError(kind)
+        defaults = dict(_TORCH_DEFAULTS[kind])
+        defaults.update(overrides)
+        self.kind = kind
+        self.dense_named = list(dense_named_params)
+        self.table_sets = list(table_sets)
+        all_params = [p for _, p in self.dense_named] + [p for ts in self.table_sets for p in ts.params]
+        super().__init__(all_params, defaults)
+        self._l2_of_param = l2_of_param          # id(param) -> l2 strength (sum over registrations)
+        self._flat = None
+        self.sparse_embedding_update = False     # True: only rows touched by the batch are updated (NOT reference semantics)
+        self.reg_accum = None                    # float64 [1] device: sum of l2*w^2 seen by the last step(s)
+        self.steps = 0
+
+    # -------------------------------------------------------------------------------------------
+    def _cfg(self, l2):
+        g = self.param_groups[0]
+        c = N.OptCfg()
+        c.kind = N.OPT[self.kind]
+        c.lr = float(g["lr"])
+        b1, b2 = g.get("betas", (0.9, 0.999))
+        c.beta1, c.beta2 = float(b1), float(b2)
+        c.eps = float(g.get("eps", 1e-8))
+        c.alpha = float(g.get("alpha", 0.99))
+        c.lr_decay = float(g.get("lr_decay", 0.0))
+        c.l2 = float(l2)
+        return c
+
+    def _dense_params(self):
+        return [p for _, p in self.dense_named]
+
+    def _flat_valid(self):
+        if self._flat is None:
+            return False
+        w = self._flat["w"]
+        off = 0
+        for p in self._dense_params():
+            if p.data_ptr() != w.data_ptr() + off * 4 or p.device != w.device:
+                return False
+            off += p.numel()
+        return True
+
+    def prepare(self):
+        """(Re)build the flat views; called lazily and whenever the parameters were moved (.to(device))."""
+        params = self._dense_params()
+        if self._flat_valid():
+            return
+        dev = params[0].device if params else self.table_sets[0].params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("FusedOptimizer needs the model on a CUDA device (no CPU fallback); got %s" % dev)
+        n = sum(p.numel() for p in params)
+        old = self._flat
+        w = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+        g = torch.zeros(max(n, 1), dtype=torch.float32, device=dev)
+        l2vec = torch.zeros(max(n, 1), dtype=torch.float32, device=dev)
+        off = 0
+        for p in params:
+            k = p.numel()
+            w[off:off + k].copy_(p.data.reshape(-1))
+            p.data = w[off:off + k].view(p.shape)
+            p.grad = g[off:off + k].view(p.shape)
+            l2vec[off:off + k] = self._l2_of_param.get(id(p), 0.0)
+            off += k
+        ns = _N_STATES[self.kind]
+        s1 = torch.zeros_like(w) if ns >= 1 else None
+        s2 = torch.zeros_like(w) if ns >= 2 else None
+        if old is not None and old["w"].numel() == w.numel():
+            if s1 is not None and old["s1"] is not None:
+                s1.copy_(old["s1"])
+            if s2 is not None and old["s2"] is not None:
+                s2.copy_(old["s2"])
+        opt_dev = torch.zeros(8, dtype=torch.float32, device=dev)
+        if old is not None:
+            opt_dev.copy_(old["opt_dev"])
+        self._flat = dict(w=w, g=g, s1=s1, s2=s2, l2vec=l2vec, n=n, opt_dev=opt_dev, any_l2=bool((l2vec != 0).any().item()))
+        self.reg_accum = torch.zeros(1, dtype=torch.float64, device=dev)
+        for ts in self.table_sets:
+            if ts.s1 is None or ts.s1[0].device != dev:
+                ts.s1 = [torch.zeros_like(p.data) for p in ts.params] if ns >= 1 else None
+                ts.s2 = [torch.zeros_like(p.data) for p in ts.params] if ns >= 2 else None
+                ts.bitmap = torch.zeros((ts.plan.row_off[-1] + 31) // 32 + 1, dtype=torch.int32, device=dev)
+
+    # -------------------------------------------------------------------------------------------
+    def zero_grad(self, set_to_none=True):
+        if self._flat is not None and self._flat_valid():
+            self._flat["g"].zero_()
+        else:
+            for _, p in self.dense_named:
+                p.grad = None
+        for ts in self.table_sets:
+            ts.plan.stash = None
+            for p in ts.params:
+                p.grad = None
+
+    @torch.no_grad()
+    def step(self, closure=None, apply_l2=False, grad_scale=1.0):
+        """One optimizer step.  apply_l2=True adds the regulariser gradient 2*l2*w inside the kernels (fused fit path);
+        with apply_l2=False the gradients are used as they are (the caller back-propagated the reg loss itself)."""
+        if closure is not None:
+            raise NotImplementedError("closure is not supported")
+        self.prepare()
+        L = N.lib()
+        f = self._flat
+        st = N.stream_ptr()
+        cfg0 = self._cfg(0.0)
+        N.check(L.xdfm_opt_tick(N.ptr(f["opt_dev"]), cfg0, st))
+        if f["n"] > 0:
+            N.check(L.xdfm_flat_opt(cfg0, N.ptr(f["opt_dev"]), f["n"], N.ptr(f["w"]), N.ptr(f["g"]), N.ptr(f["s1"]), N.ptr(f["s2"]),
+                                    N.ptr(f["l2vec"]) if (apply_l2 and f["any_l2"]) else None, float(grad_scale),
+                                    N.ptr(self.reg_accum), st))
+        for ts in self.table_sets:
+            plan = ts.plan
+            cfg = self._cfg(ts.l2 if apply_l2 else 0.0)
+            dense_grads = [p.grad for p in ts.params]
+            if plan.stash is not None:
+                (uniq, seg_off, pos, nseg, n), gsum = plan.stash
+                dense_pass = 0 if self.sparse_embedding_update else 1
+                if self.kind == "sgd" and cfg.l2 == 0.0:
+                    dense_pass = 0      # nothing moves on untouched rows: g == 0 and no optimizer state
+                with ops.timed("rows_opt"):
+                    N.check(L.xdfm_rows_opt(cfg, N.ptr(f["opt_dev"]), N.ptr_array([p.data for p in ts.params]),
+                                            N.ptr_array(ts.s1) if ts.s1 else None, N.ptr_array(ts.s2) if ts.s2 else None,
+                                            plan._c_row_off, plan.T, plan.width, N.ptr(uniq), N.ptr(gsum), N.ptr(nseg), n,
+                                            float(grad_scale), N.ptr(ts.bitmap), dense_pass, N.ptr(self.reg_accum), st))
+                plan.stash = None
+            elif any(g is not None for g in dense_grads):
+                # dense .grad tensors (generic autograd path): every table is one flat update
+                for i, p in enumerate(ts.params):
+                    if p.grad is None:
+                        continue
+                    l2v = None
+                    N.check(L.xdfm_flat_opt(cfg, N.ptr(f["opt_dev"]), p.numel(), N.ptr(p.data), N.ptr(p.grad.contiguous()),
+                                            N.ptr(ts.s1[i]) if ts.s1 else None, N.ptr(ts.s2[i]) if ts.s2 else None, l2v,
+                                            float(grad_scale), None, st))
+        self.steps += 1
+        return None
+
+    def pop_reg_loss(self):
+        """Sum of l2*w^2 accumulated since the last call (device float64 -> python float; one sync)."""
+        v = float(self.reg_accum.item())
+        self.reg_accum.zero_()
+        return v
