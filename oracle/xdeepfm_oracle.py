@@ -132,7 +132,7 @@ def _activation(name, x):
 
 
 def cin_forward(x0: torch.Tensor, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor],
-                split_half=True, activation="relu", pool=True):
+                split_half=True, activation="relu", pool=True, relu_masks=None):
     """Compressed Interaction Network (interaction.py:207-248).
 
     x0 [B, m, D];  weights[k] is the Conv1d(k=1) weight [H_k, h_{k-1}*m, 1] (or [H_k, h_{k-1}*m]);
@@ -149,7 +149,12 @@ def cin_forward(x0: torch.Tensor, weights: Sequence[torch.Tensor], biases: Seque
         W2 = W.reshape(W.shape[0], -1)
         z = torch.einsum("bhd,bmd->bhmd", hidden, x0).reshape(B, hidden.shape[1] * m, D)
         y = torch.einsum("hk,bkd->bhd", W2, z) + b.view(1, -1, 1)     # Conv1d(kernel_size=1) == GEMM + bias
-        y = _activation(activation, y)
+        if relu_masks is not None and activation == "relu":
+            # test hook: use a GIVEN active-set (e.g. the one the fp32/bf16 kernel chose) so that pre-activations on
+            # the ReLU kink do not turn rounding noise into O(1) gradient differences
+            y = y * relu_masks[k].to(y.dtype)
+        else:
+            y = _activation(activation, y)
         H = W2.shape[0]
         if split_half:
             if k != n - 1:
@@ -161,6 +166,23 @@ def cin_forward(x0: torch.Tensor, weights: Sequence[torch.Tensor], biases: Seque
         finals.append(direct)
     maps = torch.cat(finals, dim=1)
     return maps.sum(-1) if pool else maps
+
+
+def cin_preactivations(x0, weights, biases, split_half=True, activation="relu"):
+    """Pre-activation tensors [B, H_k, D] of every CIN layer (test helper: lets parity tests drop samples whose
+    pre-activation sits on the ReLU kink, where fp32 and fp64 legitimately pick different gradient masks)."""
+    B, m, D = x0.shape
+    hidden, pres = x0, []
+    n = len(weights)
+    for k, (W, b) in enumerate(zip(weights, biases)):
+        W2 = W.reshape(W.shape[0], -1)
+        z = torch.einsum("bhd,bmd->bhmd", hidden, x0).reshape(B, hidden.shape[1] * m, D)
+        pre = torch.einsum("hk,bkd->bhd", W2, z) + b.view(1, -1, 1)
+        pres.append(pre)
+        y = _activation(activation, pre)
+        H = W2.shape[0]
+        hidden = y[:, : H // 2] if (split_half and k != n - 1) else y
+    return pres
 
 
 def dnn_forward(x, weights, biases, activation="relu"):

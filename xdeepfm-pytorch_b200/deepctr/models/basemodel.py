@@ -416,6 +416,7 @@ class BaseModel(nn.Module):
     def train_step(self, ids, dense, y, loss_accum, pred_log=None, pred_off=0):
         """One fused training step on device tensors: forward, loss, backward, optimizer (+L2).  No host sync."""
         opt = self.optim
+        opt.prepare()       # flat parameter / gradient views must exist BEFORE backward accumulates into them
         opt.zero_grad()
         for ts in opt.table_sets:
             ts.plan.sparse_grad = True      # backward leaves (unique rows, segment sums) for the fused optimizer
