@@ -135,6 +135,10 @@ int xdfm_rows_opt(const xdfm_opt_cfg* cfg, const float* opt_dev, float* const* w
                   const int32_t* num_segments, int64_t max_segments, float grad_scale, uint32_t* touched_bitmap, int dense_pass,
                   double* reg_out, void* stream);
 
+/* ---- tcgen05 self-test (diagnostic): D[128,N] = A[128,K] * B[N,K]^T, bf16 in / fp32 out, one CTA.
+ * mode 0: A via TMA + shared-memory descriptor (SS); mode 1: A stored to TMEM by the threads (TS, the CIN operand path). */
+int xdfm_tc_selftest_gemm(const void* A, const void* Bm, int N, int K, int mode, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

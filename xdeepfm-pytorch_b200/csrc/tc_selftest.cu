@@ -1,0 +1,139 @@
+// Minimal tcgen05 self-test: one CTA computes D[128, N] = A[128, K] * B[N, K]^T (bf16 in, fp32 out) with
+//   mode 0: A from shared memory (TMA, SWIZZLE_128B, K-major)        -- tcgen05.mma  SS
+//   mode 1: A written into TMEM by the threads (tcgen05.st, packed)  -- tcgen05.mma  TS
+// It exercises exactly the primitives the CIN kernels are built from (TMEM alloc, TMA swizzle vs. UMMA descriptor,
+// A-in-TMEM layout, commit/mbarrier, tcgen05.ld) so that a descriptor/layout mistake shows up in a 40-line kernel.
+#include "tc_common.cuh"
+#include "../../include/xdfm.h"
+#include <cudaTypedefs.h>
+
+using namespace tc;
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+  }
+  return fn;
+}
+
+int xdfm_make_tmap_bf16_sw128(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t row_pitch_bytes,
+                              uint32_t box_rows) {
+  PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode_fn();
+  if (enc == nullptr) {
+    xdfm_set_error("cuTensorMapEncodeTiled entry point not available");
+    return XDFM_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {row_pitch_bytes};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    xdfm_set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu pitch=%llu box_rows=%u", (int)r, (unsigned long long)rows,
+                   (unsigned long long)cols, (unsigned long long)row_pitch_bytes, box_rows);
+    return XDFM_ERR_CUDA;
+  }
+  return XDFM_OK;
+}
+
+__global__ void __launch_bounds__(128) tc_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                          const __nv_bfloat16* __restrict__ A, int N, int K, int mode,
+                                                          float* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_tma, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nchunk = K / 64;
+  uint8_t* sB = smem;                                  // nchunk x [N rows x 128 B]
+  uint8_t* sA = smem + (size_t)nchunk * N * 128;       // nchunk x [128 rows x 128 B]  (mode 0)
+  sA = (uint8_t*)(((uintptr_t)sA + 1023) & ~(uintptr_t)1023);
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) {
+    mbar_init(&bar_tma, 1);
+    mbar_init(&bar_mma, 1);
+    fence_barrier_init();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t acc_col = 0, a_col = 256;
+  if (tid == 0) {
+    uint32_t bytes = (uint32_t)nchunk * N * 128 + (mode == 0 ? (uint32_t)nchunk * 128 * 128 : 0u);
+    mbar_arrive_expect_tx(&bar_tma, bytes);
+    for (int c = 0; c < nchunk; ++c) {
+      tma_load_2d(sB + (size_t)c * N * 128, &tmB, c * 64, 0, &bar_tma);
+      if (mode == 0) tma_load_2d(sA + (size_t)c * 128 * 128, &tmA, c * 64, 0, &bar_tma);
+    }
+  }
+  if (mode == 1) {
+    // thread = row; pack (k, k+1) pairs into 32-bit columns
+    const int row = tid;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      uint32_t r[4];
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(A + (size_t)row * K + k0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r[i] = src[i];
+      tmem_st_x4(tmem_base + lane_base + a_col + k0 / 2, r);
+    }
+    tmem_wait_st();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  if (tid == 0) {
+    mbar_wait(&bar_tma, 0);
+    fence_after_sync();
+    const uint32_t idesc = make_idesc_bf16(128, N);
+    for (int ks = 0; ks < K / 16; ++ks) {
+      int c = ks / 4, o = (ks % 4) * 32;
+      uint64_t bdesc = make_desc_k_sw128(smem_u32(sB + (size_t)c * N * 128) + o);
+      if (mode == 0) {
+        uint64_t adesc = make_desc_k_sw128(smem_u32(sA + (size_t)c * 128 * 128) + o);
+        umma_ss(tmem_base + acc_col, adesc, bdesc, idesc, ks > 0);
+      } else {
+        umma_ts(tmem_base + acc_col, tmem_base + a_col + ks * 8, bdesc, idesc, ks > 0);
+      }
+    }
+    umma_commit(&bar_mma);
+  }
+  mbar_wait(&bar_mma, 0);
+  fence_after_sync();
+  {
+    const int row = tid;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld_x16(tmem_base + lane_base + acc_col + c0, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) out[(size_t)row * N + c0 + i] = __uint_as_float(v[i]);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+  (void)lane;
+}
+
+// A [128, K] bf16 row-major, Bm [N, K] bf16 row-major (both device), out [128, N] fp32; K % 64 == 0, N % 16 == 0, N <= 256, K <= 256
+extern "C" int xdfm_tc_selftest_gemm(const void* A, const void* Bm, int N, int K, int mode, float* out, void* stream) {
+  XDFM_CHECK_ARG(N % 16 == 0 && N >= 16 && N <= 256 && K % 64 == 0 && K >= 64 && K <= 256, "tc_selftest: bad N=%d K=%d", N, K);
+  CUtensorMap tmA, tmB;
+  int rc = xdfm_make_tmap_bf16_sw128(&tmA, A, 128, K, (uint64_t)K * 2, 128);
+  if (rc) return rc;
+  rc = xdfm_make_tmap_bf16_sw128(&tmB, Bm, N, K, (uint64_t)K * 2, N);
+  if (rc) return rc;
+  size_t sm = (size_t)(K / 64) * N * 128 + (size_t)(K / 64) * 128 * 128 + 2048;
+  XDFM_CUDA(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  tc_selftest_kernel<<<1, 128, sm, (cudaStream_t)stream>>>(tmA, tmB, (const __nv_bfloat16*)A, N, K, mode, out);
+  XDFM_LAUNCH_CHECK();
+  return XDFM_OK;
+}

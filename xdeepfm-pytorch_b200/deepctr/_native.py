@@ -48,6 +48,7 @@ _SIGS = {
     "xdfm_head_fwd": (c_int, [_P, _P, _P, c_int, _P, _P, c_int, _P, c_int64, c_int, _P, _P]),
     "xdfm_head_bwd": (c_int, [_P, _P, c_int64, c_int, _P, c_int, _P, c_int, _P, _P, _P, _P]),
     "xdfm_bce_sum": (c_int, [_P, _P, c_int64, c_float, _P, _P, _P, _P]),
+    "xdfm_tc_selftest_gemm": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
     "xdfm_opt_tick": (c_int, [_P, POINTER(OptCfg), _P]),
     "xdfm_flat_opt": (c_int, [POINTER(OptCfg), _P, c_int64, _P, _P, _P, _P, _P, c_float, _P, _P]),
     "xdfm_rows_opt": (c_int, [POINTER(OptCfg), _P, POINTER(_P), POINTER(_P), POINTER(_P), POINTER(c_int64), c_int, c_int, _P, _P, _P,
