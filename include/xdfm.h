@@ -135,6 +135,17 @@ int xdfm_rows_opt(const xdfm_opt_cfg* cfg, const float* opt_dev, float* const* w
                   const int32_t* num_segments, int64_t max_segments, float grad_scale, uint32_t* touched_bitmap, int dense_pass,
                   double* reg_out, void* stream);
 
+/* ---- CIN layer on the tensor cores (bf16 operands, fp32 accumulate; deepctr/layers/interaction.py:218-246).
+ * x0b [B,m,D] bf16; xkb bf16 with (b,i,d) at xkb[b*xk_bstride + i*D + d]; W fp32 [H, Hp*m] + bias [H] as the reference holds
+ * them; wprime = bf16 scratch of xdfm_cin_tc_wprime_elems() elements (permuted/padded copy of W made by the call).
+ * yb [B,H,D] bf16 = act(W.(xk (x) x0) + bias); pooled / maps as in xdfm_cin_fwd_f32 (fp32, from the fp32 accumulators).
+ * Supported: D in {8,16,32,64,128}, Hp <= 128, H <= 256; otherwise returns an error (use the fp32 path). */
+int xdfm_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+int64_t xdfm_cin_tc_wprime_elems(int m, int Hp, int H, int D);
+int xdfm_cin_fwd_tc(const void* x0b, const void* xkb, int64_t xk_bstride, const float* W, const float* bias, void* wprime, int64_t B,
+                    int m, int Hp, int H, int D, int act, void* yb, int direct_begin, float* pooled, float* maps, int fm_total,
+                    int col_off, void* stream);
+
 /* ---- tcgen05 self-test (diagnostic): D[128,N] = A[128,K] * B[N,K]^T, bf16 in / fp32 out, one CTA.
  * mode 0: A via TMA + shared-memory descriptor (SS); mode 1: A stored to TMEM by the threads (TS, the CIN operand path). */
 int xdfm_tc_selftest_gemm(const void* A, const void* Bm, int N, int K, int mode, float* out, void* stream);

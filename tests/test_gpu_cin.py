@@ -36,8 +36,9 @@ def _product_masks(x0, Ws, bs, split_half, act):
     xk, stride, masks = x, m * D, []
     for k, H in enumerate(cfg.layer_size):
         y = torch.empty(B, H, D, device=DEV)
-        N.check(N.lib().xdfm_cin_fwd_f32(N.ptr(x), N.ptr(xk), stride, N.ptr(Ws[k].to(DEV).reshape(H, -1).contiguous()),
-                                         N.ptr(bs[k].to(DEV)), B, m, cfg.Hp[k], H, D, cfg.act, N.ptr(y), cfg.direct_begin[k],
+        Wd, bd = Ws[k].to(DEV).reshape(H, -1).contiguous(), bs[k].to(DEV)     # keep alive across the launch
+        N.check(N.lib().xdfm_cin_fwd_f32(N.ptr(x), N.ptr(xk), stride, N.ptr(Wd), N.ptr(bd), B, m, cfg.Hp[k], H, D, cfg.act,
+                                         N.ptr(y), cfg.direct_begin[k],
                                          N.ptr(out), None, cfg.fm, cfg.col_off[k], N.stream_ptr()))
         masks.append((y > 0).cpu())
         xk, stride = y, H * D
