@@ -61,6 +61,9 @@ TC_CASES = [
     (9, 26, 64, 256, 26),
     (5, 26, 128, 64, 26),
     (40, 7, 16, 48, 24),
+    (2500, 26, 16, 200, 26),      # 313 tiles -> several tiles per persistent CTA (ring / phase wrap-around)
+    (1300, 12, 32, 64, 12),
+    (700, 10, 8, 32, 10),
 ]
 
 

@@ -1,0 +1,48 @@
+"""Micro-benchmark of the tensor-core CIN kernels at BASELINE config shapes (CUDA events, L2 flushed between launches)."""
+import os
+import sys
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "xdeepfm-pytorch_b200"))
+from deepctr import _native as Nv  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def time_layer(B, m, D, H, Hp, Hprev, reps=10):
+    L = Nv.lib()
+    g = torch.Generator().manual_seed(0)
+    x0 = (torch.randn(B, m, D, generator=g) * 0.5).to(torch.bfloat16).to(DEV)
+    xk = x0 if Hp == m else (torch.randn(B, Hprev, D, generator=g) * 0.5).to(torch.bfloat16).to(DEV)
+    K = Hp * m
+    W = (torch.randn(H, K, generator=g) / K ** 0.5).to(DEV)
+    b = torch.zeros(H, device=DEV)
+    wprime = torch.empty(L.xdfm_cin_tc_wprime_elems(m, Hp, H, D), dtype=torch.bfloat16, device=DEV)
+    yb = torch.empty(B, H, D, dtype=torch.bfloat16, device=DEV)
+    pooled = torch.empty(B, H, device=DEV)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    ts = []
+    for r in range(reps + 3):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        Nv.check(L.xdfm_cin_fwd_tc(Nv.ptr(x0), Nv.ptr(xk), xk.shape[1] * D, Nv.ptr(W), Nv.ptr(b), Nv.ptr(wprime), B, m, Hp, H, D, 1,
+                                   Nv.ptr(yb), H // 2, Nv.ptr(pooled), None, H, 0, Nv.stream_ptr()))
+        e1.record()
+        torch.cuda.synchronize()
+        if r >= 3:
+            ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[len(ts) // 2]
+    flops = 2.0 * B * D * H * K
+    print("B=%d m=%d D=%d H=%d Hp=%d: %.3f ms  %.1f TFLOP/s (algorithmic)" % (B, m, D, H, Hp, ms, flops / ms / 1e9), flush=True)
+    return ms
+
+
+if __name__ == "__main__":
+    time_layer(8192, 26, 16, 200, 26, 26)
+    time_layer(8192, 26, 16, 200, 100, 200)
+    time_layer(16384, 26, 16, 256, 26, 26)
+    time_layer(16384, 26, 16, 128, 128, 256)
+    time_layer(8192, 22, 32, 256, 128, 256)

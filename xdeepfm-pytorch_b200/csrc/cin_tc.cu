@@ -72,6 +72,74 @@ __device__ __forceinline__ void tmem_st_regs(uint32_t taddr, const uint32_t* r) 
   }
 }
 
+struct EpiRow {
+  __nv_bfloat16* yb;   // &yb[b, 0, d] or null
+  float* maps;         // &maps[b, col_off - hdb, d] or null (index by h)
+  float* pooled;       // &pooled[b, col_off - hdb] or null (index by h)
+  float* spool;        // per-warp scratch [H_pad] (D > 32)
+  bool valid;
+};
+
+// One 16-column accumulator chunk of one row: bias + activation, bf16 / fp32 stores, and the sum over the sample's D lanes.
+// The lane-sum uses a transposing butterfly: every shuffle level halves the number of live values per lane, so 16 columns
+// cost 8+4+2+1 shuffles instead of 16*log2(LD); afterwards lane l holds the finished sum of column `col_of_lane`.
+template <int LD>   // lanes per sample inside the warp: min(D, 32)
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[16], int c0, int lane, const float* __restrict__ sBias,
+                                               const CinTcParams& p, const EpiRow& r) {
+  float y[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float t = __uint_as_float(v[i]) + sBias[c0 + i];
+    if (p.act == XDFM_ACT_RELU) t = fmaxf(t, 0.f);
+    else if (p.act == XDFM_ACT_SIGMOID) t = 1.f / (1.f + __expf(-t));
+    y[i] = r.valid ? t : 0.f;
+  }
+  const int hmax = p.H - c0;   // columns >= hmax are padding
+  if (r.yb != nullptr) {
+    __nv_bfloat16* yp = r.yb + (int64_t)c0 * p.D;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < hmax) yp[i * p.D] = __float2bfloat16(y[i]);
+  }
+  if (r.maps != nullptr) {
+    float* mp = r.maps + (int64_t)c0 * p.D;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < hmax && c0 + i >= p.hdb) mp[(int64_t)i * p.D] = y[i];
+  }
+  if (p.pooled == nullptr) return;
+  int nv = 16, col = 0;
+#pragma unroll
+  for (int o = LD / 2; o >= 1; o >>= 1) {
+    if (nv > 1) {
+      const bool upper = (lane & o) != 0;
+      const int half = nv / 2;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (i < half) {
+          const float send = upper ? y[i] : y[i + half];
+          const float keep = upper ? y[i + half] : y[i];
+          y[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+      }
+      if (upper) col += half;
+      nv = half;
+    } else {
+      y[0] += __shfl_xor_sync(0xffffffffu, y[0], o);
+    }
+  }
+  // lane now owns columns c0 + col .. c0 + col + nv - 1 (LD=8: two columns, LD=16: one, LD=32: one shared by a lane pair)
+  if (LD == 32 && (lane & 1)) return;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    if (i < nv) {
+      const int h = c0 + col + i;
+      if (p.D > 32) r.spool[h] = y[i];
+      else if (r.pooled != nullptr && h >= p.hdb && h < p.H) r.pooled[h] = y[i];
+    }
+  }
+}
+
 // NI8 = HpP / 8 (channels of X^{k-1} padded to a multiple of 8, HpP <= 128)
 template <int NI8>
 __global__ void __launch_bounds__(TC_THREADS, 1) cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW, CinTcParams p) {
@@ -240,33 +308,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cin_fwd_tc_kernel(const __grid_
     for (int64_t tile = tile0; tile < p.n_tiles; tile += tstep, ++it) {
       const int64_t b = tile * p.TB + bl;
       const bool valid = bl < p.TB && b < p.B;
+      EpiRow r;
+      r.valid = valid;
+      r.yb = (p.yb && valid) ? p.yb + b * (int64_t)p.H * p.D + d : nullptr;
+      r.maps = (p.maps && valid) ? p.maps + (b * p.fm_total + p.col_off - p.hdb) * (int64_t)p.D + d : nullptr;
+      r.pooled = (p.pooled && valid) ? p.pooled + b * p.fm_total + p.col_off - p.hdb : nullptr;
+      r.spool = sPool + ew * p.H_pad;
       mbar_wait(&bars->acc_full, it & 1);
       fence_after_sync();
       for (int c0 = 0; c0 < p.H_pad; c0 += 16) {
         uint32_t v[16];
         tmem_ld_x16(tmem_base + lane_addr + c0, v);
         tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int h = c0 + i;
-          float y = __uint_as_float(v[i]) + sBias[h];
-          if (p.act == XDFM_ACT_RELU) y = fmaxf(y, 0.f);
-          else if (p.act == XDFM_ACT_SIGMOID) y = 1.f / (1.f + __expf(-y));
-          if (!valid) y = 0.f;
-          if (valid && h < p.H) {
-            if (p.yb) p.yb[(b * p.H + h) * (int64_t)p.D + d] = __float2bfloat16(y);
-            if (p.maps && h >= p.hdb) p.maps[(b * p.fm_total + p.col_off + (h - p.hdb)) * (int64_t)p.D + d] = y;
-          }
-          if (p.pooled) {
-            // sum over the D lanes of this sample (D is a power of two: 8..128)
-            float s = y;
-            for (int o = 1; o < min(p.D, 32); o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (p.D <= 32) {
-              if (valid && d == 0 && h >= p.hdb && h < p.H) p.pooled[b * p.fm_total + p.col_off + (h - p.hdb)] = s;
-            } else if (lane == 0) {
-              sPool[ew * p.H_pad + h] = s;       // one partial per warp; combined below
-            }
-          }
+        switch (p.D) {
+          case 8: epilogue_chunk<8>(v, c0, lane, sBias, p, r); break;
+          case 16: epilogue_chunk<16>(v, c0, lane, sBias, p, r); break;
+          default: epilogue_chunk<32>(v, c0, lane, sBias, p, r); break;   // D = 32, 64, 128: full-warp segments
         }
       }
       fence_before_sync();
