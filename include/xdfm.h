@@ -136,14 +136,19 @@ int xdfm_rows_opt(const xdfm_opt_cfg* cfg, const float* opt_dev, float* const* w
                   double* reg_out, void* stream);
 
 /* ---- CIN layer on the tensor cores (bf16 operands, fp32 accumulate; deepctr/layers/interaction.py:218-246).
- * x0b [B,m,D] bf16; xkb bf16 with (b,i,d) at xkb[b*xk_bstride + i*D + d]; W fp32 [H, Hp*m] + bias [H] as the reference holds
- * them; wprime = bf16 scratch of xdfm_cin_tc_wprime_elems() elements (permuted/padded copy of W made by the call).
- * yb [B,H,D] bf16 = act(W.(xk (x) x0) + bias); pooled / maps as in xdfm_cin_fwd_f32 (fp32, from the fp32 accumulators).
- * Supported: D in {8,16,32,64,128}, Hp <= 128, H <= 256; otherwise returns an error (use the fp32 path). */
-int xdfm_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+ * Activations use a ROW layout: one row per (sample, d), channels contiguous:
+ *   x0t [B*D, mP] bf16 (mP = m rounded up to 8, zero padded; produced by xdfm_to_rows_bf16),
+ *   xkt = layer input rows with pitch xk_pitch elements (layer k>0: the previous layer's yt, first Hp channels; layer 0: x0t),
+ *   yt  [B*D, Hs] bf16 = act(W.(xk (x) x0) + bias), Hs = H rounded up to 8 (padding channels are written as zeros).
+ * W fp32 [H, Hp*m] + bias [H] as the reference holds them; wprime = bf16 scratch of xdfm_cin_tc_wprime_elems() elements
+ * (permuted/padded copy of W made by the call).  pooled / maps as in xdfm_cin_fwd_f32 (fp32, from the fp32 accumulators).
+ * Supported: D in {8,16,32,64,128}, Hp <= 128, H <= 256; otherwise returns an error (use the fp32 path).
+ * xdfm_cin_tc_set_cluster(c): thread-block cluster size (1, 2 or 4) used to multicast the weight stream (default 2). */
+int xdfm_to_rows_bf16(const float* x, int64_t B, int C, int D, int CP, void* xt, void* stream);
 int64_t xdfm_cin_tc_wprime_elems(int m, int Hp, int H, int D);
-int xdfm_cin_fwd_tc(const void* x0b, const void* xkb, int64_t xk_bstride, const float* W, const float* bias, void* wprime, int64_t B,
-                    int m, int Hp, int H, int D, int act, void* yb, int direct_begin, float* pooled, float* maps, int fm_total,
+void xdfm_cin_tc_set_cluster(int c);
+int xdfm_cin_fwd_tc(const void* x0t, const void* xkt, int64_t xk_pitch, const float* W, const float* bias, void* wprime, int64_t B,
+                    int m, int Hp, int H, int D, int act, void* yt, int direct_begin, float* pooled, float* maps, int fm_total,
                     int col_off, void* stream);
 
 /* ---- tcgen05 self-test (diagnostic): D[128,N] = A[128,K] * B[N,K]^T, bf16 in / fp32 out, one CTA.

@@ -1,4 +1,4 @@
-"""tcgen05 building-block self-test and the bf16 tensor-core CIN path."""
+"""tcgen05 building-block self-test and the bf16 tensor-core CIN forward kernel (through the C ABI)."""
 import pytest
 import torch
 
@@ -22,25 +22,40 @@ def test_tcgen05_selftest_gemm(mode, N, K):
     assert_close(out, ref, 1e-5, 1e-4, "selftest mode %d" % mode)
 
 
-def _tc_layer(x0b, xkb, xk_stride, W, b, m, Hp, H, D, act, direct_begin, fm, col_off, pool=True):
-    """One CIN layer through the C ABI (bf16 tensor-core path)."""
+def to_rows(x, CP):
+    """[B, C, D] fp32 (device) -> row layout [B*D, CP] bf16 via the library."""
+    from deepctr import _native as Nv
+    B, C, D = x.shape
+    xt = torch.empty((B * D, CP), dtype=torch.bfloat16, device=DEV)
+    Nv.check(Nv.lib().xdfm_to_rows_bf16(Nv.ptr(x), B, C, D, CP, Nv.ptr(xt), Nv.stream_ptr()))
+    return xt
+
+
+def from_rows(yt, B, H, D):
+    return yt.view(B, D, -1)[:, :, :H].permute(0, 2, 1).contiguous()
+
+
+def tc_layer(x0t, xkt, W, b, B, m, Hp, H, D, act, direct_begin, fm, col_off, pool=True):
+    """One CIN layer through the C ABI (bf16 tensor-core path); returns (y [B,H,D] bf16, yt rows, pooled, maps)."""
     from deepctr import _native as Nv
     L = Nv.lib()
-    B = x0b.shape[0]
     n = L.xdfm_cin_tc_wprime_elems(m, Hp, H, D)
     assert n > 0, L.xdfm_last_error()
+    Hs = (H + 7) // 8 * 8
     wprime = torch.empty(n, dtype=torch.bfloat16, device=DEV)
-    yb = torch.full((B, H, D), float("nan"), dtype=torch.bfloat16, device=DEV)
+    yt = torch.full((B * D, Hs), float("nan"), dtype=torch.bfloat16, device=DEV)
     pooled = torch.full((B, fm), float("nan"), device=DEV)
     maps = torch.full((B, fm, D), float("nan"), device=DEV) if not pool else None
-    Nv.check(L.xdfm_cin_fwd_tc(Nv.ptr(x0b), Nv.ptr(xkb), xk_stride, Nv.ptr(W), Nv.ptr(b), Nv.ptr(wprime), B, m, Hp, H, D,
-                               Nv.ACT[act], Nv.ptr(yb), direct_begin, Nv.ptr(pooled), Nv.ptr(maps), fm, col_off, Nv.stream_ptr()))
+    Nv.check(L.xdfm_cin_fwd_tc(Nv.ptr(x0t), Nv.ptr(xkt), xkt.shape[1], Nv.ptr(W), Nv.ptr(b), Nv.ptr(wprime), B, m, Hp, H, D,
+                               Nv.ACT[act], Nv.ptr(yt), direct_begin, Nv.ptr(pooled) if pool else None, Nv.ptr(maps), fm, col_off,
+                               Nv.stream_ptr()))
     torch.cuda.synchronize()
-    return yb, pooled, maps
+    return from_rows(yt, B, H, D), yt, pooled, maps
 
 
-def _emulated_layer(x0b, xkb, W, b, act):
-    """fp64 accumulation over bf16-rounded operands and bf16-rounded products (what the kernel computes)."""
+def emulated_layer(x0b, xkb, W, b, act):
+    """fp64 accumulation over bf16-rounded operands and bf16-rounded products (what the kernel computes).
+    x0b [B,m,D], xkb [B,Hp,D] bf16 (cpu)."""
     Bn, m, D = x0b.shape
     z = (xkb.float()[:, :, None, :] * x0b.float()[:, None, :, :]).to(torch.bfloat16)        # [B, Hp, m, D], k = i*m + j
     z = z.reshape(Bn, -1, D).double()
@@ -63,27 +78,56 @@ TC_CASES = [
     (40, 7, 16, 48, 24),
     (2500, 26, 16, 200, 26),      # 313 tiles -> several tiles per persistent CTA (ring / phase wrap-around)
     (1300, 12, 32, 64, 12),
-    (700, 10, 8, 32, 10),
+    (700, 10, 8, 36, 10),         # H not a multiple of 8
 ]
 
 
+@pytest.mark.parametrize("cluster", [1, 2, 4])
 @pytest.mark.parametrize("case", TC_CASES, ids=[str(c) for c in TC_CASES])
-def test_cin_tc_single_layer_matches_emulation(case):
+def test_cin_tc_single_layer_matches_emulation(case, cluster):
+    from deepctr import _native as Nv
     B, m, D, H, Hp = case
     g = torch.Generator().manual_seed(sum(case))
-    x0 = (torch.randn(B, m, D, generator=g) * 0.5).to(torch.bfloat16)
-    Hprev = max(Hp, 2 * Hp if Hp != m else Hp)          # xk is a channel-slice of a wider previous layer when Hp != m
-    xk_full = x0 if Hp == m else (torch.randn(B, Hprev, D, generator=g) * 0.5).to(torch.bfloat16)
-    xk = xk_full[:, :Hp]
+    x0 = (torch.randn(B, m, D, generator=g) * 0.5)
+    Hprev = Hp if Hp == m else 2 * Hp               # xk is a channel-slice of a wider previous layer when Hp != m
+    xk_full = x0 if Hp == m else (torch.randn(B, Hprev, D, generator=g) * 0.5)
     K = Hp * m
     W = torch.randn(H, K, generator=g) / K ** 0.5
     b = torch.randn(H, generator=g) * 0.1
     hdb = H // 2
     fm = H - hdb + 3
-    x0d, xkd, Wd, bd = x0.to(DEV), xk_full.to(DEV), W.to(DEV), b.to(DEV)
-    yb, pooled, _ = _tc_layer(x0d, xkd, xk_full.shape[1] * D, Wd, bd, m, Hp, H, D, "relu", hdb, fm, 3)
-    ref = _emulated_layer(x0, xk, W, b, "relu")
+    x0t = to_rows(x0.to(DEV), (m + 7) // 8 * 8)
+    xkt = x0t if Hp == m else to_rows(xk_full.to(DEV), (Hprev + 7) // 8 * 8)
+    Wd, bd = W.to(DEV), b.to(DEV)
+    Nv.lib().xdfm_cin_tc_set_cluster(cluster)
+    try:
+        y, yt, pooled, _ = tc_layer(x0t, xkt, Wd, bd, B, m, Hp, H, D, "relu", hdb, fm, 3)
+    finally:
+        Nv.lib().xdfm_cin_tc_set_cluster(2)
+    ref = emulated_layer(x0.to(torch.bfloat16), xk_full[:, :Hp].to(torch.bfloat16), W, b, "relu")
     scale = ref.abs().max().item()
     # bf16 storage of y: 2^-9 relative; accumulation order differences are ~1e-6
-    assert_close(yb.float(), ref, 6e-3, 1e-3 * scale, "y (bf16)")
+    assert_close(y.float(), ref, 6e-3, 1e-3 * scale, "y (bf16)")
     assert_close(pooled[:, 3:], ref[:, hdb:].sum(-1), 2e-4, 2e-4 * scale * D ** 0.5, "pooled (fp32 from accumulators)")
+    Hs = (H + 7) // 8 * 8
+    if Hs > H:
+        assert float(yt[:, H:].float().abs().max()) == 0.0, "padding channels must be zero"
+
+
+def test_cin_tc_maps_output():
+    B, m, D, H, Hp = 21, 6, 16, 32, 6
+    g = torch.Generator().manual_seed(3)
+    x0 = torch.randn(B, m, D, generator=g) * 0.5
+    W = torch.randn(H, Hp * m, generator=g) / (Hp * m) ** 0.5
+    b = torch.randn(H, generator=g) * 0.1
+    x0t = to_rows(x0.to(DEV), 8)
+    Wd, bd = W.to(DEV), b.to(DEV)
+    y, _, _, maps = tc_layer(x0t, x0t, Wd, bd, B, m, Hp, H, D, "relu", 16, 20, 4, pool=False)
+    ref = emulated_layer(x0.to(torch.bfloat16), x0.to(torch.bfloat16), W, b, "relu")
+    assert_close(maps[:, 4:20], ref[:, 16:], 2e-4, 2e-4 * ref.abs().max().item(), "maps (fp32)")
+
+
+def test_cin_tc_rejects_unsupported_dim():
+    from deepctr import _native as Nv
+    assert Nv.lib().xdfm_cin_tc_wprime_elems(26, 26, 200, 10) < 0
+    assert b"unsupported" in Nv.lib().xdfm_last_error()

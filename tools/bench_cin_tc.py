@@ -1,6 +1,7 @@
-"""Micro-benchmark of the tensor-core CIN kernels at BASELINE config shapes (CUDA events, L2 flushed between launches)."""
+"""Micro-benchmark of the tensor-core CIN forward kernel at BASELINE config shapes (CUDA events, L2 flushed between launches)."""
 import os
 import sys
+
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -11,38 +12,45 @@ from deepctr import _native as Nv  # noqa: E402
 DEV = "cuda:0"
 
 
-def time_layer(B, m, D, H, Hp, Hprev, reps=10):
+def r8(x):
+    return (x + 7) // 8 * 8
+
+
+def time_layer(B, m, D, H, Hp, Hprev, cluster, reps=7):
     L = Nv.lib()
+    L.xdfm_cin_tc_set_cluster(cluster)
     g = torch.Generator().manual_seed(0)
-    x0 = (torch.randn(B, m, D, generator=g) * 0.5).to(torch.bfloat16).to(DEV)
-    xk = x0 if Hp == m else (torch.randn(B, Hprev, D, generator=g) * 0.5).to(torch.bfloat16).to(DEV)
+    x0t = (torch.randn(B * D, r8(m), generator=g) * 0.5).to(torch.bfloat16).to(DEV)
+    xkt = x0t if Hp == m else (torch.randn(B * D, r8(Hprev), generator=g) * 0.5).to(torch.bfloat16).to(DEV)
     K = Hp * m
     W = (torch.randn(H, K, generator=g) / K ** 0.5).to(DEV)
     b = torch.zeros(H, device=DEV)
     wprime = torch.empty(L.xdfm_cin_tc_wprime_elems(m, Hp, H, D), dtype=torch.bfloat16, device=DEV)
-    yb = torch.empty(B, H, D, dtype=torch.bfloat16, device=DEV)
+    yt = torch.empty(B * D, r8(H), dtype=torch.bfloat16, device=DEV)
     pooled = torch.empty(B, H, device=DEV)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
     ts = []
-    for r in range(reps + 3):
+    for r in range(reps + 2):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        Nv.check(L.xdfm_cin_fwd_tc(Nv.ptr(x0), Nv.ptr(xk), xk.shape[1] * D, Nv.ptr(W), Nv.ptr(b), Nv.ptr(wprime), B, m, Hp, H, D, 1,
-                                   Nv.ptr(yb), H // 2, Nv.ptr(pooled), None, H, 0, Nv.stream_ptr()))
+        Nv.check(L.xdfm_cin_fwd_tc(Nv.ptr(x0t), Nv.ptr(xkt), xkt.shape[1], Nv.ptr(W), Nv.ptr(b), Nv.ptr(wprime), B, m, Hp, H, D, 1,
+                                   Nv.ptr(yt), H // 2, Nv.ptr(pooled), None, H, 0, Nv.stream_ptr()))
         e1.record()
         torch.cuda.synchronize()
-        if r >= 3:
+        if r >= 2:
             ts.append(e0.elapsed_time(e1))
     ms = sorted(ts)[len(ts) // 2]
     flops = 2.0 * B * D * H * K
-    print("B=%d m=%d D=%d H=%d Hp=%d: %.3f ms  %.1f TFLOP/s (algorithmic)" % (B, m, D, H, Hp, ms, flops / ms / 1e9), flush=True)
+    print("cluster=%d B=%d m=%d D=%d H=%d Hp=%d: %.3f ms  %.1f TFLOP/s (algorithmic)" % (cluster, B, m, D, H, Hp, ms, flops / ms / 1e9),
+          flush=True)
     return ms
 
 
 if __name__ == "__main__":
-    time_layer(8192, 26, 16, 200, 26, 26)
-    time_layer(8192, 26, 16, 200, 100, 200)
-    time_layer(16384, 26, 16, 256, 26, 26)
-    time_layer(16384, 26, 16, 128, 128, 256)
-    time_layer(8192, 22, 32, 256, 128, 256)
+    clusters = [int(c) for c in sys.argv[1:]] or [1, 2, 4]
+    for c in clusters:
+        time_layer(8192, 26, 16, 200, 26, 26, c)
+        time_layer(8192, 26, 16, 200, 100, 200, c)
+        time_layer(16384, 26, 16, 128, 128, 256, c)
+        time_layer(8192, 22, 32, 256, 128, 256, c)

@@ -1,88 +1,96 @@
-// CIN layer on the 5th-gen tensor cores (bf16 operands, fp32 accumulation in TMEM).
+// CIN layer forward on the 5th-gen tensor cores (bf16 operands, fp32 accumulation in TMEM).
 //
 // Replaces (reference, file:line): deepctr/layers/interaction.py:218-246 -- einsum outer product -> Conv1d(k=1) -> ReLU ->
 // split-half -> sum over D.  The reference materialises Z = X^{k-1} (x) X^0 as [B, h*m, D] fp32 in HBM and runs a batched GEMM
 // with N = D.  Here the contraction is ONE implicit GEMM per layer
 //
-//        Y[n, h] = sum_k Z[n, k] * W'[h, k],      n = (sample, d) -> M rows,   h -> N columns,   k = (j, i) -> K
+//        Y[r, h] = sum_k Z[r, k] * W'[h, k],      r = (sample b, d) -> M rows,   h -> N columns,   k = (j, i) -> K
 //
-// whose A operand Z never exists in memory: 128 producer threads (one per row n) hold X^{k-1}[n, :] in registers, multiply by
-// X^0[n, j] and write packed bf16 pairs straight into TENSOR MEMORY with tcgen05.st; tcgen05.mma (kind::f16, M=128,
+// whose A operand Z never exists in memory: 128 producer threads (one per row r) hold X^{k-1}[r, :] in registers, multiply by
+// X^0[r, j] and write packed bf16 pairs straight into TENSOR MEMORY with tcgen05.st; tcgen05.mma (kind::f16, M=128,
 // N=H_pad<=256, K=16) reads A from TMEM and B = W' (bf16, K-major, SWIZZLE_128B) from shared memory where TMA put it; the fp32
 // accumulator [128 x H_pad] lives in TMEM and the epilogue (tcgen05.ld -> bias -> ReLU -> split/pool/store) reads it back.
+//
+// Activations of this path use a ROW layout: one row per (sample, d), channels contiguous --
+//   x0t [B*D, mP]  bf16 (mP = m rounded up to 8, zero padded),   y_k [B*D, Hs_k] bf16 (Hs = H rounded up to 8),
+// so a producer thread reads its operand row with 128-bit loads, the epilogue writes 16 channels with two 128-bit stores, and
+// one accumulator tile = 128 consecutive rows.
 //
 // K ordering is private to this file: k' = j * HpP + i (j over X^0 fields, i over X^{k-1} channels padded to a multiple of 8),
 // W' = cin_prep_w(W) is the reference weight permuted/padded/converted accordingly each step.
 //
+// W' (up to 1.4 MB) is streamed once per tile; to keep that off the L2 -> SM path the CTAs of a thread-block cluster walk the
+// chunk sequence in lock-step and every chunk is fetched ONCE per cluster: CTA c loads rows slice c and TMA-multicasts it into
+// the shared memory of all CTAs of the cluster.
+//
 // TMEM columns (512 allocated): [0, 256) accumulator, [256, 384) and [384, 512) two A stages of up to 256 K-values each.
-// Warp roles (10 warps): 0 = TMA (W' chunks, x tiles), 1 = MMA issuer + TMEM alloc, 2..5 = Z producers, 6..9 = epilogue.
+// Warp roles (14 warps): 0 = TMA (W' chunks, x tiles), 1 = MMA issuer + TMEM alloc, 2..5 = Z producers, 6..13 = epilogue
+// (two warps per TMEM lane quarter, alternating 16-column chunks).
 #include "tc_common.cuh"
 #include "../../include/xdfm.h"
 
 using namespace tc;
 
-#define TC_THREADS 320
+#define TC_THREADS 448
 #define TC_A_COL0 256
 #define TC_A_STAGE_COLS 128
-#define TC_NS_W 4          // W' chunk ring depth
+#define TC_MAX_NS_W 6      // W' chunk ring depth (run-time, limited by shared memory)
 
 struct CinTcParams {
-  const __nv_bfloat16* x0b;   // [B, m, D]
-  const __nv_bfloat16* xkb;   // element (b, i, d) at xkb[b*xk_bstride + i*D + d]
-  int64_t xk_bstride;
+  const __nv_bfloat16* x0t;   // [R, mP]
   const float* bias;          // [H]
-  __nv_bfloat16* yb;          // [B, H, D] post-activation (next layer's input / backward)
+  __nv_bfloat16* yt;          // [R, Hs] post-activation (next layer's input / backward)
   float* pooled;              // [B, fm_total] or null
   float* maps;                // [B, fm_total, D] or null
-  int64_t B;
-  int m, Hp, H, H_pad, D, act, hdb, fm_total, col_off;
-  int TB;                     // samples per tile = 128 / D
+  int64_t R;                  // rows = B * D
+  int m, mP, Hp, H, H_pad, Hs, D, act, hdb, fm_total, col_off;
   int64_t n_tiles;
+  int n_iters;                // tile iterations per CTA (uniform over the grid)
   int G;                      // X^0 fields per A stage
   int n_stages;               // A stages per tile
   int ksteps_total;           // UMMA K-steps per tile
   int n_wchunks;              // 64-wide W' chunks per tile
+  int ns_w;                   // W' ring depth
 };
 
 struct __align__(8) CinTcBars {
-  uint64_t w_full[TC_NS_W], w_empty[TC_NS_W];
+  uint64_t w_full[TC_MAX_NS_W], w_empty[TC_MAX_NS_W];
   uint64_t a_full[2], a_empty[2];
   uint64_t x_full[2], x_empty[2];
   uint64_t acc_full, acc_empty;
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 lo, __nv_bfloat16 hi) {
-  __nv_bfloat162 v = __halves2bfloat162(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-
-template <int NREG>
-__device__ __forceinline__ void tmem_st_regs(uint32_t taddr, const uint32_t* r) {
-  // NREG is a multiple of 4; emit the widest power-of-two stores
-  if constexpr (NREG >= 16) {
-    tmem_st_x16(taddr, r);
-    tmem_st_regs<NREG - 16>(taddr + 16, r + 16);
-  } else if constexpr (NREG >= 8) {
-    tmem_st_x8(taddr, r);
-    tmem_st_regs<NREG - 8>(taddr + 8, r + 8);
-  } else if constexpr (NREG >= 4) {
-    tmem_st_x4(taddr, r);
-    tmem_st_regs<NREG - 4>(taddr + 4, r + 4);
+// z[i2] = xk2[i2] * x0 (packed bf16 pairs) for i2 in [OFF, OFF+REM), written to TMEM columns col+OFF.. in the widest
+// tcgen05.st shapes; only 16 product registers are live at a time.
+template <int OFF, int REM, int NPAIR>
+__device__ __forceinline__ void produce_row(const __nv_bfloat162 (&xk2)[NPAIR], __nv_bfloat162 xv2, uint32_t col) {
+  if constexpr (REM > 0) {
+    constexpr int N = REM >= 16 ? 16 : (REM >= 8 ? 8 : 4);
+    uint32_t z[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      __nv_bfloat162 prod = __hmul2(xk2[OFF + i], xv2);
+      z[i] = *reinterpret_cast<uint32_t*>(&prod);
+    }
+    if constexpr (N == 16) tmem_st_x16(col + OFF, z);
+    else if constexpr (N == 8) tmem_st_x8(col + OFF, z);
+    else tmem_st_x4(col + OFF, z);
+    produce_row<OFF + N, REM - N, NPAIR>(xk2, xv2, col);
   }
 }
 
 struct EpiRow {
-  __nv_bfloat16* yb;   // &yb[b, 0, d] or null
-  float* maps;         // &maps[b, col_off - hdb, d] or null (index by h)
+  __nv_bfloat16* yt;   // &yt[r, 0] or null
+  float* maps;         // &maps[b, col_off - hdb, d] or null (index by h, stride D)
   float* pooled;       // &pooled[b, col_off - hdb] or null (index by h)
-  float* spool;        // per-warp scratch [H_pad] (D > 32)
+  float* spool;        // per-lane-quarter scratch [H_pad] (D > 32)
   bool valid;
 };
 
 // One 16-column accumulator chunk of one row: bias + activation, bf16 / fp32 stores, and the sum over the sample's D lanes.
 // The lane-sum uses a transposing butterfly: every shuffle level halves the number of live values per lane, so 16 columns
-// cost 8+4+2+1 shuffles instead of 16*log2(LD); afterwards lane l holds the finished sum of column `col_of_lane`.
+// cost 8+4+2+1 shuffles instead of 16*log2(LD); afterwards each lane holds the finished sum of its own column(s).
 template <int LD>   // lanes per sample inside the warp: min(D, 32)
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[16], int c0, int lane, const float* __restrict__ sBias,
                                                const CinTcParams& p, const EpiRow& r) {
@@ -92,20 +100,29 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[16], int c0, 
     float t = __uint_as_float(v[i]) + sBias[c0 + i];
     if (p.act == XDFM_ACT_RELU) t = fmaxf(t, 0.f);
     else if (p.act == XDFM_ACT_SIGMOID) t = 1.f / (1.f + __expf(-t));
-    y[i] = r.valid ? t : 0.f;
+    y[i] = (r.valid && c0 + i < p.H) ? t : 0.f;
   }
-  const int hmax = p.H - c0;   // columns >= hmax are padding
-  if (r.yb != nullptr) {
-    __nv_bfloat16* yp = r.yb + (int64_t)c0 * p.D;
+  if (r.yt != nullptr) {
+    // channels [c0, c0+16) of this row; columns H..Hs-1 are written as zeros, columns >= Hs do not exist
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (i < hmax) yp[i * p.D] = __float2bfloat16(y[i]);
+    for (int g8 = 0; g8 < 2; ++g8) {
+      if (c0 + g8 * 8 < p.Hs) {
+        uint4 pk;
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(y[g8 * 8 + 0], y[g8 * 8 + 1]);
+        __nv_bfloat162 t1 = __floats2bfloat162_rn(y[g8 * 8 + 2], y[g8 * 8 + 3]);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(y[g8 * 8 + 4], y[g8 * 8 + 5]);
+        __nv_bfloat162 t3 = __floats2bfloat162_rn(y[g8 * 8 + 6], y[g8 * 8 + 7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+        pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+        *reinterpret_cast<uint4*>(r.yt + c0 + g8 * 8) = pk;
+      }
+    }
   }
   if (r.maps != nullptr) {
     float* mp = r.maps + (int64_t)c0 * p.D;
 #pragma unroll
     for (int i = 0; i < 16; ++i)
-      if (i < hmax && c0 + i >= p.hdb) mp[(int64_t)i * p.D] = y[i];
+      if (c0 + i < p.H && c0 + i >= p.hdb) mp[(int64_t)i * p.D] = y[i];
   }
   if (p.pooled == nullptr) return;
   int nv = 16, col = 0;
@@ -142,68 +159,79 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[16], int c0, 
 
 // NI8 = HpP / 8 (channels of X^{k-1} padded to a multiple of 8, HpP <= 128)
 template <int NI8>
-__global__ void __launch_bounds__(TC_THREADS, 1) cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW, CinTcParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1)
+cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmXk, CinTcParams p) {
   constexpr int HpP = NI8 * 8;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // ---- shared memory carve-up
   const uint32_t w_stage_bytes = (uint32_t)p.H_pad * 128;
-  uint8_t* sW = smem;                                                       // TC_NS_W x [H_pad x 128 B], 1024-aligned
-  const uint32_t x0_bytes = (uint32_t)p.TB * p.m * p.D * 2;
-  const uint32_t xk_row_bytes = (uint32_t)p.Hp * p.D * 2;                   // one sample
-  const uint32_t xk_bytes = (uint32_t)p.TB * xk_row_bytes;
-  uint8_t* sX0 = sW + (size_t)TC_NS_W * w_stage_bytes;                      // 2 x [TB][m][D] bf16
-  uint8_t* sXk = sX0 + 2 * (size_t)((x0_bytes + 127) & ~127u);              // 2 x [TB][Hp][D] bf16
-  uint8_t* sEnd = sXk + 2 * (size_t)((xk_bytes + 127) & ~127u);
-  float* sBias = reinterpret_cast<float*>(sEnd);                            // [H_pad]
-  float* sPool = sBias + p.H_pad;                                           // [4][H_pad] cross-warp pooling scratch (D > 32)
+  uint8_t* sW = smem;                                                       // ns_w x [H_pad x 128 B], 1024-aligned
+  const uint32_t x0_tile = (uint32_t)128 * p.mP * 2;                        // [128][mP] bf16
+  const uint32_t xk_tile = (uint32_t)128 * HpP * 2;                         // [128][HpP] bf16
+  uint8_t* sX0 = sW + (size_t)p.ns_w * w_stage_bytes;                       // 2 tiles
+  uint8_t* sXk = sX0 + 2 * (size_t)x0_tile;                                 // 2 tiles
+  float* sBias = reinterpret_cast<float*>(sXk + 2 * (size_t)xk_tile);       // [H_pad]
+  float* sPool = sBias + p.H_pad;                                           // [4][H_pad] pooling scratch (D > 32)
   CinTcBars* bars = reinterpret_cast<CinTcBars*>(sPool + 4 * p.H_pad);
-  const uint32_t x0_stride = (x0_bytes + 127) & ~127u, xk_stride = (xk_bytes + 127) & ~127u;
+
+  const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
+  const uint16_t cmask = (uint16_t)((1u << csize) - 1);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TC_NS_W; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
+    for (int i = 0; i < TC_MAX_NS_W; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], csize); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->a_full[i], 128); mbar_init(&bars->a_empty[i], 1);
       mbar_init(&bars->x_full[i], 1);   mbar_init(&bars->x_empty[i], 128);
     }
     mbar_init(&bars->acc_full, 1);
-    mbar_init(&bars->acc_empty, 128);
+    mbar_init(&bars->acc_empty, 256);
     fence_barrier_init();
   }
   for (int h = threadIdx.x; h < p.H_pad; h += TC_THREADS) sBias[h] = h < p.H ? p.bias[h] : 0.f;
   if (warp == 1) tmem_alloc(&bars->tmem_base, 512);
   fence_before_sync();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();            // remote barriers must be initialised before any multicast / remote arrive
   fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
 
-  const int64_t tile0 = blockIdx.x, tstep = gridDim.x;
+  // every CTA runs n_iters iterations so that the CTAs of a cluster stay in lock-step on the W' chunk stream;
+  // iterations whose tile index is out of range only keep the W' ring moving.
+  auto tile_of = [&](int it) -> int64_t { return (int64_t)it * gridDim.x + blockIdx.x; };
 
   if (warp == 0) {
     // =============================== TMA producer: x tiles (one tile ahead) and the W' chunk stream ===============================
     if (lane == 0) {
       prefetch_tmap(&tmW);
-      auto load_x = [&](int64_t tile, int it) {
-        const int buf = it & 1;
-        if (it >= 2) mbar_wait(&bars->x_empty[buf], ((it >> 1) - 1) & 1);
-        const int64_t b0 = tile * p.TB;
-        const int nb = (int)min((int64_t)p.TB, p.B - b0);
-        mbar_arrive_expect_tx(&bars->x_full[buf], (uint32_t)nb * (uint32_t)(p.m * p.D * 2) + (uint32_t)nb * xk_row_bytes);
-        bulk_load_1d(sX0 + (size_t)buf * x0_stride, p.x0b + b0 * p.m * p.D, (uint32_t)nb * (uint32_t)(p.m * p.D * 2), &bars->x_full[buf]);
-        for (int s = 0; s < nb; ++s)
-          bulk_load_1d(sXk + (size_t)buf * xk_stride + (size_t)s * xk_row_bytes, p.xkb + (b0 + s) * p.xk_bstride, xk_row_bytes,
-                       &bars->x_full[buf]);
+      prefetch_tmap(&tmXk);
+      // W' rows [wr0, wr1) are this CTA's multicast slice (the host picks a cluster size that divides H_pad/8)
+      const int slice = p.H_pad / (int)csize;
+      const int wr0 = (int)crank * slice, wr1 = wr0 + slice;
+      int xit = 0;                               // number of x tiles loaded so far
+      auto load_x = [&](int64_t tile) {
+        const int buf = xit & 1;
+        if (xit >= 2) mbar_wait(&bars->x_empty[buf], ((xit >> 1) - 1) & 1);
+        const int64_t r0 = tile * 128;
+        const uint32_t nrows = (uint32_t)min((int64_t)128, p.R - r0);
+        mbar_arrive_expect_tx(&bars->x_full[buf], nrows * (uint32_t)(p.mP * 2) + xk_tile);
+        bulk_load_1d(sX0 + (size_t)buf * x0_tile, p.x0t + r0 * p.mP, nrows * (uint32_t)(p.mP * 2), &bars->x_full[buf]);
+        tma_load_2d(sXk + (size_t)buf * xk_tile, &tmXk, 0, (int)r0, &bars->x_full[buf]);   // OOB rows are zero-filled
+        ++xit;
       };
-      int it = 0;
       uint32_t wc = 0;  // global W' chunk counter (ring position)
-      if (tile0 < p.n_tiles) load_x(tile0, 0);
-      for (int64_t tile = tile0; tile < p.n_tiles; tile += tstep, ++it) {
-        if (tile + tstep < p.n_tiles) load_x(tile + tstep, it + 1);
+      if (tile_of(0) < p.n_tiles) load_x(tile_of(0));
+      for (int it = 0; it < p.n_iters; ++it) {
+        if (it + 1 < p.n_iters && tile_of(it + 1) < p.n_tiles) load_x(tile_of(it + 1));
         for (int c = 0; c < p.n_wchunks; ++c, ++wc) {
-          const int ws = wc % TC_NS_W;
-          if (wc >= TC_NS_W) mbar_wait(&bars->w_empty[ws], ((wc / TC_NS_W) - 1) & 1);
+          const int ws = wc % p.ns_w;
+          if (wc >= (uint32_t)p.ns_w) mbar_wait(&bars->w_empty[ws], ((wc / p.ns_w) - 1) & 1);
           mbar_arrive_expect_tx(&bars->w_full[ws], w_stage_bytes);
-          tma_load_2d(sW + (size_t)ws * w_stage_bytes, &tmW, c * 64, 0, &bars->w_full[ws]);
+          if (wr1 > wr0) {
+            uint8_t* dst = sW + (size_t)ws * w_stage_bytes + (size_t)wr0 * 128;
+            if (csize > 1) tma_load_2d_mcast(dst, &tmW, c * 64, wr0, &bars->w_full[ws], cmask);
+            else tma_load_2d(dst, &tmW, c * 64, wr0, &bars->w_full[ws]);
+          }
         }
       }
     }
@@ -212,59 +240,73 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cin_fwd_tc_kernel(const __grid_
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, p.H_pad);
       uint32_t wc = 0, sc = 0;  // global W' chunk / A stage counters
-      int it = 0;
-      for (int64_t tile = tile0; tile < p.n_tiles; tile += tstep, ++it) {
-        if (it > 0) {
-          mbar_wait(&bars->acc_empty, (it - 1) & 1);
+      int at = 0;               // active tiles so far
+      for (int it = 0; it < p.n_iters; ++it) {
+        const bool active = tile_of(it) < p.n_tiles;
+        if (active && at > 0) {
+          mbar_wait(&bars->acc_empty, (at - 1) & 1);
           fence_after_sync();
         }
         int ks = 0;  // K-step within the tile
-        for (int s = 0; s < p.n_stages; ++s, ++sc) {
+        for (int s = 0; s < p.n_stages; ++s) {
           const int sb = sc & 1;
-          mbar_wait(&bars->a_full[sb], (sc >> 1) & 1);
-          fence_after_sync();
+          if (active) {
+            mbar_wait(&bars->a_full[sb], (sc >> 1) & 1);
+            fence_after_sync();
+          }
           const int nj = min(p.G, p.m - s * p.G);
           const int nks = (nj * HpP + 15) / 16;
           const uint32_t a_col = TC_A_COL0 + sb * TC_A_STAGE_COLS;
           for (int t = 0; t < nks; ++t, ++ks) {
-            const int ws = wc % TC_NS_W;
+            const int ws = wc % p.ns_w;
             if ((ks & 3) == 0) {
-              mbar_wait(&bars->w_full[ws], (wc / TC_NS_W) & 1);
+              mbar_wait(&bars->w_full[ws], (wc / p.ns_w) & 1);
               fence_after_sync();
             }
-            const uint64_t bdesc = make_desc_k_sw128(smem_u32(sW + (size_t)ws * w_stage_bytes) + (ks & 3) * 32);
-            umma_ts(tmem_base, tmem_base + a_col + t * 8, bdesc, idesc, ks > 0);
+            if (active) {
+              const uint64_t bdesc = make_desc_k_sw128(smem_u32(sW + (size_t)ws * w_stage_bytes) + (ks & 3) * 32);
+              umma_ts(tmem_base, tmem_base + a_col + t * 8, bdesc, idesc, ks > 0);
+            }
             if ((ks & 3) == 3 || ks == p.ksteps_total - 1) {
-              umma_commit(&bars->w_empty[ws]);   // W' chunk consumed
+              // W' chunk consumed by this CTA: tell every CTA of the cluster (each may overwrite this slot by multicast)
+              if (csize > 1) umma_commit_mcast(&bars->w_empty[ws], cmask);
+              else umma_commit(&bars->w_empty[ws]);
               ++wc;
             }
           }
-          umma_commit(&bars->a_empty[sb]);       // A stage consumed
+          if (active) {
+            umma_commit(&bars->a_empty[sb]);     // A stage consumed
+            ++sc;
+          }
         }
-        umma_commit(&bars->acc_full);            // accumulator complete
+        if (active) {
+          umma_commit(&bars->acc_full);          // accumulator complete
+          ++at;
+        }
       }
     }
   } else if (warp < 6) {
-    // =============================== Z producers: thread <-> accumulator row n = (sample bl, d) ===============================
+    // =============================== Z producers: thread <-> accumulator row ===============================
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
-    const int n = q * 32 + lane;
-    const int bl = n / p.D, d = n - bl * p.D;
+    const int rl = q * 32 + lane;                // row within the tile
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     uint32_t sc = 0;
-    int it = 0;
-    for (int64_t tile = tile0; tile < p.n_tiles; tile += tstep, ++it) {
-      const int buf = it & 1;
-      mbar_wait(&bars->x_full[buf], (it >> 1) & 1);
-      const __nv_bfloat16* x0s = reinterpret_cast<const __nv_bfloat16*>(sX0 + (size_t)buf * x0_stride) + (size_t)bl * p.m * p.D + d;
-      const __nv_bfloat16* xks = reinterpret_cast<const __nv_bfloat16*>(sXk + (size_t)buf * xk_stride) + (size_t)bl * p.Hp * p.D + d;
-      // X^{k-1}[n, 0..HpP) as packed bf16 pairs (zero padded)
+    int at = 0;
+    for (int it = 0; it < p.n_iters; ++it) {
+      if (tile_of(it) >= p.n_tiles) continue;
+      const int buf = at & 1;
+      mbar_wait(&bars->x_full[buf], (at >> 1) & 1);
+      const __nv_bfloat16* x0row = reinterpret_cast<const __nv_bfloat16*>(sX0 + (size_t)buf * x0_tile) + (size_t)rl * p.mP;
+      const uint4* xkrow = reinterpret_cast<const uint4*>(sXk + (size_t)buf * xk_tile + (size_t)rl * HpP * 2);
+      // X^{k-1}[r, 0..HpP) as packed bf16 pairs: channels >= Hp are other data / padding and meet zero columns of W'
       __nv_bfloat162 xk2[HpP / 2];
 #pragma unroll
-      for (int i2 = 0; i2 < HpP / 2; ++i2) {
-        const int i = 2 * i2;
-        __nv_bfloat16 lo = (i < p.Hp && bl < p.TB) ? xks[(size_t)i * p.D] : __float2bfloat16(0.f);
-        __nv_bfloat16 hi = (i + 1 < p.Hp && bl < p.TB) ? xks[(size_t)(i + 1) * p.D] : __float2bfloat16(0.f);
-        xk2[i2] = __halves2bfloat162(lo, hi);
+      for (int v8 = 0; v8 < NI8; ++v8) {
+        const uint4 t = xkrow[v8];
+        xk2[v8 * 4 + 0] = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
+        xk2[v8 * 4 + 1] = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+        xk2[v8 * 4 + 2] = *reinterpret_cast<const __nv_bfloat162*>(&t.z);
+        xk2[v8 * 4 + 3] = *reinterpret_cast<const __nv_bfloat162*>(&t.w);
       }
       for (int s = 0; s < p.n_stages; ++s, ++sc) {
         const int sb = sc & 1;
@@ -275,16 +317,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cin_fwd_tc_kernel(const __grid_
         const int nj = min(p.G, p.m - s * p.G);
         uint32_t col = tmem_base + lane_addr + TC_A_COL0 + sb * TC_A_STAGE_COLS;
         for (int jj = 0; jj < nj; ++jj) {
-          const int j = s * p.G + jj;
-          const __nv_bfloat16 xv = (bl < p.TB) ? x0s[(size_t)j * p.D] : __float2bfloat16(0.f);
-          const __nv_bfloat162 xv2 = __halves2bfloat162(xv, xv);
-          uint32_t z[HpP / 2];
-#pragma unroll
-          for (int i2 = 0; i2 < HpP / 2; ++i2) {
-            __nv_bfloat162 prod = __hmul2(xk2[i2], xv2);
-            z[i2] = *reinterpret_cast<uint32_t*>(&prod);
-          }
-          tmem_st_regs<HpP / 2>(col, z);
+          const __nv_bfloat16 xv = x0row[s * p.G + jj];
+          produce_row<0, HpP / 2, HpP / 2>(xk2, __halves2bfloat162(xv, xv), col);
           col += HpP / 2;
         }
         if ((nj * HpP) & 15) {   // odd tail: pad the last K-step of the stage with zeros
@@ -296,57 +330,70 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cin_fwd_tc_kernel(const __grid_
         mbar_arrive(&bars->a_full[sb]);
       }
       mbar_arrive(&bars->x_empty[buf]);
+      ++at;
     }
   } else {
     // =============================== epilogue: TMEM -> bias -> activation -> y / pooled / maps ===============================
     const int q = warp & 3;
-    const int n = q * 32 + lane;
-    const int bl = n / p.D, d = n - bl * p.D;
+    const int rl = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const int ew = warp - 6;                     // 0..3 (epilogue warp index, for the cross-warp pooling scratch)
-    int it = 0;
-    for (int64_t tile = tile0; tile < p.n_tiles; tile += tstep, ++it) {
-      const int64_t b = tile * p.TB + bl;
-      const bool valid = bl < p.TB && b < p.B;
+    const int half = (warp - 6) >> 2;            // which of the two warps of this lane quarter: chunks c0 = 16*half, +32, ...
+    int at = 0;
+    for (int it = 0; it < p.n_iters; ++it) {
+      const int64_t tile = tile_of(it);
+      if (tile >= p.n_tiles) continue;
+      const int64_t row = tile * 128 + rl;
+      const int64_t b = row / p.D;
+      const int d = (int)(row - b * p.D);
       EpiRow r;
-      r.valid = valid;
-      r.yb = (p.yb && valid) ? p.yb + b * (int64_t)p.H * p.D + d : nullptr;
-      r.maps = (p.maps && valid) ? p.maps + (b * p.fm_total + p.col_off - p.hdb) * (int64_t)p.D + d : nullptr;
-      r.pooled = (p.pooled && valid) ? p.pooled + b * p.fm_total + p.col_off - p.hdb : nullptr;
-      r.spool = sPool + ew * p.H_pad;
-      mbar_wait(&bars->acc_full, it & 1);
+      r.valid = row < p.R;
+      r.yt = (p.yt && r.valid) ? p.yt + row * p.Hs : nullptr;
+      r.maps = (p.maps && r.valid) ? p.maps + (b * p.fm_total + p.col_off - p.hdb) * (int64_t)p.D + d : nullptr;
+      r.pooled = (p.pooled && r.valid) ? p.pooled + b * p.fm_total + p.col_off - p.hdb : nullptr;
+      r.spool = sPool + q * p.H_pad;
+      mbar_wait(&bars->acc_full, at & 1);
       fence_after_sync();
-      for (int c0 = 0; c0 < p.H_pad; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(tmem_base + lane_addr + c0, v);
+      // software pipeline: the tcgen05.ld of the next chunk is in flight while the current one is processed
+      uint32_t va[16], vb[16];
+      int c0 = half * 16;
+      if (c0 < p.H_pad) tmem_ld_x16(tmem_base + lane_addr + c0, va);
+      for (; c0 < p.H_pad; c0 += 64) {
         tmem_wait_ld();
-        switch (p.D) {
-          case 8: epilogue_chunk<8>(v, c0, lane, sBias, p, r); break;
-          case 16: epilogue_chunk<16>(v, c0, lane, sBias, p, r); break;
-          default: epilogue_chunk<32>(v, c0, lane, sBias, p, r); break;   // D = 32, 64, 128: full-warp segments
+        if (c0 + 32 < p.H_pad) tmem_ld_x16(tmem_base + lane_addr + c0 + 32, vb);
+        if (p.D == 8) epilogue_chunk<8>(va, c0, lane, sBias, p, r);
+        else if (p.D == 16) epilogue_chunk<16>(va, c0, lane, sBias, p, r);
+        else epilogue_chunk<32>(va, c0, lane, sBias, p, r);            // D = 32, 64, 128: full-warp segments
+        if (c0 + 32 < p.H_pad) {
+          tmem_wait_ld();
+          if (c0 + 64 < p.H_pad) tmem_ld_x16(tmem_base + lane_addr + c0 + 64, va);
+          if (p.D == 8) epilogue_chunk<8>(vb, c0 + 32, lane, sBias, p, r);
+          else if (p.D == 16) epilogue_chunk<16>(vb, c0 + 32, lane, sBias, p, r);
+          else epilogue_chunk<32>(vb, c0 + 32, lane, sBias, p, r);
         }
       }
       fence_before_sync();
       mbar_arrive(&bars->acc_empty);             // accumulator drained: the next tile's MMAs may start
       if (p.pooled && p.D > 32) {
-        // D = 64: warps (0,1) and (2,3) hold one sample each; D = 128: all four warps hold one sample
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int wps = p.D / 32;                // warps per sample
-        for (int e = threadIdx.x - 6 * 32; e < (4 / wps) * p.H_pad; e += 128) {
+        // D = 64: lane quarters (0,1) and (2,3) hold one sample each; D = 128: all four quarters hold one sample
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int qps = p.D / 32;                // lane quarters per sample
+        for (int e = threadIdx.x - 6 * 32; e < (4 / qps) * p.H_pad; e += 256) {
           const int sidx = e / p.H_pad, h = e - sidx * p.H_pad;
-          const int64_t bb = tile * p.TB + sidx;
-          if (bb < p.B && h >= p.hdb && h < p.H) {
+          const int64_t bb = (tile * 128) / p.D + sidx;
+          if (bb * p.D < p.R && h >= p.hdb && h < p.H) {
             float s = 0.f;
-            for (int w2 = 0; w2 < wps; ++w2) s += sPool[(((sidx * wps + w2) + 2) & 3) * p.H_pad + h];
+            for (int w2 = 0; w2 < qps; ++w2) s += sPool[(sidx * qps + w2) * p.H_pad + h];
             p.pooled[bb * p.fm_total + p.col_off + (h - p.hdb)] = s;
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
+      ++at;
     }
   }
   fence_before_sync();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();            // no CTA may exit while a peer can still multicast into it / arrive on its barriers
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -365,15 +412,24 @@ __global__ void cin_prep_w_kernel(const float* __restrict__ W, int H, int Hp, in
   }
 }
 
-__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    dst[i] = __float2bfloat16(src[i]);
+// x [B, C, D] fp32 -> xt [B*D, CP] bf16 (row layout, channels contiguous, zero padded to CP)
+__global__ void to_rows_bf16_kernel(const float* __restrict__ x, int64_t B, int C, int D, int CP, __nv_bfloat16* __restrict__ xt) {
+  int64_t total = B * (int64_t)D * CP;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(e % CP);
+    int64_t r = e / CP;
+    int d = (int)(r % D);
+    int64_t b = r / D;
+    xt[e] = __float2bfloat16(c < C ? x[(b * C + c) * (int64_t)D + d] : 0.f);
+  }
 }
 
-extern "C" int xdfm_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
-  if (n == 0) return XDFM_OK;
-  int blocks = (int)std::min<int64_t>((int64_t)xdfm_num_sms() * 8, ceil_div64(n, 256));
-  f32_to_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+extern "C" int xdfm_to_rows_bf16(const float* x, int64_t B, int C, int D, int CP, void* xt, void* stream) {
+  XDFM_CHECK_ARG(CP >= C && CP % 8 == 0, "to_rows_bf16: CP=%d must be a multiple of 8 and >= C=%d", CP, C);
+  int64_t total = B * (int64_t)D * CP;
+  if (total == 0) return XDFM_OK;
+  int blocks = (int)std::min<int64_t>((int64_t)xdfm_num_sms() * 8, ceil_div64(total, 256));
+  to_rows_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, B, C, D, CP, (__nv_bfloat16*)xt);
   XDFM_LAUNCH_CHECK();
   return XDFM_OK;
 }
@@ -381,7 +437,7 @@ extern "C" int xdfm_f32_to_bf16(const float* src, void* dst, int64_t n, void* st
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 struct CinTcGeom {
-  int HpP, H_pad, KP, G, n_stages, ksteps_total, n_wchunks, TB;
+  int HpP, H_pad, Hs, mP, KP, G, n_stages, ksteps_total, n_wchunks, ns_w;
   size_t smem;
 };
 
@@ -396,6 +452,8 @@ static int cin_tc_geom(int m, int Hp, int H, int D, CinTcGeom* g) {
   }
   g->HpP = round_up(Hp, 8);
   g->H_pad = round_up(H, 16);
+  g->Hs = round_up(H, 8);
+  g->mP = round_up(m, 8);
   g->G = 256 / g->HpP;
   if ((g->HpP % 16) != 0) g->G -= (g->G & 1);
   if (g->G < 1) g->G = 1;
@@ -408,14 +466,16 @@ static int cin_tc_geom(int m, int Hp, int H, int D, CinTcGeom* g) {
   g->ksteps_total = ks;
   g->n_wchunks = (ks + 3) / 4;
   g->KP = g->n_wchunks * 64;
-  g->TB = 128 / D;
-  size_t x0 = ((size_t)g->TB * m * D * 2 + 127) & ~(size_t)127;
-  size_t xk = ((size_t)g->TB * Hp * D * 2 + 127) & ~(size_t)127;
-  g->smem = (size_t)TC_NS_W * g->H_pad * 128 + 2 * x0 + 2 * xk + (size_t)5 * g->H_pad * 4 + sizeof(CinTcBars) + 1024;
-  if (g->smem > 227 * 1024) {
-    xdfm_set_error("cin_tc: shared memory %zu exceeds 227 KB (m=%d Hp=%d H=%d D=%d)", g->smem, m, Hp, H, D);
+  size_t fixed = 2 * (size_t)128 * g->mP * 2 + 2 * (size_t)128 * g->HpP * 2 + (size_t)5 * g->H_pad * 4 + sizeof(CinTcBars) + 256;
+  size_t stage = (size_t)g->H_pad * 128;
+  int ns = (int)((227 * 1024 - fixed) / stage);
+  ns = std::min(ns, TC_MAX_NS_W);
+  if (ns < 2) {
+    xdfm_set_error("cin_tc: shared memory too small for m=%d Hp=%d H=%d D=%d", m, Hp, H, D);
     return XDFM_ERR_UNSUPPORTED;
   }
+  g->ns_w = ns;
+  g->smem = fixed + (size_t)ns * stage;
   return XDFM_OK;
 }
 
@@ -425,44 +485,71 @@ extern "C" int64_t xdfm_cin_tc_wprime_elems(int m, int Hp, int H, int D) {
   return (int64_t)g.H_pad * g.KP;
 }
 
+static int g_cin_tc_cluster = 2;
+extern "C" void xdfm_cin_tc_set_cluster(int c) { g_cin_tc_cluster = (c == 1 || c == 2 || c == 4) ? c : 2; }
+
 template <int NI8>
-static int launch_cin_fwd_tc(const CUtensorMap& tm, const CinTcParams& p, size_t smem, int blocks, cudaStream_t st) {
+static int launch_cin_fwd_tc(const CUtensorMap& tmW, const CUtensorMap& tmXk, const CinTcParams& p, size_t smem, int blocks, int cluster,
+                             cudaStream_t st) {
   XDFM_CUDA(cudaFuncSetAttribute(cin_fwd_tc_kernel<NI8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cin_fwd_tc_kernel<NI8><<<blocks, TC_THREADS, smem, st>>>(tm, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  XDFM_CUDA(cudaLaunchKernelEx(&cfg, cin_fwd_tc_kernel<NI8>, tmW, tmXk, p));
   XDFM_LAUNCH_CHECK();
   return XDFM_OK;
 }
 
-// x0b [B,m,D] bf16; xkb bf16 (b,i,d) at xkb[b*xk_bstride + i*D + d]; W fp32 [H, Hp*m]; wprime = scratch bf16 [xdfm_cin_tc_wprime_elems]
-// yb [B,H,D] bf16 out; pooled / maps as in xdfm_cin_fwd_f32.
-extern "C" int xdfm_cin_fwd_tc(const void* x0b, const void* xkb, int64_t xk_bstride, const float* W, const float* bias, void* wprime,
-                               int64_t B, int m, int Hp, int H, int D, int act, void* yb, int direct_begin, float* pooled, float* maps,
+// Row-layout operands: x0t [B*D, mP] bf16 (mP = m rounded up to 8); xkt = layer input rows with pitch xk_pitch (elements), the
+// layer uses its first Hp channels; W fp32 [H, Hp*m], bias [H]; wprime = bf16 scratch [xdfm_cin_tc_wprime_elems].
+// yt [B*D, Hs] bf16 out (Hs = H rounded up to 8); pooled / maps as in xdfm_cin_fwd_f32.
+extern "C" int xdfm_cin_fwd_tc(const void* x0t, const void* xkt, int64_t xk_pitch, const float* W, const float* bias, void* wprime,
+                               int64_t B, int m, int Hp, int H, int D, int act, void* yt, int direct_begin, float* pooled, float* maps,
                                int fm_total, int col_off, void* stream) {
   CinTcGeom g;
   int rc = cin_tc_geom(m, Hp, H, D, &g);
   if (rc) return rc;
   if (B == 0) return XDFM_OK;
-  XDFM_CHECK_ARG(((uintptr_t)x0b % 16 == 0) && ((uintptr_t)xkb % 16 == 0) && (xk_bstride * 2) % 16 == 0 && (Hp * D * 2) % 16 == 0,
-                 "cin_fwd_tc: x tiles must be 16-byte aligned (Hp*D*2=%d)", Hp * D * 2);
+  XDFM_CHECK_ARG(((uintptr_t)x0t % 16 == 0) && ((uintptr_t)xkt % 16 == 0) && ((uintptr_t)yt % 16 == 0) && xk_pitch % 8 == 0 &&
+                     xk_pitch >= g.HpP,
+                 "cin_fwd_tc: operands must be 16-byte aligned, xk_pitch (%lld) a multiple of 8 and >= %d", (long long)xk_pitch, g.HpP);
   cudaStream_t st = (cudaStream_t)stream;
   {
     int64_t total = (int64_t)g.H_pad * g.KP;
     int blocks = (int)std::min<int64_t>((int64_t)xdfm_num_sms() * 4, ceil_div64(total, 256));
-    // the K order inside a stage is contiguous in k' = j*HpP + i, so the padded column index equals k'
     cin_prep_w_kernel<<<blocks, 256, 0, st>>>(W, H, Hp, m, g.HpP, g.H_pad, g.KP, (__nv_bfloat16*)wprime);
     XDFM_LAUNCH_CHECK();
   }
-  CUtensorMap tm;
-  rc = xdfm_make_tmap_bf16_sw128(&tm, wprime, (uint64_t)g.H_pad, (uint64_t)g.KP, (uint64_t)g.KP * 2, (uint32_t)g.H_pad);
+  const int64_t R = B * (int64_t)D;
+  CUtensorMap tmW, tmXk;
+  int cluster = g_cin_tc_cluster;
+  while (cluster > 1 && ((g.H_pad / 8) % cluster) != 0) cluster >>= 1;
+  // one TMA box = one CTA's multicast slice of a 64-wide W' chunk
+  rc = xdfm_make_tmap_bf16(&tmW, wprime, (uint64_t)g.H_pad, (uint64_t)g.KP, (uint64_t)g.KP * 2, (uint32_t)(g.H_pad / cluster), 64, 1);
+  if (rc) return rc;
+  rc = xdfm_make_tmap_bf16(&tmXk, xkt, (uint64_t)R, (uint64_t)xk_pitch, (uint64_t)xk_pitch * 2, 128, (uint32_t)g.HpP, 0);
   if (rc) return rc;
   CinTcParams p;
-  p.x0b = (const __nv_bfloat16*)x0b; p.xkb = (const __nv_bfloat16*)xkb; p.xk_bstride = xk_bstride; p.bias = bias;
-  p.yb = (__nv_bfloat16*)yb; p.pooled = pooled; p.maps = maps; p.B = B;
-  p.m = m; p.Hp = Hp; p.H = H; p.H_pad = g.H_pad; p.D = D; p.act = act; p.hdb = direct_begin; p.fm_total = fm_total; p.col_off = col_off;
-  p.TB = g.TB; p.n_tiles = ceil_div64(B, g.TB); p.G = g.G; p.n_stages = g.n_stages; p.ksteps_total = g.ksteps_total; p.n_wchunks = g.n_wchunks;
-  int blocks = (int)std::min<int64_t>(p.n_tiles, xdfm_num_sms());
+  p.x0t = (const __nv_bfloat16*)x0t; p.bias = bias; p.yt = (__nv_bfloat16*)yt; p.pooled = pooled; p.maps = maps; p.R = R;
+  p.m = m; p.mP = g.mP; p.Hp = Hp; p.H = H; p.H_pad = g.H_pad; p.Hs = g.Hs; p.D = D; p.act = act; p.hdb = direct_begin;
+  p.fm_total = fm_total; p.col_off = col_off;
+  p.n_tiles = ceil_div64(R, 128); p.G = g.G; p.n_stages = g.n_stages; p.ksteps_total = g.ksteps_total; p.n_wchunks = g.n_wchunks;
+  p.ns_w = g.ns_w;
+  int sms = xdfm_num_sms();
+  int blocks = (int)std::min<int64_t>(ceil_div64(p.n_tiles, cluster) * cluster, (int64_t)(sms / cluster) * cluster);
+  blocks = std::max(blocks, cluster);
+  p.n_iters = (int)ceil_div64(p.n_tiles, blocks);
   switch (g.HpP / 8) {
-#define CASE_NI8(n) case n: return launch_cin_fwd_tc<n>(tm, p, g.smem, blocks, st);
+#define CASE_NI8(n) case n: return launch_cin_fwd_tc<n>(tmW, tmXk, p, g.smem, blocks, cluster, st);
     CASE_NI8(1) CASE_NI8(2) CASE_NI8(3) CASE_NI8(4) CASE_NI8(5) CASE_NI8(6) CASE_NI8(7) CASE_NI8(8)
     CASE_NI8(9) CASE_NI8(10) CASE_NI8(11) CASE_NI8(12) CASE_NI8(13) CASE_NI8(14) CASE_NI8(15) CASE_NI8(16)
 #undef CASE_NI8

@@ -54,6 +54,27 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* tmap, int x, int y, uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(x), "r"(y), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
@@ -74,6 +95,13 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// same, arriving on the barrier at the same shared-memory offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
 }
 
 // D[tmem] (+)= A[smem desc] * B[smem desc]
@@ -148,6 +176,8 @@ __device__ __forceinline__ bool elect_one() {
 
 }  // namespace tc
 
+int xdfm_make_tmap_bf16(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t row_pitch_bytes, uint32_t box_rows,
+                        uint32_t box_cols, int swizzle128);
 // host: encode a 2-D bf16 tensor map (row-major [rows, cols], box [box_rows, 64 cols], SWIZZLE_128B)
 int xdfm_make_tmap_bf16_sw128(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t row_pitch_bytes,
                               uint32_t box_rows);

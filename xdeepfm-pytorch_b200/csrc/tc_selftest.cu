@@ -20,8 +20,10 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   return fn;
 }
 
-int xdfm_make_tmap_bf16_sw128(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t row_pitch_bytes,
-                              uint32_t box_rows) {
+// 2-D bf16 tensor map over a row-major [rows, cols] matrix (row pitch in bytes), box [box_rows, box_cols];
+// swizzle: 0 = none, 1 = 128-byte (box_cols must then be 64)
+int xdfm_make_tmap_bf16(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t row_pitch_bytes, uint32_t box_rows,
+                        uint32_t box_cols, int swizzle128) {
   PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode_fn();
   if (enc == nullptr) {
     xdfm_set_error("cuTensorMapEncodeTiled entry point not available");
@@ -29,17 +31,22 @@ int xdfm_make_tmap_bf16_sw128(CUtensorMap* out, const void* gptr, uint64_t rows,
   }
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {row_pitch_bytes};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    xdfm_set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu pitch=%llu box_rows=%u", (int)r, (unsigned long long)rows,
-                   (unsigned long long)cols, (unsigned long long)row_pitch_bytes, box_rows);
+    xdfm_set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu pitch=%llu box=%ux%u", (int)r, (unsigned long long)rows,
+                   (unsigned long long)cols, (unsigned long long)row_pitch_bytes, box_rows, box_cols);
     return XDFM_ERR_CUDA;
   }
   return XDFM_OK;
+}
+
+int xdfm_make_tmap_bf16_sw128(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t row_pitch_bytes,
+                              uint32_t box_rows) {
+  return xdfm_make_tmap_bf16(out, gptr, rows, cols, row_pitch_bytes, box_rows, 64, 1);
 }
 
 __global__ void __launch_bounds__(128) tc_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,

@@ -48,7 +48,8 @@ _SIGS = {
     "xdfm_head_fwd": (c_int, [_P, _P, _P, c_int, _P, _P, c_int, _P, c_int64, c_int, _P, _P]),
     "xdfm_head_bwd": (c_int, [_P, _P, c_int64, c_int, _P, c_int, _P, c_int, _P, _P, _P, _P]),
     "xdfm_bce_sum": (c_int, [_P, _P, c_int64, c_float, _P, _P, _P, _P]),
-    "xdfm_f32_to_bf16": (c_int, [_P, _P, c_int64, _P]),
+    "xdfm_to_rows_bf16": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P]),
+    "xdfm_cin_tc_set_cluster": (None, [c_int]),
     "xdfm_cin_tc_wprime_elems": (c_int64, [c_int, c_int, c_int, c_int]),
     "xdfm_cin_fwd_tc": (c_int, [_P, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_int,
                                 c_int, _P]),
