@@ -207,7 +207,7 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       prefetch_tmap(&tmXk);
       // W' rows [wr0, wr1) are this CTA's multicast slice (the host picks a cluster size that divides H_pad/8)
       const int slice = p.H_pad / (int)csize;
-      const int wr0 = (int)crank * slice, wr1 = wr0 + slice;
+      const int wr0 = (int)crank * slice;
       int xit = 0;                               // number of x tiles loaded so far
       auto load_x = [&](int64_t tile) {
         const int buf = xit & 1;
@@ -219,35 +219,42 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         tma_load_2d(sXk + (size_t)buf * xk_tile, &tmXk, 0, (int)r0, &bars->x_full[buf]);   // OOB rows are zero-filled
         ++xit;
       };
-      uint32_t wc = 0;  // global W' chunk counter (ring position)
+      uint32_t ws = 0, wphase = 1;  // ring slot; parity of the "slot free" phase to wait for (first pass: free already)
+      bool first_pass = true;
       if (tile_of(0) < p.n_tiles) load_x(tile_of(0));
       for (int it = 0; it < p.n_iters; ++it) {
         if (it + 1 < p.n_iters && tile_of(it + 1) < p.n_tiles) load_x(tile_of(it + 1));
-        for (int c = 0; c < p.n_wchunks; ++c, ++wc) {
-          const int ws = wc % p.ns_w;
-          if (wc >= (uint32_t)p.ns_w) mbar_wait(&bars->w_empty[ws], ((wc / p.ns_w) - 1) & 1);
+        for (int c = 0; c < p.n_wchunks; ++c) {
+          if (!first_pass) mbar_wait(&bars->w_empty[ws], wphase);
           mbar_arrive_expect_tx(&bars->w_full[ws], w_stage_bytes);
-          if (wr1 > wr0) {
-            uint8_t* dst = sW + (size_t)ws * w_stage_bytes + (size_t)wr0 * 128;
-            if (csize > 1) tma_load_2d_mcast(dst, &tmW, c * 64, wr0, &bars->w_full[ws], cmask);
-            else tma_load_2d(dst, &tmW, c * 64, wr0, &bars->w_full[ws]);
-          }
+          uint8_t* dst = sW + (size_t)ws * w_stage_bytes + (size_t)wr0 * 128;
+          if (csize > 1) tma_load_2d_mcast(dst, &tmW, c * 64, wr0, &bars->w_full[ws], cmask);
+          else tma_load_2d(dst, &tmW, c * 64, wr0, &bars->w_full[ws]);
+          if (++ws == (uint32_t)p.ns_w) { ws = 0; wphase ^= 1; first_pass = false; }
         }
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
+    // One thread issues every tcgen05.mma of the CTA: the loop body is kept to a handful of instructions per K-step
+    // (ring position / phase tracked incrementally, descriptors advanced by adds) so that issue never paces the tensor pipe.
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, p.H_pad);
-      uint32_t wc = 0, sc = 0;  // global W' chunk / A stage counters
-      int at = 0;               // active tiles so far
+      const uint64_t bdesc0 = make_desc_k_sw128(smem_u32(sW));
+      const uint32_t stage_desc_step = w_stage_bytes >> 4;     // descriptor start-address units (16 B)
+      uint32_t ws = 0, wphase = 0;                              // W' ring slot / phase parity
+      uint64_t bdesc = bdesc0;                                  // descriptor of ring slot ws
+      uint32_t sc = 0;                                          // A stages consumed so far
+      int at = 0;                                               // active tiles so far
       for (int it = 0; it < p.n_iters; ++it) {
         const bool active = tile_of(it) < p.n_tiles;
         if (active && at > 0) {
           mbar_wait(&bars->acc_empty, (at - 1) & 1);
           fence_after_sync();
         }
-        int ks = 0;  // K-step within the tile
+        int kc = 0;          // K-step inside the current W' chunk (0..3)
+        int ks_left = p.ksteps_total;
+        uint32_t accum = 0;
         for (int s = 0; s < p.n_stages; ++s) {
           const int sb = sc & 1;
           if (active) {
@@ -255,23 +262,27 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             fence_after_sync();
           }
           const int nj = min(p.G, p.m - s * p.G);
-          const int nks = (nj * HpP + 15) / 16;
-          const uint32_t a_col = TC_A_COL0 + sb * TC_A_STAGE_COLS;
-          for (int t = 0; t < nks; ++t, ++ks) {
-            const int ws = wc % p.ns_w;
-            if ((ks & 3) == 0) {
-              mbar_wait(&bars->w_full[ws], (wc / p.ns_w) & 1);
+          const int nks = (nj * HpP + 15) >> 4;
+          uint32_t a_addr = tmem_base + TC_A_COL0 + sb * TC_A_STAGE_COLS;
+          for (int t = 0; t < nks; ++t) {
+            if (kc == 0) {
+              mbar_wait(&bars->w_full[ws], wphase);
               fence_after_sync();
             }
             if (active) {
-              const uint64_t bdesc = make_desc_k_sw128(smem_u32(sW + (size_t)ws * w_stage_bytes) + (ks & 3) * 32);
-              umma_ts(tmem_base, tmem_base + a_col + t * 8, bdesc, idesc, ks > 0);
+              umma_ts(tmem_base, a_addr, bdesc + (uint64_t)(kc * 2), idesc, accum);
+              accum = 1;
+              a_addr += 8;
             }
-            if ((ks & 3) == 3 || ks == p.ksteps_total - 1) {
+            ++kc;
+            --ks_left;
+            if (kc == 4 || ks_left == 0) {
               // W' chunk consumed by this CTA: tell every CTA of the cluster (each may overwrite this slot by multicast)
               if (csize > 1) umma_commit_mcast(&bars->w_empty[ws], cmask);
               else umma_commit(&bars->w_empty[ws]);
-              ++wc;
+              kc = 0;
+              if (++ws == (uint32_t)p.ns_w) { ws = 0; wphase ^= 1; bdesc = bdesc0; }
+              else bdesc += stage_desc_step;
             }
           }
           if (active) {
