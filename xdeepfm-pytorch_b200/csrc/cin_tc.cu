@@ -23,7 +23,8 @@
 // chunk sequence in lock-step and every chunk is fetched ONCE per cluster: CTA c loads rows slice c and TMA-multicasts it into
 // the shared memory of all CTAs of the cluster.
 //
-// TMEM columns (512 allocated): [0, 256) accumulator, [256, 384) and [384, 512) two A stages of up to 256 K-values each.
+// TMEM columns (512 allocated): [0, 256) accumulator, [256, 512) a ring of 8 A chunks (64 K-values = 32 columns each) that
+// is aligned with the 64-wide W' chunks, so the MMA warp's inner loop is "wait two barriers, issue four MMAs, commit".
 // Warp roles (14 warps): 0 = TMA (W' chunks, x tiles), 1 = MMA issuer + TMEM alloc, 2..5 = Z producers, 6..13 = epilogue
 // (two warps per TMEM lane quarter, alternating 16-column chunks).
 #include "tc_common.cuh"
@@ -33,7 +34,8 @@ using namespace tc;
 
 #define TC_THREADS 448
 #define TC_A_COL0 256
-#define TC_A_STAGE_COLS 128
+#define TC_A_SLOTS 8        // A-chunk ring slots
+#define TC_A_SLOT_COLS 32  // 64 bf16 K-values
 #define TC_MAX_NS_W 6      // W' chunk ring depth (run-time, limited by shared memory)
 
 struct CinTcParams {
@@ -46,16 +48,13 @@ struct CinTcParams {
   int m, mP, Hp, H, H_pad, Hs, D, act, hdb, fm_total, col_off;
   int64_t n_tiles;
   int n_iters;                // tile iterations per CTA (uniform over the grid)
-  int G;                      // X^0 fields per A stage
-  int n_stages;               // A stages per tile
-  int ksteps_total;           // UMMA K-steps per tile
-  int n_wchunks;              // 64-wide W' chunks per tile
+  int n_wchunks;              // 64-wide K chunks per tile (K' = m*HpP padded to a multiple of 64)
   int ns_w;                   // W' ring depth
 };
 
 struct __align__(8) CinTcBars {
   uint64_t w_full[TC_MAX_NS_W], w_empty[TC_MAX_NS_W];
-  uint64_t a_full[2], a_empty[2];
+  uint64_t a_full[TC_A_SLOTS], a_empty[TC_A_SLOTS];
   uint64_t x_full[2], x_empty[2];
   uint64_t acc_full, acc_empty;
   uint32_t tmem_base;
@@ -180,12 +179,10 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TC_MAX_NS_W; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], csize); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars->a_full[i], 128); mbar_init(&bars->a_empty[i], 1);
-      mbar_init(&bars->x_full[i], 1);   mbar_init(&bars->x_empty[i], 128);
-    }
+    for (int i = 0; i < TC_A_SLOTS; ++i) { mbar_init(&bars->a_full[i], 4); mbar_init(&bars->a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->x_full[i], 1); mbar_init(&bars->x_empty[i], 4); }
     mbar_init(&bars->acc_full, 1);
-    mbar_init(&bars->acc_empty, 256);
+    mbar_init(&bars->acc_empty, 8);
     fence_barrier_init();
   }
   for (int h = threadIdx.x; h < p.H_pad; h += TC_THREADS) sBias[h] = h < p.H ? p.bias[h] : 0.f;
@@ -236,72 +233,58 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    // One thread issues every tcgen05.mma of the CTA: the loop body is kept to a handful of instructions per K-step
-    // (ring position / phase tracked incrementally, descriptors advanced by adds) so that issue never paces the tensor pipe.
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, p.H_pad);
-      const uint64_t bdesc0 = make_desc_k_sw128(smem_u32(sW));
-      const uint32_t stage_desc_step = w_stage_bytes >> 4;     // descriptor start-address units (16 B)
-      uint32_t ws = 0, wphase = 0;                              // W' ring slot / phase parity
-      uint64_t bdesc = bdesc0;                                  // descriptor of ring slot ws
-      uint32_t sc = 0;                                          // A stages consumed so far
-      int at = 0;                                               // active tiles so far
-      for (int it = 0; it < p.n_iters; ++it) {
-        const bool active = tile_of(it) < p.n_tiles;
-        if (active && at > 0) {
-          mbar_wait(&bars->acc_empty, (at - 1) & 1);
-          fence_after_sync();
-        }
-        int kc = 0;          // K-step inside the current W' chunk (0..3)
-        int ks_left = p.ksteps_total;
-        uint32_t accum = 0;
-        for (int s = 0; s < p.n_stages; ++s) {
-          const int sb = sc & 1;
+    // The whole warp runs the loop (warp-uniform control flow and operands stay in uniform registers); one elected lane
+    // issues the tcgen05 instructions.  Per 64-wide K chunk: wait W' + A, issue four K=16 MMAs, release both slots.
+    const uint32_t idesc = make_idesc_bf16(128, p.H_pad);
+    const uint64_t bdesc0 = make_desc_k_sw128(smem_u32(sW));
+    const uint32_t stage_desc_step = w_stage_bytes >> 4;       // descriptor start-address units (16 B)
+    uint32_t ws = 0, wphase = 0;                                // W' ring slot / phase parity
+    uint64_t bdesc = bdesc0;                                    // descriptor of ring slot ws
+    uint32_t as = 0, aphase = 0;                                // A ring slot / phase parity
+    int at = 0;                                                 // active tiles so far
+    for (int it = 0; it < p.n_iters; ++it) {
+      const bool active = tile_of(it) < p.n_tiles;
+      if (active && at > 0) {
+        mbar_wait(&bars->acc_empty, (at - 1) & 1);
+        fence_after_sync();
+      }
+      for (int c = 0; c < p.n_wchunks; ++c) {
+        mbar_wait(&bars->w_full[ws], wphase);
+        if (active) mbar_wait(&bars->a_full[as], aphase);
+        fence_after_sync();
+        if (elect_one()) {
           if (active) {
-            mbar_wait(&bars->a_full[sb], (sc >> 1) & 1);
-            fence_after_sync();
+            const uint32_t a_addr = tmem_base + TC_A_COL0 + as * TC_A_SLOT_COLS;
+            umma_ts(tmem_base, a_addr, bdesc, idesc, c > 0 ? 1u : 0u);
+            umma_ts(tmem_base, a_addr + 8, bdesc + 2, idesc, 1u);
+            umma_ts(tmem_base, a_addr + 16, bdesc + 4, idesc, 1u);
+            umma_ts(tmem_base, a_addr + 24, bdesc + 6, idesc, 1u);
+            umma_commit(&bars->a_empty[as]);     // A chunk consumed
           }
-          const int nj = min(p.G, p.m - s * p.G);
-          const int nks = (nj * HpP + 15) >> 4;
-          uint32_t a_addr = tmem_base + TC_A_COL0 + sb * TC_A_STAGE_COLS;
-          for (int t = 0; t < nks; ++t) {
-            if (kc == 0) {
-              mbar_wait(&bars->w_full[ws], wphase);
-              fence_after_sync();
-            }
-            if (active) {
-              umma_ts(tmem_base, a_addr, bdesc + (uint64_t)(kc * 2), idesc, accum);
-              accum = 1;
-              a_addr += 8;
-            }
-            ++kc;
-            --ks_left;
-            if (kc == 4 || ks_left == 0) {
-              // W' chunk consumed by this CTA: tell every CTA of the cluster (each may overwrite this slot by multicast)
-              if (csize > 1) umma_commit_mcast(&bars->w_empty[ws], cmask);
-              else umma_commit(&bars->w_empty[ws]);
-              kc = 0;
-              if (++ws == (uint32_t)p.ns_w) { ws = 0; wphase ^= 1; bdesc = bdesc0; }
-              else bdesc += stage_desc_step;
-            }
-          }
-          if (active) {
-            umma_commit(&bars->a_empty[sb]);     // A stage consumed
-            ++sc;
-          }
+          // W' chunk consumed by this CTA: tell every CTA of the cluster (each may overwrite this slot by multicast)
+          if (csize > 1) umma_commit_mcast(&bars->w_empty[ws], cmask);
+          else umma_commit(&bars->w_empty[ws]);
         }
-        if (active) {
-          umma_commit(&bars->acc_full);          // accumulator complete
-          ++at;
-        }
+        __syncwarp();
+        if (++ws == (uint32_t)p.ns_w) { ws = 0; wphase ^= 1; bdesc = bdesc0; }
+        else bdesc += stage_desc_step;
+        if (active && ++as == TC_A_SLOTS) { as = 0; aphase ^= 1; }
+      }
+      if (active) {
+        if (elect_one()) umma_commit(&bars->acc_full);   // accumulator complete
+        __syncwarp();
+        ++at;
       }
     }
   } else if (warp < 6) {
     // =============================== Z producers: thread <-> accumulator row ===============================
+    // Z[r, k'] for k' = j*HpP + i is written in k' order into the A ring, one 8-value granule (4 columns) at a time; a ring slot
+    // (64 K-values) is published as soon as its last granule has been stored.
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     const int rl = q * 32 + lane;                // row within the tile
-    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    uint32_t sc = 0;
+    const uint32_t a_base = tmem_base + ((uint32_t)(q * 32) << 16) + TC_A_COL0;
+    uint32_t as = 0, aphase = 1;                 // ring slot being filled; parity of the "slot free" phase (first pass: free)
+    bool a_first = true;
     int at = 0;
     for (int it = 0; it < p.n_iters; ++it) {
       if (tile_of(it) >= p.n_tiles) continue;
@@ -319,28 +302,43 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         xk2[v8 * 4 + 2] = *reinterpret_cast<const __nv_bfloat162*>(&t.z);
         xk2[v8 * 4 + 3] = *reinterpret_cast<const __nv_bfloat162*>(&t.w);
       }
-      for (int s = 0; s < p.n_stages; ++s, ++sc) {
-        const int sb = sc & 1;
-        if (sc >= 2) {
-          mbar_wait(&bars->a_empty[sb], ((sc >> 1) - 1) & 1);
+      int pos = 0;                               // column inside the current ring slot (0, 4, .., 28)
+      auto put_granule = [&](const uint32_t (&z)[4]) {
+        if (pos == 0 && !a_first) {              // entering a slot that was used before: wait until its MMAs are done
+          mbar_wait(&bars->a_empty[as], aphase);
           fence_after_sync();
         }
-        const int nj = min(p.G, p.m - s * p.G);
-        uint32_t col = tmem_base + lane_addr + TC_A_COL0 + sb * TC_A_STAGE_COLS;
-        for (int jj = 0; jj < nj; ++jj) {
-          const __nv_bfloat16 xv = x0row[s * p.G + jj];
-          produce_row<0, HpP / 2, HpP / 2>(xk2, __halves2bfloat162(xv, xv), col);
-          col += HpP / 2;
+        tmem_st_x4(a_base + as * TC_A_SLOT_COLS + pos, z);
+        pos += 4;
+        if (pos == TC_A_SLOT_COLS) {             // slot complete: publish it
+          tmem_wait_st();
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->a_full[as]);
+          pos = 0;
+          if (++as == TC_A_SLOTS) { as = 0; aphase ^= 1; a_first = false; }
         }
-        if ((nj * HpP) & 15) {   // odd tail: pad the last K-step of the stage with zeros
-          uint32_t zz[4] = {0u, 0u, 0u, 0u};
-          tmem_st_x4(col, zz);
+      };
+      for (int j = 0; j < p.m; ++j) {
+        const __nv_bfloat16 xv = x0row[j];
+        const __nv_bfloat162 xv2 = __halves2bfloat162(xv, xv);
+#pragma unroll
+        for (int g8 = 0; g8 < NI8; ++g8) {
+          uint32_t z[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 prod = __hmul2(xk2[g8 * 4 + i], xv2);
+            z[i] = *reinterpret_cast<uint32_t*>(&prod);
+          }
+          put_granule(z);
         }
-        tmem_wait_st();
-        fence_before_sync();
-        mbar_arrive(&bars->a_full[sb]);
       }
-      mbar_arrive(&bars->x_empty[buf]);
+      while (pos != 0) {                         // zero-fill the tail of the last K chunk
+        const uint32_t zz[4] = {0u, 0u, 0u, 0u};
+        put_granule(zz);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->x_empty[buf]);
       ++at;
     }
   } else {
@@ -383,7 +381,8 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         }
       }
       fence_before_sync();
-      mbar_arrive(&bars->acc_empty);             // accumulator drained: the next tile's MMAs may start
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->acc_empty);   // accumulator drained: the next tile's MMAs may start
       if (p.pooled && p.D > 32) {
         // D = 64: lane quarters (0,1) and (2,3) hold one sample each; D = 128: all four quarters hold one sample
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -448,7 +447,7 @@ extern "C" int xdfm_to_rows_bf16(const float* x, int64_t B, int C, int D, int CP
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 struct CinTcGeom {
-  int HpP, H_pad, Hs, mP, KP, G, n_stages, ksteps_total, n_wchunks, ns_w;
+  int HpP, H_pad, Hs, mP, KP, n_wchunks, ns_w;
   size_t smem;
 };
 
@@ -465,17 +464,7 @@ static int cin_tc_geom(int m, int Hp, int H, int D, CinTcGeom* g) {
   g->H_pad = round_up(H, 16);
   g->Hs = round_up(H, 8);
   g->mP = round_up(m, 8);
-  g->G = 256 / g->HpP;
-  if ((g->HpP % 16) != 0) g->G -= (g->G & 1);
-  if (g->G < 1) g->G = 1;
-  g->n_stages = (m + g->G - 1) / g->G;
-  int ks = 0;
-  for (int s = 0; s < g->n_stages; ++s) {
-    int nj = std::min(g->G, m - s * g->G);
-    ks += (nj * g->HpP + 15) / 16;
-  }
-  g->ksteps_total = ks;
-  g->n_wchunks = (ks + 3) / 4;
+  g->n_wchunks = (m * g->HpP + 63) / 64;
   g->KP = g->n_wchunks * 64;
   size_t fixed = 2 * (size_t)128 * g->mP * 2 + 2 * (size_t)128 * g->HpP * 2 + (size_t)5 * g->H_pad * 4 + sizeof(CinTcBars) + 256;
   size_t stage = (size_t)g->H_pad * 128;
@@ -553,7 +542,7 @@ extern "C" int xdfm_cin_fwd_tc(const void* x0t, const void* xkt, int64_t xk_pitc
   p.x0t = (const __nv_bfloat16*)x0t; p.bias = bias; p.yt = (__nv_bfloat16*)yt; p.pooled = pooled; p.maps = maps; p.R = R;
   p.m = m; p.mP = g.mP; p.Hp = Hp; p.H = H; p.H_pad = g.H_pad; p.Hs = g.Hs; p.D = D; p.act = act; p.hdb = direct_begin;
   p.fm_total = fm_total; p.col_off = col_off;
-  p.n_tiles = ceil_div64(R, 128); p.G = g.G; p.n_stages = g.n_stages; p.ksteps_total = g.ksteps_total; p.n_wchunks = g.n_wchunks;
+  p.n_tiles = ceil_div64(R, 128); p.n_wchunks = g.n_wchunks;
   p.ns_w = g.ns_w;
   int sms = xdfm_num_sms();
   int blocks = (int)std::min<int64_t>(ceil_div64(p.n_tiles, cluster) * cluster, (int64_t)(sms / cluster) * cluster);
