@@ -60,22 +60,64 @@ struct __align__(8) CinTcBars {
   uint32_t tmem_base;
 };
 
-// z[i2] = xk2[i2] * x0 (packed bf16 pairs) for i2 in [OFF, OFF+REM), written to TMEM columns col+OFF.. in the widest
-// tcgen05.st shapes; only 16 product registers are live at a time.
-template <int OFF, int REM, int NPAIR>
-__device__ __forceinline__ void produce_row(const __nv_bfloat162 (&xk2)[NPAIR], __nv_bfloat162 xv2, uint32_t col) {
-  if constexpr (REM > 0) {
-    constexpr int N = REM >= 16 ? 16 : (REM >= 8 ? 8 : 4);
-    uint32_t z[N];
+// ---- Z producer helpers -------------------------------------------------------------------------------------------------
+struct ARing {
+  CinTcBars* bars;
+  uint32_t base;      // TMEM address of ring column 0 for this warp's lane quarter
+  uint32_t as;        // slot being filled
+  uint32_t aphase;    // parity of the "slot free" phase to wait for
+  bool first;         // first pass over the ring: slots are free, nothing to wait for
+  int lane;
+};
+
+__device__ __forceinline__ void ring_acquire(ARing& r) {   // entering slot r.as at column 0
+  if (!r.first) {
+    mbar_wait(&r.bars->a_empty[r.as], r.aphase);
+    fence_after_sync();
+  }
+}
+__device__ __forceinline__ void ring_publish(ARing& r) {   // slot r.as completely written by this warp
+  tmem_wait_st();
+  fence_before_sync();
+  __syncwarp();
+  if (r.lane == 0) mbar_arrive(&r.bars->a_full[r.as]);
+  if (++r.as == TC_A_SLOTS) { r.as = 0; r.aphase ^= 1; r.first = false; }
+}
+
+// products xk2[OFF .. OFF+N) * xv2 -> N TMEM columns at addr (N = 4, 8 or 16)
+template <int NPAIR, int OFF, int N>
+__device__ __forceinline__ void st_products(const __nv_bfloat162 (&xk2)[NPAIR], __nv_bfloat162 xv2, uint32_t addr) {
+  uint32_t z[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      __nv_bfloat162 prod = __hmul2(xk2[OFF + i], xv2);
-      z[i] = *reinterpret_cast<uint32_t*>(&prod);
+  for (int i = 0; i < N; ++i) {
+    __nv_bfloat162 prod = __hmul2(xk2[OFF + i], xv2);
+    z[i] = *reinterpret_cast<uint32_t*>(&prod);
+  }
+  if constexpr (N == 16) tmem_st_x16(addr, z);
+  else if constexpr (N == 8) tmem_st_x8(addr, z);
+  else tmem_st_x4(addr, z);
+}
+template <int NPAIR, int OFF, int SEG>   // SEG columns (multiple of 4) in the widest shapes
+__device__ __forceinline__ void st_segment(const __nv_bfloat162 (&xk2)[NPAIR], __nv_bfloat162 xv2, uint32_t addr) {
+  if constexpr (SEG > 0) {
+    constexpr int N = SEG >= 16 ? 16 : (SEG >= 8 ? 8 : 4);
+    st_products<NPAIR, OFF, N>(xk2, xv2, addr);
+    st_segment<NPAIR, OFF + N, SEG - N>(xk2, xv2, addr + N);
+  }
+}
+// One X^0 field j: NPAIR columns starting at column CIN of the current slot; slot boundaries are compile-time positions.
+template <int NPAIR, int CIN, int OFF>
+__device__ __forceinline__ void emit_field(const __nv_bfloat162 (&xk2)[NPAIR], __nv_bfloat162 xv2, ARing& r) {
+  if constexpr (OFF < NPAIR) {
+    if constexpr (CIN == 0) ring_acquire(r);
+    constexpr int room = TC_A_SLOT_COLS - CIN;
+    constexpr int rem = NPAIR - OFF;
+    constexpr int seg = rem < room ? rem : room;
+    st_segment<NPAIR, OFF, seg>(xk2, xv2, r.base + r.as * TC_A_SLOT_COLS + CIN);
+    if constexpr (CIN + seg == TC_A_SLOT_COLS) {
+      ring_publish(r);
+      emit_field<NPAIR, 0, OFF + seg>(xk2, xv2, r);
     }
-    if constexpr (N == 16) tmem_st_x16(col + OFF, z);
-    else if constexpr (N == 8) tmem_st_x8(col + OFF, z);
-    else tmem_st_x4(col + OFF, z);
-    produce_row<OFF + N, REM - N, NPAIR>(xk2, xv2, col);
   }
 }
 
@@ -282,9 +324,10 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     // (64 K-values) is published as soon as its last granule has been stored.
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     const int rl = q * 32 + lane;                // row within the tile
-    const uint32_t a_base = tmem_base + ((uint32_t)(q * 32) << 16) + TC_A_COL0;
-    uint32_t as = 0, aphase = 1;                 // ring slot being filled; parity of the "slot free" phase (first pass: free)
-    bool a_first = true;
+    ARing ring;
+    ring.bars = bars;
+    ring.base = tmem_base + ((uint32_t)(q * 32) << 16) + TC_A_COL0;
+    ring.as = 0; ring.aphase = 1; ring.first = true; ring.lane = lane;
     int at = 0;
     for (int it = 0; it < p.n_iters; ++it) {
       if (tile_of(it) >= p.n_tiles) continue;
@@ -302,40 +345,26 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         xk2[v8 * 4 + 2] = *reinterpret_cast<const __nv_bfloat162*>(&t.z);
         xk2[v8 * 4 + 3] = *reinterpret_cast<const __nv_bfloat162*>(&t.w);
       }
-      int pos = 0;                               // column inside the current ring slot (0, 4, .., 28)
-      auto put_granule = [&](const uint32_t (&z)[4]) {
-        if (pos == 0 && !a_first) {              // entering a slot that was used before: wait until its MMAs are done
-          mbar_wait(&bars->a_empty[as], aphase);
-          fence_after_sync();
-        }
-        tmem_st_x4(a_base + as * TC_A_SLOT_COLS + pos, z);
-        pos += 4;
-        if (pos == TC_A_SLOT_COLS) {             // slot complete: publish it
-          tmem_wait_st();
-          fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->a_full[as]);
-          pos = 0;
-          if (++as == TC_A_SLOTS) { as = 0; aphase ^= 1; a_first = false; }
-        }
-      };
+      int ph = 0;                                // granule (4 columns) inside the current ring slot where the next field starts
       for (int j = 0; j < p.m; ++j) {
         const __nv_bfloat16 xv = x0row[j];
         const __nv_bfloat162 xv2 = __halves2bfloat162(xv, xv);
-#pragma unroll
-        for (int g8 = 0; g8 < NI8; ++g8) {
-          uint32_t z[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            __nv_bfloat162 prod = __hmul2(xk2[g8 * 4 + i], xv2);
-            z[i] = *reinterpret_cast<uint32_t*>(&prod);
-          }
-          put_granule(z);
+        switch (ph) {
+          case 0: emit_field<HpP / 2, 0, 0>(xk2, xv2, ring); break;
+          case 1: emit_field<HpP / 2, 4, 0>(xk2, xv2, ring); break;
+          case 2: emit_field<HpP / 2, 8, 0>(xk2, xv2, ring); break;
+          case 3: emit_field<HpP / 2, 12, 0>(xk2, xv2, ring); break;
+          case 4: emit_field<HpP / 2, 16, 0>(xk2, xv2, ring); break;
+          case 5: emit_field<HpP / 2, 20, 0>(xk2, xv2, ring); break;
+          case 6: emit_field<HpP / 2, 24, 0>(xk2, xv2, ring); break;
+          default: emit_field<HpP / 2, 28, 0>(xk2, xv2, ring); break;
         }
+        ph = (ph + NI8) & 7;
       }
-      while (pos != 0) {                         // zero-fill the tail of the last K chunk
+      if (ph != 0) {                             // zero-fill the tail of the last K chunk and publish it
         const uint32_t zz[4] = {0u, 0u, 0u, 0u};
-        put_granule(zz);
+        for (; ph < 8; ++ph) tmem_st_x4(ring.base + ring.as * TC_A_SLOT_COLS + ph * 4, zz);
+        ring_publish(ring);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->x_empty[buf]);
