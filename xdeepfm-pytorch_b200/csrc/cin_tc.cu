@@ -126,25 +126,38 @@ struct EpiRow {
   float* maps;         // &maps[b, col_off - hdb, d] or null (index by h, stride D)
   float* pooled;       // &pooled[b, col_off - hdb] or null (index by h)
   float* spool;        // per-lane-quarter scratch [H_pad] (D > 32)
+  float act_floor;     // 0 for ReLU, -inf for linear
   bool valid;
 };
 
 // One 16-column accumulator chunk of one row: bias + activation, bf16 / fp32 stores, and the sum over the sample's D lanes.
 // The lane-sum uses a transposing butterfly: every shuffle level halves the number of live values per lane, so 16 columns
 // cost 8+4+2+1 shuffles instead of 16*log2(LD); afterwards each lane holds the finished sum of its own column(s).
-template <int LD>   // lanes per sample inside the warp: min(D, 32)
+// Rows past the end of the batch need no masking: a sample's D rows are all valid or all invalid, so garbage never mixes
+// into a valid sample, and invalid rows have null output pointers.  Columns >= H are exact zeros for ReLU / linear
+// (zero rows of W', zero bias) and are masked explicitly for sigmoid.
+template <int LD, int ACT>   // LD = lanes per sample inside the warp: min(D, 32)
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[16], int c0, int lane, const float* __restrict__ sBias,
                                                const CinTcParams& p, const EpiRow& r) {
   float y[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    float t = __uint_as_float(v[i]) + sBias[c0 + i];
-    if (p.act == XDFM_ACT_RELU) t = fmaxf(t, 0.f);
-    else if (p.act == XDFM_ACT_SIGMOID) t = 1.f / (1.f + __expf(-t));
-    y[i] = (r.valid && c0 + i < p.H) ? t : 0.f;
+  for (int g4 = 0; g4 < 4; ++g4) {
+    const float4 bv = *reinterpret_cast<const float4*>(sBias + c0 + g4 * 4);
+    y[g4 * 4 + 0] = __uint_as_float(v[g4 * 4 + 0]) + bv.x;
+    y[g4 * 4 + 1] = __uint_as_float(v[g4 * 4 + 1]) + bv.y;
+    y[g4 * 4 + 2] = __uint_as_float(v[g4 * 4 + 2]) + bv.z;
+    y[g4 * 4 + 3] = __uint_as_float(v[g4 * 4 + 3]) + bv.w;
+  }
+  if constexpr (ACT != XDFM_ACT_SIGMOID) {
+    // ReLU and linear share one path: max(y, floor) with floor = 0 or -inf
+#pragma unroll
+    for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], r.act_floor);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) y[i] = (c0 + i < p.H) ? 1.f / (1.f + __expf(-y[i])) : 0.f;
   }
   if (r.yt != nullptr) {
-    // channels [c0, c0+16) of this row; columns H..Hs-1 are written as zeros, columns >= Hs do not exist
+    // channels [c0, c0+16) of this row; columns H..Hs-1 are zeros, columns >= Hs do not exist
 #pragma unroll
     for (int g8 = 0; g8 < 2; ++g8) {
       if (c0 + g8 * 8 < p.Hs) {
@@ -165,7 +178,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[16], int c0, 
     for (int i = 0; i < 16; ++i)
       if (c0 + i < p.H && c0 + i >= p.hdb) mp[(int64_t)i * p.D] = y[i];
   }
-  if (p.pooled == nullptr) return;
+  if (p.pooled == nullptr || c0 + 16 <= p.hdb) return;    // no direct channel in this chunk
   int nv = 16, col = 0;
 #pragma unroll
   for (int o = LD / 2; o >= 1; o >>= 1) {
@@ -196,6 +209,32 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[16], int c0, 
       else if (r.pooled != nullptr && h >= p.hdb && h < p.H) r.pooled[h] = y[i];
     }
   }
+}
+
+// All 16-column chunks of one accumulator tile that belong to this warp (c0 = 16*half, +32, ...); the tcgen05.ld of the next
+// chunk is in flight while the current one is processed.
+template <int LD, int ACT>
+__device__ __forceinline__ void epilogue_tile(uint32_t tmem_row, int half, int lane, const float* __restrict__ sBias,
+                                              const CinTcParams& p, const EpiRow& r) {
+  uint32_t va[16], vb[16];
+  int c0 = half * 16;
+  if (c0 < p.H_pad) tmem_ld_x16(tmem_row + c0, va);
+  for (; c0 < p.H_pad; c0 += 64) {
+    tmem_wait_ld();
+    if (c0 + 32 < p.H_pad) tmem_ld_x16(tmem_row + c0 + 32, vb);
+    epilogue_chunk<LD, ACT>(va, c0, lane, sBias, p, r);
+    if (c0 + 32 < p.H_pad) {
+      tmem_wait_ld();
+      if (c0 + 64 < p.H_pad) tmem_ld_x16(tmem_row + c0 + 64, va);
+      epilogue_chunk<LD, ACT>(vb, c0 + 32, lane, sBias, p, r);
+    }
+  }
+}
+
+template <int LD>
+__device__ __forceinline__ void epilogue_tile_act(uint32_t tmem_row, int half, int lane, const float* __restrict__ sBias,
+                                                  const CinTcParams& p, const EpiRow& r) {
+  epilogue_tile<LD, XDFM_ACT_RELU>(tmem_row, half, lane, sBias, p, r);
 }
 
 // NI8 = HpP / 8 (channels of X^{k-1} padded to a multiple of 8, HpP <= 128)
@@ -391,24 +430,10 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       r.spool = sPool + q * p.H_pad;
       mbar_wait(&bars->acc_full, at & 1);
       fence_after_sync();
-      // software pipeline: the tcgen05.ld of the next chunk is in flight while the current one is processed
-      uint32_t va[16], vb[16];
-      int c0 = half * 16;
-      if (c0 < p.H_pad) tmem_ld_x16(tmem_base + lane_addr + c0, va);
-      for (; c0 < p.H_pad; c0 += 64) {
-        tmem_wait_ld();
-        if (c0 + 32 < p.H_pad) tmem_ld_x16(tmem_base + lane_addr + c0 + 32, vb);
-        if (p.D == 8) epilogue_chunk<8>(va, c0, lane, sBias, p, r);
-        else if (p.D == 16) epilogue_chunk<16>(va, c0, lane, sBias, p, r);
-        else epilogue_chunk<32>(va, c0, lane, sBias, p, r);            // D = 32, 64, 128: full-warp segments
-        if (c0 + 32 < p.H_pad) {
-          tmem_wait_ld();
-          if (c0 + 64 < p.H_pad) tmem_ld_x16(tmem_base + lane_addr + c0 + 64, va);
-          if (p.D == 8) epilogue_chunk<8>(vb, c0 + 32, lane, sBias, p, r);
-          else if (p.D == 16) epilogue_chunk<16>(vb, c0 + 32, lane, sBias, p, r);
-          else epilogue_chunk<32>(vb, c0 + 32, lane, sBias, p, r);
-        }
-      }
+      r.act_floor = p.act == XDFM_ACT_RELU ? 0.f : __int_as_float(0xff800000);
+      if (p.D == 8) epilogue_tile_act<8>(tmem_base + lane_addr, half, lane, sBias, p, r);
+      else if (p.D == 16) epilogue_tile_act<16>(tmem_base + lane_addr, half, lane, sBias, p, r);
+      else epilogue_tile_act<32>(tmem_base + lane_addr, half, lane, sBias, p, r);      // D = 32, 64, 128: full-warp segments
       fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->acc_empty);   // accumulator drained: the next tile's MMAs may start
@@ -548,6 +573,10 @@ extern "C" int xdfm_cin_fwd_tc(const void* x0t, const void* xkt, int64_t xk_pitc
   int rc = cin_tc_geom(m, Hp, H, D, &g);
   if (rc) return rc;
   if (B == 0) return XDFM_OK;
+  if (act != XDFM_ACT_RELU && act != XDFM_ACT_NONE) {
+    xdfm_set_error("cin_fwd_tc: activation %d is not fused in the bf16 tensor-core path (relu / linear); use cin_precision='fp32'", act);
+    return XDFM_ERR_UNSUPPORTED;
+  }
   XDFM_CHECK_ARG(((uintptr_t)x0t % 16 == 0) && ((uintptr_t)xkt % 16 == 0) && ((uintptr_t)yt % 16 == 0) && xk_pitch % 8 == 0 &&
                      xk_pitch >= g.HpP,
                  "cin_fwd_tc: operands must be 16-byte aligned, xk_pitch (%lld) a multiple of 8 and >= %d", (long long)xk_pitch, g.HpP);
