@@ -151,6 +151,22 @@ int xdfm_cin_fwd_tc(const void* x0t, const void* xkt, int64_t xk_pitch, const fl
                     int m, int Hp, int H, int D, int act, void* yt, int direct_begin, float* pooled, float* maps, int fm_total,
                     int col_off, void* stream);
 
+/* row-layout helpers of the tensor-core path:
+ * cin_dy_rows: dyt [B*D, Hs] bf16 = act'(yt) * (dpooled / dmaps on channels [direct_begin, H) + dnext [B*D, dnext_pitch] fp32
+ *              (row layout) on channels [0, n_next));  from_rows_f32: [B*D, CP] fp32 rows -> [B, C, D] (optionally +=);
+ * add_rows_f32: a[r, :C] += b[r, :C]. */
+int xdfm_cin_dy_rows(const void* yt, int64_t B, int D, int H, int Hs, int direct_begin, const float* dpooled, const float* dmaps,
+                     int fm_total, int col_off, const float* dnext, int64_t dnext_pitch, int n_next, int act, void* dyt, void* stream);
+int xdfm_from_rows_f32(const float* xt, int64_t B, int C, int D, int CP, float* x, int accumulate, void* stream);
+int xdfm_add_rows_f32(float* a, int64_t pitch_a, const float* b, int64_t pitch_b, int64_t R, int C, void* stream);
+
+/* CIN backward w.r.t. activations on the tensor cores: dyt [B*D, Hs] bf16 (act'(y) * upstream), x0t / xkt as in the forward,
+ * wt = bf16 scratch [xdfm_cin_bwd_dx_tc_wt_elems]; dxk [B*D, HpQ] fp32 (overwritten, HpQ = Hp rounded up to 16),
+ * dx0 [B*D, mP] fp32 (accumulated +=). */
+int64_t xdfm_cin_bwd_dx_tc_wt_elems(int m, int Hp, int H, int D);
+int xdfm_cin_bwd_dx_tc(const void* dyt, const void* x0t, const void* xkt, int64_t xk_pitch, const float* W, void* wt, int64_t B, int m,
+                       int Hp, int H, int D, float* dxk, float* dx0, void* stream);
+
 /* ---- tcgen05 self-test (diagnostic): D[128,N] = A[128,K] * B[N,K]^T, bf16 in / fp32 out, one CTA.
  * mode 0: A via TMA + shared-memory descriptor (SS); mode 1: A stored to TMEM by the threads (TS, the CIN operand path). */
 int xdfm_tc_selftest_gemm(const void* A, const void* Bm, int N, int K, int mode, float* out, void* stream);

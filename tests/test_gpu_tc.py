@@ -131,3 +131,80 @@ def test_cin_tc_rejects_unsupported_dim():
     from deepctr import _native as Nv
     assert Nv.lib().xdfm_cin_tc_wprime_elems(26, 26, 200, 10) < 0
     assert b"unsupported" in Nv.lib().xdfm_last_error()
+
+
+DX_CASES = [
+    # B, m, D, H, Hp
+    (8, 2, 16, 16, 2),
+    (19, 26, 16, 200, 100),
+    (300, 26, 16, 200, 26),
+    (33, 26, 8, 128, 128),
+    (20, 22, 32, 256, 128),
+    (9, 26, 64, 256, 26),
+    (2500, 12, 16, 40, 20),
+]
+
+
+@pytest.mark.parametrize("cluster", [1, 2])
+@pytest.mark.parametrize("case", DX_CASES, ids=[str(c) for c in DX_CASES])
+def test_cin_tc_backward_dx_matches_emulation(case, cluster):
+    from deepctr import _native as Nv
+    L = Nv.lib()
+    B, m, D, H, Hp = case
+    g = torch.Generator().manual_seed(sum(case) + 1)
+    r8 = lambda v: (v + 7) // 8 * 8
+    r16 = lambda v: (v + 15) // 16 * 16
+    x0 = torch.randn(B, m, D, generator=g) * 0.5
+    Hprev = Hp if Hp == m else 2 * Hp
+    xk_full = x0 if Hp == m else torch.randn(B, Hprev, D, generator=g) * 0.5
+    W = torch.randn(H, Hp * m, generator=g) / (Hp * m) ** 0.5
+    dy = torch.randn(B, H, D, generator=g)
+    x0t = to_rows(x0.to(DEV), r8(m))
+    xkt = x0t if Hp == m else to_rows(xk_full.to(DEV), r8(Hprev))
+    dyt = to_rows(dy.to(DEV), r8(H))
+    Wd = W.to(DEV)
+    wt = torch.empty(L.xdfm_cin_bwd_dx_tc_wt_elems(m, Hp, H, D), dtype=torch.bfloat16, device=DEV)
+    HpQ, mP = r16(Hp), r8(m)
+    dxk = torch.full((B * D, HpQ), float("nan"), device=DEV)
+    dx0_init = torch.randn(B * D, mP, generator=g)
+    dx0 = dx0_init.to(DEV).clone()
+    L.xdfm_cin_tc_set_cluster(cluster)
+    try:
+        Nv.check(L.xdfm_cin_bwd_dx_tc(Nv.ptr(dyt), Nv.ptr(x0t), Nv.ptr(xkt), xkt.shape[1], Nv.ptr(Wd), Nv.ptr(wt), B, m, Hp, H, D,
+                                      Nv.ptr(dxk), Nv.ptr(dx0), Nv.stream_ptr()))
+        torch.cuda.synchronize()
+    finally:
+        L.xdfm_cin_tc_set_cluster(2)
+    bf = lambda t: t.to(torch.bfloat16).double()
+    dz = torch.einsum("bhd,hij->bijd", bf(dy), bf(W).view(H, Hp, m))            # [B, Hp, m, D]
+    ref_dxk = torch.einsum("bijd,bjd->bid", dz, bf(x0))
+    ref_dx0 = torch.einsum("bijd,bid->bjd", dz, bf(xk_full[:, :Hp]))
+    got_dxk = dxk.view(B, D, HpQ)[:, :, :Hp].permute(0, 2, 1)
+    got_dx0 = (dx0.cpu() - dx0_init).view(B, D, mP)[:, :, :m].permute(0, 2, 1)
+    assert_close(got_dxk, ref_dxk, 1e-3, 1e-3 * ref_dxk.abs().max().item(), "dxk")
+    assert_close(got_dx0, ref_dx0, 1e-3, 1e-3 * ref_dx0.abs().max().item(), "dx0")
+
+
+def test_cin_dy_rows():
+    from deepctr import _native as Nv
+    L = Nv.lib()
+    B, D, H, hdb, fm, col_off, n_next = 7, 16, 20, 10, 17, 3, 10
+    g = torch.Generator().manual_seed(5)
+    y = torch.relu(torch.randn(B, H, D, generator=g))
+    dpool = torch.randn(B, fm, generator=g)
+    dnext = torch.randn(B, n_next, D, generator=g)
+    yt = to_rows(y.to(DEV), 24)
+    dnext_rows = dnext.permute(0, 2, 1).reshape(B * D, n_next).contiguous()
+    dnext_pad = torch.zeros(B * D, 16)
+    dnext_pad[:, :n_next] = dnext_rows
+    dyt = torch.full((B * D, 24), float("nan"), dtype=torch.bfloat16, device=DEV)
+    dpd, dnd = dpool.to(DEV), dnext_pad.to(DEV)
+    Nv.check(L.xdfm_cin_dy_rows(Nv.ptr(yt), B, D, H, 24, hdb, Nv.ptr(dpd), None, fm, col_off, Nv.ptr(dnd), 16, n_next, 1, Nv.ptr(dyt),
+                                Nv.stream_ptr()))
+    ref = torch.zeros(B, H, D)
+    ref[:, hdb:] += dpool[:, col_off:col_off + H - hdb, None]
+    ref[:, :n_next] += dnext
+    ref = ref * (y.to(torch.bfloat16).float() > 0)
+    got = from_rows(dyt, B, H, D).float().cpu()
+    assert_close(got, ref.to(torch.bfloat16).float(), 0, 0, "dy rows")
+    assert float(dyt[:, H:].float().abs().max()) == 0.0

@@ -539,8 +539,8 @@ extern "C" int64_t xdfm_cin_tc_wprime_elems(int m, int Hp, int H, int D) {
   return (int64_t)g.H_pad * g.KP;
 }
 
-static int g_cin_tc_cluster = 2;
-extern "C" void xdfm_cin_tc_set_cluster(int c) { g_cin_tc_cluster = (c == 1 || c == 2 || c == 4) ? c : 2; }
+int g_cin_tc_cluster_shared = 2;   // cluster size of the weight-stream multicast (all tensor-core CIN kernels)
+extern "C" void xdfm_cin_tc_set_cluster(int c) { g_cin_tc_cluster_shared = (c == 1 || c == 2 || c == 4) ? c : 2; }
 
 template <int NI8>
 static int launch_cin_fwd_tc(const CUtensorMap& tmW, const CUtensorMap& tmXk, const CinTcParams& p, size_t smem, int blocks, int cluster,
@@ -589,7 +589,7 @@ extern "C" int xdfm_cin_fwd_tc(const void* x0t, const void* xkt, int64_t xk_pitc
   }
   const int64_t R = B * (int64_t)D;
   CUtensorMap tmW, tmXk;
-  int cluster = g_cin_tc_cluster;
+  int cluster = g_cin_tc_cluster_shared;
   while (cluster > 1 && ((g.H_pad / 8) % cluster) != 0) cluster >>= 1;
   // one TMA box = one CTA's multicast slice of a 64-wide W' chunk
   rc = xdfm_make_tmap_bf16(&tmW, wprime, (uint64_t)g.H_pad, (uint64_t)g.KP, (uint64_t)g.KP * 2, (uint32_t)(g.H_pad / cluster), 64, 1);

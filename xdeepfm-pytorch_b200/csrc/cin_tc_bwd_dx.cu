@@ -1,0 +1,395 @@
+// CIN layer backward w.r.t. the activations on the tensor cores.
+//
+// Replaces the dZ / dX part of torch's autograd of deepctr/layers/interaction.py:218-224 (convolution_backward input grad +
+// einsum backward).  With dY = act'(y) * upstream (bf16, row layout [R, Hs], R = B*D rows r = (sample, d)):
+//
+//     dZ[r, (j,i)] = sum_h dY[r,h] * W[h, i*m + j]                 (implicit GEMM, never materialised)
+//     dXk[r, i]    = sum_j dZ[r,(j,i)] * X0[r, j]                   (layer input gradient, fp32 row layout [R, HpQ])
+//     dX0[r, j]   += sum_i dZ[r,(j,i)] * Xk[r, i]                   (accumulated over layers, fp32 row layout [R, mP])
+//
+// One accumulator tile = 128 rows.  A = dY tile, written to TMEM once per tile by the row warps (tcgen05.st, TS-mode MMA).
+// For every X^0 field j one MMA group computes dZ_j[128 x HpQ] = dY[128 x H_pad] . W''_j[HpQ x H_pad]^T into one of two TMEM
+// accumulators (HpQ = Hp rounded up to 16); while the tensor core works on field j+1 the row warps drain field j:
+// each thread owns one row, multiplies the chunk by X0[r,j] into its register-resident dXk row and dots it with its
+// register-resident Xk row for dX0[r,j].  Two warps share a TMEM lane quarter and split the channel range.
+// W'' = weights permuted to [m*HpQ rows (j-major), H_pad cols] bf16 (K-major for this GEMM), streamed by TMA per field and
+// multicast across the CTAs of a cluster exactly like the forward weight stream.
+//
+// TMEM columns: [0,128) dY of the current tile (A operand), [256,384) / [384,512) the two dZ accumulators.
+// Warps: 0 = TMA, 1 = MMA + TMEM alloc, 2..9 = row warps (quarter = warp & 3, channel half = (warp - 2) >> 2).
+#include "tc_common.cuh"
+#include "../../include/xdfm.h"
+
+using namespace tc;
+
+#define DX_THREADS 320
+#define DX_ACC_COL0 256
+#define DX_ACC_COLS 128
+#define DX_MAX_NS 4
+
+struct CinDxParams {
+  const __nv_bfloat16* dyt;   // [R, Hs]
+  const __nv_bfloat16* x0t;   // [R, mP]
+  const __nv_bfloat16* xkt;   // rows with pitch xk_pitch, first Hp channels used
+  float* dxk;                 // [R, HpQ] fp32 (overwritten)
+  float* dx0;                 // [R, mP]  fp32 (accumulated)
+  int64_t R, xk_pitch;
+  int m, mP, Hp, HpQ, H, H_pad, Hs;
+  int64_t n_tiles;
+  int n_iters;
+  int n_hchunks;              // 64-wide chunks of the reduction dim h per field = ceil(H_pad / 64)
+  int ns;                     // W'' ring depth (slots of one h-chunk: [HpQ rows x 128 B])
+};
+
+struct __align__(8) CinDxBars {
+  uint64_t w_full[DX_MAX_NS], w_empty[DX_MAX_NS];
+  uint64_t a_full, a_empty;          // dY tile in TMEM (count 8 / 1)
+  uint64_t acc_full[2], acc_empty[2];
+  uint64_t x_full[2], x_empty[2];
+  uint32_t tmem_base;
+};
+
+// NQ = HpQ / 16
+template <int NQ>
+__global__ void __launch_bounds__(DX_THREADS, 1) cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmW, CinDxParams p) {
+  constexpr int HpQ = NQ * 16;
+  constexpr int HALF = HpQ / 2;                    // channels per row warp (multiple of 8)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t w_slot_bytes = (uint32_t)HpQ * 128;
+  uint8_t* sW = smem;                                                         // ns x [HpQ x 128 B]
+  const uint32_t x0_tile = (uint32_t)128 * p.mP * 2;
+  uint8_t* sX0 = sW + (size_t)p.ns * w_slot_bytes;                            // 2 x [128][mP] bf16
+  float* sDx0 = reinterpret_cast<float*>(sX0 + 2 * (size_t)x0_tile);          // [2 halves][128][mP] fp32 dX0 partials
+  CinDxBars* bars = reinterpret_cast<CinDxBars*>(sDx0 + 2 * 128 * p.mP);
+
+  const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
+  const uint16_t cmask = (uint16_t)((1u << csize) - 1);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < DX_MAX_NS; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], csize); }
+    mbar_init(&bars->a_full, 8);
+    mbar_init(&bars->a_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 8);
+      mbar_init(&bars->x_full[i], 1);   mbar_init(&bars->x_empty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, 512);
+  fence_before_sync();
+  __syncthreads();
+  if (csize > 1) cluster_sync_all();
+  fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+  auto tile_of = [&](int it) -> int64_t { return (int64_t)it * gridDim.x + blockIdx.x; };
+
+  if (warp == 0) {
+    // =============================== TMA: x0 tiles (one ahead) + W'' stream ===============================
+    if (lane == 0) {
+      prefetch_tmap(&tmW);
+      const int slice = HpQ / (int)csize;            // rows of a W'' slot loaded (and multicast) by this CTA
+      const int wr0 = (int)crank * slice;
+      int xit = 0;
+      auto load_x = [&](int64_t tile) {
+        const int buf = xit & 1;
+        if (xit >= 2) mbar_wait(&bars->x_empty[buf], ((xit >> 1) - 1) & 1);
+        const int64_t r0 = tile * 128;
+        const uint32_t nrows = (uint32_t)min((int64_t)128, p.R - r0);
+        mbar_arrive_expect_tx(&bars->x_full[buf], nrows * (uint32_t)(p.mP * 2));
+        bulk_load_1d(sX0 + (size_t)buf * x0_tile, p.x0t + r0 * p.mP, nrows * (uint32_t)(p.mP * 2), &bars->x_full[buf]);
+        ++xit;
+      };
+      uint32_t ws = 0, wphase = 1;
+      bool first_pass = true;
+      if (tile_of(0) < p.n_tiles) load_x(tile_of(0));
+      for (int it = 0; it < p.n_iters; ++it) {
+        if (it + 1 < p.n_iters && tile_of(it + 1) < p.n_tiles) load_x(tile_of(it + 1));
+        for (int j = 0; j < p.m; ++j) {
+          for (int c = 0; c < p.n_hchunks; ++c) {
+            if (!first_pass) mbar_wait(&bars->w_empty[ws], wphase);
+            mbar_arrive_expect_tx(&bars->w_full[ws], w_slot_bytes);
+            uint8_t* dst = sW + (size_t)ws * w_slot_bytes + (size_t)wr0 * 128;
+            if (csize > 1) tma_load_2d_mcast(dst, &tmW, c * 64, j * HpQ + wr0, &bars->w_full[ws], cmask);
+            else tma_load_2d(dst, &tmW, c * 64, j * HpQ + wr0, &bars->w_full[ws]);
+            if (++ws == (uint32_t)p.ns) { ws = 0; wphase ^= 1; first_pass = false; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer (warp-uniform loop, elected lane issues) ===============================
+    const uint32_t idesc = make_idesc_bf16(128, HpQ);
+    const uint64_t bdesc0 = make_desc_k_sw128(smem_u32(sW));
+    const uint32_t slot_desc_step = w_slot_bytes >> 4;
+    uint32_t ws = 0, wphase = 0;
+    uint64_t bdesc = bdesc0;
+    uint32_t jc = 0;            // fields processed so far (accumulator buffer = jc & 1)
+    int at = 0;
+    const int ksteps = p.H_pad / 16;
+    for (int it = 0; it < p.n_iters; ++it) {
+      const bool active = tile_of(it) < p.n_tiles;
+      if (active) {
+        mbar_wait(&bars->a_full, at & 1);
+        fence_after_sync();
+      }
+      for (int j = 0; j < p.m; ++j) {
+        const uint32_t ab = jc & 1;
+        if (active && jc >= 2) {
+          mbar_wait(&bars->acc_empty[ab], ((jc >> 1) - 1) & 1);
+          fence_after_sync();
+        }
+        int ks = 0;
+        for (int c = 0; c < p.n_hchunks; ++c) {
+          mbar_wait(&bars->w_full[ws], wphase);
+          fence_after_sync();
+          if (elect_one()) {
+            if (active) {
+              const uint32_t d_addr = tmem_base + DX_ACC_COL0 + ab * DX_ACC_COLS;
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                if (ks + k4 < ksteps) umma_ts(d_addr, tmem_base + (uint32_t)(ks + k4) * 8, bdesc + (uint64_t)(k4 * 2), idesc, (ks + k4) > 0 ? 1u : 0u);
+              }
+            }
+            if (csize > 1) umma_commit_mcast(&bars->w_empty[ws], cmask);
+            else umma_commit(&bars->w_empty[ws]);
+          }
+          __syncwarp();
+          ks += 4;
+          if (++ws == (uint32_t)p.ns) { ws = 0; wphase ^= 1; bdesc = bdesc0; }
+          else bdesc += slot_desc_step;
+        }
+        if (active) {
+          if (elect_one()) umma_commit(&bars->acc_full[ab]);
+          __syncwarp();
+          ++jc;
+        }
+      }
+      if (active) {
+        if (elect_one()) umma_commit(&bars->a_empty);     // all MMAs reading this tile's dY have been issued and will complete
+        __syncwarp();
+        ++at;
+      }
+    }
+  } else {
+    // =============================== row warps ===============================
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;              // 0: channels [0, HALF), 1: [HALF, HpQ)
+    const int rl = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint32_t jc = 0;
+    int at = 0;
+    for (int it = 0; it < p.n_iters; ++it) {
+      const int64_t tile = tile_of(it);
+      if (tile >= p.n_tiles) continue;
+      const int64_t row = tile * 128 + rl;
+      const bool valid = row < p.R;
+      // ---- stage this tile's dY rows into TMEM (A operand): this warp writes columns [half*H_pad/4 ...) of its lane quarter
+      if (at > 0) {
+        mbar_wait(&bars->a_empty, (at - 1) & 1);
+        fence_after_sync();
+      }
+      {
+        const int ncol = p.H_pad / 2;                // 32-bit columns of the A tile
+        const int c_beg = half == 0 ? 0 : ((ncol / 2 + 3) & ~3);
+        const int c_end = half == 0 ? ((ncol / 2 + 3) & ~3) : ncol;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(p.dyt + row * p.Hs);
+        for (int c = c_beg; c < c_end; c += 4) {
+          uint32_t v[4] = {0u, 0u, 0u, 0u};
+          if (valid && c * 2 < p.Hs) {               // Hs is a multiple of 8 -> whole 16-byte granules
+            const uint4 t = *reinterpret_cast<const uint4*>(src + c);
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+          }
+          tmem_st_x4(tmem_base + lane_addr + c, v);
+        }
+        tmem_wait_st();
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->a_full);
+      }
+      // ---- this row's operands
+      const int buf = at & 1;
+      mbar_wait(&bars->x_full[buf], (at >> 1) & 1);
+      const __nv_bfloat16* x0row = reinterpret_cast<const __nv_bfloat16*>(sX0 + (size_t)buf * x0_tile) + (size_t)rl * p.mP;
+      __nv_bfloat162 xk2[HALF / 2];
+      {
+        const __nv_bfloat16* xr = p.xkt + row * p.xk_pitch + half * HALF;
+#pragma unroll
+        for (int v8 = 0; v8 < HALF / 8; ++v8) {
+          uint4 t = make_uint4(0u, 0u, 0u, 0u);
+          if (valid && half * HALF + v8 * 8 < p.xk_pitch) t = *reinterpret_cast<const uint4*>(xr + v8 * 8);
+          xk2[v8 * 4 + 0] = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
+          xk2[v8 * 4 + 1] = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+          xk2[v8 * 4 + 2] = *reinterpret_cast<const __nv_bfloat162*>(&t.z);
+          xk2[v8 * 4 + 3] = *reinterpret_cast<const __nv_bfloat162*>(&t.w);
+        }
+      }
+      float dxk[HALF];
+#pragma unroll
+      for (int i = 0; i < HALF; ++i) dxk[i] = 0.f;
+      for (int j = 0; j < p.m; ++j, ++jc) {
+        const uint32_t ab = jc & 1;
+        const float x0v = __bfloat162float(x0row[j]);
+        mbar_wait(&bars->acc_full[ab], (jc >> 1) & 1);
+        fence_after_sync();
+        const uint32_t acc = tmem_base + lane_addr + DX_ACC_COL0 + ab * DX_ACC_COLS + half * HALF;
+        float dot = 0.f;
+#pragma unroll
+        for (int c0 = 0; c0 < HALF; c0 += 8) {
+          uint32_t v[8];
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                       : "r"(acc + c0)
+                       : "memory");
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            const float2 xf = __bfloat1622float2(xk2[(c0 + i) / 2]);
+            const float z0 = __uint_as_float(v[i]), z1 = __uint_as_float(v[i + 1]);
+            dxk[c0 + i] = fmaf(z0, x0v, dxk[c0 + i]);
+            dxk[c0 + i + 1] = fmaf(z1, x0v, dxk[c0 + i + 1]);
+            dot = fmaf(z0, xf.x, dot);
+            dot = fmaf(z1, xf.y, dot);
+          }
+        }
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->acc_empty[ab]);
+        // dX0[r, j] partial of this warp's channel half: parked in shared memory (plane = half), combined at tile end
+        sDx0[(half * 128 + rl) * p.mP + j] = dot;
+      }
+      // ---- tile outputs
+      if (valid) {
+        float* o = p.dxk + row * p.HpQ + half * HALF;
+#pragma unroll
+        for (int i = 0; i < HALF; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(dxk[i], dxk[i + 1], dxk[i + 2], dxk[i + 3]);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // both halves' dX0 partials are in shared memory
+      if (half == 0 && valid) {
+        float* g = p.dx0 + row * p.mP;
+        for (int j = 0; j < p.m; ++j) g[j] += sDx0[rl * p.mP + j] + sDx0[(128 + rl) * p.mP + j];
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // partial planes may be overwritten by the next tile
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->x_empty[buf]);
+      ++at;
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (csize > 1) cluster_sync_all();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// W fp32 [H, Hp*m] (k = i*m + j) -> W'' bf16 [m*HpQ rows (row = j*HpQ + i), HC cols (h), zero padded]
+__global__ void cin_prep_wt_kernel(const float* __restrict__ W, int H, int Hp, int m, int HpQ, int HC, __nv_bfloat16* __restrict__ Wt) {
+  int64_t total = (int64_t)m * HpQ * HC;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int h = (int)(e % HC);
+    int64_t r = e / HC;
+    int i = (int)(r % HpQ), j = (int)(r / HpQ);
+    float v = 0.f;
+    if (h < H && i < Hp) v = W[(int64_t)h * Hp * m + (int64_t)i * m + j];
+    Wt[e] = __float2bfloat16(v);
+  }
+}
+
+static int round_up_i(int a, int b) { return (a + b - 1) / b * b; }
+
+struct CinDxGeom {
+  int HpQ, H_pad, Hs, mP, HC, n_hchunks, ns;
+  size_t smem;
+};
+
+static int cin_dx_geom(int m, int Hp, int H, int D, CinDxGeom* g) {
+  if (!(D == 8 || D == 16 || D == 32 || D == 64 || D == 128) || Hp > 128 || H > 256 || m > XDFM_MAX_FIELDS) {
+    xdfm_set_error("cin_bwd_dx_tc: unsupported shape (D=%d in {8..128 pow2}, Hp=%d<=128, H=%d<=256, m=%d<=64)", D, Hp, H, m);
+    return XDFM_ERR_UNSUPPORTED;
+  }
+  g->HpQ = round_up_i(Hp, 16);
+  g->H_pad = round_up_i(H, 16);
+  g->Hs = round_up_i(H, 8);
+  g->mP = round_up_i(m, 8);
+  g->n_hchunks = (g->H_pad + 63) / 64;
+  g->HC = g->n_hchunks * 64;
+  size_t fixed = 2 * (size_t)128 * g->mP * 2 + 2 * (size_t)128 * g->mP * 4 + sizeof(CinDxBars) + 256;
+  size_t slot = (size_t)g->HpQ * 128;
+  int ns = (int)std::min<size_t>((227 * 1024 - fixed) / slot, DX_MAX_NS * 1);
+  ns = std::min(ns, DX_MAX_NS);
+  if (ns < 2) {
+    xdfm_set_error("cin_bwd_dx_tc: shared memory too small");
+    return XDFM_ERR_UNSUPPORTED;
+  }
+  g->ns = ns;
+  g->smem = fixed + (size_t)ns * slot;
+  return XDFM_OK;
+}
+
+extern "C" int64_t xdfm_cin_bwd_dx_tc_wt_elems(int m, int Hp, int H, int D) {
+  CinDxGeom g;
+  if (cin_dx_geom(m, Hp, H, D, &g) != XDFM_OK) return -1;
+  return (int64_t)m * g.HpQ * g.HC;
+}
+
+extern int g_cin_tc_cluster_shared;
+
+template <int NQ>
+static int launch_dx(const CUtensorMap& tmW, const CinDxParams& p, size_t smem, int blocks, int cluster, cudaStream_t st) {
+  XDFM_CUDA(cudaFuncSetAttribute(cin_bwd_dx_tc_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(DX_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  XDFM_CUDA(cudaLaunchKernelEx(&cfg, cin_bwd_dx_tc_kernel<NQ>, tmW, p));
+  XDFM_LAUNCH_CHECK();
+  return XDFM_OK;
+}
+
+// dyt [B*D, Hs] bf16; x0t [B*D, mP] bf16; xkt rows (pitch xk_pitch) bf16; W fp32 [H, Hp*m]; wt = bf16 scratch
+// [xdfm_cin_bwd_dx_tc_wt_elems]; dxk [B*D, HpQ] fp32 out (HpQ = Hp rounded up to 16); dx0 [B*D, mP] fp32 accumulated (+=).
+extern "C" int xdfm_cin_bwd_dx_tc(const void* dyt, const void* x0t, const void* xkt, int64_t xk_pitch, const float* W, void* wt,
+                                  int64_t B, int m, int Hp, int H, int D, float* dxk, float* dx0, void* stream) {
+  CinDxGeom g;
+  int rc = cin_dx_geom(m, Hp, H, D, &g);
+  if (rc) return rc;
+  if (B == 0) return XDFM_OK;
+  XDFM_CHECK_ARG(((uintptr_t)dyt % 16 == 0) && ((uintptr_t)x0t % 16 == 0) && ((uintptr_t)xkt % 16 == 0) && xk_pitch % 8 == 0 &&
+                     ((uintptr_t)dxk % 16 == 0),
+                 "cin_bwd_dx_tc: operands must be 16-byte aligned and xk_pitch a multiple of 8");
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    int64_t total = (int64_t)m * g.HpQ * g.HC;
+    int blocks = (int)std::min<int64_t>((int64_t)xdfm_num_sms() * 4, ceil_div64(total, 256));
+    cin_prep_wt_kernel<<<blocks, 256, 0, st>>>(W, H, Hp, m, g.HpQ, g.HC, (__nv_bfloat16*)wt);
+    XDFM_LAUNCH_CHECK();
+  }
+  int cluster = g_cin_tc_cluster_shared;
+  while (cluster > 1 && ((g.HpQ / 8) % cluster) != 0) cluster >>= 1;
+  CUtensorMap tmW;
+  rc = xdfm_make_tmap_bf16(&tmW, wt, (uint64_t)m * g.HpQ, (uint64_t)g.HC, (uint64_t)g.HC * 2, (uint32_t)(g.HpQ / cluster), 64, 1);
+  if (rc) return rc;
+  const int64_t R = B * (int64_t)D;
+  CinDxParams p;
+  p.dyt = (const __nv_bfloat16*)dyt; p.x0t = (const __nv_bfloat16*)x0t; p.xkt = (const __nv_bfloat16*)xkt; p.dxk = dxk; p.dx0 = dx0;
+  p.R = R; p.xk_pitch = xk_pitch; p.m = m; p.mP = g.mP; p.Hp = Hp; p.HpQ = g.HpQ; p.H = H; p.H_pad = g.H_pad; p.Hs = g.Hs;
+  p.n_tiles = ceil_div64(R, 128); p.n_hchunks = g.n_hchunks; p.ns = g.ns;
+  int sms = xdfm_num_sms();
+  int blocks = (int)std::min<int64_t>(ceil_div64(p.n_tiles, cluster) * cluster, (int64_t)(sms / cluster) * cluster);
+  blocks = std::max(blocks, cluster);
+  p.n_iters = (int)ceil_div64(p.n_tiles, blocks);
+  switch (g.HpQ / 16) {
+#define CASE_NQ(n) case n: return launch_dx<n>(tmW, p, g.smem, blocks, cluster, st);
+    CASE_NQ(1) CASE_NQ(2) CASE_NQ(3) CASE_NQ(4) CASE_NQ(5) CASE_NQ(6) CASE_NQ(7) CASE_NQ(8)
+#undef CASE_NQ
+  }
+  xdfm_set_error("cin_bwd_dx_tc: unreachable HpQ=%d", g.HpQ);
+  return XDFM_ERR_UNSUPPORTED;
+}

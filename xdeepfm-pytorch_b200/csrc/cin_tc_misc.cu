@@ -1,0 +1,98 @@
+// Elementwise / layout helpers of the tensor-core CIN path (row layout: one row per (sample, d), channels contiguous).
+#include "common.cuh"
+#include "../../include/xdfm.h"
+
+// dY[r, h] = act'(y[r,h]) * ( direct-path grad (channels [hdb, H)) + next-layer grad (channels [0, n_next)) ), bf16 row layout.
+// One thread = 8 consecutive channels of one row.
+__global__ void __launch_bounds__(256) cin_dy_rows_kernel(const __nv_bfloat16* __restrict__ yt, int64_t R, int D, int H, int Hs, int hdb,
+                                                          const float* __restrict__ dpooled, const float* __restrict__ dmaps, int fm_total,
+                                                          int col_off, const float* __restrict__ dnext, int64_t dnext_pitch, int n_next,
+                                                          int act, __nv_bfloat16* __restrict__ dyt) {
+  const int g8 = Hs / 8;
+  const int64_t total = R * g8;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / g8;
+    const int h0 = (int)(e - r * g8) * 8;
+    const int64_t b = r / D;
+    const int d = (int)(r - b * D);
+    const uint4 yv = *reinterpret_cast<const uint4*>(yt + r * Hs + h0);
+    const __nv_bfloat16* yb = reinterpret_cast<const __nv_bfloat16*>(&yv);
+    float g[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int h = h0 + i;
+      float v = 0.f;
+      if (h < H) {
+        if (h >= hdb) {
+          if (dpooled) v += dpooled[b * fm_total + col_off + (h - hdb)];
+          if (dmaps) v += dmaps[(b * fm_total + col_off + (h - hdb)) * (int64_t)D + d];
+        }
+        if (h < n_next && dnext) v += dnext[r * dnext_pitch + h];
+        if (act == XDFM_ACT_RELU && !(__bfloat162float(yb[i]) > 0.f)) v = 0.f;
+      }
+      g[i] = v;
+    }
+    uint4 o;
+    __nv_bfloat162 t0 = __floats2bfloat162_rn(g[0], g[1]), t1 = __floats2bfloat162_rn(g[2], g[3]);
+    __nv_bfloat162 t2 = __floats2bfloat162_rn(g[4], g[5]), t3 = __floats2bfloat162_rn(g[6], g[7]);
+    o.x = *reinterpret_cast<uint32_t*>(&t0); o.y = *reinterpret_cast<uint32_t*>(&t1);
+    o.z = *reinterpret_cast<uint32_t*>(&t2); o.w = *reinterpret_cast<uint32_t*>(&t3);
+    *reinterpret_cast<uint4*>(dyt + r * Hs + h0) = o;
+  }
+}
+
+extern "C" int xdfm_cin_dy_rows(const void* yt, int64_t B, int D, int H, int Hs, int direct_begin, const float* dpooled, const float* dmaps,
+                                int fm_total, int col_off, const float* dnext, int64_t dnext_pitch, int n_next, int act, void* dyt,
+                                void* stream) {
+  XDFM_CHECK_ARG(Hs % 8 == 0 && Hs >= H, "cin_dy_rows: Hs=%d must be a multiple of 8 and >= H=%d", Hs, H);
+  XDFM_CHECK_ARG(act == XDFM_ACT_RELU || act == XDFM_ACT_NONE, "cin_dy_rows: activation %d not supported on the bf16 path", act);
+  const int64_t R = B * (int64_t)D;
+  const int64_t total = R * (Hs / 8);
+  if (total == 0) return XDFM_OK;
+  int blocks = (int)std::min<int64_t>((int64_t)xdfm_num_sms() * 8, ceil_div64(total, 256));
+  cin_dy_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)yt, R, D, H, Hs, direct_begin, dpooled, dmaps, fm_total,
+                                                               col_off, dnext, dnext_pitch, n_next, act, (__nv_bfloat16*)dyt);
+  XDFM_LAUNCH_CHECK();
+  return XDFM_OK;
+}
+
+// rows [R, CP] fp32 (row layout) -> [B, C, D] fp32 (reference layout), optionally accumulating: out (+)= in
+__global__ void from_rows_f32_kernel(const float* __restrict__ xt, int64_t B, int C, int D, int CP, float* __restrict__ x, int accumulate) {
+  int64_t total = B * (int64_t)C * D;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int d = (int)(e % D);
+    int64_t bc = e / D;
+    int c = (int)(bc % C);
+    int64_t b = bc / C;
+    float v = xt[(b * D + d) * (int64_t)CP + c];
+    x[e] = accumulate ? x[e] + v : v;
+  }
+}
+
+extern "C" int xdfm_from_rows_f32(const float* xt, int64_t B, int C, int D, int CP, float* x, int accumulate, void* stream) {
+  int64_t total = B * (int64_t)C * D;
+  if (total == 0) return XDFM_OK;
+  int blocks = (int)std::min<int64_t>((int64_t)xdfm_num_sms() * 8, ceil_div64(total, 256));
+  from_rows_f32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(xt, B, C, D, CP, x, accumulate);
+  XDFM_LAUNCH_CHECK();
+  return XDFM_OK;
+}
+
+// a[r, c] += b[r, c] for c < C on two row-layout fp32 matrices with different pitches (layer 0: dX0 += dXk)
+__global__ void add_rows_f32_kernel(float* __restrict__ a, int64_t pa, const float* __restrict__ b, int64_t pb, int64_t R, int C) {
+  int64_t total = R * C;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = e / C;
+    int c = (int)(e - r * C);
+    a[r * pa + c] += b[r * pb + c];
+  }
+}
+
+extern "C" int xdfm_add_rows_f32(float* a, int64_t pitch_a, const float* b, int64_t pitch_b, int64_t R, int C, void* stream) {
+  int64_t total = R * C;
+  if (total == 0) return XDFM_OK;
+  int blocks = (int)std::min<int64_t>((int64_t)xdfm_num_sms() * 8, ceil_div64(total, 256));
+  add_rows_f32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, pitch_a, b, pitch_b, R, C);
+  XDFM_LAUNCH_CHECK();
+  return XDFM_OK;
+}
