@@ -167,6 +167,14 @@ int64_t xdfm_cin_bwd_dx_tc_wt_elems(int m, int Hp, int H, int D);
 int xdfm_cin_bwd_dx_tc(const void* dyt, const void* x0t, const void* xkt, int64_t xk_pitch, const float* W, void* wt, int64_t B, int m,
                        int Hp, int H, int D, float* dxk, float* dx0, void* stream);
 
+/* CIN weight gradient on the tensor cores.  Operands are CHANNEL-MAJOR bf16 copies (xdfm_rows_to_cols_bf16: rows [R, pitch]
+ * -> [CP, R], rows >= C zero): dyT [H_pad, R], xkT [HpQ, R], x0T [mP, R] with H_pad/HpQ = H/Hp rounded up to 16, mP = m rounded
+ * up to 8, R = B*D.  dW fp32 [H, Hp*m] (reference layout) and db [H] are overwritten; deterministic two-stage reduction. */
+int xdfm_rows_to_cols_bf16(const void* src, int64_t pitch, int64_t R, int C, int CP, void* dst, void* stream);
+int64_t xdfm_cin_bwd_dw_tc_workspace_bytes(int64_t B, int m, int Hp, int H, int D);
+int xdfm_cin_bwd_dw_tc(const void* dyT, const void* xkT, const void* x0T, int64_t B, int m, int Hp, int H, int D, float* dW, float* db,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- tcgen05 self-test (diagnostic): D[128,N] = A[128,K] * B[N,K]^T, bf16 in / fp32 out, one CTA.
  * mode 0: A via TMA + shared-memory descriptor (SS); mode 1: A stored to TMEM by the threads (TS, the CIN operand path). */
 int xdfm_tc_selftest_gemm(const void* A, const void* Bm, int N, int K, int mode, float* out, void* stream);

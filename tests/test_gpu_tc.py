@@ -208,3 +208,61 @@ def test_cin_dy_rows():
     got = from_rows(dyt, B, H, D).float().cpu()
     assert_close(got, ref.to(torch.bfloat16).float(), 0, 0, "dy rows")
     assert float(dyt[:, H:].float().abs().max()) == 0.0
+
+
+def to_cols(rows, C, CP):
+    from deepctr import _native as Nv
+    R = rows.shape[0]
+    out = torch.full((CP, R), float("nan"), dtype=torch.bfloat16, device=DEV)
+    Nv.check(Nv.lib().xdfm_rows_to_cols_bf16(Nv.ptr(rows), rows.shape[1], R, C, CP, Nv.ptr(out), Nv.stream_ptr()))
+    return out
+
+
+DW_CASES = [
+    # B, m, D, H, Hp
+    (8, 2, 16, 16, 2),
+    (19, 26, 16, 200, 100),
+    (300, 26, 16, 200, 26),
+    (33, 26, 8, 128, 128),
+    (20, 22, 32, 256, 128),
+    (9, 25, 64, 256, 26),
+    (2500, 12, 16, 40, 20),
+]
+
+
+@pytest.mark.parametrize("cluster", [1, 2])
+@pytest.mark.parametrize("case", DW_CASES, ids=[str(c) for c in DW_CASES])
+def test_cin_tc_backward_dw_matches_emulation(case, cluster):
+    from deepctr import _native as Nv
+    L = Nv.lib()
+    B, m, D, H, Hp = case
+    g = torch.Generator().manual_seed(sum(case) + 2)
+    r8 = lambda v: (v + 7) // 8 * 8
+    r16 = lambda v: (v + 15) // 16 * 16
+    x0 = torch.randn(B, m, D, generator=g) * 0.5
+    Hprev = Hp if Hp == m else 2 * Hp
+    xk_full = x0 if Hp == m else torch.randn(B, Hprev, D, generator=g) * 0.5
+    dy = torch.randn(B, H, D, generator=g)
+    x0t = to_rows(x0.to(DEV), r8(m))
+    xkt = x0t if Hp == m else to_rows(xk_full.to(DEV), r8(Hprev))
+    dyt = to_rows(dy.to(DEV), r8(H))
+    x0T, xkT, dyT = to_cols(x0t, m, r8(m)), to_cols(xkt, Hp, r16(Hp)), to_cols(dyt, H, r16(H))
+    assert float(dyT[H:].float().abs().sum()) == 0.0 and float(xkT[Hp:].float().abs().sum()) == 0.0
+    dW = torch.full((H, Hp * m), float("nan"), device=DEV)
+    db = torch.full((H,), float("nan"), device=DEV)
+    L.xdfm_cin_tc_set_cluster(cluster)
+    try:
+        nb = L.xdfm_cin_bwd_dw_tc_workspace_bytes(B, m, Hp, H, D)
+        assert nb > 0, L.xdfm_last_error()
+        ws = torch.empty(nb, dtype=torch.uint8, device=DEV)
+        Nv.check(L.xdfm_cin_bwd_dw_tc(Nv.ptr(dyT), Nv.ptr(xkT), Nv.ptr(x0T), B, m, Hp, H, D, Nv.ptr(dW), Nv.ptr(db), Nv.ptr(ws), nb,
+                                      Nv.stream_ptr()))
+        torch.cuda.synchronize()
+    finally:
+        L.xdfm_cin_tc_set_cluster(2)
+    bf = lambda t: t.to(torch.bfloat16).double()
+    z = (bf(xk_full[:, :Hp])[:, :, None, :].float() * bf(x0)[:, None, :, :].float()).to(torch.bfloat16).double()    # [B,Hp,m,D]
+    ref_dW = torch.einsum("bhd,bijd->hij", bf(dy), z).reshape(H, Hp * m)
+    ref_db = bf(dy).sum(dim=(0, 2))
+    assert_close(dW, ref_dW, 1e-3, 1e-3 * ref_dW.abs().max().item(), "dW")
+    assert_close(db, ref_db, 1e-4, 1e-4 * ref_db.abs().max().item(), "db")
