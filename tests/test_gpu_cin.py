@@ -132,3 +132,59 @@ def test_cin_rejects_bad_rank():
         CIN(3, (3, 2), split_half=True)
     with pytest.raises(ValueError):
         CIN(3, ())
+
+
+TC_MODEL_CASES = [
+    (33, 5, 8, (16, 8), True, "relu", True),
+    (17, 5, 8, (6, 5, 4), False, "relu", True),
+    (12, 5, 8, (16, 8), True, "relu", False),
+    (64, 26, 8, (256, 128), True, "relu", True),
+    (40, 26, 16, (200, 200, 200), True, "relu", True),
+    (16, 22, 32, (256, 256), True, "relu", True),
+    (9, 6, 16, (8, 6, 3), True, "linear", True),
+]
+
+
+@pytest.mark.parametrize("case", TC_MODEL_CASES, ids=[str(c[:5]) for c in TC_MODEL_CASES])
+def test_cin_bf16_tensor_core_path_matches_oracle(case):
+    """bf16 tensor-core CIN (forward + backward through autograd) vs the fp64 oracle on bf16-rounded x0 / W.
+    Tolerance: bf16 products and bf16 layer outputs -> 2e-2 of the tensor's scale (stated bf16 tolerance)."""
+    from deepctr import ops
+    B, m, D, layers, split_half, act, pool = case
+    x0, Ws, bs, g = _rand_case(B, m, D, layers, split_half, seed=B + m + D + 1)
+    x0 = x0.to(torch.bfloat16).float()
+    Ws = [W.to(torch.bfloat16).float() for W in Ws]
+    fm = (sum(layers[:-1]) // 2 + layers[-1]) if split_half else sum(layers)
+    gout = torch.randn((B, fm) if pool else (B, fm, D), generator=g)
+    cfg = ops.CINConfig(m, [W.shape[0] for W in Ws], split_half, act, pool=pool, impl="bf16")
+    x = x0.to(DEV).requires_grad_(True)
+    wb = []
+    for W, b in zip(Ws, bs):
+        wb += [W.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)]
+    out = ops.cin_apply(cfg, x, *wb)
+    out.backward(gout.to(DEV))
+    masks = None
+    if act == "relu":
+        # active-set chosen by the bf16 kernels (from the saved bf16 layer outputs)
+        ctx_masks = []
+        xk_ref = None
+        pres = O.cin_preactivations(x0.double(), [W.double() for W in Ws], [b.double() for b in bs], split_half, act)
+        # recompute the kernel's outputs layer by layer through the C ABI to get its masks
+        from tests.test_gpu_tc import tc_layer, to_rows
+        x0t = to_rows(x0.to(DEV), (m + 7) // 8 * 8)
+        xkt = x0t
+        for k, H in enumerate(cfg.layer_size):
+            y, yt, _, _ = tc_layer(x0t, xkt, Ws[k].to(DEV).reshape(H, -1).contiguous(), bs[k].to(DEV), B, m, cfg.Hp[k], H, D, act,
+                                   cfg.direct_begin[k], cfg.fm, cfg.col_off[k])
+            ctx_masks.append((y.float() > 0).cpu())
+            xkt = yt
+        masks = ctx_masks
+        for mk, pre in zip(masks, pres):
+            flipped = mk != (pre > 0)
+            assert flipped.double().mean().item() < 2e-2
+    ro, rdx, rdwb = _run_oracle(x0, Ws, bs, split_half, act, pool, gout, masks)
+    tol = 2e-2
+    assert_close(out, ro, tol, tol * max(ro.abs().max().item(), 1.0), "cin out (bf16 path)")
+    assert_close(x.grad, rdx, tol, tol * rdx.abs().max().item(), "cin dx0 (bf16 path)")
+    for i, (a, b) in enumerate(zip([t.grad for t in wb], rdwb)):
+        assert_close(a, b.reshape(a.shape), tol, tol * b.abs().max().item(), "cin grad %d (bf16 path)" % i)

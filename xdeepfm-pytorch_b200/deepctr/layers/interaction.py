@@ -1,4 +1,6 @@
 """Compressed Interaction Network (reference: deepctr/layers/interaction.py:159-248) on the fused CIN kernels."""
+import os
+
 import torch.nn as nn
 
 from .. import ops
@@ -42,10 +44,22 @@ class CIN(nn.Module):
             raise NotImplementedError("CIN activation '%s' is not fused in this build (relu / linear / sigmoid)" % activation)
         self.activation = activation_layer(activation)
         _build_cin_convs(self, field_size, layer_size, split_half)
-        self._cfg = ops.CINConfig(field_size, layer_size, split_half, act, pool=True)
+        self._cfg = ops.CINConfig(field_size, layer_size, split_half, act, pool=True,
+                                  impl=os.environ.get("XDFM_CIN_PRECISION", "fp32"))
         self.to(device)
+
+    @property
+    def precision(self):
+        """'fp32' (CUDA-core kernels, the reference's precision; default) or 'bf16' (tcgen05 tensor-core kernels, fp32 accumulate)."""
+        return self._cfg.impl
+
+    @precision.setter
+    def precision(self, value):
+        if value not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self._cfg.impl = value
 
     def forward(self, inputs):
         if len(inputs.shape) != 3:
             raise ValueError("Unexpected inputs dimensions %d, expect to be 3 dimensions" % (len(inputs.shape)))
-        return ops.CINFunction.apply(self._cfg, inputs, *_cin_wb(self))
+        return ops.cin_apply(self._cfg, inputs, *_cin_wb(self))

@@ -329,6 +329,115 @@ class CINFunction(torch.autograd.Function):
         return (None, dx0) + tuple(grads)
 
 
+def _r8(v):
+    return (v + 7) // 8 * 8
+
+
+def _r16(v):
+    return (v + 15) // 16 * 16
+
+
+class CINFunctionTC(torch.autograd.Function):
+    """CIN on the tensor cores (bf16 operands, fp32 accumulation): same signature as CINFunction.
+
+    Activations live in the row layout of csrc/cin_tc.cu ([B*D, channels] bf16); the forward keeps x0t and every layer's yt for
+    the backward, which runs per layer: dy (elementwise) -> dW (tcgen05, channel-major operands) -> dX (tcgen05)."""
+
+    @staticmethod
+    def forward(ctx, cfg, x0, *wb):
+        require_cuda(x0, "CIN")
+        x0 = _f32c(x0)
+        B, m, D = x0.shape
+        dev = x0.device
+        L = N.lib()
+        mP = _r8(m)
+        out = torch.empty((B, cfg.fm) if cfg.pool else (B, cfg.fm, D), dtype=torch.float32, device=dev)
+        x0t = torch.empty((B * D, mP), dtype=torch.bfloat16, device=dev)
+        with timed("cin_layout"):
+            N.check(L.xdfm_to_rows_bf16(N.ptr(x0), B, m, D, mP, N.ptr(x0t), N.stream_ptr()))
+        yts = []
+        xkt = x0t
+        for k, H in enumerate(cfg.layer_size):
+            W = _f32c(wb[2 * k]).view(H, -1)
+            b = _f32c(wb[2 * k + 1])
+            nw = L.xdfm_cin_tc_wprime_elems(m, cfg.Hp[k], H, D)
+            if nw < 0:
+                raise RuntimeError("libxdfm: " + L.xdfm_last_error().decode())
+            wprime = workspace("cin_wprime", nw * 2, dev)
+            yt = torch.empty((B * D, _r8(H)), dtype=torch.bfloat16, device=dev)
+            with timed("cin_fwd"):
+                N.check(L.xdfm_cin_fwd_tc(N.ptr(x0t), N.ptr(xkt), xkt.shape[1], N.ptr(W), N.ptr(b), N.ptr(wprime), B, m, cfg.Hp[k], H,
+                                          D, cfg.act, N.ptr(yt), cfg.direct_begin[k], N.ptr(out) if cfg.pool else None,
+                                          None if cfg.pool else N.ptr(out), cfg.fm, cfg.col_off[k], N.stream_ptr()))
+            yts.append(yt)
+            xkt = yt
+        ctx.cfg, ctx.x0t, ctx.yts, ctx.wb, ctx.shape = cfg, x0t, yts, wb, (B, m, D)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        cfg, x0t, yts, wb = ctx.cfg, ctx.x0t, ctx.yts, ctx.wb
+        B, m, D = ctx.shape
+        dout = _f32c(dout)
+        dev = x0t.device
+        L = N.lib()
+        R, mP = B * D, _r8(m)
+        st = N.stream_ptr()
+        x0T = torch.empty((mP, R), dtype=torch.bfloat16, device=dev)
+        with timed("cin_layout"):
+            N.check(L.xdfm_rows_to_cols_bf16(N.ptr(x0t), mP, R, m, mP, N.ptr(x0T), st))
+        dx0_rows = torch.zeros((R, mP), dtype=torch.float32, device=dev)
+        grads = [None] * len(wb)
+        dnext, dnext_pitch = None, 0
+        for k in range(len(cfg.layer_size) - 1, -1, -1):
+            H, Hp = cfg.layer_size[k], cfg.Hp[k]
+            Hs, H_pad, HpQ = _r8(H), _r16(H), _r16(Hp)
+            yt = yts[k]
+            xkt = x0t if k == 0 else yts[k - 1]
+            dyt = torch.empty_like(yt)
+            dyT = torch.empty((H_pad, R), dtype=torch.bfloat16, device=dev)
+            xkT = torch.empty((HpQ, R), dtype=torch.bfloat16, device=dev)
+            with timed("cin_layout"):
+                N.check(L.xdfm_cin_dy_rows(N.ptr(yt), B, D, H, Hs, cfg.direct_begin[k], N.ptr(dout) if cfg.pool else None,
+                                           None if cfg.pool else N.ptr(dout), cfg.fm, cfg.col_off[k], N.ptr(dnext), dnext_pitch,
+                                           cfg.n_next[k], cfg.act, N.ptr(dyt), st))
+                N.check(L.xdfm_rows_to_cols_bf16(N.ptr(dyt), Hs, R, H, H_pad, N.ptr(dyT), st))
+                N.check(L.xdfm_rows_to_cols_bf16(N.ptr(xkt), xkt.shape[1], R, Hp, HpQ, N.ptr(xkT), st))
+            W = _f32c(wb[2 * k]).view(H, -1)
+            dW = torch.empty_like(W)
+            db = torch.empty(H, dtype=torch.float32, device=dev)
+            nb = L.xdfm_cin_bwd_dw_tc_workspace_bytes(B, m, Hp, H, D)
+            if nb < 0:
+                raise RuntimeError("libxdfm: " + L.xdfm_last_error().decode())
+            ws = workspace("cin_dw_part", nb, dev)
+            with timed("cin_bwd"):
+                N.check(L.xdfm_cin_bwd_dw_tc(N.ptr(dyT), N.ptr(xkT), N.ptr(x0T), B, m, Hp, H, D, N.ptr(dW), N.ptr(db), N.ptr(ws),
+                                             ws.numel(), st))
+            nwt = L.xdfm_cin_bwd_dx_tc_wt_elems(m, Hp, H, D)
+            wt = workspace("cin_wt", nwt * 2, dev)
+            dxk = torch.empty((R, HpQ), dtype=torch.float32, device=dev)
+            with timed("cin_bwd"):
+                N.check(L.xdfm_cin_bwd_dx_tc(N.ptr(dyt), N.ptr(x0t), N.ptr(xkt), xkt.shape[1], N.ptr(W), N.ptr(wt), B, m, Hp, H, D,
+                                             N.ptr(dxk), N.ptr(dx0_rows), st))
+            grads[2 * k] = dW.view(wb[2 * k].shape)
+            grads[2 * k + 1] = db
+            dnext, dnext_pitch = dxk, HpQ
+        dx0 = torch.empty((B, m, D), dtype=torch.float32, device=dev)
+        with timed("cin_layout"):
+            N.check(L.xdfm_add_rows_f32(N.ptr(dx0_rows), mP, N.ptr(dnext), dnext_pitch, R, m, st))   # layer 0: X^{k-1} is X^0 itself
+            N.check(L.xdfm_from_rows_f32(N.ptr(dx0_rows), B, m, D, mP, N.ptr(dx0), 0, st))
+        return (None, dx0) + tuple(grads)
+
+
+def cin_apply(cfg, x0, *wb):
+    """Dispatch on the configured precision: 'fp32' = CUDA-core kernels (reference precision), 'bf16' = tcgen05 kernels."""
+    if cfg.impl == "bf16":
+        return CINFunctionTC.apply(cfg, x0, *wb)
+    if cfg.impl != "fp32":
+        raise ValueError("cin precision must be 'fp32' or 'bf16', got %r" % (cfg.impl,))
+    return CINFunction.apply(cfg, x0, *wb)
+
+
 # ------------------------------------------------------------------------------------------------
 # dense layers
 # ------------------------------------------------------------------------------------------------
