@@ -198,7 +198,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--cin-impl", default="fp32")
+    ap.add_argument("--cin-impl", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--ref-batch", type=int, default=1024)
     ap.add_argument("--ref-vocab-cap", type=int, default=100000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -223,6 +223,7 @@ def main():
     model = build_product_model(spec, dev)
     # reference initialisation (init_std=1e-4 embeddings, default-init CIN) is what a user trains from
     model.compile("adam", "binary_crossentropy")
+    model.cin.precision = args.cin_impl
     if world > 1:
         raise NotImplementedError("multi-GPU bench arm lands with deepctr.distributed")
     n_pool = 4

@@ -445,8 +445,9 @@ def gemm(transA, transB, M, Nn, K, A, lda, Bm, ldb, C, ldc, bias=None, act=0, ac
     L = N.lib()
     nb = L.xdfm_gemm_workspace_bytes(M, Nn, K)
     ws = workspace("gemm", nb, C.device) if nb > 0 else None
-    N.check(L.xdfm_gemm_f32(int(transA), int(transB), M, Nn, K, N.ptr(A), lda, N.ptr(Bm), ldb, N.ptr(C), ldc, N.ptr(bias), act,
-                            int(accumulate), N.ptr(ws), 0 if ws is None else ws.numel(), N.stream_ptr()))
+    with timed("gemm"):
+        N.check(L.xdfm_gemm_f32(int(transA), int(transB), M, Nn, K, N.ptr(A), lda, N.ptr(Bm), ldb, N.ptr(C), ldc, N.ptr(bias), act,
+                                int(accumulate), N.ptr(ws), 0 if ws is None else ws.numel(), N.stream_ptr()))
 
 
 class LinearAct(torch.autograd.Function):
