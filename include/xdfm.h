@@ -175,6 +175,37 @@ int64_t xdfm_cin_bwd_dw_tc_workspace_bytes(int64_t B, int m, int Hp, int H, int 
 int xdfm_cin_bwd_dw_tc(const void* dyT, const void* xkT, const void* x0T, int64_t B, int m, int Hp, int H, int D, float* dW, float* db,
                        void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- single-node multi-GPU: row-sharded tables over NVLink peer memory (no reference equivalent: the reference replicates whole
+ * tables under nn.DataParallel, deepctr/models/basemodel.py:206-209, deepctr/inputs.py:167-180).
+ * Global row r of a table lives on rank r % G at local row r / G; a rank keeps its shards of all tables of a set in ONE buffer
+ * [rows_g, width]; feature f of rank g starts at local row feat_base[g*m + f] of buffer g.
+ * xdfm_ipc_*: cudaMalloc'ed (zero-filled) memory that other processes of the node can map (cudaIpc handles are 64 bytes). */
+int xdfm_ipc_alloc(int64_t bytes, void** dptr);
+int xdfm_ipc_free(void* dptr);
+int xdfm_ipc_export(void* dptr, void* handle64);
+int xdfm_ipc_open(const void* handle64, void** dptr);
+int xdfm_ipc_close(void* dptr);
+/* forward: out_emb[b,f,:] = emb_shards[id % G][feat_base[(id % G)*m + f] + id / G, :], out_lin as xdfm_embed_gather.
+ * emb_shards_dev / lin_shards_dev: DEVICE arrays [G] of (peer-mapped) buffer pointers; feat_base_dev: DEVICE int64 [G*m];
+ * vocab: HOST [m].  Either output may be NULL. */
+int xdfm_embed_gather_sharded(const float* const* emb_shards_dev, const float* const* lin_shards_dev, const int64_t* feat_base_dev,
+                              const int32_t* vocab, const int32_t* ids, int64_t B, int m, int D, int G, float* out_emb,
+                              const float* dense, int nd, const float* dense_w, float* out_lin, void* stream);
+/* backward, batch side: keys = owner*key_stride + local row, sorted owner-major -> run-length segments (outputs as
+ * xdfm_embed_bwd_segments) + owner_ranges [G+1]: rank g's segments are [owner_ranges[g], owner_ranges[g+1]). */
+int64_t xdfm_shard_workspace_bytes(int64_t n_keys);
+int xdfm_shard_segments(const int32_t* ids, int64_t B, int m, int G, uint32_t key_stride, const int64_t* feat_base_dev,
+                        const int32_t* vocab, void* workspace, int64_t workspace_bytes, uint32_t* uniq_keys, int32_t* seg_offsets,
+                        int32_t* sorted_pos, int32_t* num_segments, int32_t* owner_ranges, void* stream);
+/* backward, owner side: pull this rank's ranges (keys, row sums [.,D], first-order sums [.]) from every peer's exchange buffers
+ * (HOST arrays [G] of peer-mapped device pointers), concatenate them in rank order into rows / rows_lin ([n_cap, D] / [n_cap]),
+ * stable-sort + run-length encode the local keys: uniq_keys (local rows), seg_offsets [n_cap+1], sorted_pos [n_cap],
+ * num_segments.  n_cap = capacity (sum over peers of their batch keys); workspace of xdfm_shard_workspace_bytes(n_cap). */
+int xdfm_shard_pull_segments(const void* const* peer_keys, const void* const* peer_gsum, const void* const* peer_gsum_lin,
+                             const void* const* peer_ranges, int G, int rank, uint32_t key_stride, int D, int64_t n_cap,
+                             void* workspace, int64_t workspace_bytes, float* rows, float* rows_lin, uint32_t* uniq_keys,
+                             int32_t* seg_offsets, int32_t* sorted_pos, int32_t* num_segments, void* stream);
+
 /* ---- tcgen05 self-test (diagnostic): D[128,N] = A[128,K] * B[N,K]^T, bf16 in / fp32 out, one CTA.
  * mode 0: A via TMA + shared-memory descriptor (SS); mode 1: A stored to TMEM by the threads (TS, the CIN operand path). */
 int xdfm_tc_selftest_gemm(const void* A, const void* Bm, int N, int K, int mode, float* out, void* stream);

@@ -62,6 +62,16 @@ _SIGS = {
     "xdfm_cin_bwd_dw_tc_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int, c_int]),
     "xdfm_cin_bwd_dw_tc": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, c_int64, _P]),
     "xdfm_tc_selftest_gemm": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
+    "xdfm_ipc_alloc": (c_int, [c_int64, POINTER(_P)]),
+    "xdfm_ipc_free": (c_int, [_P]),
+    "xdfm_ipc_export": (c_int, [_P, _P]),
+    "xdfm_ipc_open": (c_int, [_P, POINTER(_P)]),
+    "xdfm_ipc_close": (c_int, [_P]),
+    "xdfm_embed_gather_sharded": (c_int, [_P, _P, _P, POINTER(c_int32), _P, c_int64, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P]),
+    "xdfm_shard_workspace_bytes": (c_int64, [c_int64]),
+    "xdfm_shard_segments": (c_int, [_P, c_int64, c_int, c_int, c_uint32, _P, POINTER(c_int32), _P, c_int64, _P, _P, _P, _P, _P, _P]),
+    "xdfm_shard_pull_segments": (c_int, [POINTER(_P), POINTER(_P), POINTER(_P), POINTER(_P), c_int, c_int, c_uint32, c_int, c_int64,
+                                         _P, c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "xdfm_opt_tick": (c_int, [_P, POINTER(OptCfg), _P]),
     "xdfm_flat_opt": (c_int, [POINTER(OptCfg), _P, c_int64, _P, _P, _P, _P, _P, c_float, _P, _P]),
     "xdfm_rows_opt": (c_int, [POINTER(OptCfg), _P, POINTER(_P), POINTER(_P), POINTER(_P), POINTER(c_int64), c_int, c_int, _P, _P, _P,

@@ -137,6 +137,13 @@ class ModelCheckpoint(Callback):
         self.monitor_op, self.best = _monitor_direction(monitor, mode)
 
     def _save(self, path):
+        dist_ctx = getattr(self.model, "_dist", None)
+        if dist_ctx is not None:
+            # row-sharded tables: state_dict() is a collective that re-assembles the reference key layout; rank 0 writes
+            sd = self.model.state_dict()
+            if dist_ctx.rank == 0:
+                torch.save(sd, path)
+            return
         torch.save(self.model.state_dict() if self.save_weights_only else self.model, path)
 
     def on_epoch_end(self, epoch, logs=None):

@@ -140,6 +140,8 @@ class BaseModel(nn.Module):
         self.history = History()
         self.stop_training = False
         self.sparse_embedding_update = False   # True: update only rows touched by the batch (NOT reference semantics)
+        self._dist = None                      # deepctr.distributed.DistContext after distribute()
+        self._optimizer_spec = None
 
     @staticmethod
     def _selector(idx, n):
@@ -161,12 +163,21 @@ class BaseModel(nn.Module):
     def embed(self, ids_all):
         """Fused multi-table gather -> [B, m, D] for the deep part's sparse features."""
         ids = self._select(ids_all, self._dnn_sparse_sel)
+        if self._dist is not None:
+            from ..distributed import ShardedGather
+            sh = self._dist.sharded
+            return ShardedGather.apply(sh, ids, sh.anchor)
         tables = [emb.weight for emb in self.embedding_dict.values()]
         return ops.SparseGather.apply(self._emb_plan, self._seg_cache, ids, *tables)
 
     def linear_logit(self, ids_all, dense_all):
         ids = self._select(ids_all, self._lin_sparse_sel)
         dense = self._select(dense_all, self._lin_dense_sel)
+        if self._dist is not None:
+            from ..distributed import ShardedLinearTerm
+            sh = self._dist.sharded
+            has_w = len(self.linear_model.dense_feature_columns) > 0
+            return ShardedLinearTerm.apply(sh, ids, dense if has_w else None, self.linear_model.weight if has_w else None, sh.anchor)
         return self.linear_model.forward_ids(ids, dense, cache=self._seg_cache)
 
     def dnn_dense(self, dense_all):
@@ -251,6 +262,7 @@ class BaseModel(nn.Module):
     # ------------------------------------------------------------------------------------------
     def compile(self, optimizer, loss=None, metrics=None):
         self.metrics_names = ["loss"]
+        self._optimizer_spec = optimizer
         self.optim = self._get_optim(optimizer)
         self.loss_func = self._get_loss_func(loss)
         self._loss_name = loss if isinstance(loss, str) else None
@@ -259,6 +271,8 @@ class BaseModel(nn.Module):
     def _table_sets(self):
         l2map, _ = self._l2_map()
         sets = []
+        if self._dist is not None:
+            return sets                 # tables are row-sharded: the optimizer updates them through self._dist.sharded
         emb_params = [e.weight for e in self.embedding_dict.values()]
         if self._emb_plan is not None:
             sets.append(TableSet(self._emb_plan, emb_params, l2map.get(id(emb_params[0]), 0.0)))
@@ -274,9 +288,50 @@ class BaseModel(nn.Module):
             raise NotImplementedError
         sets = self._table_sets()
         table_ids = set(id(p) for ts in sets for p in ts.params)
-        dense_named = [(n, p) for n, p in self.named_parameters() if id(p) not in table_ids]
         l2map, _ = self._l2_map()
-        return FusedOptimizer(optimizer, dense_named, sets, l2map)
+        l2_sharded = (0.0, 0.0)
+        if self._dist is not None:
+            emb_p = [e.weight for e in self.embedding_dict.values()]
+            lin_p = [e.weight for e in self.linear_model.embedding_dict.values()]
+            table_ids = set(id(p) for p in emb_p + lin_p)
+            l2_sharded = (l2map.get(id(emb_p[0]), 0.0), l2map.get(id(lin_p[0]), 0.0))
+        dense_named = [(n, p) for n, p in self.named_parameters() if id(p) not in table_ids]
+        return FusedOptimizer(optimizer, dense_named, sets, l2map, dist_ctx=self._dist, l2_sharded=l2_sharded)
+
+    # ------------------------------------------------------------------------------------------
+    # multi-GPU (replaces nn.DataParallel, basemodel.py:206-209): one process per GPU, see deepctr/distributed.py
+    # ------------------------------------------------------------------------------------------
+    def distribute(self, group=None, max_batch=None):
+        """Collective.  Row-shard the embedding / first-order tables over the ranks of `group` (NVLink peer memory) and make
+        the dense parameters data-parallel (rank 0's values are broadcast).  `max_batch` = largest per-GPU batch."""
+        from .. import distributed
+        if self._dist is not None:
+            raise RuntimeError("distribute() was already called on this model")
+        distributed.attach(self, group, max_batch)
+        if self._optimizer_spec is not None:
+            self.optim = self._get_optim(self._optimizer_spec)     # re-bind the optimizer to the sharded tables
+        return self
+
+    def state_dict(self, *args, **kwargs):
+        """Reference key layout.  With row-sharded tables this is a COLLECTIVE: every rank must call it; the
+        full tables are re-assembled from the shards (save on rank 0 only)."""
+        sd = super().state_dict(*args, **kwargs)
+        if self._dist is not None:
+            from ..distributed import gather_tables
+            prefix = kwargs.get("prefix", args[1] if len(args) > 1 else "")
+            for k, v in gather_tables(self).items():
+                sd[prefix + k] = v
+        return sd
+
+    def load_state_dict(self, state_dict, strict=True, **kwargs):
+        if self._dist is None:
+            return super().load_state_dict(state_dict, strict=strict, **kwargs)
+        from ..distributed import scatter_tables
+        used = set(scatter_tables(self, state_dict))
+        rest = {k: v for k, v in state_dict.items() if k not in used}
+        for k in used:                       # placeholders keep the module's own (empty) table parameters untouched
+            rest[k] = super().state_dict()[k]
+        return super().load_state_dict(rest, strict=strict, **kwargs)
 
     def _get_loss_func(self, loss):
         if isinstance(loss, str):
@@ -357,10 +412,25 @@ class BaseModel(nn.Module):
             ids_t, dense_t = ids_t.pin_memory(), dense_t.pin_memory()
         return ids_t, dense_t
 
+    def _dist_local_order(self, order, sample_num, batch_size):
+        """Row indices this rank trains on, in step order: its slice of every global batch (identical permutation on all ranks)."""
+        from ..distributed import rank_slice
+        ctx = self._dist
+        if order is not None and ctx.world > 1:
+            o = order.to(torch.device(self.device))
+            ctx.broadcast(o, 0)
+            order = o.cpu()
+        gbs = batch_size * ctx.world
+        parts = []
+        for lo in range(0, sample_num, gbs):
+            a, b = rank_slice(lo, min(sample_num, lo + gbs), ctx.rank, ctx.world)
+            parts.append(torch.arange(a, b) if order is None else order[a:b])
+        return torch.cat(parts) if parts else torch.empty(0, dtype=torch.int64)
+
     def _batches(self, ids, dense, y, batch_size, order=None):
         """Yield device batches (ids, dense, y or None); H2D copies run one batch ahead on a side stream."""
         dev = torch.device(self.device)
-        n = ids.shape[0]
+        n = ids.shape[0] if order is None else order.shape[0]
         steps = (n - 1) // batch_size + 1 if n > 0 else 0
         copy_stream = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream(dev)
@@ -418,6 +488,12 @@ class BaseModel(nn.Module):
         opt = self.optim
         opt.prepare()       # flat parameter / gradient views must exist BEFORE backward accumulates into them
         opt.zero_grad()
+        if self._dist is not None:
+            self._dist.ensure_capacity(ids.shape[0] * self._dist.sharded.m)
+            self._dist.sharded.stash = {}
+            if ids.shape[0] == 0:           # this rank has no rows in the last partial batch: take part in the collectives only
+                opt.step(apply_l2=True)
+                return None
         for ts in opt.table_sets:
             ts.plan.sparse_grad = True      # backward leaves (unique rows, segment sums) for the fused optimizer
         try:
@@ -492,6 +568,15 @@ class BaseModel(nn.Module):
         y_t = y_t.pin_memory()
         sample_num = ids.shape[0]
         steps_per_epoch = (sample_num - 1) // batch_size + 1
+        ctx = self._dist
+        if ctx is not None:
+            # one process per GPU: `batch_size` is per GPU (as with the reference's `gpus=`, basemodel.py:209); every rank holds
+            # the same arrays and trains on its slice of each global batch of batch_size * world samples
+            if not self._fused_ok():
+                raise NotImplementedError("distributed fit() needs a named optimizer ('sgd'/'adam'/'adagrad'/'rmsprop'), a single "
+                                          "loss and no l1 / auxiliary loss")
+            steps_per_epoch = (sample_num - 1) // (batch_size * ctx.world) + 1
+            ctx.ensure_capacity(batch_size * ctx.sharded.m)
         dev = torch.device(self.device)
         self.train()
         fused = self._fused_ok()
@@ -515,8 +600,13 @@ class BaseModel(nn.Module):
                 self.optim.prepare()
                 self.optim.reg_accum.zero_()
             order = torch.randperm(sample_num) if shuffle else None
+            local_steps = steps_per_epoch
+            if ctx is not None:
+                order = self._dist_local_order(order, sample_num, batch_size)
+                local_steps = (order.shape[0] - 1) // batch_size + 1 if order.shape[0] > 0 else 0
+            n_local = sample_num if order is None else order.shape[0]
             want_metrics = verbose > 0 and len(self.metrics) > 0
-            pred_log = torch.empty(sample_num, dtype=torch.float32, device=dev) if want_metrics else None
+            pred_log = torch.empty(n_local, dtype=torch.float32, device=dev) if want_metrics else None
             off = 0
             self.train()
             for ids_b, dense_b, y_b in self._batches(ids, dense, y_t, batch_size, order):
@@ -539,6 +629,10 @@ class BaseModel(nn.Module):
                     if pred_log is not None:
                         pred_log[off:off + nb] = y_pred.detach().reshape(-1)
                 off += nb
+            if ctx is not None:
+                for _ in range(steps_per_epoch - local_steps):      # ranks without rows in the last partial batch
+                    self.train_step(ids[:0].to(dev), dense[:0].to(dev), y_t[:0].to(dev), loss_accum)
+                ctx.all_reduce_sum(loss_accum)
             # ---- one host sync per epoch
             if fused:
                 total_loss_epoch = float(loss_accum.item()) + self.optim.pop_reg_loss()
@@ -550,10 +644,16 @@ class BaseModel(nn.Module):
                 y_host = y_t.numpy() if order is None else y_t[order].numpy()
                 for name, fn in self.metrics.items():
                     vals = []
-                    for s in range(steps_per_epoch):
-                        lo, hi = s * batch_size, min(sample_num, (s + 1) * batch_size)
+                    for s in range(local_steps):
+                        lo, hi = s * batch_size, min(n_local, (s + 1) * batch_size)
                         vals.append(fn(y_host[lo:hi], pred_host[lo:hi]))
-                    epoch_logs[name] = np.sum(vals) / steps_per_epoch
+                    if ctx is not None:
+                        # per-step metrics of the LOCAL sub-batches, averaged over all ranks' steps
+                        t = torch.tensor([float(np.sum(vals)), float(len(vals))], dtype=torch.float64, device=dev)
+                        ctx.all_reduce_sum(t)
+                        epoch_logs[name] = float(t[0].item() / max(t[1].item(), 1.0))
+                    else:
+                        epoch_logs[name] = np.sum(vals) / steps_per_epoch
             if do_validation:
                 for name, result in self.evaluate(val_x, val_y, batch_size).items():
                     epoch_logs["val_" + name] = result

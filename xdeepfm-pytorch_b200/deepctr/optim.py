@@ -32,7 +32,7 @@ class TableSet:
 class FusedOptimizer(torch.optim.Optimizer):
     """torch.optim.Optimizer-compatible (param_groups / state_dict) front end of the fused kernels."""
 
-    def __init__(self, kind, dense_named_params, table_sets, l2_of_param, **overrides):
+    def __init__(self, kind, dense_named_params, table_sets, l2_of_param, dist_ctx=None, l2_sharded=(0.0, 0.0), **overrides):
         if kind not in _TORCH_DEFAULTS:
             raise NotImplementedError(kind)
         defaults = dict(_TORCH_DEFAULTS[kind])
@@ -47,6 +47,10 @@ class FusedOptimizer(torch.optim.Optimizer):
         self.sparse_embedding_update = False     # True: only rows touched by the batch are updated (NOT reference semantics)
         self.reg_accum = None                    # float64 [1] device: sum of l2*w^2 seen by the last step(s)
         self.steps = 0
+        # multi-GPU (deepctr.distributed): dense gradients are all-reduced, the row-sharded tables are updated by their owner
+        self.dist_ctx = dist_ctx
+        self.l2_sharded = (float(l2_sharded[0]), float(l2_sharded[1]))     # (embedding tables, first-order tables)
+        self.reg_accum_shard = None              # float64 [1]: this rank's share of the table regulariser
 
     # -------------------------------------------------------------------------------------------
     def _cfg(self, l2):
@@ -110,6 +114,13 @@ class FusedOptimizer(torch.optim.Optimizer):
             opt_dev.copy_(old["opt_dev"])
         self._flat = dict(w=w, g=g, s1=s1, s2=s2, l2vec=l2vec, n=n, opt_dev=opt_dev, any_l2=bool((l2vec != 0).any().item()))
         self.reg_accum = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.reg_accum_shard = torch.zeros(1, dtype=torch.float64, device=dev)
+        if self.dist_ctx is not None:
+            sh = self.dist_ctx.sharded
+            if ns >= 1 and sh.s1 is None:
+                sh.s1, sh.s1_lin = torch.zeros_like(sh.emb), torch.zeros_like(sh.lin)
+            if ns >= 2 and sh.s2 is None:
+                sh.s2, sh.s2_lin = torch.zeros_like(sh.emb), torch.zeros_like(sh.lin)
         for ts in self.table_sets:
             if ts.s1 is None or ts.s1[0].device != dev:
                 ts.s1 = [torch.zeros_like(p.data) for p in ts.params] if ns >= 1 else None
@@ -139,6 +150,12 @@ class FusedOptimizer(torch.optim.Optimizer):
         f = self._flat
         st = N.stream_ptr()
         cfg0 = self._cfg(0.0)
+        ctx = self.dist_ctx
+        if ctx is not None:
+            # batch side of the sharded backward, then the data-parallel gradient SUM (losses are reduction='sum'); the
+            # all-reduce is also the barrier after which every rank's exchange buffers are complete
+            ctx.sharded.reduce_local()
+            ctx.all_reduce_sum(f["g"])
         N.check(L.xdfm_opt_tick(N.ptr(f["opt_dev"]), cfg0, st))
         if f["n"] > 0:
             N.check(L.xdfm_flat_opt(cfg0, N.ptr(f["opt_dev"]), f["n"], N.ptr(f["w"]), N.ptr(f["g"]), N.ptr(f["s1"]), N.ptr(f["s2"]),
@@ -168,11 +185,26 @@ class FusedOptimizer(torch.optim.Optimizer):
                     N.check(L.xdfm_flat_opt(cfg, N.ptr(f["opt_dev"]), p.numel(), N.ptr(p.data), N.ptr(p.grad.contiguous()),
                                             N.ptr(ts.s1[i]) if ts.s1 else None, N.ptr(ts.s2[i]) if ts.s2 else None, l2v,
                                             float(grad_scale), None, st))
+        if ctx is not None:
+            sh = ctx.sharded
+            sh.pull_segments()
+            dense_pass = 0 if self.sparse_embedding_update else 1
+            sh.apply_optimizer(self._cfg(self.l2_sharded[0] if apply_l2 else 0.0), self._cfg(self.l2_sharded[1] if apply_l2 else 0.0),
+                               f["opt_dev"], grad_scale, dense_pass, self.reg_accum_shard)
+            # peers may read this shard / overwrite their exchange buffers only after every owner is done
+            ctx.barrier(sh.device)
         self.steps += 1
         return None
 
     def pop_reg_loss(self):
-        """Sum of l2*w^2 accumulated since the last call (device float64 -> python float; one sync)."""
-        v = float(self.reg_accum.item())
+        """Sum of l2*w^2 accumulated since the last call (device float64 -> python float; one sync).  Multi-GPU: the dense
+        part is identical on every rank (counted once), the table part is summed over the owners."""
+        if self.dist_ctx is not None:
+            t = self.reg_accum_shard.clone()
+            self.dist_ctx.all_reduce_sum(t)
+            v = float(self.reg_accum.item()) + float(t.item())
+            self.reg_accum_shard.zero_()
+        else:
+            v = float(self.reg_accum.item())
         self.reg_accum.zero_()
         return v
