@@ -175,6 +175,26 @@ int64_t xdfm_cin_bwd_dw_tc_workspace_bytes(int64_t B, int m, int Hp, int H, int 
 int xdfm_cin_bwd_dw_tc(const void* dyT, const void* xkT, const void* x0T, int64_t B, int m, int Hp, int H, int D, float* dW, float* db,
                        void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- field self-attention block over the CIN feature maps (deepctr/layers/cin_attention.py).
+ * q/k/v/o/dout [B, L, E] fp32 (E = heads * head_dim, head_dim <= 32); lse [B, heads, L] = log2-sum-exp2 of the scaled scores.
+ * o = softmax(q k^T / sqrt(head_dim)) v per head (cin_attention.py:73-95, dropout p = 0); nothing of size L x L leaves the SM;
+ * the backward recomputes the probabilities from lse. */
+int xdfm_mhsa_fwd(const float* q, const float* k, const float* v, int64_t B, int L, int E, int heads, float* o, float* lse, void* stream);
+int xdfm_mhsa_bwd(const float* q, const float* k, const float* v, const float* o, const float* lse, const float* dout, int64_t B, int L,
+                  int E, int heads, float* dq, float* dk, float* dv, void* stream);
+/* y = LayerNorm_E(a + r) * gamma + beta (cin_attention.py:305-311; r may be NULL; normalize = 0: y = a + r only).
+ * mean / rstd [rows] are saved for the backward, which returns dx (= d a = d r) and per-block partial sums
+ * partial [xdfm_add_ln_bwd_blocks(rows), 2E] of (dgamma, dbeta) to be column-summed (xdfm_wcolsum). E <= 64. */
+int xdfm_add_ln_fwd(const float* a, const float* r, const float* gamma, const float* beta, int64_t rows, int E, float eps, int normalize,
+                    float* y, float* mean, float* rstd, void* stream);
+int xdfm_add_ln_bwd_blocks(int64_t rows);
+int xdfm_add_ln_bwd(const float* dy, const float* a, const float* r, const float* gamma, const float* mean, const float* rstd,
+                    int64_t rows, int E, float* dx, float* partial, void* stream);
+/* attention pooling (cin_attention.py:138-142): attn = softmax over L of score [B, L]; out [B, E] = sum_l attn[b,l] x[b,l,:]. */
+int xdfm_attn_pool_fwd(const float* score, const float* x, int64_t B, int L, int E, float* attn, float* out, void* stream);
+int xdfm_attn_pool_bwd(const float* dout, const float* attn, const float* x, int64_t B, int L, int E, float* dscore, float* dx,
+                       void* stream);
+
 /* ---- single-node multi-GPU: row-sharded tables over NVLink peer memory (no reference equivalent: the reference replicates whole
  * tables under nn.DataParallel, deepctr/models/basemodel.py:206-209, deepctr/inputs.py:167-180).
  * Global row r of a table lives on rank r % G at local row r / G; a rank keeps its shards of all tables of a set in ONE buffer

@@ -1,0 +1,115 @@
+"""Field self-attention block (csrc/attn.cu) against the oracle's restatement of deepctr/layers/cin_attention.py (fp64 on CPU).
+Tolerances: fp32 kernels with exp2f/rsqrtf -> 2e-5 relative to each tensor's scale."""
+import math
+
+import pytest
+import torch
+
+from deepctr import ops
+from oracle import xdeepfm_oracle as O
+from tests.helpers import assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _close(a, b, what, tol=2e-5):
+    b = torch.as_tensor(b)
+    assert_close(a, b, tol, tol * max(b.abs().max().item(), 1e-6), what)
+
+
+@pytest.mark.parametrize("B,L,E,h", [(3, 256, 16, 4), (5, 24, 10, 2), (2, 40, 8, 4), (4, 17, 12, 1), (2, 300, 32, 2), (1, 8, 6, 6),
+                                     (0, 16, 8, 2)])
+def test_mhsa_core_matches_softmax_attention(B, L, E, h):
+    g = torch.Generator().manual_seed(B * 1000 + L + E)
+    q, k, v, do = (torch.randn(B, L, E, generator=g) for _ in range(4))
+    qd, kd, vd = (t.double().requires_grad_(True) for t in (q, k, v))
+    hd = E // h
+    split = lambda t: t.view(B, L, h, hd).transpose(1, 2)
+    p = torch.softmax(split(qd).matmul(split(kd).transpose(-2, -1)) / math.sqrt(hd), dim=-1)
+    ref = p.matmul(split(vd)).transpose(1, 2).contiguous().view(B, L, E)
+    ref.backward(do.double())
+    qg, kg, vg = (t.to(DEV).requires_grad_(True) for t in (q, k, v))
+    out = ops.MHSACore.apply(qg, kg, vg, h)
+    out.backward(do.to(DEV))
+    if B == 0:
+        assert out.shape == (0, L, E)
+        return
+    _close(out, ref, "attention output")
+    _close(qg.grad, qd.grad, "dq")
+    _close(kg.grad, kd.grad, "dk")
+    _close(vg.grad, vd.grad, "dv")
+
+
+@pytest.mark.parametrize("rows_shape,E,residual,normalize", [((4, 33), 16, True, True), ((1000,), 10, False, True), ((7, 5), 8, True, False),
+                                                               ((3, 300), 64, True, True), ((513,), 32, True, True)])
+def test_add_layer_norm(rows_shape, E, residual, normalize):
+    g = torch.Generator().manual_seed(E)
+    a = torch.randn(*rows_shape, E, generator=g)
+    r = torch.randn(*rows_shape, E, generator=g) if residual else None
+    gamma, beta = 1 + 0.1 * torch.randn(E, generator=g), 0.1 * torch.randn(E, generator=g)
+    dy = torch.randn(*rows_shape, E, generator=g)
+    ad, gd, bd = a.double().requires_grad_(True), gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    rd = r.double().requires_grad_(True) if residual else None
+    x = ad + rd if residual else ad
+    ref = torch.nn.functional.layer_norm(x, (E,), gd, bd, 1e-5) if normalize else x
+    ref.backward(dy.double())
+    ag, gg, bg = a.to(DEV).requires_grad_(True), gamma.to(DEV).requires_grad_(True), beta.to(DEV).requires_grad_(True)
+    rg = r.to(DEV).requires_grad_(True) if residual else None
+    out = ops.AddLayerNorm.apply(ag, rg, gg if normalize else None, bg if normalize else None, 1e-5, normalize)
+    out.backward(dy.to(DEV))
+    _close(out, ref, "layer norm output")
+    _close(ag.grad, ad.grad, "d a")
+    if residual:
+        _close(rg.grad, rd.grad, "d residual")
+    if normalize:
+        _close(gg.grad, gd.grad, "d gamma", 1e-4)
+        _close(bg.grad, bd.grad, "d beta", 1e-4)
+
+
+@pytest.mark.parametrize("B,L,E", [(3, 256, 16), (5, 24, 10), (2, 300, 64), (1, 1, 8)])
+def test_attention_pooling(B, L, E):
+    g = torch.Generator().manual_seed(L)
+    score, x, dout = 2 * torch.randn(B, L, 1, generator=g), torch.randn(B, L, E, generator=g), torch.randn(B, E, generator=g)
+    sd, xd = score.double().requires_grad_(True), x.double().requires_grad_(True)
+    ref = (torch.softmax(sd, dim=1) * xd).sum(dim=1)
+    ref.backward(dout.double())
+    sg, xg = score.to(DEV).requires_grad_(True), x.to(DEV).requires_grad_(True)
+    out = ops.AttnPool.apply(sg, xg)
+    out.backward(dout.to(DEV))
+    _close(out, ref, "pooled")
+    _close(sg.grad, sd.grad, "d score")
+    _close(xg.grad, xd.grad, "d x")
+
+
+@pytest.mark.parametrize("variant,heads,layers,ln,res", [("attn", 4, 1, True, True), ("attn", 3, 1, False, True), ("attn", 2, 1, True, False),
+                                                        ("attn_v2", 2, 2, True, True), ("attn_v2", 4, 1, False, False)])
+def test_cin_attention_tail_matches_oracle(variant, heads, layers, ln, res):
+    """CINAttention / CINAttentionV2 modules (maps -> MHSA -> residual/LN -> pooling [-> projection]) with oracle weights."""
+    from deepctr.layers.cin_attention import CINAttention, CINAttentionV2
+    m, E, sizes, B = 5, 8, (16, 8), 9
+    spec = O.ModelSpec(sparse_names=["C%d" % i for i in range(m)], vocab_sizes=[10] * m, embedding_dim=E, cin_layer_size=sizes,
+                       variant=variant, num_heads=heads, use_layer_norm=ln, use_residual=res, num_attn_layers=layers)
+    params = O.make_params(spec, seed=heads + layers)
+    cin_sd = {k[len("cin."):]: v for k, v in params.items() if k.startswith("cin.")}
+    if variant == "attn":
+        mod = CINAttention(m, E, sizes, num_heads=heads, use_layer_norm=ln, use_residual=res, device=DEV)
+    else:
+        mod = CINAttentionV2(m, E, sizes, num_heads=heads, use_layer_norm=ln, use_residual=res, num_attn_layers=layers, device=DEV)
+    mod.load_state_dict(cin_sd, strict=True)
+    g = torch.Generator().manual_seed(3)
+    x0 = 0.5 * torch.randn(B, m, E, generator=g)
+    pd = {k: v.double().requires_grad_(True) for k, v in params.items()}
+    Ws, bs = O.cin_params(pd, spec)
+    xd = x0.double().requires_grad_(True)
+    maps = O.cin_forward(xd, Ws, bs, True, "relu", pool=False)
+    ref = O.cin_attention_tail(pd, spec, maps)
+    gout = torch.randn(ref.shape, generator=g)
+    ref.backward(gout.double())
+    xg = x0.to(DEV).requires_grad_(True)
+    out = mod(xg)
+    out.backward(gout.to(DEV))
+    _close(out, ref, "cin attention output", 5e-5)
+    _close(xg.grad, xd.grad, "d x0", 2e-4)
+    for name, p in mod.named_parameters():
+        _close(p.grad, pd["cin." + name].grad, "grad " + name, 2e-4)

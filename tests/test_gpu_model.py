@@ -11,7 +11,7 @@ from tests.helpers import FIT_CASES, assert_close, build_product_model, golden_g
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 XDEEPFM_CASES = ["xdeepfm_small", "xdeepfm_small_nosplit", "xdeepfm_small_linearact", "xdeepfm_small_nodense",
-                 "xdeepfm_small_zipf", "xdeepfm_cfg1"]
+                 "xdeepfm_small_zipf", "xdeepfm_cfg1", "attn_small", "attn_small_3heads", "attn_v2_small"]
 
 
 @pytest.mark.parametrize("name", XDEEPFM_CASES)

@@ -72,6 +72,13 @@ _SIGS = {
     "xdfm_shard_segments": (c_int, [_P, c_int64, c_int, c_int, c_uint32, _P, POINTER(c_int32), _P, c_int64, _P, _P, _P, _P, _P, _P]),
     "xdfm_shard_pull_segments": (c_int, [POINTER(_P), POINTER(_P), POINTER(_P), POINTER(_P), c_int, c_int, c_uint32, c_int, c_int64,
                                          _P, c_int64, _P, _P, _P, _P, _P, _P, _P]),
+    "xdfm_mhsa_fwd": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P]),
+    "xdfm_mhsa_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "xdfm_add_ln_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_float, c_int, _P, _P, _P, _P]),
+    "xdfm_add_ln_bwd_blocks": (c_int, [c_int64]),
+    "xdfm_add_ln_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P]),
+    "xdfm_attn_pool_fwd": (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P, _P]),
+    "xdfm_attn_pool_bwd": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, _P, _P]),
     "xdfm_opt_tick": (c_int, [_P, POINTER(OptCfg), _P]),
     "xdfm_flat_opt": (c_int, [POINTER(OptCfg), _P, c_int64, _P, _P, _P, _P, _P, c_float, _P, _P]),
     "xdfm_rows_opt": (c_int, [POINTER(OptCfg), _P, POINTER(_P), POINTER(_P), POINTER(_P), POINTER(c_int64), c_int, c_int, _P, _P, _P,

@@ -1,2 +1,3 @@
 from .basemodel import BaseModel, Linear
 from .xdeepfm import xDeepFM
+from .xdeepfm_attn import xDeepFMAttention, xDeepFMAttentionV2

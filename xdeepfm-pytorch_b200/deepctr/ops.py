@@ -563,3 +563,104 @@ def bce_sum(y_pred, labels, loss_accum=None, scale=1.0, want_grad=True):
     g = torch.empty_like(p) if want_grad else None
     N.check(N.lib().xdfm_bce_sum(N.ptr(p), N.ptr(y), B, float(scale), None, N.ptr(g), N.ptr(loss_accum), N.stream_ptr()))
     return loss_accum, g
+
+
+# ------------------------------------------------------------------------------------------------
+# field self-attention block over the CIN feature maps (deepctr/layers/cin_attention.py)
+# ------------------------------------------------------------------------------------------------
+class MHSACore(torch.autograd.Function):
+    """o = softmax(q k^T / sqrt(head_dim)) v per head; q, k, v [B, L, E].  Scores never leave the SM; the backward recomputes
+    the probabilities from the saved log-sum-exp (reference: cin_attention.py:73-95 materialises [B, h, L, L] twice)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, heads):
+        require_cuda(q, "MHSACore")
+        q, k, v = _f32c(q), _f32c(k), _f32c(v)
+        B, L, E = q.shape
+        o = torch.empty_like(q)
+        lse = torch.empty((B, heads, L), dtype=torch.float32, device=q.device)
+        with timed("mhsa"):
+            N.check(N.lib().xdfm_mhsa_fwd(N.ptr(q), N.ptr(k), N.ptr(v), B, L, E, heads, N.ptr(o), N.ptr(lse), N.stream_ptr()))
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.heads = heads
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, o, lse = ctx.saved_tensors
+        B, L, E = q.shape
+        do = _f32c(do)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        with timed("mhsa"):
+            N.check(N.lib().xdfm_mhsa_bwd(N.ptr(q), N.ptr(k), N.ptr(v), N.ptr(o), N.ptr(lse), N.ptr(do), B, L, E, ctx.heads, N.ptr(dq),
+                                          N.ptr(dk), N.ptr(dv), N.stream_ptr()))
+        return dq, dk, dv, None
+
+
+class AddLayerNorm(torch.autograd.Function):
+    """y = LayerNorm_E(a + r) * gamma + beta (r and the normalisation are optional): residual + nn.LayerNorm of
+    cin_attention.py:305-311 in one pass."""
+
+    @staticmethod
+    def forward(ctx, a, r, gamma, beta, eps, normalize):
+        require_cuda(a, "AddLayerNorm")
+        a = _f32c(a)
+        r = None if r is None else _f32c(r)
+        E = a.shape[-1]
+        rows = a.numel() // E
+        y = torch.empty_like(a)
+        mean = torch.empty(rows, dtype=torch.float32, device=a.device) if normalize else None
+        rstd = torch.empty(rows, dtype=torch.float32, device=a.device) if normalize else None
+        g = None if gamma is None else _f32c(gamma)
+        bt = None if beta is None else _f32c(beta)
+        N.check(N.lib().xdfm_add_ln_fwd(N.ptr(a), N.ptr(r), N.ptr(g), N.ptr(bt), rows, E, float(eps), int(bool(normalize)), N.ptr(y),
+                                        N.ptr(mean), N.ptr(rstd), N.stream_ptr()))
+        ctx.saved = (a, r, g, mean, rstd)
+        ctx.normalize, ctx.has_r = bool(normalize), r is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, r, g, mean, rstd = ctx.saved
+        dy = _f32c(dy)
+        if not ctx.normalize:
+            return dy, (dy if ctx.has_r else None), None, None, None, None
+        E = a.shape[-1]
+        rows = a.numel() // E
+        L = N.lib()
+        dx = torch.empty_like(a)
+        nblk = L.xdfm_add_ln_bwd_blocks(rows)
+        partial = torch.empty((nblk, 2 * E), dtype=torch.float32, device=a.device)
+        N.check(L.xdfm_add_ln_bwd(N.ptr(dy), N.ptr(a), N.ptr(r), N.ptr(g), N.ptr(mean), N.ptr(rstd), rows, E, N.ptr(dx), N.ptr(partial),
+                                  N.stream_ptr()))
+        dgb = torch.empty(2 * E, dtype=torch.float32, device=a.device)
+        ws = workspace("wcolsum", L.xdfm_wcolsum_workspace_bytes(2 * E), a.device)
+        N.check(L.xdfm_wcolsum(N.ptr(partial), nblk, 2 * E, 2 * E, None, N.ptr(dgb), 0, N.ptr(ws), ws.numel(), N.stream_ptr()))
+        return dx, (dx if ctx.has_r else None), dgb[:E], dgb[E:], None, None
+
+
+class AttnPool(torch.autograd.Function):
+    """out [B, E] = sum_l softmax_L(score)[b, l] * x[b, l, :]  (cin_attention.py:138-142)."""
+
+    @staticmethod
+    def forward(ctx, score, x):
+        require_cuda(x, "AttnPool")
+        x = _f32c(x)
+        B, Lq, E = x.shape
+        s = _f32c(score).reshape(B, Lq)
+        attn = torch.empty((B, Lq), dtype=torch.float32, device=x.device)
+        out = torch.empty((B, E), dtype=torch.float32, device=x.device)
+        N.check(N.lib().xdfm_attn_pool_fwd(N.ptr(s), N.ptr(x), B, Lq, E, N.ptr(attn), N.ptr(out), N.stream_ptr()))
+        ctx.save_for_backward(attn, x)
+        ctx.score_shape = score.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        attn, x = ctx.saved_tensors
+        B, Lq, E = x.shape
+        dout = _f32c(dout)
+        dscore = torch.empty_like(attn)
+        dx = torch.empty_like(x)
+        N.check(N.lib().xdfm_attn_pool_bwd(N.ptr(dout), N.ptr(attn), N.ptr(x), B, Lq, E, N.ptr(dscore), N.ptr(dx), N.stream_ptr()))
+        return dscore.view(ctx.score_shape), dx
