@@ -195,6 +195,16 @@ int xdfm_attn_pool_fwd(const float* score, const float* x, int64_t B, int L, int
 int xdfm_attn_pool_bwd(const float* dout, const float* attn, const float* x, int64_t B, int L, int E, float* dscore, float* dx,
                        void* stream);
 
+/* ---- xDeepFM Pro: Supervised-Feature-Generation loss (deepctr/xdeepfm_pro/sfg_decoder.py:266-309).
+ * row_w[b] = mask_b / num (mask = label == 1, num = sum(mask) + 1e-8 when positive_only; else 1 / B);
+ * masked_ce:  row_loss[r] = row_w[r] * CE(logits[r, :V], targets[r * target_stride]), dlogits = d(sum row_loss)/d logits;
+ * masked_mse: row_loss[r] = row_w[r] * mean_j (pred - target)^2, dpred likewise. */
+int xdfm_sfg_row_weights(const float* labels, int64_t B, int positive_only, float* row_w, void* stream);
+int xdfm_masked_ce(const float* logits, const int32_t* targets, int64_t target_stride, const float* row_w, int64_t R, int V,
+                   float* row_loss, float* dlogits, void* stream);
+int xdfm_masked_mse(const float* pred, const float* target, const float* row_w, int64_t R, int nd, float* row_loss, float* dpred,
+                    void* stream);
+
 /* ---- single-node multi-GPU: row-sharded tables over NVLink peer memory (no reference equivalent: the reference replicates whole
  * tables under nn.DataParallel, deepctr/models/basemodel.py:206-209, deepctr/inputs.py:167-180).
  * Global row r of a table lives on rank r % G at local row r / G; a rank keeps its shards of all tables of a set in ONE buffer

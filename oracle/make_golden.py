@@ -33,6 +33,7 @@ def spec_to_json(spec: ModelSpec):
     d = dict(spec.__dict__)
     d["cin_layer_size"] = list(d["cin_layer_size"])
     d["dnn_hidden_units"] = list(d["dnn_hidden_units"])
+    d["sfg_hidden_units"] = list(d["sfg_hidden_units"])
     return d
 
 
@@ -46,6 +47,11 @@ def build_reference_model(spec: ModelSpec, **extra):
     common.update(extra)
     if spec.variant == "xdeepfm":
         return xDeepFM(cols, cols, **common)
+    if spec.variant == "pro":
+        from deepctr.xdeepfm_pro import xDeepFMPro
+        return xDeepFMPro(cols, cols, use_sfg=spec.use_sfg, sfg_weight=spec.sfg_weight, sfg_hidden_units=spec.sfg_hidden_units,
+                          sfg_dropout=0.0, sfg_positive_only=spec.sfg_positive_only,
+                          sfg_use_label_attention=spec.sfg_use_label_attention, **common)
     if spec.variant == "attn":
         return xDeepFMAttention(cols, cols, cin_num_heads=spec.num_heads, cin_use_layer_norm=spec.use_layer_norm,
                                 cin_use_residual=spec.use_residual, **common)
@@ -116,6 +122,37 @@ def forward_backward_case(name, spec: ModelSpec, B, seed, store_params=True, gra
     print(name, "loss", float(loss), "total", float(total), "y_pred[:3]", y_pred[:3].tolist())
 
 
+def pro_case(name, spec: ModelSpec, B, seed):
+    """One reference xDeepFM Pro train step (basemodel_sfg.py:316-349): y_pred, BCE-sum, sfg_loss, total, parameter gradients."""
+    params = make_params(spec, seed=seed)
+    X, y = make_inputs(spec, B, seed=seed)
+    model = build_reference_model(spec)
+    model.load_state_dict(params, strict=True)
+    model.train()
+    y_pred, info = model.forward_with_sfg(X, y)
+    y_pred = y_pred.squeeze()
+    loss = torch.nn.functional.binary_cross_entropy(y_pred, y, reduction="sum")
+    reg = model.get_regularization_loss()
+    sfg = info["sfg_loss"] if info is not None else torch.tensor(0.0)
+    total = loss + reg + model.aux_loss + model.sfg_weight * sfg
+    model.zero_grad()
+    total.backward()
+    out = {"X": X.numpy(), "y": y.numpy(), "y_pred": y_pred.detach().numpy(), "loss": loss.detach().numpy(),
+           "reg_loss": reg.detach().numpy(), "sfg_loss": np.float64(float(sfg)), "total": total.detach().numpy()}
+    for k, p in model.named_parameters():
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        out["grad::" + k] = g.numpy()
+    model.eval()
+    with torch.no_grad():
+        out["y_pred_eval"] = model(X).numpy()
+    for k, v in params.items():
+        out["param::" + k] = v.numpy()
+    out["spec_json"] = np.array(json.dumps(spec_to_json(spec)))
+    out["seed"] = np.int64(seed)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(name, "loss", float(loss), "sfg", float(sfg), "total", float(total))
+
+
 def fit_case(name, spec: ModelSpec, N, batch_size, epochs, optimizer, seed, lr=None):
     """Trajectory of the reference's own fit(): History['loss'] per epoch + final weights + predictions."""
     params = make_params(spec, seed=seed)
@@ -135,6 +172,7 @@ def fit_case(name, spec: ModelSpec, N, batch_size, epochs, optimizer, seed, lr=N
                          shuffle=False, validation_data=(dict(xdict), y.numpy().reshape(-1, 1)))
         pred = model.predict(dict(xdict), batch_size=batch_size)
     out = {"X": X.numpy(), "y": y.numpy(), "pred": pred,
+           "history_sfg_loss": np.array(hist.history.get("sfg_loss", []), dtype=np.float64),
            "history_loss": np.array(hist.history["loss"], dtype=np.float64),
            "history_val_auc": np.array(hist.history["val_auc"], dtype=np.float64),
            "history_val_bce": np.array(hist.history["val_binary_crossentropy"], dtype=np.float64),
@@ -182,5 +220,21 @@ def main():
     fit_case("fit_small_rmsprop", small_spec(), N=80, batch_size=32, epochs=2, optimizer="rmsprop", seed=14, lr=1e-3)
 
 
+def main_pro():
+    """xDeepFM Pro fixtures (added after the first batch; `python -m oracle.make_golden pro` regenerates only these)."""
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(4)
+    pro = dict(variant="pro", sfg_hidden_units=(16, 8))
+    pro_case("pro_small", small_spec(**pro), B=40, seed=21)
+    pro_case("pro_small_allrows_noattn", small_spec(sfg_positive_only=False, sfg_use_label_attention=False, sfg_weight=0.5, **pro),
+             B=24, seed=22)
+    pro_case("pro_small_nodense", small_spec(dense_names=[], embedding_dim=4, **pro), B=24, seed=23)
+    fit_case("fit_pro_small_adam", small_spec(**pro), N=96, batch_size=32, epochs=2, optimizer="adam", seed=24, lr=1e-2)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "pro":
+        main_pro()
+    else:
+        main()
+        main_pro()

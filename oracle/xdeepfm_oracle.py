@@ -56,11 +56,17 @@ class ModelSpec:
     l2_reg_dnn: float = 0.0
     l2_reg_cin: float = 0.0
     # attention variants (cin_attention.py)
-    variant: str = "xdeepfm"        # xdeepfm | attn | attn_v2
+    variant: str = "xdeepfm"        # xdeepfm | attn | attn_v2 | pro
     num_heads: int = 4
     use_layer_norm: bool = True
     use_residual: bool = True
     num_attn_layers: int = 1
+    # xDeepFM Pro (xdeepfm_pro.py:57-87): SFG decoder; dropout is 0 in every parity case
+    use_sfg: bool = True
+    sfg_weight: float = 0.1
+    sfg_hidden_units: Tuple[int, ...] = (128, 64)
+    sfg_positive_only: bool = True
+    sfg_use_label_attention: bool = True
     # column order of the flat input matrix X: feature_index order (inputs.py:99-123).  The scripts
     # build sparse columns first, then dense (xdftrain.py:240-256).
     sparse_first: bool = True
@@ -266,7 +272,7 @@ def xdeepfm_logit(params, spec: ModelSpec, X, return_parts=False):
     parts = {"emb": emb, "linear_logit": lin}
     if len(spec.cin_layer_size) > 0:
         Ws, bs = cin_params(params, spec)
-        if spec.variant == "xdeepfm":
+        if spec.variant in ("xdeepfm", "pro"):
             cin_out = cin_forward(emb, Ws, bs, spec.cin_split_half, spec.cin_activation, pool=True)
         else:
             maps = cin_forward(emb, Ws, bs, spec.cin_split_half, spec.cin_activation, pool=False)
@@ -318,6 +324,57 @@ def train_loss(params, spec: ModelSpec, X, y):
     y_pred = xdeepfm_forward(params, spec, X).squeeze(-1)
     loss = F.binary_cross_entropy(y_pred, y.to(y_pred.dtype).reshape(-1), reduction="sum")
     return loss, loss + reg_loss(params, spec).squeeze()
+
+
+def sfg_loss(params, spec: ModelSpec, X, y):
+    """SFG reconstruction loss of xDeepFM Pro in training mode, dropout p = 0 (sfg_decoder.py:116-157 decoder forward,
+    :198-204 label-aware attention, :266-309 loss; targets re-read from X: basemodel_sfg.py:446-466)."""
+    ids, dense = split_input(spec, X)
+    dt = params["out.bias"].dtype
+    dense = dense.to(dt)
+    emb = embedding_lookup(params, spec, ids)                                  # [B, m, D]
+    x = torch.cat([emb.reshape(emb.shape[0], -1), dense], dim=-1)               # sparse embeddings in field order, then dense
+    labels = y.reshape(-1)
+    P = "sfg_decoder."
+    if spec.sfg_use_label_attention:
+        lab = params[P + "label_attention.label_embedding.weight"][labels.long()]
+        h = torch.relu(torch.cat([x, lab], dim=-1).matmul(params[P + "label_attention.attention_net.0.weight"].t())
+                       + params[P + "label_attention.attention_net.0.bias"])
+        gate = torch.sigmoid(h.matmul(params[P + "label_attention.attention_net.2.weight"].t())
+                             + params[P + "label_attention.attention_net.2.bias"])
+        x = x * gate
+    hid = x
+    for i in range(len(spec.sfg_hidden_units)):
+        hid = torch.relu(hid.matmul(params[P + "shared_layers.%d.weight" % (3 * i)].t()) + params[P + "shared_layers.%d.bias" % (3 * i)])
+    if spec.sfg_positive_only:
+        mask = (labels == 1).to(dt)
+        num = mask.sum() + 1e-8
+    else:
+        mask = torch.ones_like(labels, dtype=dt)
+        num = labels.shape[0]
+    total_sparse = torch.zeros((), dtype=dt)
+    for f, name in enumerate(spec.sparse_names):
+        logits = hid.matmul(params[P + "sparse_heads.%s.weight" % name].t()) + params[P + "sparse_heads.%s.bias" % name]
+        ce = F.cross_entropy(logits, ids[:, f], reduction="none")
+        total_sparse = total_sparse + (ce * mask).sum() / num
+    total_dense = torch.zeros((), dtype=dt)
+    if spec.nd > 0:
+        pred = hid.matmul(params[P + "dense_head.weight"].t()) + params[P + "dense_head.bias"]
+        mse = ((pred - dense) ** 2).mean(dim=-1)
+        total_dense = (mse * mask).sum() / num
+    return total_sparse + total_dense
+
+
+def pro_loss_and_grads(params, spec: ModelSpec, X, y):
+    """xDeepFM Pro train step (basemodel_sfg.py:316-349): total = BCE_sum + reg + sfg_weight * sfg_loss."""
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+    y_pred = xdeepfm_forward(leaves, spec, X)
+    loss = F.binary_cross_entropy(y_pred.squeeze(-1), y.to(y_pred.dtype).reshape(-1), reduction="sum")
+    sfg = sfg_loss(leaves, spec, X, y) if spec.use_sfg else torch.zeros((), dtype=y_pred.dtype)
+    total = loss + reg_loss(leaves, spec).squeeze() + spec.sfg_weight * sfg
+    total.backward()
+    grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
+    return y_pred.detach(), loss.detach(), sfg.detach(), total.detach(), grads
 
 
 def loss_and_grads(params, spec: ModelSpec, X, y):
@@ -380,6 +437,27 @@ def param_shapes(spec: ModelSpec):
         if spec.variant == "attn":
             shapes["cin.output_proj.weight"] = (spec.featuremap_num, E)
         shapes["cin_linear.weight"] = (1, E if spec.variant == "attn_v2" else spec.featuremap_num)
+    if spec.variant == "pro" and spec.use_sfg:
+        # sfg_decoder.py:42-83 (shared_layers = Linear, ReLU, Dropout per hidden unit -> indices 0, 3, ...)
+        d_in = m * D + nd
+        prev = d_in
+        for i, h in enumerate(spec.sfg_hidden_units):
+            shapes["sfg_decoder.shared_layers.%d.weight" % (3 * i)] = (h, prev)
+            shapes["sfg_decoder.shared_layers.%d.bias" % (3 * i)] = (h,)
+            prev = h
+        for name, V in zip(spec.sparse_names, spec.vocab_sizes):
+            shapes["sfg_decoder.sparse_heads.%s.weight" % name] = (V, prev)
+            shapes["sfg_decoder.sparse_heads.%s.bias" % name] = (V,)
+        if nd > 0:
+            shapes["sfg_decoder.dense_head.weight"] = (nd, prev)
+            shapes["sfg_decoder.dense_head.bias"] = (nd,)
+        if spec.sfg_use_label_attention:
+            h0 = spec.sfg_hidden_units[0] if spec.sfg_hidden_units else 64
+            shapes["sfg_decoder.label_attention.label_embedding.weight"] = (2, h0)
+            shapes["sfg_decoder.label_attention.attention_net.0.weight"] = (h0, d_in + h0)
+            shapes["sfg_decoder.label_attention.attention_net.0.bias"] = (h0,)
+            shapes["sfg_decoder.label_attention.attention_net.2.weight"] = (d_in, h0)
+            shapes["sfg_decoder.label_attention.attention_net.2.bias"] = (d_in,)
     return shapes
 
 

@@ -11,6 +11,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 FWD_BWD_CASES = ["xdeepfm_small", "xdeepfm_small_nosplit", "xdeepfm_small_linearact", "xdeepfm_small_nodense",
                  "xdeepfm_small_zipf", "attn_small", "attn_small_3heads", "attn_v2_small", "xdeepfm_cfg1"]
+PRO_CASES = ["pro_small", "pro_small_allrows_noattn", "pro_small_nodense"]
 FIT_CASES = ["fit_small_adam", "fit_small_sgd", "fit_small_adagrad", "fit_small_rmsprop"]
 
 
@@ -19,6 +20,8 @@ def load_case(name):
     d = json.loads(str(z["spec_json"]))
     d["cin_layer_size"] = tuple(d["cin_layer_size"])
     d["dnn_hidden_units"] = tuple(d["dnn_hidden_units"])
+    if "sfg_hidden_units" in d:
+        d["sfg_hidden_units"] = tuple(d["sfg_hidden_units"])
     spec = ModelSpec(**d)
     params = {k[len("param::"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param::")}
     if not params:
@@ -49,6 +52,12 @@ def build_product_model(spec, device="cuda:0", **extra):
     common.update(extra)
     if spec.variant == "xdeepfm":
         return M.xDeepFM(cols, cols, **common)
+    if spec.variant == "pro":
+        from deepctr.xdeepfm_pro import xDeepFMPro
+        kw = dict(use_sfg=spec.use_sfg, sfg_weight=spec.sfg_weight, sfg_hidden_units=spec.sfg_hidden_units, sfg_dropout=0.0,
+                  sfg_positive_only=spec.sfg_positive_only, sfg_use_label_attention=spec.sfg_use_label_attention)
+        kw.update(common)
+        return xDeepFMPro(cols, cols, **kw)
     if spec.variant == "attn":
         return M.xDeepFMAttention(cols, cols, cin_num_heads=spec.num_heads, cin_use_layer_norm=spec.use_layer_norm,
                                   cin_use_residual=spec.use_residual, **common)

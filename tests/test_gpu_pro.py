@@ -1,0 +1,120 @@
+"""xDeepFM Pro (SFG auxiliary decoder) on the GPU against fixtures produced by the unmodified reference
+(oracle/make_golden.py pro) and against torch for the masked-loss kernels."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from deepctr import ops
+from tests.helpers import PRO_CASES, assert_close, build_product_model, golden_grads, load_case
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("R,V,positive_only", [(37, 50, True), (5, 3, False), (64, 5000, True), (1, 1, True), (16, 257, False)])
+def test_masked_cross_entropy_kernel(R, V, positive_only):
+    g = torch.Generator().manual_seed(R + V)
+    logits = 3 * torch.randn(R, V, generator=g)
+    ids = torch.randint(0, V, (R, 3), generator=g).to(torch.int32)
+    labels = (torch.rand(R, generator=g) < 0.4).float()
+    mask = (labels == 1).double() if positive_only else torch.ones(R, dtype=torch.float64)
+    num = mask.sum() + 1e-8 if positive_only else R
+    ld = logits.double().requires_grad_(True)
+    ref = (F.cross_entropy(ld, ids[:, 1].long(), reduction="none") * mask).sum() / num
+    ref.backward()
+    lg = logits.to(DEV).requires_grad_(True)
+    row_w = ops.sfg_row_weights(labels.to(DEV), positive_only)
+    assert_close(row_w, mask / num, 1e-6, 1e-9, "row weights")
+    out = ops.MaskedCE.apply(lg, ids.to(DEV), 1, row_w)
+    (2.5 * out).backward()
+    assert_close(out.reshape(()), ref.detach(), 2e-5, 1e-7, "masked CE")
+    assert_close(lg.grad, 2.5 * ld.grad, 2e-5, 2e-5 * float(ld.grad.abs().max()) + 1e-12, "d logits")
+
+
+def test_masked_mse_kernel():
+    g = torch.Generator().manual_seed(0)
+    pred, tgt = torch.randn(33, 3, generator=g), torch.rand(33, 3, generator=g)
+    labels = (torch.rand(33, generator=g) < 0.4).float()
+    mask = (labels == 1).double()
+    pd = pred.double().requires_grad_(True)
+    ref = (((pd - tgt.double()) ** 2).mean(-1) * mask).sum() / (mask.sum() + 1e-8)
+    ref.backward()
+    pg = pred.to(DEV).requires_grad_(True)
+    out = ops.MaskedMSE.apply(pg, tgt.to(DEV), ops.sfg_row_weights(labels.to(DEV), True))
+    out.backward()
+    assert_close(out.reshape(()), ref.detach(), 2e-5, 1e-7, "masked MSE")
+    assert_close(pg.grad, pd.grad, 2e-5, 1e-8, "d pred")
+
+
+@pytest.mark.parametrize("name", PRO_CASES)
+def test_pro_train_step_matches_reference_fixture(name):
+    spec, params, z = load_case(name)
+    model = build_product_model(spec, DEV)
+    model.load_state_dict(params, strict=True)
+    X, y = torch.from_numpy(z["X"]).to(DEV), torch.from_numpy(z["y"]).to(DEV)
+    model.train()
+    y_pred, info = model.forward_with_sfg(X, y)
+    y_pred = y_pred.squeeze()
+    assert_close(y_pred, z["y_pred"], 2e-5, 2e-6, "y_pred")
+    sfg = info["sfg_loss"]
+    assert abs(sfg.item() - float(z["sfg_loss"])) <= 2e-5 * abs(float(z["sfg_loss"]))
+    loss = F.binary_cross_entropy(y_pred, y, reduction="sum")
+    total = loss + model.get_regularization_loss() + model.aux_loss + model.sfg_weight * sfg
+    assert abs(total.item() - float(z["total"].item())) <= 2e-5 * abs(float(z["total"].item()))
+    model.zero_grad()
+    total.backward()
+    named = dict(model.named_parameters())
+    for k, g in golden_grads(z).items():
+        got = named[k].grad
+        got = torch.zeros_like(named[k]) if got is None else got
+        assert_close(got, g, 2e-4, 2e-5 * max(g.abs().max().item(), 1e-6), "grad " + k)
+    model.eval()
+    with torch.no_grad():
+        y_eval, info = model.forward_with_sfg(X, y)
+        assert info is None                       # no SFG term in eval mode (SURVEY.md 3.5 [probed])
+        assert_close(y_eval, z["y_pred_eval"], 2e-5, 2e-6, "eval y_pred")
+
+
+def test_pro_fused_sgd_step_equals_gradient_step():
+    spec, params, z = load_case("pro_small")
+    model = build_product_model(spec, DEV)
+    model.load_state_dict(params, strict=True)
+    model.compile("sgd", "binary_crossentropy")
+    X, y = torch.from_numpy(z["X"]).to(DEV), torch.from_numpy(z["y"]).to(DEV)
+    ids, dense = model.split_input(X)
+    accum = torch.zeros(1, dtype=torch.float64, device=DEV)
+    model.train()
+    model.train_step(ids, dense, y, accum)
+    assert abs(accum.item() - float(z["loss"])) <= 2e-5 * abs(float(z["loss"]))
+    assert abs(model._sfg_accum.item() - float(z["sfg_loss"])) <= 2e-5 * abs(float(z["sfg_loss"]))
+    grads = golden_grads(z)
+    for k, p in model.state_dict().items():
+        expect = params[k].double() - 0.01 * grads[k].double()
+        scale = (0.01 * grads[k]).abs().max().item()
+        assert_close(p, expect, 0, 3e-4 * scale + 1e-7 * params[k].abs().max().item(), "sgd step " + k)
+
+
+def test_pro_fit_trajectory_matches_reference():
+    spec, params, z = load_case("fit_pro_small_adam")
+    model = build_product_model(spec, DEV)
+    model.load_state_dict(params, strict=True)
+    model.compile("adam", "binary_crossentropy", metrics=["binary_crossentropy", "auc"])
+    for g in model.optim.param_groups:
+        g["lr"] = float(z["lr"])
+    X, y = z["X"], z["y"]
+    names = list(model.feature_index.keys())
+    xd = {n: X[:, i].copy() for i, n in enumerate(names)}
+    hist = model.fit(xd, y.reshape(-1, 1), batch_size=int(z["batch_size"]), epochs=int(z["epochs"]), verbose=0, shuffle=False,
+                     validation_data=(dict(xd), y.reshape(-1, 1)))
+    assert np.allclose(hist.history["loss"], z["history_loss"], rtol=1e-3), (hist.history["loss"], z["history_loss"])
+    assert np.allclose(hist.history["sfg_loss"], z["history_sfg_loss"], rtol=1e-3), (hist.history["sfg_loss"], z["history_sfg_loss"])
+    assert np.allclose(hist.history["val_auc"], z["history_val_auc"], atol=5e-3)
+    pred = model.predict(dict(xd), batch_size=int(z["batch_size"]))
+    assert np.allclose(pred, z["pred"], rtol=2e-3, atol=2e-4)
+
+
+def test_autodis_is_refused_explicitly():
+    spec, params, z = load_case("pro_small")
+    with pytest.raises(NotImplementedError):
+        build_product_model(spec, DEV, use_autodis=True)

@@ -6,5 +6,6 @@ Same import paths as the reference (`deepctr.inputs`, `deepctr.models`, `deepctr
 from . import inputs  # noqa: F401
 from . import layers  # noqa: F401
 from . import models  # noqa: F401
+from . import xdeepfm_pro  # noqa: F401
 
 __version__ = "0.2.9+b200"

@@ -79,6 +79,9 @@ _SIGS = {
     "xdfm_add_ln_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P]),
     "xdfm_attn_pool_fwd": (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P, _P]),
     "xdfm_attn_pool_bwd": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, _P, _P]),
+    "xdfm_sfg_row_weights": (c_int, [_P, c_int64, c_int, _P, _P]),
+    "xdfm_masked_ce": (c_int, [_P, _P, c_int64, _P, c_int64, c_int, _P, _P, _P]),
+    "xdfm_masked_mse": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P, _P]),
     "xdfm_opt_tick": (c_int, [_P, POINTER(OptCfg), _P]),
     "xdfm_flat_opt": (c_int, [POINTER(OptCfg), _P, c_int64, _P, _P, _P, _P, _P, c_float, _P, _P]),
     "xdfm_rows_opt": (c_int, [POINTER(OptCfg), _P, POINTER(_P), POINTER(_P), POINTER(_P), POINTER(c_int64), c_int, c_int, _P, _P, _P,

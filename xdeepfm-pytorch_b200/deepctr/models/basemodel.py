@@ -517,6 +517,13 @@ class BaseModel(nn.Module):
             pred_log[pred_off:pred_off + yv.shape[0]] = y_pred.detach().reshape(-1)
         return y_pred
 
+    def _epoch_begin(self):
+        """Hook for subclasses with extra device-side accumulators (xDeepFM Pro)."""
+
+    def _epoch_extra(self, sample_num):
+        """Hook: (extra sum added to the epoch's total loss, extra History entries)."""
+        return 0.0, {}
+
     def train_on_batch(self, ids, dense, y):
         """Public single-step API: HOST tensors (ids int32 [B, m_all], dense float32 [B, nd_all], y float32 [B]; pinned
         memory makes the copies asynchronous) -> python float BCE-sum of the batch.  H2D copy, fused step, D2H of the loss."""
@@ -596,6 +603,7 @@ class BaseModel(nn.Module):
             start_time = time.time()
             loss_accum.zero_()
             total_accum.zero_()
+            self._epoch_begin()
             if fused:
                 self.optim.prepare()
                 self.optim.reg_accum.zero_()
@@ -638,7 +646,9 @@ class BaseModel(nn.Module):
                 total_loss_epoch = float(loss_accum.item()) + self.optim.pop_reg_loss()
             else:
                 total_loss_epoch = float(total_accum.item())
-            epoch_logs["loss"] = total_loss_epoch / sample_num
+            extra_total, extra_logs = self._epoch_extra(sample_num)
+            epoch_logs["loss"] = (total_loss_epoch + extra_total) / sample_num
+            epoch_logs.update(extra_logs)
             if want_metrics:
                 pred_host = pred_log.cpu().numpy().astype("float64")
                 y_host = y_t.numpy() if order is None else y_t[order].numpy()

@@ -664,3 +664,77 @@ class AttnPool(torch.autograd.Function):
         dx = torch.empty_like(x)
         N.check(N.lib().xdfm_attn_pool_bwd(N.ptr(dout), N.ptr(attn), N.ptr(x), B, Lq, E, N.ptr(dscore), N.ptr(dx), N.stream_ptr()))
         return dscore.view(ctx.score_shape), dx
+
+
+# ------------------------------------------------------------------------------------------------
+# xDeepFM Pro: SFG reconstruction losses (deepctr/xdeepfm_pro/sfg_decoder.py:266-309)
+# ------------------------------------------------------------------------------------------------
+def sfg_row_weights(labels, positive_only):
+    """[B] weights mask / num_positive (sfg_decoder.py:266-273); stays on the device."""
+    require_cuda(labels, "sfg_row_weights")
+    y = _f32c(labels).reshape(-1)
+    w = torch.empty_like(y)
+    N.check(N.lib().xdfm_sfg_row_weights(N.ptr(y), y.shape[0], int(bool(positive_only)), N.ptr(w), N.stream_ptr()))
+    return w
+
+
+def _sum1(row_loss):
+    out = torch.empty(1, dtype=torch.float32, device=row_loss.device)
+    n = row_loss.shape[0]
+    if n == 0:
+        return out.zero_()
+    ws = workspace("wcolsum", N.lib().xdfm_wcolsum_workspace_bytes(1), row_loss.device)
+    N.check(N.lib().xdfm_wcolsum(N.ptr(row_loss), n, 1, 1, None, N.ptr(out), 0, N.ptr(ws), ws.numel(), N.stream_ptr()))
+    return out
+
+
+class MaskedCE(torch.autograd.Function):
+    """sum_r row_w[r] * cross_entropy(logits[r], ids[r, col])  ->  [1].  Forward and gradient in one pass per row."""
+
+    @staticmethod
+    def forward(ctx, logits, ids, col, row_w):
+        require_cuda(logits, "MaskedCE")
+        logits = _f32c(logits)
+        R, V = logits.shape
+        row_loss = torch.empty(R, dtype=torch.float32, device=logits.device)
+        dlogits = torch.empty_like(logits)
+        tgt = ids[:, col:]           # element (r, 0) at stride ids.shape[1]
+        N.check(N.lib().xdfm_masked_ce(N.ptr(logits), ctypes_ptr_offset(ids, col), ids.shape[1], N.ptr(row_w), R, V, N.ptr(row_loss),
+                                       N.ptr(dlogits), N.stream_ptr()))
+        del tgt
+        ctx.save_for_backward(dlogits)
+        return _sum1(row_loss)
+
+    @staticmethod
+    def backward(ctx, g):
+        (dlogits,) = ctx.saved_tensors
+        return dlogits * g.reshape(1, 1), None, None, None
+
+
+class MaskedMSE(torch.autograd.Function):
+    """sum_r row_w[r] * mean_j (pred[r, j] - target[r, j])^2  ->  [1]."""
+
+    @staticmethod
+    def forward(ctx, pred, target, row_w):
+        require_cuda(pred, "MaskedMSE")
+        pred, target = _f32c(pred), _f32c(target)
+        R, nd = pred.shape
+        row_loss = torch.empty(R, dtype=torch.float32, device=pred.device)
+        dpred = torch.empty_like(pred)
+        N.check(N.lib().xdfm_masked_mse(N.ptr(pred), N.ptr(target), N.ptr(row_w), R, nd, N.ptr(row_loss), N.ptr(dpred), N.stream_ptr()))
+        ctx.save_for_backward(dpred)
+        return _sum1(row_loss)
+
+    @staticmethod
+    def backward(ctx, g):
+        (dpred,) = ctx.saved_tensors
+        return dpred * g.reshape(1, 1), None, None
+
+
+def ctypes_ptr_offset(t, elem_offset):
+    """Device pointer of element `elem_offset` of a contiguous CUDA tensor."""
+    import ctypes
+    require_cuda(t, "pointer")
+    if not t.is_contiguous():
+        raise RuntimeError("xdeepfm-b200 ops need contiguous tensors")
+    return ctypes.c_void_p(t.data_ptr() + int(elem_offset) * t.element_size())

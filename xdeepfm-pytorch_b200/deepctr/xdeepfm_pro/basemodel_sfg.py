@@ -1,0 +1,120 @@
+"""BaseModel + Supervised Feature Generation (reference: deepctr/xdeepfm_pro/basemodel_sfg.py:96-677).
+
+The reference copies the whole BaseModel and adds `forward_with_sfg`, `compute_sfg_loss` and the `+ sfg_weight * sfg_loss` term
+(basemodel_sfg.py:316-349); here the B200 BaseModel is extended instead: the fused train step back-propagates the BCE gradient
+and the SFG loss in one autograd pass, the SFG loss is accumulated on the device and reported as `History['sfg_loss']`."""
+import torch
+
+from .. import ops
+from ..inputs import DenseFeat, SparseFeat
+from ..models.basemodel import BaseModel
+from .sfg_decoder import SFGDecoder, SFGLoss
+
+
+class BaseModelSFG(BaseModel):
+    def __init__(self, linear_feature_columns, dnn_feature_columns, l2_reg_linear=1e-5, l2_reg_embedding=1e-5, init_std=0.0001,
+                 seed=1024, task='binary', device='cpu', gpus=None, use_sfg=True, sfg_weight=0.1, sfg_hidden_units=(128, 64),
+                 sfg_dropout=0.1, sfg_positive_only=True, sfg_use_label_attention=True):
+        super().__init__(linear_feature_columns, dnn_feature_columns, l2_reg_linear=l2_reg_linear,
+                         l2_reg_embedding=l2_reg_embedding, init_std=init_std, seed=seed, task=task, device=device, gpus=gpus)
+        self.use_sfg, self.sfg_weight, self.sfg_positive_only = use_sfg, sfg_weight, sfg_positive_only
+        self.sparse_feature_columns = [fc for fc in dnn_feature_columns if isinstance(fc, SparseFeat)] if dnn_feature_columns else []
+        self.dense_feature_columns = [fc for fc in dnn_feature_columns if isinstance(fc, DenseFeat)] if dnn_feature_columns else []
+        self.embedding_dim = self.sparse_feature_columns[0].embedding_dim if self.sparse_feature_columns else 8
+        if use_sfg:
+            dims = {fc.name: fc.vocabulary_size for fc in self.sparse_feature_columns}
+            dense_names = [fc.name for fc in self.dense_feature_columns]
+            self.sfg_decoder = SFGDecoder(self.embedding_dim, dims, dense_names, hidden_units=sfg_hidden_units,
+                                          dropout_rate=sfg_dropout, use_label_aware_attention=sfg_use_label_attention, device=device)
+            self.sfg_loss_fn = SFGLoss([fc.name for fc in self.sparse_feature_columns], dense_names,
+                                       positive_only=sfg_positive_only, device=device)
+        else:
+            self.sfg_decoder = None
+            self.sfg_loss_fn = None
+        self._sfg_accum = None
+        self.to(device)
+
+    # ---- SFG loss on the split (ids, dense) feed ------------------------------------------------------
+    def sfg_loss_ids(self, ids_all, dense_all, emb, labels):
+        """SFG loss [scalar tensor] from this step's embeddings `emb` [B, m, D] (sfg_decoder.py:116-157, 266-309); the targets
+        are the ids / dense values themselves (basemodel_sfg.py:446-466)."""
+        ids = self._select(ids_all, self._dnn_sparse_sel)
+        dd = self.dnn_dense(dense_all)
+        dec = self.sfg_decoder
+        flat = emb.reshape(emb.shape[0], -1)
+        dec_in = torch.cat([flat, dd], dim=-1) if dd.shape[1] > 0 else flat
+        h = dec.hidden(dec_in, labels)
+        row_w = ops.sfg_row_weights(labels, self.sfg_positive_only)
+        fn = self.sfg_loss_fn
+        total = None
+        for f, fc in enumerate(self.sparse_feature_columns):
+            head = dec.sparse_heads[fc.name]
+            l = ops.MaskedCE.apply(ops.linear_act(h, head.weight, head.bias), ids, f, row_w)
+            total = l if total is None else total + l
+        total = torch.zeros(1, device=emb.device) if total is None else fn.sparse_weight * total
+        if dec.dense_head is not None and dd.shape[1] > 0:
+            pred = ops.linear_act(h, dec.dense_head.weight, dec.dense_head.bias)
+            total = total + fn.dense_weight * ops.MaskedMSE.apply(pred, dd, row_w)
+        return total.reshape(())
+
+    def compute_sfg_loss(self, X, sparse_embedding_list, dense_value_list, labels):
+        """Reference-shaped entry (basemodel_sfg.py:420-476)."""
+        if not self.use_sfg or self.sfg_decoder is None:
+            return torch.tensor(0.0, device=self.device), {}
+        ids, dense = self.split_input(X)
+        emb = torch.cat(list(sparse_embedding_list), dim=1)
+        loss = self.sfg_loss_ids(ids, dense, emb, labels)
+        return loss, {'sfg_loss': loss, 'sfg_loss_dict': {'sfg_total': loss.detach()}}
+
+    def forward_with_sfg(self, X, y=None):
+        """(y_pred, sfg_info) like the reference (xdeepfm_pro.py:203-274): sfg_info only in training mode with labels."""
+        X = X.to(self.device) if not X.is_cuda else X
+        ids, dense = self.split_input(X)
+        y_pred = self.forward_ids(ids, dense)
+        info = None
+        if self.use_sfg and y is not None and self.training:
+            loss = self.sfg_loss_ids(ids, dense, self._last_emb, y.to(self.device))
+            info = {'sfg_loss': loss, 'sfg_loss_dict': {'sfg_total': loss.detach()}}
+        return y_pred, info
+
+    def forward(self, X):
+        return self.forward_with_sfg(X, None)[0]
+
+    # ---- fused train step: BCE gradient and sfg_weight * SFG loss back-propagated together ---------------
+    def _train_step_inner(self, opt, ids, dense, y, loss_accum, pred_log, pred_off):
+        y_pred = self.forward_ids(ids, dense)
+        yv = y.reshape(-1)
+        roots, grads = [], []
+        if self._loss_name == "binary_crossentropy":
+            _, dy = ops.bce_sum(y_pred, yv, loss_accum)
+            roots.append(y_pred)
+            grads.append(dy.view_as(y_pred))
+        else:
+            loss = self.loss_func(y_pred.reshape(-1), yv, reduction="sum")
+            loss_accum += loss.detach().double()
+            roots.append(loss)
+            grads.append(torch.ones_like(loss))
+        if self.use_sfg and self.sfg_decoder is not None:
+            sfg = self.sfg_loss_ids(ids, dense, self._last_emb, yv)
+            if self._sfg_accum is None or self._sfg_accum.device != sfg.device:
+                self._sfg_accum = torch.zeros(1, dtype=torch.float64, device=sfg.device)
+            self._sfg_accum += sfg.detach().double()
+            roots.append(sfg)
+            grads.append(torch.full_like(sfg, float(self.sfg_weight)))
+        torch.autograd.backward(roots, grads)
+        opt.step(apply_l2=True)
+        if pred_log is not None:
+            pred_log[pred_off:pred_off + yv.shape[0]] = y_pred.detach().reshape(-1)
+        return y_pred
+
+    def _epoch_begin(self):
+        if self._sfg_accum is not None:
+            self._sfg_accum.zero_()
+
+    def _epoch_extra(self, sample_num):
+        """(extra total-loss sum, extra History entries): total += sfg_weight * sum(sfg), History['sfg_loss'] = sum(sfg) / N
+        (basemodel_sfg.py:344, 369-371)."""
+        if not self.use_sfg:
+            return 0.0, {}
+        s = 0.0 if self._sfg_accum is None else float(self._sfg_accum.item())
+        return self.sfg_weight * s, {"sfg_loss": s / sample_num}
