@@ -135,6 +135,9 @@ int xdfm_rows_opt(const xdfm_opt_cfg* cfg, const float* opt_dev, float* const* w
                   const int32_t* num_segments, int64_t max_segments, float grad_scale, uint32_t* touched_bitmap, int dense_pass,
                   double* reg_out, void* stream);
 
+/* diagnostic: 1 = first version of the dense-table streaming pass, 2 = unrolled / streaming-hint version (default) */
+void xdfm_set_rows_opt_dense_version(int v);
+
 /* ---- CIN layer on the tensor cores (bf16 operands, fp32 accumulate; deepctr/layers/interaction.py:218-246).
  * Activations use a ROW layout: one row per (sample, d), channels contiguous:
  *   x0t [B*D, mP] bf16 (mP = m rounded up to 8, zero padded; produced by xdfm_to_rows_bf16),
@@ -174,6 +177,16 @@ int xdfm_rows_to_cols_bf16(const void* src, int64_t pitch, int64_t R, int C, int
 int64_t xdfm_cin_bwd_dw_tc_workspace_bytes(int64_t B, int m, int Hp, int H, int D);
 int xdfm_cin_bwd_dw_tc(const void* dyT, const void* xkT, const void* x0T, int64_t B, int m, int Hp, int H, int D, float* dW, float* db,
                        void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- dense layers on the tensor cores (bf16 operands, fp32 accumulate): DNN.forward / autograd in bf16 precision
+ * (deepctr/layers/core.py:120-134).  C[M,N] fp32 (row pitch ldc) = act(A[M,K] . B[N,K]^T + bias[N]); A / B are bf16 K-major with
+ * row pitches lda / ldb (elements, multiples of 8) as produced by xdfm_cvt_bf16; workspace = xdfm_gemm_tc_workspace_bytes (split-K
+ * partials, reduced in a fixed order).
+ * xdfm_cvt_bf16: fp32 [R, C] (row pitch ld) -> bf16 [R, dst_pitch] or, transposed, [C, dst_pitch]; padding columns are zeros. */
+int64_t xdfm_gemm_tc_workspace_bytes(int M, int N, int K);
+int xdfm_gemm_tc(int M, int N, int K, const void* A, int64_t lda, const void* Bm, int64_t ldb, float* C, int ldc, const float* bias,
+                 int act, void* workspace, int64_t workspace_bytes, void* stream);
+int xdfm_cvt_bf16(const float* src, int R, int C, int64_t ld, int transpose, void* dst, int64_t dst_pitch, void* stream);
 
 /* ---- field self-attention block over the CIN feature maps (deepctr/layers/cin_attention.py).
  * q/k/v/o/dout [B, L, E] fp32 (E = heads * head_dim, head_dim <= 32); lse [B, heads, L] = log2-sum-exp2 of the scaled scores.

@@ -1,0 +1,55 @@
+"""Tensor-core dense layers (csrc/gemm_tc.cu): bf16 operands / fp32 accumulate.  Reference = the same product computed in fp64 on
+bf16-rounded operands (tolerance 1e-5 of the output scale: only the accumulation order differs), and the fp32 oracle layer at the
+stated bf16 tolerance 2e-2."""
+import pytest
+import torch
+
+from deepctr import ops
+from tests.helpers import assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).double()
+
+
+@pytest.mark.parametrize("M,N,K,act", [(8192, 400, 429, "relu"), (300, 16, 40, None), (128, 256, 64, "tanh"), (1, 1, 1, None),
+                                      (1000, 429, 400, None), (400, 429, 8192, None), (64, 600, 100, "sigmoid"), (129, 257, 65, "relu")])
+def test_gemm_tc_matches_bf16_product(M, N, K, act):
+    g = torch.Generator().manual_seed(M + N + K)
+    A, Bm, bias = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    ref = _bf(A) @ _bf(Bm).t() + bias.double()
+    ref = {"relu": torch.relu, "tanh": torch.tanh, "sigmoid": torch.sigmoid, None: lambda t: t}[act](ref)
+    Ab, Bb = ops.cvt_bf16(A.to(DEV)), ops.cvt_bf16(Bm.to(DEV))
+    assert Ab.shape == (M, (K + 7) // 8 * 8) and bool((Ab[:, K:] == 0).all())
+    out = ops.gemm_tc(Ab, Bb, M, N, K, bias.to(DEV), ops.N.ACT[act])
+    assert_close(out, ref, 1e-5, 1e-5 * max(ref.abs().max().item(), 1.0), "gemm_tc")
+
+
+def test_cvt_bf16_transpose():
+    g = torch.Generator().manual_seed(0)
+    src = torch.randn(77, 45, generator=g)
+    big = torch.randn(77, 60, generator=g)
+    big[:, :45] = src
+    t = ops.cvt_bf16(big.to(DEV)[:, :45], transpose=True)          # strided source (row pitch 60)
+    assert t.shape == (45, 80)
+    assert torch.equal(t[:, :77].cpu(), src.t().to(torch.bfloat16)) and bool((t[:, 77:] == 0).all())
+
+
+@pytest.mark.parametrize("B,K,Nn,act", [(513, 429, 400, "relu"), (64, 40, 24, None)])
+def test_linear_act_bf16_forward_backward(B, K, Nn, act):
+    g = torch.Generator().manual_seed(B)
+    x, W, b, dy = torch.randn(B, K, generator=g), torch.randn(Nn, K, generator=g) / K ** 0.5, torch.randn(Nn, generator=g), \
+        torch.randn(B, Nn, generator=g)
+    xd, Wd, bd = x.double().requires_grad_(True), W.double().requires_grad_(True), b.double().requires_grad_(True)
+    ref = xd @ Wd.t() + bd
+    ref = torch.relu(ref) if act == "relu" else ref
+    ref.backward(dy.double())
+    xg, Wg, bg = x.to(DEV).requires_grad_(True), W.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    out = ops.linear_act(xg, Wg, bg, act, precision="bf16")
+    out.backward(dy.to(DEV))
+    tol = 2e-2          # stated bf16 tolerance (operands rounded to 8 mantissa bits), relative to each tensor's scale
+    for got, want, what in ((out, ref, "y"), (xg.grad, xd.grad, "dx"), (Wg.grad, Wd.grad, "dW"), (bg.grad, bd.grad, "db")):
+        assert_close(got, want, tol, tol * want.abs().max().item(), what)

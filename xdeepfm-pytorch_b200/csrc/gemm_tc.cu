@@ -1,0 +1,242 @@
+// Dense layers on the tensor cores: C[M,N] = act(A[M,K] . B[N,K]^T + bias[N]), bf16 operands, fp32 accumulate in TMEM.
+//
+// Replaces (reference, file:line): nn.Linear + ReLU of DNN.forward (deepctr/layers/core.py:120-134) and its autograd
+// (dX = dY.W, dW = dY^T.X) when the model runs in bf16 precision (BASELINE config 2 "bf16"); the fp32 SGEMM of dense.cu stays
+// the exact-precision mode.
+//
+// Both operands are K-major bf16 matrices (row pitch a multiple of 8 elements) produced by xdfm_cvt_bf16 -- which also does the
+// transposes the backward GEMMs need -- and streamed by TMA (SWIZZLE_128B, 64-wide K chunks, OOB rows/cols zero-filled) through
+// a 4-stage mbarrier ring; one elected thread issues tcgen05.mma kind::f16 (M=128, N=BN<=256, K=16) with both operands in
+// shared memory; four epilogue warps read the accumulator back with tcgen05.ld and apply bias + activation.  One CTA per
+// 128 x BN output tile and K split; split-K partials are reduced in a fixed order by a second kernel (deterministic).
+#include "tc_common.cuh"
+#include "../../include/xdfm.h"
+
+using namespace tc;
+
+#define GT_THREADS 192     // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
+#define GT_STAGES 4
+
+struct GemmTcParams {
+  float* C;                 // [M, ldc] (splits == 1)
+  float* partial;           // [splits, M, N] (splits > 1)
+  const float* bias;
+  int M, N, K, ldc, BN, act, splits, chunks_total, chunks_per_split;
+};
+
+struct __align__(8) GemmTcBars {
+  uint64_t full[GT_STAGES], empty[GT_STAGES];
+  uint64_t acc_full;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == XDFM_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == XDFM_ACT_TANH) return tanhf(v);
+  if (act == XDFM_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+  return v;
+}
+
+__global__ void __launch_bounds__(GT_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_bytes = 128 * 128, b_bytes = (uint32_t)p.BN * 128;
+  const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
+  GemmTcBars* bars = reinterpret_cast<GemmTcBars*>(smem + (size_t)GT_STAGES * stage_bytes);
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * p.BN, split = blockIdx.z;
+  const int c_begin = split * p.chunks_per_split;
+  const int c_end = min(p.chunks_total, c_begin + p.chunks_per_split);
+  const int nchunks = c_end - c_begin;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < GT_STAGES; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    mbar_init(&bars->acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, 256);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&tmA);
+      prefetch_tmap(&tmB);
+      for (int c = 0; c < nchunks; ++c) {
+        const int s = c % GT_STAGES;
+        if (c >= GT_STAGES) mbar_wait(&bars->empty[s], ((c / GT_STAGES) - 1) & 1);
+        mbar_arrive_expect_tx(&bars->full[s], a_bytes + b_bytes);
+        uint8_t* sa = smem + (size_t)s * stage_bytes;
+        tma_load_2d(sa, &tmA, (c_begin + c) * 64, m0, &bars->full[s]);
+        tma_load_2d(sa + a_bytes, &tmB, (c_begin + c) * 64, n0, &bars->full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_bf16(128, p.BN);
+    for (int c = 0; c < nchunks; ++c) {
+      const int s = c % GT_STAGES;
+      mbar_wait(&bars->full[s], (c / GT_STAGES) & 1);
+      fence_after_sync();
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint64_t adesc = make_desc_k_sw128(sa), bdesc = make_desc_k_sw128(sa + a_bytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&bars->empty[s]);
+        if (c == nchunks - 1) umma_commit(&bars->acc_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;                       // TMEM lane quarter of this warp
+    const int row = m0 + q * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (nchunks > 0) {
+      mbar_wait(&bars->acc_full, 0);
+      fence_after_sync();
+    }
+    float* dst = nullptr;
+    if (row < p.M) dst = p.splits > 1 ? p.partial + ((size_t)split * p.M + row) * p.N : p.C + (size_t)row * p.ldc;
+    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+      uint32_t v[16];
+      if (nchunks > 0) {
+        tmem_ld_x16(taddr + c0, v);
+        tmem_wait_ld();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0u;
+      }
+      if (dst == nullptr) continue;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int col = n0 + c0 + i;
+        if (col < p.N) {
+          float y = __uint_as_float(v[i]);
+          if (p.splits == 1) {
+            if (p.bias != nullptr) y += __ldg(p.bias + col);
+            y = apply_act(y, p.act);
+          }
+          dst[col] = y;
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+__global__ void gemm_tc_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, const float* __restrict__ bias, int act,
+                                      float* __restrict__ C, int ldc) {
+  const int64_t total = (int64_t)M * N;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += partial[(int64_t)z * total + e];
+    const int col = (int)(e % N);
+    if (bias != nullptr) s += bias[col];
+    C[(e / N) * ldc + col] = apply_act(s, act);
+  }
+}
+
+static int gemm_tc_plan(int M, int N, int K, int* BN, int* n_tiles, int* splits, int* chunks_per_split) {
+  *n_tiles = (N + 255) / 256;
+  *BN = ((N + *n_tiles - 1) / *n_tiles + 15) / 16 * 16;
+  const int chunks = (K + 63) / 64;
+  const int tiles = ((M + 127) / 128) * *n_tiles;
+  int s = 1;
+  const int sms = xdfm_num_sms();
+  if (tiles * 2 <= sms) s = std::min(chunks, std::max(1, sms / tiles));     // few output tiles, long K: split the reduction
+  *chunks_per_split = (chunks + s - 1) / s;
+  *splits = (chunks + *chunks_per_split - 1) / *chunks_per_split;
+  return chunks;
+}
+
+extern "C" int64_t xdfm_gemm_tc_workspace_bytes(int M, int N, int K) {
+  int BN, nt, splits, cps;
+  gemm_tc_plan(M, N, K, &BN, &nt, &splits, &cps);
+  return splits > 1 ? (int64_t)splits * M * N * 4 : 256;
+}
+
+// A [M, K] bf16 row pitch lda, Bm [N, K] bf16 row pitch ldb (elements, multiples of 8; 16-byte aligned bases); C fp32 [M, ldc]
+extern "C" int xdfm_gemm_tc(int M, int N, int K, const void* A, int64_t lda, const void* Bm, int64_t ldb, float* C, int ldc,
+                            const float* bias, int act, void* workspace, int64_t workspace_bytes, void* stream) {
+  XDFM_CHECK_ARG(M >= 0 && N >= 1 && K >= 1 && ldc >= N, "gemm_tc: bad shape M=%d N=%d K=%d ldc=%d", M, N, K, ldc);
+  XDFM_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && lda >= K && ldb >= K && ((uintptr_t)A % 16 == 0) && ((uintptr_t)Bm % 16 == 0),
+                 "gemm_tc: operands must be 16-byte aligned with row pitches (%lld, %lld) multiples of 8 and >= K=%d", (long long)lda,
+                 (long long)ldb, K);
+  if (M == 0) return XDFM_OK;
+  GemmTcParams p;
+  int n_tiles;
+  p.chunks_total = gemm_tc_plan(M, N, K, &p.BN, &n_tiles, &p.splits, &p.chunks_per_split);
+  p.C = C; p.partial = (float*)workspace; p.bias = bias; p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.act = act;
+  if (p.splits > 1)
+    XDFM_CHECK_ARG(workspace != nullptr && workspace_bytes >= (int64_t)p.splits * M * N * 4, "gemm_tc: workspace too small");
+  CUtensorMap tmA, tmB;
+  int rc = xdfm_make_tmap_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 128, 64, 1);
+  if (rc) return rc;
+  rc = xdfm_make_tmap_bf16(&tmB, Bm, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, (uint32_t)p.BN, 64, 1);
+  if (rc) return rc;
+  const uint32_t stage_bytes = 128 * 128 + (((uint32_t)p.BN * 128 + 1023) & ~1023u);
+  const size_t smem = (size_t)GT_STAGES * stage_bytes + sizeof(GemmTcBars) + 64;
+  cudaStream_t st = (cudaStream_t)stream;
+  XDFM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((M + 127) / 128, n_tiles, p.splits);
+  gemm_tc_kernel<<<grid, GT_THREADS, smem, st>>>(tmA, tmB, p);
+  XDFM_LAUNCH_CHECK();
+  if (p.splits > 1) {
+    int blocks = (int)std::min<int64_t>((int64_t)xdfm_num_sms() * 4, ceil_div64((int64_t)M * N, 256));
+    gemm_tc_reduce_kernel<<<blocks, 256, 0, st>>>(p.partial, p.splits, M, N, bias, act, C, ldc);
+    XDFM_LAUNCH_CHECK();
+  }
+  return XDFM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 [R, C] (row pitch ld) -> bf16, either [R, CP] (transpose = 0) or [C, RP] (transpose = 1); padding columns are zero
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cvt_bf16_kernel(const float* __restrict__ src, int R, int C, int64_t ld, __nv_bfloat16* __restrict__ dst,
+                                                       int64_t dpitch, int dcols) {
+  const int64_t total = (int64_t)R * dcols;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / dcols;
+    const int c = (int)(e - r * dcols);
+    dst[r * dpitch + c] = __float2bfloat16(c < C ? src[r * ld + c] : 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(256) cvt_bf16_t_kernel(const float* __restrict__ src, int R, int C, int64_t ld,
+                                                         __nv_bfloat16* __restrict__ dst, int64_t dpitch, int dcols) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < R && c < C) ? src[(int64_t)r * ld + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;          // dst row = c, dst col = r
+    if (c < C && r < dcols) dst[(int64_t)c * dpitch + r] = __float2bfloat16(tile[tx][i]);
+  }
+}
+
+extern "C" int xdfm_cvt_bf16(const float* src, int R, int C, int64_t ld, int transpose, void* dst, int64_t dst_pitch, void* stream) {
+  const int drows = transpose ? C : R, dcols_true = transpose ? R : C;
+  XDFM_CHECK_ARG(R >= 0 && C >= 1 && ld >= C && dst_pitch % 8 == 0 && dst_pitch >= dcols_true,
+                 "cvt_bf16: bad shape R=%d C=%d ld=%lld dst_pitch=%lld", R, C, (long long)ld, (long long)dst_pitch);
+  if (R == 0) return XDFM_OK;
+  (void)drows;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int dcols = (int)dst_pitch;            // write the padding too (zeros)
+  if (!transpose) {
+    int blocks = (int)std::min<int64_t>((int64_t)xdfm_num_sms() * 8, ceil_div64((int64_t)R * dcols, 256));
+    cvt_bf16_kernel<<<blocks, 256, 0, st>>>(src, R, C, ld, (__nv_bfloat16*)dst, dst_pitch, dcols);
+  } else {
+    dim3 grid((dcols + 31) / 32, (C + 31) / 32);
+    cvt_bf16_t_kernel<<<grid, 256, 0, st>>>(src, R, C, ld, (__nv_bfloat16*)dst, dst_pitch, dcols);
+  }
+  XDFM_LAUNCH_CHECK();
+  return XDFM_OK;
+}

@@ -231,6 +231,90 @@ __global__ void __launch_bounds__(256) rows_opt_dense_kernel(xdfm_opt_cfg cfg, c
   block_accumulate_double(reg, reg_out);
 }
 
+// v2 of the dense pass: two independent 4-element vectors per thread and iteration (6 x 16-byte loads in flight before any
+// arithmetic), streaming (evict-first) loads/stores -- every byte is touched exactly once per step --, one bitmap probe per
+// vector when a row is a whole number of vectors, optimizer kind resolved at compile time.
+__device__ __forceinline__ float4 ld_stream(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st_stream(float* p, const float4& v) { __stcs(reinterpret_cast<float4*>(p), v); }
+
+template <int KIND>
+__device__ __forceinline__ void opt_apply_k(const OptScalars& h, float& w, float g, float& s1, float& s2) {
+  if (KIND == XDFM_OPT_SGD) {
+    w = w - h.lr * g;
+  } else if (KIND == XDFM_OPT_ADAM) {
+    s1 = s1 + h.one_minus_b1 * (g - s1);
+    s2 = s2 * h.b2 + h.one_minus_b2 * (g * g);
+    float denom = sqrtf(s2) / h.bc2_sqrt + h.eps;
+    w = w - h.step_size * (s1 / denom);
+  } else if (KIND == XDFM_OPT_ADAGRAD) {
+    s1 = s1 + g * g;
+    float stdv = sqrtf(s1) + h.eps;
+    w = w - h.clr * (g / stdv);
+  } else {
+    s1 = s1 * h.alpha + h.one_minus_alpha * (g * g);
+    float avg = sqrtf(s1) + h.eps;
+    w = w - h.lr * (g / avg);
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256, 4) rows_opt_dense_v2_kernel(xdfm_opt_cfg cfg, const float* __restrict__ d, TableSet ts, int T, int width,
+                                                                   const uint32_t* __restrict__ touched, double* reg_out) {
+  constexpr bool HAS1 = KIND != XDFM_OPT_SGD, HAS2 = KIND == XDFM_OPT_ADAM;
+  constexpr int U = 2;
+  OptScalars h = load_scalars(cfg, d);
+  const int64_t nvec = ts.vec_off[T];
+  const int wv = width >> 2;                 // vectors per row (width % 4 == 0 on this path)
+  const float l2x2 = 2.f * cfg.l2;
+  float reg = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v0 < nvec; v0 += stride * U) {
+    float4 wq[U], aq[U], bq[U];
+    float* pw[U];
+    float* pa[U];
+    float* pb[U];
+    bool live[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = v0 + u * stride;
+      live[u] = v < nvec;
+      if (live[u]) {
+        const int t = find_tab(ts.vec_off, T, v);
+        const int64_t lv = v - ts.vec_off[t];
+        const int64_t key = ts.row_off[t] + lv / wv;
+        pw[u] = ts.w[t] + lv * 4;
+        wq[u] = ld_stream(pw[u]);
+        if (HAS1) { pa[u] = ts.s1[t] + lv * 4; aq[u] = ld_stream(pa[u]); }
+        if (HAS2) { pb[u] = ts.s2[t] + lv * 4; bq[u] = ld_stream(pb[u]); }
+        if (touched != nullptr && ((__ldg(touched + (key >> 5)) >> (key & 31)) & 1u)) live[u] = false;   // updated by the sparse kernel
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!live[u]) continue;
+      float* wf = reinterpret_cast<float*>(&wq[u]);
+      float* af = reinterpret_cast<float*>(&aq[u]);
+      float* bf = reinterpret_cast<float*>(&bq[u]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float wi = wf[i];
+        reg += cfg.l2 * (wi * wi);
+        float a = HAS1 ? af[i] : 0.f, b = HAS2 ? bf[i] : 0.f;
+        opt_apply_k<KIND>(h, wf[i], l2x2 * wi, a, b);
+        if (HAS1) af[i] = a;
+        if (HAS2) bf[i] = b;
+      }
+      st_stream(pw[u], wq[u]);
+      if (HAS1) st_stream(pa[u], aq[u]);
+      if (HAS2) st_stream(pb[u], bq[u]);
+    }
+  }
+  block_accumulate_double(reg, reg_out);
+}
+
+int g_rows_opt_dense_version = 2;
+extern "C" void xdfm_set_rows_opt_dense_version(int v) { g_rows_opt_dense_version = v; }
+
 static int fill_table_set(TableSet& ts, float* const* w, float* const* s1, float* const* s2, const int64_t* row_off, int T, int width) {
   int64_t voff = 0;
   for (int t = 0; t < T; ++t) {
@@ -268,8 +352,20 @@ extern "C" int xdfm_rows_opt(const xdfm_opt_cfg* cfg, const float* opt_dev, floa
   if (dense_pass) {
     int64_t nvec = ts.vec_off[T];
     if (nvec > 0) {
-      int blocks = (int)min((int64_t)xdfm_num_sms() * 16, ceil_div64(nvec, 256));
-      rows_opt_dense_kernel<<<max(blocks, 1), 256, 0, st>>>(*cfg, opt_dev, ts, T, width, touched_bitmap, reg_out);
+      bool whole = width % 4 == 0;     // every table is a whole number of 4-element vectors and every vector lies inside one row
+      if (g_rows_opt_dense_version == 2 && whole) {
+        int blocks = (int)min((int64_t)xdfm_num_sms() * 4 * 4, ceil_div64(nvec, 256 * 2));
+        blocks = max(blocks, 1);
+        switch (cfg->kind) {
+          case XDFM_OPT_SGD: rows_opt_dense_v2_kernel<XDFM_OPT_SGD><<<blocks, 256, 0, st>>>(*cfg, opt_dev, ts, T, width, touched_bitmap, reg_out); break;
+          case XDFM_OPT_ADAM: rows_opt_dense_v2_kernel<XDFM_OPT_ADAM><<<blocks, 256, 0, st>>>(*cfg, opt_dev, ts, T, width, touched_bitmap, reg_out); break;
+          case XDFM_OPT_ADAGRAD: rows_opt_dense_v2_kernel<XDFM_OPT_ADAGRAD><<<blocks, 256, 0, st>>>(*cfg, opt_dev, ts, T, width, touched_bitmap, reg_out); break;
+          default: rows_opt_dense_v2_kernel<XDFM_OPT_RMSPROP><<<blocks, 256, 0, st>>>(*cfg, opt_dev, ts, T, width, touched_bitmap, reg_out); break;
+        }
+      } else {
+        int blocks = (int)min((int64_t)xdfm_num_sms() * 16, ceil_div64(nvec, 256));
+        rows_opt_dense_kernel<<<max(blocks, 1), 256, 0, st>>>(*cfg, opt_dev, ts, T, width, touched_bitmap, reg_out);
+      }
       XDFM_LAUNCH_CHECK();
     }
   }

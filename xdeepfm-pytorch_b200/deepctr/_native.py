@@ -82,6 +82,10 @@ _SIGS = {
     "xdfm_sfg_row_weights": (c_int, [_P, c_int64, c_int, _P, _P]),
     "xdfm_masked_ce": (c_int, [_P, _P, c_int64, _P, c_int64, c_int, _P, _P, _P]),
     "xdfm_masked_mse": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P, _P]),
+    "xdfm_gemm_tc_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
+    "xdfm_gemm_tc": (c_int, [c_int, c_int, c_int, _P, c_int64, _P, c_int64, _P, c_int, _P, c_int, _P, c_int64, _P]),
+    "xdfm_cvt_bf16": (c_int, [_P, c_int, c_int, c_int64, c_int, _P, c_int64, _P]),
+    "xdfm_set_rows_opt_dense_version": (None, [c_int]),
     "xdfm_opt_tick": (c_int, [_P, POINTER(OptCfg), _P]),
     "xdfm_flat_opt": (c_int, [POINTER(OptCfg), _P, c_int64, _P, _P, _P, _P, _P, c_float, _P, _P]),
     "xdfm_rows_opt": (c_int, [POINTER(OptCfg), _P, POINTER(_P), POINTER(_P), POINTER(_P), POINTER(c_int64), c_int, c_int, _P, _P, _P,

@@ -1,4 +1,6 @@
 """DNN and PredictionLayer (reference: deepctr/layers/core.py:67-160) on the fused GEMM+bias+activation kernel."""
+import os
+
 import torch
 import torch.nn as nn
 
@@ -25,6 +27,7 @@ class DNN(nn.Module):
         if use_bn:
             self.bn = nn.ModuleList([nn.BatchNorm1d(dims[i + 1]) for i in range(len(dims) - 1)])
         self._fused_act = activation_name(activation)
+        self.precision = os.environ.get("XDFM_DNN_PRECISION", "fp32")   # 'fp32' (SGEMM, reference precision) | 'bf16' (tcgen05)
         self.activation_layers = nn.ModuleList(
             [activation_layer(activation, dims[i + 1], dice_dim) for i in range(len(dims) - 1)])
         for name, p in self.linears.named_parameters():
@@ -36,12 +39,12 @@ class DNN(nn.Module):
         x = inputs
         for i, lin in enumerate(self.linears):
             if self.use_bn or self._fused_act is None:
-                x = ops.linear_act(x, lin.weight, lin.bias, None)
+                x = ops.linear_act(x, lin.weight, lin.bias, None, precision=self.precision)
                 if self.use_bn:
                     x = self.bn[i](x)
                 x = self.activation_layers[i](x)
             else:
-                x = ops.linear_act(x, lin.weight, lin.bias, self._fused_act)
+                x = ops.linear_act(x, lin.weight, lin.bias, self._fused_act, precision=self.precision)
             if self.dropout_rate > 0:
                 x = self.dropout(x)
         return x

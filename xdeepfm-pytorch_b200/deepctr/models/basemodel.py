@@ -616,7 +616,10 @@ class BaseModel(nn.Module):
             want_metrics = verbose > 0 and len(self.metrics) > 0
             pred_log = torch.empty(n_local, dtype=torch.float32, device=dev) if want_metrics else None
             off = 0
-            self.train()
+            # NB: like the reference (basemodel.py:202, :332 / basemodel_sfg.py:275, :488) the model is put in train mode ONCE
+            # before the epoch loop; the validation predict() leaves it in eval mode, so from the second epoch on dropout -- and
+            # the SFG term of xDeepFM Pro, which is gated on self.training (xdeepfm_pro.py:265) -- are off when validation data
+            # is given.  Kept for result parity (tests/golden/fit_pro_small_adam.npz: reference History['sfg_loss'] = [0.41, 0.0]).
             for ids_b, dense_b, y_b in self._batches(ids, dense, y_t, batch_size, order):
                 nb = ids_b.shape[0]
                 if fused:

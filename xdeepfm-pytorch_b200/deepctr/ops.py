@@ -494,7 +494,77 @@ class LinearAct(torch.autograd.Function):
         return dx, dW, db, None
 
 
-def linear_act(x, W, b=None, activation=None):
+def cvt_bf16(src, transpose=False):
+    """fp32 [R, C] -> bf16 [R, C8] (or, transposed, [C, R8]); pitch rounded up to 8 elements, padding zero."""
+    R, C = src.shape
+    rows, cols = (C, R) if transpose else (R, C)
+    dst = torch.empty((rows, _r8(cols)), dtype=torch.bfloat16, device=src.device)
+    N.check(N.lib().xdfm_cvt_bf16(N.ptr(src), R, C, src.stride(0), int(transpose), N.ptr(dst), dst.shape[1], N.stream_ptr()))
+    return dst
+
+
+def gemm_tc(A, Bm, M, Nn, K, bias=None, act=0):
+    """fp32 [M, Nn] = act(A[M, K] . Bm[Nn, K]^T + bias) on tcgen05; A / Bm bf16 K-major (from cvt_bf16)."""
+    L = N.lib()
+    C = torch.empty((M, Nn), dtype=torch.float32, device=A.device)
+    nb = L.xdfm_gemm_tc_workspace_bytes(M, Nn, K)
+    ws = workspace("gemm_tc", nb, A.device)
+    with timed("gemm"):
+        N.check(L.xdfm_gemm_tc(M, Nn, K, N.ptr(A), A.shape[1], N.ptr(Bm), Bm.shape[1], N.ptr(C), Nn, N.ptr(bias), act, N.ptr(ws),
+                               ws.numel(), N.stream_ptr()))
+    return C
+
+
+class LinearActTC(torch.autograd.Function):
+    """y = act(x @ W.T + b) with bf16 operands on the tensor cores (fp32 accumulate, fp32 activations in HBM)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, act):
+        require_cuda(x, "LinearActTC")
+        shp = x.shape
+        x2 = _f32c(x).reshape(-1, shp[-1])
+        W = _f32c(W)
+        Bn, K = x2.shape
+        Nn = W.shape[0]
+        with timed("gemm_cvt"):
+            xb, wb = cvt_bf16(x2), cvt_bf16(W)
+        y = gemm_tc(xb, wb, Bn, Nn, K, None if b is None else _f32c(b), act)
+        ctx.save_for_backward(x2, W, y)
+        ctx.act, ctx.has_bias, ctx.shp = act, b is not None, shp
+        return y.view(*shp[:-1], Nn)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, W, y = ctx.saved_tensors
+        Bn, K = x2.shape
+        Nn = W.shape[0]
+        dy = _f32c(dy).reshape(Bn, Nn)
+        L = N.lib()
+        if ctx.act != 0:
+            dym = torch.empty_like(dy)
+            N.check(L.xdfm_act_bwd(N.ptr(dy), N.ptr(y), N.ptr(dym), dy.numel(), ctx.act, N.stream_ptr()))
+        else:
+            dym = dy
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            with timed("gemm_cvt"):
+                dyb, wT = cvt_bf16(dym), cvt_bf16(W, transpose=True)             # [Bn, Nn], [K, Nn]
+            dx = gemm_tc(dyb, wT, Bn, K, Nn).view(ctx.shp)
+        if ctx.needs_input_grad[1]:
+            with timed("gemm_cvt"):
+                dyT, xT = cvt_bf16(dym, transpose=True), cvt_bf16(x2, transpose=True)   # [Nn, Bn], [K, Bn]
+            dW = gemm_tc(dyT, xT, Nn, K, Bn)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.empty(Nn, dtype=torch.float32, device=dy.device)
+            ws = workspace("wcolsum", L.xdfm_wcolsum_workspace_bytes(Nn), dy.device)
+            N.check(L.xdfm_wcolsum(N.ptr(dym), Bn, Nn, Nn, None, N.ptr(db), 0, N.ptr(ws), ws.numel(), N.stream_ptr()))
+        return dx, dW, db, None
+
+
+def linear_act(x, W, b=None, activation=None, precision="fp32"):
+    """precision 'fp32' = exact CUDA-core SGEMM, 'bf16' = tcgen05 GEMM (bf16 operands, fp32 accumulate)."""
+    if precision == "bf16":
+        return LinearActTC.apply(x, W, b, N.ACT[activation])
     return LinearAct.apply(x, W, b, N.ACT[activation])
 
 

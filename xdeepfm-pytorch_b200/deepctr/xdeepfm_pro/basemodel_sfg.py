@@ -94,7 +94,7 @@ class BaseModelSFG(BaseModel):
             loss_accum += loss.detach().double()
             roots.append(loss)
             grads.append(torch.ones_like(loss))
-        if self.use_sfg and self.sfg_decoder is not None:
+        if self.use_sfg and self.sfg_decoder is not None and self.training:      # gated on training mode: xdeepfm_pro.py:265
             sfg = self.sfg_loss_ids(ids, dense, self._last_emb, yv)
             if self._sfg_accum is None or self._sfg_accum.device != sfg.device:
                 self._sfg_accum = torch.zeros(1, dtype=torch.float64, device=sfg.device)
