@@ -498,8 +498,12 @@ def cvt_bf16(src, transpose=False):
     """fp32 [R, C] -> bf16 [R, C8] (or, transposed, [C, R8]); pitch rounded up to 8 elements, padding zero."""
     R, C = src.shape
     rows, cols = (C, R) if transpose else (R, C)
+    require_cuda(src, "cvt_bf16")
+    if src.dtype != torch.float32 or (C > 1 and src.stride(1) != 1):
+        src = _f32c(src)
     dst = torch.empty((rows, _r8(cols)), dtype=torch.bfloat16, device=src.device)
-    N.check(N.lib().xdfm_cvt_bf16(N.ptr(src), R, C, src.stride(0), int(transpose), N.ptr(dst), dst.shape[1], N.stream_ptr()))
+    N.check(N.lib().xdfm_cvt_bf16(ctypes_ptr_offset_any(src), R, C, max(src.stride(0), C), int(transpose), N.ptr(dst), dst.shape[1],
+                                  N.stream_ptr()))
     return dst
 
 
@@ -799,6 +803,12 @@ class MaskedMSE(torch.autograd.Function):
     def backward(ctx, g):
         (dpred,) = ctx.saved_tensors
         return dpred * g.reshape(1, 1), None, None
+
+
+def ctypes_ptr_offset_any(t):
+    """Device pointer of a (possibly row-strided) CUDA tensor."""
+    import ctypes
+    return ctypes.c_void_p(t.data_ptr())
 
 
 def ctypes_ptr_offset(t, elem_offset):
