@@ -23,8 +23,9 @@
 // chunk sequence in lock-step and every chunk is fetched ONCE per cluster: CTA c loads rows slice c and TMA-multicasts it into
 // the shared memory of all CTAs of the cluster.
 //
-// TMEM columns (512 allocated): [0, 256) accumulator, [256, 512) a ring of 8 A chunks (64 K-values = 32 columns each) that
-// is aligned with the 64-wide W' chunks, so the MMA warp's inner loop is "wait two barriers, issue four MMAs, commit".
+// TMEM columns (512 allocated): [0, 256) accumulator, [256, 512) a ring of 4 A slots (128 K-values = 64 columns each) that is
+// aligned with the 128-wide W' stages (two 64-wide TMA boxes per barrier), so the MMA warp's inner loop is "wait two barriers,
+// issue eight MMAs, commit": the issue loop costs ~500 cycles per iteration (ncu, round 1), eight MMAs are 832 cycles of tensor work.
 // Warp roles (14 warps): 0 = TMA (W' chunks, x tiles), 1 = MMA issuer + TMEM alloc, 2..5 = Z producers, 6..13 = epilogue
 // (two warps per TMEM lane quarter, alternating 16-column chunks).
 #include "tc_common.cuh"
@@ -34,9 +35,9 @@ using namespace tc;
 
 #define TC_THREADS 448
 #define TC_A_COL0 256
-#define TC_A_SLOTS 8        // A-chunk ring slots
-#define TC_A_SLOT_COLS 32  // 64 bf16 K-values
-#define TC_MAX_NS_W 6      // W' chunk ring depth (run-time, limited by shared memory)
+#define TC_A_SLOTS 4        // A ring slots
+#define TC_A_SLOT_COLS 64  // 128 bf16 K-values = one W' stage (two 64-wide TMA boxes): 8 MMAs per barrier round trip
+#define TC_MAX_NS_W 4      // W' stage ring depth (run-time, limited by shared memory)
 
 struct CinTcParams {
   const __nv_bfloat16* x0t;   // [R, mP]
@@ -48,8 +49,8 @@ struct CinTcParams {
   int m, mP, Hp, H, H_pad, Hs, D, act, hdb, fm_total, col_off;
   int64_t n_tiles;
   int n_iters;                // tile iterations per CTA (uniform over the grid)
-  int n_wchunks;              // 64-wide K chunks per tile (K' = m*HpP padded to a multiple of 64)
-  int ns_w;                   // W' ring depth
+  int n_wchunks;              // 128-wide K stages per tile (K' = m*HpP padded to a multiple of 128)
+  int ns_w;                   // W' ring depth (stages)
 };
 
 struct __align__(8) CinTcBars {
@@ -245,8 +246,9 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // ---- shared memory carve-up
-  const uint32_t w_stage_bytes = (uint32_t)p.H_pad * 128;
-  uint8_t* sW = smem;                                                       // ns_w x [H_pad x 128 B], 1024-aligned
+  const uint32_t w_box_bytes = (uint32_t)p.H_pad * 128;                     // one 64-wide K chunk
+  const uint32_t w_stage_bytes = 2 * w_box_bytes;
+  uint8_t* sW = smem;                                                       // ns_w x 2 x [H_pad x 128 B], 1024-aligned
   const uint32_t x0_tile = (uint32_t)128 * p.mP * 2;                        // [128][mP] bf16
   const uint32_t xk_tile = (uint32_t)128 * HpP * 2;                         // [128][HpP] bf16
   uint8_t* sX0 = sW + (size_t)p.ns_w * w_stage_bytes;                       // 2 tiles
@@ -306,8 +308,13 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           if (!first_pass) mbar_wait(&bars->w_empty[ws], wphase);
           mbar_arrive_expect_tx(&bars->w_full[ws], w_stage_bytes);
           uint8_t* dst = sW + (size_t)ws * w_stage_bytes + (size_t)wr0 * 128;
-          if (csize > 1) tma_load_2d_mcast(dst, &tmW, c * 64, wr0, &bars->w_full[ws], cmask);
-          else tma_load_2d(dst, &tmW, c * 64, wr0, &bars->w_full[ws]);
+          if (csize > 1) {
+            tma_load_2d_mcast(dst, &tmW, c * 128, wr0, &bars->w_full[ws], cmask);
+            tma_load_2d_mcast(dst + w_box_bytes, &tmW, c * 128 + 64, wr0, &bars->w_full[ws], cmask);
+          } else {
+            tma_load_2d(dst, &tmW, c * 128, wr0, &bars->w_full[ws]);
+            tma_load_2d(dst + w_box_bytes, &tmW, c * 128 + 64, wr0, &bars->w_full[ws]);
+          }
           if (++ws == (uint32_t)p.ns_w) { ws = 0; wphase ^= 1; first_pass = false; }
         }
       }
@@ -319,6 +326,7 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     const uint32_t idesc = make_idesc_bf16(128, p.H_pad);
     const uint64_t bdesc0 = make_desc_k_sw128(smem_u32(sW));
     const uint32_t stage_desc_step = w_stage_bytes >> 4;       // descriptor start-address units (16 B)
+    const uint32_t box_desc_step = w_box_bytes >> 4;
     uint32_t ws = 0, wphase = 0;                                // W' ring slot / phase parity
     uint64_t bdesc = bdesc0;                                    // descriptor of ring slot ws
     uint32_t as = 0, aphase = 0;                                // A ring slot / phase parity
@@ -340,6 +348,11 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             umma_ts(tmem_base, a_addr + 8, bdesc + 2, idesc, 1u);
             umma_ts(tmem_base, a_addr + 16, bdesc + 4, idesc, 1u);
             umma_ts(tmem_base, a_addr + 24, bdesc + 6, idesc, 1u);
+            const uint64_t bdesc1 = bdesc + box_desc_step;
+            umma_ts(tmem_base, a_addr + 32, bdesc1, idesc, 1u);
+            umma_ts(tmem_base, a_addr + 40, bdesc1 + 2, idesc, 1u);
+            umma_ts(tmem_base, a_addr + 48, bdesc1 + 4, idesc, 1u);
+            umma_ts(tmem_base, a_addr + 56, bdesc1 + 6, idesc, 1u);
             umma_commit(&bars->a_empty[as]);     // A chunk consumed
           }
           // W' chunk consumed by this CTA: tell every CTA of the cluster (each may overwrite this slot by multicast)
@@ -396,13 +409,21 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           case 4: emit_field<HpP / 2, 16, 0>(xk2, xv2, ring); break;
           case 5: emit_field<HpP / 2, 20, 0>(xk2, xv2, ring); break;
           case 6: emit_field<HpP / 2, 24, 0>(xk2, xv2, ring); break;
-          default: emit_field<HpP / 2, 28, 0>(xk2, xv2, ring); break;
+          case 7: emit_field<HpP / 2, 28, 0>(xk2, xv2, ring); break;
+          case 8: emit_field<HpP / 2, 32, 0>(xk2, xv2, ring); break;
+          case 9: emit_field<HpP / 2, 36, 0>(xk2, xv2, ring); break;
+          case 10: emit_field<HpP / 2, 40, 0>(xk2, xv2, ring); break;
+          case 11: emit_field<HpP / 2, 44, 0>(xk2, xv2, ring); break;
+          case 12: emit_field<HpP / 2, 48, 0>(xk2, xv2, ring); break;
+          case 13: emit_field<HpP / 2, 52, 0>(xk2, xv2, ring); break;
+          case 14: emit_field<HpP / 2, 56, 0>(xk2, xv2, ring); break;
+          default: emit_field<HpP / 2, 60, 0>(xk2, xv2, ring); break;
         }
-        ph = (ph + NI8) & 7;
+        ph = (ph + NI8) & 15;
       }
-      if (ph != 0) {                             // zero-fill the tail of the last K chunk and publish it
+      if (ph != 0) {                             // zero-fill the tail of the last K stage and publish it
         const uint32_t zz[4] = {0u, 0u, 0u, 0u};
-        for (; ph < 8; ++ph) tmem_st_x4(ring.base + ring.as * TC_A_SLOT_COLS + ph * 4, zz);
+        for (; ph < 16; ++ph) tmem_st_x4(ring.base + ring.as * TC_A_SLOT_COLS + ph * 4, zz);
         ring_publish(ring);
       }
       __syncwarp();
@@ -518,10 +539,10 @@ static int cin_tc_geom(int m, int Hp, int H, int D, CinTcGeom* g) {
   g->H_pad = round_up(H, 16);
   g->Hs = round_up(H, 8);
   g->mP = round_up(m, 8);
-  g->n_wchunks = (m * g->HpP + 63) / 64;
-  g->KP = g->n_wchunks * 64;
+  g->n_wchunks = (m * g->HpP + 127) / 128;     // 128-wide stages
+  g->KP = g->n_wchunks * 128;
   size_t fixed = 2 * (size_t)128 * g->mP * 2 + 2 * (size_t)128 * g->HpP * 2 + (size_t)5 * g->H_pad * 4 + sizeof(CinTcBars) + 256;
-  size_t stage = (size_t)g->H_pad * 128;
+  size_t stage = (size_t)g->H_pad * 256;
   int ns = (int)((227 * 1024 - fixed) / stage);
   ns = std::min(ns, TC_MAX_NS_W);
   if (ns < 2) {

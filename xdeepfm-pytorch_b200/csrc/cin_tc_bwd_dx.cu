@@ -25,7 +25,7 @@ using namespace tc;
 #define DX_THREADS 320
 #define DX_ACC_COL0 256
 #define DX_ACC_COLS 128
-#define DX_MAX_NS 4
+#define DX_MAX_NS 8
 
 struct CinDxParams {
   const __nv_bfloat16* dyt;   // [R, Hs]
@@ -38,7 +38,7 @@ struct CinDxParams {
   int64_t n_tiles;
   int n_iters;
   int n_hchunks;              // 64-wide chunks of the reduction dim h per field = ceil(H_pad / 64)
-  int ns;                     // W'' ring depth (slots of one h-chunk: [HpQ rows x 128 B])
+  int ns;                     // W'' ring depth (one slot = one FIELD: n_hchunks boxes of [HpQ rows x 128 B] on one barrier)
 };
 
 struct __align__(8) CinDxBars {
@@ -56,8 +56,9 @@ __global__ void __launch_bounds__(DX_THREADS, 1) cin_bwd_dx_tc_kernel(const __gr
   constexpr int HALF = HpQ / 2;                    // channels per row warp (multiple of 8)
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t w_slot_bytes = (uint32_t)HpQ * 128;
-  uint8_t* sW = smem;                                                         // ns x [HpQ x 128 B]
+  const uint32_t w_box_bytes = (uint32_t)HpQ * 128;                          // one 64-wide h-chunk of one field
+  const uint32_t w_slot_bytes = w_box_bytes * (uint32_t)p.n_hchunks;         // one field
+  uint8_t* sW = smem;                                                         // ns x n_hchunks x [HpQ x 128 B]
   const uint32_t x0_tile = (uint32_t)128 * p.mP * 2;
   uint8_t* sX0 = sW + (size_t)p.ns * w_slot_bytes;                            // 2 x [128][mP] bf16
   float* sDx0 = reinterpret_cast<float*>(sX0 + 2 * (size_t)x0_tile);          // [2 halves][128][mP] fp32 dX0 partials
@@ -106,14 +107,14 @@ __global__ void __launch_bounds__(DX_THREADS, 1) cin_bwd_dx_tc_kernel(const __gr
       for (int it = 0; it < p.n_iters; ++it) {
         if (it + 1 < p.n_iters && tile_of(it + 1) < p.n_tiles) load_x(tile_of(it + 1));
         for (int j = 0; j < p.m; ++j) {
+          if (!first_pass) mbar_wait(&bars->w_empty[ws], wphase);
+          mbar_arrive_expect_tx(&bars->w_full[ws], w_slot_bytes);
           for (int c = 0; c < p.n_hchunks; ++c) {
-            if (!first_pass) mbar_wait(&bars->w_empty[ws], wphase);
-            mbar_arrive_expect_tx(&bars->w_full[ws], w_slot_bytes);
-            uint8_t* dst = sW + (size_t)ws * w_slot_bytes + (size_t)wr0 * 128;
+            uint8_t* dst = sW + (size_t)ws * w_slot_bytes + (size_t)c * w_box_bytes + (size_t)wr0 * 128;
             if (csize > 1) tma_load_2d_mcast(dst, &tmW, c * 64, j * HpQ + wr0, &bars->w_full[ws], cmask);
             else tma_load_2d(dst, &tmW, c * 64, j * HpQ + wr0, &bars->w_full[ws]);
-            if (++ws == (uint32_t)p.ns) { ws = 0; wphase ^= 1; first_pass = false; }
           }
+          if (++ws == (uint32_t)p.ns) { ws = 0; wphase ^= 1; first_pass = false; }
         }
       }
     }
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(DX_THREADS, 1) cin_bwd_dx_tc_kernel(const __gr
     const uint32_t idesc = make_idesc_bf16(128, HpQ);
     const uint64_t bdesc0 = make_desc_k_sw128(smem_u32(sW));
     const uint32_t slot_desc_step = w_slot_bytes >> 4;
+    const uint32_t box_desc_step = w_box_bytes >> 4;
     uint32_t ws = 0, wphase = 0;
     uint64_t bdesc = bdesc0;
     uint32_t jc = 0;            // fields processed so far (accumulator buffer = jc & 1)
@@ -139,31 +141,27 @@ __global__ void __launch_bounds__(DX_THREADS, 1) cin_bwd_dx_tc_kernel(const __gr
           mbar_wait(&bars->acc_empty[ab], ((jc >> 1) - 1) & 1);
           fence_after_sync();
         }
-        int ks = 0;
-        for (int c = 0; c < p.n_hchunks; ++c) {
-          mbar_wait(&bars->w_full[ws], wphase);
-          fence_after_sync();
-          if (elect_one()) {
-            if (active) {
-              const uint32_t d_addr = tmem_base + DX_ACC_COL0 + ab * DX_ACC_COLS;
+        mbar_wait(&bars->w_full[ws], wphase);
+        fence_after_sync();
+        if (elect_one()) {
+          if (active) {
+            const uint32_t d_addr = tmem_base + DX_ACC_COL0 + ab * DX_ACC_COLS;
+            uint64_t bd = bdesc;
+            for (int ks = 0; ks < ksteps; ks += 4, bd += box_desc_step) {
 #pragma unroll
               for (int k4 = 0; k4 < 4; ++k4) {
-                if (ks + k4 < ksteps) umma_ts(d_addr, tmem_base + (uint32_t)(ks + k4) * 8, bdesc + (uint64_t)(k4 * 2), idesc, (ks + k4) > 0 ? 1u : 0u);
+                if (ks + k4 < ksteps) umma_ts(d_addr, tmem_base + (uint32_t)(ks + k4) * 8, bd + (uint64_t)(k4 * 2), idesc, (ks + k4) > 0 ? 1u : 0u);
               }
             }
-            if (csize > 1) umma_commit_mcast(&bars->w_empty[ws], cmask);
-            else umma_commit(&bars->w_empty[ws]);
           }
-          __syncwarp();
-          ks += 4;
-          if (++ws == (uint32_t)p.ns) { ws = 0; wphase ^= 1; bdesc = bdesc0; }
-          else bdesc += slot_desc_step;
+          if (csize > 1) umma_commit_mcast(&bars->w_empty[ws], cmask);
+          else umma_commit(&bars->w_empty[ws]);
+          if (active) umma_commit(&bars->acc_full[ab]);
         }
-        if (active) {
-          if (elect_one()) umma_commit(&bars->acc_full[ab]);
-          __syncwarp();
-          ++jc;
-        }
+        __syncwarp();
+        if (++ws == (uint32_t)p.ns) { ws = 0; wphase ^= 1; bdesc = bdesc0; }
+        else bdesc += slot_desc_step;
+        if (active) ++jc;
       }
       if (active) {
         if (elect_one()) umma_commit(&bars->a_empty);     // all MMAs reading this tile's dY have been issued and will complete
@@ -234,27 +232,30 @@ __global__ void __launch_bounds__(DX_THREADS, 1) cin_bwd_dx_tc_kernel(const __gr
         fence_after_sync();
         const uint32_t acc = tmem_base + lane_addr + DX_ACC_COL0 + ab * DX_ACC_COLS + half * HALF;
         float dot = 0.f;
+        // all of this warp's dZ columns of the field in ONE batch of TMEM loads and one wait: the accumulator is handed back to
+        // the tensor core before the contraction starts
+        uint32_t v[HALF];
 #pragma unroll
         for (int c0 = 0; c0 < HALF; c0 += 8) {
-          uint32_t v[8];
           asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                       : "=r"(v[c0 + 0]), "=r"(v[c0 + 1]), "=r"(v[c0 + 2]), "=r"(v[c0 + 3]), "=r"(v[c0 + 4]), "=r"(v[c0 + 5]),
+                         "=r"(v[c0 + 6]), "=r"(v[c0 + 7])
                        : "r"(acc + c0)
                        : "memory");
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 8; i += 2) {
-            const float2 xf = __bfloat1622float2(xk2[(c0 + i) / 2]);
-            const float z0 = __uint_as_float(v[i]), z1 = __uint_as_float(v[i + 1]);
-            dxk[c0 + i] = fmaf(z0, x0v, dxk[c0 + i]);
-            dxk[c0 + i + 1] = fmaf(z1, x0v, dxk[c0 + i + 1]);
-            dot = fmaf(z0, xf.x, dot);
-            dot = fmaf(z1, xf.y, dot);
-          }
         }
+        tmem_wait_ld();
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->acc_empty[ab]);
+#pragma unroll
+        for (int i = 0; i < HALF; i += 2) {
+          const float2 xf = __bfloat1622float2(xk2[i / 2]);
+          const float z0 = __uint_as_float(v[i]), z1 = __uint_as_float(v[i + 1]);
+          dxk[i] = fmaf(z0, x0v, dxk[i]);
+          dxk[i + 1] = fmaf(z1, x0v, dxk[i + 1]);
+          dot = fmaf(z0, xf.x, dot);
+          dot = fmaf(z1, xf.y, dot);
+        }
         // dX0[r, j] partial of this warp's channel half: parked in shared memory (plane = half), combined at tile end
         sDx0[(half * 128 + rl) * p.mP + j] = dot;
       }
@@ -313,7 +314,7 @@ static int cin_dx_geom(int m, int Hp, int H, int D, CinDxGeom* g) {
   g->n_hchunks = (g->H_pad + 63) / 64;
   g->HC = g->n_hchunks * 64;
   size_t fixed = 2 * (size_t)128 * g->mP * 2 + 2 * (size_t)128 * g->mP * 4 + sizeof(CinDxBars) + 256;
-  size_t slot = (size_t)g->HpQ * 128;
+  size_t slot = (size_t)g->HpQ * 128 * g->n_hchunks;        // one field
   int ns = (int)std::min<size_t>((227 * 1024 - fixed) / slot, DX_MAX_NS * 1);
   ns = std::min(ns, DX_MAX_NS);
   if (ns < 2) {
