@@ -150,6 +150,8 @@ void xdfm_set_rows_opt_dense_version(int v);
 int xdfm_to_rows_bf16(const float* x, int64_t B, int C, int D, int CP, void* xt, void* stream);
 int64_t xdfm_cin_tc_wprime_elems(int m, int Hp, int H, int D);
 void xdfm_cin_tc_set_cluster(int c);
+/* 1 (default): kernels that contract two 128-row tiles per streamed weight chunk are used whenever the shape allows; 0: single-tile */
+void xdfm_cin_tc_set_pair(int v);
 int xdfm_cin_fwd_tc(const void* x0t, const void* xkt, int64_t xk_pitch, const float* W, const float* bias, void* wprime, int64_t B,
                     int m, int Hp, int H, int D, int act, void* yt, int direct_begin, float* pooled, float* maps, int fm_total,
                     int col_off, void* stream);
@@ -167,6 +169,8 @@ int xdfm_add_rows_f32(float* a, int64_t pitch_a, const float* b, int64_t pitch_b
  * wt = bf16 scratch [xdfm_cin_bwd_dx_tc_wt_elems]; dxk [B*D, HpQ] fp32 (overwritten, HpQ = Hp rounded up to 16),
  * dx0 [B*D, mP] fp32 (accumulated +=). */
 int64_t xdfm_cin_bwd_dx_tc_wt_elems(int m, int Hp, int H, int D);
+/* diagnostic bit mask for profiling experiments (0 = production): 1 skip the epilogue contraction, 2 skip TMEM loads, 4 skip MMAs */
+void xdfm_cin_dx_set_debug(int v);
 int xdfm_cin_bwd_dx_tc(const void* dyt, const void* x0t, const void* xkt, int64_t xk_pitch, const float* W, void* wt, int64_t B, int m,
                        int Hp, int H, int D, float* dxk, float* dx0, void* stream);
 

@@ -114,6 +114,17 @@ def test_cin_tc_single_layer_matches_emulation(case, cluster):
         assert float(yt[:, H:].float().abs().max()) == 0.0, "padding channels must be zero"
 
 
+@pytest.mark.parametrize("case", [(2500, 26, 16, 200, 26), (300, 26, 16, 200, 100), (1300, 12, 32, 64, 12)], ids=str)
+def test_cin_tc_single_tile_kernel_still_matches(case):
+    """Shapes that default to the tile-pair kernel, forced through the single-tile kernel (xdfm_cin_tc_set_pair(0))."""
+    from deepctr import _native as Nv
+    Nv.lib().xdfm_cin_tc_set_pair(0)
+    try:
+        test_cin_tc_single_layer_matches_emulation(case, 2)
+    finally:
+        Nv.lib().xdfm_cin_tc_set_pair(1)
+
+
 def test_cin_tc_maps_output():
     B, m, D, H, Hp = 21, 6, 16, 32, 6
     g = torch.Generator().manual_seed(3)

@@ -38,6 +38,7 @@ struct CinDxParams {
   int64_t n_tiles;
   int n_iters;
   int n_hchunks;              // 64-wide chunks of the reduction dim h per field = ceil(H_pad / 64)
+  int debug;                  // diagnostic bit mask (0 in production): 1 skip contraction FMAs, 2 skip TMEM loads, 4 skip MMAs
   int ns;                     // W'' ring depth (one slot = one FIELD: n_hchunks boxes of [HpQ rows x 128 B] on one barrier)
 };
 
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(DX_THREADS, 1) cin_bwd_dx_tc_kernel(const __gr
         mbar_wait(&bars->w_full[ws], wphase);
         fence_after_sync();
         if (elect_one()) {
-          if (active) {
+          if (active && !(p.debug & 4)) {
             const uint32_t d_addr = tmem_base + DX_ACC_COL0 + ab * DX_ACC_COLS;
             uint64_t bd = bdesc;
             for (int ks = 0; ks < ksteps; ks += 4, bd += box_desc_step) {
@@ -235,6 +236,10 @@ __global__ void __launch_bounds__(DX_THREADS, 1) cin_bwd_dx_tc_kernel(const __gr
         // all of this warp's dZ columns of the field in ONE batch of TMEM loads and one wait: the accumulator is handed back to
         // the tensor core before the contraction starts
         uint32_t v[HALF];
+        if (p.debug & 2) {
+#pragma unroll
+          for (int i = 0; i < HALF; ++i) v[i] = 0u;
+        } else
 #pragma unroll
         for (int c0 = 0; c0 < HALF; c0 += 8) {
           asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -247,6 +252,7 @@ __global__ void __launch_bounds__(DX_THREADS, 1) cin_bwd_dx_tc_kernel(const __gr
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->acc_empty[ab]);
+        if (!(p.debug & 1))
 #pragma unroll
         for (int i = 0; i < HALF; i += 2) {
           const float2 xf = __bfloat1622float2(xk2[i / 2]);
@@ -333,6 +339,8 @@ extern "C" int64_t xdfm_cin_bwd_dx_tc_wt_elems(int m, int Hp, int H, int D) {
 }
 
 extern int g_cin_tc_cluster_shared;
+int g_cin_dx_debug = 0;
+extern "C" void xdfm_cin_dx_set_debug(int v) { g_cin_dx_debug = v; }
 
 template <int NQ>
 static int launch_dx(const CUtensorMap& tmW, const CinDxParams& p, size_t smem, int blocks, int cluster, cudaStream_t st) {
@@ -381,7 +389,7 @@ extern "C" int xdfm_cin_bwd_dx_tc(const void* dyt, const void* x0t, const void* 
   CinDxParams p;
   p.dyt = (const __nv_bfloat16*)dyt; p.x0t = (const __nv_bfloat16*)x0t; p.xkt = (const __nv_bfloat16*)xkt; p.dxk = dxk; p.dx0 = dx0;
   p.R = R; p.xk_pitch = xk_pitch; p.m = m; p.mP = g.mP; p.Hp = Hp; p.HpQ = g.HpQ; p.H = H; p.H_pad = g.H_pad; p.Hs = g.Hs;
-  p.n_tiles = ceil_div64(R, 128); p.n_hchunks = g.n_hchunks; p.ns = g.ns;
+  p.n_tiles = ceil_div64(R, 128); p.n_hchunks = g.n_hchunks; p.ns = g.ns; p.debug = g_cin_dx_debug;
   int sms = xdfm_num_sms();
   int blocks = (int)std::min<int64_t>(ceil_div64(p.n_tiles, cluster) * cluster, (int64_t)(sms / cluster) * cluster);
   blocks = std::max(blocks, cluster);

@@ -50,6 +50,7 @@ _SIGS = {
     "xdfm_bce_sum": (c_int, [_P, _P, c_int64, c_float, _P, _P, _P, _P]),
     "xdfm_to_rows_bf16": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P]),
     "xdfm_cin_tc_set_cluster": (None, [c_int]),
+    "xdfm_cin_tc_set_pair": (None, [c_int]),
     "xdfm_cin_tc_wprime_elems": (c_int64, [c_int, c_int, c_int, c_int]),
     "xdfm_cin_fwd_tc": (c_int, [_P, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_int,
                                 c_int, _P]),
@@ -86,6 +87,7 @@ _SIGS = {
     "xdfm_gemm_tc": (c_int, [c_int, c_int, c_int, _P, c_int64, _P, c_int64, _P, c_int, _P, c_int, _P, c_int64, _P]),
     "xdfm_cvt_bf16": (c_int, [_P, c_int, c_int, c_int64, c_int, _P, c_int64, _P]),
     "xdfm_set_rows_opt_dense_version": (None, [c_int]),
+    "xdfm_cin_dx_set_debug": (None, [c_int]),
     "xdfm_opt_tick": (c_int, [_P, POINTER(OptCfg), _P]),
     "xdfm_flat_opt": (c_int, [POINTER(OptCfg), _P, c_int64, _P, _P, _P, _P, _P, c_float, _P, _P]),
     "xdfm_rows_opt": (c_int, [POINTER(OptCfg), _P, POINTER(_P), POINTER(_P), POINTER(_P), POINTER(c_int64), c_int, c_int, _P, _P, _P,
