@@ -150,7 +150,7 @@ void xdfm_set_rows_opt_dense_version(int v);
 int xdfm_to_rows_bf16(const float* x, int64_t B, int C, int D, int CP, void* xt, void* stream);
 int64_t xdfm_cin_tc_wprime_elems(int m, int Hp, int H, int D);
 void xdfm_cin_tc_set_cluster(int c);
-/* 1 (default): kernels that contract two 128-row tiles per streamed weight chunk are used whenever the shape allows; 0: single-tile */
+/* 1 (default): dual-producer forward kernel (row warps generate Z, then drain the accumulator) when D <= 32; 0: original kernel */
 void xdfm_cin_tc_set_pair(int v);
 int xdfm_cin_fwd_tc(const void* x0t, const void* xkt, int64_t xk_pitch, const float* W, const float* bias, void* wprime, int64_t B,
                     int m, int Hp, int H, int D, int act, void* yt, int direct_begin, float* pooled, float* maps, int fm_total,

@@ -482,7 +482,7 @@ cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-#include "cin_tc_pair.cuh"
+#include "cin_tc_dual.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // W fp32 [H, Hp*m] (k = i*m + j) -> W' bf16 [H_pad, KP] (k' = j*HpP + i), zero padded
@@ -587,9 +587,9 @@ static int launch_cin_fwd_tc(const CUtensorMap& tmW, const CUtensorMap& tmXk, co
 }
 
 template <int NI8>
-static int launch_cin_fwd_tc_pair(const CUtensorMap& tmW, const CUtensorMap& tmXk, const CinTcParams& p, size_t smem, int blocks, int cluster,
+static int launch_cin_fwd_tc_dual(const CUtensorMap& tmW, const CUtensorMap& tmXk, const CinTcParams& p, size_t smem, int blocks, int cluster,
                                   cudaStream_t st) {
-  XDFM_CUDA(cudaFuncSetAttribute(cin_fwd_tc_pair_kernel<NI8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  XDFM_CUDA(cudaFuncSetAttribute(cin_fwd_tc_dual_kernel<NI8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(blocks);
   cfg.blockDim = dim3(TP_THREADS);
@@ -602,12 +602,12 @@ static int launch_cin_fwd_tc_pair(const CUtensorMap& tmW, const CUtensorMap& tmX
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  XDFM_CUDA(cudaLaunchKernelEx(&cfg, cin_fwd_tc_pair_kernel<NI8>, tmW, tmXk, p));
+  XDFM_CUDA(cudaLaunchKernelEx(&cfg, cin_fwd_tc_dual_kernel<NI8>, tmW, tmXk, p));
   XDFM_LAUNCH_CHECK();
   return XDFM_OK;
 }
 
-int g_cin_tc_pair = 1;      // 1: two row tiles per streamed W' chunk whenever the shape allows it (default), 0: single-tile kernels only
+int g_cin_tc_pair = 1;      // 1: dual-producer forward kernel whenever the shape allows it (default), 0: original warp-specialised kernel
 extern "C" void xdfm_cin_tc_set_pair(int v) { g_cin_tc_pair = v ? 1 : 0; }
 
 // Row-layout operands: x0t [B*D, mP] bf16 (mP = m rounded up to 8); xkt = layer input rows with pitch xk_pitch (elements), the
@@ -653,18 +653,16 @@ extern "C" int xdfm_cin_fwd_tc(const void* x0t, const void* xkt, int64_t xk_pitc
   int blocks = (int)std::min<int64_t>(ceil_div64(p.n_tiles, cluster) * cluster, (int64_t)(sms / cluster) * cluster);
   blocks = std::max(blocks, cluster);
   p.n_iters = (int)ceil_div64(p.n_tiles, blocks);
-  if (g_cin_tc_pair && g.H_pad <= 224 && D <= 32) {
-    // tile-pair kernel: both accumulators + an A ring of >= 2 slots fit the 512 TMEM columns
+  if (g_cin_tc_pair && D <= 32) {
+    // dual-producer kernel (cin_tc_dual.cuh): same tile schedule and W' layout, 128-wide K stages
     const size_t fixed = 2 * (size_t)128 * g.mP * 2 + 2 * (size_t)128 * g.HpP * 2 + (size_t)g.H_pad * 4 + sizeof(CinTpBars) + 256;
-    const size_t stage = (size_t)g.H_pad * 128;
+    const size_t stage = (size_t)g.H_pad * 256;
     int ns = (int)std::min<size_t>((227 * 1024 - fixed) / stage, TP_MAX_NS_W);
     if (ns >= 2) {
       p.ns_w = ns;
-      p.n_wchunks = (m * g.HpP + 63) / 64;
-      p.n_iters = (int)ceil_div64(p.n_tiles, 2 * (int64_t)blocks);
-      const size_t smem_pair = fixed + (size_t)ns * stage;
+      const size_t smem_dual = fixed + (size_t)ns * stage;
       switch (g.HpP / 8) {
-#define CASE_NI8P(n) case n: return launch_cin_fwd_tc_pair<n>(tmW, tmXk, p, smem_pair, blocks, cluster, st);
+#define CASE_NI8P(n) case n: return launch_cin_fwd_tc_dual<n>(tmW, tmXk, p, smem_dual, blocks, cluster, st);
         CASE_NI8P(1) CASE_NI8P(2) CASE_NI8P(3) CASE_NI8P(4) CASE_NI8P(5) CASE_NI8P(6) CASE_NI8P(7) CASE_NI8P(8)
         CASE_NI8P(9) CASE_NI8P(10) CASE_NI8P(11) CASE_NI8P(12) CASE_NI8P(13) CASE_NI8P(14) CASE_NI8P(15) CASE_NI8P(16)
 #undef CASE_NI8P
