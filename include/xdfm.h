@@ -135,6 +135,23 @@ int xdfm_rows_opt(const xdfm_opt_cfg* cfg, const float* opt_dev, float* const* w
                   const int32_t* num_segments, int64_t max_segments, float grad_scale, uint32_t* touched_bitmap, int dense_pass,
                   double* reg_out, void* stream);
 
+/* ---- lazy ("deferred catch-up") form of the reference's dense table semantics (basemodel.py:126, 412-428, 447-461): every row
+ * of every table moves every step (g = 2*l2*w through the optimizer's moments); a row the batch does not touch evolves on its own,
+ * so its update is postponed -- last[row] (int32, key space of the scatter-add) = step up to which it is current, hist = per-step
+ * scalars (4 floats per step: adam step size, sqrt(bias_correction2), adagrad clr, lr; slot = step - hist_base) -- and replayed in registers, bit-for-bit the arithmetic of the dense pass,
+ * by whoever needs the row.  xdfm_opt_tick_hist = xdfm_opt_tick + history record.  xdfm_rows_catchup: rows in uniq_keys are
+ * replayed to the completed-step count and written back (call before the forward lookup of a training step).
+ * xdfm_rows_mark_current: last[row] = step for the rows just updated by xdfm_rows_opt(dense_pass = 0).  xdfm_rows_flush: all rows
+ * (before predict / state_dict / at the end of an epoch).  reg_out accumulates l2*w^2 of every replayed (row, step). */
+int xdfm_opt_tick_hist(float* opt_dev, const xdfm_opt_cfg* cfg, float* hist, int64_t hist_cap, int64_t hist_base, void* stream);
+int xdfm_rows_catchup(const xdfm_opt_cfg* cfg, const float* opt_dev, const float* hist, int64_t hist_base, float* const* w,
+                      float* const* s1, float* const* s2, int32_t* last, const int64_t* table_row_offset, int T, int width,
+                      const uint32_t* uniq_keys, const int32_t* num_segments, int64_t max_segments, double* reg_out, void* stream);
+int xdfm_rows_mark_current(int32_t* last, const uint32_t* uniq_keys, const int32_t* num_segments, int64_t max_segments,
+                           const float* opt_dev, void* stream);
+int xdfm_rows_flush(const xdfm_opt_cfg* cfg, const float* opt_dev, const float* hist, int64_t hist_base, float* const* w, float* const* s1,
+                    float* const* s2, int32_t* last, const int64_t* table_row_offset, int T, int width, double* reg_out, void* stream);
+
 /* diagnostic: 1 = first version of the dense-table streaming pass, 2 = unrolled / streaming-hint version (default) */
 void xdfm_set_rows_opt_dense_version(int v);
 

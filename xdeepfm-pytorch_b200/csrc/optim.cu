@@ -371,3 +371,220 @@ extern "C" int xdfm_rows_opt(const xdfm_opt_cfg* cfg, const float* opt_dev, floa
   }
   return XDFM_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Lazy ("deferred catch-up") form of the reference's dense table semantics.
+//
+// The reference moves EVERY table row EVERY step (g = 2*l2*w through Adam's moments: basemodel.py:126, 412-428, 447-461), which
+// costs a 24 B/element stream over all tables per step (13.8 GB at Criteo cardinalities) although a batch touches ~0.6 % of the
+// rows.  A row that is not touched evolves autonomously -- its update depends only on its own (w, m, v) and on the step's bias
+// corrections -- so the update can be postponed without changing a single bit: `last[row]` records the step up to which the row
+// is current, every step's scalars are kept in `hist`, and whoever needs the row (the batch that looks it up, a flush before
+// predict / state_dict / the end of an epoch) replays the missing steps in registers with exactly the arithmetic of the dense
+// pass.  HBM traffic drops to the touched rows; the replay is pure ALU work.
+//   hist[(s - hist_base) * 4 + {0,1,2}] = (adam step_size, adam sqrt(bias_correction2), adagrad clr) of step s.
+// ------------------------------------------------------------------------------------------------
+__global__ void opt_tick_hist_kernel(float* d, xdfm_opt_cfg cfg, float* hist, long long hist_cap, long long hist_base) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int step = __float_as_int(d[0]) + 1;
+  d[0] = __int_as_float(step);
+  double bc1 = 1.0 - pow((double)cfg.beta1, (double)step);
+  double bc2 = 1.0 - pow((double)cfg.beta2, (double)step);
+  d[1] = (float)((double)cfg.lr / bc1);
+  d[2] = (float)sqrt(bc2);
+  d[3] = (float)((double)cfg.lr / (1.0 + (double)(step - 1) * (double)cfg.lr_decay));
+  long long slot = (long long)step - hist_base;
+  if (hist != nullptr && slot >= 0 && slot < hist_cap) {
+    hist[slot * 4 + 0] = d[1];
+    hist[slot * 4 + 1] = d[2];
+    hist[slot * 4 + 2] = d[3];
+    hist[slot * 4 + 3] = cfg.lr;
+  }
+}
+
+extern "C" int xdfm_opt_tick_hist(float* opt_dev, const xdfm_opt_cfg* cfg, float* hist, int64_t hist_cap, int64_t hist_base, void* stream) {
+  opt_tick_hist_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(opt_dev, *cfg, hist, (long long)hist_cap, (long long)hist_base);
+  XDFM_LAUNCH_CHECK();
+  return XDFM_OK;
+}
+
+// replay steps (from, to] of an untouched row piece: g = 2*l2*w at every step, exactly as rows_opt_dense does
+template <int VEC>
+__device__ __forceinline__ void replay_steps(const xdfm_opt_cfg& cfg, OptScalars h, const float4* __restrict__ hist, long long hist_base,
+                                             int from, int to, float* w, float* a, float* b, float& reg) {
+  for (int s = from + 1; s <= to; ++s) {
+    const float4 hs = __ldg(hist + ((long long)s - hist_base));
+    h.step_size = hs.x;
+    h.bc2_sqrt = hs.y;
+    h.clr = hs.z;
+    h.lr = hs.w;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float wi = w[i];
+      reg += cfg.l2 * (wi * wi);
+      opt_apply(h, w[i], 2.f * cfg.l2 * wi, a[i], b[i]);
+    }
+  }
+}
+
+// rows named by uniq_keys: replay up to `done` completed steps (done = step counter in d[0]) and write back.
+// One thread = one 4-element piece of a row (width % 4 == 0) or one element (generic).
+template <int VEC>
+__global__ void __launch_bounds__(256) rows_catchup_kernel(xdfm_opt_cfg cfg, const float* __restrict__ d, const float4* __restrict__ hist,
+                                                           long long hist_base, TableSet ts, int T, int width, int32_t* __restrict__ last,
+                                                           const uint32_t* __restrict__ uniq_keys, const int32_t* __restrict__ num_segments,
+                                                           double* reg_out) {
+  OptScalars h = load_scalars(cfg, d);
+  const int done = __float_as_int(d[0]);
+  const int nseg = *num_segments;
+  const int ppr = width / VEC;                       // pieces per row
+  const int64_t total = (int64_t)nseg * ppr;
+  const bool has1 = ts.s1[0] != nullptr, has2 = ts.s2[0] != nullptr;
+  float reg = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t sidx = i / ppr;
+    const int piece = (int)(i - sidx * ppr);
+    const int64_t key = uniq_keys[sidx];
+    const int from = last[key];
+    if (from >= done) continue;
+    const int t = find_tab(ts.row_off, T, key);
+    const int64_t e = (key - ts.row_off[t]) * width + (int64_t)piece * VEC;
+    float w[VEC], a[VEC], b[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      w[k] = ts.w[t][e + k];
+      a[k] = has1 ? ts.s1[t][e + k] : 0.f;
+      b[k] = has2 ? ts.s2[t][e + k] : 0.f;
+    }
+    replay_steps<VEC>(cfg, h, hist, hist_base, from, done, w, a, b, reg);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      ts.w[t][e + k] = w[k];
+      if (has1) ts.s1[t][e + k] = a[k];
+      if (has2) ts.s2[t][e + k] = b[k];
+    }
+  }
+  block_accumulate_double(reg, reg_out);
+}
+
+// second pass (separate launch: all pieces of a row must have read last[key] before it changes)
+__global__ void rows_mark_kernel(int32_t* __restrict__ last, const uint32_t* __restrict__ uniq_keys, const int32_t* __restrict__ num_segments,
+                                 const float* __restrict__ d, int plus) {
+  const int nseg = *num_segments;
+  const int v = __float_as_int(d[0]) + plus;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nseg; i += (int64_t)gridDim.x * blockDim.x) last[uniq_keys[i]] = v;
+}
+
+// every row: replay up to `done`; then last[:] = done (second launch)
+template <int VEC>
+__global__ void __launch_bounds__(256) rows_flush_kernel(xdfm_opt_cfg cfg, const float* __restrict__ d, const float4* __restrict__ hist,
+                                                         long long hist_base, TableSet ts, int T, int width, const int32_t* __restrict__ last,
+                                                         double* reg_out) {
+  OptScalars h = load_scalars(cfg, d);
+  const int done = __float_as_int(d[0]);
+  const int64_t npieces = ts.vec_off[T];             // VEC == 4: 4-element vectors; VEC == 1: elements (vec_off built accordingly)
+  const bool has1 = ts.s1[0] != nullptr, has2 = ts.s2[0] != nullptr;
+  float reg = 0.f;
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < npieces; v += (int64_t)gridDim.x * blockDim.x) {
+    const int t = find_tab(ts.vec_off, T, v);
+    const int64_t e = (v - ts.vec_off[t]) * VEC;
+    const int64_t key = ts.row_off[t] + e / width;
+    const int from = last[key];
+    if (from >= done) continue;
+    float w[VEC], a[VEC], b[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      w[k] = ts.w[t][e + k];
+      a[k] = has1 ? ts.s1[t][e + k] : 0.f;
+      b[k] = has2 ? ts.s2[t][e + k] : 0.f;
+    }
+    replay_steps<VEC>(cfg, h, hist, hist_base, from, done, w, a, b, reg);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      ts.w[t][e + k] = w[k];
+      if (has1) ts.s1[t][e + k] = a[k];
+      if (has2) ts.s2[t][e + k] = b[k];
+    }
+  }
+  block_accumulate_double(reg, reg_out);
+}
+
+__global__ void fill_i32_from_step_kernel(int32_t* __restrict__ last, int64_t n, const float* __restrict__ d) {
+  const int v = __float_as_int(d[0]);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) last[i] = v;
+}
+
+static int fill_table_set_pieces(TableSet& ts, float* const* w, float* const* s1, float* const* s2, const int64_t* row_off, int T, int width,
+                                 int vec) {
+  int64_t voff = 0;
+  for (int t = 0; t < T; ++t) {
+    ts.w[t] = w[t];
+    ts.s1[t] = s1 ? s1[t] : nullptr;
+    ts.s2[t] = s2 ? s2[t] : nullptr;
+    ts.row_off[t] = row_off[t];
+    ts.vec_off[t] = voff;
+    voff += (row_off[t + 1] - row_off[t]) * width / vec;
+  }
+  ts.row_off[T] = row_off[T];
+  ts.vec_off[T] = voff;
+  return 0;
+}
+
+extern "C" int xdfm_rows_catchup(const xdfm_opt_cfg* cfg, const float* opt_dev, const float* hist, int64_t hist_base, float* const* w,
+                                 float* const* s1, float* const* s2, int32_t* last, const int64_t* table_row_offset, int T, int width,
+                                 const uint32_t* uniq_keys, const int32_t* num_segments, int64_t max_segments, double* reg_out, void* stream) {
+  XDFM_CHECK_ARG(cfg->kind >= 0 && cfg->kind <= 3, "rows_catchup: unknown optimizer kind %d", cfg->kind);
+  XDFM_CHECK_ARG(T >= 1 && T <= XDFM_MAX_FIELDS && hist != nullptr && last != nullptr, "rows_catchup: bad arguments (T=%d)", T);
+  if (max_segments == 0) return XDFM_OK;
+  const int vec = width % 4 == 0 ? 4 : 1;
+  TableSet ts;
+  fill_table_set_pieces(ts, w, s1, s2, table_row_offset, T, width, vec);
+  cudaStream_t st = (cudaStream_t)stream;
+  int blocks = (int)min((int64_t)xdfm_num_sms() * 8, ceil_div64(max_segments * (width / vec), 256));
+  blocks = max(blocks, 1);
+  if (vec == 4)
+    rows_catchup_kernel<4><<<blocks, 256, 0, st>>>(*cfg, opt_dev, (const float4*)hist, (long long)hist_base, ts, T, width, last, uniq_keys,
+                                                   num_segments, reg_out);
+  else
+    rows_catchup_kernel<1><<<blocks, 256, 0, st>>>(*cfg, opt_dev, (const float4*)hist, (long long)hist_base, ts, T, width, last, uniq_keys,
+                                                   num_segments, reg_out);
+  XDFM_LAUNCH_CHECK();
+  int mblocks = (int)min((int64_t)xdfm_num_sms() * 4, ceil_div64(max_segments, 256));
+  rows_mark_kernel<<<max(mblocks, 1), 256, 0, st>>>(last, uniq_keys, num_segments, opt_dev, 0);
+  XDFM_LAUNCH_CHECK();
+  return XDFM_OK;
+}
+
+// after the optimizer step of the touched rows (xdfm_rows_opt with dense_pass = 0): last[row] = step
+extern "C" int xdfm_rows_mark_current(int32_t* last, const uint32_t* uniq_keys, const int32_t* num_segments, int64_t max_segments,
+                                      const float* opt_dev, void* stream) {
+  if (max_segments == 0) return XDFM_OK;
+  int mblocks = (int)min((int64_t)xdfm_num_sms() * 4, ceil_div64(max_segments, 256));
+  rows_mark_kernel<<<max(mblocks, 1), 256, 0, (cudaStream_t)stream>>>(last, uniq_keys, num_segments, opt_dev, 0);
+  XDFM_LAUNCH_CHECK();
+  return XDFM_OK;
+}
+
+extern "C" int xdfm_rows_flush(const xdfm_opt_cfg* cfg, const float* opt_dev, const float* hist, int64_t hist_base, float* const* w,
+                               float* const* s1, float* const* s2, int32_t* last, const int64_t* table_row_offset, int T, int width,
+                               double* reg_out, void* stream) {
+  XDFM_CHECK_ARG(cfg->kind >= 0 && cfg->kind <= 3, "rows_flush: unknown optimizer kind %d", cfg->kind);
+  XDFM_CHECK_ARG(T >= 1 && T <= XDFM_MAX_FIELDS && hist != nullptr && last != nullptr, "rows_flush: bad arguments (T=%d)", T);
+  const int vec = width % 4 == 0 ? 4 : 1;
+  TableSet ts;
+  fill_table_set_pieces(ts, w, s1, s2, table_row_offset, T, width, vec);
+  const int64_t np = ts.vec_off[T];
+  if (np == 0) return XDFM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int blocks = (int)min((int64_t)xdfm_num_sms() * 16, ceil_div64(np, 256));
+  if (vec == 4)
+    rows_flush_kernel<4><<<max(blocks, 1), 256, 0, st>>>(*cfg, opt_dev, (const float4*)hist, (long long)hist_base, ts, T, width, last, reg_out);
+  else
+    rows_flush_kernel<1><<<max(blocks, 1), 256, 0, st>>>(*cfg, opt_dev, (const float4*)hist, (long long)hist_base, ts, T, width, last, reg_out);
+  XDFM_LAUNCH_CHECK();
+  const int64_t rows = table_row_offset[T];
+  int fb = (int)min((int64_t)xdfm_num_sms() * 8, ceil_div64(rows, 256));
+  fill_i32_from_step_kernel<<<max(fb, 1), 256, 0, st>>>(last, rows, opt_dev);
+  XDFM_LAUNCH_CHECK();
+  return XDFM_OK;
+}

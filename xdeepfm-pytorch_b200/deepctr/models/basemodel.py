@@ -167,6 +167,7 @@ class BaseModel(nn.Module):
             from ..distributed import ShardedGather
             sh = self._dist.sharded
             return ShardedGather.apply(sh, ids, sh.anchor)
+        self._tables_current(self._emb_plan, ids)
         tables = [emb.weight for emb in self.embedding_dict.values()]
         return ops.SparseGather.apply(self._emb_plan, self._seg_cache, ids, *tables)
 
@@ -178,7 +179,18 @@ class BaseModel(nn.Module):
             sh = self._dist.sharded
             has_w = len(self.linear_model.dense_feature_columns) > 0
             return ShardedLinearTerm.apply(sh, ids, dense if has_w else None, self.linear_model.weight if has_w else None, sh.anchor)
+        self._tables_current(self.linear_model._plan, ids)
         return self.linear_model.forward_ids(ids, dense, cache=self._seg_cache)
+
+    def _tables_current(self, plan, ids):
+        """Lazy dense-table semantics (optim.FusedOptimizer): rows the optimizer has postponed are replayed before they are read --
+        the looked-up rows in a training step, every row otherwise."""
+        opt = getattr(self, "optim", None)
+        if isinstance(opt, FusedOptimizer) and opt._dirty:
+            if self.training:
+                opt.catch_up(plan, self._seg_cache, ids)
+            else:
+                opt.flush()
 
     def dnn_dense(self, dense_all):
         return self._select(dense_all, self._dnn_dense_sel)
@@ -315,6 +327,9 @@ class BaseModel(nn.Module):
     def state_dict(self, *args, **kwargs):
         """Reference key layout.  With row-sharded tables this is a COLLECTIVE: every rank must call it; the
         full tables are re-assembled from the shards (save on rank 0 only)."""
+        opt = getattr(self, "optim", None)
+        if isinstance(opt, FusedOptimizer):
+            opt.flush()                          # postponed row updates (lazy dense-table semantics) are applied first
         sd = super().state_dict(*args, **kwargs)
         if self._dist is not None:
             from ..distributed import gather_tables
@@ -324,6 +339,9 @@ class BaseModel(nn.Module):
         return sd
 
     def load_state_dict(self, state_dict, strict=True, **kwargs):
+        opt = getattr(self, "optim", None)
+        if isinstance(opt, FusedOptimizer):
+            opt.flush()
         if self._dist is None:
             return super().load_state_dict(state_dict, strict=strict, **kwargs)
         from ..distributed import scatter_tables
@@ -488,6 +506,7 @@ class BaseModel(nn.Module):
         opt = self.optim
         opt.prepare()       # flat parameter / gradient views must exist BEFORE backward accumulates into them
         opt.zero_grad()
+        self._seg_cache.clear()     # the key holds a device address: never let a recycled allocation hit a previous batch's segments
         if self._dist is not None:
             self._dist.ensure_capacity(ids.shape[0] * self._dist.sharded.m)
             self._dist.sharded.stash = {}

@@ -27,6 +27,7 @@ class TableSet:
         self.plan, self.params, self.l2 = plan, list(params), float(l2)
         self.s1 = self.s2 = None
         self.bitmap = None
+        self.last = None            # int32 [total_rows]: step up to which each row is current (lazy dense semantics)
 
 
 class FusedOptimizer(torch.optim.Optimizer):
@@ -47,6 +48,14 @@ class FusedOptimizer(torch.optim.Optimizer):
         self.sparse_embedding_update = False     # True: only rows touched by the batch are updated (NOT reference semantics)
         self.reg_accum = None                    # float64 [1] device: sum of l2*w^2 seen by the last step(s)
         self.steps = 0
+        # Lazy form of the reference's dense table semantics: rows the batch does not touch are not streamed every step; their
+        # (deterministic) L2 / momentum updates are replayed bit-for-bit when the row is next looked up or at flush() time
+        # (csrc/optim.cu).  False = stream every table every step (first implementation; kept for A/B tests).
+        self.lazy_tables = True
+        self._hist = None
+        self._hist_cap = 1 << 16
+        self._hist_base = 0
+        self._dirty = False
         # multi-GPU (deepctr.distributed): dense gradients are all-reduced, the row-sharded tables are updated by their owner
         self.dist_ctx = dist_ctx
         self.l2_sharded = (float(l2_sharded[0]), float(l2_sharded[1]))     # (embedding tables, first-order tables)
@@ -126,6 +135,9 @@ class FusedOptimizer(torch.optim.Optimizer):
                 ts.s1 = [torch.zeros_like(p.data) for p in ts.params] if ns >= 1 else None
                 ts.s2 = [torch.zeros_like(p.data) for p in ts.params] if ns >= 2 else None
                 ts.bitmap = torch.zeros((ts.plan.row_off[-1] + 31) // 32 + 1, dtype=torch.int32, device=dev)
+                ts.last = torch.zeros(max(ts.plan.row_off[-1], 1), dtype=torch.int32, device=dev)
+        if self._hist is None or self._hist.device != dev:
+            self._hist = torch.zeros(self._hist_cap * 4, dtype=torch.float32, device=dev)
 
     # -------------------------------------------------------------------------------------------
     def zero_grad(self, set_to_none=True):
@@ -156,7 +168,14 @@ class FusedOptimizer(torch.optim.Optimizer):
             # all-reduce is also the barrier after which every rank's exchange buffers are complete
             ctx.sharded.reduce_local()
             ctx.all_reduce_sum(f["g"])
-        N.check(L.xdfm_opt_tick(N.ptr(f["opt_dev"]), cfg0, st))
+        lazy = self._lazy_active()
+        if lazy:
+            if self.steps + 1 - self._hist_base >= self._hist_cap:      # history ring full: settle every row, start a new window
+                self.flush()
+                self._hist_base = self.steps
+            N.check(L.xdfm_opt_tick_hist(N.ptr(f["opt_dev"]), cfg0, N.ptr(self._hist), self._hist_cap, self._hist_base, st))
+        else:
+            N.check(L.xdfm_opt_tick(N.ptr(f["opt_dev"]), cfg0, st))
         if f["n"] > 0:
             N.check(L.xdfm_flat_opt(cfg0, N.ptr(f["opt_dev"]), f["n"], N.ptr(f["w"]), N.ptr(f["g"]), N.ptr(f["s1"]), N.ptr(f["s2"]),
                                     N.ptr(f["l2vec"]) if (apply_l2 and f["any_l2"]) else None, float(grad_scale),
@@ -170,11 +189,17 @@ class FusedOptimizer(torch.optim.Optimizer):
                 dense_pass = 0 if self.sparse_embedding_update else 1
                 if self.kind == "sgd" and cfg.l2 == 0.0:
                     dense_pass = 0      # nothing moves on untouched rows: g == 0 and no optimizer state
+                mark = False
+                if dense_pass and lazy:
+                    dense_pass, mark = 0, True      # untouched rows are replayed later (catch_up / flush)
                 with ops.timed("rows_opt"):
                     N.check(L.xdfm_rows_opt(cfg, N.ptr(f["opt_dev"]), N.ptr_array([p.data for p in ts.params]),
                                             N.ptr_array(ts.s1) if ts.s1 else None, N.ptr_array(ts.s2) if ts.s2 else None,
                                             plan._c_row_off, plan.T, plan.width, N.ptr(uniq), N.ptr(gsum), N.ptr(nseg), n,
                                             float(grad_scale), N.ptr(ts.bitmap), dense_pass, N.ptr(self.reg_accum), st))
+                    if mark:
+                        N.check(L.xdfm_rows_mark_current(N.ptr(ts.last), N.ptr(uniq), N.ptr(nseg), n, N.ptr(f["opt_dev"]), st))
+                        self._dirty = True
                 plan.stash = None
             elif any(g is not None for g in dense_grads):
                 # dense .grad tensors (generic autograd path): every table is one flat update
@@ -196,9 +221,43 @@ class FusedOptimizer(torch.optim.Optimizer):
         self.steps += 1
         return None
 
+    # ---- lazy dense-table semantics -------------------------------------------------------------------
+    def _lazy_active(self):
+        if not self.lazy_tables or self.sparse_embedding_update or self.dist_ctx is not None or not self.table_sets:
+            return False
+        return not (self.kind == "sgd" and all(ts.l2 == 0.0 for ts in self.table_sets))
+
+    def catch_up(self, plan, cache, ids):
+        """Training forward: bring the rows this batch looks up to the current step before they are read."""
+        if not self._dirty or not self._lazy_active() or ids.shape[0] == 0:
+            return
+        for ts in self.table_sets:
+            if ts.plan is plan and ts.last is not None:
+                uniq, seg_off, pos, nseg, n = cache.get(plan, ids)
+                with ops.timed("rows_opt"):
+                    N.check(N.lib().xdfm_rows_catchup(self._cfg(ts.l2), N.ptr(self._flat["opt_dev"]), N.ptr(self._hist), self._hist_base,
+                                                      N.ptr_array([p.data for p in ts.params]), N.ptr_array(ts.s1) if ts.s1 else None,
+                                                      N.ptr_array(ts.s2) if ts.s2 else None, N.ptr(ts.last), plan._c_row_off, plan.T,
+                                                      plan.width, N.ptr(uniq), N.ptr(nseg), n, N.ptr(self.reg_accum), N.stream_ptr()))
+
+    def flush(self):
+        """Replay every postponed row update (before anything reads whole tables: predict, state_dict, end of an epoch)."""
+        if not self._dirty or self._flat is None:
+            return
+        for ts in self.table_sets:
+            if ts.last is None:
+                continue
+            with ops.timed("rows_opt"):
+                N.check(N.lib().xdfm_rows_flush(self._cfg(ts.l2), N.ptr(self._flat["opt_dev"]), N.ptr(self._hist), self._hist_base,
+                                                N.ptr_array([p.data for p in ts.params]), N.ptr_array(ts.s1) if ts.s1 else None,
+                                                N.ptr_array(ts.s2) if ts.s2 else None, N.ptr(ts.last), ts.plan._c_row_off, ts.plan.T,
+                                                ts.plan.width, N.ptr(self.reg_accum), N.stream_ptr()))
+        self._dirty = False
+
     def pop_reg_loss(self):
         """Sum of l2*w^2 accumulated since the last call (device float64 -> python float; one sync).  Multi-GPU: the dense
         part is identical on every rank (counted once), the table part is summed over the owners."""
+        self.flush()
         if self.dist_ctx is not None:
             t = self.reg_accum_shard.clone()
             self.dist_ctx.all_reduce_sum(t)
