@@ -52,32 +52,39 @@ __device__ __forceinline__ OptScalars load_scalars(const xdfm_opt_cfg& c, const 
   return s;
 }
 
-// one element; mirrors torch's single-tensor optimizer arithmetic (torch/optim/{sgd,adam,adagrad,rmsprop}.py)
+// one element; mirrors torch's single-tensor optimizer arithmetic (torch/optim/{sgd,adam,adagrad,rmsprop}.py).
+// Every operation is an explicit round-to-nearest intrinsic: the compiler may not contract or re-associate, so the streaming pass,
+// the touched-row kernel and the lazy replay produce bit-identical results wherever the same update is computed.
 __device__ __forceinline__ void opt_apply(const OptScalars& h, float& w, float g, float& s1, float& s2) {
   switch (h.kind) {
     case XDFM_OPT_SGD:
-      w = w - h.lr * g;
+      w = __fsub_rn(w, __fmul_rn(h.lr, g));
       break;
     case XDFM_OPT_ADAM: {
-      s1 = s1 + h.one_minus_b1 * (g - s1);                 // exp_avg.lerp_(grad, 1-beta1)
-      s2 = s2 * h.b2 + h.one_minus_b2 * (g * g);           // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1-beta2)
-      float denom = sqrtf(s2) / h.bc2_sqrt + h.eps;
-      w = w - h.step_size * (s1 / denom);                  // param.addcdiv_(exp_avg, denom, value=-step_size)
+      s1 = __fmaf_rn(h.one_minus_b1, __fsub_rn(g, s1), s1);                      // exp_avg.lerp_(grad, 1-beta1)
+      s2 = __fmaf_rn(h.one_minus_b2, __fmul_rn(g, g), __fmul_rn(s2, h.b2));      // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1-beta2)
+      const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(s2), h.bc2_sqrt), h.eps);
+      w = __fsub_rn(w, __fmul_rn(h.step_size, __fdiv_rn(s1, denom)));            // param.addcdiv_(exp_avg, denom, value=-step_size)
       break;
     }
     case XDFM_OPT_ADAGRAD: {
-      s1 = s1 + g * g;                                     // state_sum.addcmul_(grad, grad, value=1)
-      float stdv = sqrtf(s1) + h.eps;
-      w = w - h.clr * (g / stdv);
+      s1 = __fmaf_rn(g, g, s1);                                                  // state_sum.addcmul_(grad, grad, value=1)
+      const float stdv = __fadd_rn(__fsqrt_rn(s1), h.eps);
+      w = __fsub_rn(w, __fmul_rn(h.clr, __fdiv_rn(g, stdv)));
       break;
     }
     case XDFM_OPT_RMSPROP: {
-      s1 = s1 * h.alpha + h.one_minus_alpha * (g * g);     // square_avg.mul_(alpha).addcmul_(g, g, 1-alpha)
-      float avg = sqrtf(s1) + h.eps;
-      w = w - h.lr * (g / avg);
+      s1 = __fmaf_rn(h.one_minus_alpha, __fmul_rn(g, g), __fmul_rn(s1, h.alpha));   // square_avg.mul_(alpha).addcmul_(g, g, 1-alpha)
+      const float avg = __fadd_rn(__fsqrt_rn(s1), h.eps);
+      w = __fsub_rn(w, __fmul_rn(h.lr, __fdiv_rn(g, avg)));
       break;
     }
   }
+}
+// gradient of the L2 term alone (rows the batch did not touch) / added to a scattered gradient
+__device__ __forceinline__ float l2_grad(float l2, float w) { return __fmul_rn(__fmul_rn(2.f, l2), w); }
+__device__ __forceinline__ float l2_plus_grad(float gsum, float grad_scale, float l2, float w) {
+  return __fadd_rn(__fmul_rn(gsum, grad_scale), l2_grad(l2, w));
 }
 
 __device__ __forceinline__ void block_accumulate_double(float local, double* out) {
@@ -105,7 +112,7 @@ __global__ void __launch_bounds__(256) flat_opt_kernel(xdfm_opt_cfg cfg, const f
     float wi = w[i];
     float l2 = l2vec ? l2vec[i] : 0.f;
     reg += l2 * (wi * wi);
-    float gi = g[i] * grad_scale + 2.f * l2 * wi;
+    float gi = l2_plus_grad(g[i], grad_scale, l2, wi);
     float a = s1 ? s1[i] : 0.f, b = s2 ? s2[i] : 0.f;
     opt_apply(h, wi, gi, a, b);
     w[i] = wi;
@@ -161,7 +168,7 @@ __global__ void __launch_bounds__(256) rows_opt_sparse_kernel(xdfm_opt_cfg cfg, 
     int64_t e = (key - ts.row_off[t]) * width + c;
     float wi = ts.w[t][e];
     reg += cfg.l2 * (wi * wi);
-    float gi = gsum[i] * grad_scale + 2.f * cfg.l2 * wi;
+    float gi = l2_plus_grad(gsum[i], grad_scale, cfg.l2, wi);
     float a = ts.s1[t] ? ts.s1[t][e] : 0.f, b = ts.s2[t] ? ts.s2[t][e] : 0.f;
     opt_apply(h, wi, gi, a, b);
     ts.w[t][e] = wi;
@@ -208,7 +215,7 @@ __global__ void __launch_bounds__(256) rows_opt_dense_kernel(xdfm_opt_cfg cfg, c
         if (!tch) {
           float wi = wv[i];
           reg += cfg.l2 * (wi * wi);
-          opt_apply(h, wv[i], 2.f * cfg.l2 * wi, av[i], bv[i]);
+          opt_apply(h, wv[i], l2_grad(cfg.l2, wi), av[i], bv[i]);
           any = true;
         }
       }
@@ -239,22 +246,9 @@ __device__ __forceinline__ void st_stream(float* p, const float4& v) { __stcs(re
 
 template <int KIND>
 __device__ __forceinline__ void opt_apply_k(const OptScalars& h, float& w, float g, float& s1, float& s2) {
-  if (KIND == XDFM_OPT_SGD) {
-    w = w - h.lr * g;
-  } else if (KIND == XDFM_OPT_ADAM) {
-    s1 = s1 + h.one_minus_b1 * (g - s1);
-    s2 = s2 * h.b2 + h.one_minus_b2 * (g * g);
-    float denom = sqrtf(s2) / h.bc2_sqrt + h.eps;
-    w = w - h.step_size * (s1 / denom);
-  } else if (KIND == XDFM_OPT_ADAGRAD) {
-    s1 = s1 + g * g;
-    float stdv = sqrtf(s1) + h.eps;
-    w = w - h.clr * (g / stdv);
-  } else {
-    s1 = s1 * h.alpha + h.one_minus_alpha * (g * g);
-    float avg = sqrtf(s1) + h.eps;
-    w = w - h.lr * (g / avg);
-  }
+  OptScalars hk = h;
+  hk.kind = KIND;            // compile-time constant: the switch in opt_apply folds away
+  opt_apply(hk, w, g, s1, s2);
 }
 
 template <int KIND>
@@ -265,7 +259,6 @@ __global__ void __launch_bounds__(256, 4) rows_opt_dense_v2_kernel(xdfm_opt_cfg 
   OptScalars h = load_scalars(cfg, d);
   const int64_t nvec = ts.vec_off[T];
   const int wv = width >> 2;                 // vectors per row (width % 4 == 0 on this path)
-  const float l2x2 = 2.f * cfg.l2;
   float reg = 0.f;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t v0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v0 < nvec; v0 += stride * U) {
@@ -300,7 +293,7 @@ __global__ void __launch_bounds__(256, 4) rows_opt_dense_v2_kernel(xdfm_opt_cfg 
         const float wi = wf[i];
         reg += cfg.l2 * (wi * wi);
         float a = HAS1 ? af[i] : 0.f, b = HAS2 ? bf[i] : 0.f;
-        opt_apply_k<KIND>(h, wf[i], l2x2 * wi, a, b);
+        opt_apply_k<KIND>(h, wf[i], l2_grad(cfg.l2, wi), a, b);
         if (HAS1) af[i] = a;
         if (HAS2) bf[i] = b;
       }
@@ -422,7 +415,7 @@ __device__ __forceinline__ void replay_steps(const xdfm_opt_cfg& cfg, OptScalars
     for (int i = 0; i < VEC; ++i) {
       const float wi = w[i];
       reg += cfg.l2 * (wi * wi);
-      opt_apply(h, w[i], 2.f * cfg.l2 * wi, a[i], b[i]);
+      opt_apply(h, w[i], l2_grad(cfg.l2, wi), a[i], b[i]);
     }
   }
 }
