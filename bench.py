@@ -82,31 +82,57 @@ def cin_flops_per_sample(spec):
 
 
 class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons DURING the timed region (NVML every 20 ms; nvidia-smi as a fallback)."""
+    BITS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+
     def __init__(self, index=0):
         super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.stop_flag, self.sm_max = index, [], set(), False, None
+        self.index, self.samples, self.reasons, self.stop_flag, self.sm_max, self.how = index, [], set(), False, None, "nvml"
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._h, self.how = None, "nvidia-smi"
 
-    def run(self):
+    def _sample_smi(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                           capture_output=True, text=True, timeout=5)
+        f = [x.strip() for x in r.stdout.strip().split(",")]
+        self.samples.append(float(f[0]))
+        self.sm_max = float(f[1])
+        for nme, v in zip(names, f[2:]):
+            if v.lower().startswith("active"):
+                self.reasons.add(nme)
+
+    def run(self):
         while not self.stop_flag:
             try:
-                r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5)
-                f = [x.strip() for x in r.stdout.strip().split(",")]
-                self.samples.append(float(f[0]))
-                self.sm_max = float(f[1])
-                for nme, v in zip(names, f[2:]):
-                    if v.lower().startswith("active"):
-                        self.reasons.add(nme)
+                if self._h is not None:
+                    nv = self._nv
+                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                    try:
+                        mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                    except Exception:
+                        mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                    for nme, bit in self.BITS.items():
+                        if mask & bit:
+                            self.reasons.add(nme)
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.02 if self._h is not None else 0.1)
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.sm_max,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "how": self.how}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -191,8 +217,12 @@ def workload_config(args, w):
             "dp%d dense (NCCL all-reduce) + tables row-sharded x%d over NVLink peer memory" % (
                 int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("WORLD_SIZE", "1"))),
             "optimizer": "adam", "cin_precision": args.cin_impl,
-            "l2_flush": "not needed: every step streams all tables + Adam state (%.1f GB) >> 126 MB L2" % (
-                sum(w["vocab"]) * (w["D"] + 1) * 4 * 3 / 1e9)}
+            "table_semantics": "reference dense L2+Adam over every row, evaluated lazily (bit-identical replay of untouched rows; all "
+                               "postponed updates are flushed inside the timed region)" if not args.dense_table_pass else
+                               "reference dense L2+Adam over every row, streamed every step",
+            "l2_flush": "not needed: 4 rotating batches; each step touches ~1 GB of fresh activations / gradients / random table rows "
+                        "(>> 126 MB L2) and the flush streams all tables + Adam state (%.1f GB)" % (
+                            sum(w["vocab"]) * (w["D"] + 1) * 4 * 3 / 1e9)}
 
 
 def main():
@@ -233,6 +263,8 @@ def main():
         model.distribute(max_batch=B)
     model.compile("adam", "binary_crossentropy")
     model.cin.precision = args.cin_impl
+    if hasattr(model, "dnn"):
+        model.dnn.precision = "bf16" if args.cin_impl == "bf16" else "fp32"      # tcgen05 dense layers in the bf16 configuration
     model.optim.lazy_tables = not args.dense_table_pass
     n_pool = 4
     host = [(i.pin_memory(), d.pin_memory(), y.pin_memory()) for i, d, y in synth_batches(spec, B, n_pool, seed=2025 + rank)]
@@ -302,6 +334,15 @@ def main():
                 "traffic": None, "peak_source": "%s MEASURED_PEAKS.json bf16 sustained (kernel timed inside a long step)" % peaks["src"],
                 "share_of_step": cin_ms / ms if ms > 0 else None,
                 "other_ms_per_step": {k: v[0] / args.steps for k, v in timers.items()}}
+    # secondary (HBM-bound) kernels, timed live in the same run: algorithmic bytes / CUDA-event time
+    hbm = {}
+    if "embed_gather" in timers and timers["embed_gather"][0] > 0:
+        gb = B * spec.m * (4 + 2 * spec.embedding_dim * 4) * timers["embed_gather"][1]
+        a = gb / (timers["embed_gather"][0] / 1e3) / 1e9
+        hbm["embed_gather"] = {"achieved": a, "peak": peaks["hbm"], "unit": "GB/s", "frac": a / peaks["hbm"],
+                               "note": "id + row read + row write per looked-up row; 15 MB per launch at this batch (latency-bound: see "
+                                       "profiles/ for the 450 MB/launch cfg5-shape measurement)"}
+    roofline["hbm_kernels"] = hbm
     h2d = sum(t.numel() * t.element_size() for t in host[0])
     line = {"metric": "train samples/sec (Criteo-shape xDeepFM)", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,

@@ -138,7 +138,7 @@ int xdfm_rows_opt(const xdfm_opt_cfg* cfg, const float* opt_dev, float* const* w
 /* ---- lazy ("deferred catch-up") form of the reference's dense table semantics (basemodel.py:126, 412-428, 447-461): every row
  * of every table moves every step (g = 2*l2*w through the optimizer's moments); a row the batch does not touch evolves on its own,
  * so its update is postponed -- last[row] (int32, key space of the scatter-add) = step up to which it is current, hist = per-step
- * scalars (4 floats per step: adam step size, sqrt(bias_correction2), adagrad clr, lr; slot = step - hist_base) -- and replayed in registers, bit-for-bit the arithmetic of the dense pass,
+ * scalars (4 floats per step: adam step size, 1/sqrt(bias_correction2), adagrad clr, lr; slot = step - hist_base) -- and replayed in registers, bit-for-bit the arithmetic of the dense pass,
  * by whoever needs the row.  xdfm_opt_tick_hist = xdfm_opt_tick + history record.  xdfm_rows_catchup: rows in uniq_keys are
  * replayed to the completed-step count and written back (call before the forward lookup of a training step).
  * xdfm_rows_mark_current: last[row] = step for the rows just updated by xdfm_rows_opt(dense_pass = 0).  xdfm_rows_flush: all rows

@@ -13,7 +13,7 @@
 #include "../../include/xdfm.h"
 
 // device-side per-step scalars written by opt_tick_kernel (keeps the step CUDA-graph capturable)
-// d[0] = step (int32 bits), d[1] = adam step_size, d[2] = adam sqrt(bias_correction2), d[3] = adagrad clr
+// d[0] = step (int32 bits), d[1] = adam step_size, d[2] = adam 1/sqrt(bias_correction2), d[3] = adagrad clr
 __global__ void opt_tick_kernel(float* d, xdfm_opt_cfg cfg) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   int step = __float_as_int(d[0]) + 1;
@@ -21,7 +21,7 @@ __global__ void opt_tick_kernel(float* d, xdfm_opt_cfg cfg) {
   double bc1 = 1.0 - pow((double)cfg.beta1, (double)step);
   double bc2 = 1.0 - pow((double)cfg.beta2, (double)step);
   d[1] = (float)((double)cfg.lr / bc1);
-  d[2] = (float)sqrt(bc2);
+  d[2] = (float)(1.0 / sqrt(bc2));
   d[3] = (float)((double)cfg.lr / (1.0 + (double)(step - 1) * (double)cfg.lr_decay));
 }
 
@@ -33,7 +33,7 @@ extern "C" int xdfm_opt_tick(float* opt_dev, const xdfm_opt_cfg* cfg, void* stre
 
 struct OptScalars {
   int kind;
-  float lr, one_minus_b1, b2, one_minus_b2, eps, alpha, one_minus_alpha, step_size, bc2_sqrt, clr;
+  float lr, one_minus_b1, b2, one_minus_b2, eps, alpha, one_minus_alpha, step_size, bc2_sqrt, clr;   // bc2_sqrt holds 1/sqrt(bc2)
 };
 
 __device__ __forceinline__ OptScalars load_scalars(const xdfm_opt_cfg& c, const float* __restrict__ d) {
@@ -53,8 +53,15 @@ __device__ __forceinline__ OptScalars load_scalars(const xdfm_opt_cfg& c, const 
 }
 
 // one element; mirrors torch's single-tensor optimizer arithmetic (torch/optim/{sgd,adam,adagrad,rmsprop}.py).
-// Every operation is an explicit round-to-nearest intrinsic: the compiler may not contract or re-associate, so the streaming pass,
-// the touched-row kernel and the lazy replay produce bit-identical results wherever the same update is computed.
+// Every operation is an explicit intrinsic: the compiler may not contract or re-associate, so the streaming pass, the touched-row
+// kernel and the lazy replay produce bit-identical results wherever the same update is computed.  Square roots and quotients use
+// the SFU approximations (sqrt.approx / rcp-based division, <= 2 ulp): the lazy replay of postponed rows is pure ALU work and two
+// IEEE divisions per element and step would triple its cost; the parity tests against torch.optim hold at 1e-4 of the update.
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ void opt_apply(const OptScalars& h, float& w, float g, float& s1, float& s2) {
   switch (h.kind) {
     case XDFM_OPT_SGD:
@@ -63,20 +70,20 @@ __device__ __forceinline__ void opt_apply(const OptScalars& h, float& w, float g
     case XDFM_OPT_ADAM: {
       s1 = __fmaf_rn(h.one_minus_b1, __fsub_rn(g, s1), s1);                      // exp_avg.lerp_(grad, 1-beta1)
       s2 = __fmaf_rn(h.one_minus_b2, __fmul_rn(g, g), __fmul_rn(s2, h.b2));      // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1-beta2)
-      const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(s2), h.bc2_sqrt), h.eps);
-      w = __fsub_rn(w, __fmul_rn(h.step_size, __fdiv_rn(s1, denom)));            // param.addcdiv_(exp_avg, denom, value=-step_size)
+      const float denom = __fmaf_rn(fast_sqrt(s2), h.bc2_sqrt, h.eps);           // sqrt(v) / sqrt(bias_correction2) + eps
+      w = __fsub_rn(w, __fmul_rn(h.step_size, __fdividef(s1, denom)));           // param.addcdiv_(exp_avg, denom, value=-step_size)
       break;
     }
     case XDFM_OPT_ADAGRAD: {
       s1 = __fmaf_rn(g, g, s1);                                                  // state_sum.addcmul_(grad, grad, value=1)
-      const float stdv = __fadd_rn(__fsqrt_rn(s1), h.eps);
-      w = __fsub_rn(w, __fmul_rn(h.clr, __fdiv_rn(g, stdv)));
+      const float stdv = __fadd_rn(fast_sqrt(s1), h.eps);
+      w = __fsub_rn(w, __fmul_rn(h.clr, __fdividef(g, stdv)));
       break;
     }
     case XDFM_OPT_RMSPROP: {
       s1 = __fmaf_rn(h.one_minus_alpha, __fmul_rn(g, g), __fmul_rn(s1, h.alpha));   // square_avg.mul_(alpha).addcmul_(g, g, 1-alpha)
-      const float avg = __fadd_rn(__fsqrt_rn(s1), h.eps);
-      w = __fsub_rn(w, __fmul_rn(h.lr, __fdiv_rn(g, avg)));
+      const float avg = __fadd_rn(fast_sqrt(s1), h.eps);
+      w = __fsub_rn(w, __fmul_rn(h.lr, __fdividef(g, avg)));
       break;
     }
   }
@@ -384,7 +391,7 @@ __global__ void opt_tick_hist_kernel(float* d, xdfm_opt_cfg cfg, float* hist, lo
   double bc1 = 1.0 - pow((double)cfg.beta1, (double)step);
   double bc2 = 1.0 - pow((double)cfg.beta2, (double)step);
   d[1] = (float)((double)cfg.lr / bc1);
-  d[2] = (float)sqrt(bc2);
+  d[2] = (float)(1.0 / sqrt(bc2));
   d[3] = (float)((double)cfg.lr / (1.0 + (double)(step - 1) * (double)cfg.lr_decay));
   long long slot = (long long)step - hist_base;
   if (hist != nullptr && slot >= 0 && slot < hist_cap) {
