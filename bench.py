@@ -331,7 +331,10 @@ def main():
     peak = peaks["tf_sust"]
     roofline = {"bound": "tensor", "kernel": "CIN contraction (cin_fwd + cin_bwd launches, %d per step)" % (cin_calls // max(args.steps, 1)),
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": None, "peak_source": "%s MEASURED_PEAKS.json bf16 sustained (kernel timed inside a long step)" % peaks["src"],
+                "traffic": 0.813e9 if args.workload == "cfg2" and args.cin_impl == "bf16" else None,
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the 9 CIN contraction launches of one step, bytes, from "
+                                "profiles/r01_ncu_full_cfg2.md (ncu --set full); algorithmic HBM bytes of the group ~0.62e9",
+                "peak_source": "%s MEASURED_PEAKS.json bf16 sustained (kernel timed inside a long step)" % peaks["src"],
                 "share_of_step": cin_ms / ms if ms > 0 else None,
                 "other_ms_per_step": {k: v[0] / args.steps for k, v in timers.items()}}
     # secondary (HBM-bound) kernels, timed live in the same run: algorithmic bytes / CUDA-event time

@@ -179,6 +179,10 @@ int xdfm_cin_fwd_tc(const void* x0t, const void* xkt, int64_t xk_pitch, const fl
  * add_rows_f32: a[r, :C] += b[r, :C]. */
 int xdfm_cin_dy_rows(const void* yt, int64_t B, int D, int H, int Hs, int direct_begin, const float* dpooled, const float* dmaps,
                      int fm_total, int col_off, const float* dnext, int64_t dnext_pitch, int n_next, int act, void* dyt, void* stream);
+/* fused: dyt [B*D, Hs] (row layout) AND dyT [H_pad, B*D] (channel-major, rows >= H zero) in one pass (= cin_dy_rows + rows_to_cols) */
+int xdfm_cin_dy_rows_cols(const void* yt, int64_t B, int D, int H, int Hs, int H_pad, int direct_begin, const float* dpooled,
+                          const float* dmaps, int fm_total, int col_off, const float* dnext, int64_t dnext_pitch, int n_next, int act,
+                          void* dyt, void* dyT, void* stream);
 int xdfm_from_rows_f32(const float* xt, int64_t B, int C, int D, int CP, float* x, int accumulate, void* stream);
 int xdfm_add_rows_f32(float* a, int64_t pitch_a, const float* b, int64_t pitch_b, int64_t R, int C, void* stream);
 

@@ -221,6 +221,32 @@ def test_cin_dy_rows():
     assert float(dyt[:, H:].float().abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("B,D,H,n_next,use_maps", [(7, 16, 20, 10, False), (300, 16, 200, 100, False), (33, 8, 36, 0, True), (5, 32, 128, 64, False)])
+def test_cin_dy_rows_cols_fused_equals_two_kernels(B, D, H, n_next, use_maps):
+    """The fused kernel must write exactly what cin_dy_rows followed by rows_to_cols_bf16 write (both layouts, padding zero)."""
+    from deepctr import _native as Nv
+    L = Nv.lib()
+    hdb, col_off = H - H // 2, 3
+    fm = col_off + (H - hdb) + 2
+    Hs, H_pad, R = (H + 7) // 8 * 8, (H + 15) // 16 * 16, B * D
+    g = torch.Generator().manual_seed(B + H)
+    yt = to_rows(torch.relu(torch.randn(B, H, D, generator=g)).to(DEV), Hs)
+    dpool = torch.randn(B, fm, generator=g).to(DEV)
+    dmaps = torch.randn(B, fm, D, generator=g).to(DEV)
+    npitch = max((n_next + 15) // 16 * 16, 16)
+    dnext = torch.randn(R, npitch, generator=g).to(DEV)
+    args = (Nv.ptr(None if use_maps else dpool), Nv.ptr(dmaps if use_maps else None), fm, col_off, Nv.ptr(dnext if n_next else None),
+            npitch, n_next, 1)
+    dyt_a = torch.full((R, Hs), float("nan"), dtype=torch.bfloat16, device=DEV)
+    Nv.check(L.xdfm_cin_dy_rows(Nv.ptr(yt), B, D, H, Hs, hdb, *args, Nv.ptr(dyt_a), Nv.stream_ptr()))
+    dyT_a = to_cols(dyt_a, H, H_pad)
+    dyt_b = torch.full((R, Hs), float("nan"), dtype=torch.bfloat16, device=DEV)
+    dyT_b = torch.full((H_pad, R), float("nan"), dtype=torch.bfloat16, device=DEV)
+    Nv.check(L.xdfm_cin_dy_rows_cols(Nv.ptr(yt), B, D, H, Hs, H_pad, hdb, *args, Nv.ptr(dyt_b), Nv.ptr(dyT_b), Nv.stream_ptr()))
+    assert torch.equal(dyt_a.view(torch.int16), dyt_b.view(torch.int16))
+    assert torch.equal(dyT_a.view(torch.int16), dyT_b.view(torch.int16))
+
+
 def to_cols(rows, C, CP):
     from deepctr import _native as Nv
     R = rows.shape[0]

@@ -96,3 +96,88 @@ extern "C" int xdfm_add_rows_f32(float* a, int64_t pitch_a, const float* b, int6
   XDFM_LAUNCH_CHECK();
   return XDFM_OK;
 }
+
+// Fused form of cin_dy_rows + rows_to_cols: one pass over y / upstream gradients produces dY in BOTH layouts the backward needs --
+// row layout dyt [R, Hs] (A operand of the dX kernel) and channel-major dyT [H_pad, R] (B operand of the dW kernel) -- through a
+// 64 x 64 shared-memory tile.  Channels >= H are written as zeros in both.
+__global__ void __launch_bounds__(256) cin_dy_rows_cols_kernel(const __nv_bfloat16* __restrict__ yt, int64_t R, int D, int H, int Hs, int H_pad,
+                                                               int hdb, const float* __restrict__ dpooled, const float* __restrict__ dmaps,
+                                                               int fm_total, int col_off, const float* __restrict__ dnext,
+                                                               int64_t dnext_pitch, int n_next, int act, __nv_bfloat16* __restrict__ dyt,
+                                                               __nv_bfloat16* __restrict__ dyT) {
+  __shared__ __align__(16) __nv_bfloat16 tile[64][72];       // 144-byte rows: 16-byte aligned granules
+  const int64_t r0 = (int64_t)blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64;
+  {
+    const int rr = threadIdx.x >> 2, cg = (threadIdx.x & 3) * 16;
+    const int64_t r = r0 + rr;
+    const int64_t b = r / D;
+    const int d = (int)(r - b * D);
+#pragma unroll
+    for (int g8 = 0; g8 < 2; ++g8) {
+      const int h0 = c0 + cg + g8 * 8;
+      float g[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = 0.f;
+      if (r < R && h0 < Hs) {
+        const uint4 yv = *reinterpret_cast<const uint4*>(yt + r * Hs + h0);
+        const __nv_bfloat16* yb = reinterpret_cast<const __nv_bfloat16*>(&yv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int h = h0 + i;
+          float v = 0.f;
+          if (h < H) {
+            if (h >= hdb) {
+              if (dpooled) v += dpooled[b * fm_total + col_off + (h - hdb)];
+              if (dmaps) v += dmaps[(b * fm_total + col_off + (h - hdb)) * (int64_t)D + d];
+            }
+            if (h < n_next && dnext) v += dnext[r * dnext_pitch + h];
+            if (act == XDFM_ACT_RELU && !(__bfloat162float(yb[i]) > 0.f)) v = 0.f;
+          }
+          g[i] = v;
+        }
+      }
+      uint4 o;
+      __nv_bfloat162 t0 = __floats2bfloat162_rn(g[0], g[1]), t1 = __floats2bfloat162_rn(g[2], g[3]);
+      __nv_bfloat162 t2 = __floats2bfloat162_rn(g[4], g[5]), t3 = __floats2bfloat162_rn(g[6], g[7]);
+      o.x = *reinterpret_cast<uint32_t*>(&t0); o.y = *reinterpret_cast<uint32_t*>(&t1);
+      o.z = *reinterpret_cast<uint32_t*>(&t2); o.w = *reinterpret_cast<uint32_t*>(&t3);
+      *reinterpret_cast<uint4*>(&tile[rr][cg + g8 * 8]) = o;
+      if (r < R && h0 < Hs) *reinterpret_cast<uint4*>(dyt + r * Hs + h0) = o;
+    }
+  }
+  __syncthreads();
+  {
+    const int cc = threadIdx.x >> 2, rg = (threadIdx.x & 3) * 16;
+    const int c = c0 + cc;
+    if (c < H_pad) {
+      __align__(16) __nv_bfloat16 col[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) col[i] = tile[rg + i][cc];
+      const int64_t r = r0 + rg;
+      __nv_bfloat16* dst = dyT + (int64_t)c * R + r;
+      if (r + 16 <= R && ((R & 7) == 0)) {
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(&col[0]);
+        *reinterpret_cast<uint4*>(dst + 8) = *reinterpret_cast<const uint4*>(&col[8]);
+      } else {
+        for (int i = 0; i < 16; ++i)
+          if (r + i < R) dst[i] = col[i];
+      }
+    }
+  }
+}
+
+extern "C" int xdfm_cin_dy_rows_cols(const void* yt, int64_t B, int D, int H, int Hs, int H_pad, int direct_begin, const float* dpooled,
+                                     const float* dmaps, int fm_total, int col_off, const float* dnext, int64_t dnext_pitch, int n_next,
+                                     int act, void* dyt, void* dyT, void* stream) {
+  XDFM_CHECK_ARG(Hs % 8 == 0 && Hs >= H && H_pad >= Hs, "cin_dy_rows_cols: Hs=%d (multiple of 8, >= H=%d), H_pad=%d >= Hs", Hs, H, H_pad);
+  XDFM_CHECK_ARG(act == XDFM_ACT_RELU || act == XDFM_ACT_NONE, "cin_dy_rows_cols: activation %d not supported on the bf16 path", act);
+  const int64_t R = B * (int64_t)D;
+  if (R == 0) return XDFM_OK;
+  dim3 grid((unsigned)ceil_div64(R, 64), (unsigned)ceil_div64(H_pad, 64));
+  cin_dy_rows_cols_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)yt, R, D, H, Hs, H_pad, direct_begin, dpooled, dmaps,
+                                                                  fm_total, col_off, dnext, dnext_pitch, n_next, act, (__nv_bfloat16*)dyt,
+                                                                  (__nv_bfloat16*)dyT);
+  XDFM_LAUNCH_CHECK();
+  return XDFM_OK;
+}

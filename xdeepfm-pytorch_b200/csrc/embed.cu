@@ -281,6 +281,43 @@ __device__ __forceinline__ void vec_add(float* a, const float* b) {
   for (int i = 0; i < VEC; ++i) a[i] += b[i];
 }
 
+// One slot's share of a segment: entries first, first + stride, ... < end, added in increasing order.  Four independent
+// (position -> row) load chains are in flight per iteration; the additions still happen in entry order, so the result is the
+// same fixed function of (segment length, D) as a plain sequential loop.
+template <int VEC>
+__device__ __forceinline__ void seg_accumulate(const float* __restrict__ demb, const float* __restrict__ dlin,
+                                               const int32_t* __restrict__ sorted_pos, int first, int end, int stride, int m, int D,
+                                               int sub, bool active, float (&acc)[VEC], float& accl) {
+  typedef typename VecT<VEC>::T V;
+  constexpr int U = 4;
+  int e = first;
+  for (; e + (U - 1) * stride < end; e += U * stride) {
+    int p[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) p[u] = __ldg(sorted_pos + e + u * stride);
+    V v[U];
+    float l[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (active && demb != nullptr) v[u] = __ldg(reinterpret_cast<const V*>(demb + (int64_t)p[u] * D) + sub);
+      l[u] = (sub == 0 && dlin != nullptr) ? __ldg(dlin + p[u] / m) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (active && demb != nullptr) vec_add<VEC>(acc, reinterpret_cast<const float*>(&v[u]));
+      accl += l[u];
+    }
+  }
+  for (; e < end; e += stride) {
+    const int p = __ldg(sorted_pos + e);
+    if (active && demb != nullptr) {
+      V v = __ldg(reinterpret_cast<const V*>(demb + (int64_t)p * D) + sub);
+      vec_add<VEC>(acc, reinterpret_cast<const float*>(&v));
+    }
+    if (sub == 0 && dlin != nullptr) accl += __ldg(dlin + p / m);
+  }
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(256) seg_reduce_kernel(const float* __restrict__ demb, const float* __restrict__ dlin,
                                                          const int32_t* __restrict__ sorted_pos,
@@ -305,14 +342,7 @@ __global__ void __launch_bounds__(256) seg_reduce_kernel(const float* __restrict
 #pragma unroll
       for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
       float accl = 0.f;
-      for (int e = beg + slot; e < end; e += S) {
-        int p = __ldg(sorted_pos + e);
-        if (active && demb != nullptr) {
-          V v = __ldg(reinterpret_cast<const V*>(demb + (int64_t)p * D) + sub);
-          vec_add<VEC>(acc, reinterpret_cast<const float*>(&v));
-        }
-        if (sub == 0 && dlin != nullptr) accl += __ldg(dlin + p / m);
-      }
+      seg_accumulate<VEC>(demb, dlin, sorted_pos, beg + slot, end, S, m, D, sub, active, acc, accl);
       for (int o = lpr; o < 32; o <<= 1) {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
@@ -336,14 +366,7 @@ __global__ void __launch_bounds__(256) seg_reduce_kernel(const float* __restrict
 #pragma unroll
       for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
       float accl = 0.f;
-      for (int e = beg + w * S + slot; e < end; e += 8 * S) {
-        int p = __ldg(sorted_pos + e);
-        if (active && demb != nullptr) {
-          V v = __ldg(reinterpret_cast<const V*>(demb + (int64_t)p * D) + sub);
-          vec_add<VEC>(acc, reinterpret_cast<const float*>(&v));
-        }
-        if (sub == 0 && dlin != nullptr) accl += __ldg(dlin + p / m);
-      }
+      seg_accumulate<VEC>(demb, dlin, sorted_pos, beg + w * S + slot, end, 8 * S, m, D, sub, active, acc, accl);
       for (int o = lpr; o < 32; o <<= 1) {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);

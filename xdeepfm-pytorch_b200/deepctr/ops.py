@@ -398,10 +398,9 @@ class CINFunctionTC(torch.autograd.Function):
             dyT = torch.empty((H_pad, R), dtype=torch.bfloat16, device=dev)
             xkT = torch.empty((HpQ, R), dtype=torch.bfloat16, device=dev)
             with timed("cin_layout"):
-                N.check(L.xdfm_cin_dy_rows(N.ptr(yt), B, D, H, Hs, cfg.direct_begin[k], N.ptr(dout) if cfg.pool else None,
-                                           None if cfg.pool else N.ptr(dout), cfg.fm, cfg.col_off[k], N.ptr(dnext), dnext_pitch,
-                                           cfg.n_next[k], cfg.act, N.ptr(dyt), st))
-                N.check(L.xdfm_rows_to_cols_bf16(N.ptr(dyt), Hs, R, H, H_pad, N.ptr(dyT), st))
+                N.check(L.xdfm_cin_dy_rows_cols(N.ptr(yt), B, D, H, Hs, H_pad, cfg.direct_begin[k], N.ptr(dout) if cfg.pool else None,
+                                                None if cfg.pool else N.ptr(dout), cfg.fm, cfg.col_off[k], N.ptr(dnext), dnext_pitch,
+                                                cfg.n_next[k], cfg.act, N.ptr(dyt), N.ptr(dyT), st))
                 N.check(L.xdfm_rows_to_cols_bf16(N.ptr(xkt), xkt.shape[1], R, Hp, HpQ, N.ptr(xkT), st))
             W = _f32c(wb[2 * k]).view(H, -1)
             dW = torch.empty_like(W)
