@@ -292,9 +292,11 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     e0.record()
+    t_host0 = time.perf_counter()
     for i in range(args.steps):
         model.train_step(*devb[i % n_pool], accum)
     model.optim.flush()      # lazy dense-table semantics: every postponed row update is replayed INSIDE the timed region
+    host_enqueue_ms = 1e3 * (time.perf_counter() - t_host0) / args.steps      # Python + launch time per step (no sync inside)
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
@@ -353,7 +355,7 @@ def main():
             "config": workload_config(args, w), "clocks": sampler.summary(),
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "roofline": roofline}
+            "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms, "roofline": roofline}
     if not args.no_cpu_baseline and world == 1:
         # bounded CPU sample in a separate process (the reference package shares the name `deepctr` with the product)
         try:
