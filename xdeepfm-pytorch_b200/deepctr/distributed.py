@@ -541,6 +541,6 @@ def scatter_tables(model, state):
                     raise RuntimeError("size mismatch for %s: checkpoint has %d rows, model has %d" % (key, full.shape[0], V))
                 a = sh.base[ctx.rank][t]
                 k = shard_rows(V, ctx.rank, ctx.world)
-                buf[a:a + k].copy_(take_shard(full, ctx.rank, ctx.world).to(sh.device, torch.float32).reshape(k, -1))
+                buf[a:a + k].copy_(take_shard(full, ctx.rank, ctx.world).to(sh.device, torch.float32).reshape(k, buf.shape[1]))
                 used.append(key)
     return used
