@@ -278,8 +278,8 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- warm-up
-    for i in range(max(args.warmup, 3)):
+    # ---- warm-up (>= 3 steps; the third call with the same shapes captures the step into a CUDA graph)
+    for i in range(max(args.warmup, 3) + 1):
         model.train_step(*devb[i % n_pool], accum)
     model.optim.flush()
     sync_all()
@@ -287,8 +287,6 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ops.TIMERS = {}
-    l0 = _native.lib().xdfm_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     e0.record()
@@ -300,9 +298,23 @@ def main():
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
-    launches = _native.lib().xdfm_launch_count() - l0
+    graphed = bool(model._graphs)
+    # ---- per-kernel-group device times (CUDA events around every operator; eager launches, same step, same data)
+    prof_steps = min(args.steps, 20)
+    ops.TIMERS = {}
+    l0 = _native.lib().xdfm_launch_count()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for i in range(prof_steps):
+        model.train_step(*devb[i % n_pool], accum)
+    p1.record()
+    sync_all()
+    prof_ms = p0.elapsed_time(p1)
+    launches_per_step = (_native.lib().xdfm_launch_count() - l0) // prof_steps
+    launches = launches_per_step * args.steps
     timers = ops.timer_totals()
     ops.TIMERS = None
+    model.optim.flush()
     # ---- timed: end-to-end through the public API with pinned host inputs
     for i in range(2):
         model.train_on_batch(*host[i % n_pool])
@@ -329,16 +341,18 @@ def main():
     cin_ms = sum(timers.get(k, (0.0, 0))[0] for k in ("cin_fwd", "cin_bwd"))
     cin_calls = sum(timers.get(k, (0.0, 0))[1] for k in ("cin_fwd", "cin_bwd"))
     flops_step = 3.0 * cin_flops_per_sample(spec) * B
-    achieved = flops_step * args.steps / (cin_ms / 1e3) / 1e12 if cin_ms > 0 else None
+    achieved = flops_step * prof_steps / (cin_ms / 1e3) / 1e12 if cin_ms > 0 else None
     peak = peaks["tf_sust"]
-    roofline = {"bound": "tensor", "kernel": "CIN contraction (cin_fwd + cin_bwd launches, %d per step)" % (cin_calls // max(args.steps, 1)),
+    roofline = {"bound": "tensor", "kernel": "CIN contraction (cin_fwd + cin_bwd launches, %d per step)" % (cin_calls // max(prof_steps, 1)),
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": 0.813e9 if args.workload == "cfg2" and args.cin_impl == "bf16" else None,
                 "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the 9 CIN contraction launches of one step, bytes, from "
                                 "profiles/r01_ncu_full_cfg2.md (ncu --set full); algorithmic HBM bytes of the group ~0.62e9",
                 "peak_source": "%s MEASURED_PEAKS.json bf16 sustained (kernel timed inside a long step)" % peaks["src"],
-                "share_of_step": cin_ms / ms if ms > 0 else None,
-                "other_ms_per_step": {k: v[0] / args.steps for k, v in timers.items()}}
+                "share_of_step": cin_ms / prof_ms if prof_ms > 0 else None,
+                "timed_how": "CUDA events around every operator over %d eager steps after the timed region (%.3f ms/step with the event "
+                             "overhead; the timed region itself replays a CUDA graph: %s)" % (prof_steps, prof_ms / prof_steps, graphed),
+                "other_ms_per_step": {k: v[0] / prof_steps for k, v in timers.items()}}
     # secondary (HBM-bound) kernels, timed live in the same run: algorithmic bytes / CUDA-event time
     hbm = {}
     if "embed_gather" in timers and timers["embed_gather"][0] > 0:
@@ -355,7 +369,9 @@ def main():
             "config": workload_config(args, w), "clocks": sampler.summary(),
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms, "roofline": roofline}
+            "gpu_launches": int(launches), "gpu_launches_note": "%d kernels of libxdfm_sm100a.so per step (counted on eager steps) x %d "
+            "steps; in the timed region they run as nodes of a replayed CUDA graph: %s" % (launches_per_step, args.steps, graphed),
+            "host_enqueue_ms_per_step": host_enqueue_ms, "roofline": roofline}
     if not args.no_cpu_baseline and world == 1:
         # bounded CPU sample in a separate process (the reference package shares the name `deepctr` with the product)
         try:

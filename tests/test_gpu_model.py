@@ -122,3 +122,30 @@ def test_no_cpu_fallback():
     model = build_product_model(spec, "cpu")
     with pytest.raises(RuntimeError):
         model.forward_ids(torch.zeros(2, 5, dtype=torch.int32), torch.zeros(2, 3))
+
+
+@pytest.mark.parametrize("optimizer", ["adam", "sgd"])
+def test_cuda_graph_replay_equals_eager_steps(optimizer):
+    """train_step captures itself into a CUDA graph on the third call with the same shapes; replayed steps must leave exactly the
+    weights, optimizer state and loss that eager launches leave."""
+    spec, params, z = load_case("xdeepfm_small_zipf")
+    X, y = torch.from_numpy(z["X"]), torch.from_numpy(z["y"])
+    batches = [(X[i * 16:(i + 1) * 16], y[i * 16:(i + 1) * 16]) for i in range(4)] * 2
+    out = []
+    for graph in (False, True):
+        model = build_product_model(spec, DEV)
+        model.load_state_dict(params, strict=True)
+        model.compile(optimizer, "binary_crossentropy")
+        model.use_cuda_graph = graph
+        model.train()
+        accum = torch.zeros(1, dtype=torch.float64, device=DEV)
+        for Xb, yb in batches:
+            ids, dense = model.split_input(Xb.to(DEV))
+            model.train_step(ids, dense, yb.to(DEV), accum)
+        assert bool(model._graphs) == graph
+        reg = model.optim.pop_reg_loss()
+        out.append(({k: v.detach().clone() for k, v in model.state_dict().items()}, accum.item(), reg))
+    (sd_e, loss_e, reg_e), (sd_g, loss_g, reg_g) = out
+    for k in sd_e:
+        assert torch.equal(sd_e[k], sd_g[k]), k
+    assert abs(loss_e - loss_g) <= 1e-9 * abs(loss_e) and abs(reg_e - reg_g) <= 1e-6 * abs(reg_e)

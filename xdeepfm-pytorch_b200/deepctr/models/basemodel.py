@@ -142,6 +142,10 @@ class BaseModel(nn.Module):
         self.sparse_embedding_update = False   # True: update only rows touched by the batch (NOT reference semantics)
         self._dist = None                      # deepctr.distributed.DistContext after distribute()
         self._optimizer_spec = None
+        import os as _os
+        self.use_cuda_graph = _os.environ.get("XDFM_CUDA_GRAPH", "1") != "0"
+        self._graph_dist_ok = _os.environ.get("XDFM_CUDA_GRAPH_DIST", "0") == "1"     # NCCL collectives inside the captured step
+        self._graphs, self._graph_seen, self._graph_failed = {}, {}, False
 
     @staticmethod
     def _selector(idx, n):
@@ -502,7 +506,79 @@ class BaseModel(nn.Module):
         return isinstance(self.optim, FusedOptimizer) and not has_l1 and aux_zero and not isinstance(self.loss_func, list)
 
     def train_step(self, ids, dense, y, loss_accum, pred_log=None, pred_off=0):
-        """One fused training step on device tensors: forward, loss, backward, optimizer (+L2).  No host sync."""
+        """One fused training step on device tensors: forward, loss, backward, optimizer (+L2).  No host sync.
+
+        The step issues ~120 kernel launches from Python (3-3.5 ms of host time at BASELINE config 2, about the GPU time of the
+        step itself), so after two eager steps with the same shapes and hyper-parameters it is captured into a CUDA graph and
+        replayed: inputs are copied into the graph's static buffers, the loss comes back through a static accumulator.
+        `model.use_cuda_graph = False` (or XDFM_CUDA_GRAPH=0) keeps every step eager."""
+        if self.use_cuda_graph and ids.shape[0] > 0:
+            out = self._train_step_graphed(ids, dense, y, loss_accum, pred_log, pred_off)
+            if out is not None:
+                return out
+        return self._train_step_eager(ids, dense, y, loss_accum, pred_log, pred_off)
+
+    # ---- CUDA-graph replay of the fused step ------------------------------------------------------------
+    def _graph_key(self, ids, dense, y):
+        opt = self.optim
+        hp = tuple((k, v) for k, v in sorted(opt.param_groups[0].items()) if isinstance(v, (int, float, tuple)))
+        prec = tuple(getattr(getattr(self, n, None), "precision", None) for n in ("cin", "dnn"))
+        return (tuple(ids.shape), tuple(dense.shape), tuple(y.shape), id(opt), hp, prec, opt._hist_base, opt.lazy_tables,
+                opt.sparse_embedding_update, self.training, getattr(self, "sfg_weight", None))
+
+    def _train_step_graphed(self, ids, dense, y, loss_accum, pred_log, pred_off):
+        opt = self.optim
+        if not isinstance(opt, FusedOptimizer) or self._graph_failed or ops.TIMERS is not None:
+            return None
+        if self._dist is not None and not self._graph_dist_ok:
+            return None
+        if opt._lazy_active() and opt.steps + 2 - opt._hist_base >= opt._hist_cap:
+            return None                      # the history window is about to be rebased: take the eager path for that step
+        key = self._graph_key(ids, dense, y)
+        st = self._graphs.get(key)
+        if st is None:
+            seen = self._graph_seen.get(key, 0)
+            self._graph_seen[key] = seen + 1
+            if seen < 2:
+                return None                  # eager warm-up (allocators, workspaces, NCCL communicators, lazy-table state)
+            try:
+                st = self._capture_step(ids, dense, y)
+            except Exception as e:           # pragma: no cover - depends on driver / torch build
+                import warnings
+                warnings.warn("CUDA-graph capture of the training step failed (%s); staying on eager launches" % (e,))
+                self._graph_failed = True
+                return None
+            if len(self._graphs) >= 4:       # a handful of batch shapes at most (full batch, last partial batch)
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = st
+        st["ids"].copy_(ids, non_blocking=True)
+        st["dense"].copy_(dense, non_blocking=True)
+        st["y"].copy_(y.reshape(st["y"].shape), non_blocking=True)
+        st["graph"].replay()
+        opt.steps += 1
+        if opt._lazy_active():
+            opt._dirty = True
+        loss_accum += st["loss"]
+        if pred_log is not None:
+            pred_log[pred_off:pred_off + ids.shape[0]] = st["y_pred"].detach().reshape(-1)
+        return st["y_pred"]
+
+    def _capture_step(self, ids, dense, y):
+        opt = self.optim
+        st = {"ids": ids.clone(), "dense": dense.clone(), "y": y.clone(),
+              "loss": torch.zeros(1, dtype=torch.float64, device=ids.device)}
+        steps0, dirty0 = opt.steps, opt._dirty
+        opt._dirty = True                    # the captured step always runs the (idempotent) catch-up of the looked-up rows
+        torch.cuda.synchronize(ids.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+            st["loss"].zero_()
+            st["y_pred"] = self._train_step_eager(st["ids"], st["dense"], st["y"], st["loss"])
+        opt.steps, opt._dirty = steps0, dirty0          # capturing does not execute the step
+        st["graph"] = graph
+        return st
+
+    def _train_step_eager(self, ids, dense, y, loss_accum, pred_log=None, pred_off=0):
         opt = self.optim
         opt.prepare()       # flat parameter / gradient views must exist BEFORE backward accumulates into them
         opt.zero_grad()
