@@ -278,27 +278,12 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- warm-up (>= 3 steps; the third call with the same shapes captures the step into a CUDA graph)
-    for i in range(max(args.warmup, 3) + 1):
+    # ---- warm-up, eager launches
+    graph_wanted = model.use_cuda_graph
+    model.use_cuda_graph = False
+    for i in range(max(args.warmup, 3)):
         model.train_step(*devb[i % n_pool], accum)
-    model.optim.flush()
     sync_all()
-    # ---- timed: device-resident inputs
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    e0.record()
-    t_host0 = time.perf_counter()
-    for i in range(args.steps):
-        model.train_step(*devb[i % n_pool], accum)
-    model.optim.flush()      # lazy dense-table semantics: every postponed row update is replayed INSIDE the timed region
-    host_enqueue_ms = 1e3 * (time.perf_counter() - t_host0) / args.steps      # Python + launch time per step (no sync inside)
-    e1.record()
-    sync_all()
-    ms = e0.elapsed_time(e1)
-    graphed = bool(model._graphs)
     # ---- per-kernel-group device times (CUDA events around every operator; eager launches, same step, same data)
     prof_steps = min(args.steps, 20)
     ops.TIMERS = {}
@@ -314,7 +299,28 @@ def main():
     launches = launches_per_step * args.steps
     timers = ops.timer_totals()
     ops.TIMERS = None
+    # ---- the step captures itself into a CUDA graph on the third call with the same shapes
+    model.use_cuda_graph = graph_wanted
+    for i in range(4):
+        model.train_step(*devb[i % n_pool], accum)
     model.optim.flush()
+    sync_all()
+    graphed = bool(model._graphs)
+    # ---- timed: device-resident inputs
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    t_host0 = time.perf_counter()
+    for i in range(args.steps):
+        model.train_step(*devb[i % n_pool], accum)
+    model.optim.flush()      # lazy dense-table semantics: every postponed row update is replayed INSIDE the timed region
+    host_enqueue_ms = 1e3 * (time.perf_counter() - t_host0) / args.steps      # Python + launch time per step (no sync inside)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
     # ---- timed: end-to-end through the public API with pinned host inputs
     for i in range(2):
         model.train_on_batch(*host[i % n_pool])
@@ -349,9 +355,10 @@ def main():
                 "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the 9 CIN contraction launches of one step, bytes, from "
                                 "profiles/r01_ncu_full_cfg2.md (ncu --set full); algorithmic HBM bytes of the group ~0.62e9",
                 "peak_source": "%s MEASURED_PEAKS.json bf16 sustained (kernel timed inside a long step)" % peaks["src"],
-                "share_of_step": cin_ms / prof_ms if prof_ms > 0 else None,
-                "timed_how": "CUDA events around every operator over %d eager steps after the timed region (%.3f ms/step with the event "
-                             "overhead; the timed region itself replays a CUDA graph: %s)" % (prof_steps, prof_ms / prof_steps, graphed),
+                "share_of_step": (cin_ms / prof_steps) / (ms / args.steps) if ms > 0 else None,
+                "timed_how": "CUDA events around every operator over %d eager steps before the timed region (%.3f ms/step incl. event "
+                             "overhead); share_of_step = that per-step kernel time / the timed region's ms_per_step (CUDA graph "
+                             "replay: %s)" % (prof_steps, prof_ms / prof_steps, graphed),
                 "other_ms_per_step": {k: v[0] / prof_steps for k, v in timers.items()}}
     # secondary (HBM-bound) kernels, timed live in the same run: algorithmic bytes / CUDA-event time
     hbm = {}

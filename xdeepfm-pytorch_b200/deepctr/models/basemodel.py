@@ -528,7 +528,7 @@ class BaseModel(nn.Module):
 
     def _train_step_graphed(self, ids, dense, y, loss_accum, pred_log, pred_off):
         opt = self.optim
-        if not isinstance(opt, FusedOptimizer) or self._graph_failed or ops.TIMERS is not None:
+        if not isinstance(opt, FusedOptimizer) or self._graph_failed or ops.TIMERS is not None or not self.training:
             return None
         if self._dist is not None and not self._graph_dist_ok:
             return None

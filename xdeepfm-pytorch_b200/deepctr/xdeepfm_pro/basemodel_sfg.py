@@ -32,6 +32,8 @@ class BaseModelSFG(BaseModel):
             self.sfg_decoder = None
             self.sfg_loss_fn = None
         self._sfg_accum = None
+        # the SFG step (label-embedding index backward, per-field heads) is not validated under CUDA-graph capture yet: eager launches
+        self.use_cuda_graph = False
         self.to(device)
 
     # ---- SFG loss on the split (ids, dense) feed ------------------------------------------------------
