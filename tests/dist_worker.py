@@ -27,7 +27,7 @@ def spec_for_test():
                        l2_reg_embedding=1e-4, l2_reg_dnn=1e-4, l2_reg_cin=1e-4)
 
 
-def run(rank, world, optimizer="adam", steps=4, per_rank=48, fit_check=True):
+def run(rank, world, optimizer="adam", steps=6, per_rank=48, fit_check=True):
     from deepctr.distributed import rank_slice
     dev = "cuda:%d" % torch.cuda.current_device()
     spec = spec_for_test()
