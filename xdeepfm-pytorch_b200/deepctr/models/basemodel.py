@@ -144,8 +144,8 @@ class BaseModel(nn.Module):
         self._optimizer_spec = None
         import os as _os
         self.use_cuda_graph = _os.environ.get("XDFM_CUDA_GRAPH", "1") != "0"
-        self._graph_dist_ok = _os.environ.get("XDFM_CUDA_GRAPH_DIST", "0") == "1"     # NCCL collectives inside the captured step
         self._graphs, self._graph_seen, self._graph_failed = {}, {}, False
+        self._capturing_half = False
 
     @staticmethod
     def _selector(idx, n):
@@ -530,8 +530,8 @@ class BaseModel(nn.Module):
         opt = self.optim
         if not isinstance(opt, FusedOptimizer) or self._graph_failed or ops.TIMERS is not None or not self.training:
             return None
-        if self._dist is not None and not self._graph_dist_ok:
-            return None
+        if self._dist is not None and type(self)._train_step_inner is not BaseModel._train_step_inner:
+            return None                      # subclasses with their own step body (xDeepFM Pro) stay eager under distribution
         if opt._lazy_active() and opt.steps + 2 - opt._hist_base >= opt._hist_cap:
             return None                      # the history window is about to be rebased: take the eager path for that step
         key = self._graph_key(ids, dense, y)
@@ -555,6 +555,11 @@ class BaseModel(nn.Module):
         st["dense"].copy_(dense, non_blocking=True)
         st["y"].copy_(y.reshape(st["y"].shape), non_blocking=True)
         st["graph"].replay()
+        if st.get("graph_apply") is not None:
+            # multi-GPU: the two NCCL collectives stay outside the graphs (captured collectives can hang at process-group teardown)
+            opt.step_exchange()
+            st["graph_apply"].replay()
+            opt.step_barrier()
         opt.steps += 1
         if opt._lazy_active():
             opt._dirty = True
@@ -571,9 +576,24 @@ class BaseModel(nn.Module):
         opt._dirty = True                    # the captured step always runs the (idempotent) catch-up of the looked-up rows
         torch.cuda.synchronize(ids.device)
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-            st["loss"].zero_()
-            st["y_pred"] = self._train_step_eager(st["ids"], st["dense"], st["y"], st["loss"])
+        if self._dist is None:
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                st["loss"].zero_()
+                st["y_pred"] = self._train_step_eager(st["ids"], st["dense"], st["y"], st["loss"])
+            st["graph_apply"] = None
+        else:
+            # graph 1: forward, loss, backward, batch side of the sharded scatter-add; graph 2: dense + shard optimizer kernels
+            self._capturing_half = True
+            try:
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    st["loss"].zero_()
+                    st["y_pred"] = self._train_step_eager(st["ids"], st["dense"], st["y"], st["loss"])
+            finally:
+                self._capturing_half = False
+            graph2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph2, pool=graph.pool(), capture_error_mode="thread_local"):
+                opt.step_apply(apply_l2=True)
+            st["graph_apply"] = graph2
         opt.steps, opt._dirty = steps0, dirty0          # capturing does not execute the step
         st["graph"] = graph
         return st
@@ -607,7 +627,7 @@ class BaseModel(nn.Module):
             loss = self.loss_func(y_pred.reshape(-1), yv, reduction="sum")
             loss_accum += loss.detach().double()
             loss.backward()
-        opt.step(apply_l2=True)
+        self._optimizer_phases(opt)
         if pred_log is not None:
             pred_log[pred_off:pred_off + yv.shape[0]] = y_pred.detach().reshape(-1)
         return y_pred
@@ -618,6 +638,15 @@ class BaseModel(nn.Module):
     def _epoch_extra(self, sample_num):
         """Hook: (extra sum added to the epoch's total loss, extra History entries)."""
         return 0.0, {}
+
+    def _optimizer_phases(self, opt):
+        """opt.step(apply_l2=True), or only its first phase while the first half of a multi-GPU step is being captured."""
+        opt.step_local()
+        if self._capturing_half:
+            return
+        opt.step_exchange()
+        opt.step_apply(apply_l2=True)
+        opt.step_barrier()
 
     def train_on_batch(self, ids, dense, y):
         """Public single-step API: HOST tensors (ids int32 [B, m_all], dense float32 [B, nd_all], y float32 [B]; pinned

@@ -157,17 +157,36 @@ class FusedOptimizer(torch.optim.Optimizer):
         with apply_l2=False the gradients are used as they are (the caller back-propagated the reg loss itself)."""
         if closure is not None:
             raise NotImplementedError("closure is not supported")
+        self.step_local()
+        self.step_exchange()
+        self.step_apply(apply_l2, grad_scale)
+        self.step_barrier()
+        return None
+
+    # The four phases of a step.  Single GPU: only step_apply does anything.  Multi-GPU: step_local and step_apply are pure kernel
+    # sequences (capturable into CUDA graphs); step_exchange / step_barrier are the two NCCL collectives in between.
+    def step_local(self):
+        """Batch side of the sharded backward: this rank's (keys, row sums, owner ranges) into the exported exchange buffers."""
         self.prepare()
+        if self.dist_ctx is not None:
+            self.dist_ctx.sharded.reduce_local()
+
+    def step_exchange(self):
+        """Data-parallel gradient SUM (losses are reduction='sum'); also the barrier after which all exchange buffers are complete."""
+        if self.dist_ctx is not None:
+            self.dist_ctx.all_reduce_sum(self._flat["g"])
+
+    def step_barrier(self):
+        """Peers may read this shard / overwrite their exchange buffers only after every owner has applied its updates."""
+        if self.dist_ctx is not None:
+            self.dist_ctx.barrier(self.dist_ctx.sharded.device)
+
+    def step_apply(self, apply_l2=False, grad_scale=1.0):
         L = N.lib()
         f = self._flat
         st = N.stream_ptr()
         cfg0 = self._cfg(0.0)
         ctx = self.dist_ctx
-        if ctx is not None:
-            # batch side of the sharded backward, then the data-parallel gradient SUM (losses are reduction='sum'); the
-            # all-reduce is also the barrier after which every rank's exchange buffers are complete
-            ctx.sharded.reduce_local()
-            ctx.all_reduce_sum(f["g"])
         lazy = self._lazy_active()
         if lazy:
             if self.steps + 1 - self._hist_base >= self._hist_cap:      # history ring full: settle every row, start a new window
@@ -216,10 +235,7 @@ class FusedOptimizer(torch.optim.Optimizer):
             dense_pass = 0 if self.sparse_embedding_update else 1
             sh.apply_optimizer(self._cfg(self.l2_sharded[0] if apply_l2 else 0.0), self._cfg(self.l2_sharded[1] if apply_l2 else 0.0),
                                f["opt_dev"], grad_scale, dense_pass, self.reg_accum_shard)
-            # peers may read this shard / overwrite their exchange buffers only after every owner is done
-            ctx.barrier(sh.device)
         self.steps += 1
-        return None
 
     # ---- lazy dense-table semantics -------------------------------------------------------------------
     def _lazy_active(self):
