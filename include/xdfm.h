@@ -152,6 +152,14 @@ int xdfm_rows_mark_current(int32_t* last, const uint32_t* uniq_keys, const int32
 int xdfm_rows_flush(const xdfm_opt_cfg* cfg, const float* opt_dev, const float* hist, int64_t hist_base, float* const* w, float* const* s1,
                     float* const* s2, int32_t* last, const int64_t* table_row_offset, int T, int width, double* reg_out, void* stream);
 
+/* lazy semantics for row-sharded tables: the READER replays.  ptrs_dev = DEVICE int64 [8*G], for every rank g the peer-mapped
+ * addresses of its shard's (emb, lin, s1, s1_lin, s2, s2_lin, last, last_lin); rows behind the local step counter are replayed in registers
+ * (nothing is written back: the owner catches its rows up when it applies the step). Other arguments as xdfm_embed_gather_sharded. */
+int xdfm_embed_gather_sharded_lazy(const void* ptrs_dev, const int64_t* feat_base_dev, const int32_t* vocab, const int32_t* ids, int64_t B,
+                                   int m, int D, int G, const xdfm_opt_cfg* cfg_emb, const xdfm_opt_cfg* cfg_lin, const float* opt_dev,
+                                   const float* hist, int64_t hist_base, float* out_emb, const float* dense, int nd, const float* dense_w,
+                                   float* out_lin, void* stream);
+
 /* diagnostic: 1 = first version of the dense-table streaming pass, 2 = unrolled / streaming-hint version (default) */
 void xdfm_set_rows_opt_dense_version(int v);
 

@@ -588,3 +588,115 @@ extern "C" int xdfm_rows_flush(const xdfm_opt_cfg* cfg, const float* opt_dev, co
   XDFM_LAUNCH_CHECK();
   return XDFM_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Lazy semantics for ROW-SHARDED tables (csrc/shard.cu): the reader replays.  A rank that looks up a row owned by a peer reads
+// (w, m, v, last) through peer memory and, if the row is behind, replays the missing steps in registers (read-only: nothing is
+// written back, the owner does its own catch-up when it applies the step's update).  All ranks run the same steps with the same
+// hyper-parameters, so every rank's local `hist` is identical.
+//   ptrs: DEVICE int64 [8 * G]: for g in 0..G-1: emb, lin, s1, s1_lin, s2, s2_lin, last, last_lin (peer-mapped addresses of rank g's shard)
+// ------------------------------------------------------------------------------------------------
+struct VocabArr2 {
+  int32_t v[XDFM_MAX_FIELDS];
+};
+
+__global__ void __launch_bounds__(256) gather_sharded_lazy_kernel(const long long* __restrict__ ptrs, const long long* __restrict__ feat_base,
+                                                                  VocabArr2 vocab, const int32_t* __restrict__ ids, int64_t n_rows, int m,
+                                                                  int D, int G, xdfm_opt_cfg cfg, const float* __restrict__ d,
+                                                                  const float4* __restrict__ hist, long long hist_base,
+                                                                  float* __restrict__ out) {
+  OptScalars h = load_scalars(cfg, d);
+  const int done = __float_as_int(d[0]);
+  const int vpr = D >> 2;
+  const int64_t total = n_rows * vpr;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / vpr;
+    const int v = (int)(i - row * vpr);
+    const int f = (int)(row % m);
+    int id = __ldg(ids + row);
+    id = max(0, min(id, vocab.v[f] - 1));
+    const int owner = id % G;
+    const int64_t lrow = feat_base[owner * m + f] + id / G;
+    const long long* pp = ptrs + owner * 8;
+    const int64_t e = lrow * D + v * 4;
+    float4 w4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(pp[0]) + e);
+    const int from = *(reinterpret_cast<const int32_t*>(pp[6]) + lrow);
+    if (from < done) {
+      float w[4] = {w4.x, w4.y, w4.z, w4.w}, a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+      if (pp[2]) { const float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(pp[2]) + e); a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w; }
+      if (pp[4]) { const float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(pp[4]) + e); b[0] = t.x; b[1] = t.y; b[2] = t.z; b[3] = t.w; }
+      float reg = 0.f;
+      replay_steps<4>(cfg, h, hist, hist_base, from, done, w, a, b, reg);
+      w4 = make_float4(w[0], w[1], w[2], w[3]);
+    }
+    reinterpret_cast<float4*>(out)[i] = w4;
+  }
+}
+
+__global__ void __launch_bounds__(256) linear_term_sharded_lazy_kernel(const long long* __restrict__ ptrs, const long long* __restrict__ feat_base,
+                                                                       VocabArr2 vocab, const int32_t* __restrict__ ids, int64_t B, int m, int G,
+                                                                       xdfm_opt_cfg cfg, const float* __restrict__ d,
+                                                                       const float4* __restrict__ hist, long long hist_base,
+                                                                       const float* __restrict__ dense, int nd, const float* __restrict__ dense_w,
+                                                                       float* __restrict__ out_lin) {
+  OptScalars h = load_scalars(cfg, d);
+  const int done = __float_as_int(d[0]);
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t b = warp; b < B; b += nwarps) {
+    float acc = 0.f;
+    for (int f = lane; f < m; f += 32) {
+      int id = __ldg(ids + b * m + f);
+      id = max(0, min(id, vocab.v[f] - 1));
+      const int owner = id % G;
+      const int64_t lrow = feat_base[owner * m + f] + id / G;
+      const long long* pp = ptrs + owner * 8;
+      float w[1] = {*(reinterpret_cast<const float*>(pp[1]) + lrow)};
+      const int from = *(reinterpret_cast<const int32_t*>(pp[7]) + lrow);
+      if (from < done) {
+        float a[1] = {pp[3] ? *(reinterpret_cast<const float*>(pp[3]) + lrow) : 0.f};
+        float bb[1] = {pp[5] ? *(reinterpret_cast<const float*>(pp[5]) + lrow) : 0.f};
+        float reg = 0.f;
+        replay_steps<1>(cfg, h, hist, hist_base, from, done, w, a, bb, reg);
+      }
+      acc += w[0];
+    }
+    float accd = 0.f;
+    if (dense_w != nullptr)
+      for (int j = lane; j < nd; j += 32) accd += __ldg(dense + b * nd + j) * __ldg(dense_w + j);
+    acc = warp_sum(acc);
+    accd = warp_sum(accd);
+    if (lane == 0) out_lin[b] = acc + accd;
+  }
+}
+
+extern "C" int xdfm_embed_gather_sharded_lazy(const void* ptrs_dev, const int64_t* feat_base_dev, const int32_t* vocab, const int32_t* ids,
+                                              int64_t B, int m, int D, int G, const xdfm_opt_cfg* cfg_emb, const xdfm_opt_cfg* cfg_lin,
+                                              const float* opt_dev, const float* hist, int64_t hist_base, float* out_emb, const float* dense,
+                                              int nd, const float* dense_w, float* out_lin, void* stream) {
+  XDFM_CHECK_ARG(m >= 1 && m <= XDFM_MAX_FIELDS && G >= 1 && G <= 16, "embed_gather_sharded_lazy: m=%d G=%d", m, G);
+  XDFM_CHECK_ARG(ptrs_dev != nullptr && feat_base_dev != nullptr && hist != nullptr && opt_dev != nullptr,
+                 "embed_gather_sharded_lazy: null argument");
+  if (B == 0) return XDFM_OK;
+  VocabArr2 va;
+  for (int f = 0; f < m; ++f) va.v[f] = vocab[f];
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_emb != nullptr) {
+    XDFM_CHECK_ARG(D >= 4 && D % 4 == 0, "embed_gather_sharded_lazy: D=%d must be a multiple of 4", D);
+    const int64_t total = B * (int64_t)m * (D / 4);
+    int blocks = (int)min((int64_t)xdfm_num_sms() * 16, ceil_div64(total, 256));
+    gather_sharded_lazy_kernel<<<max(blocks, 1), 256, 0, st>>>((const long long*)ptrs_dev, (const long long*)feat_base_dev, va, ids,
+                                                               B * (int64_t)m, m, D, G, *cfg_emb, opt_dev, (const float4*)hist,
+                                                               (long long)hist_base, out_emb);
+    XDFM_LAUNCH_CHECK();
+  }
+  if (out_lin != nullptr) {
+    int blocks = (int)min((int64_t)xdfm_num_sms() * 8, ceil_div64(B, 8));
+    linear_term_sharded_lazy_kernel<<<max(blocks, 1), 256, 0, st>>>((const long long*)ptrs_dev, (const long long*)feat_base_dev, va, ids, B, m,
+                                                                    G, *cfg_lin, opt_dev, (const float4*)hist, (long long)hist_base, dense, nd,
+                                                                    nd > 0 ? dense_w : nullptr, out_lin);
+    XDFM_LAUNCH_CHECK();
+  }
+  return XDFM_OK;
+}

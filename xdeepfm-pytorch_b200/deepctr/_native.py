@@ -96,6 +96,8 @@ _SIGS = {
     "xdfm_rows_mark_current": (c_int, [_P, _P, _P, c_int64, _P, _P]),
     "xdfm_rows_flush": (c_int, [POINTER(OptCfg), _P, _P, c_int64, POINTER(_P), POINTER(_P), POINTER(_P), _P, POINTER(c_int64), c_int, c_int, _P,
                                 _P]),
+    "xdfm_embed_gather_sharded_lazy": (c_int, [_P, _P, POINTER(c_int32), _P, c_int64, c_int, c_int, c_int, POINTER(OptCfg), POINTER(OptCfg), _P, _P,
+                                               c_int64, _P, _P, c_int, _P, _P, _P]),
     "xdfm_opt_tick": (c_int, [_P, POINTER(OptCfg), _P]),
     "xdfm_flat_opt": (c_int, [POINTER(OptCfg), _P, c_int64, _P, _P, _P, _P, _P, c_float, _P, _P]),
     "xdfm_rows_opt": (c_int, [POINTER(OptCfg), _P, POINTER(_P), POINTER(_P), POINTER(_P), POINTER(c_int64), c_int, c_int, _P, _P, _P,

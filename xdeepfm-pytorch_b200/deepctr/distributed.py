@@ -189,12 +189,28 @@ class ShardedSparse:
         self.base, self.total = shard_layout(self.rows, self.G)
         self.S = key_stride(self.total, self.G)
         self.local_rows = self.total[self.rank]
-        # tables: [local_rows, D] then [local_rows] in one exported allocation
-        self._emb_off = 0
-        self._lin_off = _align(max(self.local_rows, 1) * self.D * 4)
-        self.tables = PeerBuffer(self._lin_off + _align(max(self.local_rows, 1) * 4), self.device)
-        self.emb = self.tables.view(self._emb_off, (self.local_rows, self.D), torch.float32)
-        self.lin = self.tables.view(self._lin_off, (self.local_rows, 1), torch.float32)
+        # one exported allocation: tables [local_rows, D] / [local_rows], both optimizer moments of each, and the per-row
+        # "current up to step" counters of the lazy table semantics (peers read all of them when they replay a stale row)
+        nr = max(self.local_rows, 1)
+        sizes = [("emb", nr * self.D * 4), ("lin", nr * 4), ("s1", nr * self.D * 4), ("s1_lin", nr * 4), ("s2", nr * self.D * 4),
+                 ("s2_lin", nr * 4), ("last", nr * 4), ("last_lin", nr * 4)]
+        self._off, off = {}, 0
+        for name, nb in sizes:
+            self._off[name] = off
+            off += _align(nb)
+        self._emb_off, self._lin_off = self._off["emb"], self._off["lin"]
+        self.tables = PeerBuffer(off, self.device)
+        self.emb = self.tables.view(self._off["emb"], (self.local_rows, self.D), torch.float32)
+        self.lin = self.tables.view(self._off["lin"], (self.local_rows, 1), torch.float32)
+        self._s1_buf = self.tables.view(self._off["s1"], (self.local_rows, self.D), torch.float32)
+        self._s1_lin_buf = self.tables.view(self._off["s1_lin"], (self.local_rows, 1), torch.float32)
+        self._s2_buf = self.tables.view(self._off["s2"], (self.local_rows, self.D), torch.float32)
+        self._s2_lin_buf = self.tables.view(self._off["s2_lin"], (self.local_rows, 1), torch.float32)
+        self.last = self.tables.view(self._off["last"], (max(self.local_rows, 1),), torch.int32)
+        self.last_lin = self.tables.view(self._off["last_lin"], (max(self.local_rows, 1),), torch.int32)
+        self.n_states = 2           # set by the optimizer (0 sgd, 1 adagrad/rmsprop, 2 adam)
+        self.lazy = None            # set by the optimizer: dict(cfg_emb, cfg_lin, opt_dev, hist, hist_base) -> lookups replay stale rows
+        self.peer_ptrs = None       # device int64 [8 * G]
         self.feat_base = torch.tensor([[self.base[g][t] for t in self.table_of] for g in range(self.G)], dtype=torch.int64,
                                       device=self.device).reshape(-1).contiguous()
         self._c_vocab = N.i32_array(self.vocab)
@@ -248,12 +264,12 @@ class ShardedSparse:
 
     def export(self):
         """Picklable description of this rank's exported buffers (all_gather_object it, then connect())."""
-        return {"rank": self.rank, "tables": self.tables.handle(), "lin_off": self._lin_off,
+        return {"rank": self.rank, "tables": self.tables.handle(), "lin_off": self._lin_off, "off": dict(self._off),
                 "exchange": self.exchange.handle() if self.exchange is not None else None, "xl": getattr(self, "_xl", None)}
 
     def local_pointers(self):
         """Same description with raw pointers (in-process wiring)."""
-        return {"rank": self.rank, "tables_ptr": self.tables.ptr, "lin_off": self._lin_off,
+        return {"rank": self.rank, "tables_ptr": self.tables.ptr, "lin_off": self._lin_off, "off": dict(self._off),
                 "exchange_ptr": self.exchange.ptr if self.exchange is not None else None, "xl": getattr(self, "_xl", None)}
 
     def connect(self, infos):
@@ -277,12 +293,32 @@ class ShardedSparse:
         dev = self.device
         self.peer_emb = torch.tensor(tp, dtype=torch.int64, device=dev)
         self.peer_lin = torch.tensor([tp[g] + infos[g]["lin_off"] for g in range(self.G)], dtype=torch.int64, device=dev)
+        self._peer_tp, self._peer_off = tp, [info["off"] for info in infos]
+        self._build_peer_ptrs()
         if self.exchange is not None:
             xls = [info["xl"] for info in infos]
             self._c_peer_keys = _ptr_array([xp[g] + xls[g]["keys"] for g in range(self.G)])
             self._c_peer_gsum = _ptr_array([xp[g] + xls[g]["gsum"] for g in range(self.G)])
             self._c_peer_gsum_lin = _ptr_array([xp[g] + xls[g]["gsum_lin"] for g in range(self.G)])
             self._c_peer_ranges = _ptr_array([xp[g] + xls[g]["ranges"] for g in range(self.G)])
+
+    def _build_peer_ptrs(self):
+        """[8 * G] addresses: emb, lin, s1, s1_lin, s2, s2_lin, last, last_lin of every rank's shard (missing moments are 0)."""
+        names = ["emb", "lin", "s1", "s1_lin", "s2", "s2_lin", "last", "last_lin"]
+        need = {"emb": 0, "lin": 0, "s1": 1, "s1_lin": 1, "s2": 2, "s2_lin": 2, "last": 0, "last_lin": 0}
+        vals = []
+        for g in range(self.G):
+            for nme in names:
+                vals.append(self._peer_tp[g] + self._peer_off[g][nme] if self.n_states >= need[nme] else 0)
+        self.peer_ptrs = torch.tensor(vals, dtype=torch.int64, device=self.device)
+
+    def set_states(self, n_states):
+        """Called by the optimizer: which moment buffers exist (0 sgd, 1 adagrad / rmsprop, 2 adam)."""
+        self.n_states = int(n_states)
+        self.s1, self.s1_lin = (self._s1_buf, self._s1_lin_buf) if n_states >= 1 else (None, None)
+        self.s2, self.s2_lin = (self._s2_buf, self._s2_lin_buf) if n_states >= 2 else (None, None)
+        if getattr(self, "_peer_tp", None) is not None:
+            self._build_peer_ptrs()
 
     # ---- forward ------------------------------------------------------------------------------------
     def gather(self, ids, want_emb=True, dense=None, dense_w=None, want_lin=False):
@@ -292,6 +328,15 @@ class ShardedSparse:
         out = torch.empty((B, m, self.D), dtype=torch.float32, device=dev) if want_emb else None
         lin = torch.empty((B,), dtype=torch.float32, device=dev) if want_lin else None
         nd = 0 if dense is None or dense_w is None else dense.shape[1]
+        if self.lazy is not None:
+            lz = self.lazy
+            with ops.timed("embed_gather"):
+                N.check(N.lib().xdfm_embed_gather_sharded_lazy(N.ptr(self.peer_ptrs), N.ptr(self.feat_base), self._c_vocab, N.ptr(ids), B, m,
+                                                               self.D, self.G, lz["cfg_emb"], lz["cfg_lin"], N.ptr(lz["opt_dev"]),
+                                                               N.ptr(lz["hist"]), lz["hist_base"], N.ptr(out),
+                                                               N.ptr(dense) if nd > 0 else None, nd, N.ptr(dense_w) if nd > 0 else None,
+                                                               N.ptr(lin), N.stream_ptr()))
+            return out, lin
         with ops.timed("embed_gather"):
             N.check(N.lib().xdfm_embed_gather_sharded(N.ptr(self.peer_emb), N.ptr(self.peer_lin), N.ptr(self.feat_base), self._c_vocab,
                                                       N.ptr(ids), B, m, self.D, self.G, N.ptr(out), N.ptr(dense) if nd > 0 else None,
@@ -343,6 +388,37 @@ class ShardedSparse:
                                                N.ptr(self.p_nseg), st))
             N.check(L.xdfm_embed_bwd_reduce(N.ptr(self.p_rows), N.ptr(self.p_rows_lin), N.ptr(self.p_pos), N.ptr(self.p_seg_off),
                                             N.ptr(self.p_nseg), n_cap, 1, self.D, N.ptr(self.p_gsum), N.ptr(self.p_gsum_lin), st))
+
+    def catch_up_pulled(self, cfg_emb, cfg_lin, opt_dev, hist, hist_base, reg_out):
+        """Lazy semantics, owner side: the rows about to be updated (p_uniq) are replayed up to the completed-step count first.
+        Must run BEFORE the step counter is advanced."""
+        L = N.lib()
+        st = N.stream_ptr()
+        n_cap = self.cap * self.G
+        with ops.timed("rows_opt"):
+            for cfg, w, s1, s2, width, last in ((cfg_emb, self.emb, self.s1, self.s2, self.D, self.last),
+                                                (cfg_lin, self.lin, self.s1_lin, self.s2_lin, 1, self.last_lin)):
+                N.check(L.xdfm_rows_catchup(cfg, N.ptr(opt_dev), N.ptr(hist), hist_base, N.ptr_array([w]),
+                                            N.ptr_array([s1]) if s1 is not None else None, N.ptr_array([s2]) if s2 is not None else None,
+                                            N.ptr(last), self._row_off, 1, width, N.ptr(self.p_uniq), N.ptr(self.p_nseg), n_cap,
+                                            N.ptr(reg_out), st))
+
+    def mark_pulled(self, opt_dev):
+        for last in (self.last, self.last_lin):
+            N.check(N.lib().xdfm_rows_mark_current(N.ptr(last), N.ptr(self.p_uniq), N.ptr(self.p_nseg), self.cap * self.G, N.ptr(opt_dev),
+                                                   N.stream_ptr()))
+
+    def flush_rows(self, cfg_emb, cfg_lin, opt_dev, hist, hist_base, reg_out):
+        L = N.lib()
+        st = N.stream_ptr()
+        if self.local_rows == 0:
+            return
+        with ops.timed("rows_opt"):
+            for cfg, w, s1, s2, width, last in ((cfg_emb, self.emb, self.s1, self.s2, self.D, self.last),
+                                                (cfg_lin, self.lin, self.s1_lin, self.s2_lin, 1, self.last_lin)):
+                N.check(L.xdfm_rows_flush(cfg, N.ptr(opt_dev), N.ptr(hist), hist_base, N.ptr_array([w]),
+                                          N.ptr_array([s1]) if s1 is not None else None, N.ptr_array([s2]) if s2 is not None else None,
+                                          N.ptr(last), self._row_off, 1, width, N.ptr(reg_out), st))
 
     def apply_optimizer(self, cfg_emb, cfg_lin, opt_dev, grad_scale, dense_pass, reg_out):
         L = N.lib()

@@ -125,11 +125,7 @@ class FusedOptimizer(torch.optim.Optimizer):
         self.reg_accum = torch.zeros(1, dtype=torch.float64, device=dev)
         self.reg_accum_shard = torch.zeros(1, dtype=torch.float64, device=dev)
         if self.dist_ctx is not None:
-            sh = self.dist_ctx.sharded
-            if ns >= 1 and sh.s1 is None:
-                sh.s1, sh.s1_lin = torch.zeros_like(sh.emb), torch.zeros_like(sh.lin)
-            if ns >= 2 and sh.s2 is None:
-                sh.s2, sh.s2_lin = torch.zeros_like(sh.emb), torch.zeros_like(sh.lin)
+            self.dist_ctx.sharded.set_states(ns)        # moments live in the exported shard buffer (peers replay stale rows)
         for ts in self.table_sets:
             if ts.s1 is None or ts.s1[0].device != dev:
                 ts.s1 = [torch.zeros_like(p.data) for p in ts.params] if ns >= 1 else None
@@ -138,6 +134,7 @@ class FusedOptimizer(torch.optim.Optimizer):
                 ts.last = torch.zeros(max(ts.plan.row_off[-1], 1), dtype=torch.int32, device=dev)
         if self._hist is None or self._hist.device != dev:
             self._hist = torch.zeros(self._hist_cap * 4, dtype=torch.float32, device=dev)
+        self._publish_lazy()
 
     # -------------------------------------------------------------------------------------------
     def zero_grad(self, set_to_none=True):
@@ -188,10 +185,18 @@ class FusedOptimizer(torch.optim.Optimizer):
         cfg0 = self._cfg(0.0)
         ctx = self.dist_ctx
         lazy = self._lazy_active()
+        if ctx is not None:
+            sh = ctx.sharded
+            sh.pull_segments()      # unique local rows touched by ANY rank's batch + their summed gradients
+            if lazy:
+                # owner-side catch-up of those rows, BEFORE the step counter advances (replays up to the completed steps)
+                sh.catch_up_pulled(self._cfg(self.l2_sharded[0]), self._cfg(self.l2_sharded[1]), f["opt_dev"], self._hist, self._hist_base,
+                                   self.reg_accum_shard)
         if lazy:
             if self.steps + 1 - self._hist_base >= self._hist_cap:      # history ring full: settle every row, start a new window
                 self.flush()
                 self._hist_base = self.steps
+                self._publish_lazy()
             N.check(L.xdfm_opt_tick_hist(N.ptr(f["opt_dev"]), cfg0, N.ptr(self._hist), self._hist_cap, self._hist_base, st))
         else:
             N.check(L.xdfm_opt_tick(N.ptr(f["opt_dev"]), cfg0, st))
@@ -231,17 +236,35 @@ class FusedOptimizer(torch.optim.Optimizer):
                                             float(grad_scale), None, st))
         if ctx is not None:
             sh = ctx.sharded
-            sh.pull_segments()
-            dense_pass = 0 if self.sparse_embedding_update else 1
+            dense_pass = 0 if (self.sparse_embedding_update or lazy) else 1
             sh.apply_optimizer(self._cfg(self.l2_sharded[0] if apply_l2 else 0.0), self._cfg(self.l2_sharded[1] if apply_l2 else 0.0),
                                f["opt_dev"], grad_scale, dense_pass, self.reg_accum_shard)
+            if lazy:
+                sh.mark_pulled(f["opt_dev"])
+                self._dirty = True
+                self._publish_lazy()
         self.steps += 1
 
     # ---- lazy dense-table semantics -------------------------------------------------------------------
     def _lazy_active(self):
-        if not self.lazy_tables or self.sparse_embedding_update or self.dist_ctx is not None or not self.table_sets:
+        if not self.lazy_tables or self.sparse_embedding_update:
+            return False
+        if self.dist_ctx is not None:
+            return not (self.kind == "sgd" and self.l2_sharded == (0.0, 0.0))
+        if not self.table_sets:
             return False
         return not (self.kind == "sgd" and all(ts.l2 == 0.0 for ts in self.table_sets))
+
+    def _publish_lazy(self):
+        """Row-sharded tables: tell the lookup which history to replay stale rows with (None = rows are always current)."""
+        if self.dist_ctx is None:
+            return
+        sh = self.dist_ctx.sharded
+        if self._lazy_active() and self._flat is not None:
+            sh.lazy = dict(cfg_emb=self._cfg(self.l2_sharded[0]), cfg_lin=self._cfg(self.l2_sharded[1]), opt_dev=self._flat["opt_dev"],
+                           hist=self._hist, hist_base=self._hist_base)
+        else:
+            sh.lazy = None
 
     def catch_up(self, plan, cache, ids):
         """Training forward: bring the rows this batch looks up to the current step before they are read."""
@@ -260,6 +283,9 @@ class FusedOptimizer(torch.optim.Optimizer):
         """Replay every postponed row update (before anything reads whole tables: predict, state_dict, end of an epoch)."""
         if not self._dirty or self._flat is None:
             return
+        if self.dist_ctx is not None:
+            self.dist_ctx.sharded.flush_rows(self._cfg(self.l2_sharded[0]), self._cfg(self.l2_sharded[1]), self._flat["opt_dev"], self._hist,
+                                             self._hist_base, self.reg_accum_shard)
         for ts in self.table_sets:
             if ts.last is None:
                 continue
