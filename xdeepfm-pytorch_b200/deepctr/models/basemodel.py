@@ -146,6 +146,7 @@ class BaseModel(nn.Module):
         self.use_cuda_graph = _os.environ.get("XDFM_CUDA_GRAPH", "1") != "0"
         self._graphs, self._graph_seen, self._graph_failed = {}, {}, False
         self._capturing_half = False
+        self._capturing = False
 
     @staticmethod
     def _selector(idx, n):
@@ -563,6 +564,7 @@ class BaseModel(nn.Module):
         opt.steps += 1
         if opt._lazy_active():
             opt._dirty = True
+            opt.maybe_flush()
         loss_accum += st["loss"]
         if pred_log is not None:
             pred_log[pred_off:pred_off + ids.shape[0]] = st["y_pred"].detach().reshape(-1)
@@ -576,6 +578,13 @@ class BaseModel(nn.Module):
         opt._dirty = True                    # the captured step always runs the (idempotent) catch-up of the looked-up rows
         torch.cuda.synchronize(ids.device)
         graph = torch.cuda.CUDAGraph()
+        self._capturing = True
+        try:
+            return self._capture_graphs(opt, st, graph, steps0, dirty0)
+        finally:
+            self._capturing = False
+
+    def _capture_graphs(self, opt, st, graph, steps0, dirty0):
         if self._dist is None:
             with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 st["loss"].zero_()
@@ -647,6 +656,8 @@ class BaseModel(nn.Module):
         opt.step_exchange()
         opt.step_apply(apply_l2=True)
         opt.step_barrier()
+        if not self._capturing:
+            opt.maybe_flush()
 
     def train_on_batch(self, ids, dense, y):
         """Public single-step API: HOST tensors (ids int32 [B, m_all], dense float32 [B, nd_all], y float32 [B]; pinned

@@ -52,6 +52,10 @@ class FusedOptimizer(torch.optim.Optimizer):
         # (deterministic) L2 / momentum updates are replayed bit-for-bit when the row is next looked up or at flush() time
         # (csrc/optim.cu).  False = stream every table every step (first implementation; kept for A/B tests).
         self.lazy_tables = True
+        # The replay cost of a row grows with the number of steps it is behind, so the backlog is bounded: every `flush_interval`
+        # steps all rows are settled (one streaming pass; amortised cost ~ the replay ALU work, independent of the interval).
+        self.flush_interval = 64
+        self._last_flush_step = 0
         self._hist = None
         self._hist_cap = 1 << 16
         self._hist_base = 0
@@ -158,7 +162,13 @@ class FusedOptimizer(torch.optim.Optimizer):
         self.step_exchange()
         self.step_apply(apply_l2, grad_scale)
         self.step_barrier()
+        self.maybe_flush()
         return None
+
+    def maybe_flush(self):
+        """Bound the replay backlog of the lazy table semantics (call between steps, never inside a CUDA-graph capture)."""
+        if self._dirty and self.flush_interval and self.steps - self._last_flush_step >= self.flush_interval:
+            self.flush()
 
     # The four phases of a step.  Single GPU: only step_apply does anything.  Multi-GPU: step_local and step_apply are pure kernel
     # sequences (capturable into CUDA graphs); step_exchange / step_barrier are the two NCCL collectives in between.
@@ -281,11 +291,15 @@ class FusedOptimizer(torch.optim.Optimizer):
 
     def flush(self):
         """Replay every postponed row update (before anything reads whole tables: predict, state_dict, end of an epoch)."""
+        self._last_flush_step = self.steps
         if not self._dirty or self._flat is None:
             return
         if self.dist_ctx is not None:
+            # collective: every rank settles its shard at the same step; peers replay stale rows from (w, m, v, last) when they look
+            # them up, so nobody may read a shard while its owner rewrites it -> barrier before anyone's next lookup
             self.dist_ctx.sharded.flush_rows(self._cfg(self.l2_sharded[0]), self._cfg(self.l2_sharded[1]), self._flat["opt_dev"], self._hist,
                                              self._hist_base, self.reg_accum_shard)
+            self.dist_ctx.barrier(self.dist_ctx.sharded.device)
         for ts in self.table_sets:
             if ts.last is None:
                 continue
