@@ -35,6 +35,13 @@ WORKLOADS = {
     "cfg2": dict(m=26, nd=13, D=16, cin=(200, 200, 200), dnn=(400, 400), batch=8192, vocab=CRITEO_VOCAB),
     # BASELINE.json configs[0] (reference's CPU-runnable case) -- parity-test shape, selectable for quick runs
     "cfg1": dict(m=26, nd=13, D=8, cin=(256, 128), dnn=(256, 256), batch=256, vocab=[min(v, 100000) for v in CRITEO_VOCAB]),
+    # BASELINE.json configs[2]: xDeepFM + field self-attention over the CIN maps (xdftrain_attn.py), 4 heads, batch 16384
+    "cfg3": dict(m=26, nd=13, D=16, cin=(256, 128), dnn=(256, 256), batch=16384, vocab=CRITEO_VOCAB, variant="attn", heads=4),
+    # BASELINE.json configs[3]: xdeepfm_pro, Avazu-shape 22 sparse fields, emb_dim 32, CIN 256x4; SFG heads need capped vocabularies
+    # (Linear(64, V_f) + full-vocab cross-entropy per field: SURVEY.md 7.7), here <= 1e4 rows/field
+    "cfg4": dict(m=22, nd=0, D=32, cin=(256, 256, 256, 256), dnn=(256, 256), batch=8192,
+                 vocab=[241, 8, 8, 4738, 7746, 27, 8553, 560, 37, 10000, 10000, 8252, 6, 5, 2627, 9, 10, 436, 5, 69, 173, 61],
+                 variant="pro"),
 }
 
 
@@ -52,7 +59,7 @@ def make_spec(w, vocab_cap=None):
     vocab = [min(v, vocab_cap) if vocab_cap else v for v in w["vocab"]]
     return ModelSpec(sparse_names=["C%d" % i for i in range(1, w["m"] + 1)], vocab_sizes=vocab, embedding_dim=w["D"],
                      dense_names=["I%d" % i for i in range(1, w["nd"] + 1)], cin_layer_size=tuple(w["cin"]),
-                     dnn_hidden_units=tuple(w["dnn"]))
+                     dnn_hidden_units=tuple(w["dnn"]), variant=w.get("variant", "xdeepfm"), num_heads=w.get("heads", 4))
 
 
 def synth_batches(spec, batch, n_batches, seed):
@@ -209,9 +216,11 @@ def run_reference_arm(args, w):
 
 
 def workload_config(args, w):
-    return {"workload": "%s: xDeepFM Criteo-shape, %d sparse + %d dense, emb_dim %d, CIN %s, DNN %s, batch %d/GPU, Adam, "
-                        "Criteo cardinalities (%.1fM rows), reference dense-table L2+Adam semantics" % (
-                            args.workload, w["m"], w["nd"], w["D"], tuple(w["cin"]), tuple(w["dnn"]), w["batch"], sum(w["vocab"]) / 1e6),
+    return {"workload": "%s: %s, %d sparse + %d dense, emb_dim %d, CIN %s, DNN %s, batch %d/GPU, Adam, "
+                        "synthetic cardinalities (%.1fM rows), reference dense-table L2+Adam semantics" % (
+                            args.workload, {"xdeepfm": "xDeepFM Criteo-shape", "attn": "xDeepFMAttention (4-head self-attention over the CIN "
+                                            "maps) Criteo-shape", "pro": "xDeepFMPro (SFG decoder) Avazu-shape"}[w.get("variant", "xdeepfm")],
+                            w["m"], w["nd"], w["D"], tuple(w["cin"]), tuple(w["dnn"]), w["batch"], sum(w["vocab"]) / 1e6),
             "batch_per_gpu": w["batch"], "global_batch": w["batch"] * int(os.environ.get("WORLD_SIZE", "1")),
             "parallelism": "1 GPU" if int(os.environ.get("WORLD_SIZE", "1")) == 1 else
             "dp%d dense (NCCL all-reduce) + tables row-sharded x%d over NVLink peer memory" % (
