@@ -274,6 +274,8 @@ def main():
     model.cin.precision = args.cin_impl
     if hasattr(model, "dnn"):
         model.dnn.precision = "bf16" if args.cin_impl == "bf16" else "fp32"      # tcgen05 dense layers in the bf16 configuration
+    if getattr(model, "sfg_decoder", None) is not None:
+        model.sfg_decoder.precision = "bf16" if args.cin_impl == "bf16" else "fp32"
     model.optim.lazy_tables = not args.dense_table_pass
     n_pool = 4
     host = [(i.pin_memory(), d.pin_memory(), y.pin_memory()) for i, d, y in synth_batches(spec, B, n_pool, seed=2025 + rank)]

@@ -27,7 +27,9 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int transA, int transB, int 
   __shared__ float Bs[GT_K][GT_N + 4];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const int m0 = blockIdx.y * GT_M, n0 = blockIdx.x * GT_N;
+  // the larger tile count rides on gridDim.x (limit 2^31-1): M = B*L reaches 4 M rows in the attention block
+  const int m_on_x = (M + GT_M - 1) / GT_M >= (N + GT_N - 1) / GT_N;
+  const int m0 = (m_on_x ? blockIdx.x : blockIdx.y) * GT_M, n0 = (m_on_x ? blockIdx.y : blockIdx.x) * GT_N;
   const int kbeg = blockIdx.z * k_per_split;
   const int kend = min(K, kbeg + k_per_split);
   float acc[4][4];
@@ -133,7 +135,9 @@ extern "C" int xdfm_gemm_f32(int transA, int transB, int M, int N, int K, const 
   int kps = (int)ceil_div64(max(K, 1), S);
   kps = (int)ceil_div64(kps, GT_K) * GT_K;
   S = (int)ceil_div64(max(K, 1), kps);
-  dim3 grid((unsigned)ceil_div64(N, GT_N), (unsigned)ceil_div64(M, GT_M), (unsigned)S);
+  const unsigned mt = (unsigned)ceil_div64(M, GT_M), nt = (unsigned)ceil_div64(N, GT_N);
+  dim3 grid(mt >= nt ? mt : nt, mt >= nt ? nt : mt, (unsigned)S);
+  XDFM_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "gemm_f32: shape %d x %d x %d exceeds the launch grid", M, N, K);
   if (S == 1) {
     sgemm_kernel<<<grid, 256, 0, st>>>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, act, accumulate, kps, nullptr);
     XDFM_LAUNCH_CHECK();

@@ -39,6 +39,7 @@ class MultiHeadSelfAttention(nn.Module):
         self.W_o = nn.Linear(embed_dim, embed_dim, bias=False)
         self.dropout = nn.Dropout(dropout)
         self.dropout_rate = dropout
+        self.precision = "fp32"      # projections: 'fp32' SGEMM | 'bf16' tcgen05 GEMM (the attention core itself is always fp32)
         for mod in (self.W_q, self.W_k, self.W_v, self.W_o):
             nn.init.xavier_uniform_(mod.weight)
         self.to(device)
@@ -47,11 +48,11 @@ class MultiHeadSelfAttention(nn.Module):
         if self.dropout_rate > 0 and self.training:
             raise NotImplementedError("attention dropout > 0 is not fused (the probabilities never leave the SM); the reference "
                                       "default and its run scripts use 0.0")
-        q = ops.linear_act(x, self.W_q.weight)
-        k = ops.linear_act(x, self.W_k.weight)
-        v = ops.linear_act(x, self.W_v.weight)
+        q = ops.linear_act(x, self.W_q.weight, precision=self.precision)
+        k = ops.linear_act(x, self.W_k.weight, precision=self.precision)
+        v = ops.linear_act(x, self.W_v.weight, precision=self.precision)
         o = ops.MHSACore.apply(q, k, v, self.num_heads)
-        return ops.linear_act(o, self.W_o.weight)
+        return ops.linear_act(o, self.W_o.weight, precision=self.precision)
 
 
 class AttentionPooling(nn.Module):
@@ -62,6 +63,7 @@ class AttentionPooling(nn.Module):
         super().__init__()
         hidden_dim = hidden_dim or embed_dim
         self.attention = nn.Sequential(nn.Linear(embed_dim, hidden_dim), nn.Tanh(), nn.Linear(hidden_dim, 1, bias=False))
+        self.precision = "fp32"
         for mod in self.attention:
             if isinstance(mod, nn.Linear):
                 nn.init.xavier_uniform_(mod.weight)
@@ -70,8 +72,8 @@ class AttentionPooling(nn.Module):
         self.to(device)
 
     def forward(self, x):
-        t = ops.linear_act(x, self.attention[0].weight, self.attention[0].bias, "tanh")
-        score = ops.linear_act(t, self.attention[2].weight)            # [B, L, 1]
+        t = ops.linear_act(x, self.attention[0].weight, self.attention[0].bias, "tanh", precision=self.precision)
+        score = ops.linear_act(t, self.attention[2].weight, precision=self.precision)            # [B, L, 1]
         return ops.AttnPool.apply(score, x)
 
 
@@ -97,6 +99,9 @@ class _CINAttentionBase(nn.Module):
         if value not in ("fp32", "bf16"):
             raise ValueError("precision must be 'fp32' or 'bf16'")
         self._cfg.impl = value
+        for mod in self.modules():
+            if isinstance(mod, (MultiHeadSelfAttention, AttentionPooling)):
+                mod.precision = value
 
     def _maps(self, inputs):
         if len(inputs.shape) != 3:

@@ -51,11 +51,11 @@ class BaseModelSFG(BaseModel):
         total = None
         for f, fc in enumerate(self.sparse_feature_columns):
             head = dec.sparse_heads[fc.name]
-            l = ops.MaskedCE.apply(ops.linear_act(h, head.weight, head.bias), ids, f, row_w)
+            l = ops.MaskedCE.apply(ops.linear_act(h, head.weight, head.bias, precision=dec.precision), ids, f, row_w)
             total = l if total is None else total + l
         total = torch.zeros(1, device=emb.device) if total is None else fn.sparse_weight * total
         if dec.dense_head is not None and dd.shape[1] > 0:
-            pred = ops.linear_act(h, dec.dense_head.weight, dec.dense_head.bias)
+            pred = ops.linear_act(h, dec.dense_head.weight, dec.dense_head.bias, precision=dec.precision)
             total = total + fn.dense_weight * ops.MaskedMSE.apply(pred, dd, row_w)
         return total.reshape(())
 

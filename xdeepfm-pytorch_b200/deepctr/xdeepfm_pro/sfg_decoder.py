@@ -15,6 +15,7 @@ class LabelAwareAttention(nn.Module):
 
     def __init__(self, input_dim, hidden_dim=64, device='cpu'):
         super().__init__()
+        self.precision = "fp32"
         self.label_embedding = nn.Embedding(2, hidden_dim)
         self.attention_net = nn.Sequential(nn.Linear(input_dim + hidden_dim, hidden_dim), nn.ReLU(),
                                            nn.Linear(hidden_dim, input_dim), nn.Sigmoid())
@@ -25,8 +26,8 @@ class LabelAwareAttention(nn.Module):
             labels = labels.squeeze(-1)
         label_emb = self.label_embedding.weight[labels.long()]
         combined = torch.cat([x, label_emb], dim=-1)
-        h = ops.linear_act(combined, self.attention_net[0].weight, self.attention_net[0].bias, "relu")
-        return ops.linear_act(h, self.attention_net[2].weight, self.attention_net[2].bias, "sigmoid")
+        h = ops.linear_act(combined, self.attention_net[0].weight, self.attention_net[0].bias, "relu", precision=self.precision)
+        return ops.linear_act(h, self.attention_net[2].weight, self.attention_net[2].bias, "sigmoid", precision=self.precision)
 
 
 class SFGDecoder(nn.Module):
@@ -43,6 +44,7 @@ class SFGDecoder(nn.Module):
         self.num_sparse_features = len(sparse_feature_dims)
         self.num_dense_features = len(dense_feature_names)
         self.dropout_rate = dropout_rate
+        self._precision = "fp32"     # 'fp32' (SGEMM, reference precision) | 'bf16' (tcgen05 GEMMs for decoder layers and per-field heads)
         input_dim = self.num_sparse_features * embedding_dim + self.num_dense_features
         layers = []
         prev_dim = input_dim
@@ -58,6 +60,18 @@ class SFGDecoder(nn.Module):
             self.label_attention = LabelAwareAttention(input_dim, hidden_units[0] if hidden_units else 64, device=device)
         self.to(device)
 
+    @property
+    def precision(self):
+        return self._precision
+
+    @precision.setter
+    def precision(self, value):
+        if value not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self._precision = value
+        if self.use_label_aware_attention:
+            self.label_attention.precision = value
+
     def hidden(self, decoder_input, labels=None):
         """decoder_input [B, m*D + nd] -> last shared hidden state [B, h_last]."""
         if self.use_label_aware_attention and labels is not None:
@@ -65,7 +79,7 @@ class SFGDecoder(nn.Module):
         h = decoder_input
         for mod in self.shared_layers:
             if isinstance(mod, nn.Linear):
-                h = ops.linear_act(h, mod.weight, mod.bias, "relu")
+                h = ops.linear_act(h, mod.weight, mod.bias, "relu", precision=self._precision)
             elif isinstance(mod, nn.Dropout) and self.dropout_rate > 0:
                 h = mod(h)
         return h
@@ -75,9 +89,10 @@ class SFGDecoder(nn.Module):
         parts = [emb.reshape(emb.shape[0], -1) for emb in sparse_embeddings] + list(dense_values)
         decoder_input = torch.cat(parts, dim=-1) if len(parts) > 1 else parts[0]
         h = self.hidden(decoder_input, labels)
-        sparse_logits = {name: ops.linear_act(h, head.weight, head.bias) for name, head in self.sparse_heads.items()}
+        sparse_logits = {name: ops.linear_act(h, head.weight, head.bias, precision=self._precision)
+                         for name, head in self.sparse_heads.items()}
         if self.dense_head is not None:
-            dense_preds = ops.linear_act(h, self.dense_head.weight, self.dense_head.bias)
+            dense_preds = ops.linear_act(h, self.dense_head.weight, self.dense_head.bias, precision=self._precision)
         else:
             dense_preds = torch.zeros(h.shape[0], 0, device=h.device)
         return sparse_logits, dense_preds
