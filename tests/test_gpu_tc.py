@@ -196,6 +196,17 @@ def test_cin_tc_backward_dx_matches_emulation(case, cluster):
     assert_close(got_dx0, ref_dx0, 1e-3, 1e-3 * ref_dx0.abs().max().item(), "dx0")
 
 
+@pytest.mark.parametrize("case", [(19, 26, 16, 200, 100), (2500, 26, 16, 200, 26), (700, 22, 32, 64, 22)], ids=str)
+def test_cin_tc_backward_dx_single_tile_kernel_still_matches(case):
+    """Shapes that default to the tile-pair dX kernel, forced through the single-tile kernel (xdfm_cin_dx_set_pair(0))."""
+    from deepctr import _native as Nv
+    Nv.lib().xdfm_cin_dx_set_pair(0)
+    try:
+        test_cin_tc_backward_dx_matches_emulation(case, 2)
+    finally:
+        Nv.lib().xdfm_cin_dx_set_pair(1)
+
+
 def test_cin_dy_rows():
     from deepctr import _native as Nv
     L = Nv.lib()

@@ -288,6 +288,300 @@ __global__ void __launch_bounds__(DX_THREADS, 1) cin_bwd_dx_tc_kernel(const __gr
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tile-pair variant: every CTA contracts TWO 128-row tiles against each streamed W''_j.
+//
+// Switch-off experiments (profiles/r01_cin_findings.md) showed two thirds of the single-tile kernel's time to be its skeleton -- the
+// W'' stream (1.5 GB per launch, ~7 TB/s of SM ingest) -- not MMAs, TMEM loads or FMAs.  Here a field's weights are fetched once per
+// 256 rows: half the stream.  The two tiles' accumulators double-buffer each other (while the row warps drain tile 0's dZ_j the
+// tensor core computes tile 1's), so TMEM holds A0 [0,128), A1 [128,256), acc0 [256,384), acc1 [384,512).  The same 8 row warps
+// serve both tiles; to stay inside the register file their X^{k-1} row halves live in a thread-private shared-memory area
+// ([tile][half][pair][row]: conflict-free) instead of registers, and each dZ chunk is drained in batches of 32 columns.  The two
+// channel halves' dX0 partials meet in shared memory by atomicAdd onto a zeroed plane (two addends: order-independent).
+// Tile schedule: iteration `it` of CTA b owns tiles it*2G + b and it*2G + G + b; 2, 1 or 0 of them exist.
+// ------------------------------------------------------------------------------------------------
+struct __align__(8) CinDxPairBars {
+  uint64_t w_full[DX_MAX_NS], w_empty[DX_MAX_NS];
+  uint64_t a_full[2], a_empty[2];
+  uint64_t acc_full[2], acc_empty[2];
+  uint64_t x_full[2], x_empty[2];
+  uint32_t tmem_base;
+};
+
+template <int NQ>
+__global__ void __launch_bounds__(DX_THREADS, 1) cin_bwd_dx_tc_pair_kernel(const __grid_constant__ CUtensorMap tmW, CinDxParams p) {
+  constexpr int HpQ = NQ * 16;
+  constexpr int HALF = HpQ / 2;                    // channels per row warp (multiple of 8)
+  constexpr int NPAIR = HALF / 2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t w_box_bytes = (uint32_t)HpQ * 128;
+  const uint32_t w_slot_bytes = w_box_bytes * (uint32_t)p.n_hchunks;
+  uint8_t* sW = smem;                                                         // ns x n_hchunks x [HpQ x 128 B]
+  const uint32_t x0_tile = (uint32_t)128 * p.mP * 2;
+  uint8_t* sX0 = sW + (size_t)p.ns * w_slot_bytes;                            // 2 tiles x [128][mP] bf16
+  uint32_t* sXk = reinterpret_cast<uint32_t*>(sX0 + 2 * (size_t)x0_tile);     // [2 tiles][2 halves][NPAIR][128] bf16x2 (thread-private)
+  float* sDx0 = reinterpret_cast<float*>(sXk + 2 * 2 * NPAIR * 128);          // [2 tiles][128][mP] fp32, zero between tiles
+  CinDxPairBars* bars = reinterpret_cast<CinDxPairBars*>(sDx0 + 2 * 128 * p.mP);
+
+  const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
+  const uint16_t cmask = (uint16_t)((1u << csize) - 1);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < DX_MAX_NS; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], csize); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->a_full[i], 8);   mbar_init(&bars->a_empty[i], 1);
+      mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 8);
+      mbar_init(&bars->x_full[i], 1);   mbar_init(&bars->x_empty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 2 * 128 * p.mP; i += DX_THREADS) sDx0[i] = 0.f;
+  if (warp == 1) tmem_alloc(&bars->tmem_base, 512);
+  fence_before_sync();
+  __syncthreads();
+  if (csize > 1) cluster_sync_all();
+  fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+  const int64_t G = gridDim.x;
+  auto tile_of = [&](int it, int t) -> int64_t { return (int64_t)it * 2 * G + (int64_t)t * G + blockIdx.x; };
+  auto ntiles_of = [&](int it) -> int { return tile_of(it, 1) < p.n_tiles ? 2 : (tile_of(it, 0) < p.n_tiles ? 1 : 0); };
+
+  if (warp == 0) {
+    // =============================== TMA: x0 rows of the iteration's tiles + the W'' stream ===============================
+    if (lane == 0) {
+      prefetch_tmap(&tmW);
+      const int slice = HpQ / (int)csize;
+      const int wr0 = (int)crank * slice;
+      uint32_t ws = 0, wphase = 1;
+      bool first_pass = true;
+      int xuse[2] = {0, 0};
+      for (int it = 0; it < p.n_iters; ++it) {
+        const int nt = ntiles_of(it);
+        for (int t = 0; t < nt; ++t) {
+          if (xuse[t] > 0) mbar_wait(&bars->x_empty[t], (xuse[t] - 1) & 1);
+          const int64_t r0 = tile_of(it, t) * 128;
+          const uint32_t nrows = (uint32_t)min((int64_t)128, p.R - r0);
+          mbar_arrive_expect_tx(&bars->x_full[t], nrows * (uint32_t)(p.mP * 2));
+          bulk_load_1d(sX0 + (size_t)t * x0_tile, p.x0t + r0 * p.mP, nrows * (uint32_t)(p.mP * 2), &bars->x_full[t]);
+          ++xuse[t];
+        }
+        for (int j = 0; j < p.m; ++j) {
+          if (!first_pass) mbar_wait(&bars->w_empty[ws], wphase);
+          mbar_arrive_expect_tx(&bars->w_full[ws], w_slot_bytes);
+          for (int c = 0; c < p.n_hchunks; ++c) {
+            uint8_t* dst = sW + (size_t)ws * w_slot_bytes + (size_t)c * w_box_bytes + (size_t)wr0 * 128;
+            if (csize > 1) tma_load_2d_mcast(dst, &tmW, c * 64, j * HpQ + wr0, &bars->w_full[ws], cmask);
+            else tma_load_2d(dst, &tmW, c * 64, j * HpQ + wr0, &bars->w_full[ws]);
+          }
+          if (++ws == (uint32_t)p.ns) { ws = 0; wphase ^= 1; first_pass = false; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    const uint32_t idesc = make_idesc_bf16(128, HpQ);
+    const uint64_t bdesc0 = make_desc_k_sw128(smem_u32(sW));
+    const uint32_t slot_desc_step = w_slot_bytes >> 4;
+    const uint32_t box_desc_step = w_box_bytes >> 4;
+    uint32_t ws = 0, wphase = 0;
+    uint64_t bdesc = bdesc0;
+    uint32_t fuse[2] = {0, 0};      // fields issued so far per tile slot (accumulator phase)
+    int ause[2] = {0, 0};           // tiles staged so far per tile slot
+    const int ksteps = p.H_pad / 16;
+    for (int it = 0; it < p.n_iters; ++it) {
+      const int nt = ntiles_of(it);
+      for (int t = 0; t < nt; ++t) {
+        mbar_wait(&bars->a_full[t], ause[t] & 1);
+        fence_after_sync();
+      }
+      for (int j = 0; j < p.m; ++j) {
+        mbar_wait(&bars->w_full[ws], wphase);
+        fence_after_sync();
+        for (int t = 0; t < nt; ++t) {
+          if (fuse[t] > 0) {
+            mbar_wait(&bars->acc_empty[t], (fuse[t] - 1) & 1);
+            fence_after_sync();
+          }
+          if (elect_one()) {
+            const uint32_t d_addr = tmem_base + DX_ACC_COL0 + (uint32_t)t * DX_ACC_COLS;
+            const uint32_t a_addr = tmem_base + (uint32_t)t * 128;
+            uint64_t bd = bdesc;
+            for (int ks = 0; ks < ksteps; ks += 4, bd += box_desc_step) {
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                if (ks + k4 < ksteps) umma_ts(d_addr, a_addr + (uint32_t)(ks + k4) * 8, bd + (uint64_t)(k4 * 2), idesc, (ks + k4) > 0 ? 1u : 0u);
+              }
+            }
+            umma_commit(&bars->acc_full[t]);
+          }
+          __syncwarp();
+          ++fuse[t];
+        }
+        if (elect_one()) {
+          if (csize > 1) umma_commit_mcast(&bars->w_empty[ws], cmask);
+          else umma_commit(&bars->w_empty[ws]);
+        }
+        __syncwarp();
+        if (++ws == (uint32_t)p.ns) { ws = 0; wphase ^= 1; bdesc = bdesc0; }
+        else bdesc += slot_desc_step;
+      }
+      for (int t = 0; t < nt; ++t) {
+        if (elect_one()) umma_commit(&bars->a_empty[t]);     // every MMA that reads this tile's dY has been issued and will complete
+        __syncwarp();
+        ++ause[t];
+      }
+    }
+  } else {
+    // =============================== row warps (both tiles) ===============================
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int rl = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint32_t fuse[2] = {0, 0};
+    int use[2] = {0, 0};
+    uint32_t* myXk[2] = {sXk + ((0 * 2 + half) * NPAIR) * 128 + rl, sXk + ((1 * 2 + half) * NPAIR) * 128 + rl};
+    for (int it = 0; it < p.n_iters; ++it) {
+      const int nt = ntiles_of(it);
+      if (nt == 0) continue;
+      int64_t row[2];
+      bool valid[2];
+      float dxk[2][HALF];
+      for (int t = 0; t < 2; ++t) {
+        row[t] = tile_of(it, t) * 128 + rl;
+        valid[t] = t < nt && row[t] < p.R;
+      }
+      // ---- stage the tiles' dY rows into TMEM (A operands); all global loads of a row half are issued before the first store
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (t < nt) {
+          if (use[t] > 0) {
+            mbar_wait(&bars->a_empty[t], (use[t] - 1) & 1);
+            fence_after_sync();
+          }
+          const int ncol = p.H_pad / 2;                // 32-bit columns of the A tile
+          const int c_beg = half == 0 ? 0 : ((ncol / 2 + 3) & ~3);
+          const int c_end = half == 0 ? ((ncol / 2 + 3) & ~3) : ncol;
+          const uint32_t* src = reinterpret_cast<const uint32_t*>(p.dyt + row[t] * p.Hs);
+          uint4 buf[17];                               // (128 / 2 + 3) / 4 granules at most
+          int ng = 0;
+          for (int c = c_beg; c < c_end; c += 4, ++ng) {
+            buf[ng] = make_uint4(0u, 0u, 0u, 0u);
+            if (valid[t] && c * 2 < p.Hs) buf[ng] = *reinterpret_cast<const uint4*>(src + c);
+          }
+          ng = 0;
+          for (int c = c_beg; c < c_end; c += 4, ++ng) {
+            const uint32_t v4[4] = {buf[ng].x, buf[ng].y, buf[ng].z, buf[ng].w};
+            tmem_st_x4(tmem_base + lane_addr + (uint32_t)t * 128 + c, v4);
+          }
+          tmem_wait_st();
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->a_full[t]);
+        }
+      }
+      // ---- this thread's X^{k-1} row halves -> private shared-memory columns; accumulators
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) dxk[t][i] = 0.f;
+        if (t < nt) {
+          const __nv_bfloat16* xr = p.xkt + row[t] * p.xk_pitch + half * HALF;
+#pragma unroll
+          for (int v8 = 0; v8 < HALF / 8; ++v8) {
+            uint4 x = make_uint4(0u, 0u, 0u, 0u);
+            if (valid[t] && half * HALF + v8 * 8 < p.xk_pitch) x = *reinterpret_cast<const uint4*>(xr + v8 * 8);
+            myXk[t][(v8 * 4 + 0) * 128] = x.x;
+            myXk[t][(v8 * 4 + 1) * 128] = x.y;
+            myXk[t][(v8 * 4 + 2) * 128] = x.z;
+            myXk[t][(v8 * 4 + 3) * 128] = x.w;
+          }
+          mbar_wait(&bars->x_full[t], use[t] & 1);
+        }
+      }
+      // ---- fields
+      for (int j = 0; j < p.m; ++j) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (t < nt) {
+            const __nv_bfloat16* x0row = reinterpret_cast<const __nv_bfloat16*>(sX0 + (size_t)t * x0_tile) + (size_t)rl * p.mP;
+            const float x0v = __bfloat162float(x0row[j]);
+            mbar_wait(&bars->acc_full[t], fuse[t] & 1);
+            fence_after_sync();
+            const uint32_t acc = tmem_base + lane_addr + DX_ACC_COL0 + (uint32_t)t * DX_ACC_COLS + half * HALF;
+            float dot = 0.f;
+#pragma unroll
+            for (int b0 = 0; b0 < HALF; b0 += 32) {
+              constexpr int dummy = 0;
+              (void)dummy;
+              uint32_t v[32];
+#pragma unroll
+              for (int c0 = 0; c0 < 32; c0 += 8) {
+                if (b0 + c0 < HALF) {
+                  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                               : "=r"(v[c0 + 0]), "=r"(v[c0 + 1]), "=r"(v[c0 + 2]), "=r"(v[c0 + 3]), "=r"(v[c0 + 4]), "=r"(v[c0 + 5]),
+                                 "=r"(v[c0 + 6]), "=r"(v[c0 + 7])
+                               : "r"(acc + b0 + c0)
+                               : "memory");
+                }
+              }
+              tmem_wait_ld();
+              if (b0 + 32 >= HALF) {                     // last batch: the accumulator goes back to the tensor core
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->acc_empty[t]);
+              }
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                if (b0 + i < HALF) {
+                  const uint32_t xp = myXk[t][((b0 + i) / 2) * 128];
+                  const float2 xf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xp));
+                  const float z0 = __uint_as_float(v[i]), z1 = __uint_as_float(v[i + 1]);
+                  dxk[t][b0 + i] = fmaf(z0, x0v, dxk[t][b0 + i]);
+                  dxk[t][b0 + i + 1] = fmaf(z1, x0v, dxk[t][b0 + i + 1]);
+                  dot = fmaf(z0, xf.x, dot);
+                  dot = fmaf(z1, xf.y, dot);
+                }
+              }
+            }
+            atomicAdd(&sDx0[((size_t)t * 128 + rl) * p.mP + j], dot);      // two addends per element (the channel halves)
+            ++fuse[t];
+          }
+        }
+      }
+      // ---- tile outputs
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (valid[t]) {
+          float* o = p.dxk + row[t] * p.HpQ + half * HALF;
+#pragma unroll
+          for (int i = 0; i < HALF; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(dxk[t][i], dxk[t][i + 1], dxk[t][i + 2], dxk[t][i + 3]);
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // all dX0 partials of both tiles are in shared memory
+      {
+        const int t = half;                              // the half-0 warps flush tile 0, the half-1 warps tile 1
+        float* plane = sDx0 + ((size_t)t * 128 + rl) * p.mP;
+        if (valid[t]) {
+          float* gx = p.dx0 + row[t] * p.mP;
+          for (int j = 0; j < p.m; ++j) gx[j] += plane[j];
+        }
+        for (int j = 0; j < p.m; ++j) plane[j] = 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // planes are zero again, x0 rows no longer needed
+      __syncwarp();
+      for (int t = 0; t < nt; ++t) {
+        if (lane == 0) mbar_arrive(&bars->x_empty[t]);
+        ++use[t];
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (csize > 1) cluster_sync_all();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 // W fp32 [H, Hp*m] (k = i*m + j) -> W'' bf16 [m*HpQ rows (row = j*HpQ + i), HC cols (h), zero padded]
 __global__ void cin_prep_wt_kernel(const float* __restrict__ W, int H, int Hp, int m, int HpQ, int HC, __nv_bfloat16* __restrict__ Wt) {
   int64_t total = (int64_t)m * HpQ * HC;
@@ -342,6 +636,29 @@ extern int g_cin_tc_cluster_shared;
 int g_cin_dx_debug = 0;
 extern "C" void xdfm_cin_dx_set_debug(int v) { g_cin_dx_debug = v; }
 
+int g_cin_dx_pair = 1;
+extern "C" void xdfm_cin_dx_set_pair(int v) { g_cin_dx_pair = v ? 1 : 0; }
+
+template <int NQ>
+static int launch_dx_pair(const CUtensorMap& tmW, const CinDxParams& p, size_t smem, int blocks, int cluster, cudaStream_t st) {
+  XDFM_CUDA(cudaFuncSetAttribute(cin_bwd_dx_tc_pair_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(DX_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  XDFM_CUDA(cudaLaunchKernelEx(&cfg, cin_bwd_dx_tc_pair_kernel<NQ>, tmW, p));
+  XDFM_LAUNCH_CHECK();
+  return XDFM_OK;
+}
+
 template <int NQ>
 static int launch_dx(const CUtensorMap& tmW, const CinDxParams& p, size_t smem, int blocks, int cluster, cudaStream_t st) {
   XDFM_CUDA(cudaFuncSetAttribute(cin_bwd_dx_tc_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -394,6 +711,24 @@ extern "C" int xdfm_cin_bwd_dx_tc(const void* dyt, const void* x0t, const void* 
   int blocks = (int)std::min<int64_t>(ceil_div64(p.n_tiles, cluster) * cluster, (int64_t)(sms / cluster) * cluster);
   blocks = std::max(blocks, cluster);
   p.n_iters = (int)ceil_div64(p.n_tiles, blocks);
+  if (g_cin_dx_pair && g_cin_dx_debug == 0) {
+    // tile-pair kernel: needs the pair's shared-memory areas next to at least two W'' slots
+    const size_t slot = (size_t)g.HpQ * 128 * g.n_hchunks;
+    const size_t fixed = 2 * (size_t)128 * g.mP * 2 + (size_t)2 * 2 * (g.HpQ / 4) * 128 * 4 + 2 * (size_t)128 * g.mP * 4 +
+                         sizeof(CinDxPairBars) + 256;
+    int ns = (227 * 1024 > fixed) ? (int)std::min<size_t>((227 * 1024 - fixed) / slot, DX_MAX_NS) : 0;
+    if (ns >= 2) {
+      CinDxParams pp = p;
+      pp.ns = ns;
+      pp.n_iters = (int)ceil_div64(p.n_tiles, 2 * (int64_t)blocks);
+      const size_t smem_pair = fixed + (size_t)ns * slot;
+      switch (g.HpQ / 16) {
+#define CASE_NQP(n) case n: return launch_dx_pair<n>(tmW, pp, smem_pair, blocks, cluster, st);
+        CASE_NQP(1) CASE_NQP(2) CASE_NQP(3) CASE_NQP(4) CASE_NQP(5) CASE_NQP(6) CASE_NQP(7) CASE_NQP(8)
+#undef CASE_NQP
+      }
+    }
+  }
   switch (g.HpQ / 16) {
 #define CASE_NQ(n) case n: return launch_dx<n>(tmW, p, g.smem, blocks, cluster, st);
     CASE_NQ(1) CASE_NQ(2) CASE_NQ(3) CASE_NQ(4) CASE_NQ(5) CASE_NQ(6) CASE_NQ(7) CASE_NQ(8)
