@@ -197,14 +197,14 @@ def test_cin_tc_backward_dx_matches_emulation(case, cluster):
 
 
 @pytest.mark.parametrize("case", [(19, 26, 16, 200, 100), (2500, 26, 16, 200, 26), (700, 22, 32, 64, 22)], ids=str)
-def test_cin_tc_backward_dx_single_tile_kernel_still_matches(case):
-    """Shapes that default to the tile-pair dX kernel, forced through the single-tile kernel (xdfm_cin_dx_set_pair(0))."""
+def test_cin_tc_backward_dx_tile_pair_kernel_matches(case):
+    """The optional tile-pair dX kernel (xdfm_cin_dx_set_pair(1)): two 128-row tiles per streamed weight field."""
     from deepctr import _native as Nv
-    Nv.lib().xdfm_cin_dx_set_pair(0)
+    Nv.lib().xdfm_cin_dx_set_pair(1)
     try:
         test_cin_tc_backward_dx_matches_emulation(case, 2)
     finally:
-        Nv.lib().xdfm_cin_dx_set_pair(1)
+        Nv.lib().xdfm_cin_dx_set_pair(0)
 
 
 def test_cin_dy_rows():

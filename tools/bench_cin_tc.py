@@ -91,7 +91,7 @@ def time_dx(B, m, D, H, Hp, cluster=2, reps=5):
         ms = sorted(ts)[len(ts) // 2]
         print("dX B=%d m=%d D=%d H=%d Hp=%d %s: %.3f ms  %.1f TFLOP/s" % (B, m, D, H, Hp, "tile-pair" if dbg == 0 else "single-tile", ms,
                                                                          2.0 * R * H * Hp * m / ms / 1e9), flush=True)
-    L.xdfm_cin_dx_set_pair(1)
+    L.xdfm_cin_dx_set_pair(0)
 
 
 if __name__ == "__main__" and os.environ.get("BENCH_DX"):
