@@ -196,6 +196,17 @@ def test_cin_tc_backward_dx_matches_emulation(case, cluster):
     assert_close(got_dx0, ref_dx0, 1e-3, 1e-3 * ref_dx0.abs().max().item(), "dx0")
 
 
+@pytest.mark.parametrize("case", [(19, 26, 16, 200, 100), (2500, 26, 16, 200, 26), (33, 26, 8, 128, 128), (2500, 12, 16, 40, 20)], ids=str)
+def test_cin_tc_backward_dx_two_row_warps_per_quarter(case):
+    """The dX kernel's older warp layout (2 row warps per TMEM lane quarter; the default is 4)."""
+    from deepctr import _native as Nv
+    Nv.lib().xdfm_cin_dx_set_groups(2)
+    try:
+        test_cin_tc_backward_dx_matches_emulation(case, 2)
+    finally:
+        Nv.lib().xdfm_cin_dx_set_groups(4)
+
+
 @pytest.mark.parametrize("case", [(19, 26, 16, 200, 100), (2500, 26, 16, 200, 26), (700, 22, 32, 64, 22)], ids=str)
 def test_cin_tc_backward_dx_tile_pair_kernel_matches(case):
     """The optional tile-pair dX kernel (xdfm_cin_dx_set_pair(1)): two 128-row tiles per streamed weight field."""

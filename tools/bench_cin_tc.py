@@ -74,9 +74,10 @@ def time_dx(B, m, D, H, Hp, cluster=2, reps=5):
     dxk = torch.empty(R, HpQ, device=DEV)
     dx0 = torch.zeros(R, r8(m), device=DEV)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
-    for dbg in (0, -1):
+    for dbg in (4, 2):
         L.xdfm_cin_dx_set_debug(0)
-        L.xdfm_cin_dx_set_pair(1 if dbg == 0 else 0)
+        L.xdfm_cin_dx_set_groups(4)
+        L.xdfm_cin_dx_set_groups(dbg)
         ts = []
         for r in range(reps + 2):
             flush.zero_()
@@ -89,9 +90,9 @@ def time_dx(B, m, D, H, Hp, cluster=2, reps=5):
             if r >= 2:
                 ts.append(e0.elapsed_time(e1))
         ms = sorted(ts)[len(ts) // 2]
-        print("dX B=%d m=%d D=%d H=%d Hp=%d %s: %.3f ms  %.1f TFLOP/s" % (B, m, D, H, Hp, "tile-pair" if dbg == 0 else "single-tile", ms,
+        print("dX B=%d m=%d D=%d H=%d Hp=%d %s: %.3f ms  %.1f TFLOP/s" % (B, m, D, H, Hp, "%d row warps per lane quarter" % dbg, ms,
                                                                          2.0 * R * H * Hp * m / ms / 1e9), flush=True)
-    L.xdfm_cin_dx_set_pair(0)
+    L.xdfm_cin_dx_set_groups(4)
 
 
 if __name__ == "__main__" and os.environ.get("BENCH_DX"):

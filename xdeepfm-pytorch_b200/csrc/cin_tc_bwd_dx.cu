@@ -50,11 +50,13 @@ struct __align__(8) CinDxBars {
   uint32_t tmem_base;
 };
 
-// NQ = HpQ / 16
-template <int NQ>
-__global__ void __launch_bounds__(DX_THREADS, 1) cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmW, CinDxParams p) {
+// NQ = HpQ / 16; NG = row warps per TMEM lane quarter (2 or 4): each drains HpQ / NG channels of every dZ_j.  ncu (round 1) shows the
+// row warps, not the tensor core, pacing this kernel at low IPC (TMEM-load and FMA latencies, spills at 168 registers); with NG = 4
+// there are twice as many resident warps to hide those latencies and each needs half the registers.
+template <int NQ, int NG>
+__global__ void __launch_bounds__((2 + 4 * NG) * 32, 1) cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmW, CinDxParams p) {
   constexpr int HpQ = NQ * 16;
-  constexpr int HALF = HpQ / 2;                    // channels per row warp (multiple of 8)
+  constexpr int HALF = HpQ / NG;                   // channels per row warp (multiple of 4)
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t w_box_bytes = (uint32_t)HpQ * 128;                          // one 64-wide h-chunk of one field
@@ -62,19 +64,19 @@ __global__ void __launch_bounds__(DX_THREADS, 1) cin_bwd_dx_tc_kernel(const __gr
   uint8_t* sW = smem;                                                         // ns x n_hchunks x [HpQ x 128 B]
   const uint32_t x0_tile = (uint32_t)128 * p.mP * 2;
   uint8_t* sX0 = sW + (size_t)p.ns * w_slot_bytes;                            // 2 x [128][mP] bf16
-  float* sDx0 = reinterpret_cast<float*>(sX0 + 2 * (size_t)x0_tile);          // [2 halves][128][mP] fp32 dX0 partials
-  CinDxBars* bars = reinterpret_cast<CinDxBars*>(sDx0 + 2 * 128 * p.mP);
+  float* sDx0 = reinterpret_cast<float*>(sX0 + 2 * (size_t)x0_tile);          // [NG groups][128][mP] fp32 dX0 partials
+  CinDxBars* bars = reinterpret_cast<CinDxBars*>(sDx0 + NG * 128 * p.mP);
 
   const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
   const uint16_t cmask = (uint16_t)((1u << csize) - 1);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < DX_MAX_NS; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], csize); }
-    mbar_init(&bars->a_full, 8);
+    mbar_init(&bars->a_full, 4 * NG);
     mbar_init(&bars->a_empty, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 8);
-      mbar_init(&bars->x_full[i], 1);   mbar_init(&bars->x_empty[i], 8);
+      mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 4 * NG);
+      mbar_init(&bars->x_full[i], 1);   mbar_init(&bars->x_empty[i], 4 * NG);
     }
     fence_barrier_init();
   }
@@ -173,7 +175,7 @@ __global__ void __launch_bounds__(DX_THREADS, 1) cin_bwd_dx_tc_kernel(const __gr
   } else {
     // =============================== row warps ===============================
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;              // 0: channels [0, HALF), 1: [HALF, HpQ)
+    const int half = (warp - 2) >> 2;              // channel group: channels [half * HALF, (half + 1) * HALF)
     const int rl = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     uint32_t jc = 0;
@@ -190,20 +192,22 @@ __global__ void __launch_bounds__(DX_THREADS, 1) cin_bwd_dx_tc_kernel(const __gr
       }
       {
         const int ncol = p.H_pad / 2;                // 32-bit columns of the A tile
-        const int c_beg = half == 0 ? 0 : ((ncol / 2 + 3) & ~3);
-        const int c_end = half == 0 ? ((ncol / 2 + 3) & ~3) : ncol;
+        const int per = ((ncol + NG - 1) / NG + 3) & ~3;
+        const int c_beg = half * per;
+        const int c_end = min(ncol, c_beg + per);
         const uint32_t* src = reinterpret_cast<const uint32_t*>(p.dyt + row * p.Hs);
         // all global loads of the row half are issued before the first TMEM store (ncu, round 1: 12.6 % of the kernel's samples sat
         // on the STTM of a load -> store loop that paid one global-load latency per 16 bytes); at most 17 granules (H_pad <= 256)
-        uint4 gbuf[17];
+        constexpr int GB = 32 / NG + 1;
+        uint4 gbuf[GB];
 #pragma unroll
-        for (int gi = 0; gi < 17; ++gi) {
+        for (int gi = 0; gi < GB; ++gi) {
           const int c = c_beg + gi * 4;
           gbuf[gi] = make_uint4(0u, 0u, 0u, 0u);
           if (c < c_end && valid && c * 2 < p.Hs) gbuf[gi] = *reinterpret_cast<const uint4*>(src + c);   // Hs multiple of 8: whole granules
         }
 #pragma unroll
-        for (int gi = 0; gi < 17; ++gi) {
+        for (int gi = 0; gi < GB; ++gi) {
           const int c = c_beg + gi * 4;
           if (c < c_end) {
             const uint32_t v[4] = {gbuf[gi].x, gbuf[gi].y, gbuf[gi].z, gbuf[gi].w};
@@ -223,13 +227,11 @@ __global__ void __launch_bounds__(DX_THREADS, 1) cin_bwd_dx_tc_kernel(const __gr
       {
         const __nv_bfloat16* xr = p.xkt + row * p.xk_pitch + half * HALF;
 #pragma unroll
-        for (int v8 = 0; v8 < HALF / 8; ++v8) {
-          uint4 t = make_uint4(0u, 0u, 0u, 0u);
-          if (valid && half * HALF + v8 * 8 < p.xk_pitch) t = *reinterpret_cast<const uint4*>(xr + v8 * 8);
-          xk2[v8 * 4 + 0] = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
-          xk2[v8 * 4 + 1] = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
-          xk2[v8 * 4 + 2] = *reinterpret_cast<const __nv_bfloat162*>(&t.z);
-          xk2[v8 * 4 + 3] = *reinterpret_cast<const __nv_bfloat162*>(&t.w);
+        for (int v4 = 0; v4 < HALF / 4; ++v4) {
+          uint2 t = make_uint2(0u, 0u);
+          if (valid && half * HALF + v4 * 4 < p.xk_pitch) t = *reinterpret_cast<const uint2*>(xr + v4 * 4);
+          xk2[v4 * 2 + 0] = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
+          xk2[v4 * 2 + 1] = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
         }
       }
       float dxk[HALF];
@@ -249,13 +251,22 @@ __global__ void __launch_bounds__(DX_THREADS, 1) cin_bwd_dx_tc_kernel(const __gr
 #pragma unroll
           for (int i = 0; i < HALF; ++i) v[i] = 0u;
         } else
+        {
 #pragma unroll
-        for (int c0 = 0; c0 < HALF; c0 += 8) {
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                       : "=r"(v[c0 + 0]), "=r"(v[c0 + 1]), "=r"(v[c0 + 2]), "=r"(v[c0 + 3]), "=r"(v[c0 + 4]), "=r"(v[c0 + 5]),
-                         "=r"(v[c0 + 6]), "=r"(v[c0 + 7])
-                       : "r"(acc + c0)
-                       : "memory");
+          for (int c0 = 0; c0 + 8 <= HALF; c0 += 8) {
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(v[c0 + 0]), "=r"(v[c0 + 1]), "=r"(v[c0 + 2]), "=r"(v[c0 + 3]), "=r"(v[c0 + 4]), "=r"(v[c0 + 5]),
+                           "=r"(v[c0 + 6]), "=r"(v[c0 + 7])
+                         : "r"(acc + c0)
+                         : "memory");
+          }
+          if constexpr (HALF % 8 != 0) {
+            constexpr int c0 = HALF - 4;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(v[c0 + 0]), "=r"(v[c0 + 1]), "=r"(v[c0 + 2]), "=r"(v[c0 + 3])
+                         : "r"(acc + c0)
+                         : "memory");
+          }
         }
         tmem_wait_ld();
         fence_before_sync();
@@ -274,7 +285,7 @@ __global__ void __launch_bounds__(DX_THREADS, 1) cin_bwd_dx_tc_kernel(const __gr
           }
           dot = (d4[0] + d4[1]) + (d4[2] + d4[3]);
         }
-        // dX0[r, j] partial of this warp's channel half: parked in shared memory (plane = half), combined at tile end
+        // dX0[r, j] partial of this warp's channel group: parked in shared memory (plane = group), combined in group order at tile end
         sDx0[(half * 128 + rl) * p.mP + j] = dot;
       }
       // ---- tile outputs
@@ -283,12 +294,17 @@ __global__ void __launch_bounds__(DX_THREADS, 1) cin_bwd_dx_tc_kernel(const __gr
 #pragma unroll
         for (int i = 0; i < HALF; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(dxk[i], dxk[i + 1], dxk[i + 2], dxk[i + 3]);
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");     // both halves' dX0 partials are in shared memory
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * NG) : "memory");     // all groups' dX0 partials are in shared memory
       if (half == 0 && valid) {
         float* g = p.dx0 + row * p.mP;
-        for (int j = 0; j < p.m; ++j) g[j] += sDx0[rl * p.mP + j] + sDx0[(128 + rl) * p.mP + j];
+        for (int j = 0; j < p.m; ++j) {
+          float sacc = sDx0[rl * p.mP + j];
+#pragma unroll
+          for (int gq = 1; gq < NG; ++gq) sacc += sDx0[(gq * 128 + rl) * p.mP + j];
+          g[j] += sacc;
+        }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");     // partial planes may be overwritten by the next tile
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * NG) : "memory");     // partial planes may be overwritten by the next tile
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->x_empty[buf]);
       ++at;
@@ -671,12 +687,15 @@ static int launch_dx_pair(const CUtensorMap& tmW, const CinDxParams& p, size_t s
   return XDFM_OK;
 }
 
-template <int NQ>
+int g_cin_dx_groups = 4;     // row warps per TMEM lane quarter in the dX kernel (2 or 4)
+extern "C" void xdfm_cin_dx_set_groups(int v) { g_cin_dx_groups = (v == 2) ? 2 : 4; }
+
+template <int NQ, int NG>
 static int launch_dx(const CUtensorMap& tmW, const CinDxParams& p, size_t smem, int blocks, int cluster, cudaStream_t st) {
-  XDFM_CUDA(cudaFuncSetAttribute(cin_bwd_dx_tc_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  XDFM_CUDA(cudaFuncSetAttribute(cin_bwd_dx_tc_kernel<NQ, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(blocks);
-  cfg.blockDim = dim3(DX_THREADS);
+  cfg.blockDim = dim3((2 + 4 * NG) * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -686,7 +705,7 @@ static int launch_dx(const CUtensorMap& tmW, const CinDxParams& p, size_t smem, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  XDFM_CUDA(cudaLaunchKernelEx(&cfg, cin_bwd_dx_tc_kernel<NQ>, tmW, p));
+  XDFM_CUDA(cudaLaunchKernelEx(&cfg, cin_bwd_dx_tc_kernel<NQ, NG>, tmW, p));
   XDFM_LAUNCH_CHECK();
   return XDFM_OK;
 }
@@ -741,8 +760,24 @@ extern "C" int xdfm_cin_bwd_dx_tc(const void* dyt, const void* x0t, const void* 
       }
     }
   }
+  if (g_cin_dx_groups == 4) {
+    // four row warps per lane quarter: two more dX0 partial planes in shared memory
+    const size_t slot = (size_t)g.HpQ * 128 * g.n_hchunks;
+    const size_t fixed4 = 2 * (size_t)128 * g.mP * 2 + 4 * (size_t)128 * g.mP * 4 + sizeof(CinDxBars) + 256;
+    int ns4 = (227 * 1024 > fixed4) ? (int)std::min<size_t>((227 * 1024 - fixed4) / slot, DX_MAX_NS) : 0;
+    if (ns4 >= 2) {
+      CinDxParams p4 = p;
+      p4.ns = ns4;
+      const size_t smem4 = fixed4 + (size_t)ns4 * slot;
+      switch (g.HpQ / 16) {
+#define CASE_NQ4(n) case n: return launch_dx<n, 4>(tmW, p4, smem4, blocks, cluster, st);
+        CASE_NQ4(1) CASE_NQ4(2) CASE_NQ4(3) CASE_NQ4(4) CASE_NQ4(5) CASE_NQ4(6) CASE_NQ4(7) CASE_NQ4(8)
+#undef CASE_NQ4
+      }
+    }
+  }
   switch (g.HpQ / 16) {
-#define CASE_NQ(n) case n: return launch_dx<n>(tmW, p, g.smem, blocks, cluster, st);
+#define CASE_NQ(n) case n: return launch_dx<n, 2>(tmW, p, g.smem, blocks, cluster, st);
     CASE_NQ(1) CASE_NQ(2) CASE_NQ(3) CASE_NQ(4) CASE_NQ(5) CASE_NQ(6) CASE_NQ(7) CASE_NQ(8)
 #undef CASE_NQ
   }

@@ -90,6 +90,7 @@ _SIGS = {
     "xdfm_cvt_bf16": (c_int, [_P, c_int, c_int, c_int64, c_int, _P, c_int64, _P]),
     "xdfm_set_rows_opt_dense_version": (None, [c_int]),
     "xdfm_cin_dx_set_debug": (None, [c_int]),
+    "xdfm_cin_dx_set_groups": (None, [c_int]),
     "xdfm_cin_dx_set_pair": (None, [c_int]),
     "xdfm_opt_tick_hist": (c_int, [_P, POINTER(OptCfg), _P, c_int64, c_int64, _P]),
     "xdfm_rows_catchup": (c_int, [POINTER(OptCfg), _P, _P, c_int64, POINTER(_P), POINTER(_P), POINTER(_P), _P, POINTER(c_int64), c_int, c_int,
