@@ -200,7 +200,8 @@ int xdfm_add_rows_f32(float* a, int64_t pitch_a, const float* b, int64_t pitch_b
 int64_t xdfm_cin_bwd_dx_tc_wt_elems(int m, int Hp, int H, int D);
 /* diagnostic bit mask for profiling experiments (0 = production): 1 skip the epilogue contraction, 2 skip TMEM loads, 4 skip MMAs */
 void xdfm_cin_dx_set_debug(int v);
-/* row warps per TMEM lane quarter in the dX kernel: 4 (default; twice the resident warps, half the registers each) or 2 */
+/* row warps per TMEM lane quarter in the dX kernel: 2 (default) or 4 (twice the resident warps, half the registers each; measured
+ * slower in round 1) */
 void xdfm_cin_dx_set_groups(int v);
 /* 1: dX kernel that contracts two 128-row tiles per streamed W'' field when shared memory allows; 0 (default): single-tile kernel
  * (the pair variant halves the weight stream but measured the same time in round 1: profiles/r01_cin_findings.md) */

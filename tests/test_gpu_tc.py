@@ -197,14 +197,14 @@ def test_cin_tc_backward_dx_matches_emulation(case, cluster):
 
 
 @pytest.mark.parametrize("case", [(19, 26, 16, 200, 100), (2500, 26, 16, 200, 26), (33, 26, 8, 128, 128), (2500, 12, 16, 40, 20)], ids=str)
-def test_cin_tc_backward_dx_two_row_warps_per_quarter(case):
-    """The dX kernel's older warp layout (2 row warps per TMEM lane quarter; the default is 4)."""
+def test_cin_tc_backward_dx_four_row_warps_per_quarter(case):
+    """The dX kernel's optional warp layout with 4 row warps per TMEM lane quarter (the default is 2)."""
     from deepctr import _native as Nv
-    Nv.lib().xdfm_cin_dx_set_groups(2)
+    Nv.lib().xdfm_cin_dx_set_groups(4)
     try:
         test_cin_tc_backward_dx_matches_emulation(case, 2)
     finally:
-        Nv.lib().xdfm_cin_dx_set_groups(4)
+        Nv.lib().xdfm_cin_dx_set_groups(2)
 
 
 @pytest.mark.parametrize("case", [(19, 26, 16, 200, 100), (2500, 26, 16, 200, 26), (700, 22, 32, 64, 22)], ids=str)

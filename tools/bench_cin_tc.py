@@ -76,7 +76,7 @@ def time_dx(B, m, D, H, Hp, cluster=2, reps=5):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
     for dbg in (4, 2):
         L.xdfm_cin_dx_set_debug(0)
-        L.xdfm_cin_dx_set_groups(4)
+        L.xdfm_cin_dx_set_groups(2)
         L.xdfm_cin_dx_set_groups(dbg)
         ts = []
         for r in range(reps + 2):
@@ -92,7 +92,7 @@ def time_dx(B, m, D, H, Hp, cluster=2, reps=5):
         ms = sorted(ts)[len(ts) // 2]
         print("dX B=%d m=%d D=%d H=%d Hp=%d %s: %.3f ms  %.1f TFLOP/s" % (B, m, D, H, Hp, "%d row warps per lane quarter" % dbg, ms,
                                                                          2.0 * R * H * Hp * m / ms / 1e9), flush=True)
-    L.xdfm_cin_dx_set_groups(4)
+    L.xdfm_cin_dx_set_groups(2)
 
 
 if __name__ == "__main__" and os.environ.get("BENCH_DX"):
