@@ -1,0 +1,73 @@
+"""Drop-in surface of the `deepctr` package (no GPU): the imports the reference's CLI scripts make (xdftrain.py:22-24,
+xdftrain_attn.py:26-28, xdftrain_pro.py:28-30), constructor signatures, state_dict keys and the Python-level error behaviour."""
+import inspect
+
+import pytest
+import torch
+
+from oracle import xdeepfm_oracle as O
+from tests.helpers import build_product_model
+
+
+def test_reference_script_imports_resolve():
+    from deepctr.callbacks import EarlyStopping, History, ModelCheckpoint  # noqa: F401
+    from deepctr.inputs import DenseFeat, SparseFeat, VarLenSparseFeat, build_input_features, combined_dnn_input, get_feature_names  # noqa: F401
+    from deepctr.layers import CIN, DNN, PredictionLayer  # noqa: F401
+    from deepctr.layers.cin_attention import AttentionPooling, CINAttention, CINAttentionV2, MultiHeadSelfAttention  # noqa: F401
+    from deepctr.models import xDeepFM, xDeepFMAttention, xDeepFMAttentionV2  # noqa: F401
+    from deepctr.xdeepfm_pro import (AutoDisLayer, BaseModelSFG, DenseFeatureEncoder, LabelAwareAttention, SFGDecoder, SFGLoss,  # noqa: F401
+                                     xDeepFMPro, xDeepFMProLight)
+
+
+def test_constructor_signatures_match_the_reference():
+    from deepctr.models import xDeepFM, xDeepFMAttention, xDeepFMAttentionV2
+    from deepctr.xdeepfm_pro import xDeepFMPro, xDeepFMProLight
+    base = ["linear_feature_columns", "dnn_feature_columns", "dnn_hidden_units", "cin_layer_size", "cin_split_half", "cin_activation"]
+    tail = ["l2_reg_linear", "l2_reg_embedding", "l2_reg_dnn", "l2_reg_cin", "init_std", "seed", "dnn_dropout", "dnn_activation",
+            "dnn_use_bn", "task", "device", "gpus"]
+
+    def names(cls):
+        return [p for p in inspect.signature(cls.__init__).parameters if p != "self"]
+    assert names(xDeepFM) == base + tail                                                                      # xdeepfm.py:42-45
+    attn = ["cin_num_heads", "cin_attn_dropout", "cin_use_layer_norm", "cin_use_residual"]
+    assert names(xDeepFMAttention) == base + attn + tail                                                      # xdeepfm_attn.py:55-62
+    assert names(xDeepFMAttentionV2) == base + attn + ["cin_num_attn_layers"] + tail                          # xdeepfm_attn.py:185-193
+    pro = ["use_sfg", "sfg_weight", "sfg_hidden_units", "sfg_dropout", "sfg_positive_only", "sfg_use_label_attention", "use_autodis",
+           "autodis_buckets", "autodis_temperature"]
+    assert names(xDeepFMPro) == base + tail + pro                                                             # xdeepfm_pro.py:57-87
+    assert names(xDeepFMProLight) == base + tail + pro
+    d = inspect.signature(xDeepFM.__init__).parameters
+    assert d["dnn_hidden_units"].default == (256, 256) and d["cin_layer_size"].default == (256, 128) and d["l2_reg_linear"].default == 1e-5
+    assert inspect.signature(xDeepFMProLight.__init__).parameters["sfg_weight"].default == 0.05
+
+
+@pytest.mark.parametrize("variant", ["xdeepfm", "attn", "attn_v2", "pro"])
+def test_state_dict_keys_and_shapes_match_the_reference_layout(variant):
+    spec = O.ModelSpec(sparse_names=["C1", "C2", "C3"], vocab_sizes=[11, 5, 40], embedding_dim=8, dense_names=["I1", "I2"],
+                       cin_layer_size=(8, 4), dnn_hidden_units=(8, 6), variant=variant, num_heads=2, num_attn_layers=2,
+                       sfg_hidden_units=(8, 4))
+    model = build_product_model(spec, "cpu")
+    want = O.param_shapes(spec)                                   # SURVEY.md 8a-K, probed on the reference
+    got = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert got == {k: tuple(v) for k, v in want.items()}
+
+
+def test_python_level_errors_mirror_the_reference():
+    from deepctr.inputs import DenseFeat, SparseFeat
+    from deepctr.layers import CIN
+    from deepctr.models import xDeepFM
+    with pytest.raises(ValueError):
+        CIN(3, ())                                                # interaction.py:178-180
+    with pytest.raises(ValueError):
+        CIN(3, (3, 2), split_half=True)                           # interaction.py:195-197
+    cols = [SparseFeat("C1", 10, 4), DenseFeat("I1", 1)]
+    with pytest.raises(ValueError):
+        xDeepFM(cols, cols, device="cuda:0", gpus=[1])            # basemodel.py:107-109
+    m = xDeepFM(cols, cols, device="cpu")
+    with pytest.raises(NotImplementedError):
+        m.compile("lbfgs", "binary_crossentropy")                 # basemodel.py:458
+    with pytest.raises(NotImplementedError):
+        m.compile("adam", "hinge")                                # basemodel.py:480
+    assert SparseFeat("a", 10000, "auto").embedding_dim == 6 * int(pow(10000, 0.25))     # inputs.py:29-30
+    with pytest.raises(RuntimeError):
+        m.fit({"C1": torch.zeros(4).numpy(), "I1": torch.zeros(4).numpy()}, torch.zeros(4, 1).numpy(), batch_size=2, verbose=0)   # no CPU fallback

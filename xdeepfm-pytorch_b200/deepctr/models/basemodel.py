@@ -84,12 +84,12 @@ class BaseModel(nn.Module):
         torch.manual_seed(seed)
         self.dnn_feature_columns = dnn_feature_columns
         self.linear_feature_columns = linear_feature_columns
-        self.reg_loss = torch.zeros((1,), device=device)
-        self.aux_loss = torch.zeros((1,), device=device)
         self.device = device
         self.gpus = gpus
         if gpus and str(self.gpus[0]) not in self.device:
             raise ValueError("`gpus[0]` should be the same gpu with `device`")
+        self.reg_loss = torch.zeros((1,), device=device)
+        self.aux_loss = torch.zeros((1,), device=device)
         if varlen_columns(list(linear_feature_columns) + list(dnn_feature_columns)):
             raise NotImplementedError("VarLenSparseFeat is outside the xDeepFM hot path of this build")
 
