@@ -149,3 +149,23 @@ def test_cuda_graph_replay_equals_eager_steps(optimizer):
     for k in sd_e:
         assert torch.equal(sd_e[k], sd_g[k]), k
     assert abs(loss_e - loss_g) <= 1e-9 * abs(loss_e) and abs(reg_e - reg_g) <= 1e-6 * abs(reg_e)
+
+
+def test_fit_verbose_metrics_on_the_fused_graph_path():
+    """verbose > 0: per-step train metrics come from a device-side prediction log (filled from the CUDA graph's static output);
+    losses must equal the verbose = 0 run and the History keys those of the reference."""
+    spec, params, z = load_case("fit_small_adam")
+    X, y = z["X"], z["y"]
+    hists = []
+    for verbose in (0, 2):
+        model = build_product_model(spec, DEV)
+        model.load_state_dict(params, strict=True)
+        model.compile("adam", "binary_crossentropy", metrics=["binary_crossentropy", "auc"])
+        names = list(model.feature_index.keys())
+        xd = {n: X[:, i].copy() for i, n in enumerate(names)}
+        hists.append(model.fit(xd, y.reshape(-1, 1), batch_size=16, epochs=2, verbose=verbose, shuffle=False,
+                               validation_data=(dict(xd), y.reshape(-1, 1))).history)
+        assert model._graphs, "6 steps per epoch: the step should have been captured"
+    assert np.allclose(hists[0]["loss"], hists[1]["loss"], rtol=1e-6)
+    assert set(hists[1]) >= {"loss", "binary_crossentropy", "auc", "val_binary_crossentropy", "val_auc"}
+    assert all(0.0 <= v <= 1.0 for v in hists[1]["auc"])
