@@ -42,6 +42,13 @@ WORKLOADS = {
     "cfg4": dict(m=22, nd=0, D=32, cin=(256, 256, 256, 256), dnn=(256, 256), batch=8192,
                  vocab=[241, 8, 8, 4738, 7746, 27, 8553, 560, 37, 10000, 10000, 8252, 6, 5, 2627, 9, 10, 436, 5, 69, 173, 61],
                  variant="pro"),
+    # BASELINE.json configs[4]: large-vocab xDeepFM, 26 tables up to 50 M rows x 64 dims (192.7 M rows = 50 GB of fp32 tables, 150 GB
+    # with Adam moments): never materialised whole (deferred_tables), row-sharded over the GPUs of the run (needs --gpus >= 2),
+    # global batch 65536 at 8 GPUs (8192 / GPU).  Optimizer semantics: only the rows a batch touches are updated
+    # (sparse_embedding_update; the reference's every-row-every-step Adam + L2 cannot run at this size).
+    "cfg5": dict(m=26, nd=13, D=64, cin=(256, 128), dnn=(256, 256), batch=8192, deferred=True, sparse_update=True,
+                 vocab=[50000000, 40000000, 30000000, 20000000, 10000000, 10000000, 10000000, 5000000, 5000000, 5000000, 2000000,
+                        2000000, 1000000, 1000000, 1000000, 500000, 100000, 50000, 10000, 5000, 1000, 500, 100, 50, 10, 4]),
 }
 
 
@@ -226,7 +233,9 @@ def workload_config(args, w):
             "dp%d dense (NCCL all-reduce) + tables row-sharded x%d over NVLink peer memory" % (
                 int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("WORLD_SIZE", "1"))),
             "optimizer": "adam", "cin_precision": args.cin_impl,
-            "table_semantics": "reference dense L2+Adam over every row, evaluated lazily (bit-identical replay of untouched rows; all "
+            "table_semantics": "only rows touched by a batch are updated (tables never materialised whole; NOT the reference's dense "
+                               "semantics, which cannot run at this vocabulary size)" if w.get("sparse_update") else
+                               "reference dense L2+Adam over every row, evaluated lazily (bit-identical replay of untouched rows; all "
                                "postponed updates are flushed inside the timed region)" if not args.dense_table_pass else
                                "reference dense L2+Adam over every row, streamed every step",
             "l2_flush": "not needed: 4 rotating batches; each step touches ~1 GB of fresh activations / gradients / random table rows "
@@ -265,7 +274,14 @@ def main():
     peaks = load_peaks()
     spec = make_spec(w)
     B = w["batch"]
-    model = build_product_model(spec, dev)
+    if w.get("deferred"):
+        if world < 2:
+            raise SystemExit("workload %s keeps its tables row-sharded over the GPUs of the run: launch with --gpus >= 2 (torchrun)" % args.workload)
+        from deepctr.inputs import deferred_tables
+        with deferred_tables():
+            model = build_product_model(spec, dev)
+    else:
+        model = build_product_model(spec, dev)
     # reference initialisation (init_std=1e-4 embeddings, default-init CIN) is what a user trains from
     if world > 1:
         # hybrid parallel: tables row-sharded over NVLink peer memory, dense part data-parallel (deepctr/distributed.py)
@@ -277,6 +293,8 @@ def main():
     if getattr(model, "sfg_decoder", None) is not None:
         model.sfg_decoder.precision = "bf16" if args.cin_impl == "bf16" else "fp32"
     model.optim.lazy_tables = not args.dense_table_pass
+    if w.get("sparse_update"):
+        model.optim.sparse_embedding_update = True
     n_pool = 4
     host = [(i.pin_memory(), d.pin_memory(), y.pin_memory()) for i, d, y in synth_batches(spec, B, n_pool, seed=2025 + rank)]
     devb = [(i.to(dev), d.to(dev), y.to(dev)) for i, d, y in host]

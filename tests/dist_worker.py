@@ -99,12 +99,45 @@ def run(rank, world, optimizer="adam", steps=6, per_rank=48, fit_check=True):
     print("dist parity ok: world=%d optimizer=%s losses=%s" % (world, optimizer, ["%.4f" % l for l in losses]), flush=True)
 
 
+def run_deferred(rank, world):
+    """Tables that are never materialised whole (deepctr.inputs.deferred_tables): shards are initialised in place; training runs;
+    the per-rank checkpoint carries the shard and its routing."""
+    from deepctr.distributed import shard_rows, sharded_state_dict
+    from deepctr.inputs import deferred_tables
+    dev = "cuda:%d" % torch.cuda.current_device()
+    spec = spec_for_test()
+    with deferred_tables():
+        model = build_product_model(spec, dev)
+    assert all(e.weight.shape[0] == 1 for e in model.embedding_dict.values())
+    model.distribute(max_batch=32)
+    model.compile("adam", "binary_crossentropy")
+    model.optim.sparse_embedding_update = True
+    model.train()
+    accum = torch.zeros(1, dtype=torch.float64, device=dev)
+    for s in range(4):
+        X, y = O.make_inputs(spec, 32, seed=500 + s + 10 * rank)
+        ids, dense = model.split_input(X.to(dev))
+        model.train_step(ids, dense, y.to(dev), accum)
+    assert torch.isfinite(accum).all() and accum.item() > 0
+    ck = sharded_state_dict(model)
+    sh = model._dist.sharded
+    assert ck["emb_shard"].shape == (sum(shard_rows(V, rank, world) for V in spec.vocab_sizes), spec.embedding_dim)
+    std = ck["emb_shard"].std().item()
+    assert 0.2e-4 < std < 5e-3, std            # N(0, 1e-4) init, a few rows moved by Adam
+    assert float(ck["emb_shard"].abs().max()) > 0
+    if rank == 0:
+        print("deferred tables ok: world=%d local rows=%d" % (world, sh.local_rows), flush=True)
+
+
 def spawn_entry(rank, world, init_file, optimizer):
     torch.cuda.set_device(rank % torch.cuda.device_count())
     dist.init_process_group("nccl", init_method="file://" + init_file, rank=rank, world_size=world,
                             device_id=torch.device("cuda", rank % torch.cuda.device_count()))
     try:
-        run(rank, world, optimizer)
+        if optimizer == "deferred":
+            run_deferred(rank, world)
+        else:
+            run(rank, world, optimizer)
     finally:
         dist.destroy_process_group()
 
@@ -115,6 +148,9 @@ if __name__ == "__main__":
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", rank))))
     try:
         for opt in (sys.argv[1:] or ["adam", "sgd"]):
-            run(rank, world, opt)
+            if opt == "deferred":
+                run_deferred(rank, world)
+            else:
+                run(rank, world, opt)
     finally:
         dist.destroy_process_group()

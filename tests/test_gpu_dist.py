@@ -108,6 +108,10 @@ def _run_in_subprocess(world, optimizer):
         mp.spawn(dist_worker.spawn_entry, args=(world, os.path.join(d, "init"), optimizer), nprocs=world, join=True)
 
 
+def test_deferred_tables_world_size_1():
+    _run_in_subprocess(1, "deferred")
+
+
 @pytest.mark.parametrize("optimizer", ["adam", "sgd"])
 def test_distribute_world_size_1_equals_plain_model(optimizer):
     _run_in_subprocess(1, optimizer)

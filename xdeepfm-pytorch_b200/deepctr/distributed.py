@@ -554,13 +554,24 @@ def attach(model, group=None, max_batch=None):
             if id(p) not in table_ids:
                 ctx.broadcast(p.data, 0)
         sh = ShardedSparse(ctx.rank, ctx.world, emb_plan.table_of, emb_plan.rows, emb_plan.vocab, emb_plan.width, dev)
+        emb_mods = list(model.embedding_dict.values())
+        ctx.deferred = any(hasattr(e, "deferred_rows") for e in emb_mods)
+        gen = torch.Generator(device=dev)
         for t, (we, wl) in enumerate(zip(emb_tables, lin_tables)):
-            ctx.broadcast(we.data, 0)
-            ctx.broadcast(wl.data, 0)
             a = sh.base[ctx.rank][t]
             k = shard_rows(sh.rows[t], ctx.rank, ctx.world)
-            sh.emb[a:a + k].copy_(take_shard(we.data, ctx.rank, ctx.world))
-            sh.lin[a:a + k].copy_(take_shard(wl.data, ctx.rank, ctx.world))
+            if hasattr(emb_mods[t], "deferred_rows"):
+                # built under deferred_tables(): the table never existed as a whole; this rank's rows are initialised in place
+                # (N(0, init_std) as inputs.create_embedding_matrix does), seeded per (table, rank)
+                std = float(getattr(emb_mods[t], "init_std", 1e-4))
+                gen.manual_seed(1024 + 7919 * t + ctx.rank)
+                sh.emb[a:a + k].normal_(0.0, std, generator=gen)
+                sh.lin[a:a + k].normal_(0.0, std, generator=gen)
+            else:
+                ctx.broadcast(we.data, 0)
+                ctx.broadcast(wl.data, 0)
+                sh.emb[a:a + k].copy_(take_shard(we.data, ctx.rank, ctx.world))
+                sh.lin[a:a + k].copy_(take_shard(wl.data, ctx.rank, ctx.world))
             # the full tables are not kept: state_dict() re-assembles them from the shards
             we.data = torch.empty((0, we.shape[1]), dtype=we.dtype, device=dev)
             wl.data = torch.empty((0, 1), dtype=wl.dtype, device=dev)
@@ -580,6 +591,10 @@ def gather_tables(model):
     ctx = model._dist
     sh = ctx.sharded
     out = {}
+    total_bytes = sum(sh.rows) * (sh.D + 1) * 4
+    if getattr(ctx, "deferred", False) and total_bytes > (8 << 30):
+        raise RuntimeError("state_dict(): the tables of this model (%.1f GB) were built sharded (deferred_tables) and are not re-assembled "
+                           "on one device; use deepctr.distributed.sharded_state_dict(model) (per-rank shards)" % (total_bytes / 1e9))
     emb_names = list(model.embedding_dict.keys())
     lin_names = list(model.linear_model.embedding_dict.keys())
     for t, V in enumerate(sh.rows):
@@ -620,3 +635,19 @@ def scatter_tables(model, state):
                 buf[a:a + k].copy_(take_shard(full, ctx.rank, ctx.world).to(sh.device, torch.float32).reshape(k, buf.shape[1]))
                 used.append(key)
     return used
+
+
+def sharded_state_dict(model):
+    """Per-rank checkpoint of a distributed model whose tables are too large to re-assemble: dense parameters (identical on every
+    rank) + this rank's shard buffers and the routing needed to interpret them (row r of table t = shard[base[t] + r // world] on
+    rank r % world).  Collective only through the flush of the lazy table semantics."""
+    ctx = model._dist
+    sh = ctx.sharded
+    opt = getattr(model, "optim", None)
+    if opt is not None and hasattr(opt, "flush"):
+        opt.flush()
+    table_keys = set("embedding_dict.%s.weight" % n for n in model.embedding_dict.keys()) | \
+        set("linear_model.embedding_dict.%s.weight" % n for n in model.linear_model.embedding_dict.keys())
+    dense = {k: v for k, v in torch.nn.Module.state_dict(model).items() if k not in table_keys}
+    return {"dense": dense, "rank": ctx.rank, "world": ctx.world, "rows": list(sh.rows), "base": list(sh.base[ctx.rank]),
+            "emb_shard": sh.emb.detach().clone(), "lin_shard": sh.lin.detach().clone()}

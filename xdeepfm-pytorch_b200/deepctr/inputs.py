@@ -101,6 +101,29 @@ def varlen_columns(feature_columns):
     return [fc for fc in feature_columns if isinstance(fc, VarLenSparseFeat)] if feature_columns else []
 
 
+_DEFERRED_TABLES = [False]
+
+
+class deferred_tables:
+    """`with deferred_tables(): model = xDeepFM(...)` builds the model WITHOUT materialising its embedding tables (1-row placeholders
+    that remember their vocabulary size): for vocabularies that do not fit one GPU (BASELINE config 5: tables up to 50 M rows x 64).
+    `model.distribute()` then initialises every rank's row shard in place, N(0, init_std) like create_embedding_matrix."""
+
+    def __enter__(self):
+        self._prev = _DEFERRED_TABLES[0]
+        _DEFERRED_TABLES[0] = True
+        return self
+
+    def __exit__(self, *exc):
+        _DEFERRED_TABLES[0] = self._prev
+        return False
+
+
+def table_rows(emb):
+    """Rows of an embedding table module (the vocabulary size, also for deferred placeholders)."""
+    return int(getattr(emb, "deferred_rows", emb.weight.shape[0]))
+
+
 def create_embedding_matrix(feature_columns, init_std=0.0001, linear=False, sparse=False, device="cpu"):
     """nn.ModuleDict {embedding_name: nn.Embedding(vocab, D or 1)} initialised N(0, init_std)
     (reference: inputs.py:158-180).  The modules are parameter containers: the CUDA gather reads `.weight` directly."""
@@ -109,7 +132,13 @@ def create_embedding_matrix(feature_columns, init_std=0.0001, linear=False, spar
     tables = nn.ModuleDict()
     for fc in sparse_columns(feature_columns):
         if fc.embedding_name not in tables:
-            tables[fc.embedding_name] = nn.Embedding(fc.vocabulary_size, 1 if linear else fc.embedding_dim, sparse=sparse)
+            if _DEFERRED_TABLES[0]:
+                emb = nn.Embedding(1, 1 if linear else fc.embedding_dim, sparse=sparse)
+                emb.deferred_rows = int(fc.vocabulary_size)
+                emb.init_std = init_std
+                tables[fc.embedding_name] = emb
+            else:
+                tables[fc.embedding_name] = nn.Embedding(fc.vocabulary_size, 1 if linear else fc.embedding_dim, sparse=sparse)
     for emb in tables.values():
         nn.init.normal_(emb.weight, mean=0, std=init_std)
     return tables.to(device)

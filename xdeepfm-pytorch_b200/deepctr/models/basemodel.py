@@ -23,7 +23,7 @@ import torch.nn.functional as F
 from .. import ops
 from ..callbacks import CallbackList, History
 from ..inputs import (DenseFeat, SparseFeat, VarLenSparseFeat, build_input_features, create_embedding_matrix,
-                      dense_columns, sparse_columns, varlen_columns)
+                      dense_columns, sparse_columns, table_rows, varlen_columns)
 from ..layers import PredictionLayer
 from ..layers.utils import slice_arrays
 from ..optim import FusedOptimizer, TableSet
@@ -40,7 +40,7 @@ def _expand_cols(feature_index, columns):
 def _make_plan(columns, embedding_dict, width):
     names = list(embedding_dict.keys())
     table_of = [names.index(fc.embedding_name) for fc in columns]
-    rows = [embedding_dict[n].weight.shape[0] for n in names]
+    rows = [table_rows(embedding_dict[n]) for n in names]
     return ops.SparsePlan(table_of, rows, width)
 
 
@@ -168,6 +168,8 @@ class BaseModel(nn.Module):
     def embed(self, ids_all):
         """Fused multi-table gather -> [B, m, D] for the deep part's sparse features."""
         ids = self._select(ids_all, self._dnn_sparse_sel)
+        if self._dist is None and any(hasattr(e, "deferred_rows") for e in self.embedding_dict.values()):
+            raise RuntimeError("this model was built under deepctr.inputs.deferred_tables(): call model.distribute() first")
         if self._dist is not None:
             from ..distributed import ShardedGather
             sh = self._dist.sharded
