@@ -118,3 +118,27 @@ def test_autodis_is_refused_explicitly():
     spec, params, z = load_case("pro_small")
     with pytest.raises(NotImplementedError):
         build_product_model(spec, DEV, use_autodis=True)
+
+
+def test_pro_cuda_graph_replay_equals_eager_steps():
+    """The SFG step (decoder, per-field heads, masked losses) replayed from a CUDA graph leaves the same weights and losses."""
+    spec, params, z = load_case("pro_small")
+    X, y = torch.from_numpy(z["X"]), torch.from_numpy(z["y"])
+    batches = [(X[i * 10:(i + 1) * 10], y[i * 10:(i + 1) * 10]) for i in range(4)] * 2
+    out = []
+    for graph in (False, True):
+        model = build_product_model(spec, DEV)
+        model.load_state_dict(params, strict=True)
+        model.compile("adam", "binary_crossentropy")
+        model.use_cuda_graph = graph
+        model.train()
+        accum = torch.zeros(1, dtype=torch.float64, device=DEV)
+        for Xb, yb in batches:
+            ids, dense = model.split_input(Xb.to(DEV))
+            model.train_step(ids, dense, yb.to(DEV), accum)
+        assert bool(model._graphs) == graph
+        out.append(({k: v.detach().clone() for k, v in model.state_dict().items()}, accum.item(), model._sfg_accum.item()))
+    (sd_e, loss_e, sfg_e), (sd_g, loss_g, sfg_g) = out
+    for k in sd_e:
+        assert torch.equal(sd_e[k], sd_g[k]), k
+    assert abs(loss_e - loss_g) <= 1e-9 * abs(loss_e) and abs(sfg_e - sfg_g) <= 1e-9 * abs(sfg_e)

@@ -32,8 +32,9 @@ class BaseModelSFG(BaseModel):
             self.sfg_decoder = None
             self.sfg_loss_fn = None
         self._sfg_accum = None
-        # the SFG step (label-embedding index backward, per-field heads) is not validated under CUDA-graph capture yet: eager launches
-        self.use_cuda_graph = False
+        import os as _os
+        if _os.environ.get("XDFM_CUDA_GRAPH_SFG", "1") == "0":
+            self.use_cuda_graph = False
         self.to(device)
 
     # ---- SFG loss on the split (ids, dense) feed ------------------------------------------------------
@@ -104,7 +105,7 @@ class BaseModelSFG(BaseModel):
             roots.append(sfg)
             grads.append(torch.full_like(sfg, float(self.sfg_weight)))
         torch.autograd.backward(roots, grads)
-        opt.step(apply_l2=True)
+        self._optimizer_phases(opt)
         if pred_log is not None:
             pred_log[pred_off:pred_off + yv.shape[0]] = y_pred.detach().reshape(-1)
         return y_pred

@@ -24,7 +24,11 @@ class LabelAwareAttention(nn.Module):
     def forward(self, x, labels):
         if len(labels.shape) > 1:
             labels = labels.squeeze(-1)
-        label_emb = self.label_embedding.weight[labels.long()]
+        # 2-row lookup written as a blend (labels are 0/1): elementwise only, so the step stays CUDA-graph capturable and the
+        # backward is a plain reduction instead of index_put
+        w = self.label_embedding.weight
+        lab = labels.to(w.dtype).reshape(-1, 1)
+        label_emb = w[0].unsqueeze(0) + lab * (w[1] - w[0]).unsqueeze(0)
         combined = torch.cat([x, label_emb], dim=-1)
         h = ops.linear_act(combined, self.attention_net[0].weight, self.attention_net[0].bias, "relu", precision=self.precision)
         return ops.linear_act(h, self.attention_net[2].weight, self.attention_net[2].bias, "sigmoid", precision=self.precision)
