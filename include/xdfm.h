@@ -257,6 +257,20 @@ int xdfm_masked_ce(const float* logits, const int32_t* targets, int64_t target_s
 int xdfm_masked_mse(const float* pred, const float* target, const float* row_w, int64_t R, int nd, float* row_loss, float* dpred,
                     void* stream);
 
+/* ---- xDeepFM Pro: AutoDis soft-bucket encoder of the dense features (deepctr/xdeepfm_pro/autodis.py:63-69, 100-127):
+ * per dense feature f and sample b, with v = x[b, f]:
+ *   h = LeakyReLU_0.2(w1[f,:] * v + b1[f,:]);  score = W2[f] h + b2[f];  p = softmax(score / temp[f]);  out[b, f, :] = p @ meta[f]
+ * x [B, nd]; w1, b1, b2 [nd, nb]; W2 [nd, nb, nb]; meta [nd, nb, E]; temp [nd]; out [B, nd*E].
+ * bwd: dout [B, nd*E] -> gpack [nd, xdfm_autodis_param_count(nb, E)], per feature in the order meta | W2 | b2 | w1 | b1 | temp
+ * (deterministic two-stage reduction over the batch); workspace sized by xdfm_autodis_bwd_workspace_bytes. */
+int xdfm_autodis_fwd(const float* x, const float* w1, const float* b1, const float* W2, const float* b2, const float* meta,
+                     const float* temp, int64_t B, int nd, int nb, int E, float* out, void* stream);
+int64_t xdfm_autodis_param_count(int nb, int E);
+int64_t xdfm_autodis_bwd_workspace_bytes(int64_t B, int nd, int nb, int E);
+int xdfm_autodis_bwd(const float* x, const float* w1, const float* b1, const float* W2, const float* b2, const float* meta,
+                     const float* temp, const float* dout, int64_t B, int nd, int nb, int E, float* gpack, void* workspace,
+                     void* stream);
+
 /* ---- single-node multi-GPU: row-sharded tables over NVLink peer memory (no reference equivalent: the reference replicates whole
  * tables under nn.DataParallel, deepctr/models/basemodel.py:206-209, deepctr/inputs.py:167-180).
  * Global row r of a table lives on rank r % G at local row r / G; a rank keeps its shards of all tables of a set in ONE buffer

@@ -51,7 +51,8 @@ def build_reference_model(spec: ModelSpec, **extra):
         from deepctr.xdeepfm_pro import xDeepFMPro
         return xDeepFMPro(cols, cols, use_sfg=spec.use_sfg, sfg_weight=spec.sfg_weight, sfg_hidden_units=spec.sfg_hidden_units,
                           sfg_dropout=0.0, sfg_positive_only=spec.sfg_positive_only,
-                          sfg_use_label_attention=spec.sfg_use_label_attention, **common)
+                          sfg_use_label_attention=spec.sfg_use_label_attention, use_autodis=spec.use_autodis,
+                          autodis_buckets=spec.autodis_buckets, autodis_temperature=spec.autodis_temperature, **common)
     if spec.variant == "attn":
         return xDeepFMAttention(cols, cols, cin_num_heads=spec.num_heads, cin_use_layer_norm=spec.use_layer_norm,
                                 cin_use_residual=spec.use_residual, **common)
@@ -230,11 +231,26 @@ def main_pro():
              B=24, seed=22)
     pro_case("pro_small_nodense", small_spec(dense_names=[], embedding_dim=4, **pro), B=24, seed=23)
     fit_case("fit_pro_small_adam", small_spec(**pro), N=96, batch_size=32, epochs=2, optimizer="adam", seed=24, lr=1e-2)
+    main_autodis()
+
+
+def main_autodis():
+    """xDeepFM Pro with the AutoDis dense-feature encoder (`python -m oracle.make_golden autodis` regenerates only these)."""
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(4)
+    pro = dict(variant="pro", sfg_hidden_units=(16, 8), use_autodis=True)
+    pro_case("pro_autodis_small", small_spec(autodis_buckets=16, **pro), B=40, seed=31)
+    pro_case("pro_autodis_b5_nosfg", small_spec(autodis_buckets=5, autodis_temperature=0.5, use_sfg=False, embedding_dim=4, **pro),
+             B=150, seed=32)
+    fit_case("fit_pro_autodis_adam", small_spec(autodis_buckets=8, **pro), N=96, batch_size=32, epochs=2, optimizer="adam", seed=33,
+             lr=1e-2)
 
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "pro":
         main_pro()
+    elif len(sys.argv) > 1 and sys.argv[1] == "autodis":
+        main_autodis()
     else:
         main()
         main_pro()

@@ -17,6 +17,7 @@ What it restates (reference = Syclus123/xDeepFM-pytorch, vendored DeepCTR-Torch 
   reg_loss               deepctr/models/basemodel.py:412-428 (+ group registration :126-127, xdeepfm.py:57-60, 74-75)
   train_loss             deepctr/models/basemodel.py:254-257  (BCE on probabilities, reduction='sum')
   sfg_loss               deepctr/xdeepfm_pro/sfg_decoder.py:116-157, 198-204, 266-309; basemodel_sfg.py:420-476
+  autodis_forward        deepctr/xdeepfm_pro/autodis.py:63-69, 100-127; xdeepfm_pro.py:130-153, 233-240
 
 All arithmetic on this path lives in the third-party dependency torch (pinned torch==2.6.0 in the
 reference's requirements.txt:60; this image has 2.11.0): the restatement is written with plain torch
@@ -67,6 +68,10 @@ class ModelSpec:
     sfg_hidden_units: Tuple[int, ...] = (128, 64)
     sfg_positive_only: bool = True
     sfg_use_label_attention: bool = True
+    # AutoDis encoder of the dense features for the DNN branch (xdeepfm_pro.py:82-86, 130-153)
+    use_autodis: bool = False
+    autodis_buckets: int = 16
+    autodis_temperature: float = 1.0
     # column order of the flat input matrix X: feature_index order (inputs.py:99-123).  The scripts
     # build sparse columns first, then dense (xdftrain.py:240-256).
     sparse_first: bool = True
@@ -249,6 +254,24 @@ def cin_attention_tail(params, spec: ModelSpec, maps):
                           params["cin.attn_pooling.attention.2.weight"])
 
 
+def autodis_forward(params, spec: ModelSpec, dense):
+    """AutoDis (autodis.py:100-127): per dense feature Linear(1,nb) -> LeakyReLU(0.2) -> Linear(nb,nb), softmax(scores / temp_f),
+    weighted sum of the feature's meta-embeddings; features concatenated -> [B, nd * D]."""
+    P = "autodis_encoder.autodis."
+    outs = []
+    for f in range(spec.nd):
+        v = dense[:, f:f + 1]
+        h = F.leaky_relu(v.matmul(params[P + "bucket_projectors.%d.0.weight" % f].t()) + params[P + "bucket_projectors.%d.0.bias" % f], 0.2)
+        scores = h.matmul(params[P + "bucket_projectors.%d.2.weight" % f].t()) + params[P + "bucket_projectors.%d.2.bias" % f]
+        w = torch.softmax(scores / params[P + "feature_temperatures"][f], dim=-1)
+        outs.append(w.matmul(params[P + "meta_embeddings"][f]))
+    return torch.cat(outs, dim=-1)
+
+
+def _uses_autodis(spec: ModelSpec):
+    return spec.variant == "pro" and spec.use_autodis and spec.nd > 0
+
+
 def cin_params(params, spec: ModelSpec):
     n = len(spec.cin_layer_size)
     return ([params["cin.conv1ds.%d.weight" % k] for k in range(n)],
@@ -282,7 +305,8 @@ def xdeepfm_logit(params, spec: ModelSpec, X, return_parts=False):
         parts["cin_out"], parts["cin_logit"] = cin_out, cin_logit
         logit = logit + cin_logit
     if len(spec.dnn_hidden_units) > 0:
-        dnn_in = torch.cat([emb.reshape(emb.shape[0], -1), dense], dim=-1) if spec.nd > 0 else emb.reshape(emb.shape[0], -1)
+        dnn_dense = autodis_forward(params, spec, dense) if _uses_autodis(spec) else dense      # xdeepfm_pro.py:233-242
+        dnn_in = torch.cat([emb.reshape(emb.shape[0], -1), dnn_dense], dim=-1) if spec.nd > 0 else emb.reshape(emb.shape[0], -1)
         Ws, bs = dnn_params(params, spec)
         dnn_out = dnn_forward(dnn_in, Ws, bs, spec.dnn_activation)
         dnn_logit = dnn_out.matmul(params["dnn_linear.weight"].t())
@@ -404,7 +428,7 @@ def param_shapes(spec: ModelSpec):
         shapes["linear_model.embedding_dict.%s.weight" % name] = (V, 1)
     shapes["out.bias"] = (1,)
     if len(spec.dnn_hidden_units) > 0:
-        dims = [m * D + nd] + list(spec.dnn_hidden_units)
+        dims = [m * D + (nd * D if _uses_autodis(spec) else nd)] + list(spec.dnn_hidden_units)
         for i in range(len(dims) - 1):
             shapes["dnn.linears.%d.weight" % i] = (dims[i + 1], dims[i])
             shapes["dnn.linears.%d.bias" % i] = (dims[i + 1],)
@@ -458,6 +482,17 @@ def param_shapes(spec: ModelSpec):
             shapes["sfg_decoder.label_attention.attention_net.0.bias"] = (h0,)
             shapes["sfg_decoder.label_attention.attention_net.2.weight"] = (d_in, h0)
             shapes["sfg_decoder.label_attention.attention_net.2.bias"] = (d_in,)
+    if _uses_autodis(spec):
+        # autodis.py:56-74 (appended last so that the seeded values of every other fixture stay what they were)
+        nb = spec.autodis_buckets
+        P = "autodis_encoder.autodis."
+        shapes[P + "meta_embeddings"] = (nd, nb, D)
+        for f in range(nd):
+            shapes[P + "bucket_projectors.%d.0.weight" % f] = (nb, 1)
+            shapes[P + "bucket_projectors.%d.0.bias" % f] = (nb,)
+            shapes[P + "bucket_projectors.%d.2.weight" % f] = (nb, nb)
+            shapes[P + "bucket_projectors.%d.2.bias" % f] = (nb,)
+        shapes[P + "feature_temperatures"] = (nd,)
     return shapes
 
 
@@ -477,6 +512,11 @@ def make_params(spec: ModelSpec, seed=0, scale=None, dtype=torch.float32):
         elif "layer_norm" in k and k.endswith("weight"):
             out[k] = (1.0 + 0.1 * torch.randn(shp, generator=g)).to(dtype)
             continue
+        elif k.endswith("feature_temperatures"):
+            out[k] = (0.6 + 0.8 * torch.rand(shp, generator=g)).to(dtype)       # positive, per-feature distinct
+            continue
+        elif k.endswith("meta_embeddings"):
+            std = 0.5
         else:
             std = 1.0 / math.sqrt(max(fan_in, 1))
         if scale is not None and k in scale:

@@ -11,7 +11,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 FWD_BWD_CASES = ["xdeepfm_small", "xdeepfm_small_nosplit", "xdeepfm_small_linearact", "xdeepfm_small_nodense",
                  "xdeepfm_small_zipf", "attn_small", "attn_small_3heads", "attn_v2_small", "xdeepfm_cfg1"]
-PRO_CASES = ["pro_small", "pro_small_allrows_noattn", "pro_small_nodense"]
+PRO_CASES = ["pro_small", "pro_small_allrows_noattn", "pro_small_nodense", "pro_autodis_small", "pro_autodis_b5_nosfg"]
 FIT_CASES = ["fit_small_adam", "fit_small_sgd", "fit_small_adagrad", "fit_small_rmsprop"]
 
 
@@ -55,7 +55,8 @@ def build_product_model(spec, device="cuda:0", **extra):
     if spec.variant == "pro":
         from deepctr.xdeepfm_pro import xDeepFMPro
         kw = dict(use_sfg=spec.use_sfg, sfg_weight=spec.sfg_weight, sfg_hidden_units=spec.sfg_hidden_units, sfg_dropout=0.0,
-                  sfg_positive_only=spec.sfg_positive_only, sfg_use_label_attention=spec.sfg_use_label_attention)
+                  sfg_positive_only=spec.sfg_positive_only, sfg_use_label_attention=spec.sfg_use_label_attention,
+                  use_autodis=spec.use_autodis, autodis_buckets=spec.autodis_buckets, autodis_temperature=spec.autodis_temperature)
         kw.update(common)
         return xDeepFMPro(cols, cols, **kw)
     if spec.variant == "attn":

@@ -41,11 +41,12 @@ def test_constructor_signatures_match_the_reference():
     assert inspect.signature(xDeepFMProLight.__init__).parameters["sfg_weight"].default == 0.05
 
 
-@pytest.mark.parametrize("variant", ["xdeepfm", "attn", "attn_v2", "pro"])
+@pytest.mark.parametrize("variant", ["xdeepfm", "attn", "attn_v2", "pro", "pro+autodis"])
 def test_state_dict_keys_and_shapes_match_the_reference_layout(variant):
+    autodis = variant.endswith("+autodis")
     spec = O.ModelSpec(sparse_names=["C1", "C2", "C3"], vocab_sizes=[11, 5, 40], embedding_dim=8, dense_names=["I1", "I2"],
-                       cin_layer_size=(8, 4), dnn_hidden_units=(8, 6), variant=variant, num_heads=2, num_attn_layers=2,
-                       sfg_hidden_units=(8, 4))
+                       cin_layer_size=(8, 4), dnn_hidden_units=(8, 6), variant=variant.split("+")[0], num_heads=2, num_attn_layers=2,
+                       sfg_hidden_units=(8, 4), use_autodis=autodis, autodis_buckets=6)
     model = build_product_model(spec, "cpu")
     want = O.param_shapes(spec)                                   # SURVEY.md 8a-K, probed on the reference
     got = {k: tuple(v.shape) for k, v in model.state_dict().items()}

@@ -82,6 +82,10 @@ _SIGS = {
     "xdfm_add_ln_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P]),
     "xdfm_attn_pool_fwd": (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P, _P]),
     "xdfm_attn_pool_bwd": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, _P, _P]),
+    "xdfm_autodis_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P]),
+    "xdfm_autodis_param_count": (c_int64, [c_int, c_int]),
+    "xdfm_autodis_bwd_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int]),
+    "xdfm_autodis_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P]),
     "xdfm_sfg_row_weights": (c_int, [_P, c_int64, c_int, _P, _P]),
     "xdfm_masked_ce": (c_int, [_P, _P, c_int64, _P, c_int64, c_int, _P, _P, _P]),
     "xdfm_masked_mse": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P, _P]),

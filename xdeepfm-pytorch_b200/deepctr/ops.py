@@ -804,6 +804,62 @@ class MaskedMSE(torch.autograd.Function):
         return dpred * g.reshape(1, 1), None, None
 
 
+# ------------------------------------------------------------------------------------------------
+# xDeepFM Pro: AutoDis dense-feature encoder (deepctr/xdeepfm_pro/autodis.py:100-127)
+# ------------------------------------------------------------------------------------------------
+class AutoDis(torch.autograd.Function):
+    """out [B, nd*E]: per feature Linear(1,nb) -> LeakyReLU(0.2) -> Linear(nb,nb) -> softmax(. / temp) @ meta[f], one launch.
+
+    Inputs: x [B, nd], meta [nd, nb, E], temp [nd], then the reference's per-feature projector tensors in module order
+    (w1_f [nb,1], b1_f [nb], W2_f [nb,nb], b2_f [nb]) * nd.  They are packed per call (4 small stacks); the backward returns views
+    of one packed gradient buffer, no gradient w.r.t. x (dense inputs are data)."""
+
+    @staticmethod
+    def forward(ctx, x, meta, temp, *proj):
+        require_cuda(x, "AutoDis")
+        x = _f32c(x)
+        B, nd = x.shape
+        _, nb, E = meta.shape
+        if len(proj) != 4 * nd:
+            raise ValueError("AutoDis: expected %d projector tensors, got %d" % (4 * nd, len(proj)))
+        w1 = torch.stack([proj[4 * f].reshape(nb) for f in range(nd)])
+        b1 = torch.stack([proj[4 * f + 1] for f in range(nd)])
+        W2 = torch.stack([proj[4 * f + 2] for f in range(nd)])
+        b2 = torch.stack([proj[4 * f + 3] for f in range(nd)])
+        meta_c, temp_c = _f32c(meta), _f32c(temp)
+        out = torch.empty((B, nd * E), dtype=torch.float32, device=x.device)
+        with timed("autodis"):
+            N.check(N.lib().xdfm_autodis_fwd(N.ptr(x), N.ptr(w1), N.ptr(b1), N.ptr(W2), N.ptr(b2), N.ptr(meta_c), N.ptr(temp_c), B, nd, nb,
+                                             E, N.ptr(out), N.stream_ptr()))
+        ctx.save_for_backward(x, w1, b1, W2, b2, meta_c, temp_c)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w1, b1, W2, b2, meta, temp = ctx.saved_tensors
+        B, nd = x.shape
+        _, nb, E = meta.shape
+        L = N.lib()
+        n_par = L.xdfm_autodis_param_count(nb, E)
+        gpack = torch.empty((nd, n_par), dtype=torch.float32, device=x.device)
+        ws = workspace("autodis_bwd", L.xdfm_autodis_bwd_workspace_bytes(B, nd, nb, E), x.device)
+        dout = _f32c(dout)
+        with timed("autodis"):
+            N.check(L.xdfm_autodis_bwd(N.ptr(x), N.ptr(w1), N.ptr(b1), N.ptr(W2), N.ptr(b2), N.ptr(meta), N.ptr(temp), N.ptr(dout), B, nd,
+                                       nb, E, N.ptr(gpack), N.ptr(ws), N.stream_ptr()))
+        o = 0
+        g_meta = gpack[:, o:o + nb * E].reshape(nd, nb, E); o += nb * E
+        g_W2 = gpack[:, o:o + nb * nb]; o += nb * nb
+        g_b2 = gpack[:, o:o + nb]; o += nb
+        g_w1 = gpack[:, o:o + nb]; o += nb
+        g_b1 = gpack[:, o:o + nb]; o += nb
+        g_temp = gpack[:, o]
+        grads = []
+        for f in range(nd):
+            grads += [g_w1[f].reshape(nb, 1), g_b1[f], g_W2[f].reshape(nb, nb), g_b2[f]]
+        return (None, g_meta, g_temp) + tuple(grads)
+
+
 def ctypes_ptr_offset_any(t):
     """Device pointer of a (possibly row-strided) CUDA tensor."""
     import ctypes

@@ -23,12 +23,23 @@ class xDeepFMPro(BaseModelSFG):
         self.dnn_hidden_units = dnn_hidden_units
         self.use_dnn = len(dnn_feature_columns) > 0 and len(dnn_hidden_units) > 0
         self.use_autodis = use_autodis
+        # AutoDis encoder of the dense features for the DNN branch (xdeepfm_pro.py:130-143); built before the DNN like the reference
         if use_autodis and len(self.dense_feature_columns) > 0:
             from .autodis import DenseFeatureEncoder
-            DenseFeatureEncoder()          # raises: AutoDis is a "next" item of the hot-path scope
-        self.autodis_encoder = None
+            if any(fc.dimension != 1 for fc in self.dense_feature_columns):
+                raise ValueError("use_autodis=True needs DenseFeat(dimension=1) columns (the reference's Linear(1, buckets) projectors)")
+            self.autodis_encoder = DenseFeatureEncoder(dense_feature_names=[fc.name for fc in self.dense_feature_columns],
+                                                       embedding_dim=self.embedding_dim, use_autodis=True, num_buckets=autodis_buckets,
+                                                       temperature=autodis_temperature, device=device)
+            autodis_output_dim = self.autodis_encoder.get_output_dim()
+        else:
+            self.autodis_encoder = None
+            autodis_output_dim = 0
         if self.use_dnn:
-            self.dnn = DNN(self.compute_input_dim(dnn_feature_columns), dnn_hidden_units, activation=dnn_activation,
+            dnn_input_dim = self.compute_input_dim(dnn_feature_columns)
+            if self.autodis_encoder is not None:       # raw dense columns are replaced by their AutoDis embeddings (xdeepfm_pro.py:150-153)
+                dnn_input_dim += autodis_output_dim - sum(fc.dimension for fc in self.dense_feature_columns)
+            self.dnn = DNN(dnn_input_dim, dnn_hidden_units, activation=dnn_activation,
                            l2_reg=l2_reg_dnn, dropout_rate=dnn_dropout, use_bn=dnn_use_bn, init_std=init_std, device=device)
             self.dnn_linear = nn.Linear(dnn_hidden_units[-1], 1, bias=False).to(device)
             self.add_regularization_weight(
@@ -62,6 +73,8 @@ class xDeepFMPro(BaseModelSFG):
                 parts.append(emb.reshape(emb.shape[0], -1))
             dd = self.dnn_dense(dense)
             if dd.shape[1] > 0:
+                if self.autodis_encoder is not None:   # xdeepfm_pro.py:233-240
+                    dd = self.autodis_encoder(dd)[0]
                 parts.append(dd)
             dnn_in = parts[0] if len(parts) == 1 else torch.cat(parts, dim=-1)
             dnn_out, w_dnn = self.dnn(dnn_in), self.dnn_linear.weight
