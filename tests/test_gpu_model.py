@@ -169,3 +169,43 @@ def test_fit_verbose_metrics_on_the_fused_graph_path():
     assert np.allclose(hists[0]["loss"], hists[1]["loss"], rtol=1e-6)
     assert set(hists[1]) >= {"loss", "binary_crossentropy", "auc", "val_binary_crossentropy", "val_auc"}
     assert all(0.0 <= v <= 1.0 for v in hists[1]["auc"])
+
+
+def test_failed_graph_capture_falls_back_to_eager_launches_and_leaves_the_rng_usable():
+    """A step that cannot be captured (here: a stream synchronisation injected into the capture) must not poison the process:
+    training continues on eager launches with the same results and torch's CUDA generator keeps working (a capture that dies in
+    capture_end() otherwise leaves it flagged as capturing and every later randn / model construction raises)."""
+    import warnings
+    spec, params, z = load_case("xdeepfm_small_zipf")
+    X, y = torch.from_numpy(z["X"]), torch.from_numpy(z["y"])
+    batches = [(X[i * 16:(i + 1) * 16], y[i * 16:(i + 1) * 16]) for i in range(4)]
+    out = []
+    for sabotage in (False, True):
+        model = build_product_model(spec, DEV)
+        model.load_state_dict(params, strict=True)
+        model.compile("adam", "binary_crossentropy")
+        model.use_cuda_graph = sabotage
+        if sabotage:
+            orig = model._train_step_eager
+
+            def bad(*a, _orig=orig, _m=model, **k):
+                if _m._capturing:
+                    torch.cuda.current_stream().synchronize()          # illegal while capturing
+                return _orig(*a, **k)
+            model._train_step_eager = bad
+        model.train()
+        accum = torch.zeros(1, dtype=torch.float64, device=DEV)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for Xb, yb in batches:
+                ids, dense = model.split_input(Xb.to(DEV))
+                model.train_step(ids, dense, yb.to(DEV), accum)
+        if sabotage:
+            assert model._graph_failed and not model._graphs
+        out.append(({k: v.detach().clone() for k, v in model.state_dict().items()}, accum.item()))
+        assert torch.isfinite(torch.randn(8, device=DEV)).all()          # generator usable after the failed capture
+    (sd_a, loss_a), (sd_b, loss_b) = out
+    for k in sd_a:
+        assert torch.equal(sd_a[k], sd_b[k]), k
+    assert abs(loss_a - loss_b) <= 1e-9 * abs(loss_a)
+    build_product_model(spec, DEV)                                       # model construction (nn.init on cuda) still works

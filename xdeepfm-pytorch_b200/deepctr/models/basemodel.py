@@ -16,6 +16,8 @@ from __future__ import print_function
 import time
 
 import numpy as np
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -548,6 +550,9 @@ class BaseModel(nn.Module):
                 st = self._capture_step(ids, dense, y)
             except Exception as e:           # pragma: no cover - depends on driver / torch build
                 import warnings
+                self._recover_after_failed_capture(ids.device)
+                if os.environ.get("XDFM_GRAPH_DEBUG"):
+                    raise
                 warnings.warn("CUDA-graph capture of the training step failed (%s); staying on eager launches" % (e,))
                 self._graph_failed = True
                 return None
@@ -571,6 +576,21 @@ class BaseModel(nn.Module):
         if pred_log is not None:
             pred_log[pred_off:pred_off + ids.shape[0]] = st["y_pred"].detach().reshape(-1)
         return st["y_pred"]
+
+    @staticmethod
+    def _recover_after_failed_capture(device):
+        """A capture that dies in capture_end() leaves torch's CUDA generator flagged as 'capturing' (every later randn / dropout on
+        the device raises 'Offset increment outside graph capture').  A trivial successful capture runs the generator's capture
+        prologue / epilogue pair again and clears the flag."""
+        try:
+            torch.cuda.synchronize(device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                torch.zeros(1, device=device)
+            del g
+            torch.cuda.synchronize(device)
+        except Exception:                    # pragma: no cover
+            pass
 
     def _capture_step(self, ids, dense, y):
         opt = self.optim
@@ -639,8 +659,9 @@ class BaseModel(nn.Module):
             loss_accum += loss.detach().double()
             loss.backward()
         self._optimizer_phases(opt)
+        y_pred = y_pred.detach()             # the caller must not keep the step's autograd graph alive (see BaseModelSFG)
         if pred_log is not None:
-            pred_log[pred_off:pred_off + yv.shape[0]] = y_pred.detach().reshape(-1)
+            pred_log[pred_off:pred_off + yv.shape[0]] = y_pred.reshape(-1)
         return y_pred
 
     def _epoch_begin(self):

@@ -78,6 +78,7 @@ class BaseModelSFG(BaseModel):
         if self.use_sfg and y is not None and self.training:
             loss = self.sfg_loss_ids(ids, dense, self._last_emb, y.to(self.device))
             info = {'sfg_loss': loss, 'sfg_loss_dict': {'sfg_total': loss.detach()}}
+        self._last_emb = None
         return y_pred, info
 
     def forward(self, X):
@@ -105,9 +106,15 @@ class BaseModelSFG(BaseModel):
             roots.append(sfg)
             grads.append(torch.full_like(sfg, float(self.sfg_weight)))
         torch.autograd.backward(roots, grads)
+        # nothing may keep this step's autograd graph alive: a surviving graph pins its AccumulateGrad nodes (bound to the stream
+        # they were created on), the next step would reuse them, and under CUDA-graph capture (side stream) autograd would then
+        # synchronise with the uncaptured default stream -> cudaErrorStreamCaptureIsolation
+        self._last_emb = None
+        del roots, grads
         self._optimizer_phases(opt)
+        y_pred = y_pred.detach()
         if pred_log is not None:
-            pred_log[pred_off:pred_off + yv.shape[0]] = y_pred.detach().reshape(-1)
+            pred_log[pred_off:pred_off + yv.shape[0]] = y_pred.reshape(-1)
         return y_pred
 
     def _epoch_begin(self):
