@@ -247,6 +247,21 @@ int xdfm_attn_pool_fwd(const float* score, const float* x, int64_t B, int L, int
 int xdfm_attn_pool_bwd(const float* dout, const float* attn, const float* x, int64_t B, int L, int E, float* dscore, float* dx,
                        void* stream);
 
+/* ---- narrow dense layers over very tall activations (K, N <= 32; up to three weight matrices sharing the input): the bias-free
+ * E x E projections W_q / W_k / W_v / W_o of MultiHeadSelfAttention (deepctr/layers/cin_attention.py:49-61, 73-79, 95) and the
+ * Linear(E,E)-Tanh-Linear(E,1) score MLP of AttentionPooling (cin_attention.py:114-118, 135-136), plus their autograd.
+ * fwd:    y_q[R, N] = act(x[R, K] . w_q[N, K]^T + bias), q < nout (bias only with nout == 1; unused w / y pointers NULL).
+ * bwd_dx: dx[R, K] = sum_q dy_q[R, N] . w_q[N, K].
+ * bwd_dw: dw_q[N, K] = dy_q^T . x, db[N] = column sums of dy_0 (db may be NULL); deterministic two-stage reduction, workspace
+ *         sized by xdfm_small_linear_bwd_dw_workspace_bytes (-1 = unsupported shape). */
+int xdfm_small_linear_fwd(const float* x, const float* w0, const float* w1, const float* w2, const float* bias, int act, int64_t R,
+                          int K, int N, int nout, float* y0, float* y1, float* y2, void* stream);
+int xdfm_small_linear_bwd_dx(const float* dy0, const float* dy1, const float* dy2, const float* w0, const float* w1, const float* w2,
+                             int64_t R, int K, int N, int nout, float* dx, void* stream);
+int64_t xdfm_small_linear_bwd_dw_workspace_bytes(int64_t R, int K, int N, int nout);
+int xdfm_small_linear_bwd_dw(const float* x, const float* dy0, const float* dy1, const float* dy2, int64_t R, int K, int N, int nout,
+                             float* dw0, float* dw1, float* dw2, float* db, void* workspace, void* stream);
+
 /* ---- xDeepFM Pro: Supervised-Feature-Generation loss (deepctr/xdeepfm_pro/sfg_decoder.py:266-309).
  * row_w[b] = mask_b / num (mask = label == 1, num = sum(mask) + 1e-8 when positive_only; else 1 / B);
  * masked_ce:  row_loss[r] = row_w[r] * CE(logits[r, :V], targets[r * target_stride]), dlogits = d(sum row_loss)/d logits;

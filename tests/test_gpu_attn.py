@@ -114,3 +114,71 @@ def test_cin_attention_tail_matches_oracle(variant, heads, layers, ln, res):
     _close(xg.grad, xd.grad, "d x0", 3e-3)
     for name, p in mod.named_parameters():
         _close(p.grad, pd["cin." + name].grad, "grad " + name, 3e-3)
+
+
+@pytest.mark.parametrize("R,K,N,nq,act,bias", [
+    (4096 + 37, 16, 16, 3, None, False),      # the Q/K/V projections of BASELINE config 3 (E = 16), ragged last tile
+    (1000, 16, 16, 1, "tanh", True),          # attention-pooling hidden layer
+    (777, 16, 1, 1, None, False),             # attention-pooling score layer (N = 1)
+    (300, 10, 10, 3, None, False),            # E = 10 (script default): not a multiple of 4 -> scalar load / store paths
+    (129, 32, 32, 3, None, False), (5, 8, 6, 2, "relu", False), (1, 3, 5, 1, "sigmoid", True), (0, 16, 16, 3, None, False),
+    (70000, 8, 8, 1, None, True)])
+def test_small_linear_matches_torch(R, K, N, nq, act, bias):
+    """Narrow-layer kernels (csrc/smalllin.cu) against fp64 torch: y, dx, every dW, db at 2e-5 of each tensor's scale; the
+    two-stage reductions are bit-reproducible."""
+    g = torch.Generator().manual_seed(R + K * 7 + N)
+    x = torch.randn(R, K, generator=g)
+    Ws = [torch.randn(N, K, generator=g) / math.sqrt(K) for _ in range(nq)]
+    b = 0.3 * torch.randn(N, generator=g) if bias else None
+    dys = [torch.randn(R, N, generator=g) for _ in range(nq)]
+    fn = {None: lambda t: t, "tanh": torch.tanh, "relu": torch.relu, "sigmoid": torch.sigmoid}[act]
+    xd = x.double().requires_grad_(True)
+    Wd = [W.double().requires_grad_(True) for W in Ws]
+    bd = b.double().requires_grad_(True) if bias else None
+    refs = [fn(xd @ W.t() + (bd if bias else 0.0)) for W in Wd]
+    torch.autograd.backward(refs, [d.double() for d in dys])
+
+    def run():
+        xg = x.to(DEV).requires_grad_(True)
+        Wg = [W.to(DEV).requires_grad_(True) for W in Ws]
+        bg = b.to(DEV).requires_grad_(True) if bias else None
+        from deepctr import _native as Nv
+        out = ops.SmallLinear.apply(xg, bg, Nv.ACT[act], *Wg)
+        outs = list(out) if nq > 1 else [out]
+        torch.autograd.backward(outs, [d.to(DEV) for d in dys])
+        return outs, xg.grad, [W.grad for W in Wg], (bg.grad if bias else None)
+
+    outs, dx, dWs, db = run()
+    for q in range(nq):
+        assert outs[q].shape == (R, N)
+        if R == 0:
+            assert float(dWs[q].abs().sum()) == 0.0
+            continue
+        _close(outs[q], refs[q].detach(), "y%d" % q)
+        _close(dWs[q], Wd[q].grad, "dW%d" % q)
+    if R == 0:
+        return
+    _close(dx, xd.grad, "dx")
+    if bias:
+        _close(db, bd.grad, "db")
+    outs2, dx2, dWs2, db2 = run()
+    assert all(torch.equal(a, b_) for a, b_ in zip(dWs, dWs2)) and torch.equal(dx, dx2)
+    if bias:
+        assert torch.equal(db, db2)
+
+
+def test_small_linear_partial_outputs_and_limits():
+    """Unused outputs of the fused Q/K/V pass get zero gradients; layers wider than 32 are refused by the C ABI (linear_act routes
+    them to the GEMM kernels)."""
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(50, 16, generator=g).to(DEV).requires_grad_(True)
+    Ws = [torch.randn(16, 16, generator=g).to(DEV).requires_grad_(True) for _ in range(3)]
+    q, k, v = ops.linear_multi(x, Ws)
+    (q.sum() + 2 * v.sum()).backward()
+    assert float(Ws[1].grad.abs().sum()) == 0.0 and float(Ws[0].grad.abs().sum()) > 0
+    _close(Ws[2].grad, 2 * x.detach().sum(0, keepdim=True).expand(16, 16), "dWv")
+    wide = torch.randn(48, 16, generator=g).to(DEV)
+    with pytest.raises(RuntimeError):
+        ops.SmallLinear.apply(x.detach(), None, 0, wide)
+    y = ops.linear_act(x.detach(), wide)                       # falls through to the SGEMM path
+    _close(y, x.detach().double().cpu() @ wide.double().cpu().t(), "wide layer")

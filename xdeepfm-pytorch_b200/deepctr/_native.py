@@ -82,6 +82,10 @@ _SIGS = {
     "xdfm_add_ln_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P]),
     "xdfm_attn_pool_fwd": (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P, _P]),
     "xdfm_attn_pool_bwd": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, _P, _P]),
+    "xdfm_small_linear_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "xdfm_small_linear_bwd_dx": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P]),
+    "xdfm_small_linear_bwd_dw_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int]),
+    "xdfm_small_linear_bwd_dw": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "xdfm_autodis_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P]),
     "xdfm_autodis_param_count": (c_int64, [c_int, c_int]),
     "xdfm_autodis_bwd_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int]),

@@ -48,9 +48,7 @@ class MultiHeadSelfAttention(nn.Module):
         if self.dropout_rate > 0 and self.training:
             raise NotImplementedError("attention dropout > 0 is not fused (the probabilities never leave the SM); the reference "
                                       "default and its run scripts use 0.0")
-        q = ops.linear_act(x, self.W_q.weight, precision=self.precision)
-        k = ops.linear_act(x, self.W_k.weight, precision=self.precision)
-        v = ops.linear_act(x, self.W_v.weight, precision=self.precision)
+        q, k, v = ops.linear_multi(x, [self.W_q.weight, self.W_k.weight, self.W_v.weight], precision=self.precision)
         o = ops.MHSACore.apply(q, k, v, self.num_heads)
         return ops.linear_act(o, self.W_o.weight, precision=self.precision)
 

@@ -61,6 +61,12 @@ def _f32c(t):
     return t.contiguous()
 
 
+def _f32a(t):
+    """contiguous fp32 at a 16-byte aligned address (128-bit loads): a view at an odd storage offset is copied."""
+    t = _f32c(t)
+    return t if t.data_ptr() % 16 == 0 else t.clone()
+
+
 def require_cuda(t, what):
     if not t.is_cuda:
         raise RuntimeError("%s: the xdeepfm-b200 path runs on CUDA (sm_100a) only; got a %s tensor. "
@@ -564,8 +570,86 @@ class LinearActTC(torch.autograd.Function):
         return dx, dW, db, None
 
 
+SMALL_LINEAR_MAX = 32
+
+
+class SmallLinear(torch.autograd.Function):
+    """(y_0, ..) = act(x @ W_q.T + b) for up to three [N, K] weights sharing x, K, N <= 32 (csrc/smalllin.cu): the attention
+    block's projections over B*L rows are HBM streaming, not GEMMs -- one pass over x yields Q, K and V; exact fp32."""
+
+    @staticmethod
+    def forward(ctx, x, b, act, *Ws):
+        require_cuda(x, "SmallLinear")
+        shp = x.shape
+        x2 = _f32a(x).reshape(-1, shp[-1])
+        Ws = [_f32c(W) for W in Ws]
+        R, K = x2.shape
+        Nn, nq = Ws[0].shape[0], len(Ws)
+        ys = [torch.empty((R, Nn), dtype=torch.float32, device=x.device) for _ in range(nq)]
+        wp = [N.ptr(W) for W in Ws] + [None] * (3 - nq)
+        yp = [N.ptr(y) for y in ys] + [None] * (3 - nq)
+        bias = None if b is None else _f32c(b)
+        with timed("small_linear"):
+            N.check(N.lib().xdfm_small_linear_fwd(N.ptr(x2), wp[0], wp[1], wp[2], N.ptr(bias), act, R, K, Nn, nq, yp[0], yp[1], yp[2],
+                                                  N.stream_ptr()))
+        ctx.save_for_backward(x2, *Ws, *(ys if act != 0 else []))
+        ctx.act, ctx.has_bias, ctx.shp, ctx.nq = act, b is not None, shp, nq
+        outs = tuple(y.view(*shp[:-1], Nn) for y in ys)
+        return outs if nq > 1 else outs[0]
+
+    @staticmethod
+    def backward(ctx, *dys):
+        saved = ctx.saved_tensors
+        nq = ctx.nq
+        x2, Ws = saved[0], saved[1:1 + nq]
+        ys = saved[1 + nq:]
+        R, K = x2.shape
+        Nn = Ws[0].shape[0]
+        L = N.lib()
+        dev = x2.device
+        dym = []
+        for q in range(nq):
+            dy = dys[q]
+            dy = torch.zeros((R, Nn), dtype=torch.float32, device=dev) if dy is None else _f32a(dy).reshape(R, Nn)
+            if ctx.act != 0:
+                t = torch.empty_like(dy)
+                N.check(L.xdfm_act_bwd(N.ptr(dy), N.ptr(ys[q]), N.ptr(t), dy.numel(), ctx.act, N.stream_ptr()))
+                dy = t
+            dym.append(dy)
+        dp = [N.ptr(d) for d in dym] + [None] * (3 - nq)
+        wp = [N.ptr(W) for W in Ws] + [None] * (3 - nq)
+        dx = None
+        with timed("small_linear"):
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty_like(x2)
+                N.check(L.xdfm_small_linear_bwd_dx(dp[0], dp[1], dp[2], wp[0], wp[1], wp[2], R, K, Nn, nq, N.ptr(dx), N.stream_ptr()))
+                dx = dx.view(ctx.shp)
+            dWs = [torch.empty_like(W) for W in Ws]
+            db = torch.empty(Nn, dtype=torch.float32, device=dev) if ctx.has_bias else None
+            ws = workspace("small_linear_dw", L.xdfm_small_linear_bwd_dw_workspace_bytes(R, K, Nn, nq), dev)
+            gp = [N.ptr(g) for g in dWs] + [None] * (3 - nq)
+            N.check(L.xdfm_small_linear_bwd_dw(N.ptr(x2), dp[0], dp[1], dp[2], R, K, Nn, nq, gp[0], gp[1], gp[2], N.ptr(db), N.ptr(ws),
+                                               N.stream_ptr()))
+        return (dx, db, None) + tuple(dWs)
+
+
+def small_linear_ok(x, *Ws):
+    return all(W.shape[0] <= SMALL_LINEAR_MAX and W.shape[1] <= SMALL_LINEAR_MAX for W in Ws) and 1 <= len(Ws) <= 3
+
+
+def linear_multi(x, Ws, precision="fp32"):
+    """[x @ W.T for W in Ws] (bias-free, same shapes): one fused pass when the layers are narrow, else one GEMM each."""
+    if small_linear_ok(x, *Ws) and len(set(tuple(W.shape) for W in Ws)) == 1:
+        out = SmallLinear.apply(x, None, 0, *Ws)
+        return list(out) if len(Ws) > 1 else [out]
+    return [linear_act(x, W, precision=precision) for W in Ws]
+
+
 def linear_act(x, W, b=None, activation=None, precision="fp32"):
-    """precision 'fp32' = exact CUDA-core SGEMM, 'bf16' = tcgen05 GEMM (bf16 operands, fp32 accumulate)."""
+    """precision 'fp32' = exact CUDA-core SGEMM, 'bf16' = tcgen05 GEMM (bf16 operands, fp32 accumulate); layers with K, N <= 32
+    (attention projections, pooling MLP) stream through the narrow-layer kernels in exact fp32 whatever the precision."""
+    if small_linear_ok(x, W):
+        return SmallLinear.apply(x, b, N.ACT[activation], W)
     if precision == "bf16":
         return LinearActTC.apply(x, W, b, N.ACT[activation])
     return LinearAct.apply(x, W, b, N.ACT[activation])
