@@ -153,6 +153,9 @@ DX_CASES = [
     (20, 22, 32, 256, 128),
     (9, 26, 64, 256, 26),
     (2500, 12, 16, 40, 20),
+    (2500, 26, 16, 200, 100),     # 313 tiles on 148 CTAs: 2-3 tiles per CTA, the next tile's dY is staged while the current one drains
+    (1250, 22, 32, 256, 128),     # same with the widest A tile (16 granules per row warp, 22 fields)
+    (5000, 5, 8, 64, 32),         # fewer fields than granules: several tiles per CTA, each staged at its start
 ]
 
 

@@ -15,7 +15,10 @@
 // W'' = weights permuted to [m*HpQ rows (j-major), H_pad cols] bf16 (K-major for this GEMM), streamed by TMA per field and
 // multicast across the CTAs of a cluster exactly like the forward weight stream.
 //
-// TMEM columns: [0,128) dY of the current tile (A operand), [256,384) / [384,512) the two dZ accumulators.
+// TMEM columns: [0,128) / [128,256) dY of the current / next tile (A operand, double buffered), [256,384) / [384,512) the two dZ
+// accumulators.  The row warps stage the NEXT tile's dY one 16-byte granule per field while they drain the current tile (global
+// load issued at field g, tcgen05.st at field g+1), so the tensor core rolls from the last field of a tile straight into the
+// first field of the next one; shapes with fewer fields than granules stage at the tile start instead.
 // Warps: 0 = TMA, 1 = MMA + TMEM alloc, 2..9 = row warps (quarter = warp & 3, channel half = (warp - 2) >> 2).
 #include "tc_common.cuh"
 #include "../../include/xdfm.h"
@@ -44,7 +47,7 @@ struct CinDxParams {
 
 struct __align__(8) CinDxBars {
   uint64_t w_full[DX_MAX_NS], w_empty[DX_MAX_NS];
-  uint64_t a_full, a_empty;          // dY tile in TMEM (count 8 / 1)
+  uint64_t a_full[2], a_empty[2];    // dY tiles in TMEM (count 4 * NG / 1)
   uint64_t acc_full[2], acc_empty[2];
   uint64_t x_full[2], x_empty[2];
   uint32_t tmem_base;
@@ -64,17 +67,17 @@ __global__ void __launch_bounds__((2 + 4 * NG) * 32, 1) cin_bwd_dx_tc_kernel(con
   uint8_t* sW = smem;                                                         // ns x n_hchunks x [HpQ x 128 B]
   const uint32_t x0_tile = (uint32_t)128 * p.mP * 2;
   uint8_t* sX0 = sW + (size_t)p.ns * w_slot_bytes;                            // 2 x [128][mP] bf16
-  float* sDx0 = reinterpret_cast<float*>(sX0 + 2 * (size_t)x0_tile);          // [NG groups][128][mP] fp32 dX0 partials
-  CinDxBars* bars = reinterpret_cast<CinDxBars*>(sDx0 + NG * 128 * p.mP);
+  const int dpitch = p.mP + 1;                                                // odd pitch: a warp's 32 rows hit 32 different banks
+  float* sDx0 = reinterpret_cast<float*>(sX0 + 2 * (size_t)x0_tile);          // [NG groups][128][mP + 1] fp32 dX0 partials
+  CinDxBars* bars = reinterpret_cast<CinDxBars*>(sDx0 + ((NG * 128 * dpitch + 1) & ~1));
 
   const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
   const uint16_t cmask = (uint16_t)((1u << csize) - 1);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < DX_MAX_NS; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], csize); }
-    mbar_init(&bars->a_full, 4 * NG);
-    mbar_init(&bars->a_empty, 1);
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->a_full[i], 4 * NG); mbar_init(&bars->a_empty[i], 1);
       mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 4 * NG);
       mbar_init(&bars->x_full[i], 1);   mbar_init(&bars->x_empty[i], 4 * NG);
     }
@@ -134,8 +137,10 @@ __global__ void __launch_bounds__((2 + 4 * NG) * 32, 1) cin_bwd_dx_tc_kernel(con
     const int ksteps = p.H_pad / 16;
     for (int it = 0; it < p.n_iters; ++it) {
       const bool active = tile_of(it) < p.n_tiles;
+      const uint32_t abuf = (uint32_t)(at & 1);
+      const uint32_t a_addr0 = tmem_base + abuf * 128;
       if (active) {
-        mbar_wait(&bars->a_full, at & 1);
+        mbar_wait(&bars->a_full[abuf], (at >> 1) & 1);
         fence_after_sync();
       }
       for (int j = 0; j < p.m; ++j) {
@@ -153,7 +158,7 @@ __global__ void __launch_bounds__((2 + 4 * NG) * 32, 1) cin_bwd_dx_tc_kernel(con
             for (int ks = 0; ks < ksteps; ks += 4, bd += box_desc_step) {
 #pragma unroll
               for (int k4 = 0; k4 < 4; ++k4) {
-                if (ks + k4 < ksteps) umma_ts(d_addr, tmem_base + (uint32_t)(ks + k4) * 8, bd + (uint64_t)(k4 * 2), idesc, (ks + k4) > 0 ? 1u : 0u);
+                if (ks + k4 < ksteps) umma_ts(d_addr, a_addr0 + (uint32_t)(ks + k4) * 8, bd + (uint64_t)(k4 * 2), idesc, (ks + k4) > 0 ? 1u : 0u);
               }
             }
           }
@@ -167,7 +172,7 @@ __global__ void __launch_bounds__((2 + 4 * NG) * 32, 1) cin_bwd_dx_tc_kernel(con
         if (active) ++jc;
       }
       if (active) {
-        if (elect_one()) umma_commit(&bars->a_empty);     // all MMAs reading this tile's dY have been issued and will complete
+        if (elect_one()) umma_commit(&bars->a_empty[abuf]);   // all MMAs reading this tile's dY have been issued and will complete
         __syncwarp();
         ++at;
       }
@@ -180,21 +185,25 @@ __global__ void __launch_bounds__((2 + 4 * NG) * 32, 1) cin_bwd_dx_tc_kernel(con
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     uint32_t jc = 0;
     int at = 0;
+    bool staged = false;        // this tile's dY already sits in TMEM (staged while the previous tile was drained)
     for (int it = 0; it < p.n_iters; ++it) {
       const int64_t tile = tile_of(it);
       if (tile >= p.n_tiles) continue;
       const int64_t row = tile * 128 + rl;
       const bool valid = row < p.R;
-      // ---- stage this tile's dY rows into TMEM (A operand): this warp writes columns [half*H_pad/4 ...) of its lane quarter
-      if (at > 0) {
-        mbar_wait(&bars->a_empty, (at - 1) & 1);
-        fence_after_sync();
-      }
-      {
-        const int ncol = p.H_pad / 2;                // 32-bit columns of the A tile
-        const int per = ((ncol + NG - 1) / NG + 3) & ~3;
-        const int c_beg = half * per;
-        const int c_end = min(ncol, c_beg + per);
+      // ---- this tile's dY rows in TMEM (A operand, buffer at & 1): this warp owns 32-bit columns [c_beg, c_end) of its lane quarter.
+      // Staged during the previous tile when the shape allows it (one granule per field), else here.
+      const int ncol = p.H_pad / 2;                  // 32-bit columns of the A tile
+      const int per = ((ncol + NG - 1) / NG + 3) & ~3;
+      const int c_beg = half * per;
+      const int c_end = min(ncol, c_beg + per);
+      const int ngr = c_end > c_beg ? (c_end - c_beg + 3) / 4 : 0;     // this warp's 16-byte granules
+      const uint32_t abuf = (uint32_t)(at & 1);
+      if (!staged) {
+        if (at >= 2) {
+          mbar_wait(&bars->a_empty[abuf], ((at >> 1) - 1) & 1);
+          fence_after_sync();
+        }
         const uint32_t* src = reinterpret_cast<const uint32_t*>(p.dyt + row * p.Hs);
         // all global loads of the row half are issued before the first TMEM store (ncu, round 1: 12.6 % of the kernel's samples sat
         // on the STTM of a load -> store loop that paid one global-load latency per 16 bytes); at most 17 granules (H_pad <= 256)
@@ -211,13 +220,25 @@ __global__ void __launch_bounds__((2 + 4 * NG) * 32, 1) cin_bwd_dx_tc_kernel(con
           const int c = c_beg + gi * 4;
           if (c < c_end) {
             const uint32_t v[4] = {gbuf[gi].x, gbuf[gi].y, gbuf[gi].z, gbuf[gi].w};
-            tmem_st_x4(tmem_base + lane_addr + c, v);
+            tmem_st_x4(tmem_base + lane_addr + abuf * 128 + c, v);
           }
         }
         tmem_wait_st();
         fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->a_full);
+        if (lane == 0) mbar_arrive(&bars->a_full[abuf]);
+      }
+      // next tile of this CTA: its dY is staged into the other A buffer while this tile's fields are drained
+      const int64_t ntile = (it + 1 < p.n_iters) ? tile_of(it + 1) : p.n_tiles;
+      const bool pipe = ntile < p.n_tiles && (per / 4) < p.m;          // granule g: load at field g, store at field g + 1 <= m - 1
+      const uint32_t nbuf = abuf ^ 1u;
+      const int64_t nrow = ntile * 128 + rl;
+      const bool nvalid = pipe && nrow < p.R;
+      const uint32_t* nsrc = reinterpret_cast<const uint32_t*>(p.dyt + (nvalid ? nrow : 0) * p.Hs);
+      uint4 pg = make_uint4(0u, 0u, 0u, 0u);
+      if (pipe && at >= 1) {                         // the other buffer was read by the previous tile's MMAs: long complete
+        mbar_wait(&bars->a_empty[nbuf], (((at + 1) >> 1) - 1) & 1);
+        fence_after_sync();
       }
       // ---- this row's operands
       const int buf = at & 1;
@@ -240,54 +261,85 @@ __global__ void __launch_bounds__((2 + 4 * NG) * 32, 1) cin_bwd_dx_tc_kernel(con
       for (int j = 0; j < p.m; ++j, ++jc) {
         const uint32_t ab = jc & 1;
         const float x0v = __bfloat162float(x0row[j]);
+        if (pipe && j <= ngr) {
+          if (j >= 1) {                               // granule j - 1 was loaded one field ago
+            const uint32_t v4[4] = {pg.x, pg.y, pg.z, pg.w};
+            tmem_st_x4(tmem_base + lane_addr + nbuf * 128 + c_beg + (j - 1) * 4, v4);
+          }
+          if (j < ngr) {
+            const int c = c_beg + j * 4;
+            pg = make_uint4(0u, 0u, 0u, 0u);
+            if (nvalid && c * 2 < p.Hs) pg = *reinterpret_cast<const uint4*>(nsrc + c);
+          } else {                                    // j == ngr: this warp's share of the next A tile is complete
+            tmem_wait_st();
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->a_full[nbuf]);
+          }
+        }
         mbar_wait(&bars->acc_full[ab], (jc >> 1) & 1);
         fence_after_sync();
         const uint32_t acc = tmem_base + lane_addr + DX_ACC_COL0 + ab * DX_ACC_COLS + half * HALF;
         float dot = 0.f;
-        // all of this warp's dZ columns of the field in ONE batch of TMEM loads and one wait: the accumulator is handed back to
-        // the tensor core before the contraction starts
-        uint32_t v[HALF];
-        if (p.debug & 2) {
+        // this warp's dZ columns of the field in NB batches of TMEM loads (one wait each): one batch when the columns fit the register
+        // budget next to the dXk accumulators, two otherwise (round 1: at HALF = 56 a single 56-register batch spilled the X^{k-1}
+        // row into local memory inside this loop); the accumulator goes back to the tensor core after the last batch's loads
+        constexpr int NB = HALF > 32 ? 2 : 1;
+        constexpr int BS = HALF / NB;                 // multiple of 4
+        static_assert(BS * NB == HALF && BS % 4 == 0, "dZ batch split");
+        float d4[4] = {0.f, 0.f, 0.f, 0.f};          // four independent chains (the sum order is still a fixed function of HALF)
 #pragma unroll
-          for (int i = 0; i < HALF; ++i) v[i] = 0u;
-        } else
-        {
+        for (int nb = 0; nb < NB; ++nb) {
+          uint32_t v[BS];
+          if (p.debug & 2) {
 #pragma unroll
-          for (int c0 = 0; c0 + 8 <= HALF; c0 += 8) {
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                         : "=r"(v[c0 + 0]), "=r"(v[c0 + 1]), "=r"(v[c0 + 2]), "=r"(v[c0 + 3]), "=r"(v[c0 + 4]), "=r"(v[c0 + 5]),
-                           "=r"(v[c0 + 6]), "=r"(v[c0 + 7])
-                         : "r"(acc + c0)
-                         : "memory");
+            for (int i = 0; i < BS; ++i) v[i] = 0u;
+          } else {
+#pragma unroll
+            for (int c0 = 0; c0 + 8 <= BS; c0 += 8) {
+              asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                           : "=r"(v[c0 + 0]), "=r"(v[c0 + 1]), "=r"(v[c0 + 2]), "=r"(v[c0 + 3]), "=r"(v[c0 + 4]), "=r"(v[c0 + 5]),
+                             "=r"(v[c0 + 6]), "=r"(v[c0 + 7])
+                           : "r"(acc + nb * BS + c0)
+                           : "memory");
+            }
+            if constexpr (BS % 8 != 0) {
+              constexpr int c0 = BS - 4;
+              asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(v[c0 + 0]), "=r"(v[c0 + 1]), "=r"(v[c0 + 2]), "=r"(v[c0 + 3])
+                           : "r"(acc + nb * BS + c0)
+                           : "memory");
+            }
           }
-          if constexpr (HALF % 8 != 0) {
-            constexpr int c0 = HALF - 4;
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(v[c0 + 0]), "=r"(v[c0 + 1]), "=r"(v[c0 + 2]), "=r"(v[c0 + 3])
-                         : "r"(acc + c0)
-                         : "memory");
+          tmem_wait_ld();
+          if (nb == NB - 1) {
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->acc_empty[ab]);
+          }
+          if (!(p.debug & 1)) {
+#pragma unroll
+            for (int i = 0; i < BS; i += 2) {
+              const int ci = nb * BS + i;             // channel index inside this warp's half
+              // bf16 pair -> two fp32 with volatile asm: the row is loop-invariant over the fields, and left to itself the compiler
+              // hoists the conversions out of the field loop (56 more live registers -> the row spills to local memory)
+              const uint32_t xp = *reinterpret_cast<const uint32_t*>(&xk2[ci / 2]);
+              uint32_t xlo, xhi;
+              asm volatile("shl.b32 %0, %1, 16;" : "=r"(xlo) : "r"(xp));
+              asm volatile("and.b32 %0, %1, 0xffff0000;" : "=r"(xhi) : "r"(xp));
+              const float z0 = __uint_as_float(v[i]), z1 = __uint_as_float(v[i + 1]);
+              dxk[ci] = fmaf(z0, x0v, dxk[ci]);
+              dxk[ci + 1] = fmaf(z1, x0v, dxk[ci + 1]);
+              d4[(ci / 2) & 3] = fmaf(z0, __uint_as_float(xlo), d4[(ci / 2) & 3]);
+              d4[(ci / 2 + 2) & 3] = fmaf(z1, __uint_as_float(xhi), d4[(ci / 2 + 2) & 3]);
+            }
           }
         }
-        tmem_wait_ld();
-        fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->acc_empty[ab]);
-        if (!(p.debug & 1)) {
-          float d4[4] = {0.f, 0.f, 0.f, 0.f};        // four independent chains (the sum order is still a fixed function of HALF)
-#pragma unroll
-          for (int i = 0; i < HALF; i += 2) {
-            const float2 xf = __bfloat1622float2(xk2[i / 2]);
-            const float z0 = __uint_as_float(v[i]), z1 = __uint_as_float(v[i + 1]);
-            dxk[i] = fmaf(z0, x0v, dxk[i]);
-            dxk[i + 1] = fmaf(z1, x0v, dxk[i + 1]);
-            d4[(i / 2) & 3] = fmaf(z0, xf.x, d4[(i / 2) & 3]);
-            d4[(i / 2 + 2) & 3] = fmaf(z1, xf.y, d4[(i / 2 + 2) & 3]);
-          }
-          dot = (d4[0] + d4[1]) + (d4[2] + d4[3]);
-        }
+        dot = (d4[0] + d4[1]) + (d4[2] + d4[3]);
         // dX0[r, j] partial of this warp's channel group: parked in shared memory (plane = group), combined in group order at tile end
-        sDx0[(half * 128 + rl) * p.mP + j] = dot;
+        sDx0[(half * 128 + rl) * dpitch + j] = dot;
       }
+      staged = pipe;
       // ---- tile outputs
       if (valid) {
         float* o = p.dxk + row * p.HpQ + half * HALF;
@@ -295,13 +347,37 @@ __global__ void __launch_bounds__((2 + 4 * NG) * 32, 1) cin_bwd_dx_tc_kernel(con
         for (int i = 0; i < HALF; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(dxk[i], dxk[i + 1], dxk[i + 2], dxk[i + 3]);
       }
       asm volatile("bar.sync 1, %0;" ::"n"(128 * NG) : "memory");     // all groups' dX0 partials are in shared memory
-      if (half == 0 && valid) {
-        float* g = p.dx0 + row * p.mP;
-        for (int j = 0; j < p.m; ++j) {
-          float sacc = sDx0[rl * p.mP + j];
+      if (valid) {
+        // dx0 row += the groups' partials (summed in group order): 128-bit accesses, all loads of a pass in flight before the first
+        // add (the scalar load -> add -> store chain this replaces cost one L2 round trip per field at every tile end); the
+        // channel groups split the row's float4s
+        float4* g4 = reinterpret_cast<float4*>(p.dx0 + row * p.mP);
+        const int nv4 = p.mP / 4;
+        for (int base = half; base < nv4; base += NG * 4) {
+          float4 buf[4];
 #pragma unroll
-          for (int gq = 1; gq < NG; ++gq) sacc += sDx0[(gq * 128 + rl) * p.mP + j];
-          g[j] += sacc;
+          for (int u = 0; u < 4; ++u) {
+            const int i = base + u * NG;
+            if (i < nv4) buf[u] = g4[i];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = base + u * NG;
+            if (i < nv4) {
+              float a[4] = {buf[u].x, buf[u].y, buf[u].z, buf[u].w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const int j = i * 4 + t;
+                if (j < p.m) {
+                  float sacc = sDx0[rl * dpitch + j];
+#pragma unroll
+                  for (int gq = 1; gq < NG; ++gq) sacc += sDx0[(gq * 128 + rl) * dpitch + j];
+                  a[t] += sacc;
+                }
+              }
+              g4[i] = make_float4(a[0], a[1], a[2], a[3]);
+            }
+          }
         }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(128 * NG) : "memory");     // partial planes may be overwritten by the next tile
@@ -641,7 +717,7 @@ static int cin_dx_geom(int m, int Hp, int H, int D, CinDxGeom* g) {
   g->mP = round_up_i(m, 8);
   g->n_hchunks = (g->H_pad + 63) / 64;
   g->HC = g->n_hchunks * 64;
-  size_t fixed = 2 * (size_t)128 * g->mP * 2 + 2 * (size_t)128 * g->mP * 4 + sizeof(CinDxBars) + 256;
+  size_t fixed = 2 * (size_t)128 * g->mP * 2 + 2 * (size_t)128 * (g->mP + 1) * 4 + sizeof(CinDxBars) + 256;
   size_t slot = (size_t)g->HpQ * 128 * g->n_hchunks;        // one field
   int ns = (int)std::min<size_t>((227 * 1024 - fixed) / slot, DX_MAX_NS * 1);
   ns = std::min(ns, DX_MAX_NS);
@@ -763,7 +839,7 @@ extern "C" int xdfm_cin_bwd_dx_tc(const void* dyt, const void* x0t, const void* 
   if (g_cin_dx_groups == 4) {
     // four row warps per lane quarter: two more dX0 partial planes in shared memory
     const size_t slot = (size_t)g.HpQ * 128 * g.n_hchunks;
-    const size_t fixed4 = 2 * (size_t)128 * g.mP * 2 + 4 * (size_t)128 * g.mP * 4 + sizeof(CinDxBars) + 256;
+    const size_t fixed4 = 2 * (size_t)128 * g.mP * 2 + 4 * (size_t)128 * (g.mP + 1) * 4 + sizeof(CinDxBars) + 256;
     int ns4 = (227 * 1024 > fixed4) ? (int)std::min<size_t>((227 * 1024 - fixed4) / slot, DX_MAX_NS) : 0;
     if (ns4 >= 2) {
       CinDxParams p4 = p;
