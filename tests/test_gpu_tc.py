@@ -22,6 +22,21 @@ def test_tcgen05_selftest_gemm(mode, N, K):
     assert_close(out, ref, 1e-5, 1e-4, "selftest mode %d" % mode)
 
 
+@pytest.mark.parametrize("N,K", [(112, 208), (32, 48), (16, 16), (128, 144), (256, 96), (112, 192)])
+def test_tcgen05_selftest_gemm_k_tail_in_32_byte_swizzle(N, K):
+    """Mode 2: A in TMEM, B = full 64-wide SWIZZLE_128B chunks + 16-wide SWIZZLE_32B boxes for the K tail (the layout the dX kernel
+    streams W'' in when H is not a multiple of 64)."""
+    from deepctr import _native as Nv
+    g = torch.Generator().manual_seed(N + K)
+    A = torch.randn(128, K, generator=g).to(torch.bfloat16).to(DEV)
+    B = torch.randn(N, K, generator=g).to(torch.bfloat16).to(DEV)
+    out = torch.full((128, N), float("nan"), device=DEV)
+    Nv.check(Nv.lib().xdfm_tc_selftest_gemm(Nv.ptr(A), Nv.ptr(B), N, K, 2, Nv.ptr(out), Nv.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = A.float().double() @ B.float().double().t()
+    assert_close(out, ref, 1e-5, 1e-4, "selftest mode 2")
+
+
 def to_rows(x, CP):
     """[B, C, D] fp32 (device) -> row layout [B*D, CP] bf16 via the library."""
     from deepctr import _native as Nv

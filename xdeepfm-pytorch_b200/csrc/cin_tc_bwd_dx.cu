@@ -42,7 +42,11 @@ struct CinDxParams {
   int n_iters;
   int n_hchunks;              // 64-wide chunks of the reduction dim h per field = ceil(H_pad / 64)
   int debug;                  // diagnostic bit mask (0 in production): 1 skip contraction FMAs, 2 skip TMEM loads, 4 skip MMAs
-  int ns;                     // W'' ring depth (one slot = one FIELD: n_hchunks boxes of [HpQ rows x 128 B] on one barrier)
+  int ns;                     // W'' ring depth (one slot = one FIELD on one barrier)
+  // single-tile kernel: a slot holds the field's n_full 64-wide h-chunks ([HpQ rows x 128 B], SWIZZLE_128B) followed by tail_ks
+  // 16-wide chunks ([HpQ rows x 32 B], SWIZZLE_32B) -- H_pad = 64 n_full + 16 tail_ks, nothing zero-padded is streamed
+  int n_full, tail_ks;
+  uint32_t slot_stride;       // bytes between slots (slot bytes rounded up to 1024)
 };
 
 struct __align__(8) CinDxBars {
@@ -57,19 +61,22 @@ struct __align__(8) CinDxBars {
 // row warps, not the tensor core, pacing this kernel at low IPC (TMEM-load and FMA latencies, spills at 168 registers); with NG = 4
 // there are twice as many resident warps to hide those latencies and each needs half the registers.
 template <int NQ, int NG>
-__global__ void __launch_bounds__((2 + 4 * NG) * 32, 1) cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmW, CinDxParams p) {
+__global__ void __launch_bounds__((2 + 4 * NG) * 32, 1)
+cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWt, CinDxParams p) {
   constexpr int HpQ = NQ * 16;
   constexpr int HALF = HpQ / NG;                   // channels per row warp (multiple of 4)
+  constexpr int NPL = NG == 2 ? 1 : NG;            // dX0 partial planes: the two channel groups share one (two addends commute)
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t w_box_bytes = (uint32_t)HpQ * 128;                          // one 64-wide h-chunk of one field
-  const uint32_t w_slot_bytes = w_box_bytes * (uint32_t)p.n_hchunks;         // one field
-  uint8_t* sW = smem;                                                         // ns x n_hchunks x [HpQ x 128 B]
+  const uint32_t w_tail_bytes = (uint32_t)HpQ * 32;                          // one 16-wide h-chunk of the tail
+  const uint32_t w_slot_bytes = w_box_bytes * (uint32_t)p.n_full + w_tail_bytes * (uint32_t)p.tail_ks;   // bytes TMA delivers per field
+  uint8_t* sW = smem;                                                         // ns slots, slot_stride apart
   const uint32_t x0_tile = (uint32_t)128 * p.mP * 2;
-  uint8_t* sX0 = sW + (size_t)p.ns * w_slot_bytes;                            // 2 x [128][mP] bf16
+  uint8_t* sX0 = sW + (size_t)p.ns * p.slot_stride;                           // 2 x [128][mP] bf16
   const int dpitch = p.mP + 1;                                                // odd pitch: a warp's 32 rows hit 32 different banks
-  float* sDx0 = reinterpret_cast<float*>(sX0 + 2 * (size_t)x0_tile);          // [NG groups][128][mP + 1] fp32 dX0 partials
-  CinDxBars* bars = reinterpret_cast<CinDxBars*>(sDx0 + ((NG * 128 * dpitch + 1) & ~1));
+  float* sDx0 = reinterpret_cast<float*>(sX0 + 2 * (size_t)x0_tile);          // [NPL][128][mP + 1] fp32 dX0 partials
+  CinDxBars* bars = reinterpret_cast<CinDxBars*>(sDx0 + ((NPL * 128 * dpitch + 1) & ~1));
 
   const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
   const uint16_t cmask = (uint16_t)((1u << csize) - 1);
@@ -83,6 +90,8 @@ __global__ void __launch_bounds__((2 + 4 * NG) * 32, 1) cin_bwd_dx_tc_kernel(con
     }
     fence_barrier_init();
   }
+  if (NG == 2)
+    for (int i = threadIdx.x; i < 128 * dpitch; i += blockDim.x) sDx0[i] = 0.f;
   if (warp == 1) tmem_alloc(&bars->tmem_base, 512);
   fence_before_sync();
   __syncthreads();
@@ -95,6 +104,7 @@ __global__ void __launch_bounds__((2 + 4 * NG) * 32, 1) cin_bwd_dx_tc_kernel(con
     // =============================== TMA: x0 tiles (one ahead) + W'' stream ===============================
     if (lane == 0) {
       prefetch_tmap(&tmW);
+      prefetch_tmap(&tmWt);
       const int slice = HpQ / (int)csize;            // rows of a W'' slot loaded (and multicast) by this CTA
       const int wr0 = (int)crank * slice;
       int xit = 0;
@@ -115,10 +125,16 @@ __global__ void __launch_bounds__((2 + 4 * NG) * 32, 1) cin_bwd_dx_tc_kernel(con
         for (int j = 0; j < p.m; ++j) {
           if (!first_pass) mbar_wait(&bars->w_empty[ws], wphase);
           mbar_arrive_expect_tx(&bars->w_full[ws], w_slot_bytes);
-          for (int c = 0; c < p.n_hchunks; ++c) {
-            uint8_t* dst = sW + (size_t)ws * w_slot_bytes + (size_t)c * w_box_bytes + (size_t)wr0 * 128;
+          uint8_t* slot = sW + (size_t)ws * p.slot_stride;
+          for (int c = 0; c < p.n_full; ++c) {
+            uint8_t* dst = slot + (size_t)c * w_box_bytes + (size_t)wr0 * 128;
             if (csize > 1) tma_load_2d_mcast(dst, &tmW, c * 64, j * HpQ + wr0, &bars->w_full[ws], cmask);
             else tma_load_2d(dst, &tmW, c * 64, j * HpQ + wr0, &bars->w_full[ws]);
+          }
+          for (int t = 0; t < p.tail_ks; ++t) {
+            uint8_t* dst = slot + (size_t)p.n_full * w_box_bytes + (size_t)t * w_tail_bytes + (size_t)wr0 * 32;
+            if (csize > 1) tma_load_2d_mcast(dst, &tmWt, p.n_full * 64 + t * 16, j * HpQ + wr0, &bars->w_full[ws], cmask);
+            else tma_load_2d(dst, &tmWt, p.n_full * 64 + t * 16, j * HpQ + wr0, &bars->w_full[ws]);
           }
           if (++ws == (uint32_t)p.ns) { ws = 0; wphase ^= 1; first_pass = false; }
         }
@@ -128,13 +144,15 @@ __global__ void __launch_bounds__((2 + 4 * NG) * 32, 1) cin_bwd_dx_tc_kernel(con
     // =============================== MMA issuer (warp-uniform loop, elected lane issues) ===============================
     const uint32_t idesc = make_idesc_bf16(128, HpQ);
     const uint64_t bdesc0 = make_desc_k_sw128(smem_u32(sW));
-    const uint32_t slot_desc_step = w_slot_bytes >> 4;
+    const uint64_t tdesc0 = make_desc_k_sw32(smem_u32(sW) + (uint32_t)p.n_full * w_box_bytes);
+    const uint32_t slot_desc_step = p.slot_stride >> 4;
     const uint32_t box_desc_step = w_box_bytes >> 4;
+    const uint32_t tail_desc_step = w_tail_bytes >> 4;
     uint32_t ws = 0, wphase = 0;
-    uint64_t bdesc = bdesc0;
+    uint64_t bdesc = bdesc0, tdesc = tdesc0;
     uint32_t jc = 0;            // fields processed so far (accumulator buffer = jc & 1)
     int at = 0;
-    const int ksteps = p.H_pad / 16;
+    const int ksteps = p.n_full * 4;
     for (int it = 0; it < p.n_iters; ++it) {
       const bool active = tile_of(it) < p.n_tiles;
       const uint32_t abuf = (uint32_t)(at & 1);
@@ -161,14 +179,16 @@ __global__ void __launch_bounds__((2 + 4 * NG) * 32, 1) cin_bwd_dx_tc_kernel(con
                 if (ks + k4 < ksteps) umma_ts(d_addr, a_addr0 + (uint32_t)(ks + k4) * 8, bd + (uint64_t)(k4 * 2), idesc, (ks + k4) > 0 ? 1u : 0u);
               }
             }
+            for (int t = 0; t < p.tail_ks; ++t)
+              umma_ts(d_addr, a_addr0 + (uint32_t)(ksteps + t) * 8, tdesc + (uint64_t)t * tail_desc_step, idesc, (ksteps + t) > 0 ? 1u : 0u);
           }
           if (csize > 1) umma_commit_mcast(&bars->w_empty[ws], cmask);
           else umma_commit(&bars->w_empty[ws]);
           if (active) umma_commit(&bars->acc_full[ab]);
         }
         __syncwarp();
-        if (++ws == (uint32_t)p.ns) { ws = 0; wphase ^= 1; bdesc = bdesc0; }
-        else bdesc += slot_desc_step;
+        if (++ws == (uint32_t)p.ns) { ws = 0; wphase ^= 1; bdesc = bdesc0; tdesc = tdesc0; }
+        else { bdesc += slot_desc_step; tdesc += slot_desc_step; }
         if (active) ++jc;
       }
       if (active) {
@@ -337,7 +357,8 @@ __global__ void __launch_bounds__((2 + 4 * NG) * 32, 1) cin_bwd_dx_tc_kernel(con
         }
         dot = (d4[0] + d4[1]) + (d4[2] + d4[3]);
         // dX0[r, j] partial of this warp's channel group: parked in shared memory (plane = group), combined in group order at tile end
-        sDx0[(half * 128 + rl) * dpitch + j] = dot;
+        if (NG == 2) atomicAdd(&sDx0[rl * dpitch + j], dot);      // zeroed plane + two addends (the channel groups): order-independent
+        else sDx0[(half * 128 + rl) * dpitch + j] = dot;
       }
       staged = pipe;
       // ---- tile outputs
@@ -347,6 +368,9 @@ __global__ void __launch_bounds__((2 + 4 * NG) * 32, 1) cin_bwd_dx_tc_kernel(con
         for (int i = 0; i < HALF; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(dxk[i], dxk[i + 1], dxk[i + 2], dxk[i + 3]);
       }
       asm volatile("bar.sync 1, %0;" ::"n"(128 * NG) : "memory");     // all groups' dX0 partials are in shared memory
+      if (!valid && NG == 2) {                      // rows past R: nothing to write, but the shared plane must be clean again
+        for (int j = half; j < p.m; j += NG) sDx0[rl * dpitch + j] = 0.f;
+      }
       if (valid) {
         // dx0 row += the groups' partials (summed in group order): 128-bit accesses, all loads of a pass in flight before the first
         // add (the scalar load -> add -> store chain this replaces cost one L2 round trip per field at every tile end); the
@@ -370,8 +394,9 @@ __global__ void __launch_bounds__((2 + 4 * NG) * 32, 1) cin_bwd_dx_tc_kernel(con
                 const int j = i * 4 + t;
                 if (j < p.m) {
                   float sacc = sDx0[rl * dpitch + j];
+                  if (NG == 2) sDx0[rl * dpitch + j] = 0.f;                  // ready for the next tile's atomics
 #pragma unroll
-                  for (int gq = 1; gq < NG; ++gq) sacc += sDx0[(gq * 128 + rl) * dpitch + j];
+                  for (int gq = 1; gq < NPL; ++gq) sacc += sDx0[(gq * 128 + rl) * dpitch + j];
                   a[t] += sacc;
                 }
               }
@@ -703,6 +728,8 @@ static int round_up_i(int a, int b) { return (a + b - 1) / b * b; }
 
 struct CinDxGeom {
   int HpQ, H_pad, Hs, mP, HC, n_hchunks, ns;
+  int n_full, tail_ks;
+  uint32_t slot_stride;
   size_t smem;
 };
 
@@ -717,8 +744,11 @@ static int cin_dx_geom(int m, int Hp, int H, int D, CinDxGeom* g) {
   g->mP = round_up_i(m, 8);
   g->n_hchunks = (g->H_pad + 63) / 64;
   g->HC = g->n_hchunks * 64;
-  size_t fixed = 2 * (size_t)128 * g->mP * 2 + 2 * (size_t)128 * (g->mP + 1) * 4 + sizeof(CinDxBars) + 256;
-  size_t slot = (size_t)g->HpQ * 128 * g->n_hchunks;        // one field
+  g->n_full = g->H_pad / 64;
+  g->tail_ks = (g->H_pad % 64) / 16;
+  size_t fixed = 2 * (size_t)128 * g->mP * 2 + (size_t)128 * (g->mP + 1) * 4 + sizeof(CinDxBars) + 256;     // one shared dX0 plane (NG = 2)
+  size_t slot = ((size_t)g->HpQ * 128 * g->n_full + (size_t)g->HpQ * 32 * g->tail_ks + 1023) / 1024 * 1024;   // one field
+  g->slot_stride = (uint32_t)slot;
   int ns = (int)std::min<size_t>((227 * 1024 - fixed) / slot, DX_MAX_NS * 1);
   ns = std::min(ns, DX_MAX_NS);
   if (ns < 2) {
@@ -767,7 +797,8 @@ int g_cin_dx_groups = 2;     // row warps per TMEM lane quarter in the dX kernel
 extern "C" void xdfm_cin_dx_set_groups(int v) { g_cin_dx_groups = (v == 4) ? 4 : 2; }
 
 template <int NQ, int NG>
-static int launch_dx(const CUtensorMap& tmW, const CinDxParams& p, size_t smem, int blocks, int cluster, cudaStream_t st) {
+static int launch_dx(const CUtensorMap& tmW, const CUtensorMap& tmWt, const CinDxParams& p, size_t smem, int blocks, int cluster,
+                     cudaStream_t st) {
   XDFM_CUDA(cudaFuncSetAttribute(cin_bwd_dx_tc_kernel<NQ, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(blocks);
@@ -781,7 +812,7 @@ static int launch_dx(const CUtensorMap& tmW, const CinDxParams& p, size_t smem, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  XDFM_CUDA(cudaLaunchKernelEx(&cfg, cin_bwd_dx_tc_kernel<NQ, NG>, tmW, p));
+  XDFM_CUDA(cudaLaunchKernelEx(&cfg, cin_bwd_dx_tc_kernel<NQ, NG>, tmW, tmWt, p));
   XDFM_LAUNCH_CHECK();
   return XDFM_OK;
 }
@@ -809,8 +840,13 @@ extern "C" int xdfm_cin_bwd_dx_tc(const void* dyt, const void* x0t, const void* 
   CUtensorMap tmW;
   rc = xdfm_make_tmap_bf16(&tmW, wt, (uint64_t)m * g.HpQ, (uint64_t)g.HC, (uint64_t)g.HC * 2, (uint32_t)(g.HpQ / cluster), 64, 1);
   if (rc) return rc;
+  // 16-wide SWIZZLE_32B boxes over the same matrix: the K tail (H_pad % 64) of every field
+  CUtensorMap tmWt;
+  rc = xdfm_make_tmap_bf16(&tmWt, wt, (uint64_t)m * g.HpQ, (uint64_t)g.HC, (uint64_t)g.HC * 2, (uint32_t)(g.HpQ / cluster), 16, 2);
+  if (rc) return rc;
   const int64_t R = B * (int64_t)D;
   CinDxParams p;
+  p.n_full = g.n_full; p.tail_ks = g.tail_ks; p.slot_stride = g.slot_stride;
   p.dyt = (const __nv_bfloat16*)dyt; p.x0t = (const __nv_bfloat16*)x0t; p.xkt = (const __nv_bfloat16*)xkt; p.dxk = dxk; p.dx0 = dx0;
   p.R = R; p.xk_pitch = xk_pitch; p.m = m; p.mP = g.mP; p.Hp = Hp; p.HpQ = g.HpQ; p.H = H; p.H_pad = g.H_pad; p.Hs = g.Hs;
   p.n_tiles = ceil_div64(R, 128); p.n_hchunks = g.n_hchunks; p.ns = g.ns; p.debug = g_cin_dx_debug;
@@ -837,8 +873,8 @@ extern "C" int xdfm_cin_bwd_dx_tc(const void* dyt, const void* x0t, const void* 
     }
   }
   if (g_cin_dx_groups == 4) {
-    // four row warps per lane quarter: two more dX0 partial planes in shared memory
-    const size_t slot = (size_t)g.HpQ * 128 * g.n_hchunks;
+    // four row warps per lane quarter: one dX0 partial plane per group in shared memory
+    const size_t slot = g.slot_stride;
     const size_t fixed4 = 2 * (size_t)128 * g.mP * 2 + 4 * (size_t)128 * (g.mP + 1) * 4 + sizeof(CinDxBars) + 256;
     int ns4 = (227 * 1024 > fixed4) ? (int)std::min<size_t>((227 * 1024 - fixed4) / slot, DX_MAX_NS) : 0;
     if (ns4 >= 2) {
@@ -846,14 +882,14 @@ extern "C" int xdfm_cin_bwd_dx_tc(const void* dyt, const void* x0t, const void* 
       p4.ns = ns4;
       const size_t smem4 = fixed4 + (size_t)ns4 * slot;
       switch (g.HpQ / 16) {
-#define CASE_NQ4(n) case n: return launch_dx<n, 4>(tmW, p4, smem4, blocks, cluster, st);
+#define CASE_NQ4(n) case n: return launch_dx<n, 4>(tmW, tmWt, p4, smem4, blocks, cluster, st);
         CASE_NQ4(1) CASE_NQ4(2) CASE_NQ4(3) CASE_NQ4(4) CASE_NQ4(5) CASE_NQ4(6) CASE_NQ4(7) CASE_NQ4(8)
 #undef CASE_NQ4
       }
     }
   }
   switch (g.HpQ / 16) {
-#define CASE_NQ(n) case n: return launch_dx<n, 2>(tmW, p, g.smem, blocks, cluster, st);
+#define CASE_NQ(n) case n: return launch_dx<n, 2>(tmW, tmWt, p, g.smem, blocks, cluster, st);
     CASE_NQ(1) CASE_NQ(2) CASE_NQ(3) CASE_NQ(4) CASE_NQ(5) CASE_NQ(6) CASE_NQ(7) CASE_NQ(8)
 #undef CASE_NQ
   }

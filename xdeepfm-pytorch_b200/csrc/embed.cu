@@ -273,7 +273,7 @@ extern "C" int xdfm_embed_bwd_segments(const int32_t* ids, int64_t B, int m, con
 // the S slots of ONE warp (short segments) or of ALL warps of a block (long segments); every slot adds its
 // entries in increasing e, then slots are combined by a fixed xor-shuffle tree (and a fixed smem order
 // across warps).  The summation order depends only on (len, D), never on scheduling -> bit-reproducible.
-#define SEG_LONG 1024
+#define SEG_LONG 256
 
 template <int VEC>
 __device__ __forceinline__ void vec_add(float* a, const float* b) {
@@ -318,6 +318,14 @@ __device__ __forceinline__ void seg_accumulate(const float* __restrict__ demb, c
   }
 }
 
+// Long segments (hot rows: a field with 3 distinct ids has ~B/3 entries per row) are found by the short pass and appended to a
+// per-device list; the long pass then walks that list (one block per long segment) instead of scanning all ~1e5 segment offsets
+// from every block -- the scan alone cost 130 us per table set at BASELINE config 2 (ncu, round 1).  The list order depends on
+// scheduling, the sums do not (every segment is reduced by exactly one block in a fixed order).
+#define SEG_LONG_LIST 8192
+__device__ int g_seg_long_count;
+__device__ int g_seg_long_list[SEG_LONG_LIST];
+
 template <int VEC>
 __global__ void __launch_bounds__(256) seg_reduce_kernel(const float* __restrict__ demb, const float* __restrict__ dlin,
                                                          const int32_t* __restrict__ sorted_pos,
@@ -332,12 +340,15 @@ __global__ void __launch_bounds__(256) seg_reduce_kernel(const float* __restrict
   const int sub = lane % lpr;           // which VEC piece of the row (valid if sub*VEC < D)
   const bool active = sub * VEC < D;
   __shared__ float sh[8][32 * 4 + 8];
-  if (!long_pass) {
+  if (long_pass <= 0) {                    // 0: short segments + list of the long ones; -1: short segments only (scanning fallback)
     int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t s = warp; s < nseg; s += nwarps) {
       int beg = seg_offsets[s], end = seg_offsets[s + 1];
-      if (end - beg > SEG_LONG) continue;  // handled by the long pass
+      if (end - beg > SEG_LONG) {          // handled by the long pass
+        if (long_pass == 0 && lane == 0) g_seg_long_list[atomicAdd(&g_seg_long_count, 1)] = (int)s;
+        continue;
+      }
       float acc[VEC];
 #pragma unroll
       for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
@@ -359,7 +370,10 @@ __global__ void __launch_bounds__(256) seg_reduce_kernel(const float* __restrict
   } else {
     // long segments: one block per segment (grid-stride), 8 warps x S slots
     const int w = threadIdx.x >> 5;
-    for (int64_t s = blockIdx.x; s < nseg; s += gridDim.x) {
+    const bool listed = long_pass == 1;    // 1: walk the list left by the short pass; 2: scan every segment (n_keys beyond the list)
+    const int64_t n_iter = listed ? g_seg_long_count : nseg;
+    for (int64_t it = blockIdx.x; it < n_iter; it += gridDim.x) {
+      const int64_t s = listed ? g_seg_long_list[it] : it;
       int beg = seg_offsets[s], end = seg_offsets[s + 1];
       if (end - beg <= SEG_LONG) continue;
       float acc[VEC];
@@ -414,11 +428,18 @@ extern "C" int xdfm_embed_bwd_reduce(const float* demb, const float* dlin, const
   }
   int blocks_short = (int)min((int64_t)xdfm_num_sms() * 8, ceil_div64(n_keys, 8));
   int blocks_long = xdfm_num_sms() * 2;
+  const bool listed = n_keys / SEG_LONG < SEG_LONG_LIST;      // at most n_keys / SEG_LONG long segments can exist
+  if (listed) {
+    void* cnt = nullptr;
+    XDFM_CUDA(cudaGetSymbolAddress(&cnt, g_seg_long_count));
+    XDFM_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int), st));
+  }
+  const int mode_short = listed ? 0 : -1, mode_long = listed ? 1 : 2;
 #define LAUNCH_SEG(V)                                                                                                    \
   seg_reduce_kernel<V><<<max(blocks_short, 1), 256, 0, st>>>(demb, dlin, sorted_pos, seg_offsets, num_segments, m, D, lpr, gsum, \
-                                                             gsum_lin, 0);                                               \
+                                                             gsum_lin, mode_short);                                      \
   seg_reduce_kernel<V><<<blocks_long, 256, 0, st>>>(demb, dlin, sorted_pos, seg_offsets, num_segments, m, D, lpr, gsum,  \
-                                                    gsum_lin, 1);
+                                                    gsum_lin, mode_long);
   if (vec == 4) { LAUNCH_SEG(4) } else if (vec == 2) { LAUNCH_SEG(2) } else { LAUNCH_SEG(1) }
 #undef LAUNCH_SEG
   ++g_xdfm_launches;  // two kernels above, one check below

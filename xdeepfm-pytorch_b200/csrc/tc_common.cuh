@@ -141,6 +141,18 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// same for a 16-element (32-byte) K extent: rows of 32 bytes, SWIZZLE_32B, 8-row groups 256 B apart -- exactly one UMMA_K step of
+// bf16.  Used for the K tail of an operand whose K is a multiple of 16 but not of 64 (no zero-padded 128-byte chunk to stream).
+__device__ __forceinline__ uint64_t make_desc_k_sw32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);   // start address
+  d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(256 >> 4) << 32;              // stride byte offset: 8 rows * 32 B
+  d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+  d |= (uint64_t)6 << 61;                       // layout type SWIZZLE_32B
+  return d;
+}
+
 // tcgen05.st 32x32b: thread (lane l of warp w) writes N consecutive 32-bit columns of TMEM lane 32*(w%4)+l
 __device__ __forceinline__ void tmem_st_x4(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3])
@@ -176,6 +188,7 @@ __device__ __forceinline__ bool elect_one() {
 
 }  // namespace tc
 
+// swizzle: 0 = none, 1 = 128-byte (box_cols = 64), 2 = 32-byte (box_cols = 16)
 int xdfm_make_tmap_bf16(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t row_pitch_bytes, uint32_t box_rows,
                         uint32_t box_cols, int swizzle128);
 // host: encode a 2-D bf16 tensor map (row-major [rows, cols], box [box_rows, 64 cols], SWIZZLE_128B)

@@ -21,7 +21,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 // 2-D bf16 tensor map over a row-major [rows, cols] matrix (row pitch in bytes), box [box_rows, box_cols];
-// swizzle: 0 = none, 1 = 128-byte (box_cols must then be 64)
+// swizzle: 0 = none, 1 = 128-byte (box_cols must then be 64), 2 = 32-byte (box_cols must then be 16)
 int xdfm_make_tmap_bf16(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t row_pitch_bytes, uint32_t box_rows,
                         uint32_t box_cols, int swizzle128) {
   PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode_fn();
@@ -34,7 +34,8 @@ int xdfm_make_tmap_bf16(CUtensorMap* out, const void* gptr, uint64_t rows, uint6
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle128 == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle128 == 2 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     xdfm_set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu pitch=%llu box=%ux%u", (int)r, (unsigned long long)rows,
@@ -50,15 +51,17 @@ int xdfm_make_tmap_bf16_sw128(CUtensorMap* out, const void* gptr, uint64_t rows,
 }
 
 __global__ void __launch_bounds__(128) tc_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                                                          const __nv_bfloat16* __restrict__ A, int N, int K, int mode,
-                                                          float* __restrict__ out) {
+                                                          const __grid_constant__ CUtensorMap tmBt, const __nv_bfloat16* __restrict__ A,
+                                                          int N, int K, int mode, float* __restrict__ out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_tma, bar_mma;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nchunk = K / 64;
+  const int ntail = (K % 64) / 16;                     // mode 2 only: 16-wide K steps past the last full chunk, SWIZZLE_32B boxes
   uint8_t* sB = smem;                                  // nchunk x [N rows x 128 B]
-  uint8_t* sA = smem + (size_t)nchunk * N * 128;       // nchunk x [128 rows x 128 B]  (mode 0)
+  uint8_t* sBt = smem + (size_t)nchunk * N * 128;      // ntail x [N rows x 32 B]
+  uint8_t* sA = sBt + (size_t)ntail * N * 32;          // nchunk x [128 rows x 128 B]  (mode 0)
   sA = (uint8_t*)(((uintptr_t)sA + 1023) & ~(uintptr_t)1023);
   if (warp == 0) tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
@@ -72,14 +75,15 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const __grid_constant_
   const uint32_t tmem_base = tmem_base_s;
   const uint32_t acc_col = 0, a_col = 256;
   if (tid == 0) {
-    uint32_t bytes = (uint32_t)nchunk * N * 128 + (mode == 0 ? (uint32_t)nchunk * 128 * 128 : 0u);
+    uint32_t bytes = (uint32_t)nchunk * N * 128 + (uint32_t)ntail * N * 32 + (mode == 0 ? (uint32_t)nchunk * 128 * 128 : 0u);
     mbar_arrive_expect_tx(&bar_tma, bytes);
     for (int c = 0; c < nchunk; ++c) {
       tma_load_2d(sB + (size_t)c * N * 128, &tmB, c * 64, 0, &bar_tma);
       if (mode == 0) tma_load_2d(sA + (size_t)c * 128 * 128, &tmA, c * 64, 0, &bar_tma);
     }
+    for (int t = 0; t < ntail; ++t) tma_load_2d(sBt + (size_t)t * N * 32, &tmBt, nchunk * 64 + t * 16, 0, &bar_tma);
   }
-  if (mode == 1) {
+  if (mode >= 1) {
     // thread = row; pack (k, k+1) pairs into 32-bit columns
     const int row = tid;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
@@ -101,7 +105,8 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const __grid_constant_
     const uint32_t idesc = make_idesc_bf16(128, N);
     for (int ks = 0; ks < K / 16; ++ks) {
       int c = ks / 4, o = (ks % 4) * 32;
-      uint64_t bdesc = make_desc_k_sw128(smem_u32(sB + (size_t)c * N * 128) + o);
+      uint64_t bdesc = c < nchunk ? make_desc_k_sw128(smem_u32(sB + (size_t)c * N * 128) + o)
+                                  : make_desc_k_sw32(smem_u32(sBt + (size_t)(ks - nchunk * 4) * N * 32));
       if (mode == 0) {
         uint64_t adesc = make_desc_k_sw128(smem_u32(sA + (size_t)c * 128 * 128) + o);
         umma_ss(tmem_base + acc_col, adesc, bdesc, idesc, ks > 0);
@@ -130,17 +135,21 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const __grid_constant_
   (void)lane;
 }
 
-// A [128, K] bf16 row-major, Bm [N, K] bf16 row-major (both device), out [128, N] fp32; K % 64 == 0, N % 16 == 0, N <= 256, K <= 256
+// A [128, K] bf16 row-major, Bm [N, K] bf16 row-major (both device), out [128, N] fp32; N % 16 == 0, N <= 256, K <= 256;
+// modes 0 / 1: K % 64 == 0; mode 2 (A in TMEM, K tail of B in SWIZZLE_32B boxes): K % 16 == 0
 extern "C" int xdfm_tc_selftest_gemm(const void* A, const void* Bm, int N, int K, int mode, float* out, void* stream) {
-  XDFM_CHECK_ARG(N % 16 == 0 && N >= 16 && N <= 256 && K % 64 == 0 && K >= 64 && K <= 256, "tc_selftest: bad N=%d K=%d", N, K);
-  CUtensorMap tmA, tmB;
+  XDFM_CHECK_ARG(N % 16 == 0 && N >= 16 && N <= 256 && K >= 16 && K <= 256 && (mode == 2 ? K % 16 == 0 : (K % 64 == 0)),
+                 "tc_selftest: bad N=%d K=%d mode=%d", N, K, mode);
+  CUtensorMap tmA, tmB, tmBt;
   int rc = xdfm_make_tmap_bf16_sw128(&tmA, A, 128, K, (uint64_t)K * 2, 128);
   if (rc) return rc;
   rc = xdfm_make_tmap_bf16_sw128(&tmB, Bm, N, K, (uint64_t)K * 2, N);
   if (rc) return rc;
-  size_t sm = (size_t)(K / 64) * N * 128 + (size_t)(K / 64) * 128 * 128 + 2048;
+  rc = xdfm_make_tmap_bf16(&tmBt, Bm, N, K, (uint64_t)K * 2, N, 16, 2);
+  if (rc) return rc;
+  size_t sm = (size_t)(K / 64) * N * 128 + (size_t)((K % 64) / 16) * N * 32 + (size_t)(K / 64) * 128 * 128 + 2048;
   XDFM_CUDA(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  tc_selftest_kernel<<<1, 128, sm, (cudaStream_t)stream>>>(tmA, tmB, (const __nv_bfloat16*)A, N, K, mode, out);
+  tc_selftest_kernel<<<1, 128, sm, (cudaStream_t)stream>>>(tmA, tmB, tmBt, (const __nv_bfloat16*)A, N, K, mode, out);
   XDFM_LAUNCH_CHECK();
   return XDFM_OK;
 }
