@@ -26,6 +26,9 @@ def run(B, m, D, H, Hp, dbg, reps=5):
         if r >= 2: ts.append(e0.elapsed_time(e1))
     L.xdfm_cin_dx_set_debug(0)
     print("dX Hp=%d debug=%d: %.3f ms" % (Hp, dbg, sorted(ts)[len(ts)//2]), flush=True)
+if os.environ.get("DX_ONLY"):
+    run(8192, 26, 16, 200, int(os.environ["DX_ONLY"]), 0)
+    sys.exit(0)
 for Hp in (100, 26):
     for dbg in (0, 1, 2, 3, 4, 7):
         run(8192, 26, 16, 200, Hp, dbg)

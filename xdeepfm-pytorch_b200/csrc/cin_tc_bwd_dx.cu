@@ -45,8 +45,7 @@ struct CinDxParams {
   int ns;                     // W'' ring depth (one slot = one FIELD on one barrier)
   // single-tile kernel: a slot holds the field's n_full 64-wide h-chunks ([HpQ rows x 128 B], SWIZZLE_128B) followed by tail_ks
   // 16-wide chunks ([HpQ rows x 32 B], SWIZZLE_32B) -- H_pad = 64 n_full + 16 tail_ks, nothing zero-padded is streamed
-  int n_full, tail_ks;
-  uint32_t slot_stride;       // bytes between slots (slot bytes rounded up to 1024)
+  int n_full, tail_ks;        // the ring keeps the full chunks of all slots first (1024-byte aligned), then the tails (256-byte aligned)
 };
 
 struct __align__(8) CinDxBars {
@@ -65,18 +64,20 @@ __global__ void __launch_bounds__((2 + 4 * NG) * 32, 1)
 cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWt, CinDxParams p) {
   constexpr int HpQ = NQ * 16;
   constexpr int HALF = HpQ / NG;                   // channels per row warp (multiple of 4)
-  constexpr int NPL = NG == 2 ? 1 : NG;            // dX0 partial planes: the two channel groups share one (two addends commute)
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t w_box_bytes = (uint32_t)HpQ * 128;                          // one 64-wide h-chunk of one field
   const uint32_t w_tail_bytes = (uint32_t)HpQ * 32;                          // one 16-wide h-chunk of the tail
-  const uint32_t w_slot_bytes = w_box_bytes * (uint32_t)p.n_full + w_tail_bytes * (uint32_t)p.tail_ks;   // bytes TMA delivers per field
-  uint8_t* sW = smem;                                                         // ns slots, slot_stride apart
+  const uint32_t full_stride = w_box_bytes * (uint32_t)p.n_full;             // a slot's full chunks
+  const uint32_t tail_stride = w_tail_bytes * (uint32_t)p.tail_ks;           // a slot's tail chunks
+  const uint32_t w_slot_bytes = full_stride + tail_stride;                    // bytes TMA delivers per field
+  uint8_t* sW = smem;                                                         // ns x full chunks
+  uint8_t* sWt = sW + (size_t)p.ns * full_stride;                             // ns x tail chunks
   const uint32_t x0_tile = (uint32_t)128 * p.mP * 2;
-  uint8_t* sX0 = sW + (size_t)p.ns * p.slot_stride;                           // 2 x [128][mP] bf16
-  const int dpitch = p.mP + 1;                                                // odd pitch: a warp's 32 rows hit 32 different banks
-  float* sDx0 = reinterpret_cast<float*>(sX0 + 2 * (size_t)x0_tile);          // [NPL][128][mP + 1] fp32 dX0 partials
-  CinDxBars* bars = reinterpret_cast<CinDxBars*>(sDx0 + ((NPL * 128 * dpitch + 1) & ~1));
+  uint8_t* sX0 = sWt + (size_t)p.ns * tail_stride;                            // 2 x [128][mP] bf16
+  const int dpitch = p.m | 1;                                                 // odd pitch: a warp's 32 rows hit 32 different banks
+  float* sDx0 = reinterpret_cast<float*>(sX0 + 2 * (size_t)x0_tile);          // [NG groups][128][dpitch] fp32 dX0 partials
+  CinDxBars* bars = reinterpret_cast<CinDxBars*>(sDx0 + ((NG * 128 * dpitch + 1) & ~1));
 
   const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
   const uint16_t cmask = (uint16_t)((1u << csize) - 1);
@@ -90,8 +91,6 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
     }
     fence_barrier_init();
   }
-  if (NG == 2)
-    for (int i = threadIdx.x; i < 128 * dpitch; i += blockDim.x) sDx0[i] = 0.f;
   if (warp == 1) tmem_alloc(&bars->tmem_base, 512);
   fence_before_sync();
   __syncthreads();
@@ -125,14 +124,13 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
         for (int j = 0; j < p.m; ++j) {
           if (!first_pass) mbar_wait(&bars->w_empty[ws], wphase);
           mbar_arrive_expect_tx(&bars->w_full[ws], w_slot_bytes);
-          uint8_t* slot = sW + (size_t)ws * p.slot_stride;
           for (int c = 0; c < p.n_full; ++c) {
-            uint8_t* dst = slot + (size_t)c * w_box_bytes + (size_t)wr0 * 128;
+            uint8_t* dst = sW + (size_t)ws * full_stride + (size_t)c * w_box_bytes + (size_t)wr0 * 128;
             if (csize > 1) tma_load_2d_mcast(dst, &tmW, c * 64, j * HpQ + wr0, &bars->w_full[ws], cmask);
             else tma_load_2d(dst, &tmW, c * 64, j * HpQ + wr0, &bars->w_full[ws]);
           }
           for (int t = 0; t < p.tail_ks; ++t) {
-            uint8_t* dst = slot + (size_t)p.n_full * w_box_bytes + (size_t)t * w_tail_bytes + (size_t)wr0 * 32;
+            uint8_t* dst = sWt + (size_t)ws * tail_stride + (size_t)t * w_tail_bytes + (size_t)wr0 * 32;
             if (csize > 1) tma_load_2d_mcast(dst, &tmWt, p.n_full * 64 + t * 16, j * HpQ + wr0, &bars->w_full[ws], cmask);
             else tma_load_2d(dst, &tmWt, p.n_full * 64 + t * 16, j * HpQ + wr0, &bars->w_full[ws]);
           }
@@ -144,8 +142,9 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
     // =============================== MMA issuer (warp-uniform loop, elected lane issues) ===============================
     const uint32_t idesc = make_idesc_bf16(128, HpQ);
     const uint64_t bdesc0 = make_desc_k_sw128(smem_u32(sW));
-    const uint64_t tdesc0 = make_desc_k_sw32(smem_u32(sW) + (uint32_t)p.n_full * w_box_bytes);
-    const uint32_t slot_desc_step = p.slot_stride >> 4;
+    const uint64_t tdesc0 = make_desc_k_sw32(smem_u32(sWt));
+    const uint32_t slot_desc_step = full_stride >> 4;
+    const uint32_t tslot_desc_step = tail_stride >> 4;
     const uint32_t box_desc_step = w_box_bytes >> 4;
     const uint32_t tail_desc_step = w_tail_bytes >> 4;
     uint32_t ws = 0, wphase = 0;
@@ -188,7 +187,7 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
         }
         __syncwarp();
         if (++ws == (uint32_t)p.ns) { ws = 0; wphase ^= 1; bdesc = bdesc0; tdesc = tdesc0; }
-        else { bdesc += slot_desc_step; tdesc += slot_desc_step; }
+        else { bdesc += slot_desc_step; tdesc += tslot_desc_step; }
         if (active) ++jc;
       }
       if (active) {
@@ -267,30 +266,40 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
       __nv_bfloat162 xk2[HALF / 2];
       {
         const __nv_bfloat16* xr = p.xkt + row * p.xk_pitch + half * HALF;
+        if constexpr (HALF % 8 == 0) {
 #pragma unroll
-        for (int v4 = 0; v4 < HALF / 4; ++v4) {
-          uint2 t = make_uint2(0u, 0u);
-          if (valid && half * HALF + v4 * 4 < p.xk_pitch) t = *reinterpret_cast<const uint2*>(xr + v4 * 4);
-          xk2[v4 * 2 + 0] = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
-          xk2[v4 * 2 + 1] = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+          for (int v8 = 0; v8 < HALF / 8; ++v8) {
+            uint4 t = make_uint4(0u, 0u, 0u, 0u);
+            if (valid && half * HALF + v8 * 8 < p.xk_pitch) t = *reinterpret_cast<const uint4*>(xr + v8 * 8);   // xk_pitch multiple of 8
+            xk2[v8 * 4 + 0] = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
+            xk2[v8 * 4 + 1] = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+            xk2[v8 * 4 + 2] = *reinterpret_cast<const __nv_bfloat162*>(&t.z);
+            xk2[v8 * 4 + 3] = *reinterpret_cast<const __nv_bfloat162*>(&t.w);
+          }
+        } else {
+#pragma unroll
+          for (int v4 = 0; v4 < HALF / 4; ++v4) {
+            uint2 t = make_uint2(0u, 0u);
+            if (valid && half * HALF + v4 * 4 < p.xk_pitch) t = *reinterpret_cast<const uint2*>(xr + v4 * 4);
+            xk2[v4 * 2 + 0] = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
+            xk2[v4 * 2 + 1] = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+          }
         }
       }
       float dxk[HALF];
 #pragma unroll
       for (int i = 0; i < HALF; ++i) dxk[i] = 0.f;
+      float x0n = __bfloat162float(x0row[0]);
       for (int j = 0; j < p.m; ++j, ++jc) {
         const uint32_t ab = jc & 1;
-        const float x0v = __bfloat162float(x0row[j]);
+        const float x0v = x0n;
+        if (j + 1 < p.m) x0n = __bfloat162float(x0row[j + 1]);       // next field's scale: its shared-memory latency hides behind this field
         if (pipe && j <= ngr) {
           if (j >= 1) {                               // granule j - 1 was loaded one field ago
             const uint32_t v4[4] = {pg.x, pg.y, pg.z, pg.w};
             tmem_st_x4(tmem_base + lane_addr + nbuf * 128 + c_beg + (j - 1) * 4, v4);
           }
-          if (j < ngr) {
-            const int c = c_beg + j * 4;
-            pg = make_uint4(0u, 0u, 0u, 0u);
-            if (nvalid && c * 2 < p.Hs) pg = *reinterpret_cast<const uint4*>(nsrc + c);
-          } else {                                    // j == ngr: this warp's share of the next A tile is complete
+          if (j == ngr) {                             // this warp's share of the next A tile is complete
             tmem_wait_st();
             fence_before_sync();
             __syncwarp();
@@ -336,6 +345,14 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
             fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->acc_empty[ab]);
+            // the next tile's dY granule is requested only now: the arrive above has release semantics and waits for every
+            // outstanding memory operation of the thread (ncu, round 1: 8 % of the kernel's samples were that MEMBAR with the
+            // load in flight)
+            if (pipe && j < ngr) {
+              const int c = c_beg + j * 4;
+              pg = make_uint4(0u, 0u, 0u, 0u);
+              if (nvalid && c * 2 < p.Hs) pg = *reinterpret_cast<const uint4*>(nsrc + c);
+            }
           }
           if (!(p.debug & 1)) {
 #pragma unroll
@@ -357,8 +374,7 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
         }
         dot = (d4[0] + d4[1]) + (d4[2] + d4[3]);
         // dX0[r, j] partial of this warp's channel group: parked in shared memory (plane = group), combined in group order at tile end
-        if (NG == 2) atomicAdd(&sDx0[rl * dpitch + j], dot);      // zeroed plane + two addends (the channel groups): order-independent
-        else sDx0[(half * 128 + rl) * dpitch + j] = dot;
+        sDx0[(half * 128 + rl) * dpitch + j] = dot;
       }
       staged = pipe;
       // ---- tile outputs
@@ -368,9 +384,6 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
         for (int i = 0; i < HALF; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(dxk[i], dxk[i + 1], dxk[i + 2], dxk[i + 3]);
       }
       asm volatile("bar.sync 1, %0;" ::"n"(128 * NG) : "memory");     // all groups' dX0 partials are in shared memory
-      if (!valid && NG == 2) {                      // rows past R: nothing to write, but the shared plane must be clean again
-        for (int j = half; j < p.m; j += NG) sDx0[rl * dpitch + j] = 0.f;
-      }
       if (valid) {
         // dx0 row += the groups' partials (summed in group order): 128-bit accesses, all loads of a pass in flight before the first
         // add (the scalar load -> add -> store chain this replaces cost one L2 round trip per field at every tile end); the
@@ -394,9 +407,8 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                 const int j = i * 4 + t;
                 if (j < p.m) {
                   float sacc = sDx0[rl * dpitch + j];
-                  if (NG == 2) sDx0[rl * dpitch + j] = 0.f;                  // ready for the next tile's atomics
 #pragma unroll
-                  for (int gq = 1; gq < NPL; ++gq) sacc += sDx0[(gq * 128 + rl) * dpitch + j];
+                  for (int gq = 1; gq < NG; ++gq) sacc += sDx0[(gq * 128 + rl) * dpitch + j];
                   a[t] += sacc;
                 }
               }
@@ -729,9 +741,13 @@ static int round_up_i(int a, int b) { return (a + b - 1) / b * b; }
 struct CinDxGeom {
   int HpQ, H_pad, Hs, mP, HC, n_hchunks, ns;
   int n_full, tail_ks;
-  uint32_t slot_stride;
+  size_t slot;                // bytes of one ring slot (one field, unpadded)
   size_t smem;
 };
+
+static size_t cin_dx_fixed_smem(int m, int mP, int groups) {
+  return 2 * (size_t)128 * mP * 2 + (size_t)groups * 128 * (m | 1) * 4 + 8 + sizeof(CinDxBars) + 256;
+}
 
 static int cin_dx_geom(int m, int Hp, int H, int D, CinDxGeom* g) {
   if (!(D == 8 || D == 16 || D == 32 || D == 64 || D == 128) || Hp > 128 || H > 256 || m > XDFM_MAX_FIELDS) {
@@ -746,9 +762,9 @@ static int cin_dx_geom(int m, int Hp, int H, int D, CinDxGeom* g) {
   g->HC = g->n_hchunks * 64;
   g->n_full = g->H_pad / 64;
   g->tail_ks = (g->H_pad % 64) / 16;
-  size_t fixed = 2 * (size_t)128 * g->mP * 2 + (size_t)128 * (g->mP + 1) * 4 + sizeof(CinDxBars) + 256;     // one shared dX0 plane (NG = 2)
-  size_t slot = ((size_t)g->HpQ * 128 * g->n_full + (size_t)g->HpQ * 32 * g->tail_ks + 1023) / 1024 * 1024;   // one field
-  g->slot_stride = (uint32_t)slot;
+  size_t fixed = cin_dx_fixed_smem(m, g->mP, 2);
+  size_t slot = (size_t)g->HpQ * 128 * g->n_full + (size_t)g->HpQ * 32 * g->tail_ks;      // one field
+  g->slot = slot;
   int ns = (int)std::min<size_t>((227 * 1024 - fixed) / slot, DX_MAX_NS * 1);
   ns = std::min(ns, DX_MAX_NS);
   if (ns < 2) {
@@ -846,7 +862,7 @@ extern "C" int xdfm_cin_bwd_dx_tc(const void* dyt, const void* x0t, const void* 
   if (rc) return rc;
   const int64_t R = B * (int64_t)D;
   CinDxParams p;
-  p.n_full = g.n_full; p.tail_ks = g.tail_ks; p.slot_stride = g.slot_stride;
+  p.n_full = g.n_full; p.tail_ks = g.tail_ks;
   p.dyt = (const __nv_bfloat16*)dyt; p.x0t = (const __nv_bfloat16*)x0t; p.xkt = (const __nv_bfloat16*)xkt; p.dxk = dxk; p.dx0 = dx0;
   p.R = R; p.xk_pitch = xk_pitch; p.m = m; p.mP = g.mP; p.Hp = Hp; p.HpQ = g.HpQ; p.H = H; p.H_pad = g.H_pad; p.Hs = g.Hs;
   p.n_tiles = ceil_div64(R, 128); p.n_hchunks = g.n_hchunks; p.ns = g.ns; p.debug = g_cin_dx_debug;
@@ -874,8 +890,8 @@ extern "C" int xdfm_cin_bwd_dx_tc(const void* dyt, const void* x0t, const void* 
   }
   if (g_cin_dx_groups == 4) {
     // four row warps per lane quarter: one dX0 partial plane per group in shared memory
-    const size_t slot = g.slot_stride;
-    const size_t fixed4 = 2 * (size_t)128 * g.mP * 2 + 4 * (size_t)128 * (g.mP + 1) * 4 + sizeof(CinDxBars) + 256;
+    const size_t slot = g.slot;
+    const size_t fixed4 = cin_dx_fixed_smem(m, g.mP, 4);
     int ns4 = (227 * 1024 > fixed4) ? (int)std::min<size_t>((227 * 1024 - fixed4) / slot, DX_MAX_NS) : 0;
     if (ns4 >= 2) {
       CinDxParams p4 = p;
