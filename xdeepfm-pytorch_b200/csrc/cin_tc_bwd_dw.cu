@@ -233,21 +233,49 @@ __global__ void cin_dw_reduce_tc_kernel(const float* __restrict__ part, int S, i
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) rows_to_cols_bf16_kernel(const __nv_bfloat16* __restrict__ src, int64_t pitch, int64_t R, int C, int CP,
                                                                 __nv_bfloat16* __restrict__ dst) {
-  __shared__ __nv_bfloat16 tile[64][66];
+  __shared__ __align__(16) __nv_bfloat16 tile[64][72];       // 144-byte rows: 16-byte aligned granules
   const int64_t r0 = (int64_t)blockIdx.x * 64;
   const int c0 = blockIdx.y * 64;
-  for (int e = threadIdx.x; e < 64 * 64; e += 256) {
-    const int rr = e >> 6, cc = e & 63;
+  const bool vec = ((pitch & 7) == 0) && (((uintptr_t)src & 15) == 0);
+  {
+    // 16-byte granules of a source row (8 channels); channels >= C read as zero
+    const int rr = threadIdx.x >> 2, cg = (threadIdx.x & 3) * 16;
     const int64_t r = r0 + rr;
-    const int c = c0 + cc;
-    tile[rr][cc] = (r < R && c < C) ? src[r * pitch + c] : __float2bfloat16(0.f);
+#pragma unroll
+    for (int g8 = 0; g8 < 2; ++g8) {
+      const int c = c0 + cg + g8 * 8;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (r < R && c < C) {
+        if (vec && c + 8 <= C) {
+          v = *reinterpret_cast<const uint4*>(src + r * pitch + c);
+        } else {
+          __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(&v);
+          for (int i = 0; i < 8; ++i)
+            if (c + i < C) e[i] = src[r * pitch + c + i];
+        }
+      }
+      *reinterpret_cast<uint4*>(&tile[rr][cg + g8 * 8]) = v;
+    }
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < 64 * 64; e += 256) {
-    const int cc = e >> 6, rr = e & 63;
-    const int64_t r = r0 + rr;
+  {
+    // lanes walk the channel axis (conflict-free column reads), each thread writes 16 consecutive rows of one channel
+    const int cc = threadIdx.x & 63, rg = (threadIdx.x >> 6) * 16;
     const int c = c0 + cc;
-    if (r < R && c < CP) dst[(int64_t)c * R + r] = tile[rr][cc];
+    if (c < CP) {
+      __align__(16) __nv_bfloat16 col[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) col[i] = tile[rg + i][cc];
+      const int64_t r = r0 + rg;
+      __nv_bfloat16* d = dst + (int64_t)c * R + r;
+      if (r + 16 <= R && ((R & 7) == 0) && (((uintptr_t)dst & 15) == 0)) {
+        *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(&col[0]);
+        *reinterpret_cast<uint4*>(d + 8) = *reinterpret_cast<const uint4*>(&col[8]);
+      } else {
+        for (int i = 0; i < 16; ++i)
+          if (r + i < R) d[i] = col[i];
+      }
+    }
   }
 }
 
@@ -264,7 +292,39 @@ __global__ void __launch_bounds__(256) cin_db_cols_kernel(const __nv_bfloat16* _
   const int h = blockIdx.x;
   const __nv_bfloat16* row = dyT + (int64_t)h * R;
   float acc = 0.f;
-  for (int64_t r = threadIdx.x; r < R; r += 256) acc += __bfloat162float(row[r]);
+  if ((R & 7) == 0 && ((uintptr_t)row & 15) == 0) {
+    // 16-byte granules, four in flight per thread; the order of the additions is a fixed function of R
+    const uint4* row4 = reinterpret_cast<const uint4*>(row);
+    const int64_t n4 = R >> 3;
+    int64_t g = threadIdx.x;
+    for (; g + 3 * 256 < n4; g += 4 * 256) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = row4[g + u * 256];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&v[u]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(b2[i]);
+          acc += f.x;
+          acc += f.y;
+        }
+      }
+    }
+    for (; g < n4; g += 256) {
+      const uint4 v = row4[g];
+      const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(b2[i]);
+        acc += f.x;
+        acc += f.y;
+      }
+    }
+  } else {
+    for (int64_t r = threadIdx.x; r < R; r += 256) acc += __bfloat162float(row[r]);
+  }
   __shared__ float red[256];
   red[threadIdx.x] = acc;
   __syncthreads();

@@ -46,12 +46,13 @@ struct CinDxParams {
   // single-tile kernel: a slot holds the field's n_full 64-wide h-chunks ([HpQ rows x 128 B], SWIZZLE_128B) followed by tail_ks
   // 16-wide chunks ([HpQ rows x 32 B], SWIZZLE_32B) -- H_pad = 64 n_full + 16 tail_ks, nothing zero-padded is streamed
   int n_full, tail_ks;        // the ring keeps the full chunks of all slots first (1024-byte aligned), then the tails (256-byte aligned)
+  int na_shift;               // log2 of the number of dZ accumulators in flight: 2 x 128 columns, or 4 x 64 when HpQ <= 64
 };
 
 struct __align__(8) CinDxBars {
   uint64_t w_full[DX_MAX_NS], w_empty[DX_MAX_NS];
   uint64_t a_full[2], a_empty[2];    // dY tiles in TMEM (count 4 * NG / 1)
-  uint64_t acc_full[2], acc_empty[2];
+  uint64_t acc_full[4], acc_empty[4];
   uint64_t x_full[2], x_empty[2];
   uint32_t tmem_base;
 };
@@ -84,9 +85,9 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < DX_MAX_NS; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], csize); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 4 * NG); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->a_full[i], 4 * NG); mbar_init(&bars->a_empty[i], 1);
-      mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 4 * NG);
       mbar_init(&bars->x_full[i], 1);   mbar_init(&bars->x_empty[i], 4 * NG);
     }
     fence_barrier_init();
@@ -149,9 +150,10 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
     const uint32_t tail_desc_step = w_tail_bytes >> 4;
     uint32_t ws = 0, wphase = 0;
     uint64_t bdesc = bdesc0, tdesc = tdesc0;
-    uint32_t jc = 0;            // fields processed so far (accumulator buffer = jc & 1)
+    uint32_t jc = 0;            // fields processed so far (accumulator buffer = jc & na_mask)
     int at = 0;
     const int ksteps = p.n_full * 4;
+    const uint32_t na_mask = (1u << p.na_shift) - 1, acc_stride = 256u >> p.na_shift;
     for (int it = 0; it < p.n_iters; ++it) {
       const bool active = tile_of(it) < p.n_tiles;
       const uint32_t abuf = (uint32_t)(at & 1);
@@ -161,16 +163,16 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
         fence_after_sync();
       }
       for (int j = 0; j < p.m; ++j) {
-        const uint32_t ab = jc & 1;
-        if (active && jc >= 2) {
-          mbar_wait(&bars->acc_empty[ab], ((jc >> 1) - 1) & 1);
+        const uint32_t ab = jc & na_mask;
+        if (active && jc > na_mask) {
+          mbar_wait(&bars->acc_empty[ab], ((jc >> p.na_shift) - 1) & 1);
           fence_after_sync();
         }
         mbar_wait(&bars->w_full[ws], wphase);
         fence_after_sync();
         if (elect_one()) {
           if (active && !(p.debug & 4)) {
-            const uint32_t d_addr = tmem_base + DX_ACC_COL0 + ab * DX_ACC_COLS;
+            const uint32_t d_addr = tmem_base + DX_ACC_COL0 + ab * acc_stride;
             uint64_t bd = bdesc;
             for (int ks = 0; ks < ksteps; ks += 4, bd += box_desc_step) {
 #pragma unroll
@@ -204,6 +206,7 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     uint32_t jc = 0;
     int at = 0;
+    const uint32_t na_mask = (1u << p.na_shift) - 1, acc_stride = 256u >> p.na_shift;
     bool staged = false;        // this tile's dY already sits in TMEM (staged while the previous tile was drained)
     for (int it = 0; it < p.n_iters; ++it) {
       const int64_t tile = tile_of(it);
@@ -291,7 +294,7 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
       for (int i = 0; i < HALF; ++i) dxk[i] = 0.f;
       float x0n = __bfloat162float(x0row[0]);
       for (int j = 0; j < p.m; ++j, ++jc) {
-        const uint32_t ab = jc & 1;
+        const uint32_t ab = jc & na_mask;
         const float x0v = x0n;
         if (j + 1 < p.m) x0n = __bfloat162float(x0row[j + 1]);       // next field's scale: its shared-memory latency hides behind this field
         if (pipe && j <= ngr) {
@@ -306,9 +309,9 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
             if (lane == 0) mbar_arrive(&bars->a_full[nbuf]);
           }
         }
-        mbar_wait(&bars->acc_full[ab], (jc >> 1) & 1);
+        mbar_wait(&bars->acc_full[ab], (jc >> p.na_shift) & 1);
         fence_after_sync();
-        const uint32_t acc = tmem_base + lane_addr + DX_ACC_COL0 + ab * DX_ACC_COLS + half * HALF;
+        const uint32_t acc = tmem_base + lane_addr + DX_ACC_COL0 + ab * acc_stride + half * HALF;
         float dot = 0.f;
         // this warp's dZ columns of the field in NB batches of TMEM loads (one wait each): one batch when the columns fit the register
         // budget next to the dXk accumulators, two otherwise (round 1: at HALF = 56 a single 56-register batch spilled the X^{k-1}
@@ -863,6 +866,7 @@ extern "C" int xdfm_cin_bwd_dx_tc(const void* dyt, const void* x0t, const void* 
   const int64_t R = B * (int64_t)D;
   CinDxParams p;
   p.n_full = g.n_full; p.tail_ks = g.tail_ks;
+  p.na_shift = g.HpQ <= 64 ? 2 : 1;
   p.dyt = (const __nv_bfloat16*)dyt; p.x0t = (const __nv_bfloat16*)x0t; p.xkt = (const __nv_bfloat16*)xkt; p.dxk = dxk; p.dx0 = dx0;
   p.R = R; p.xk_pitch = xk_pitch; p.m = m; p.mP = g.mP; p.Hp = Hp; p.HpQ = g.HpQ; p.H = H; p.H_pad = g.H_pad; p.Hs = g.Hs;
   p.n_tiles = ceil_div64(R, 128); p.n_hchunks = g.n_hchunks; p.ns = g.ns; p.debug = g_cin_dx_debug;

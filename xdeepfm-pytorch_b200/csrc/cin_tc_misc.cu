@@ -122,6 +122,21 @@ __global__ void __launch_bounds__(256) cin_dy_rows_cols_kernel(const __nv_bfloat
       if (r < R && h0 < Hs) {
         const uint4 yv = *reinterpret_cast<const uint4*>(yt + r * Hs + h0);
         const __nv_bfloat16* yb = reinterpret_cast<const __nv_bfloat16*>(&yv);
+        // next layer's input gradient for these 8 channels: two 128-bit loads when the whole granule lies inside it
+        float dn[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dn[i] = 0.f;
+        if (dnext != nullptr && h0 < n_next) {
+          const float* dsrc = dnext + r * dnext_pitch + h0;
+          if (h0 + 8 <= n_next && (dnext_pitch & 3) == 0) {
+            const float4 a = *reinterpret_cast<const float4*>(dsrc), c = *reinterpret_cast<const float4*>(dsrc + 4);
+            dn[0] = a.x; dn[1] = a.y; dn[2] = a.z; dn[3] = a.w; dn[4] = c.x; dn[5] = c.y; dn[6] = c.z; dn[7] = c.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (h0 + i < n_next) dn[i] = dsrc[i];
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int h = h0 + i;
@@ -131,7 +146,7 @@ __global__ void __launch_bounds__(256) cin_dy_rows_cols_kernel(const __nv_bfloat
               if (dpooled) v += dpooled[b * fm_total + col_off + (h - hdb)];
               if (dmaps) v += dmaps[(b * fm_total + col_off + (h - hdb)) * (int64_t)D + d];
             }
-            if (h < n_next && dnext) v += dnext[r * dnext_pitch + h];
+            v += dn[i];
             if (act == XDFM_ACT_RELU && !(__bfloat162float(yb[i]) > 0.f)) v = 0.f;
           }
           g[i] = v;
@@ -148,7 +163,8 @@ __global__ void __launch_bounds__(256) cin_dy_rows_cols_kernel(const __nv_bfloat
   }
   __syncthreads();
   {
-    const int cc = threadIdx.x >> 2, rg = (threadIdx.x & 3) * 16;
+    // lanes walk the channel axis (consecutive 2-byte columns of a tile row: conflict-free), warps pairs the four 16-row groups
+    const int cc = threadIdx.x & 63, rg = (threadIdx.x >> 6) * 16;
     const int c = c0 + cc;
     if (c < H_pad) {
       __align__(16) __nv_bfloat16 col[16];

@@ -402,12 +402,14 @@ class CINFunctionTC(torch.autograd.Function):
             xkt = x0t if k == 0 else yts[k - 1]
             dyt = torch.empty_like(yt)
             dyT = torch.empty((H_pad, R), dtype=torch.bfloat16, device=dev)
-            xkT = torch.empty((HpQ, R), dtype=torch.bfloat16, device=dev)
+            reuse_x0T = k == 0 and HpQ == mP        # layer 0: X^{k-1} is X^0 itself and the channel-major copy already exists
+            xkT = x0T if reuse_x0T else torch.empty((HpQ, R), dtype=torch.bfloat16, device=dev)
             with timed("cin_layout"):
                 N.check(L.xdfm_cin_dy_rows_cols(N.ptr(yt), B, D, H, Hs, H_pad, cfg.direct_begin[k], N.ptr(dout) if cfg.pool else None,
                                                 None if cfg.pool else N.ptr(dout), cfg.fm, cfg.col_off[k], N.ptr(dnext), dnext_pitch,
                                                 cfg.n_next[k], cfg.act, N.ptr(dyt), N.ptr(dyT), st))
-                N.check(L.xdfm_rows_to_cols_bf16(N.ptr(xkt), xkt.shape[1], R, Hp, HpQ, N.ptr(xkT), st))
+                if not reuse_x0T:
+                    N.check(L.xdfm_rows_to_cols_bf16(N.ptr(xkt), xkt.shape[1], R, Hp, HpQ, N.ptr(xkT), st))
             W = _f32c(wb[2 * k]).view(H, -1)
             dW = torch.empty_like(W)
             db = torch.empty(H, dtype=torch.float32, device=dev)
