@@ -90,15 +90,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
     }
   } else {
+    // ---- epilogue (4 warps): TMEM -> (+bias, activation) -> shared-memory tile -> global memory, whole rows at a time.
+    // A thread owns one accumulator ROW; writing it straight to global memory touches 32 different rows per store instruction
+    // (one 4-byte piece of 32 sectors each).  The operand ring is free once the accumulator is complete, so the tile is staged
+    // there (pitch BN + 4 floats: conflict-free 128-bit stores) and every warp then streams complete rows, lane-contiguous.
     const int q = warp & 3;                       // TMEM lane quarter of this warp
-    const int row = m0 + q * 32 + lane;
+    const int rl = q * 32 + lane;                 // row of the tile owned by this thread
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     if (nchunks > 0) {
-      mbar_wait(&bars->acc_full, 0);
+      mbar_wait(&bars->acc_full, 0);              // every MMA has completed: the ring is no longer read, all TMA loads have landed
       fence_after_sync();
     }
-    float* dst = nullptr;
-    if (row < p.M) dst = p.splits > 1 ? p.partial + ((size_t)split * p.M + row) * p.N : p.C + (size_t)row * p.ldc;
+    float* stile = reinterpret_cast<float*>(smem);
+    const int pitch = p.BN + 4;
+    const bool fin = p.splits == 1;
     for (int c0 = 0; c0 < p.BN; c0 += 16) {
       uint32_t v[16];
       if (nchunks > 0) {
@@ -108,18 +113,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = 0u;
       }
-      if (dst == nullptr) continue;
+      float y[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int col = n0 + c0 + i;
-        if (col < p.N) {
-          float y = __uint_as_float(v[i]);
-          if (p.splits == 1) {
-            if (p.bias != nullptr) y += __ldg(p.bias + col);
-            y = apply_act(y, p.act);
-          }
-          dst[col] = y;
+        float t = __uint_as_float(v[i]);
+        if (fin) {
+          if (p.bias != nullptr && col < p.N) t += __ldg(p.bias + col);
+          t = apply_act(t, p.act);
         }
+        y[i] = t;
+      }
+      float4* d4 = reinterpret_cast<float4*>(stile + (size_t)rl * pitch + c0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) d4[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");         // the four epilogue warps: tile complete
+    const int ncols = min(p.BN, p.N - n0);                  // valid columns of this tile
+    const int64_t ld = p.splits > 1 ? p.N : p.ldc;
+    float* base = p.splits > 1 ? p.partial + (size_t)split * p.M * p.N : p.C;
+    const bool vec = ((ld & 3) == 0) && ((n0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+    for (int rr = q; rr < 128; rr += 4) {
+      const int row = m0 + rr;
+      if (row >= p.M) break;
+      const float* srow = stile + (size_t)rr * pitch;
+      float* drow = base + (size_t)row * ld + n0;
+      if (vec) {
+        for (int c4 = lane; c4 * 4 < ncols; c4 += 32) {
+          const float4 t = *reinterpret_cast<const float4*>(srow + c4 * 4);
+          if (c4 * 4 + 4 <= ncols) {
+            *reinterpret_cast<float4*>(drow + c4 * 4) = t;
+          } else {
+            const float e[4] = {t.x, t.y, t.z, t.w};
+            for (int i = 0; c4 * 4 + i < ncols; ++i) drow[c4 * 4 + i] = e[i];
+          }
+        }
+      } else {
+        for (int c = lane; c < ncols; c += 32) drow[c] = srow[c];
       }
     }
   }
