@@ -268,6 +268,8 @@ def main():
     dev = "cuda:%d" % local_rank
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"        # NCCL prints its version banner on stdout: rank 0's stdout is ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device(dev))
     from deepctr import _native, ops
     from tests.helpers import build_product_model
@@ -380,9 +382,9 @@ def main():
     peak = peaks["tf_sust"]
     roofline = {"bound": "tensor", "kernel": "CIN contraction (cin_fwd + cin_bwd launches, %d per step)" % (cin_calls // max(prof_steps, 1)),
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": 0.813e9 if args.workload == "cfg2" and args.cin_impl == "bf16" else None,
+                "traffic": 0.80e9 if args.workload == "cfg2" and args.cin_impl == "bf16" else None,
                 "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the 9 CIN contraction launches of one step, bytes, from "
-                                "profiles/r01_ncu_full_cfg2.md (ncu --set full); algorithmic HBM bytes of the group ~0.62e9",
+                                "profiles/r01c_ncu_full_cfg2.md (ncu --set full); algorithmic HBM bytes of the group ~0.62e9",
                 "peak_source": "%s MEASURED_PEAKS.json bf16 sustained (kernel timed inside a long step)" % peaks["src"],
                 "share_of_step": (cin_ms / prof_steps) / (ms / args.steps) if ms > 0 else None,
                 "timed_how": "CUDA events around every operator over %d eager steps before the timed region (%.3f ms/step incl. event "

@@ -26,8 +26,37 @@ __device__ __forceinline__ void stage_rows(float* __restrict__ dst, const float*
   }
 }
 
-// HDM = compile-time bound of head_dim (loops are predicated by i < hd)
-template <int HDM>
+// 2^x on the SFU without exp2f's denormal-range wrapper (two predicated multiplies and a compare per call): the arguments here are
+// score differences <= 0 and results below 2^-126 contribute nothing to a softmax sum
+__device__ __forceinline__ float fast_exp2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// One head's slice of a shared-memory row -> registers.  EXACT (head_dim == HDM): 128- / 64-bit loads, no predicates -- with
+// predicated scalar loads the inner loops issued 8 LDS per key and the kernels were bound by the one-LDS-per-clock shared-memory
+// pipe (round 1: 19.4 ms of the 29 ms BASELINE config-3 step).  Otherwise elements >= hd read as zero, so the arithmetic loops
+// can always run over all HDM lanes.
+template <int HDM, bool EXACT>
+__device__ __forceinline__ void load_head(float (&dst)[HDM], const float* __restrict__ src, int hd) {
+  if constexpr (EXACT && HDM % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < HDM / 4; ++i) {
+      const float4 t = reinterpret_cast<const float4*>(src)[i];
+      dst[4 * i] = t.x; dst[4 * i + 1] = t.y; dst[4 * i + 2] = t.z; dst[4 * i + 3] = t.w;
+    }
+  } else if constexpr (EXACT && HDM == 2) {
+    const float2 t = *reinterpret_cast<const float2*>(src);
+    dst[0] = t.x; dst[1] = t.y;
+  } else {
+#pragma unroll
+    for (int i = 0; i < HDM; ++i) dst[i] = i < hd ? src[i] : 0.f;
+  }
+}
+
+// HDM = compile-time bound of head_dim; EXACT = (head_dim == HDM)
+template <int HDM, bool EXACT>
 __global__ void __launch_bounds__(ATT_THREADS) mhsa_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                                const float* __restrict__ v, int L, int E, int nh, int hd,
                                                                float scale_log2e, float* __restrict__ o, float* __restrict__ lse) {
@@ -51,22 +80,23 @@ __global__ void __launch_bounds__(ATT_THREADS) mhsa_fwd_kernel(const float* __re
       const float* kr = sK + h * hd;
       const float* vr = sV + h * hd;
       for (int j = 0; j < L; ++j, kr += E, vr += E) {
+        float kk[HDM], vv[HDM];
+        load_head<HDM, EXACT>(kk, kr, hd);
+        load_head<HDM, EXACT>(vv, vr, hd);
         float d = 0.f;
 #pragma unroll
-        for (int i = 0; i < HDM; ++i)
-          if (i < hd) d = fmaf(qv[i], kr[i], d);
+        for (int i = 0; i < HDM; ++i) d = fmaf(qv[i], kk[i], d);
         if (d > mx) {
-          const float c = exp2f(mx - d);
+          const float c = fast_exp2(mx - d);
           s *= c;
 #pragma unroll
           for (int i = 0; i < HDM; ++i) acc[i] *= c;
           mx = d;
         }
-        const float p = exp2f(d - mx);
+        const float p = fast_exp2(d - mx);
         s += p;
 #pragma unroll
-        for (int i = 0; i < HDM; ++i)
-          if (i < hd) acc[i] = fmaf(p, vr[i], acc[i]);
+        for (int i = 0; i < HDM; ++i) acc[i] = fmaf(p, vv[i], acc[i]);
       }
       const float inv = 1.f / s;
 #pragma unroll
@@ -77,7 +107,7 @@ __global__ void __launch_bounds__(ATT_THREADS) mhsa_fwd_kernel(const float* __re
   }
 }
 
-template <int HDM>
+template <int HDM, bool EXACT>
 __global__ void __launch_bounds__(ATT_THREADS) mhsa_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                                const float* __restrict__ v, const float* __restrict__ o,
                                                                const float* __restrict__ lse, const float* __restrict__ dout, int L, int E,
@@ -116,14 +146,15 @@ __global__ void __launch_bounds__(ATT_THREADS) mhsa_bwd_kernel(const float* __re
       const float* kr = sA + h * hd;
       const float* vr = sB + h * hd;
       for (int j = 0; j < L; ++j, kr += E, vr += E) {
+        float kk[HDM], vv[HDM];
+        load_head<HDM, EXACT>(kk, kr, hd);
+        load_head<HDM, EXACT>(vv, vr, hd);
         float d = 0.f, dp = 0.f;
 #pragma unroll
-        for (int i = 0; i < HDM; ++i)
-          if (i < hd) { d = fmaf(qv[i], kr[i], d); dp = fmaf(dov[i], vr[i], dp); }
-        const float ds = exp2f(d - ls) * (dp - Dl);
+        for (int i = 0; i < HDM; ++i) { d = fmaf(qv[i], kk[i], d); dp = fmaf(dov[i], vv[i], dp); }
+        const float ds = fast_exp2(d - ls) * (dp - Dl);
 #pragma unroll
-        for (int i = 0; i < HDM; ++i)
-          if (i < hd) acc[i] = fmaf(ds, kr[i], acc[i]);
+        for (int i = 0; i < HDM; ++i) acc[i] = fmaf(ds, kk[i], acc[i]);
       }
 #pragma unroll
       for (int i = 0; i < HDM; ++i)
@@ -150,15 +181,16 @@ __global__ void __launch_bounds__(ATT_THREADS) mhsa_bwd_kernel(const float* __re
       const float* lsr = sLse + h * L;
       const float* Dr = sD + h * L;
       for (int l = 0; l < L; ++l, qr += E, dor += E) {
+        float qq[HDM], dd[HDM];
+        load_head<HDM, EXACT>(qq, qr, hd);
+        load_head<HDM, EXACT>(dd, dor, hd);
         float d = 0.f, dp = 0.f;
 #pragma unroll
-        for (int i = 0; i < HDM; ++i)
-          if (i < hd) { d = fmaf(qr[i], kv[i], d); dp = fmaf(dor[i], vv[i], dp); }
-        const float p = exp2f(d - lsr[l]);
+        for (int i = 0; i < HDM; ++i) { d = fmaf(qq[i], kv[i], d); dp = fmaf(dd[i], vv[i], dp); }
+        const float p = fast_exp2(d - lsr[l]);
         const float ds = p * (dp - Dr[l]);
 #pragma unroll
-        for (int i = 0; i < HDM; ++i)
-          if (i < hd) { dvv[i] = fmaf(p, dor[i], dvv[i]); dkv[i] = fmaf(ds, qr[i], dkv[i]); }
+        for (int i = 0; i < HDM; ++i) { dvv[i] = fmaf(p, dd[i], dvv[i]); dkv[i] = fmaf(ds, qq[i], dkv[i]); }
       }
 #pragma unroll
       for (int i = 0; i < HDM; ++i)
@@ -193,14 +225,19 @@ extern "C" int xdfm_mhsa_fwd(const float* q, const float* k, const float* v, int
   const int hd = E / heads;
   const float scale_log2e = 1.4426950408889634f / sqrtf((float)hd);
   cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH_FWD_(HDM, EX)                                                                                                \
+  do {                                                                                                                      \
+    XDFM_CUDA(cudaFuncSetAttribute(mhsa_fwd_kernel<HDM, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem * 4))); \
+    mhsa_fwd_kernel<HDM, EX><<<(unsigned)B, ATT_THREADS, smem * 4, st>>>(q, k, v, L, E, heads, hd, scale_log2e, o, lse);    \
+  } while (0)
 #define LAUNCH_FWD(HDM)                                                                                                     \
   do {                                                                                                                      \
-    XDFM_CUDA(cudaFuncSetAttribute(mhsa_fwd_kernel<HDM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem * 4)));    \
-    mhsa_fwd_kernel<HDM><<<(unsigned)B, ATT_THREADS, smem * 4, st>>>(q, k, v, L, E, heads, hd, scale_log2e, o, lse);        \
+    if (hd == HDM) LAUNCH_FWD_(HDM, true); else LAUNCH_FWD_(HDM, false);                                                    \
   } while (0)
   if (hd <= 2) LAUNCH_FWD(2); else if (hd <= 4) LAUNCH_FWD(4); else if (hd <= 8) LAUNCH_FWD(8); else if (hd <= 16) LAUNCH_FWD(16);
   else LAUNCH_FWD(32);
 #undef LAUNCH_FWD
+#undef LAUNCH_FWD_
   XDFM_LAUNCH_CHECK();
   return XDFM_OK;
 }
@@ -214,14 +251,19 @@ extern "C" int xdfm_mhsa_bwd(const float* q, const float* k, const float* v, con
   const int hd = E / heads;
   const float scale = 1.f / sqrtf((float)hd);
   cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH_BWD_(HDM, EX)                                                                                                \
+  do {                                                                                                                      \
+    XDFM_CUDA(cudaFuncSetAttribute(mhsa_bwd_kernel<HDM, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem * 4))); \
+    mhsa_bwd_kernel<HDM, EX><<<(unsigned)B, ATT_THREADS, smem * 4, st>>>(q, k, v, o, lse, dout, L, E, heads, hd, scale, dq, dk, dv); \
+  } while (0)
 #define LAUNCH_BWD(HDM)                                                                                                     \
   do {                                                                                                                      \
-    XDFM_CUDA(cudaFuncSetAttribute(mhsa_bwd_kernel<HDM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem * 4)));    \
-    mhsa_bwd_kernel<HDM><<<(unsigned)B, ATT_THREADS, smem * 4, st>>>(q, k, v, o, lse, dout, L, E, heads, hd, scale, dq, dk, dv); \
+    if (hd == HDM) LAUNCH_BWD_(HDM, true); else LAUNCH_BWD_(HDM, false);                                                    \
   } while (0)
   if (hd <= 2) LAUNCH_BWD(2); else if (hd <= 4) LAUNCH_BWD(4); else if (hd <= 8) LAUNCH_BWD(8); else if (hd <= 16) LAUNCH_BWD(16);
   else LAUNCH_BWD(32);
 #undef LAUNCH_BWD
+#undef LAUNCH_BWD_
   XDFM_LAUNCH_CHECK();
   return XDFM_OK;
 }
