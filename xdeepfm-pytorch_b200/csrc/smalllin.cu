@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(SL_THREADS) sl_rows_kernel(SlRowParams p) {
 #pragma unroll
         for (int i4 = 0; i4 < IM / 4; ++i4) {
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (i4 * 4 < p.I) v = ldg_nc_f4(reinterpret_cast<const float4*>(src) + i4);
+          if (i4 * 4 < p.I) v = __ldg(reinterpret_cast<const float4*>(src) + i4);   // L1-allocating: a thread's next granule shares the sector
           in[j * IM + i4 * 4 + 0] = v.x; in[j * IM + i4 * 4 + 1] = v.y; in[j * IM + i4 * 4 + 2] = v.z; in[j * IM + i4 * 4 + 3] = v.w;
         }
       } else {
