@@ -216,3 +216,45 @@ def test_pro_cuda_graph_replay_equals_eager_steps():
     for k in sd_e:
         assert torch.equal(sd_e[k], sd_g[k]), k
     assert abs(loss_e - loss_g) <= 1e-9 * abs(loss_e) and abs(sfg_e - sfg_g) <= 1e-9 * abs(sfg_e)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_pro_positive_rows_only_sfg_pass_equals_all_rows(graph):
+    """train_on_batch / fit know the batch's labels on the host and run the SFG decoder, heads and masked losses on the label-1
+    rows only (bucketed static shapes, device-side stable sort, no sync); rows with weight 0 contribute nothing, so weights and
+    losses must equal the all-rows step up to summation order."""
+    spec, params, z = load_case("pro_small")
+    X, y = torch.from_numpy(z["X"]), torch.from_numpy(z["y"])
+    out = []
+    for hinted in (False, True):
+        model = build_product_model(spec, DEV)
+        model.load_state_dict(params, strict=True)
+        model.compile("sgd", "binary_crossentropy")          # linear in the gradient: summation-order noise stays noise
+        model.use_cuda_graph = graph
+        model.SFG_ROW_BUCKET = 4
+        model.train()
+        losses = []
+        for rep in range(4):                       # same shapes four times: the graph path captures on the third call
+            for lo in (0, 20):
+                Xb, yb = X[lo:lo + 20], y[lo:lo + 20]
+                ids, dense = model.split_input(Xb.to(DEV))
+                if hinted:
+                    losses.append(model.train_on_batch(ids.cpu(), dense.cpu(), yb))
+                    assert model._npos_hint is None
+                else:
+                    accum = torch.zeros(1, dtype=torch.float64, device=DEV)
+                    model.train_step(ids, dense, yb.to(DEV), accum)
+                    losses.append(accum.item())
+        if hinted:
+            npos = int((y[:20] == 1).sum())
+            model._host_label_hint(y[:20])
+            assert model._sfg_rows_cap(20) == min(20, max(4, -(-npos // 4) * 4))
+            model._npos_hint = None
+            if graph:
+                assert model._graphs
+        out.append(({k: v.detach().clone() for k, v in model.state_dict().items()}, losses, model._sfg_accum.item()))
+    (sd_a, loss_a, sfg_a), (sd_b, loss_b, sfg_b) = out
+    assert np.allclose(loss_a, loss_b, rtol=1e-5)
+    assert abs(sfg_a - sfg_b) <= 1e-5 * abs(sfg_a)
+    for k in sd_a:
+        assert_close(sd_b[k], sd_a[k], 2e-4, 2e-5 * max(sd_a[k].abs().max().item(), 1e-6), "positive-rows-only step: " + k)

@@ -510,13 +510,16 @@ class BaseModel(nn.Module):
         aux_zero = (not torch.is_tensor(self.aux_loss)) or (not self.aux_loss.requires_grad and float(self.aux_loss.abs().sum()) == 0.0)
         return isinstance(self.optim, FusedOptimizer) and not has_l1 and aux_zero and not isinstance(self.loss_func, list)
 
-    def train_step(self, ids, dense, y, loss_accum, pred_log=None, pred_off=0):
+    def train_step(self, ids, dense, y, loss_accum, pred_log=None, pred_off=0, host_labels=None):
         """One fused training step on device tensors: forward, loss, backward, optimizer (+L2).  No host sync.
+        `host_labels` (optional): the same labels as a host tensor / array, for models that size work from them (xDeepFM Pro).
 
         The step issues ~120 kernel launches from Python (3-3.5 ms of host time at BASELINE config 2, about the GPU time of the
         step itself), so after two eager steps with the same shapes and hyper-parameters it is captured into a CUDA graph and
         replayed: inputs are copied into the graph's static buffers, the loss comes back through a static accumulator.
         `model.use_cuda_graph = False` (or XDFM_CUDA_GRAPH=0) keeps every step eager."""
+        if host_labels is not None:
+            self._host_label_hint(host_labels)
         if self.use_cuda_graph and ids.shape[0] > 0:
             out = self._train_step_graphed(ids, dense, y, loss_accum, pred_log, pred_off)
             if out is not None:
@@ -692,8 +695,13 @@ class BaseModel(nn.Module):
         if not hasattr(self, "_tob_accum") or self._tob_accum.device != dev:
             self._tob_accum = torch.zeros(1, dtype=torch.float64, device=dev)
         self._tob_accum.zero_()
+        self._host_label_hint(y)
         self.train_step(ids_d, dense_d, y_d, self._tob_accum)
         return float(self._tob_accum.item())
+
+    def _host_label_hint(self, y_host):
+        """Hook: the labels of the batch about to be stepped are still on the host (xDeepFM Pro sizes its positive-rows-only SFG
+        pass from their count without a device sync).  Consumed by the next train_step."""
 
     def fit(self, x=None, y=None, batch_size=None, epochs=1, verbose=1, initial_epoch=0, validation_split=0.,
             validation_data=None, shuffle=True, callbacks=None):
@@ -781,6 +789,8 @@ class BaseModel(nn.Module):
             for ids_b, dense_b, y_b in self._batches(ids, dense, y_t, batch_size, order):
                 nb = ids_b.shape[0]
                 if fused:
+                    if ctx is None:
+                        self._host_label_hint(y_t[off:off + nb] if order is None else y_t[order[off:off + nb]])
                     self.train_step(ids_b, dense_b, y_b, loss_accum, pred_log, off)
                 else:
                     # generic path (user-supplied optimizer / loss list / l1 / aux loss): mirrors basemodel.py:245-262

@@ -37,6 +37,39 @@ class BaseModelSFG(BaseModel):
             self.use_cuda_graph = False
         self.to(device)
 
+    # ---- positive rows only -------------------------------------------------------------------------------
+    # With sfg_positive_only (the reference default) rows with label != 1 have weight 0 in every SFG term (sfg_decoder.py:266-273,
+    # 290, 303): they add nothing to the loss or to any gradient, so the decoder, its per-field heads (2 * 64 * sum(vocab) FLOP and
+    # 4 * sum(vocab) bytes of logits PER ROW) and the masked losses only need the positive rows (hard part 7).
+    # Their number is data dependent; it is taken from the HOST labels of the batch (fit() / train_on_batch have them before the
+    # copy), rounded up to a bucket of SFG_ROW_BUCKET rows so that shapes stay static (a handful of CUDA graphs); the rows are
+    # brought to the front with a stable device-side sort -- no device sync.  Rows beyond the true count inside the bucket are
+    # negatives with weight 0: exact.  No hint (train_step called directly) = all rows.
+    SFG_ROW_BUCKET = 512
+
+    def _host_label_hint(self, y_host):
+        self._npos_hint = None
+        if self.use_sfg and self.sfg_positive_only and self.training:
+            y = torch.as_tensor(y_host).reshape(-1)
+            self._npos_hint = (int((y == 1).sum()), int(y.shape[0]))
+
+    def _sfg_rows_cap(self, B):
+        """Static number of rows the SFG pass of the coming step runs on (B = all)."""
+        hint = getattr(self, "_npos_hint", None)
+        if hint is None or hint[1] != B or not self.sfg_positive_only:
+            return B
+        bucket = self.SFG_ROW_BUCKET
+        return min(B, max(bucket, -(-hint[0] // bucket) * bucket))
+
+    def _graph_key(self, ids, dense, y):
+        return super()._graph_key(ids, dense, y) + (self._sfg_rows_cap(ids.shape[0]) if self.use_sfg else None,)
+
+    def train_step(self, *args, **kwargs):
+        try:
+            return super().train_step(*args, **kwargs)
+        finally:
+            self._npos_hint = None           # a hint describes exactly one batch (eager, captured or replayed)
+
     # ---- SFG loss on the split (ids, dense) feed ------------------------------------------------------
     def sfg_loss_ids(self, ids_all, dense_all, emb, labels):
         """SFG loss [scalar tensor] from this step's embeddings `emb` [B, m, D] (sfg_decoder.py:116-157, 266-309); the targets
@@ -46,8 +79,14 @@ class BaseModelSFG(BaseModel):
         dec = self.sfg_decoder
         flat = emb.reshape(emb.shape[0], -1)
         dec_in = torch.cat([flat, dd], dim=-1) if dd.shape[1] > 0 else flat
-        h = dec.hidden(dec_in, labels)
         row_w = ops.sfg_row_weights(labels, self.sfg_positive_only)
+        B = flat.shape[0]
+        cap = self._sfg_rows_cap(B)
+        if cap < B:
+            sel = torch.argsort(labels.reshape(-1), descending=True, stable=True)[:cap]      # label-1 rows first, batch order kept
+            dec_in, labels, row_w = dec_in.index_select(0, sel), labels.reshape(-1).index_select(0, sel), row_w.index_select(0, sel)
+            ids, dd = ids.index_select(0, sel).contiguous(), dd.index_select(0, sel)
+        h = dec.hidden(dec_in, labels)
         fn = self.sfg_loss_fn
         total = None
         for f, fc in enumerate(self.sparse_feature_columns):
