@@ -97,6 +97,81 @@ __global__ void __launch_bounds__(SL_THREADS) sl_rows_kernel(SlRowParams p) {
   }
 }
 
+// Coalesced variant for I == IM (16 or 32 floats per row, a multiple of 4) and O % 4 == 0: a warp owns 32 consecutive rows = one
+// contiguous block of memory; it moves the block with lane-contiguous 128-bit accesses through a private shared-memory patch
+// ([32][IM + 4] floats: the padded pitch makes both the block-order stores and the row-order loads conflict-free) instead of
+// having every lane walk its own 64-byte row (32 half-used sectors per instruction).
+template <int IM, int NIN>
+__global__ void __launch_bounds__(SL_THREADS) sl_rows_staged_kernel(SlRowParams p) {
+  extern __shared__ __align__(16) float sl_smem[];
+  constexpr int TL = IM * NIN;
+  constexpr int PITCH = IM + 4;
+  const int OM = p.O;                                 // multiple of 4
+  const int n_w = p.nq * OM * TL;
+  for (int e = threadIdx.x; e < n_w; e += SL_THREADS) {
+    const int i = e % IM, j = (e / IM) % NIN, o = (e / TL) % OM, q = e / (TL * OM);
+    sl_smem[e] = p.transpose ? p.w[j][(size_t)i * p.O + o] : p.w[q][(size_t)o * p.I + i];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* patch = sl_smem + ((n_w + 3) & ~3) + warp * 32 * PITCH;
+  constexpr int IQ = IM / 4;                          // float4s per input row
+  const int OQ = p.O / 4;                             // float4s per output row
+  for (int64_t rb = ((int64_t)blockIdx.x * (SL_THREADS / 32) + warp) * 32; rb < p.R; rb += (int64_t)gridDim.x * SL_THREADS) {
+    float in[TL];
+#pragma unroll
+    for (int j = 0; j < NIN; ++j) {
+      const float4* src = reinterpret_cast<const float4*>(p.in[j]) + rb * IQ;
+#pragma unroll
+      for (int c = 0; c < IQ; ++c) {
+        const int idx = c * 32 + lane, row = idx / IQ, part = idx % IQ;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rb + row < p.R) v = ldg_nc_f4(src + idx);
+        *reinterpret_cast<float4*>(patch + row * PITCH + part * 4) = v;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i4 = 0; i4 < IQ; ++i4) {
+        const float4 v = *reinterpret_cast<const float4*>(patch + lane * PITCH + i4 * 4);
+        in[j * IM + i4 * 4 + 0] = v.x; in[j * IM + i4 * 4 + 1] = v.y; in[j * IM + i4 * 4 + 2] = v.z; in[j * IM + i4 * 4 + 3] = v.w;
+      }
+      __syncwarp();
+    }
+    for (int q = 0; q < p.nq; ++q) {
+      for (int o0 = 0; o0 < p.O; o0 += 4) {
+        float a[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float4* w = reinterpret_cast<const float4*>(sl_smem + ((size_t)q * OM + o0 + t) * TL);
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int i4 = 0; i4 < TL / 4; i4 += 2) {
+            const float4 wa = w[i4], wb = w[i4 + 1];
+            s0 = fmaf(in[i4 * 4 + 0], wa.x, s0); s0 = fmaf(in[i4 * 4 + 1], wa.y, s0);
+            s0 = fmaf(in[i4 * 4 + 2], wa.z, s0); s0 = fmaf(in[i4 * 4 + 3], wa.w, s0);
+            s1 = fmaf(in[i4 * 4 + 4], wb.x, s1); s1 = fmaf(in[i4 * 4 + 5], wb.y, s1);
+            s1 = fmaf(in[i4 * 4 + 6], wb.z, s1); s1 = fmaf(in[i4 * 4 + 7], wb.w, s1);
+          }
+          float sacc = s0 + s1;
+          if (p.bias != nullptr) sacc += __ldg(p.bias + o0 + t);
+          a[t] = sl_act(sacc, p.act);
+        }
+        *reinterpret_cast<float4*>(patch + lane * PITCH + o0) = make_float4(a[0], a[1], a[2], a[3]);
+      }
+      __syncwarp();
+      float4* dst = reinterpret_cast<float4*>(p.out[q]) + rb * OQ;
+      for (int c = 0; c < OQ; ++c) {
+        const int idx = c * 32 + lane, row = idx / OQ, part = idx % OQ;
+        if (rb + row < p.R) dst[idx] = *reinterpret_cast<const float4*>(patch + row * PITCH + part * 4);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+int g_sl_staged = 1;
+extern "C" void xdfm_small_linear_set_staged(int v) { g_sl_staged = v ? 1 : 0; }
+
 static int sl_check(int64_t R, int K, int N, int nq, const char* what) {
   XDFM_CHECK_ARG(R >= 0 && K >= 1 && N >= 1 && nq >= 1 && nq <= SL_MAXQ, "%s: bad shape R=%lld K=%d N=%d n=%d", what, (long long)R, K, N, nq);
   if (K > 32 || N > 32) {
@@ -108,6 +183,15 @@ static int sl_check(int64_t R, int K, int N, int nq, const char* what) {
 
 template <int IM>
 static int sl_launch_rows(const SlRowParams& p, int nin, cudaStream_t st) {
+  if (g_sl_staged && p.I == IM && (p.O & 3) == 0 && p.O <= IM) {
+    const size_t smem = ((((size_t)p.nq * p.O * IM * nin + 3) & ~(size_t)3) + (size_t)(SL_THREADS / 32) * 32 * (IM + 4)) * sizeof(float);
+    const int blocks = (int)std::min<int64_t>(ceil_div64(p.R, SL_THREADS), (int64_t)xdfm_num_sms() * 8);
+    if (nin == 1) sl_rows_staged_kernel<IM, 1><<<blocks, SL_THREADS, smem, st>>>(p);
+    else if (nin == 2) sl_rows_staged_kernel<IM, 2><<<blocks, SL_THREADS, smem, st>>>(p);
+    else sl_rows_staged_kernel<IM, 3><<<blocks, SL_THREADS, smem, st>>>(p);
+    XDFM_LAUNCH_CHECK();
+    return XDFM_OK;
+  }
   const int OM = (p.O + 3) & ~3;
   const size_t smem = (size_t)p.nq * OM * IM * nin * sizeof(float);
   const int blocks = (int)std::min<int64_t>(ceil_div64(p.R, SL_THREADS), (int64_t)xdfm_num_sms() * 8);
@@ -260,11 +344,16 @@ __global__ void __launch_bounds__(SL_THREADS) sl_dw_kernel(SlDwParams p) {
   }
 }
 
-__global__ void sl_dw_reduce_kernel(const float* __restrict__ partial, int blocks, int stride, int nw, int N, float* dw0, float* dw1,
-                                    float* dw2, int per_w, float* db) {
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nw + (db != nullptr ? N : 0); e += gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int b = 0; b < blocks; ++b) s += partial[(size_t)b * stride + e];
+// one warp per output element: lane l adds the partials of blocks l, l + 32, ... in ascending order, then a fixed xor-shuffle tree
+__global__ void __launch_bounds__(256) sl_dw_reduce_kernel(const float* __restrict__ partial, int blocks, int stride, int nw, int N,
+                                                           float* dw0, float* dw1, float* dw2, int per_w, float* db) {
+  const int lane = threadIdx.x & 31;
+  const int e = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (e >= nw + (db != nullptr ? N : 0)) return;
+  float s = 0.f;
+  for (int b = lane; b < blocks; b += 32) s += partial[(size_t)b * stride + e];
+  s = warp_sum(s);
+  if (lane == 0) {
     if (e < nw) {
       const int q = e / per_w, i = e % per_w;
       (q == 0 ? dw0 : (q == 1 ? dw1 : dw2))[i] = s;
@@ -283,7 +372,9 @@ static void sl_dw_geom(int64_t R, int K, int N, int nq, SlDwParams* p, int* bloc
   const size_t tiles = (size_t)SL_TILE * (p->KM + (size_t)nq * p->NM);
   const size_t red = (size_t)p->G * ((size_t)nq * p->NM * p->KM + p->NM);
   *smem = std::max(tiles, red) * sizeof(float);
-  *blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(R, SL_TILE), (int64_t)xdfm_num_sms() * 2));
+  // a block alternates load -> sync -> a few hundred FMAs -> sync per 128-row tile: it is latency-bound on its own, so the SM is
+  // filled with as many blocks as the tiles' shared memory allows (round 1: 2 blocks per SM ran at 1.2 TB/s)
+  *blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(R, SL_TILE), (int64_t)xdfm_num_sms() * 8));
 }
 
 extern "C" int64_t xdfm_small_linear_bwd_dw_workspace_bytes(int64_t R, int K, int N, int nout) {
@@ -318,7 +409,7 @@ extern "C" int xdfm_small_linear_bwd_dw(const float* x, const float* dy0, const 
   sl_dw_kernel<<<blocks, SL_THREADS, smem, st>>>(p);
   XDFM_LAUNCH_CHECK();
   const int nw = nout * N * K;
-  sl_dw_reduce_kernel<<<(nw + N + 255) / 256, 256, 0, st>>>((const float*)workspace, blocks, nw + N, nw, N, dw0, dw1, dw2, N * K, db);
+  sl_dw_reduce_kernel<<<(nw + N + 7) / 8, 256, 0, st>>>((const float*)workspace, blocks, nw + N, nw, N, dw0, dw1, dw2, N * K, db);
   XDFM_LAUNCH_CHECK();
   return XDFM_OK;
 }
