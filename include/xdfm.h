@@ -237,6 +237,9 @@ int xdfm_mhsa_bwd(const float* q, const float* k, const float* v, const float* o
 /* y = LayerNorm_E(a + r) * gamma + beta (cin_attention.py:305-311; r may be NULL; normalize = 0: y = a + r only).
  * mean / rstd [rows] are saved for the backward, which returns dx (= d a = d r) and per-block partial sums
  * partial [xdfm_add_ln_bwd_blocks(rows), 2E] of (dgamma, dbeta) to be column-summed (xdfm_wcolsum). E <= 64. */
+/* diagnostic switch: 1 (default) = four query / key rows per thread and shared-memory load when head_dim is exactly 2 or 4;
+ * 0 = one row per thread */
+void xdfm_mhsa_set_row_blocked(int v);
 int xdfm_add_ln_fwd(const float* a, const float* r, const float* gamma, const float* beta, int64_t rows, int E, float eps, int normalize,
                     float* y, float* mean, float* rstd, void* stream);
 int xdfm_add_ln_bwd_blocks(int64_t rows);

@@ -19,8 +19,18 @@ def _close(a, b, what, tol=2e-5):
 
 
 @pytest.mark.parametrize("B,L,E,h", [(3, 256, 16, 4), (5, 24, 10, 2), (2, 40, 8, 4), (4, 17, 12, 1), (2, 300, 32, 2), (1, 8, 6, 6),
-                                     (0, 16, 8, 2)])
-def test_mhsa_core_matches_softmax_attention(B, L, E, h):
+                                     (0, 16, 8, 2), (3, 333, 8, 2), (2, 5, 4, 1), (4, 1030, 16, 4)])
+@pytest.mark.parametrize("row_blocked", [1, 0])
+def test_mhsa_core_matches_softmax_attention(B, L, E, h, row_blocked):
+    from deepctr import _native as Nv
+    Nv.lib().xdfm_mhsa_set_row_blocked(row_blocked)
+    try:
+        _mhsa_core_case(B, L, E, h)
+    finally:
+        Nv.lib().xdfm_mhsa_set_row_blocked(1)
+
+
+def _mhsa_core_case(B, L, E, h):
     g = torch.Generator().manual_seed(B * 1000 + L + E)
     q, k, v, do = (torch.randn(B, L, E, generator=g) for _ in range(4))
     qd, kd, vd = (t.double().requires_grad_(True) for t in (q, k, v))

@@ -202,6 +202,200 @@ __global__ void __launch_bounds__(ATT_THREADS) mhsa_bwd_kernel(const float* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Row-blocked variants (head_dim == HDM): a thread owns RB = 4 query rows (forward, backward phase A) or 4 key rows (phase B) of ONE
+// head and streams over the other axis.  Every shared-memory row slice it loads (K / V, or Q / dO) is used for four rows:
+// shared memory delivers 128 bytes per clock to the register file, broadcast or not, and with one row per thread the two
+// 128-bit loads per step (8 clocks per warp) -- not the ~15 arithmetic instructions -- set the pace (round 1: forward 3.3 ms at
+// BASELINE config 3).  Work items = heads x ceil(L / 4) row groups, rows of a group L/4 apart (lanes walk consecutive rows).
+// ------------------------------------------------------------------------------------------------
+#define ATT_RB 4
+
+template <int HDM>
+__global__ void __launch_bounds__(ATT_THREADS) mhsa_fwd_rb_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                                  const float* __restrict__ v, int L, int E, int nh,
+                                                                  float scale_log2e, float* __restrict__ o, float* __restrict__ lse) {
+  extern __shared__ __align__(16) float sm_att[];
+  float* sK = sm_att;
+  float* sV = sm_att + (size_t)L * E;
+  const int64_t b = blockIdx.x;
+  const size_t base = (size_t)b * L * E;
+  stage_rows(sK, k + base, L * E);
+  stage_rows(sV, v + base, L * E);
+  __syncthreads();
+  const int G = (L + ATT_RB - 1) / ATT_RB;
+  for (int item = threadIdx.x; item < nh * G; item += blockDim.x) {
+    const int h = item / G, g = item - h * G;
+    float qv[ATT_RB][HDM], acc[ATT_RB][HDM], mx[ATT_RB], s[ATT_RB];
+#pragma unroll
+    for (int r = 0; r < ATT_RB; ++r) {
+      const int l = g + r * G;
+#pragma unroll
+      for (int i = 0; i < HDM; ++i) {
+        qv[r][i] = l < L ? q[base + (size_t)l * E + h * HDM + i] * scale_log2e : 0.f;
+        acc[r][i] = 0.f;
+      }
+      mx[r] = -CUDART_INF_F;
+      s[r] = 0.f;
+    }
+    const float* kr = sK + h * HDM;
+    const float* vr = sV + h * HDM;
+    for (int j = 0; j < L; ++j, kr += E, vr += E) {
+      float kk[HDM], vv[HDM];
+      load_head<HDM, true>(kk, kr, HDM);
+      load_head<HDM, true>(vv, vr, HDM);
+#pragma unroll
+      for (int r = 0; r < ATT_RB; ++r) {
+        float d = 0.f;
+#pragma unroll
+        for (int i = 0; i < HDM; ++i) d = fmaf(qv[r][i], kk[i], d);
+        if (d > mx[r]) {
+          const float c = fast_exp2(mx[r] - d);
+          s[r] *= c;
+#pragma unroll
+          for (int i = 0; i < HDM; ++i) acc[r][i] *= c;
+          mx[r] = d;
+        }
+        const float p = fast_exp2(d - mx[r]);
+        s[r] += p;
+#pragma unroll
+        for (int i = 0; i < HDM; ++i) acc[r][i] = fmaf(p, vv[i], acc[r][i]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < ATT_RB; ++r) {
+      const int l = g + r * G;
+      if (l < L) {
+        const float inv = 1.f / s[r];
+#pragma unroll
+        for (int i = 0; i < HDM; ++i) o[base + (size_t)l * E + h * HDM + i] = acc[r][i] * inv;
+        lse[((size_t)b * nh + h) * L + l] = mx[r] + log2f(s[r]);
+      }
+    }
+  }
+}
+
+template <int HDM>
+__global__ void __launch_bounds__(ATT_THREADS) mhsa_bwd_rb_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                                  const float* __restrict__ v, const float* __restrict__ o,
+                                                                  const float* __restrict__ lse, const float* __restrict__ dout, int L,
+                                                                  int E, int nh, float scale, float* __restrict__ dq,
+                                                                  float* __restrict__ dk, float* __restrict__ dv) {
+  extern __shared__ __align__(16) float sm_att[];
+  float* sA = sm_att;                          // phase A: K      phase B: Q
+  float* sB = sm_att + (size_t)L * E;          // phase A: V      phase B: dO
+  float2* sLD = reinterpret_cast<float2*>(sB + (size_t)L * E);      // [nh][L] (log-sum-exp, D = rowsum(dO * O))
+  const int64_t b = blockIdx.x;
+  const size_t base = (size_t)b * L * E;
+  const float scale_log2e = scale * 1.4426950408889634f;
+  stage_rows(sA, k + base, L * E);
+  stage_rows(sB, v + base, L * E);
+  for (int it = threadIdx.x; it < L * nh; it += blockDim.x) {
+    const int h = it / L, l = it - h * L;
+    float d = 0.f;
+#pragma unroll
+    for (int i = 0; i < HDM; ++i) d = fmaf(dout[base + (size_t)l * E + h * HDM + i], o[base + (size_t)l * E + h * HDM + i], d);
+    sLD[it] = make_float2(lse[(size_t)b * nh * L + it], d);
+  }
+  __syncthreads();
+  const int G = (L + ATT_RB - 1) / ATT_RB;
+  // ---- phase A: item = (head, 4 query rows) -> dQ
+  for (int item = threadIdx.x; item < nh * G; item += blockDim.x) {
+    const int h = item / G, g = item - h * G;
+    float qv[ATT_RB][HDM], dov[ATT_RB][HDM], acc[ATT_RB][HDM], ls[ATT_RB], Dl[ATT_RB];
+#pragma unroll
+    for (int r = 0; r < ATT_RB; ++r) {
+      const int l = g + r * G;
+#pragma unroll
+      for (int i = 0; i < HDM; ++i) {
+        qv[r][i] = l < L ? q[base + (size_t)l * E + h * HDM + i] * scale_log2e : 0.f;
+        dov[r][i] = l < L ? dout[base + (size_t)l * E + h * HDM + i] : 0.f;
+        acc[r][i] = 0.f;
+      }
+      const float2 t = l < L ? sLD[h * L + l] : make_float2(0.f, 0.f);
+      ls[r] = t.x;
+      Dl[r] = t.y;
+    }
+    const float* kr = sA + h * HDM;
+    const float* vr = sB + h * HDM;
+    for (int j = 0; j < L; ++j, kr += E, vr += E) {
+      float kk[HDM], vv[HDM];
+      load_head<HDM, true>(kk, kr, HDM);
+      load_head<HDM, true>(vv, vr, HDM);
+#pragma unroll
+      for (int r = 0; r < ATT_RB; ++r) {
+        float d = 0.f, dp = 0.f;
+#pragma unroll
+        for (int i = 0; i < HDM; ++i) { d = fmaf(qv[r][i], kk[i], d); dp = fmaf(dov[r][i], vv[i], dp); }
+        const float ds = fast_exp2(d - ls[r]) * (dp - Dl[r]);
+#pragma unroll
+        for (int i = 0; i < HDM; ++i) acc[r][i] = fmaf(ds, kk[i], acc[r][i]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < ATT_RB; ++r) {
+      const int l = g + r * G;
+      if (l < L) {
+#pragma unroll
+        for (int i = 0; i < HDM; ++i) dq[base + (size_t)l * E + h * HDM + i] = acc[r][i] * scale;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase B: item = (head, 4 key rows) -> dK, dV
+  stage_rows(sA, q + base, L * E);
+  stage_rows(sB, dout + base, L * E);
+  __syncthreads();
+  for (int item = threadIdx.x; item < nh * G; item += blockDim.x) {
+    const int h = item / G, g = item - h * G;
+    float kv[ATT_RB][HDM], vv[ATT_RB][HDM], dkv[ATT_RB][HDM], dvv[ATT_RB][HDM];
+#pragma unroll
+    for (int r = 0; r < ATT_RB; ++r) {
+      const int j = g + r * G;
+#pragma unroll
+      for (int i = 0; i < HDM; ++i) {
+        kv[r][i] = j < L ? k[base + (size_t)j * E + h * HDM + i] * scale_log2e : 0.f;
+        vv[r][i] = j < L ? v[base + (size_t)j * E + h * HDM + i] : 0.f;
+        dkv[r][i] = 0.f;
+        dvv[r][i] = 0.f;
+      }
+    }
+    const float* qr = sA + h * HDM;
+    const float* dor = sB + h * HDM;
+    const float2* ldr = sLD + h * L;
+    for (int l = 0; l < L; ++l, qr += E, dor += E) {
+      float qq[HDM], dd[HDM];
+      load_head<HDM, true>(qq, qr, HDM);
+      load_head<HDM, true>(dd, dor, HDM);
+      const float2 t = ldr[l];
+#pragma unroll
+      for (int r = 0; r < ATT_RB; ++r) {
+        float d = 0.f, dp = 0.f;
+#pragma unroll
+        for (int i = 0; i < HDM; ++i) { d = fmaf(qq[i], kv[r][i], d); dp = fmaf(dd[i], vv[r][i], dp); }
+        const float p = fast_exp2(d - t.x);
+        const float ds = p * (dp - t.y);
+#pragma unroll
+        for (int i = 0; i < HDM; ++i) { dvv[r][i] = fmaf(p, dd[i], dvv[r][i]); dkv[r][i] = fmaf(ds, qq[i], dkv[r][i]); }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < ATT_RB; ++r) {
+      const int j = g + r * G;
+      if (j < L) {
+#pragma unroll
+        for (int i = 0; i < HDM; ++i) {
+          dk[base + (size_t)j * E + h * HDM + i] = dkv[r][i] * scale;
+          dv[base + (size_t)j * E + h * HDM + i] = dvv[r][i];
+        }
+      }
+    }
+  }
+}
+
+int g_mhsa_row_blocked = 1;     // 1: row-blocked kernels whenever head_dim is exactly 2 or 4 (default); 0: one row per thread
+extern "C" void xdfm_mhsa_set_row_blocked(int v) { g_mhsa_row_blocked = v ? 1 : 0; }
+
 static int mhsa_check(int64_t B, int L, int E, int nh, size_t smem_floats, const char* what) {
   XDFM_CHECK_ARG(B >= 0 && L >= 1 && E >= 1 && nh >= 1 && E % nh == 0, "%s: bad shape B=%lld L=%d E=%d heads=%d", what, (long long)B, L,
                  E, nh);
@@ -234,8 +428,17 @@ extern "C" int xdfm_mhsa_fwd(const float* q, const float* k, const float* v, int
   do {                                                                                                                      \
     if (hd == HDM) LAUNCH_FWD_(HDM, true); else LAUNCH_FWD_(HDM, false);                                                    \
   } while (0)
-  if (hd <= 2) LAUNCH_FWD(2); else if (hd <= 4) LAUNCH_FWD(4); else if (hd <= 8) LAUNCH_FWD(8); else if (hd <= 16) LAUNCH_FWD(16);
+#define LAUNCH_FWD_RB(HDM)                                                                                                  \
+  do {                                                                                                                      \
+    XDFM_CUDA(cudaFuncSetAttribute(mhsa_fwd_rb_kernel<HDM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem * 4)));  \
+    mhsa_fwd_rb_kernel<HDM><<<(unsigned)B, ATT_THREADS, smem * 4, st>>>(q, k, v, L, E, heads, scale_log2e, o, lse);          \
+  } while (0)
+  // wider heads need 4 x 4 x head_dim registers per thread in the backward (8: 177, 16: spills): one row per thread there
+  const bool rb = g_mhsa_row_blocked && ((hd == 2 && E % 2 == 0) || (hd == 4 && E % 4 == 0));
+  if (rb && hd == 2) LAUNCH_FWD_RB(2); else if (rb && hd == 4) LAUNCH_FWD_RB(4);
+  else if (hd <= 2) LAUNCH_FWD(2); else if (hd <= 4) LAUNCH_FWD(4); else if (hd <= 8) LAUNCH_FWD(8); else if (hd <= 16) LAUNCH_FWD(16);
   else LAUNCH_FWD(32);
+#undef LAUNCH_FWD_RB
 #undef LAUNCH_FWD
 #undef LAUNCH_FWD_
   XDFM_LAUNCH_CHECK();
@@ -260,8 +463,16 @@ extern "C" int xdfm_mhsa_bwd(const float* q, const float* k, const float* v, con
   do {                                                                                                                      \
     if (hd == HDM) LAUNCH_BWD_(HDM, true); else LAUNCH_BWD_(HDM, false);                                                    \
   } while (0)
-  if (hd <= 2) LAUNCH_BWD(2); else if (hd <= 4) LAUNCH_BWD(4); else if (hd <= 8) LAUNCH_BWD(8); else if (hd <= 16) LAUNCH_BWD(16);
+#define LAUNCH_BWD_RB(HDM)                                                                                                  \
+  do {                                                                                                                      \
+    XDFM_CUDA(cudaFuncSetAttribute(mhsa_bwd_rb_kernel<HDM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem * 4)));  \
+    mhsa_bwd_rb_kernel<HDM><<<(unsigned)B, ATT_THREADS, smem * 4, st>>>(q, k, v, o, lse, dout, L, E, heads, scale, dq, dk, dv); \
+  } while (0)
+  const bool rb = g_mhsa_row_blocked && ((hd == 2 && E % 2 == 0) || (hd == 4 && E % 4 == 0));
+  if (rb && hd == 2) LAUNCH_BWD_RB(2); else if (rb && hd == 4) LAUNCH_BWD_RB(4);
+  else if (hd <= 2) LAUNCH_BWD(2); else if (hd <= 4) LAUNCH_BWD(4); else if (hd <= 8) LAUNCH_BWD(8); else if (hd <= 16) LAUNCH_BWD(16);
   else LAUNCH_BWD(32);
+#undef LAUNCH_BWD_RB
 #undef LAUNCH_BWD
 #undef LAUNCH_BWD_
   XDFM_LAUNCH_CHECK();
