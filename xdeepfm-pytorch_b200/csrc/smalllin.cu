@@ -212,7 +212,7 @@ static int sl_launch_rows(const SlRowParams& p, int nin, cudaStream_t st) {
   const size_t smem = (size_t)p.nq * OM * IM * nin * sizeof(float);
   // rows per thread (every weight load applied to RPT rows): measured SLOWER at BASELINE config 3 (K = N = 16: 0.198 vs 0.172 ms
   // for one output, 0.572 vs 0.381 ms for three) -- the shared-memory weight loads are not what bounds this kernel; kept at 1
-  constexpr int RPT1 = 1, RPT2 = 1, RPT3 = 1;
+  constexpr int RPT1 = 1, RPT2 = 1, RPT3 = 1;        // (2 rows per thread: 0.211 ms; 4: 0.198 ms; 1: 0.172 ms)
   const int rpt = nin == 1 ? RPT1 : (nin == 2 ? RPT2 : RPT3);
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(p.R, (int64_t)SL_THREADS * rpt), (int64_t)xdfm_num_sms() * 8));
   if (nin == 1) sl_rows_kernel<IM, 1, RPT1><<<blocks, SL_THREADS, smem, st>>>(p);
