@@ -262,8 +262,9 @@ int xdfm_small_linear_fwd(const float* x, const float* w0, const float* w1, cons
 int xdfm_small_linear_bwd_dx(const float* dy0, const float* dy1, const float* dy2, const float* w0, const float* w1, const float* w2,
                              int64_t R, int K, int N, int nout, float* dx, void* stream);
 int64_t xdfm_small_linear_bwd_dw_workspace_bytes(int64_t R, int K, int N, int nout);
-/* diagnostic switch: 1 = rows moved through a per-warp shared-memory patch with lane-contiguous 128-bit accesses when K (fwd) /
- * N (dX) is 8, 16 or 32 and the output width is a multiple of 4; 0 (default) = every lane walks its own rows (measured equal) */
+/* tuning switch: v = rows per thread (1, 2, 4; default 2) of the variant that moves 32 v rows per warp through a shared-memory
+ * patch with lane-contiguous 128-bit accesses (single-input launches with K (fwd) / N (dX) in {8, 16, 32} and an output width
+ * that is a multiple of 4); 0 = every lane walks its own row */
 void xdfm_small_linear_set_staged(int v);
 int xdfm_small_linear_bwd_dw(const float* x, const float* dy0, const float* dy1, const float* dy2, int64_t R, int K, int N, int nout,
                              float* dw0, float* dw1, float* dw2, float* db, void* workspace, void* stream);

@@ -133,9 +133,22 @@ def test_cin_attention_tail_matches_oracle(variant, heads, layers, ln, res):
     (300, 10, 10, 3, None, False),            # E = 10 (script default): not a multiple of 4 -> scalar load / store paths
     (129, 32, 32, 3, None, False), (5, 8, 6, 2, "relu", False), (1, 3, 5, 1, "sigmoid", True), (0, 16, 16, 3, None, False),
     (70000, 8, 8, 1, None, True)])
-def test_small_linear_matches_torch(R, K, N, nq, act, bias):
+@pytest.mark.parametrize("staged", [0, 2, 4, 9])
+def test_small_linear_matches_torch(R, K, N, nq, act, bias, staged):
     """Narrow-layer kernels (csrc/smalllin.cu) against fp64 torch: y, dx, every dW, db at 2e-5 of each tensor's scale; the
-    two-stage reductions are bit-reproducible."""
+    two-stage reductions are bit-reproducible.  staged = rows per thread of the coalesced row kernel (0 = per-lane rows)."""
+    from deepctr import _native as Nv0
+    Nv0.lib().xdfm_small_linear_set_staged(staged)
+    try:
+        _small_linear_case(R, K, N, nq, act, bias)
+    finally:
+        Nv0.lib().xdfm_small_linear_set_staged(SL_STAGED_DEFAULT)
+
+
+SL_STAGED_DEFAULT = 2
+
+
+def _small_linear_case(R, K, N, nq, act, bias):
     g = torch.Generator().manual_seed(R + K * 7 + N)
     x = torch.randn(R, K, generator=g)
     Ws = [torch.randn(N, K, generator=g) / math.sqrt(K) for _ in range(nq)]

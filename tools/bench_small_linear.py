@@ -36,7 +36,7 @@ def timeit(fn, reps=5):
 
 
 P = Nv.ptr
-for staged in (0, 1):
+for staged in (0, 1, 2, 4):
     L.xdfm_small_linear_set_staged(staged)
     t1 = timeit(lambda: Nv.check(L.xdfm_small_linear_fwd(P(x), P(Ws[0]), None, None, None, 0, R, K, N, 1, P(ys[0]), None, None, st)))
     t3 = timeit(lambda: Nv.check(L.xdfm_small_linear_fwd(P(x), P(Ws[0]), P(Ws[1]), P(Ws[2]), None, 0, R, K, N, 3, P(ys[0]), P(ys[1]), P(ys[2]), st)))

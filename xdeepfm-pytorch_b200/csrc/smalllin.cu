@@ -117,11 +117,12 @@ __global__ void __launch_bounds__(SL_THREADS) sl_rows_kernel(SlRowParams p) {
 // contiguous block of memory; it moves the block with lane-contiguous 128-bit accesses through a private shared-memory patch
 // ([32][IM + 4] floats: the padded pitch makes both the block-order stores and the row-order loads conflict-free) instead of
 // having every lane walk its own 64-byte row (32 half-used sectors per instruction).
-template <int IM, int NIN>
+template <int IM, int NIN, int RPT>
 __global__ void __launch_bounds__(SL_THREADS) sl_rows_staged_kernel(SlRowParams p) {
   extern __shared__ __align__(16) float sl_smem[];
   constexpr int TL = IM * NIN;
   constexpr int PITCH = IM + 4;
+  constexpr int ROWS = 32 * RPT;                      // rows a warp moves and computes per iteration (thread: rows lane + 32 u)
   const int OM = p.O;                                 // multiple of 4
   const int n_w = p.nq * OM * TL;
   for (int e = threadIdx.x; e < n_w; e += SL_THREADS) {
@@ -130,16 +131,16 @@ __global__ void __launch_bounds__(SL_THREADS) sl_rows_staged_kernel(SlRowParams 
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* patch = sl_smem + ((n_w + 3) & ~3) + warp * 32 * PITCH;
+  float* patch = sl_smem + ((n_w + 3) & ~3) + warp * ROWS * PITCH;
   constexpr int IQ = IM / 4;                          // float4s per input row
   const int OQ = p.O / 4;                             // float4s per output row
-  for (int64_t rb = ((int64_t)blockIdx.x * (SL_THREADS / 32) + warp) * 32; rb < p.R; rb += (int64_t)gridDim.x * SL_THREADS) {
-    float in[TL];
+  for (int64_t rb = ((int64_t)blockIdx.x * (SL_THREADS / 32) + warp) * ROWS; rb < p.R; rb += (int64_t)gridDim.x * (SL_THREADS / 32) * ROWS) {
+    float in[RPT][TL];
 #pragma unroll
     for (int j = 0; j < NIN; ++j) {
       const float4* src = reinterpret_cast<const float4*>(p.in[j]) + rb * IQ;
 #pragma unroll
-      for (int c = 0; c < IQ; ++c) {
+      for (int c = 0; c < IQ * RPT; ++c) {
         const int idx = c * 32 + lane, row = idx / IQ, part = idx % IQ;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (rb + row < p.R) v = ldg_nc_f4(src + idx);
@@ -147,36 +148,46 @@ __global__ void __launch_bounds__(SL_THREADS) sl_rows_staged_kernel(SlRowParams 
       }
       __syncwarp();
 #pragma unroll
-      for (int i4 = 0; i4 < IQ; ++i4) {
-        const float4 v = *reinterpret_cast<const float4*>(patch + lane * PITCH + i4 * 4);
-        in[j * IM + i4 * 4 + 0] = v.x; in[j * IM + i4 * 4 + 1] = v.y; in[j * IM + i4 * 4 + 2] = v.z; in[j * IM + i4 * 4 + 3] = v.w;
-      }
+      for (int u = 0; u < RPT; ++u)
+#pragma unroll
+        for (int i4 = 0; i4 < IQ; ++i4) {
+          const float4 v = *reinterpret_cast<const float4*>(patch + (lane + 32 * u) * PITCH + i4 * 4);
+          in[u][j * IM + i4 * 4 + 0] = v.x; in[u][j * IM + i4 * 4 + 1] = v.y;
+          in[u][j * IM + i4 * 4 + 2] = v.z; in[u][j * IM + i4 * 4 + 3] = v.w;
+        }
       __syncwarp();
     }
     for (int q = 0; q < p.nq; ++q) {
       for (int o0 = 0; o0 < p.O; o0 += 4) {
-        float a[4];
+        float a[RPT][4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const float4* w = reinterpret_cast<const float4*>(sl_smem + ((size_t)q * OM + o0 + t) * TL);
-          float s0 = 0.f, s1 = 0.f;
+          float s0[RPT], s1[RPT];
+#pragma unroll
+          for (int u = 0; u < RPT; ++u) { s0[u] = 0.f; s1[u] = 0.f; }
 #pragma unroll
           for (int i4 = 0; i4 < TL / 4; i4 += 2) {
-            const float4 wa = w[i4], wb = w[i4 + 1];
-            s0 = fmaf(in[i4 * 4 + 0], wa.x, s0); s0 = fmaf(in[i4 * 4 + 1], wa.y, s0);
-            s0 = fmaf(in[i4 * 4 + 2], wa.z, s0); s0 = fmaf(in[i4 * 4 + 3], wa.w, s0);
-            s1 = fmaf(in[i4 * 4 + 4], wb.x, s1); s1 = fmaf(in[i4 * 4 + 5], wb.y, s1);
-            s1 = fmaf(in[i4 * 4 + 6], wb.z, s1); s1 = fmaf(in[i4 * 4 + 7], wb.w, s1);
+            const float4 wa = w[i4], wb = w[i4 + 1];      // one weight load serves RPT rows
+#pragma unroll
+            for (int u = 0; u < RPT; ++u) {
+              s0[u] = fmaf(in[u][i4 * 4 + 0], wa.x, s0[u]); s0[u] = fmaf(in[u][i4 * 4 + 1], wa.y, s0[u]);
+              s0[u] = fmaf(in[u][i4 * 4 + 2], wa.z, s0[u]); s0[u] = fmaf(in[u][i4 * 4 + 3], wa.w, s0[u]);
+              s1[u] = fmaf(in[u][i4 * 4 + 4], wb.x, s1[u]); s1[u] = fmaf(in[u][i4 * 4 + 5], wb.y, s1[u]);
+              s1[u] = fmaf(in[u][i4 * 4 + 6], wb.z, s1[u]); s1[u] = fmaf(in[u][i4 * 4 + 7], wb.w, s1[u]);
+            }
           }
-          float sacc = s0 + s1;
-          if (p.bias != nullptr) sacc += __ldg(p.bias + o0 + t);
-          a[t] = sl_act(sacc, p.act);
+          const float bv = p.bias != nullptr ? __ldg(p.bias + o0 + t) : 0.f;
+#pragma unroll
+          for (int u = 0; u < RPT; ++u) a[u][t] = sl_act(s0[u] + s1[u] + bv, p.act);
         }
-        *reinterpret_cast<float4*>(patch + lane * PITCH + o0) = make_float4(a[0], a[1], a[2], a[3]);
+#pragma unroll
+        for (int u = 0; u < RPT; ++u)
+          *reinterpret_cast<float4*>(patch + (lane + 32 * u) * PITCH + o0) = make_float4(a[u][0], a[u][1], a[u][2], a[u][3]);
       }
       __syncwarp();
       float4* dst = reinterpret_cast<float4*>(p.out[q]) + rb * OQ;
-      for (int c = 0; c < OQ; ++c) {
+      for (int c = 0; c < OQ * RPT; ++c) {
         const int idx = c * 32 + lane, row = idx / OQ, part = idx % OQ;
         if (rb + row < p.R) dst[idx] = *reinterpret_cast<const float4*>(patch + row * PITCH + part * 4);
       }
@@ -185,8 +196,11 @@ __global__ void __launch_bounds__(SL_THREADS) sl_rows_staged_kernel(SlRowParams 
   }
 }
 
-int g_sl_staged = 0;     // measured equal to the per-lane-row kernel (the pace was set by shared-memory weight loads): off
-extern "C" void xdfm_small_linear_set_staged(int v) { g_sl_staged = v ? 1 : 0; }
+// rows per thread of the coalesced kernel (0 = per-lane-row kernel; >= 8: also for concatenated inputs, diagnostic).  Measured at
+// K = N = 16, R = 4.2 M: one input, one / three outputs 0.163 / 0.385 ms (0), 0.163 / 0.386 (1), 0.147 / 0.344 (2), 0.163 / 0.385 (4);
+// three inputs (dX of Q/K/V) 0.348 (0), 0.413 (1), 0.574 (2) -> 2 for single-input launches, the per-lane kernel otherwise
+int g_sl_staged = 2;
+extern "C" void xdfm_small_linear_set_staged(int v) { g_sl_staged = v < 0 ? 0 : v; }
 
 static int sl_check(int64_t R, int K, int N, int nq, const char* what) {
   XDFM_CHECK_ARG(R >= 0 && K >= 1 && N >= 1 && nq >= 1 && nq <= SL_MAXQ, "%s: bad shape R=%lld K=%d N=%d n=%d", what, (long long)R, K, N, nq);
@@ -199,12 +213,22 @@ static int sl_check(int64_t R, int K, int N, int nq, const char* what) {
 
 template <int IM>
 static int sl_launch_rows(const SlRowParams& p, int nin, cudaStream_t st) {
-  if (g_sl_staged && p.I == IM && (p.O & 3) == 0 && p.O <= IM) {
-    const size_t smem = ((((size_t)p.nq * p.O * IM * nin + 3) & ~(size_t)3) + (size_t)(SL_THREADS / 32) * 32 * (IM + 4)) * sizeof(float);
-    const int blocks = (int)std::min<int64_t>(ceil_div64(p.R, SL_THREADS), (int64_t)xdfm_num_sms() * 8);
-    if (nin == 1) sl_rows_staged_kernel<IM, 1><<<blocks, SL_THREADS, smem, st>>>(p);
-    else if (nin == 2) sl_rows_staged_kernel<IM, 2><<<blocks, SL_THREADS, smem, st>>>(p);
-    else sl_rows_staged_kernel<IM, 3><<<blocks, SL_THREADS, smem, st>>>(p);
+  if (g_sl_staged && (nin == 1 || g_sl_staged >= 8) && p.I == IM && (p.O & 3) == 0 && p.O <= IM) {
+    // g_sl_staged = rows per thread (1, 2 or 4) of the coalesced kernel; three concatenated inputs keep 1 or 2 (registers)
+    constexpr int RA = IM <= 16 ? 4 : 2;
+    int rpt = g_sl_staged >= 4 ? RA : (g_sl_staged >= 2 ? 2 : 1);
+    if (nin > 1) rpt = std::min(rpt, IM <= 16 ? 2 : 1);
+    const size_t smem = ((((size_t)p.nq * p.O * IM * nin + 3) & ~(size_t)3) + (size_t)(SL_THREADS / 32) * 32 * rpt * (IM + 4)) * sizeof(float);
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(p.R, (int64_t)SL_THREADS * rpt), (int64_t)xdfm_num_sms() * 8));
+#define SL_STAGED(NI, RP)                                                                                              \
+    do {                                                                                                               \
+      XDFM_CUDA(cudaFuncSetAttribute(sl_rows_staged_kernel<IM, NI, RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      sl_rows_staged_kernel<IM, NI, RP><<<blocks, SL_THREADS, smem, st>>>(p);                                          \
+    } while (0)
+    if (nin == 1) { if (rpt == RA) SL_STAGED(1, RA); else if (rpt == 2) SL_STAGED(1, 2); else SL_STAGED(1, 1); }
+    else if (nin == 2) { if (rpt == 2) SL_STAGED(2, 2); else SL_STAGED(2, 1); }
+    else { if (rpt == 2) SL_STAGED(3, 2); else SL_STAGED(3, 1); }
+#undef SL_STAGED
     XDFM_LAUNCH_CHECK();
     return XDFM_OK;
   }
