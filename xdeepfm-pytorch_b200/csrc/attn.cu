@@ -211,6 +211,36 @@ __global__ void __launch_bounds__(ATT_THREADS) mhsa_bwd_kernel(const float* __re
 // ------------------------------------------------------------------------------------------------
 #define ATT_RB 4
 
+// Packed fp32 arithmetic (sm_100 FFMA2 / FMUL2: two IEEE fp32 operations per instruction).  These kernels are bound by instruction
+// issue, and 8 of the ~13-21 instructions per (query, key) pair are multiply-adds over the head's HDM (even) lanes.
+template <int HDM>
+__device__ __forceinline__ float dot_p(const float (&a)[HDM], const float (&b)[HDM]) {
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < HDM; i += 2) acc = __ffma2_rn(make_float2(a[i], a[i + 1]), make_float2(b[i], b[i + 1]), acc);
+  return acc.x + acc.y;
+}
+template <int HDM>
+__device__ __forceinline__ void axpy_p(float s, const float (&x)[HDM], float (&y)[HDM]) {      // y += s * x
+  const float2 s2 = make_float2(s, s);
+#pragma unroll
+  for (int i = 0; i < HDM; i += 2) {
+    const float2 r = __ffma2_rn(s2, make_float2(x[i], x[i + 1]), make_float2(y[i], y[i + 1]));
+    y[i] = r.x;
+    y[i + 1] = r.y;
+  }
+}
+template <int HDM>
+__device__ __forceinline__ void scale_p(float s, float (&y)[HDM]) {                              // y *= s
+  const float2 s2 = make_float2(s, s);
+#pragma unroll
+  for (int i = 0; i < HDM; i += 2) {
+    const float2 r = __fmul2_rn(s2, make_float2(y[i], y[i + 1]));
+    y[i] = r.x;
+    y[i + 1] = r.y;
+  }
+}
+
 template <int HDM>
 __global__ void __launch_bounds__(ATT_THREADS) mhsa_fwd_rb_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                                   const float* __restrict__ v, int L, int E, int nh,
@@ -246,20 +276,16 @@ __global__ void __launch_bounds__(ATT_THREADS) mhsa_fwd_rb_kernel(const float* _
       load_head<HDM, true>(vv, vr, HDM);
 #pragma unroll
       for (int r = 0; r < ATT_RB; ++r) {
-        float d = 0.f;
-#pragma unroll
-        for (int i = 0; i < HDM; ++i) d = fmaf(qv[r][i], kk[i], d);
+        const float d = dot_p<HDM>(qv[r], kk);
         if (d > mx[r]) {
           const float c = fast_exp2(mx[r] - d);
           s[r] *= c;
-#pragma unroll
-          for (int i = 0; i < HDM; ++i) acc[r][i] *= c;
+          scale_p<HDM>(c, acc[r]);
           mx[r] = d;
         }
         const float p = fast_exp2(d - mx[r]);
         s[r] += p;
-#pragma unroll
-        for (int i = 0; i < HDM; ++i) acc[r][i] = fmaf(p, vv[i], acc[r][i]);
+        axpy_p<HDM>(p, vv, acc[r]);
       }
     }
 #pragma unroll
@@ -324,12 +350,9 @@ __global__ void __launch_bounds__(ATT_THREADS) mhsa_bwd_rb_kernel(const float* _
       load_head<HDM, true>(vv, vr, HDM);
 #pragma unroll
       for (int r = 0; r < ATT_RB; ++r) {
-        float d = 0.f, dp = 0.f;
-#pragma unroll
-        for (int i = 0; i < HDM; ++i) { d = fmaf(qv[r][i], kk[i], d); dp = fmaf(dov[r][i], vv[i], dp); }
+        const float d = dot_p<HDM>(qv[r], kk), dp = dot_p<HDM>(dov[r], vv);
         const float ds = fast_exp2(d - ls[r]) * (dp - Dl[r]);
-#pragma unroll
-        for (int i = 0; i < HDM; ++i) acc[r][i] = fmaf(ds, kk[i], acc[r][i]);
+        axpy_p<HDM>(ds, kk, acc[r]);
       }
     }
 #pragma unroll
@@ -370,13 +393,11 @@ __global__ void __launch_bounds__(ATT_THREADS) mhsa_bwd_rb_kernel(const float* _
       const float2 t = ldr[l];
 #pragma unroll
       for (int r = 0; r < ATT_RB; ++r) {
-        float d = 0.f, dp = 0.f;
-#pragma unroll
-        for (int i = 0; i < HDM; ++i) { d = fmaf(qq[i], kv[r][i], d); dp = fmaf(dd[i], vv[r][i], dp); }
+        const float d = dot_p<HDM>(qq, kv[r]), dp = dot_p<HDM>(dd, vv[r]);
         const float p = fast_exp2(d - t.x);
         const float ds = p * (dp - t.y);
-#pragma unroll
-        for (int i = 0; i < HDM; ++i) { dvv[r][i] = fmaf(p, dd[i], dvv[r][i]); dkv[r][i] = fmaf(ds, qq[i], dkv[r][i]); }
+        axpy_p<HDM>(p, dd, dvv[r]);
+        axpy_p<HDM>(ds, qq, dkv[r]);
       }
     }
 #pragma unroll
