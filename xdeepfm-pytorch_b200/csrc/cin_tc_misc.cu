@@ -137,13 +137,28 @@ __global__ void __launch_bounds__(256) cin_dy_rows_cols_kernel(const __nv_bfloat
               if (h0 + i < n_next) dn[i] = dsrc[i];
           }
         }
+        // pooled-output gradient of these 8 channels (direct-connect range h >= hdb): two 128-bit loads when aligned
+        float dpv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dpv[i] = 0.f;
+        if (dpooled != nullptr && h0 + 8 > hdb) {
+          const int64_t pidx = b * fm_total + col_off + (h0 - hdb);
+          if (h0 >= hdb && h0 + 8 <= H && (pidx & 3) == 0 && (reinterpret_cast<uintptr_t>(dpooled) & 15) == 0) {
+            const float4 a = *reinterpret_cast<const float4*>(dpooled + pidx), c = *reinterpret_cast<const float4*>(dpooled + pidx + 4);
+            dpv[0] = a.x; dpv[1] = a.y; dpv[2] = a.z; dpv[3] = a.w; dpv[4] = c.x; dpv[5] = c.y; dpv[6] = c.z; dpv[7] = c.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (h0 + i >= hdb && h0 + i < H) dpv[i] = dpooled[pidx + i];
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int h = h0 + i;
           float v = 0.f;
           if (h < H) {
             if (h >= hdb) {
-              if (dpooled) v += dpooled[b * fm_total + col_off + (h - hdb)];
+              v += dpv[i];
               if (dmaps) v += dmaps[(b * fm_total + col_off + (h - hdb)) * (int64_t)D + d];
             }
             v += dn[i];
