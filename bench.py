@@ -264,12 +264,15 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # rank 0's stdout carries exactly ONE JSON line: everything else written to file descriptor 1 during the run (NCCL prints its
+    # version banner there when the first communicator is created) is sent to stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dev = "cuda:%d" % local_rank
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"        # NCCL prints its version banner on stdout: rank 0's stdout is ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device(dev))
     from deepctr import _native, ops
     from tests.helpers import build_product_model
@@ -423,7 +426,8 @@ def main():
         except Exception as e:  # pragma: no cover
             line["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": "failed: %s" % e}
-    print(json.dumps(line))
+    json_out.write(json.dumps(line) + "\n")
+    json_out.flush()
 
 
 if __name__ == "__main__":
