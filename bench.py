@@ -61,7 +61,43 @@ def load_peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
 
 
+class WorkloadSpec:
+    """Shapes of one bench workload for the PRODUCT arm (no oracle/ or tests/ import on that arm)."""
+
+    def __init__(self, w):
+        self.sparse_names = ["C%d" % i for i in range(1, w["m"] + 1)]
+        self.dense_names = ["I%d" % i for i in range(1, w["nd"] + 1)]
+        self.vocab_sizes = list(w["vocab"])
+        self.embedding_dim = w["D"]
+        self.cin_layer_size = tuple(w["cin"])
+        self.cin_split_half = True
+        self.dnn_hidden_units = tuple(w["dnn"])
+        self.variant = w.get("variant", "xdeepfm")
+        self.num_heads = w.get("heads", 4)
+        self.m, self.nd = w["m"], w["nd"]
+
+
+def build_product_model(spec, device):
+    """The product model through the reference's own constructor API (xdftrain.py:269-285, xdftrain_attn.py, xdftrain_pro.py)."""
+    from deepctr import models as M
+    from deepctr.inputs import DenseFeat, SparseFeat
+    cols = [SparseFeat(n, v, spec.embedding_dim) for n, v in zip(spec.sparse_names, spec.vocab_sizes)] + \
+           [DenseFeat(n, 1) for n in spec.dense_names]
+    common = dict(dnn_hidden_units=spec.dnn_hidden_units, cin_layer_size=spec.cin_layer_size, cin_split_half=True,
+                  cin_activation="relu", l2_reg_linear=1e-5, l2_reg_embedding=1e-5, l2_reg_dnn=0.0, l2_reg_cin=0.0, device=device)
+    if spec.variant == "xdeepfm":
+        return M.xDeepFM(cols, cols, **common)
+    if spec.variant == "pro":
+        from deepctr.xdeepfm_pro import xDeepFMPro
+        return xDeepFMPro(cols, cols, use_sfg=True, sfg_weight=0.1, sfg_hidden_units=(128, 64), sfg_dropout=0.0,
+                          sfg_positive_only=True, sfg_use_label_attention=True, use_autodis=False, **common)
+    if spec.variant == "attn":
+        return M.xDeepFMAttention(cols, cols, cin_num_heads=spec.num_heads, cin_use_layer_norm=True, cin_use_residual=True, **common)
+    raise SystemExit("unknown variant %s" % spec.variant)
+
+
 def make_spec(w, vocab_cap=None):
+    """ModelSpec of the CPU legs (`--impl reference` / cpu_baseline): the only place bench.py touches oracle/."""
     from oracle.xdeepfm_oracle import ModelSpec
     vocab = [min(v, vocab_cap) if vocab_cap else v for v in w["vocab"]]
     return ModelSpec(sparse_names=["C%d" % i for i in range(1, w["m"] + 1)], vocab_sizes=vocab, embedding_dim=w["D"],
@@ -275,9 +311,8 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(dev))
     from deepctr import _native, ops
-    from tests.helpers import build_product_model
     peaks = load_peaks()
-    spec = make_spec(w)
+    spec = WorkloadSpec(w)
     B = w["batch"]
     if w.get("deferred"):
         if world < 2:
