@@ -269,6 +269,27 @@ void xdfm_small_linear_set_staged(int v);
 int xdfm_small_linear_bwd_dw(const float* x, const float* dy0, const float* dy1, const float* dy2, int64_t R, int K, int N, int nout,
                              float* dw0, float* dw1, float* dw2, float* db, void* workspace, void* stream);
 
+/* ---- Multi-value (VarLenSparseFeat) pooling: the bag mode of the embedding lookup.
+ * Replaces varlen_embedding_lookup + get_varlen_pooling_list (deepctr/inputs.py:141-155, 212-225) and
+ * SequencePoolingLayer.forward (deepctr/layers/sequence.py:51-79).  The T positions of a sequence feature are T slots of the fused
+ * gather (xdfm_embed_gather); this turns the slot tensor emb [B, S, D] into the field tensor out [B, F, D]: field f owns the slots
+ * [slot0[f], slot0[f] + slen[f]) (contiguous, in order, covering [0, S)), mode[f] = XDFM_BAG_SINGLE (copy; slen 1) / SUM / MEAN / MAX.
+ * Mask of position j: lencol[f] < 0 -> ids[b, slot0[f] + j] != 0 (supports_masking=True; 'mean' divides by the number of valid
+ * positions + 1e-8); lencol[f] >= 0 -> j < lens[b, lencol[f]] ('mean' divides by that length + 1e-8, as given).  MAX reduces
+ * x - (1 - mask) * 1e9 and records the winning position per element in argmax [B, F, D] (required when any field is MAX; first
+ * position wins ties).  ids int32 [B, S] are the ids the slot tensor was gathered with; lens int32 [B, nlen] or NULL.
+ * slot0 / slen / mode / lencol are HOST arrays [F]; S, F <= 64.  bwd: demb [B, S, D] = d(sum out * dout)/d emb. */
+#define XDFM_BAG_SINGLE 0
+#define XDFM_BAG_SUM 1
+#define XDFM_BAG_MEAN 2
+#define XDFM_BAG_MAX 3
+int xdfm_bag_pool_fwd(const float* emb, const int32_t* ids, const int32_t* lens, int nlen, int64_t B, int S, int D, int F,
+                      const int32_t* slot0, const int32_t* slen, const int32_t* mode, const int32_t* lencol, float* out,
+                      int32_t* argmax, void* stream);
+int xdfm_bag_pool_bwd(const float* dout, const int32_t* ids, const int32_t* lens, int nlen, const int32_t* argmax, int64_t B, int S,
+                      int D, int F, const int32_t* slot0, const int32_t* slen, const int32_t* mode, const int32_t* lencol,
+                      float* demb, void* stream);
+
 /* ---- xDeepFM Pro: Supervised-Feature-Generation loss (deepctr/xdeepfm_pro/sfg_decoder.py:266-309).
  * row_w[b] = mask_b / num (mask = label == 1, num = sum(mask) + 1e-8 when positive_only; else 1 / B);
  * masked_ce:  row_loss[r] = row_w[r] * CE(logits[r, :V], targets[r * target_stride]), dlogits = d(sum row_loss)/d logits;

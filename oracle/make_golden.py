@@ -246,11 +246,179 @@ def main_autodis():
              lr=1e-2)
 
 
+# ---- multi-value (VarLenSparseFeat) features: SURVEY.md 8f-4 -----------------------------------------------------
+VARLEN_COLUMNS = [
+    {"kind": "sparse", "name": "C1", "vocab": 7, "dim": 8},
+    {"kind": "dense", "name": "I1", "dim": 1},
+    {"kind": "varlen", "name": "G", "vocab": 11, "dim": 8, "maxlen": 5, "combiner": "mean", "length_name": None},
+    {"kind": "sparse", "name": "C2", "vocab": 29, "dim": 8},
+    {"kind": "varlen", "name": "H", "vocab": 9, "dim": 8, "maxlen": 3, "combiner": "max", "length_name": None},
+    {"kind": "dense", "name": "I2", "dim": 2},
+    {"kind": "varlen", "name": "S", "vocab": 13, "dim": 8, "maxlen": 4, "combiner": "sum", "length_name": "S_len"},
+    {"kind": "varlen", "name": "M", "vocab": 6, "dim": 8, "maxlen": 2, "combiner": "mean", "length_name": "M_len"},
+]
+
+
+def columns_from_desc(desc, SparseFeat, DenseFeat, VarLenSparseFeat):
+    cols = []
+    for d in desc:
+        if d["kind"] == "sparse":
+            cols.append(SparseFeat(d["name"], d["vocab"], d["dim"]))
+        elif d["kind"] == "dense":
+            cols.append(DenseFeat(d["name"], d["dim"]))
+        else:
+            cols.append(VarLenSparseFeat(SparseFeat(d["name"], d["vocab"], d["dim"]), maxlen=d["maxlen"], combiner=d["combiner"],
+                                         length_name=d["length_name"]))
+    return cols
+
+
+def varlen_inputs(desc, feature_index, n, seed):
+    """Flat float32 input matrix in feature_index order: ids uniform (0 = padding, ~40 % of the sequence positions; some sequences
+    entirely padded), lengths uniform in [0, maxlen], dense U[0,1)."""
+    g = torch.Generator().manual_seed(seed)
+    width = max(b for _, b in feature_index.values())
+    X = torch.zeros(n, width)
+    by_name = {d["name"]: d for d in desc}
+    for name, (a, b) in feature_index.items():
+        d = by_name.get(name)
+        if d is None:                                      # a length column
+            owner = [q for q in desc if q.get("length_name") == name][0]
+            X[:, a] = torch.randint(0, owner["maxlen"] + 1, (n,), generator=g).float()
+        elif d["kind"] == "dense":
+            X[:, a:b] = torch.rand(n, b - a, generator=g)
+        elif d["kind"] == "sparse":
+            X[:, a] = torch.randint(0, d["vocab"], (n,), generator=g).float()
+        else:
+            ids = torch.randint(1, d["vocab"], (n, b - a), generator=g)
+            keep = torch.rand(n, b - a, generator=g) < 0.6
+            keep[::7] = False                              # every 7th sample: an entirely padded sequence
+            if d["combiner"] == "max":
+                keep[:, 0] = True      # 'max' over an entirely padded sequence is -1e9 in the reference (sequence.py:69-72): not a model input
+            X[:, a:b] = (ids * keep).float()
+    y = (torch.rand(n, generator=g) < 0.3).float()
+    return X, y
+
+
+def varlen_params(model, seed):
+    """Deterministic, non-degenerate parameters for the reference model's own state_dict layout."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k, v in model.state_dict().items():
+        scale = 0.3 if "embedding_dict" in k else 0.08
+        out[k] = (torch.randn(v.shape, generator=g) * scale).to(v.dtype)
+    return out
+
+
+def seqpool_cases():
+    """SequencePoolingLayer of the reference (sequence.py:9-79): every mode under both mask conventions, outputs and input gradients."""
+    from deepctr.layers.sequence import SequencePoolingLayer
+    g = torch.Generator().manual_seed(41)
+    out = {}
+    for E in (8, 3, 1):
+        B, T = 13, 6
+        x = torch.randn(B, T, E, generator=g)
+        w = torch.randn(B, 1, E, generator=g)
+        mask = torch.rand(B, T, generator=g) < 0.6
+        mask[3] = False
+        mask[5] = True
+        length = torch.randint(0, T + 1, (B, 1), generator=g)
+        length[0], length[1] = 0, T
+        out["x_E%d" % E], out["w_E%d" % E], out["mask_E%d" % E], out["len_E%d" % E] = x.numpy(), w.numpy(), mask.numpy(), length.numpy()
+        for mode in ("sum", "mean", "max"):
+            for masking in (True, False):
+                if mode == "max" and not masking:
+                    continue        # the reference raises here (sequence.py:69: `1 - mask` on the bool mask of _sequence_mask)
+                xi = x.clone().requires_grad_(True)
+                layer = SequencePoolingLayer(mode=mode, supports_masking=masking)
+                o = layer([xi, mask if masking else length])
+                (o * w).sum().backward()
+                key = "%s_%s_E%d" % (mode, "mask" if masking else "len", E)
+                out["out_" + key], out["dx_" + key] = o.detach().numpy(), xi.grad.numpy()
+    np.savez_compressed(os.path.join(GOLD, "seqpool_cases.npz"), **out)
+    print("seqpool_cases", len(out), "arrays")
+
+
+def varlen_model_case(name, B, seed):
+    """One reference xDeepFM train step (no optimizer) with multi-value features in the linear, CIN and DNN parts."""
+    from deepctr.inputs import VarLenSparseFeat
+    cols = columns_from_desc(VARLEN_COLUMNS, SparseFeat, DenseFeat, VarLenSparseFeat)
+    model = xDeepFM(cols, cols, dnn_hidden_units=(32, 16), cin_layer_size=(16, 8), l2_reg_linear=1e-3, l2_reg_embedding=1e-3,
+                    l2_reg_dnn=1e-3, l2_reg_cin=1e-3, device="cpu")
+    params = varlen_params(model, seed)
+    model.load_state_dict(params, strict=True)
+    X, y = varlen_inputs(VARLEN_COLUMNS, model.feature_index, B, seed)
+    model.train()
+    y_pred = model(X).squeeze()
+    loss = torch.nn.functional.binary_cross_entropy(y_pred, y, reduction="sum")
+    reg = model.get_regularization_loss()
+    total = loss + reg + model.aux_loss
+    model.zero_grad()
+    total.backward()
+    out = {"X": X.numpy(), "y": y.numpy(), "y_pred": y_pred.detach().numpy(), "loss": loss.detach().numpy(),
+           "reg_loss": reg.detach().numpy(), "total": total.detach().numpy(), "columns_json": np.array(json.dumps(VARLEN_COLUMNS)),
+           "feature_names": np.array(json.dumps(list(model.feature_index.keys())))}
+    for k, p in model.named_parameters():
+        out["grad::" + k] = (p.grad if p.grad is not None else torch.zeros_like(p)).numpy()
+    model.eval()
+    with torch.no_grad():
+        out["y_pred_eval"] = model(X).numpy()
+        out["linear_logit"] = model.linear_model(X).numpy()
+    for k, v in params.items():
+        out["param::" + k] = v.numpy()
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(name, "loss", float(loss), "total", float(total), "y_pred[:3]", y_pred[:3].tolist())
+
+
+def varlen_fit_case(name, N, batch_size, epochs, seed, lr):
+    """Trajectory of the reference's own fit() / predict() on dict inputs with [N, maxlen] id matrices."""
+    from deepctr.inputs import VarLenSparseFeat
+    cols = columns_from_desc(VARLEN_COLUMNS, SparseFeat, DenseFeat, VarLenSparseFeat)
+    model = xDeepFM(cols, cols, dnn_hidden_units=(32, 16), cin_layer_size=(16, 8), l2_reg_linear=1e-3, l2_reg_embedding=1e-3,
+                    l2_reg_dnn=1e-3, l2_reg_cin=1e-3, device="cpu")
+    params = varlen_params(model, seed)
+    model.load_state_dict(params, strict=True)
+    X, y = varlen_inputs(VARLEN_COLUMNS, model.feature_index, N, seed)
+    model.compile("adam", "binary_crossentropy", metrics=["binary_crossentropy", "auc"])
+    for gparam in model.optim.param_groups:
+        gparam["lr"] = lr
+    xdict = {n: X[:, a:b].numpy().copy() if b - a > 1 else X[:, a].numpy().copy() for n, (a, b) in model.feature_index.items()}
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        hist = model.fit(dict(xdict), y.numpy().reshape(-1, 1), batch_size=batch_size, epochs=epochs, verbose=0, shuffle=False,
+                         validation_data=(dict(xdict), y.numpy().reshape(-1, 1)))
+        pred = model.predict(dict(xdict), batch_size=batch_size)
+    out = {"X": X.numpy(), "y": y.numpy(), "pred": pred, "history_loss": np.array(hist.history["loss"], dtype=np.float64),
+           "history_val_auc": np.array(hist.history["val_auc"], dtype=np.float64),
+           "history_val_bce": np.array(hist.history["val_binary_crossentropy"], dtype=np.float64),
+           "columns_json": np.array(json.dumps(VARLEN_COLUMNS)),
+           "feature_names": np.array(json.dumps(list(model.feature_index.keys()))),
+           "batch_size": np.int64(batch_size), "epochs": np.int64(epochs), "lr": np.float64(lr)}
+    for k, v in params.items():
+        out["param::" + k] = v.numpy()
+    for k, v in model.state_dict().items():
+        out["final::" + k] = v.numpy()
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(name, "history loss", hist.history["loss"], "val_auc", hist.history["val_auc"])
+
+
+def main_varlen():
+    """Multi-value feature fixtures (`python -m oracle.make_golden varlen` regenerates only these)."""
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(4)
+    seqpool_cases()
+    varlen_model_case("xdeepfm_varlen", B=48, seed=51)
+    varlen_fit_case("fit_varlen_adam", N=96, batch_size=32, epochs=2, seed=52, lr=1e-2)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "pro":
         main_pro()
     elif len(sys.argv) > 1 and sys.argv[1] == "autodis":
         main_autodis()
+    elif len(sys.argv) > 1 and sys.argv[1] == "varlen":
+        main_varlen()
     else:
         main()
         main_pro()
+        main_varlen()

@@ -542,3 +542,41 @@ def make_inputs(spec: ModelSpec, B, seed=0, zipf=False):
     X = torch.cat([sparse, dense], 1) if spec.sparse_first else torch.cat([dense, sparse], 1)
     y = (torch.rand(B, generator=g) < 0.25).to(torch.float32)
     return X, y
+
+
+def sequence_pool(seq, aux, mode, supports_masking):
+    """SequencePoolingLayer.forward (sequence.py:51-79): seq [B, T, E]; aux = mask [B, T] (supports_masking) or length [B, 1].
+    'mean' divides by (length + 1e-8) with the length as given; 'max' reduces seq - (1 - mask) * 1e9.  (The reference itself
+    raises for mode='max' with a length input -- `1 - mask` on a bool mask, sequence.py:69 -- the restatement defines it by the
+    same formula.)"""
+    B, T, E = seq.shape
+    if supports_masking:
+        mask = aux.reshape(B, T).to(seq.dtype)
+        length = mask.sum(dim=-1, keepdim=True)
+    else:
+        length = aux.reshape(B, 1)
+        mask = (torch.arange(T).view(1, T) < length).to(seq.dtype)
+        length = length.to(seq.dtype)
+    mask = mask.unsqueeze(2)
+    if mode == "max":
+        return (seq - (1 - mask) * 1e9).max(dim=1, keepdim=True)[0]
+    hist = (seq * mask).sum(dim=1)
+    if mode == "mean":
+        hist = hist / (length + 1e-8)
+    return hist.unsqueeze(1)
+
+
+def bag_pool(emb, ids, lens, fields):
+    """Slot tensor [B, S, D] -> field tensor [B, F, D] (the layout of include/xdfm.h xdfm_bag_pool_fwd, restating
+    get_varlen_pooling_list, inputs.py:141-155): `fields` = [(n_slots, mode, lencol)], mode 'single' copies the slot."""
+    out, s = [], 0
+    for n, mode, lencol in fields:
+        x = emb[:, s:s + n]
+        if mode == "single":
+            out.append(x)
+        elif lencol < 0:
+            out.append(sequence_pool(x, ids[:, s:s + n] != 0, mode, True))
+        else:
+            out.append(sequence_pool(x, lens[:, lencol:lencol + 1], mode, False))
+        s += n
+    return torch.cat(out, dim=1)

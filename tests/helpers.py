@@ -76,3 +76,33 @@ def assert_close(a, b, rtol, atol, what=""):
         i = int(torch.argmax(err - tol))
         raise AssertionError("%s: max |err| %.3e (ref %.3e) at flat index %d; rtol %.1e atol %.1e; frac bad %.4f" % (
             what, err.flatten()[i].item(), b.flatten()[i].item(), i, rtol, atol, float((err > tol).double().mean())))
+
+
+def load_varlen_case(name):
+    """Fixture of a model with multi-value features: (column descriptors, feature names, params, npz)."""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    desc = json.loads(str(z["columns_json"]))
+    names = json.loads(str(z["feature_names"]))
+    params = {k[len("param::"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param::")}
+    return desc, names, params, z
+
+
+def product_columns(desc):
+    from deepctr.inputs import DenseFeat, SparseFeat, VarLenSparseFeat
+    cols = []
+    for d in desc:
+        if d["kind"] == "sparse":
+            cols.append(SparseFeat(d["name"], d["vocab"], d["dim"]))
+        elif d["kind"] == "dense":
+            cols.append(DenseFeat(d["name"], d["dim"]))
+        else:
+            cols.append(VarLenSparseFeat(SparseFeat(d["name"], d["vocab"], d["dim"]), maxlen=d["maxlen"], combiner=d["combiner"],
+                                         length_name=d["length_name"]))
+    return cols
+
+
+def build_varlen_product_model(desc, device="cuda:0"):
+    from deepctr.models import xDeepFM
+    cols = product_columns(desc)
+    return xDeepFM(cols, cols, dnn_hidden_units=(32, 16), cin_layer_size=(16, 8), l2_reg_linear=1e-3, l2_reg_embedding=1e-3,
+                   l2_reg_dnn=1e-3, l2_reg_cin=1e-3, device=device)

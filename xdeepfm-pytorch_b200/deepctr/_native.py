@@ -16,6 +16,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_PKG_ROOT), "include", "xdfm.h")
 MAX_FIELDS = 64
 MAX_DENSE = 256
 ACT = {"none": 0, "linear": 0, None: 0, "relu": 1, "tanh": 2, "sigmoid": 3}
+BAG = {"single": 0, "sum": 1, "mean": 2, "max": 3}
 OPT = {"sgd": 0, "adam": 1, "adagrad": 2, "rmsprop": 3}
 
 
@@ -92,6 +93,10 @@ _SIGS = {
     "xdfm_autodis_param_count": (c_int64, [c_int, c_int]),
     "xdfm_autodis_bwd_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int]),
     "xdfm_autodis_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P]),
+    "xdfm_bag_pool_fwd": (c_int, [_P, _P, _P, c_int, c_int64, c_int, c_int, c_int, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32),
+                                  POINTER(c_int32), _P, _P, _P]),
+    "xdfm_bag_pool_bwd": (c_int, [_P, _P, _P, c_int, _P, c_int64, c_int, c_int, c_int, POINTER(c_int32), POINTER(c_int32),
+                                  POINTER(c_int32), POINTER(c_int32), _P, _P]),
     "xdfm_sfg_row_weights": (c_int, [_P, c_int64, c_int, _P, _P]),
     "xdfm_masked_ce": (c_int, [_P, _P, c_int64, _P, c_int64, c_int, _P, _P, _P]),
     "xdfm_masked_mse": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P, _P]),

@@ -31,8 +31,9 @@ class SparseFeat(namedtuple("SparseFeat", ["name", "vocabulary_size", "embedding
 
 
 class VarLenSparseFeat(namedtuple("VarLenSparseFeat", ["sparsefeat", "maxlen", "combiner", "length_name"])):
-    """Variable-length categorical column (reference: inputs.py:41-77).  Kept for API compatibility; the xDeepFM
-    hot path of this build does not pool sequences (out of scope)."""
+    """Variable-length (multi-value) categorical column (reference: inputs.py:41-77): `maxlen` id columns, pooled with
+    `combiner` ('sum' | 'mean' | 'max') under the id != 0 mask, or under positions < `length_name` column when given.
+    Looked up as `maxlen` slots of the fused gather and reduced by the bag-pooling kernel (csrc/bag.cu)."""
     __slots__ = ()
 
     def __new__(cls, sparsefeat, maxlen, combiner="mean", length_name=None):
@@ -127,10 +128,8 @@ def table_rows(emb):
 def create_embedding_matrix(feature_columns, init_std=0.0001, linear=False, sparse=False, device="cpu"):
     """nn.ModuleDict {embedding_name: nn.Embedding(vocab, D or 1)} initialised N(0, init_std)
     (reference: inputs.py:158-180).  The modules are parameter containers: the CUDA gather reads `.weight` directly."""
-    if varlen_columns(feature_columns):
-        raise NotImplementedError("VarLenSparseFeat pooling is outside the xDeepFM hot path of this build")
     tables = nn.ModuleDict()
-    for fc in sparse_columns(feature_columns):
+    for fc in sparse_columns(feature_columns) + varlen_columns(feature_columns):
         if fc.embedding_name not in tables:
             if _DEFERRED_TABLES[0]:
                 emb = nn.Embedding(1, 1 if linear else fc.embedding_dim, sparse=sparse)
@@ -154,3 +153,33 @@ def combined_dnn_input(sparse_embedding_list, dense_value_list):
     if not parts:
         raise NotImplementedError
     return parts[0] if len(parts) == 1 else torch.cat(parts, dim=-1)
+
+
+def varlen_embedding_lookup(X, embedding_dict, sequence_input_dict, varlen_sparse_feature_columns):
+    """{feature name: [B, maxlen, D]} sequence embeddings (reference: inputs.py:212-225), one fused gather per feature."""
+    from . import ops
+    out = {}
+    for fc in varlen_sparse_feature_columns:
+        a, b = sequence_input_dict[fc.name]
+        ids, _ = ops.split_input(X, list(range(a, b)), [])
+        w = embedding_dict[fc.embedding_name].weight
+        plan = ops.SparsePlan([0] * (b - a), [w.shape[0]], w.shape[1])
+        out[fc.name] = ops.SparseGather.apply(plan, ops.SegmentCache(), ids, w)
+    return out
+
+
+def get_varlen_pooling_list(embedding_dict, features, feature_index, varlen_sparse_feature_columns, device):
+    """[B, 1, D] per sequence feature (reference: inputs.py:141-155).  `embedding_dict` = the result of varlen_embedding_lookup."""
+    from .layers.sequence import SequencePoolingLayer
+    out = []
+    for fc in varlen_sparse_feature_columns:
+        seq_emb = embedding_dict[fc.name]
+        if fc.length_name is None:
+            a, b = feature_index[fc.name]
+            mask = features[:, a:b].long() != 0
+            out.append(SequencePoolingLayer(mode=fc.combiner, supports_masking=True, device=device)([seq_emb, mask]))
+        else:
+            a, b = feature_index[fc.length_name]
+            length = features[:, a:b].long()
+            out.append(SequencePoolingLayer(mode=fc.combiner, supports_masking=False, device=device)([seq_emb, length]))
+    return out

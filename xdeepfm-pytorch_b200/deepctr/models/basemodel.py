@@ -39,11 +39,38 @@ def _expand_cols(feature_index, columns):
     return cols
 
 
-def _make_plan(columns, embedding_dict, width):
+def _slot_cols(feature_index, columns, varlen=()):
+    """Input-matrix columns of the ids looked up together: one slot per SparseFeat, then `maxlen` slots per VarLenSparseFeat
+    (the order of the reference's sparse_embedding_list + varlen_sparse_embedding_list, basemodel.py:368-380)."""
+    return _expand_cols(feature_index, columns) + _expand_cols(feature_index, varlen)
+
+
+def _make_plan(columns, embedding_dict, width, varlen=()):
     names = list(embedding_dict.keys())
     table_of = [names.index(fc.embedding_name) for fc in columns]
+    for fc in varlen:
+        table_of += [names.index(fc.embedding_name)] * fc.maxlen
     rows = [table_rows(embedding_dict[n]) for n in names]
     return ops.SparsePlan(table_of, rows, width)
+
+
+def _length_names(varlen):
+    out = []
+    for fc in varlen:
+        if fc.length_name is not None and fc.length_name not in out:
+            out.append(fc.length_name)
+    return out
+
+
+def _make_bag(columns, varlen, len_names):
+    """ops.BagLayout of a lookup with multi-value features (None without them): fixed fields first, then one pooled field
+    per VarLenSparseFeat, masked by id != 0 or by its length column (inputs.py:141-155)."""
+    if not varlen:
+        return None
+    fields = [(1, "single", -1) for _ in columns]
+    for fc in varlen:
+        fields.append((fc.maxlen, fc.combiner, -1 if fc.length_name is None else len_names.index(fc.length_name)))
+    return ops.BagLayout(fields)
 
 
 class Linear(nn.Module):
@@ -60,23 +87,39 @@ class Linear(nn.Module):
         if len(self.dense_feature_columns) > 0:
             self.weight = nn.Parameter(torch.empty(sum(fc.dimension for fc in self.dense_feature_columns), 1, device=device))
             nn.init.normal_(self.weight, mean=0, std=init_std)
-        self._sparse_cols = _expand_cols(feature_index, self.sparse_feature_columns)
+        self._sparse_cols = _slot_cols(feature_index, self.sparse_feature_columns, self.varlen_sparse_feature_columns)
         self._dense_cols = _expand_cols(feature_index, self.dense_feature_columns)
-        self._plan = _make_plan(self.sparse_feature_columns, self.embedding_dict, 1)
+        self._plan = _make_plan(self.sparse_feature_columns, self.embedding_dict, 1, self.varlen_sparse_feature_columns)
         self._cache = ops.SegmentCache()
+        self._bind_lengths(_length_names(self.varlen_sparse_feature_columns))
+
+    def _bind_lengths(self, len_names):
+        """`len_names`: the length columns (in the order of the `lens` tensor forward_ids receives) of the sequence features."""
+        self._len_names = list(len_names)
+        self._len_cols = [self.feature_index[n][0] for n in self._len_names]
+        self._bag = _make_bag(self.sparse_feature_columns, self.varlen_sparse_feature_columns, self._len_names)
 
     def _tables(self):
         return [emb.weight for emb in self.embedding_dict.values()]
 
-    def forward_ids(self, ids, dense, cache=None):
+    def forward_ids(self, ids, dense, cache=None, lens=None):
         w = self.weight if len(self.dense_feature_columns) > 0 else None
-        return ops.LinearTerm.apply(self._plan, cache or self._cache, ids, dense if w is not None else None, w, *self._tables())
+        if self._bag is None:
+            return ops.LinearTerm.apply(self._plan, cache or self._cache, ids, dense if w is not None else None, w, *self._tables())
+        # multi-value features: first-order rows of every slot, pooled per field under the sequence mask, summed over the fields
+        # (basemodel.py:63-92: cat(sparse + pooled sequence embeddings, -1).sum(-1) + dense @ weight)
+        rows = ops.SparseGather.apply(self._plan, cache or self._cache, ids, *self._tables())
+        logit = ops.BagPool.apply(self._bag, rows, ids, lens).sum(dim=1)
+        if w is not None:
+            logit = logit + ops.linear_act(dense, w.t().contiguous(), None, None)
+        return logit
 
     def forward(self, X, sparse_feat_refine_weight=None):
         if sparse_feat_refine_weight is not None:
             raise NotImplementedError("sparse_feat_refine_weight (IFM/DIFM) is outside the xDeepFM hot path")
         ids, dense = ops.split_input(X, self._sparse_cols, self._dense_cols)
-        return self.forward_ids(ids, dense)
+        lens = ops.split_input(X, self._len_cols, [])[0] if self._len_cols else None
+        return self.forward_ids(ids, dense, lens=lens)
 
 
 class BaseModel(nn.Module):
@@ -92,9 +135,6 @@ class BaseModel(nn.Module):
             raise ValueError("`gpus[0]` should be the same gpu with `device`")
         self.reg_loss = torch.zeros((1,), device=device)
         self.aux_loss = torch.zeros((1,), device=device)
-        if varlen_columns(list(linear_feature_columns) + list(dnn_feature_columns)):
-            raise NotImplementedError("VarLenSparseFeat is outside the xDeepFM hot path of this build")
-
         self.feature_index = build_input_features(list(linear_feature_columns) + list(dnn_feature_columns))
         self.embedding_dict = create_embedding_matrix(dnn_feature_columns, init_std, sparse=False, device=device)
         self.linear_model = Linear(linear_feature_columns, self.feature_index, device=device)
@@ -109,12 +149,14 @@ class BaseModel(nn.Module):
 
         # fused-lookup plans: the sparse / dense columns of the deep part and of the linear part
         self._dnn_sparse = sparse_columns(dnn_feature_columns)
+        self._dnn_varlen = varlen_columns(dnn_feature_columns)
         self._dnn_dense = dense_columns(dnn_feature_columns)
-        dims = set(fc.embedding_dim for fc in self._dnn_sparse)
+        dims = set(fc.embedding_dim for fc in self._dnn_sparse + self._dnn_varlen)
         if len(dims) > 1:
             raise ValueError("embedding_dim of SparseFeat and VarlenSparseFeat must be same in this model!")
         self._emb_dim = dims.pop() if dims else 0
-        self._emb_plan = _make_plan(self._dnn_sparse, self.embedding_dict, self._emb_dim) if self._dnn_sparse else None
+        self._emb_plan = _make_plan(self._dnn_sparse, self.embedding_dict, self._emb_dim, self._dnn_varlen) \
+            if (self._dnn_sparse or self._dnn_varlen) else None
         self._seg_cache = ops.SegmentCache()
         # union column layout used by the int32/float32 feed
         all_cols = []
@@ -124,13 +166,29 @@ class BaseModel(nn.Module):
                 seen.add(fc.name)
                 all_cols.append(fc)
         self._all_sparse = sparse_columns(all_cols)
+        self._all_varlen = varlen_columns(all_cols)
         self._all_dense = dense_columns(all_cols)
-        self._all_sparse_cols = _expand_cols(self.feature_index, self._all_sparse)
+        # id-type columns of the feed: one per SparseFeat, maxlen per VarLenSparseFeat, then the length columns
+        self._len_names = _length_names(self._all_varlen)
+        self._len_cols = [self.feature_index[n][0] for n in self._len_names]
+        self._all_sparse_cols = _slot_cols(self.feature_index, self._all_sparse, self._all_varlen) + self._len_cols
         self._all_dense_cols = _expand_cols(self.feature_index, self._all_dense)
-        sp_names = [fc.name for fc in self._all_sparse]
-        self._dnn_sparse_sel = self._selector([sp_names.index(fc.name) for fc in self._dnn_sparse], len(sp_names))
-        self._lin_sparse_sel = self._selector([sp_names.index(fc.name) for fc in self.linear_model.sparse_feature_columns],
-                                              len(sp_names))
+        n_ids = len(self._all_sparse_cols)
+        slot_pos, cursor = {}, 0
+        for fc in self._all_sparse + self._all_varlen:
+            width = fc.maxlen if isinstance(fc, VarLenSparseFeat) else 1
+            slot_pos[fc.name] = list(range(cursor, cursor + width))
+            cursor += width
+        self._len_sel = list(range(cursor, n_ids))
+
+        def slots_of(sparse, varlen):
+            return [p for fc in list(sparse) + list(varlen) for p in slot_pos[fc.name]]
+
+        self._dnn_sparse_sel = self._selector(slots_of(self._dnn_sparse, self._dnn_varlen), n_ids)
+        self._lin_sparse_sel = self._selector(slots_of(self.linear_model.sparse_feature_columns,
+                                                       self.linear_model.varlen_sparse_feature_columns), n_ids)
+        self._emb_bag = _make_bag(self._dnn_sparse, self._dnn_varlen, self._len_names)
+        self.linear_model._bind_lengths(self._len_names)
         dcol_pos = {c: i for i, c in enumerate(self._all_dense_cols)}
         self._dnn_dense_sel = self._selector([dcol_pos[c] for c in _expand_cols(self.feature_index, self._dnn_dense)],
                                              len(self._all_dense_cols))
@@ -154,11 +212,17 @@ class BaseModel(nn.Module):
     def _selector(idx, n):
         return None if idx == list(range(n)) else idx
 
-    @staticmethod
-    def _select(t, sel):
+    def _select(self, t, sel):
+        """Columns `sel` of t (None = all).  The index tensor lives on the device and is built once: indexing with a Python list
+        would copy it host -> device on every call, which a CUDA-graph capture of the step does not allow."""
         if sel is None:
             return t
-        return t[:, sel].contiguous()
+        cache = self.__dict__.setdefault("_sel_cache", {})
+        key = (tuple(sel), t.device)
+        idx = cache.get(key)
+        if idx is None:
+            idx = cache[key] = torch.tensor(list(sel), dtype=torch.int64, device=t.device)
+        return torch.index_select(t, 1, idx)
 
     # ------------------------------------------------------------------------------------------
     # inputs
@@ -178,7 +242,14 @@ class BaseModel(nn.Module):
             return ShardedGather.apply(sh, ids, sh.anchor)
         self._tables_current(self._emb_plan, ids)
         tables = [emb.weight for emb in self.embedding_dict.values()]
-        return ops.SparseGather.apply(self._emb_plan, self._seg_cache, ids, *tables)
+        emb = ops.SparseGather.apply(self._emb_plan, self._seg_cache, ids, *tables)
+        if self._emb_bag is not None:       # multi-value features: [B, slots, D] -> [B, fields, D]
+            emb = ops.BagPool.apply(self._emb_bag, emb, ids, self._lens(ids_all))
+        return emb
+
+    def _lens(self, ids_all):
+        """int32 [B, n_length_columns] sequence lengths of the batch (None without length columns)."""
+        return self._select(ids_all, self._len_sel) if self._len_sel else None
 
     def linear_logit(self, ids_all, dense_all):
         ids = self._select(ids_all, self._lin_sparse_sel)
@@ -189,7 +260,7 @@ class BaseModel(nn.Module):
             has_w = len(self.linear_model.dense_feature_columns) > 0
             return ShardedLinearTerm.apply(sh, ids, dense if has_w else None, self.linear_model.weight if has_w else None, sh.anchor)
         self._tables_current(self.linear_model._plan, ids)
-        return self.linear_model.forward_ids(ids, dense, cache=self._seg_cache)
+        return self.linear_model.forward_ids(ids, dense, cache=self._seg_cache, lens=self._lens(ids_all))
 
     def _tables_current(self, plan, ids):
         """Lazy dense-table semantics (optim.FusedOptimizer): rows the optimizer has postponed are replayed before they are read --
@@ -206,14 +277,18 @@ class BaseModel(nn.Module):
 
     def input_from_feature_columns(self, X, feature_columns, embedding_dict, support_dense=True):
         """Reference-shaped helper (basemodel.py:354-380): ([B,1,D] per sparse feature, [B,w] per dense feature)."""
-        sp, de = sparse_columns(feature_columns), dense_columns(feature_columns)
+        sp, de, vl = sparse_columns(feature_columns), dense_columns(feature_columns), varlen_columns(feature_columns)
         if not support_dense and len(de) > 0:
             raise ValueError("DenseFeat is not supported in dnn_feature_columns")
-        ids, _ = ops.split_input(X, _expand_cols(self.feature_index, sp), [])
-        plan = _make_plan(sp, embedding_dict, sp[0].embedding_dim) if sp else None
+        ids, _ = ops.split_input(X, _slot_cols(self.feature_index, sp, vl), [])
+        plan = _make_plan(sp, embedding_dict, (sp + vl)[0].embedding_dim, vl) if (sp or vl) else None
         emb_list = []
-        if sp:
+        if sp or vl:
             emb = ops.SparseGather.apply(plan, ops.SegmentCache(), ids, *[e.weight for e in embedding_dict.values()])
+            if vl:
+                names = _length_names(vl)
+                lens = ops.split_input(X, [self.feature_index[n][0] for n in names], [])[0] if names else None
+                emb = ops.BagPool.apply(_make_bag(sp, vl, names), emb, ids, lens)
             emb_list = list(torch.split(emb, 1, dim=1))
         dense_list = [X[:, self.feature_index[fc.name][0]:self.feature_index[fc.name][1]] for fc in de]
         return emb_list, dense_list
@@ -328,6 +403,8 @@ class BaseModel(nn.Module):
         from .. import distributed
         if self._dist is not None:
             raise RuntimeError("distribute() was already called on this model")
+        if self._all_varlen:
+            raise NotImplementedError("distribute(): VarLenSparseFeat columns are looked up on one GPU only in this build")
         distributed.attach(self, group, max_batch)
         if self._optimizer_spec is not None:
             self.optim = self._get_optim(self._optimizer_spec)     # re-bind the optimizer to the sharded tables
@@ -421,10 +498,23 @@ class BaseModel(nn.Module):
         names = list(self.feature_index.keys())
         by_name = dict(zip(names, x))
         n = x[0].shape[0] if x else 0
-        ids = np.empty((n, len(self._all_sparse)), dtype=np.int32)
+        ids = np.empty((n, len(self._all_sparse_cols)), dtype=np.int32)
         for j, fc in enumerate(self._all_sparse):
             col = np.asarray(by_name[fc.name]).reshape(n, -1)[:, 0]
             ids[:, j] = col.astype(np.int64) if col.dtype.kind in "fc" else col   # truncation == .long()
+        j = len(self._all_sparse)
+        for fc in self._all_varlen:         # [n, maxlen] id matrix per multi-value feature
+            a = np.asarray(by_name[fc.name]).reshape(n, -1)
+            if a.shape[1] != fc.maxlen:
+                raise ValueError("feature '%s': expected %d positions per sample, got %d" % (fc.name, fc.maxlen, a.shape[1]))
+            ids[:, j:j + fc.maxlen] = a.astype(np.int64) if a.dtype.kind in "fc" else a
+            if n and (ids[:, j:j + fc.maxlen].min() < 0 or ids[:, j:j + fc.maxlen].max() >= fc.vocabulary_size):
+                raise IndexError("feature '%s': id out of range [0, %d)" % (fc.name, fc.vocabulary_size))
+            j += fc.maxlen
+        for name in self._len_names:
+            col = np.asarray(by_name[name]).reshape(n, -1)[:, 0]
+            ids[:, j] = col.astype(np.int64) if col.dtype.kind in "fc" else col
+            j += 1
         dense = np.empty((n, len(self._all_dense_cols)), dtype=np.float32)
         j = 0
         for fc in self._all_dense:

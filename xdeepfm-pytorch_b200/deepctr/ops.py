@@ -244,6 +244,66 @@ class LinearTerm(torch.autograd.Function):
         return (None, None, None, None, d_dense_w) + table_grads
 
 
+class BagLayout:
+    """Slots -> fields map of one lookup with multi-value (VarLenSparseFeat) features (csrc/bag.cu).
+
+    fields: list of (n_slots, mode, lencol): mode in 'single' | 'sum' | 'mean' | 'max' (the feature's `combiner`),
+    lencol = column of the `lens` tensor holding the sequence length, or -1 for the id != 0 mask (inputs.py:141-155)."""
+
+    def __init__(self, fields):
+        self.F = len(fields)
+        slot0, next_slot = [], 0
+        for n, mode, _ in fields:
+            if mode not in N.BAG:
+                raise ValueError("parameter mode should in [sum, mean, max]")
+            slot0.append(next_slot)
+            next_slot += int(n)
+        self.S = next_slot
+        if self.S > N.MAX_FIELDS:
+            raise ValueError("sparse features + sequence positions looked up together: %d, at most %d are supported" % (self.S, N.MAX_FIELDS))
+        self.any_max = any(mode == "max" for _, mode, _ in fields)
+        self.nlen = 1 + max([lc for _, _, lc in fields] + [-1])
+        self._c_slot0 = N.i32_array(slot0)
+        self._c_slen = N.i32_array([n for n, _, _ in fields])
+        self._c_mode = N.i32_array([N.BAG[mode] for _, mode, _ in fields])
+        self._c_lencol = N.i32_array([lc for _, _, lc in fields])
+
+
+class BagPool(torch.autograd.Function):
+    """slot tensor [B, S, D] -> field tensor [B, F, D]: fixed fields copied, sequence fields pooled under their mask."""
+
+    @staticmethod
+    def forward(ctx, lay, emb, ids, lens):
+        require_cuda(emb, "BagPool")
+        emb = _f32c(emb)
+        B, S, D = emb.shape
+        if S != lay.S or tuple(ids.shape) != (B, S) or ids.dtype != torch.int32:
+            raise ValueError("BagPool: slot tensor %s / ids %s %s do not match the layout (%d slots)" % (
+                tuple(emb.shape), tuple(ids.shape), ids.dtype, lay.S))
+        if lay.nlen > 0 and (lens is None or lens.dtype != torch.int32 or tuple(lens.shape) != (B, lay.nlen)):
+            raise ValueError("BagPool: lens must be int32 [B, %d]" % lay.nlen)
+        ids = ids.contiguous()
+        lens = lens.contiguous() if lay.nlen > 0 else None
+        out = torch.empty((B, lay.F, D), dtype=torch.float32, device=emb.device)
+        argmax = torch.empty((B, lay.F, D), dtype=torch.int32, device=emb.device) if lay.any_max else None
+        with timed("bag_pool"):
+            N.check(N.lib().xdfm_bag_pool_fwd(N.ptr(emb), N.ptr(ids), N.ptr(lens), lay.nlen, B, S, D, lay.F, lay._c_slot0, lay._c_slen,
+                                              lay._c_mode, lay._c_lencol, N.ptr(out), N.ptr(argmax), N.stream_ptr()))
+        ctx.lay, ctx.ids, ctx.lens, ctx.argmax, ctx.shape = lay, ids, lens, argmax, (B, S, D)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lay = ctx.lay
+        B, S, D = ctx.shape
+        dout = _f32c(dout)
+        demb = torch.empty((B, S, D), dtype=torch.float32, device=dout.device)
+        with timed("bag_pool"):
+            N.check(N.lib().xdfm_bag_pool_bwd(N.ptr(dout), N.ptr(ctx.ids), N.ptr(ctx.lens), lay.nlen, N.ptr(ctx.argmax), B, S, D, lay.F,
+                                              lay._c_slot0, lay._c_slen, lay._c_mode, lay._c_lencol, N.ptr(demb), N.stream_ptr()))
+        return None, demb, None, None
+
+
 # ------------------------------------------------------------------------------------------------
 # CIN
 # ------------------------------------------------------------------------------------------------
