@@ -278,6 +278,7 @@ int xdfm_small_linear_bwd_dw(const float* x, const float* dy0, const float* dy1,
  * positions + 1e-8); lencol[f] >= 0 -> j < lens[b, lencol[f]] ('mean' divides by that length + 1e-8, as given).  MAX reduces
  * x - (1 - mask) * 1e9 and records the winning position per element in argmax [B, F, D] (required when any field is MAX; first
  * position wins ties).  ids int32 [B, S] are the ids the slot tensor was gathered with; lens int32 [B, nlen] or NULL.
+ * den float [B, F] (required when any field is MEAN): the forward stores each MEAN field's divisor there for the backward.
  * slot0 / slen / mode / lencol are HOST arrays [F]; S, F <= 64.  bwd: demb [B, S, D] = d(sum out * dout)/d emb. */
 #define XDFM_BAG_SINGLE 0
 #define XDFM_BAG_SUM 1
@@ -285,10 +286,10 @@ int xdfm_small_linear_bwd_dw(const float* x, const float* dy0, const float* dy1,
 #define XDFM_BAG_MAX 3
 int xdfm_bag_pool_fwd(const float* emb, const int32_t* ids, const int32_t* lens, int nlen, int64_t B, int S, int D, int F,
                       const int32_t* slot0, const int32_t* slen, const int32_t* mode, const int32_t* lencol, float* out,
-                      int32_t* argmax, void* stream);
-int xdfm_bag_pool_bwd(const float* dout, const int32_t* ids, const int32_t* lens, int nlen, const int32_t* argmax, int64_t B, int S,
-                      int D, int F, const int32_t* slot0, const int32_t* slen, const int32_t* mode, const int32_t* lencol,
-                      float* demb, void* stream);
+                      int32_t* argmax, float* den, void* stream);
+int xdfm_bag_pool_bwd(const float* dout, const int32_t* ids, const int32_t* lens, int nlen, const int32_t* argmax, const float* den,
+                      int64_t B, int S, int D, int F, const int32_t* slot0, const int32_t* slen, const int32_t* mode,
+                      const int32_t* lencol, float* demb, void* stream);
 
 /* ---- xDeepFM Pro: Supervised-Feature-Generation loss (deepctr/xdeepfm_pro/sfg_decoder.py:266-309).
  * row_w[b] = mask_b / num (mask = label == 1, num = sum(mask) + 1e-8 when positive_only; else 1 / B);

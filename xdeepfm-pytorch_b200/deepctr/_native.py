@@ -94,8 +94,8 @@ _SIGS = {
     "xdfm_autodis_bwd_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int]),
     "xdfm_autodis_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P]),
     "xdfm_bag_pool_fwd": (c_int, [_P, _P, _P, c_int, c_int64, c_int, c_int, c_int, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32),
-                                  POINTER(c_int32), _P, _P, _P]),
-    "xdfm_bag_pool_bwd": (c_int, [_P, _P, _P, c_int, _P, c_int64, c_int, c_int, c_int, POINTER(c_int32), POINTER(c_int32),
+                                  POINTER(c_int32), _P, _P, _P, _P]),
+    "xdfm_bag_pool_bwd": (c_int, [_P, _P, _P, c_int, _P, _P, c_int64, c_int, c_int, c_int, POINTER(c_int32), POINTER(c_int32),
                                   POINTER(c_int32), POINTER(c_int32), _P, _P]),
     "xdfm_sfg_row_weights": (c_int, [_P, c_int64, c_int, _P, _P]),
     "xdfm_masked_ce": (c_int, [_P, _P, c_int64, _P, c_int64, c_int, _P, _P, _P]),

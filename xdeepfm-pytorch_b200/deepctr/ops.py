@@ -262,6 +262,7 @@ class BagLayout:
         if self.S > N.MAX_FIELDS:
             raise ValueError("sparse features + sequence positions looked up together: %d, at most %d are supported" % (self.S, N.MAX_FIELDS))
         self.any_max = any(mode == "max" for _, mode, _ in fields)
+        self.any_mean = any(mode == "mean" for _, mode, _ in fields)
         self.nlen = 1 + max([lc for _, _, lc in fields] + [-1])
         self._c_slot0 = N.i32_array(slot0)
         self._c_slen = N.i32_array([n for n, _, _ in fields])
@@ -286,10 +287,11 @@ class BagPool(torch.autograd.Function):
         lens = lens.contiguous() if lay.nlen > 0 else None
         out = torch.empty((B, lay.F, D), dtype=torch.float32, device=emb.device)
         argmax = torch.empty((B, lay.F, D), dtype=torch.int32, device=emb.device) if lay.any_max else None
+        den = torch.empty((B, lay.F), dtype=torch.float32, device=emb.device) if lay.any_mean else None
         with timed("bag_pool"):
             N.check(N.lib().xdfm_bag_pool_fwd(N.ptr(emb), N.ptr(ids), N.ptr(lens), lay.nlen, B, S, D, lay.F, lay._c_slot0, lay._c_slen,
-                                              lay._c_mode, lay._c_lencol, N.ptr(out), N.ptr(argmax), N.stream_ptr()))
-        ctx.lay, ctx.ids, ctx.lens, ctx.argmax, ctx.shape = lay, ids, lens, argmax, (B, S, D)
+                                              lay._c_mode, lay._c_lencol, N.ptr(out), N.ptr(argmax), N.ptr(den), N.stream_ptr()))
+        ctx.lay, ctx.ids, ctx.lens, ctx.argmax, ctx.den, ctx.shape = lay, ids, lens, argmax, den, (B, S, D)
         return out
 
     @staticmethod
@@ -299,7 +301,8 @@ class BagPool(torch.autograd.Function):
         dout = _f32c(dout)
         demb = torch.empty((B, S, D), dtype=torch.float32, device=dout.device)
         with timed("bag_pool"):
-            N.check(N.lib().xdfm_bag_pool_bwd(N.ptr(dout), N.ptr(ctx.ids), N.ptr(ctx.lens), lay.nlen, N.ptr(ctx.argmax), B, S, D, lay.F,
+            N.check(N.lib().xdfm_bag_pool_bwd(N.ptr(dout), N.ptr(ctx.ids), N.ptr(ctx.lens), lay.nlen, N.ptr(ctx.argmax), N.ptr(ctx.den), B, S, D,
+                                              lay.F,
                                               lay._c_slot0, lay._c_slen, lay._c_mode, lay._c_lencol, N.ptr(demb), N.stream_ptr()))
         return None, demb, None, None
 
