@@ -580,3 +580,58 @@ def bag_pool(emb, ids, lens, fields):
             out.append(sequence_pool(x, lens[:, lencol:lencol + 1], mode, False))
         s += n
     return torch.cat(out, dim=1)
+
+
+def varlen_feature_index(desc):
+    """build_input_features (inputs.py:99-123) for column descriptors {kind: sparse|dense|varlen, name, ...}: name -> (start, end)."""
+    index, cursor = {}, 0
+    for d in desc:
+        if d["name"] in index:
+            continue
+        width = {"sparse": 1, "dense": d.get("dim", 1), "varlen": d.get("maxlen", 1)}[d["kind"]]
+        index[d["name"]] = (cursor, cursor + width)
+        cursor += width
+        if d["kind"] == "varlen" and d.get("length_name") is not None and d["length_name"] not in index:
+            index[d["length_name"]] = (cursor, cursor + 1)
+            cursor += 1
+    return index
+
+
+def _varlen_fields(params, desc, X, prefix):
+    """sparse_embedding_list + varlen_sparse_embedding_list (basemodel.py:354-380; the linear model: basemodel.py:65-78):
+    [B, 1, W] per SparseFeat, then per VarLenSparseFeat the pooled sequence (inputs.py:141-155, 212-225), concatenated on dim 1."""
+    fi = varlen_feature_index(desc)
+    out = []
+    for d in desc:
+        if d["kind"] == "sparse":
+            a, _ = fi[d["name"]]
+            out.append(params[prefix + d["name"] + ".weight"][X[:, a].long()].unsqueeze(1))
+    for d in desc:
+        if d["kind"] == "varlen":
+            a, b = fi[d["name"]]
+            ids = X[:, a:b].long()
+            seq = params[prefix + d["name"] + ".weight"][ids]                      # [B, T, W]
+            if d.get("length_name") is None:
+                out.append(sequence_pool(seq, ids != 0, d["combiner"], True))
+            else:
+                la, lb = fi[d["length_name"]]
+                out.append(sequence_pool(seq, X[:, la:lb].long(), d["combiner"], False))
+    return torch.cat(out, dim=1)
+
+
+def varlen_xdeepfm_forward(params, desc, X, cin_layers=2, dnn_layers=2, return_parts=False):
+    """xDeepFM.forward (xdeepfm.py:79-107) for a model whose linear and deep parts use the columns `desc`, multi-value features
+    included; relu CIN with split_half, relu DNN, binary task."""
+    fi = varlen_feature_index(desc)
+    dt = params["out.bias"].dtype
+    dense = torch.cat([X[:, fi[d["name"]][0]:fi[d["name"]][1]] for d in desc if d["kind"] == "dense"], dim=-1).to(dt)
+    lin = _varlen_fields(params, desc, X, "linear_model.embedding_dict.").sum(dim=1) + dense.matmul(params["linear_model.weight"])
+    emb = _varlen_fields(params, desc, X, "embedding_dict.")
+    cin_out = cin_forward(emb, [params["cin.conv1ds.%d.weight" % k] for k in range(cin_layers)],
+                          [params["cin.conv1ds.%d.bias" % k] for k in range(cin_layers)], True, "relu", pool=True)
+    dnn_out = dnn_forward(torch.cat([emb.reshape(emb.shape[0], -1), dense], dim=-1),
+                          [params["dnn.linears.%d.weight" % k] for k in range(dnn_layers)],
+                          [params["dnn.linears.%d.bias" % k] for k in range(dnn_layers)], "relu")
+    logit = lin + cin_out.matmul(params["cin_linear.weight"].t()) + dnn_out.matmul(params["dnn_linear.weight"].t())
+    y = torch.sigmoid(logit + params["out.bias"])
+    return (y, {"linear_logit": lin, "emb": emb}) if return_parts else y
