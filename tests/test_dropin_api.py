@@ -12,7 +12,9 @@ from tests.helpers import build_product_model
 def test_reference_script_imports_resolve():
     from deepctr.callbacks import EarlyStopping, History, ModelCheckpoint  # noqa: F401
     from deepctr.inputs import DenseFeat, SparseFeat, VarLenSparseFeat, build_input_features, combined_dnn_input, get_feature_names  # noqa: F401
-    from deepctr.layers import CIN, DNN, PredictionLayer  # noqa: F401
+    from deepctr.inputs import create_embedding_matrix, get_varlen_pooling_list, varlen_embedding_lookup  # noqa: F401
+    from deepctr.layers import CIN, DNN, PredictionLayer, SequencePoolingLayer  # noqa: F401
+    from deepctr.layers.sequence import SequencePoolingLayer as _SPL  # noqa: F401
     from deepctr.layers.cin_attention import AttentionPooling, CINAttention, CINAttentionV2, MultiHeadSelfAttention  # noqa: F401
     from deepctr.models import xDeepFM, xDeepFMAttention, xDeepFMAttentionV2  # noqa: F401
     from deepctr.xdeepfm_pro import (AutoDisLayer, BaseModelSFG, DenseFeatureEncoder, LabelAwareAttention, SFGDecoder, SFGLoss,  # noqa: F401
@@ -72,3 +74,27 @@ def test_python_level_errors_mirror_the_reference():
     assert SparseFeat("a", 10000, "auto").embedding_dim == 6 * int(pow(10000, 0.25))     # inputs.py:29-30
     with pytest.raises(RuntimeError):
         m.fit({"C1": torch.zeros(4).numpy(), "I1": torch.zeros(4).numpy()}, torch.zeros(4, 1).numpy(), batch_size=2, verbose=0)   # no CPU fallback
+
+
+def test_varlen_feature_column_surface_matches_the_reference():
+    """VarLenSparseFeat (inputs.py:41-77): field order, defaults, forwarded properties, hashing; column layout with a length
+    column (inputs.py:99-123); tables created for multi-value features too (inputs.py:158-180)."""
+    from deepctr.inputs import DenseFeat, SparseFeat, VarLenSparseFeat, build_input_features, create_embedding_matrix, get_feature_names
+    sf = SparseFeat("hist", 30, 8, embedding_name="item")
+    v = VarLenSparseFeat(sf, maxlen=5)
+    assert VarLenSparseFeat._fields == ("sparsefeat", "maxlen", "combiner", "length_name")
+    assert (v.combiner, v.length_name, v.maxlen) == ("mean", None, 5)
+    assert (v.name, v.vocabulary_size, v.embedding_dim, v.use_hash, v.dtype, v.embedding_name, v.group_name) == \
+        ("hist", 30, 8, False, "int32", "item", "default_group")
+    assert hash(v) == hash("hist")
+    cols = [SparseFeat("item", 30, 8), VarLenSparseFeat(sf, 5, "sum", length_name="hist_len"), DenseFeat("price", 2),
+            VarLenSparseFeat(SparseFeat("tags", 9, 8), 3, "max")]
+    fi = build_input_features(cols)
+    assert list(fi.items()) == [("item", (0, 1)), ("hist", (1, 6)), ("hist_len", (6, 7)), ("price", (7, 9)), ("tags", (9, 12))]
+    assert get_feature_names(cols) == ["item", "hist", "hist_len", "price", "tags"]
+    tables = create_embedding_matrix(cols, init_std=1e-4)
+    assert {k: tuple(t.weight.shape) for k, t in tables.items()} == {"item": (30, 8), "tags": (9, 8)}        # shared table 'item'
+    lin = create_embedding_matrix(cols, linear=True)
+    assert {k: tuple(t.weight.shape) for k, t in lin.items()} == {"item": (30, 1), "tags": (9, 1)}
+    with pytest.raises(TypeError):
+        build_input_features([type("Other", (), {"name": "x"})()])               # inputs.py:121-122
