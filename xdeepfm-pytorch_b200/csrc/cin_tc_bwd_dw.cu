@@ -338,6 +338,10 @@ __global__ void __launch_bounds__(256) cin_db_cols_kernel(const __nv_bfloat16* _
 static int round_up_w(int a, int b) { return (a + b - 1) / b * b; }
 extern int g_cin_tc_cluster_shared;
 
+// 0 = automatic (two fields per CTA whenever two accumulators + a two-slot A ring fit the 512 TMEM columns), 1 = one field per CTA
+static int g_cin_dw_force_jp = 0;
+extern "C" void xdfm_cin_dw_set_jp(int v) { g_cin_dw_force_jp = (v == 1) ? 1 : 0; }
+
 struct CinDwGeom {
   int HpQ, H_pad, mP, JP, n_jgroups, n_jgroups_padded, n_splits, ns, a_slots, a_col0, cluster;
   int64_t chunks_total, chunks_per_split;
@@ -353,6 +357,7 @@ static int cin_dw_geom(int64_t B, int m, int Hp, int H, int D, CinDwGeom* g) {
   g->H_pad = round_up_w(H, 16);
   g->mP = round_up_w(m, 8);
   g->JP = (2 * g->H_pad + 64 <= 512) ? 2 : 1;
+  if (g_cin_dw_force_jp == 1) g->JP = 1;       // experiment switch (xdfm_cin_dw_set_jp): one field per CTA -> deeper A ring in TMEM
   g->a_col0 = round_up_w(g->JP * g->H_pad, 32);
   g->a_slots = std::min(DW_MAX_ASLOTS, (512 - g->a_col0) / 32);
   g->n_jgroups = (m + g->JP - 1) / g->JP;

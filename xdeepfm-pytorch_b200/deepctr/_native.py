@@ -106,6 +106,7 @@ _SIGS = {
     "xdfm_set_rows_opt_dense_version": (None, [c_int]),
     "xdfm_cin_dx_set_debug": (None, [c_int]),
     "xdfm_cin_dx_set_groups": (None, [c_int]),
+    "xdfm_cin_dw_set_jp": (None, [c_int]),
     "xdfm_cin_dx_set_pair": (None, [c_int]),
     "xdfm_opt_tick_hist": (c_int, [_P, POINTER(OptCfg), _P, c_int64, c_int64, _P]),
     "xdfm_rows_catchup": (c_int, [POINTER(OptCfg), _P, _P, c_int64, POINTER(_P), POINTER(_P), POINTER(_P), _P, POINTER(c_int64), c_int, c_int,
@@ -145,6 +146,8 @@ def lib():
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
+    if os.environ.get("XDFM_CIN_DW_JP") == "1":      # experiment switch (profiles/r01d_cin_dw_findings.md); default: automatic
+        L.xdfm_cin_dw_set_jp(1)
     _lib = L
     return L
 
