@@ -205,6 +205,8 @@ static int bag_layout(const int32_t* slot0, const int32_t* slen, const int32_t* 
   return XDFM_OK;
 }
 
+static inline bool bag_al16(const void* p) { return ((uintptr_t)p & 15) == 0; }      // NULL counts as aligned
+
 static inline int bag_grid(int64_t total) {
   const int64_t want = ceil_div64(total, 256);
   const int64_t cap = (int64_t)xdfm_num_sms() * 64;
@@ -221,7 +223,7 @@ extern "C" int xdfm_bag_pool_fwd(const float* emb, const int32_t* ids, const int
   if (B == 0) return XDFM_OK;
   XDFM_CHECK_ARG(emb && ids && out, "bag_pool_fwd: NULL tensor");
   cudaStream_t st = (cudaStream_t)stream;
-  const int vec = (D % 4 == 0) ? 4 : 1;
+  const int vec = (D % 4 == 0 && bag_al16(emb) && bag_al16(out) && bag_al16(argmax)) ? 4 : 1;     // views may start mid-row
   const int64_t total = B * F * (D / vec);
   const bool small = total < (1ll << 31);
 #define BAG_FWD(V, IT) bag_pool_fwd_kernel<V, IT><<<bag_grid(total), 256, 0, st>>>(emb, ids, lens, nlen, B, S, D, F, lay, out, argmax, den)
@@ -242,7 +244,7 @@ extern "C" int xdfm_bag_pool_bwd(const float* dout, const int32_t* ids, const in
   if (B == 0) return XDFM_OK;
   XDFM_CHECK_ARG(dout && ids && demb, "bag_pool_bwd: NULL tensor");
   cudaStream_t st = (cudaStream_t)stream;
-  const int vec = (D % 4 == 0) ? 4 : 1;
+  const int vec = (D % 4 == 0 && bag_al16(dout) && bag_al16(demb) && bag_al16(argmax)) ? 4 : 1;
   const int64_t total = B * S * (D / vec);
   const bool small = total < (1ll << 31);
 #define BAG_BWD(V, IT) bag_pool_bwd_kernel<V, IT><<<bag_grid(total), 256, 0, st>>>(dout, ids, lens, nlen, argmax, den, B, S, D, F, lay, demb)
