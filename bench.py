@@ -228,7 +228,7 @@ def cpu_reference_steps(spec, batch, steps, warmup, seed=2025):
             loss, total = O.train_loss(params, spec, X, y)
             total.backward()
             opt.step()
-        return float(loss)
+        return float(loss.detach())
 
     for i in range(warmup):
         one_step(i)
@@ -451,9 +451,10 @@ def main():
             "steps; in the timed region they run as nodes of a replayed CUDA graph: %s" % (launches_per_step, args.steps, graphed),
             "host_enqueue_ms_per_step": host_enqueue_ms, "roofline": roofline}
     if not args.no_cpu_baseline and world == 1:
-        # bounded CPU sample in a separate process (the reference package shares the name `deepctr` with the product)
+        # bounded CPU sample (~10 s of host work on the box's cores) in a separate process (the reference package shares the name
+        # `deepctr` with the product)
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1",
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "40" if args.workload in ("cfg1", "cfg2") else "10", "--warmup", "1",
                                 "--workload", args.workload, "--ref-batch", str(args.ref_batch),
                                 "--ref-vocab-cap", str(args.ref_vocab_cap)], capture_output=True, text=True, timeout=600)
             ref = json.loads(r.stdout.strip().splitlines()[-1])
