@@ -1,31 +1,39 @@
-"""Small host helpers kept from the reference surface (deepctr/layers/utils.py:12-70)."""
+"""Host helpers of the reference surface (deepctr/layers/utils.py:12-70): `concat_fun`, `slice_arrays`."""
 import numpy as np
 import torch
 
 
 def concat_fun(inputs, axis=-1):
-    return inputs[0] if len(inputs) == 1 else torch.cat(inputs, dim=axis)
+    """One tensor: returned as is; several: concatenated along `axis`."""
+    if len(inputs) == 1:
+        return inputs[0]
+    return torch.cat(inputs, dim=axis)
+
+
+def _take(a, sel, stop):
+    """a[sel:stop] for an integer `sel`, a[sel] (fancy indexing) when `sel` is an index list; None stays None."""
+    if a is None:
+        return None
+    return a[sel] if isinstance(sel, list) else a[sel:stop]
 
 
 def slice_arrays(arrays, start=None, stop=None):
-    """arrays[start:stop] for one array or a list of arrays; `start` may also be a list/array of indices."""
+    """Row slice of one array or of every array of a list (fit()'s validation_split and batch slicing).
+
+    `start` is an int (with `stop`) or a list / ndarray of row indices (then `stop` must be None).  A one-element list
+    gives back the sliced array itself, as the reference does."""
     if arrays is None:
         return [None]
-    if isinstance(arrays, np.ndarray):
-        arrays = [arrays]
+    if isinstance(start, np.ndarray):
+        start = start.tolist()
     if isinstance(start, list) and stop is not None:
         raise ValueError("The stop argument has to be None if the value of start is a list.")
-    by_index = hasattr(start, "__len__")
-    if by_index and hasattr(start, "shape"):
-        start = start.tolist()
-    if isinstance(arrays, list):
-        if by_index:
-            return [None if x is None else x[start] for x in arrays]
-        if len(arrays) == 1:
-            return arrays[0][start:stop]
-        return [None if x is None else x[start:stop] for x in arrays]
-    if by_index:
-        return arrays[start]
-    if hasattr(start, "__getitem__"):
-        return arrays[start:stop]
-    return [None]
+    if isinstance(arrays, np.ndarray):
+        arrays = [arrays]
+    if not isinstance(arrays, list):
+        if isinstance(start, list) or hasattr(start, "__getitem__"):
+            return _take(arrays, start, stop)
+        return [None]
+    if len(arrays) == 1 and not isinstance(start, list):
+        return _take(arrays[0], start, stop)
+    return [_take(a, start, stop) for a in arrays]

@@ -26,7 +26,7 @@ from .. import ops
 from ..callbacks import CallbackList, History
 from ..inputs import (DenseFeat, SparseFeat, VarLenSparseFeat, build_input_features, create_embedding_matrix,
                       dense_columns, sparse_columns, table_rows, varlen_columns)
-from ..layers import PredictionLayer
+from ..layers import CIN, DNN, PredictionLayer
 from ..layers.utils import slice_arrays
 from ..optim import FusedOptimizer, TableSet
 
@@ -207,6 +207,42 @@ class BaseModel(nn.Module):
         self._graphs, self._graph_seen, self._graph_failed = {}, {}, False
         self._capturing_half = False
         self._capturing = False
+
+    # ------------------------------------------------------------------------------------------
+    # sub-network builders shared by xDeepFM, the attention variants and xDeepFM Pro.  Modules are created in the reference's
+    # order (deep tower, its head, CIN, its head) so that a seeded construction draws the same initial weights, and registered
+    # under the reference's attribute names (state_dict keys).
+    # ------------------------------------------------------------------------------------------
+    def _add_deep_tower(self, columns, hidden_units, activation, l2, dropout, use_bn, init_std, device, input_dim=None):
+        """`dnn` + `dnn_linear` over the flattened field embeddings and dense values (reference: xdeepfm.py:50-60).  L2 group:
+        the tower's weight matrices (no biases, no BatchNorm parameters) and the head."""
+        self.dnn_hidden_units = hidden_units
+        self.use_dnn = len(columns) > 0 and len(hidden_units) > 0
+        if not self.use_dnn:
+            return
+        width = self.compute_input_dim(columns) if input_dim is None else input_dim
+        self.dnn = DNN(width, hidden_units, activation=activation, l2_reg=l2, dropout_rate=dropout, use_bn=use_bn,
+                       init_std=init_std, device=device)
+        self.dnn_linear = nn.Linear(hidden_units[-1], 1, bias=False).to(device)
+        decayed = [(n, w) for n, w in self.dnn.named_parameters() if "weight" in n and "bn" not in n]
+        self.add_regularization_weight(decayed, l2=l2)
+        self.add_regularization_weight(self.dnn_linear.weight, l2=l2)
+
+    def _add_cin(self, columns, layer_size, split_half, l2, device, make_cin, head_width=None):
+        """`cin` + `cin_linear` (reference: xdeepfm.py:62-75).  `make_cin(field_num)` builds the interaction module;
+        featuremap_num = what the pooled CIN emits: every layer's direct half, the whole last layer (or all maps without split_half).
+        L2 group: every CIN parameter whose name contains 'weight'."""
+        self.cin_layer_size = layer_size
+        self.use_cin = len(layer_size) > 0 and len(columns) > 0
+        if not self.use_cin:
+            return
+        maps = sum(layer_size)
+        if split_half:
+            maps = sum(layer_size[:-1]) // 2 + layer_size[-1]
+        self.featuremap_num = maps
+        self.cin = make_cin(len(self.embedding_dict))
+        self.cin_linear = nn.Linear(maps if head_width is None else head_width, 1, bias=False).to(device)
+        self.add_regularization_weight([(n, w) for n, w in self.cin.named_parameters() if "weight" in n], l2=l2)
 
     @staticmethod
     def _selector(idx, n):

@@ -1,9 +1,8 @@
 """xDeepFM (reference: deepctr/models/xdeepfm.py:16-107): Linear + CIN + DNN -> sigmoid, on the fused B200 ops."""
 import torch
-import torch.nn as nn
 
 from .. import ops
-from ..layers import CIN, DNN
+from ..layers import CIN
 from .basemodel import BaseModel
 
 
@@ -22,27 +21,9 @@ class xDeepFM(BaseModel):
                  dnn_activation='relu', dnn_use_bn=False, task='binary', device='cpu', gpus=None):
         super().__init__(linear_feature_columns, dnn_feature_columns, l2_reg_linear=l2_reg_linear,
                          l2_reg_embedding=l2_reg_embedding, init_std=init_std, seed=seed, task=task, device=device, gpus=gpus)
-        self.dnn_hidden_units = dnn_hidden_units
-        self.use_dnn = len(dnn_feature_columns) > 0 and len(dnn_hidden_units) > 0
-        if self.use_dnn:
-            self.dnn = DNN(self.compute_input_dim(dnn_feature_columns), dnn_hidden_units, activation=dnn_activation,
-                           l2_reg=l2_reg_dnn, dropout_rate=dnn_dropout, use_bn=dnn_use_bn, init_std=init_std, device=device)
-            self.dnn_linear = nn.Linear(dnn_hidden_units[-1], 1, bias=False).to(device)
-            self.add_regularization_weight(
-                filter(lambda x: 'weight' in x[0] and 'bn' not in x[0], self.dnn.named_parameters()), l2=l2_reg_dnn)
-            self.add_regularization_weight(self.dnn_linear.weight, l2=l2_reg_dnn)
-
-        self.cin_layer_size = cin_layer_size
-        self.use_cin = len(self.cin_layer_size) > 0 and len(dnn_feature_columns) > 0
-        if self.use_cin:
-            field_num = len(self.embedding_dict)
-            if cin_split_half:
-                self.featuremap_num = sum(cin_layer_size[:-1]) // 2 + cin_layer_size[-1]
-            else:
-                self.featuremap_num = sum(cin_layer_size)
-            self.cin = CIN(field_num, cin_layer_size, cin_activation, cin_split_half, l2_reg_cin, seed, device=device)
-            self.cin_linear = nn.Linear(self.featuremap_num, 1, bias=False).to(device)
-            self.add_regularization_weight(filter(lambda x: 'weight' in x[0], self.cin.named_parameters()), l2=l2_reg_cin)
+        self._add_deep_tower(dnn_feature_columns, dnn_hidden_units, dnn_activation, l2_reg_dnn, dnn_dropout, dnn_use_bn, init_std, device)
+        self._add_cin(dnn_feature_columns, cin_layer_size, cin_split_half, l2_reg_cin, device,
+                      lambda fields: CIN(fields, cin_layer_size, cin_activation, cin_split_half, l2_reg_cin, seed, device=device))
         self.to(device)
 
     def cin_output(self, emb):

@@ -1,8 +1,5 @@
 """xDeepFM with attention-pooled CIN (reference: deepctr/models/xdeepfm_attn.py:25-301) on the fused B200 ops."""
-import torch.nn as nn
-
 from ..inputs import SparseFeat, VarLenSparseFeat
-from ..layers import DNN
 from ..layers.cin_attention import CINAttention, CINAttentionV2
 from .basemodel import BaseModel
 from .xdeepfm import xDeepFM
@@ -11,17 +8,6 @@ from .xdeepfm import xDeepFM
 class _xDeepFMAttnBase(BaseModel):
     forward_ids = xDeepFM.forward_ids
     cin_output = xDeepFM.cin_output
-
-    def _build_dnn(self, dnn_feature_columns, dnn_hidden_units, dnn_activation, l2_reg_dnn, dnn_dropout, dnn_use_bn, init_std, device):
-        self.dnn_hidden_units = dnn_hidden_units
-        self.use_dnn = len(dnn_feature_columns) > 0 and len(dnn_hidden_units) > 0
-        if self.use_dnn:
-            self.dnn = DNN(self.compute_input_dim(dnn_feature_columns), dnn_hidden_units, activation=dnn_activation,
-                           l2_reg=l2_reg_dnn, dropout_rate=dnn_dropout, use_bn=dnn_use_bn, init_std=init_std, device=device)
-            self.dnn_linear = nn.Linear(dnn_hidden_units[-1], 1, bias=False).to(device)
-            self.add_regularization_weight(
-                filter(lambda x: 'weight' in x[0] and 'bn' not in x[0], self.dnn.named_parameters()), l2=l2_reg_dnn)
-            self.add_regularization_weight(self.dnn_linear.weight, l2=l2_reg_dnn)
 
     def _get_embedding_size(self, feature_columns):
         for feat in feature_columns:
@@ -42,22 +28,13 @@ class xDeepFMAttention(_xDeepFMAttnBase):
                  gpus=None):
         super().__init__(linear_feature_columns, dnn_feature_columns, l2_reg_linear=l2_reg_linear,
                          l2_reg_embedding=l2_reg_embedding, init_std=init_std, seed=seed, task=task, device=device, gpus=gpus)
-        self._build_dnn(dnn_feature_columns, dnn_hidden_units, dnn_activation, l2_reg_dnn, dnn_dropout, dnn_use_bn, init_std, device)
-        self.cin_layer_size = cin_layer_size
-        self.use_cin = len(self.cin_layer_size) > 0 and len(dnn_feature_columns) > 0
-        if self.use_cin:
-            field_num = len(self.embedding_dict)
-            embedding_size = self._get_embedding_size(dnn_feature_columns)
-            if cin_split_half:
-                self.featuremap_num = sum(cin_layer_size[:-1]) // 2 + cin_layer_size[-1]
-            else:
-                self.featuremap_num = sum(cin_layer_size)
-            self.cin = CINAttention(field_size=field_num, embedding_size=embedding_size, layer_size=cin_layer_size,
-                                    activation=cin_activation, split_half=cin_split_half, num_heads=cin_num_heads,
-                                    attn_dropout=cin_attn_dropout, use_layer_norm=cin_use_layer_norm, use_residual=cin_use_residual,
-                                    l2_reg=l2_reg_cin, seed=seed, device=device)
-            self.cin_linear = nn.Linear(self.featuremap_num, 1, bias=False).to(device)
-            self.add_regularization_weight(filter(lambda x: 'weight' in x[0], self.cin.named_parameters()), l2=l2_reg_cin)
+        self._add_deep_tower(dnn_feature_columns, dnn_hidden_units, dnn_activation, l2_reg_dnn, dnn_dropout, dnn_use_bn, init_std, device)
+        E = self._get_embedding_size(dnn_feature_columns)
+        self._add_cin(dnn_feature_columns, cin_layer_size, cin_split_half, l2_reg_cin, device,
+                      lambda fields: CINAttention(field_size=fields, embedding_size=E, layer_size=cin_layer_size, activation=cin_activation,
+                                                  split_half=cin_split_half, num_heads=cin_num_heads, attn_dropout=cin_attn_dropout,
+                                                  use_layer_norm=cin_use_layer_norm, use_residual=cin_use_residual, l2_reg=l2_reg_cin,
+                                                  seed=seed, device=device))
         self.to(device)
 
 
@@ -71,18 +48,14 @@ class xDeepFMAttentionV2(_xDeepFMAttnBase):
                  device='cpu', gpus=None):
         super().__init__(linear_feature_columns, dnn_feature_columns, l2_reg_linear=l2_reg_linear,
                          l2_reg_embedding=l2_reg_embedding, init_std=init_std, seed=seed, task=task, device=device, gpus=gpus)
-        self._build_dnn(dnn_feature_columns, dnn_hidden_units, dnn_activation, l2_reg_dnn, dnn_dropout, dnn_use_bn, init_std, device)
-        self.cin_layer_size = cin_layer_size
-        self.use_cin = len(self.cin_layer_size) > 0 and len(dnn_feature_columns) > 0
+        self._add_deep_tower(dnn_feature_columns, dnn_hidden_units, dnn_activation, l2_reg_dnn, dnn_dropout, dnn_use_bn, init_std, device)
+        E = self._get_embedding_size(dnn_feature_columns)
+        self._add_cin(dnn_feature_columns, cin_layer_size, cin_split_half, l2_reg_cin, device,
+                      lambda fields: CINAttentionV2(field_size=fields, embedding_size=E, layer_size=cin_layer_size, activation=cin_activation,
+                                                    split_half=cin_split_half, num_heads=cin_num_heads, attn_dropout=cin_attn_dropout,
+                                                    use_layer_norm=cin_use_layer_norm, use_residual=cin_use_residual,
+                                                    num_attn_layers=cin_num_attn_layers, l2_reg=l2_reg_cin, seed=seed, device=device),
+                      head_width=E)        # the V2 block emits one attention-pooled [B, E] vector
         if self.use_cin:
-            field_num = len(self.embedding_dict)
-            embedding_size = self._get_embedding_size(dnn_feature_columns)
-            self.embedding_size_cin = embedding_size
-            self.cin = CINAttentionV2(field_size=field_num, embedding_size=embedding_size, layer_size=cin_layer_size,
-                                      activation=cin_activation, split_half=cin_split_half, num_heads=cin_num_heads,
-                                      attn_dropout=cin_attn_dropout, use_layer_norm=cin_use_layer_norm,
-                                      use_residual=cin_use_residual, num_attn_layers=cin_num_attn_layers, l2_reg=l2_reg_cin,
-                                      seed=seed, device=device)
-            self.cin_linear = nn.Linear(embedding_size, 1, bias=False).to(device)
-            self.add_regularization_weight(filter(lambda x: 'weight' in x[0], self.cin.named_parameters()), l2=l2_reg_cin)
+            self.embedding_size_cin = E
         self.to(device)

@@ -1,9 +1,8 @@
 """xDeepFMPro / xDeepFMProLight (reference: deepctr/xdeepfm_pro/xdeepfm_pro.py:19-394) on the fused B200 ops."""
 import torch
-import torch.nn as nn
 
 from .. import ops
-from ..layers import CIN, DNN
+from ..layers import CIN
 from .basemodel_sfg import BaseModelSFG
 
 
@@ -20,10 +19,10 @@ class xDeepFMPro(BaseModelSFG):
                          l2_reg_embedding=l2_reg_embedding, init_std=init_std, seed=seed, task=task, device=device, gpus=gpus,
                          use_sfg=use_sfg, sfg_weight=sfg_weight, sfg_hidden_units=sfg_hidden_units, sfg_dropout=sfg_dropout,
                          sfg_positive_only=sfg_positive_only, sfg_use_label_attention=sfg_use_label_attention)
-        self.dnn_hidden_units = dnn_hidden_units
-        self.use_dnn = len(dnn_feature_columns) > 0 and len(dnn_hidden_units) > 0
         self.use_autodis = use_autodis
         # AutoDis encoder of the dense features for the DNN branch (xdeepfm_pro.py:130-143); built before the DNN like the reference
+        self.autodis_encoder = None
+        dnn_input_dim = self.compute_input_dim(dnn_feature_columns)
         if use_autodis and len(self.dense_feature_columns) > 0:
             from .autodis import DenseFeatureEncoder
             if any(fc.dimension != 1 for fc in self.dense_feature_columns):
@@ -31,31 +30,12 @@ class xDeepFMPro(BaseModelSFG):
             self.autodis_encoder = DenseFeatureEncoder(dense_feature_names=[fc.name for fc in self.dense_feature_columns],
                                                        embedding_dim=self.embedding_dim, use_autodis=True, num_buckets=autodis_buckets,
                                                        temperature=autodis_temperature, device=device)
-            autodis_output_dim = self.autodis_encoder.get_output_dim()
-        else:
-            self.autodis_encoder = None
-            autodis_output_dim = 0
-        if self.use_dnn:
-            dnn_input_dim = self.compute_input_dim(dnn_feature_columns)
-            if self.autodis_encoder is not None:       # raw dense columns are replaced by their AutoDis embeddings (xdeepfm_pro.py:150-153)
-                dnn_input_dim += autodis_output_dim - sum(fc.dimension for fc in self.dense_feature_columns)
-            self.dnn = DNN(dnn_input_dim, dnn_hidden_units, activation=dnn_activation,
-                           l2_reg=l2_reg_dnn, dropout_rate=dnn_dropout, use_bn=dnn_use_bn, init_std=init_std, device=device)
-            self.dnn_linear = nn.Linear(dnn_hidden_units[-1], 1, bias=False).to(device)
-            self.add_regularization_weight(
-                filter(lambda x: 'weight' in x[0] and 'bn' not in x[0], self.dnn.named_parameters()), l2=l2_reg_dnn)
-            self.add_regularization_weight(self.dnn_linear.weight, l2=l2_reg_dnn)
-        self.cin_layer_size = cin_layer_size
-        self.use_cin = len(self.cin_layer_size) > 0 and len(dnn_feature_columns) > 0
-        if self.use_cin:
-            field_num = len(self.embedding_dict)
-            if cin_split_half:
-                self.featuremap_num = sum(cin_layer_size[:-1]) // 2 + cin_layer_size[-1]
-            else:
-                self.featuremap_num = sum(cin_layer_size)
-            self.cin = CIN(field_num, cin_layer_size, cin_activation, cin_split_half, l2_reg_cin, seed, device=device)
-            self.cin_linear = nn.Linear(self.featuremap_num, 1, bias=False).to(device)
-            self.add_regularization_weight(filter(lambda x: 'weight' in x[0], self.cin.named_parameters()), l2=l2_reg_cin)
+            # raw dense columns are replaced by their AutoDis embeddings in the tower's input (xdeepfm_pro.py:150-153)
+            dnn_input_dim += self.autodis_encoder.get_output_dim() - sum(fc.dimension for fc in self.dense_feature_columns)
+        self._add_deep_tower(dnn_feature_columns, dnn_hidden_units, dnn_activation, l2_reg_dnn, dnn_dropout, dnn_use_bn, init_std, device,
+                             input_dim=dnn_input_dim)
+        self._add_cin(dnn_feature_columns, cin_layer_size, cin_split_half, l2_reg_cin, device,
+                      lambda fields: CIN(fields, cin_layer_size, cin_activation, cin_split_half, l2_reg_cin, seed, device=device))
         self._last_emb = None
         self.to(device)
 
