@@ -88,8 +88,9 @@ def cin_kat():
     print("cin_kat out", kat["out"])
 
 
-def forward_backward_case(name, spec: ModelSpec, B, seed, store_params=True, grad_keys=None, zipf=False):
-    """y_pred / BCE-sum / total loss / parameter gradients of one reference train-step (no optimizer)."""
+def forward_backward_case(name, spec: ModelSpec, B, seed, store_params=True, grad_keys=None, zipf=False, grad_sample_stride=0):
+    """y_pred / BCE-sum / total loss / parameter gradients of one reference train-step (no optimizer).
+    `grad_sample_stride` > 0: tensors outside `grad_keys` also leave every stride-th element (flat order) as `gradsample::`."""
     params = make_params(spec, seed=seed)
     X, y = make_inputs(spec, B, seed=seed, zipf=zipf)
     model = build_reference_model(spec)
@@ -108,7 +109,11 @@ def forward_backward_case(name, spec: ModelSpec, B, seed, store_params=True, gra
         g = p.grad if p.grad is not None else torch.zeros_like(p)
         if grad_keys is None or k in grad_keys:
             out["grad::" + k] = g.numpy()
+        elif grad_sample_stride > 0:
+            out["gradsample::" + k] = g.flatten()[::grad_sample_stride].numpy().copy()
         out["gradnorm::" + k] = np.float64(g.double().norm().item())
+    if grad_sample_stride > 0:
+        out["grad_sample_stride"] = np.int64(grad_sample_stride)
     model.eval()
     with torch.no_grad():
         out["y_pred_eval"] = model(X).numpy()
@@ -154,8 +159,10 @@ def pro_case(name, spec: ModelSpec, B, seed):
     print(name, "loss", float(loss), "sfg", float(sfg), "total", float(total))
 
 
-def fit_case(name, spec: ModelSpec, N, batch_size, epochs, optimizer, seed, lr=None):
-    """Trajectory of the reference's own fit(): History['loss'] per epoch + final weights + predictions."""
+def fit_case(name, spec: ModelSpec, N, batch_size, epochs, optimizer, seed, lr=None, store_params=True, final_keys=None):
+    """Trajectory of the reference's own fit(): History['loss'] per epoch + final weights + predictions.
+    `store_params=False` (large shapes): seeded parameters are regenerated by the test (checksum stored), final weights are kept in
+    full for `final_keys` only and as (norm of the final tensor, norm of its movement) for every tensor."""
     params = make_params(spec, seed=seed)
     X, y = make_inputs(spec, N, seed=seed)
     model = build_reference_model(spec)
@@ -180,10 +187,18 @@ def fit_case(name, spec: ModelSpec, N, batch_size, epochs, optimizer, seed, lr=N
            "spec_json": np.array(json.dumps(spec_to_json(spec))), "seed": np.int64(seed),
            "batch_size": np.int64(batch_size), "epochs": np.int64(epochs), "optimizer": np.array(optimizer),
            "lr": np.float64(-1.0 if lr is None else lr)}
-    for k, v in params.items():
-        out["param::" + k] = v.numpy()
-    for k, v in model.state_dict().items():
-        out["final::" + k] = v.numpy()
+    if store_params:
+        for k, v in params.items():
+            out["param::" + k] = v.numpy()
+        for k, v in model.state_dict().items():
+            out["final::" + k] = v.numpy()
+    else:
+        out["param_checksum"] = np.float64(sum(v.double().sum().item() for v in params.values()))
+        for k, v in model.state_dict().items():
+            if final_keys is not None and k in final_keys:
+                out["final::" + k] = v.numpy()
+            out["finalnorm::" + k] = np.float64(v.double().norm().item())
+            out["movednorm::" + k] = np.float64((v.double() - params[k].double()).norm().item())
     np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
     print(name, "history loss", hist.history["loss"], "val_auc", hist.history["val_auc"])
 
@@ -219,6 +234,31 @@ def main():
     fit_case("fit_small_sgd", small_spec(), N=96, batch_size=32, epochs=2, optimizer="sgd", seed=12)
     fit_case("fit_small_adagrad", small_spec(), N=80, batch_size=32, epochs=2, optimizer="adagrad", seed=13)
     fit_case("fit_small_rmsprop", small_spec(), N=80, batch_size=32, epochs=2, optimizer="rmsprop", seed=14, lr=1e-3)
+
+
+def cfg2_spec(vocab=200, **kw):
+    """BASELINE.json configs[1] shape -- the configuration bench.py measures: 26 sparse + 13 dense, D = 16, CIN (200, 200, 200),
+    DNN (400, 400); vocabularies capped (the tables are not what the tensor-core path changes)."""
+    base = dict(sparse_names=["C%d" % i for i in range(1, 27)], vocab_sizes=[vocab] * 26, embedding_dim=16,
+                dense_names=["I%d" % i for i in range(1, 14)], cin_layer_size=(200, 200, 200), dnn_hidden_units=(400, 400),
+                l2_reg_linear=1e-5, l2_reg_embedding=1e-5)
+    base.update(kw)
+    return ModelSpec(**base)
+
+
+def main_cfg2():
+    """Fixtures at the benchmarked shape (`python -m oracle.make_golden cfg2`): one train step (all gradients: small tensors and CIN
+    layer 0 in full, the rest as norms + every 61st element) and a 2-epoch Adam fit() trajectory."""
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(8)
+    keep = {"embedding_dict.C1.weight", "embedding_dict.C26.weight", "linear_model.embedding_dict.C3.weight",
+            "linear_model.weight", "out.bias", "cin.conv1ds.0.bias", "cin.conv1ds.1.bias", "cin.conv1ds.2.bias", "cin_linear.weight",
+            "dnn.linears.0.bias", "dnn.linears.1.bias", "dnn_linear.weight", "cin.conv1ds.0.weight"}
+    forward_backward_case("xdeepfm_cfg2", cfg2_spec(), B=128, seed=61, store_params=False, grad_keys=keep, zipf=True,
+                          grad_sample_stride=61)
+    fit_case("fit_cfg2_adam", cfg2_spec(vocab=50), N=768, batch_size=128, epochs=2, optimizer="adam", seed=62, lr=1e-3,
+             store_params=False, final_keys={"out.bias", "cin_linear.weight", "dnn_linear.weight", "cin.conv1ds.2.bias",
+                                             "linear_model.weight", "embedding_dict.C2.weight"})
 
 
 def main_pro():
@@ -418,6 +458,8 @@ if __name__ == "__main__":
         main_autodis()
     elif len(sys.argv) > 1 and sys.argv[1] == "varlen":
         main_varlen()
+    elif len(sys.argv) > 1 and sys.argv[1] == "cfg2":
+        main_cfg2()
     else:
         main()
         main_pro()

@@ -6,9 +6,10 @@ thread (`deepctr/__init__.py:6`, `deepctr/utils.py:19-44`).  Neither exists / wo
 loader injects minimal stand-ins *before* importing the reference.  Nothing of the reference is
 modified or copied; the stand-ins only provide the Keras callback protocol the reference calls.
 
-Used by `oracle/make_golden.py` (fixture generation) and by `bench.py --impl reference` when
-`/root/reference` is present.  `/root/reference` does not exist on the GPU box, so nothing in the
-`-m gpu` tests / `smoke()` may call `load_reference()`.
+Used by `oracle/make_golden.py` (fixture generation) and by `bench.py --impl reference`.  `/root/reference` does not exist on
+the GPU box; there the loader finds the byte-for-byte copy `oracle/_ref/` made by `oracle/build_ref.py` (git-ignored, shipped
+with the snapshot).  The `-m gpu` parity tests and `smoke()` never call `load_reference()` (the product package is also named
+`deepctr`; the reference is only ever imported in its own process).
 
 Never import this from the product package.
 """
@@ -18,7 +19,18 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("XDFM_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _default_root():
+    """/root/reference in the build container; on the GPU box the byte-for-byte copy made by oracle/build_ref.py (oracle/_ref)."""
+    for cand in ("/root/reference", os.path.join(_HERE, "_ref")):
+        if os.path.isdir(os.path.join(cand, "deepctr")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = os.environ.get("XDFM_REFERENCE_ROOT") or _default_root()
 
 
 def reference_available():

@@ -10,7 +10,7 @@ from oracle.xdeepfm_oracle import ModelSpec, make_params
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 FWD_BWD_CASES = ["xdeepfm_small", "xdeepfm_small_nosplit", "xdeepfm_small_linearact", "xdeepfm_small_nodense",
-                 "xdeepfm_small_zipf", "attn_small", "attn_small_3heads", "attn_v2_small", "xdeepfm_cfg1"]
+                 "xdeepfm_small_zipf", "attn_small", "attn_small_3heads", "attn_v2_small", "xdeepfm_cfg1", "xdeepfm_cfg2"]
 PRO_CASES = ["pro_small", "pro_small_allrows_noattn", "pro_small_nodense", "pro_autodis_small", "pro_autodis_b5_nosfg"]
 FIT_CASES = ["fit_small_adam", "fit_small_sgd", "fit_small_adagrad", "fit_small_rmsprop"]
 
@@ -33,6 +33,14 @@ def load_case(name):
 
 def golden_grads(z):
     return {k[len("grad::"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("grad::")}
+
+
+def golden_gradsamples(z):
+    """{name: (stride, every stride-th element of the flattened reference gradient)} for tensors too large to store whole."""
+    if "grad_sample_stride" not in z.files:
+        return {}
+    stride = int(z["grad_sample_stride"])
+    return {k[len("gradsample::"):]: (stride, torch.from_numpy(z[k])) for k in z.files if k.startswith("gradsample::")}
 
 
 def golden_gradnorms(z):

@@ -6,12 +6,12 @@ import torch
 import torch.nn.functional as F
 
 from oracle import xdeepfm_oracle as O
-from tests.helpers import FIT_CASES, assert_close, build_product_model, golden_gradnorms, golden_grads, load_case
+from tests.helpers import FIT_CASES, assert_close, build_product_model, golden_gradnorms, golden_grads, golden_gradsamples, load_case
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 XDEEPFM_CASES = ["xdeepfm_small", "xdeepfm_small_nosplit", "xdeepfm_small_linearact", "xdeepfm_small_nodense",
-                 "xdeepfm_small_zipf", "xdeepfm_cfg1", "attn_small", "attn_small_3heads", "attn_v2_small"]
+                 "xdeepfm_small_zipf", "xdeepfm_cfg1", "xdeepfm_cfg2", "attn_small", "attn_small_3heads", "attn_v2_small"]
 
 
 @pytest.mark.parametrize("name", XDEEPFM_CASES)
@@ -40,6 +40,8 @@ def test_forward_backward_matches_reference_fixture(name):
         got = named[k].grad
         gn = 0.0 if got is None else got.double().norm().item()
         assert abs(gn - n) <= 2e-4 * max(n, 1e-6), "grad norm " + k
+    for k, (stride, g) in golden_gradsamples(z).items():
+        assert_close(named[k].grad.flatten()[::stride], g, 2e-4, 2e-5 * max(g.abs().max().item(), 1e-6), "grad sample " + k)
     model.eval()
     with torch.no_grad():
         assert_close(model(X), z["y_pred_eval"], 2e-5, 2e-6, "eval y_pred")

@@ -320,6 +320,22 @@ class ShardedSparse:
         if getattr(self, "_peer_tp", None) is not None:
             self._build_peer_ptrs()
 
+    def optimizer_state(self):
+        """This rank's moments (call after the optimizer flushed: every row is current)."""
+        return {"rank": self.rank, "G": self.G, "local_rows": self.local_rows,
+                "s1": None if self.s1 is None else self.s1.detach().clone(), "s1_lin": None if self.s1_lin is None else self.s1_lin.detach().clone(),
+                "s2": None if self.s2 is None else self.s2.detach().clone(), "s2_lin": None if self.s2_lin is None else self.s2_lin.detach().clone()}
+
+    def load_optimizer_state(self, st, steps):
+        if (st["rank"], st["G"], st["local_rows"]) != (self.rank, self.G, self.local_rows):
+            raise ValueError("shard optimizer state of rank %d/%d (%d rows) does not fit rank %d/%d (%d rows)" % (
+                st["rank"], st["G"], st["local_rows"], self.rank, self.G, self.local_rows))
+        for mine, key in ((self.s1, "s1"), (self.s1_lin, "s1_lin"), (self.s2, "s2"), (self.s2_lin, "s2_lin")):
+            if mine is not None and st[key] is not None:
+                mine.copy_(st[key])
+        self.last.fill_(int(steps))
+        self.last_lin.fill_(int(steps))
+
     # ---- forward ------------------------------------------------------------------------------------
     def gather(self, ids, want_emb=True, dense=None, dense_w=None, want_lin=False):
         B, m = ids.shape

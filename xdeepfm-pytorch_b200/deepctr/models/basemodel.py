@@ -207,6 +207,27 @@ class BaseModel(nn.Module):
         self._graphs, self._graph_seen, self._graph_failed = {}, {}, False
         self._capturing_half = False
         self._capturing = False
+        self._in_train_step = False
+
+    # Not picklable / not meaningful in another process: captured CUDA graphs (static buffers in a private pool), cached segment
+    # sorts, device index tensors.  `torch.save(model)` -- the reference's ModelCheckpoint default, callbacks.py:58-61 -- drops them;
+    # they are re-created lazily.
+    _TRANSIENT = ("_graphs", "_graph_seen", "_sel_cache", "_seg_cache", "_tob_accum", "_dist")
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        if state.get("_dist") is not None:
+            raise RuntimeError("a distributed model cannot be pickled: save model.state_dict() (collective) instead")
+        for k in self._TRANSIENT:
+            state.pop(k, None)
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._graphs, self._graph_seen, self._graph_failed = {}, {}, False
+        self._seg_cache = ops.SegmentCache()
+        self._dist = None
+        self._capturing = self._capturing_half = self._in_train_step = False
 
     # ------------------------------------------------------------------------------------------
     # sub-network builders shared by xDeepFM, the attention variants and xDeepFM Pro.  Modules are created in the reference's
@@ -303,7 +324,9 @@ class BaseModel(nn.Module):
         the looked-up rows in a training step, every row otherwise."""
         opt = getattr(self, "optim", None)
         if isinstance(opt, FusedOptimizer) and opt._dirty:
-            if self.training:
+            # "inside a training step", not module.training: the reference's fit() leaves the model in eval mode after the first
+            # validation pass (basemodel.py:202, :332), and a full flush per step would stream every table row every step
+            if self._in_train_step:
                 opt.catch_up(plan, self._seg_cache, ids)
             else:
                 opt.flush()
@@ -657,12 +680,13 @@ class BaseModel(nn.Module):
         opt = self.optim
         hp = tuple((k, v) for k, v in sorted(opt.param_groups[0].items()) if isinstance(v, (int, float, tuple)))
         prec = tuple(getattr(getattr(self, n, None), "precision", None) for n in ("cin", "dnn"))
+        flat = opt._flat["w"].data_ptr() if opt._flat is not None else 0
         return (tuple(ids.shape), tuple(dense.shape), tuple(y.shape), id(opt), hp, prec, opt._hist_base, opt.lazy_tables,
-                opt.sparse_embedding_update, self.training, getattr(self, "sfg_weight", None))
+                opt.sparse_embedding_update, self.training, getattr(self, "sfg_weight", None), flat, ops.workspace_generation())
 
     def _train_step_graphed(self, ids, dense, y, loss_accum, pred_log, pred_off):
         opt = self.optim
-        if not isinstance(opt, FusedOptimizer) or self._graph_failed or ops.TIMERS is not None or not self.training:
+        if not isinstance(opt, FusedOptimizer) or self._graph_failed or ops.TIMERS is not None:
             return None
         if self._dist is not None and type(self)._train_step_inner is not BaseModel._train_step_inner:
             return None                      # subclasses with their own step body (xDeepFM Pro) stay eager under distribution
@@ -685,6 +709,11 @@ class BaseModel(nn.Module):
                 warnings.warn("CUDA-graph capture of the training step failed (%s); staying on eager launches" % (e,))
                 self._graph_failed = True
                 return None
+            if key != self._graph_key(ids, dense, y):
+                # the capture itself grew a cached workspace (first use of a larger shape): its graph holds addresses that are
+                # still valid (the NEW buffers), but every older graph is stale -- drop them, keep this one under the new key
+                self._graphs.clear()
+                key = self._graph_key(ids, dense, y)
             if len(self._graphs) >= 4:       # a handful of batch shapes at most (full batch, last partial batch)
                 self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = st
@@ -771,9 +800,11 @@ class BaseModel(nn.Module):
                 return None
         for ts in opt.table_sets:
             ts.plan.sparse_grad = True      # backward leaves (unique rows, segment sums) for the fused optimizer
+        self._in_train_step = True
         try:
             return self._train_step_inner(opt, ids, dense, y, loss_accum, pred_log, pred_off)
         finally:
+            self._in_train_step = False
             for ts in opt.table_sets:
                 ts.plan.sparse_grad = False
 

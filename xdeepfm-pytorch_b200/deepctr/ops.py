@@ -14,6 +14,7 @@ import torch
 from . import _native as N
 
 _WS = {}
+_WS_GENERATION = [0]      # bumped whenever a cached workspace is REPLACED: CUDA graphs captured before hold the old address
 
 # optional per-operator device timing (bench.py / profiling): name -> [(start_event, end_event), ...]
 TIMERS = None
@@ -50,9 +51,16 @@ def workspace(name, nbytes, device):
     key = (name, device.index if device.index is not None else torch.cuda.current_device())
     buf = _WS.get(key)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            _WS_GENERATION[0] += 1
         buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
         _WS[key] = buf
     return buf
+
+
+def workspace_generation():
+    """Changes whenever a cached workspace was replaced by a larger one (graphs captured earlier must not be replayed)."""
+    return _WS_GENERATION[0]
 
 
 def _f32c(t):
@@ -122,17 +130,25 @@ class SparsePlan:
     def signature(self):
         return (tuple(self.table_of), tuple(self.rows))
 
+    def __reduce__(self):       # the ctypes arrays are rebuilt by the constructor (torch.save(model), copy.deepcopy)
+        return (SparsePlan, (self.table_of, self.rows, self.width))
+
 
 class SegmentCache:
-    """Sort + run-length segments of one ids tensor, reused by every lookup that shares the key space."""
+    """Sort + run-length segments of one ids tensor, reused by every lookup that shares the key space.
+
+    The key contains the device address of `ids`; the entry therefore keeps a strong reference to that tensor so the allocator
+    cannot hand the address to another batch while the entry is alive (a freed-and-recycled allocation would otherwise look
+    identical: same pointer, version 0, same shape)."""
 
     def __init__(self):
         self.key = None
         self.val = None
+        self.ids = None
 
     def get(self, plan, ids):
         key = (ids.data_ptr(), ids._version, tuple(ids.shape), plan.signature())
-        if self.key == key:
+        if self.key == key and self.ids is not None:
             return self.val
         B, m = ids.shape
         n = B * m
@@ -146,11 +162,11 @@ class SegmentCache:
         N.check(N.lib().xdfm_embed_bwd_segments(N.ptr(ids), B, m, plan._c_feat_off, plan._c_vocab, plan.row_off[-1],
                                                 N.ptr(ws), ws.numel(), N.ptr(uniq), N.ptr(seg_off), N.ptr(pos), N.ptr(nseg),
                                                 N.stream_ptr()))
-        self.key, self.val = key, (uniq, seg_off, pos, nseg, n)
+        self.key, self.val, self.ids = key, (uniq, seg_off, pos, nseg, n), ids
         return self.val
 
     def clear(self):
-        self.key = self.val = None
+        self.key = self.val = self.ids = None
 
 
 def segment_reduce(plan, seg, demb, dlin, width):
@@ -251,6 +267,7 @@ class BagLayout:
     lencol = column of the `lens` tensor holding the sequence length, or -1 for the id != 0 mask (inputs.py:141-155)."""
 
     def __init__(self, fields):
+        self.fields = [tuple(f) for f in fields]
         self.F = len(fields)
         slot0, next_slot = [], 0
         for n, mode, _ in fields:
@@ -268,6 +285,9 @@ class BagLayout:
         self._c_slen = N.i32_array([n for n, _, _ in fields])
         self._c_mode = N.i32_array([N.BAG[mode] for _, mode, _ in fields])
         self._c_lencol = N.i32_array([lc for _, _, lc in fields])
+
+    def __reduce__(self):
+        return (BagLayout, (self.fields,))
 
 
 class BagPool(torch.autograd.Function):

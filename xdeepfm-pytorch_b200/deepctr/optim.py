@@ -29,6 +29,11 @@ class TableSet:
         self.bitmap = None
         self.last = None            # int32 [total_rows]: step up to which each row is current (lazy dense semantics)
 
+    def __getstate__(self):         # moments travel through FusedOptimizer.state_dict(); scratch is rebuilt by prepare()
+        d = dict(self.__dict__)
+        d["s1"] = d["s2"] = d["bitmap"] = d["last"] = None
+        return d
+
 
 class FusedOptimizer(torch.optim.Optimizer):
     """torch.optim.Optimizer-compatible (param_groups / state_dict) front end of the fused kernels."""
@@ -111,6 +116,8 @@ class FusedOptimizer(torch.optim.Optimizer):
             k = p.numel()
             w[off:off + k].copy_(p.data.reshape(-1))
             p.data = w[off:off + k].view(p.shape)
+            if p.grad is not None:      # a backward ran before the flat views existed (user loop / generic fit path): keep its result
+                g[off:off + k].copy_(p.grad.reshape(-1))
             p.grad = g[off:off + k].view(p.shape)
             l2vec[off:off + k] = self._l2_of_param.get(id(p), 0.0)
             off += k
@@ -139,6 +146,109 @@ class FusedOptimizer(torch.optim.Optimizer):
         if self._hist is None or self._hist.device != dev:
             self._hist = torch.zeros(self._hist_cap * 4, dtype=torch.float32, device=dev)
         self._publish_lazy()
+        pending = self.__dict__.pop("_pending_state", None)
+        if pending is not None:
+            self._load_fused_state(pending)
+
+    # -------------------------------------------------------------------------------------------
+    # checkpointing (the reference saves no optimizer state; this adds it).  state_dict() settles every postponed
+    # row update first, so the saved moments are those of a dense pass and a resumed run continues bit-identically.
+    # -------------------------------------------------------------------------------------------
+    def state_dict(self):
+        """{'fused': {kind, steps, hyper-parameters, opt_dev, dense moments by parameter NAME, table moments by table-set / table
+        index}}.  Row-sharded tables: each rank's dict holds the moments of its own shard (save one file per rank)."""
+        hp = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        out = {"kind": self.kind, "steps": int(self.steps), "hyper": hp, "lazy_tables": bool(self.lazy_tables),
+               "sparse_embedding_update": bool(self.sparse_embedding_update), "flush_interval": int(self.flush_interval)}
+        if self._flat is None:
+            return {"fused": out}
+        self.flush()
+        f = self._flat
+        out["opt_dev"] = f["opt_dev"].detach().clone()
+        dense, off = {}, 0
+        for name, p in self.dense_named:
+            k = p.numel()
+            dense[name] = tuple(None if s is None else s[off:off + k].detach().clone().view(p.shape) for s in (f["s1"], f["s2"]))
+            off += k
+        out["dense"] = dense
+        out["tables"] = [{"s1": None if ts.s1 is None else [t.detach().clone() for t in ts.s1],
+                          "s2": None if ts.s2 is None else [t.detach().clone() for t in ts.s2]} for ts in self.table_sets]
+        if self.dist_ctx is not None:
+            out["shard"] = self.dist_ctx.sharded.optimizer_state()
+        return {"fused": out}
+
+    def load_state_dict(self, state_dict):
+        st = state_dict["fused"]
+        if st["kind"] != self.kind:
+            raise ValueError("optimizer state of kind %r cannot be loaded into a %r optimizer" % (st["kind"], self.kind))
+        for k, v in st["hyper"].items():
+            self.param_groups[0][k] = v
+        self.lazy_tables = st.get("lazy_tables", self.lazy_tables)
+        self.sparse_embedding_update = st.get("sparse_embedding_update", self.sparse_embedding_update)
+        self.flush_interval = st.get("flush_interval", self.flush_interval)
+        if "opt_dev" not in st:          # saved before the first step
+            self.steps = int(st["steps"])
+            return
+        if self._flat is None or not self._flat_valid():
+            self._pending_state = st     # applied at the end of prepare()
+            self.prepare()
+        else:
+            self._load_fused_state(st)
+
+    def _load_fused_state(self, st):
+        self.flush()
+        f = self._flat
+        f["opt_dev"].copy_(st["opt_dev"])
+        off = 0
+        for name, p in self.dense_named:
+            k = p.numel()
+            if name not in st["dense"]:
+                raise KeyError("optimizer state has no entry for parameter %r" % name)
+            for buf, src in zip((f["s1"], f["s2"]), st["dense"][name]):
+                if buf is not None and src is not None:
+                    buf[off:off + k].copy_(src.reshape(-1))
+            off += k
+        if len(st["tables"]) != len(self.table_sets):
+            raise ValueError("optimizer state holds %d table sets, the model has %d" % (len(st["tables"]), len(self.table_sets)))
+        self.steps = int(st["steps"])
+        for ts, saved in zip(self.table_sets, st["tables"]):
+            for mine, theirs in ((ts.s1, saved["s1"]), (ts.s2, saved["s2"])):
+                if mine is not None and theirs is not None:
+                    for a, b in zip(mine, theirs):
+                        a.copy_(b)
+            if ts.last is not None:
+                ts.last.fill_(self.steps)          # every row is current at the saved step (state_dict() flushed)
+        if self.dist_ctx is not None and "shard" in st:
+            self.dist_ctx.sharded.load_optimizer_state(st["shard"], self.steps)
+        self._hist_base = self.steps                # history slots are (step - base): a fresh window starts at the resumed step
+        self._last_flush_step = self.steps
+        self._dirty = False
+        self._publish_lazy()
+
+    def __getstate__(self):
+        """torch.save(model) (ModelCheckpoint's default): torch.optim.Optimizer pickles defaults / state / param_groups only; keep
+        this class's configuration and the moments (through state_dict()), drop device scratch and the process-group context."""
+        if self.dist_ctx is not None:
+            raise RuntimeError("the optimizer of a distributed model cannot be pickled: save optimizer.state_dict() per rank")
+        keep = dict(self.__dict__)
+        keep["_pending_state"] = self.state_dict()["fused"] if self._flat is not None else None
+        keep["_l2_dense"] = [self._l2_of_param.get(id(p), 0.0) for _, p in self.dense_named]
+        for k in ("_flat", "_hist", "_l2_of_param", "reg_accum", "reg_accum_shard", "_optimizer_step_pre_hooks",
+                  "_optimizer_step_post_hooks"):
+            keep.pop(k, None)
+        return keep
+
+    def __setstate__(self, state):
+        l2_dense = state.pop("_l2_dense")
+        pending = state.pop("_pending_state")
+        super().__setstate__(state)
+        self._l2_of_param = {id(p): l2 for (_, p), l2 in zip(self.dense_named, l2_dense) if l2 != 0.0}
+        self._flat = self._hist = self.reg_accum = self.reg_accum_shard = None
+        self._hist_base, self._dirty = 0, False
+        for ts in self.table_sets:
+            ts.s1 = ts.s2 = ts.bitmap = ts.last = None
+        if pending is not None and "opt_dev" in pending:
+            self._pending_state = pending
 
     # -------------------------------------------------------------------------------------------
     def zero_grad(self, set_to_none=True):
