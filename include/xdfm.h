@@ -206,6 +206,9 @@ void xdfm_cin_dx_set_groups(int v);
 /* experiment switch of xdfm_cin_bwd_dw_tc: 0 = automatic fields per CTA (default), 1 = one field per CTA (deeper A ring in TMEM);
  * call before xdfm_cin_bwd_dw_tc_workspace_bytes / xdfm_cin_bwd_dw_tc of a step (both read it) */
 void xdfm_cin_dw_set_jp(int v);
+/* lane packing of xdfm_cin_bwd_dw_tc for narrow X^{k-1} (HpQ <= 64: 2 or 4 fields share the 128 TMEM lanes of one accumulator):
+ * 1 = on (default), 0 = one field per accumulator (A/B tests); same calling rule as xdfm_cin_dw_set_jp */
+void xdfm_cin_dw_set_pack(int enabled);
 /* 1: dX kernel that contracts two 128-row tiles per streamed W'' field when shared memory allows; 0 (default): single-tile kernel
  * (the pair variant halves the weight stream but measured the same time in round 1: profiles/r01_cin_findings.md) */
 void xdfm_cin_dx_set_pair(int v);

@@ -304,7 +304,49 @@ DW_CASES = [
     (20, 22, 32, 256, 128),
     (9, 25, 64, 256, 26),
     (2500, 12, 16, 40, 20),
+    # lane packing (HpQ <= 64): four fields per accumulator (HpQ <= 32) / two (HpQ <= 64); field counts that leave partial groups
+    (700, 26, 16, 200, 26),       # cfg2 layer 0: 26 fields = 3 CTAs x 8 + one with 2
+    (300, 22, 32, 256, 22),       # cfg4 layer 0: one accumulator per CTA (H_pad = 256), 4 fields each, 22 = 5 x 4 + 2
+    (257, 9, 16, 48, 9),          # HpQ = 16 < lane width 32
+    (300, 13, 8, 64, 40),         # HpQ = 48: two fields per accumulator, 13 fields
+    (120, 5, 16, 24, 64),         # HpQ = 64 exactly
 ]
+
+
+@pytest.mark.parametrize("case", [c for c in DW_CASES if (c[4] + 15) // 16 * 16 <= 64], ids=str)
+def test_cin_tc_backward_dw_lane_packing_equals_one_field_per_accumulator(case):
+    """Packing only changes which TMEM lanes / CTAs hold a field: with the same r-splits the partial sums are the same numbers."""
+    from deepctr import _native as Nv
+    L = Nv.lib()
+    B, m, D, H, Hp = case
+    g = torch.Generator().manual_seed(sum(case) + 5)
+    r8 = lambda v: (v + 7) // 8 * 8
+    r16 = lambda v: (v + 15) // 16 * 16
+    x0 = torch.randn(B, m, D, generator=g) * 0.5
+    xk_full = x0 if Hp == m else torch.randn(B, 2 * Hp, D, generator=g) * 0.5
+    dy = torch.randn(B, H, D, generator=g)
+    x0t = to_rows(x0.to(DEV), r8(m))
+    xkt = x0t if Hp == m else to_rows(xk_full.to(DEV), r8(2 * Hp))
+    dyt = to_rows(dy.to(DEV), r8(H))
+    x0T, xkT, dyT = to_cols(x0t, m, r8(m)), to_cols(xkt, Hp, r16(Hp)), to_cols(dyt, H, r16(H))
+    outs = []
+    try:
+        for pack in (1, 0):
+            L.xdfm_cin_dw_set_pack(pack)
+            nb = L.xdfm_cin_bwd_dw_tc_workspace_bytes(B, m, Hp, H, D)
+            ws = torch.empty(nb, dtype=torch.uint8, device=DEV)
+            dW = torch.full((H, Hp * m), float("nan"), device=DEV)
+            db = torch.full((H,), float("nan"), device=DEV)
+            Nv.check(L.xdfm_cin_bwd_dw_tc(Nv.ptr(dyT), Nv.ptr(xkT), Nv.ptr(x0T), B, m, Hp, H, D, Nv.ptr(dW), Nv.ptr(db), Nv.ptr(ws), nb,
+                                          Nv.stream_ptr()))
+            torch.cuda.synchronize()
+            outs.append((dW, db))
+    finally:
+        L.xdfm_cin_dw_set_pack(1)
+    assert torch.isfinite(outs[0][0]).all()
+    # the number of r-splits differs between the geometries (more CTAs per r range without packing): equal up to fp32 re-association
+    assert_close(outs[0][0], outs[1][0], 1e-5, 1e-5 * outs[1][0].abs().max().item(), "dW packed vs unpacked")
+    assert torch.equal(outs[0][1], outs[1][1])
 
 
 @pytest.mark.parametrize("cluster", [1, 2])

@@ -12,6 +12,12 @@
 // H_pad columns in TMEM) and one range of r; CTAs of a cluster share the r range (different fields), so the dyT / xkT tiles are
 // fetched once per cluster and multicast.  Each CTA writes its fp32 partial [JP, HpQ, H_pad]; a second kernel sums the r-splits
 // in fixed order and un-permutes into the reference layout [H, Hp*m] (deterministic).
+//
+// Narrow X^{k-1} (layer 0: Hp = m = 26 at Criteo shape): with one field per accumulator only Hp of the 128 TMEM lanes carry data
+// and the tensor core spends 128 / Hp of the necessary MMA work.  When HpQ <= 64 the lanes are PACKED: lane = (jsub, i) with
+// LW = 128 / PACK lanes per field (PACK = 4 for HpQ <= 32, 2 for HpQ <= 64), so ONE accumulator holds dW_j^T for PACK consecutive
+// fields and a CTA owns JP * PACK fields.  A warp covers 32 lanes = one field (PACK = 4) or half a field (PACK = 2), so the x0T
+// row a thread multiplies by is still a warp-wide broadcast.
 #include "tc_common.cuh"
 #include "../../include/xdfm.h"
 
@@ -25,7 +31,8 @@ struct CinDwParams {
   float* part;                // [n_splits, m, HpQ, H_pad] fp32
   int64_t R;
   int m, Hp, HpQ, H_pad, JP;
-  int n_jgroups;              // real field groups = ceil(m / JP)
+  int PACK, LW;               // fields per accumulator (lane packing), lanes per field = 128 / PACK
+  int n_jgroups;              // real field groups = ceil(m / (JP * PACK))
   int n_jgroups_padded;       // multiple of the cluster size
   int n_splits;
   int64_t chunks_total;       // ceil(R / 64)
@@ -47,7 +54,8 @@ cin_bwd_dw_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
                      const __grid_constant__ CUtensorMap tmX0, CinDwParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t dy_bytes = (uint32_t)p.H_pad * 128, xk_bytes = (uint32_t)p.HpQ * 128, x0_bytes = (uint32_t)p.JP * 128;
+  const int FPC = p.JP * p.PACK;                                                   // fields per CTA
+  const uint32_t dy_bytes = (uint32_t)p.H_pad * 128, xk_bytes = (uint32_t)p.HpQ * 128, x0_bytes = (uint32_t)FPC * 128;
   const uint32_t stage_bytes = dy_bytes + xk_bytes + 1024;                      // x0 rows live in the last 1 KB (keeps 1024-alignment)
   uint8_t* sStage = smem;
   CinDwBars* bars = reinterpret_cast<CinDwBars*>(smem + (size_t)p.ns * stage_bytes);
@@ -57,8 +65,8 @@ cin_bwd_dw_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
   const int jgroup = blockIdx.x % p.n_jgroups_padded;
   const int split = blockIdx.x / p.n_jgroups_padded;
   const bool active = jgroup < p.n_jgroups;
-  const int j0 = jgroup * p.JP;
-  const int nj = active ? min(p.JP, p.m - j0) : 0;
+  const int j0 = jgroup * FPC;
+  const int nj = active ? min(p.JP, (p.m - j0 + p.PACK - 1) / p.PACK) : 0;        // accumulators in use (PACK fields each)
   const int64_t c_beg = (int64_t)split * p.chunks_per_split;
   const int64_t c_end = min(p.chunks_total, c_beg + p.chunks_per_split);
   const int n_chunks = (int)max((int64_t)0, c_end - c_beg);
@@ -139,8 +147,9 @@ cin_bwd_dw_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
   } else if (active) {
     // =============================== A producers (lane = channel i) + final epilogue ===============================
     const int q = warp & 3;
-    const int il = q * 32 + lane;                                  // channel index = TMEM lane
-    const int irow = min(il, p.HpQ - 1);                           // lanes past HpQ only produce rows nobody reads
+    const int il = q * 32 + lane;                                  // TMEM lane = (jsub, i): field within the accumulator, channel
+    const int jsub = il / p.LW, ich = il - jsub * p.LW;
+    const int irow = min(ich, p.HpQ - 1);                          // lanes past HpQ only produce rows nobody reads
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     uint32_t st = 0, phase = 0, as = 0, aphase = 1;
     bool a_first = true;
@@ -156,7 +165,8 @@ cin_bwd_dw_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
           mbar_wait(&bars->a_empty[as], aphase);
           fence_after_sync();
         }
-        const uint8_t* x0row = base + dy_bytes + xk_bytes + (size_t)jj * 128;    // un-swizzled (2-row box), broadcast reads
+        // un-swizzled box of FPC rows, broadcast reads (fields >= m: TMA zero fill / zero padding rows of x0T -> a zero A tile)
+        const uint8_t* x0row = base + dy_bytes + xk_bytes + (size_t)(jj * p.PACK + jsub) * 128;
         const uint32_t a_addr = tmem_base + lane_addr + (uint32_t)(p.a_col0 + as * 32);
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
@@ -190,7 +200,9 @@ cin_bwd_dw_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
     }
     // (tcgen05.ld is warp-collective: every lane runs the loads, only lanes that own a channel store)
     for (int jj = 0; jj < nj; ++jj) {
-      float* out = p.part + (((int64_t)split * p.m + (j0 + jj)) * p.HpQ + min(il, p.HpQ - 1)) * p.H_pad;
+      const int field = j0 + jj * p.PACK + jsub;
+      const bool own = ich < p.HpQ && field < p.m;
+      float* out = p.part + (((int64_t)split * p.m + min(field, p.m - 1)) * p.HpQ + irow) * p.H_pad;
       for (int c0 = 0; c0 < p.H_pad; c0 += 16) {
         uint32_t v[16];
         if (n_chunks > 0) {
@@ -200,7 +212,7 @@ cin_bwd_dw_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = 0u;
         }
-        if (il < p.HpQ) {
+        if (own) {
 #pragma unroll
           for (int i = 0; i < 16; i += 4)
             *reinterpret_cast<float4*>(out + c0 + i) =
@@ -215,16 +227,38 @@ cin_bwd_dw_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// dW[h, i*m + j] = sum_s part[s, j, i, h]  (fixed order), db[h] handled elsewhere
-__global__ void cin_dw_reduce_tc_kernel(const float* __restrict__ part, int S, int m, int Hp, int HpQ, int H, int H_pad, float* __restrict__ dW) {
-  const int64_t total = (int64_t)H * Hp * m;
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int k = (int)(e % ((int64_t)Hp * m));
-    const int h = (int)(e / ((int64_t)Hp * m));
-    const int i = k / m, j = k - i * m;
+// dW[h, i*m + j] = sum_s part[s, j, i, h]  (fixed order), db[h] handled elsewhere.
+// part is contiguous in h, dW in k = i*m + j: a 32 x 32 (k, h) tile per block goes through shared memory so that both the reads
+// (32 consecutive h per (s, j, i): one 128-byte line per warp) and the writes (32 consecutive k per h) are coalesced -- the direct
+// form read one 4-byte word per 32-byte sector, S times per output.
+__global__ void __launch_bounds__(256) cin_dw_reduce_tc_kernel(const float* __restrict__ part, int S, int m, int Hp, int HpQ, int H, int H_pad,
+                                                               float* __restrict__ dW) {
+  __shared__ float tile[32][33];
+  const int K = Hp * m;
+  const int k0 = blockIdx.x * 32, h0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 8 warps
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int k = k0 + ty * 4 + r, h = h0 + tx;
     float v = 0.f;
-    for (int s = 0; s < S; ++s) v += part[(((int64_t)s * m + j) * HpQ + i) * H_pad + h];
-    dW[e] = v;
+    if (k < K && h < H) {
+      const int i = k / m, j = k - i * m;
+      const float* src = part + ((int64_t)j * HpQ + i) * H_pad + h;
+      const int64_t sstride = (int64_t)m * HpQ * H_pad;
+      int s = 0;
+      for (; s + 4 <= S; s += 4) {                               // four loads in flight, summed in split order
+        const float a0 = src[(s + 0) * sstride], a1 = src[(s + 1) * sstride], a2 = src[(s + 2) * sstride], a3 = src[(s + 3) * sstride];
+        v += a0; v += a1; v += a2; v += a3;
+      }
+      for (; s < S; ++s) v += src[s * sstride];
+    }
+    tile[ty * 4 + r][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int h = h0 + ty * 4 + r, k = k0 + tx;
+    if (h < H && k < K) dW[(int64_t)h * K + k] = tile[tx][ty * 4 + r];
   }
 }
 
@@ -341,9 +375,12 @@ extern int g_cin_tc_cluster_shared;
 // 0 = automatic (two fields per CTA whenever two accumulators + a two-slot A ring fit the 512 TMEM columns), 1 = one field per CTA
 static int g_cin_dw_force_jp = 0;
 extern "C" void xdfm_cin_dw_set_jp(int v) { g_cin_dw_force_jp = (v == 1) ? 1 : 0; }
+// A/B switch of the lane packing (tests compare both geometries): 1 = one field per accumulator whatever the width
+static int g_cin_dw_no_pack = 0;
+extern "C" void xdfm_cin_dw_set_pack(int enabled) { g_cin_dw_no_pack = enabled ? 0 : 1; }
 
 struct CinDwGeom {
-  int HpQ, H_pad, mP, JP, n_jgroups, n_jgroups_padded, n_splits, ns, a_slots, a_col0, cluster;
+  int HpQ, H_pad, mP, JP, PACK, n_jgroups, n_jgroups_padded, n_splits, ns, a_slots, a_col0, cluster;
   int64_t chunks_total, chunks_per_split;
   size_t smem;
 };
@@ -358,9 +395,10 @@ static int cin_dw_geom(int64_t B, int m, int Hp, int H, int D, CinDwGeom* g) {
   g->mP = round_up_w(m, 8);
   g->JP = (2 * g->H_pad + 64 <= 512) ? 2 : 1;
   if (g_cin_dw_force_jp == 1) g->JP = 1;       // experiment switch (xdfm_cin_dw_set_jp): one field per CTA -> deeper A ring in TMEM
+  g->PACK = g_cin_dw_no_pack ? 1 : (g->HpQ <= 32 ? 4 : (g->HpQ <= 64 ? 2 : 1));
   g->a_col0 = round_up_w(g->JP * g->H_pad, 32);
   g->a_slots = std::min(DW_MAX_ASLOTS, (512 - g->a_col0) / 32);
-  g->n_jgroups = (m + g->JP - 1) / g->JP;
+  g->n_jgroups = (m + g->JP * g->PACK - 1) / (g->JP * g->PACK);
   int cluster = g_cin_tc_cluster_shared;
   while (cluster > 1 && (((g->H_pad / 8) % cluster) != 0 || ((g->HpQ / 8) % cluster) != 0)) cluster >>= 1;
   g->cluster = cluster;
@@ -404,10 +442,11 @@ extern "C" int xdfm_cin_bwd_dw_tc(const void* dyT, const void* xkT, const void* 
   if (rc) return rc;
   rc = xdfm_make_tmap_bf16(&tmXk, xkT, (uint64_t)g.HpQ, (uint64_t)R, (uint64_t)R * 2, (uint32_t)(g.HpQ / g.cluster), 64, 1);
   if (rc) return rc;
-  rc = xdfm_make_tmap_bf16(&tmX0, x0T, (uint64_t)g.mP, (uint64_t)R, (uint64_t)R * 2, (uint32_t)g.JP, 64, 0);
+  rc = xdfm_make_tmap_bf16(&tmX0, x0T, (uint64_t)g.mP, (uint64_t)R, (uint64_t)R * 2, (uint32_t)(g.JP * g.PACK), 64, 0);
   if (rc) return rc;
   CinDwParams p;
   p.part = (float*)workspace; p.R = R; p.m = m; p.Hp = Hp; p.HpQ = g.HpQ; p.H_pad = g.H_pad; p.JP = g.JP;
+  p.PACK = g.PACK; p.LW = 128 / g.PACK;
   p.n_jgroups = g.n_jgroups; p.n_jgroups_padded = g.n_jgroups_padded; p.n_splits = g.n_splits;
   p.chunks_total = g.chunks_total; p.chunks_per_split = g.chunks_per_split; p.ns = g.ns; p.a_slots = g.a_slots; p.a_col0 = g.a_col0;
   XDFM_CUDA(cudaFuncSetAttribute(cin_bwd_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
@@ -426,8 +465,8 @@ extern "C" int xdfm_cin_bwd_dw_tc(const void* dyT, const void* xkT, const void* 
   XDFM_CUDA(cudaLaunchKernelEx(&cfg, cin_bwd_dw_tc_kernel, tmDy, tmXk, tmX0, p));
   XDFM_LAUNCH_CHECK();
   if (dW != nullptr) {
-    int blocks = (int)std::min<int64_t>((int64_t)xdfm_num_sms() * 4, ceil_div64((int64_t)H * Hp * m, 256));
-    cin_dw_reduce_tc_kernel<<<blocks, 256, 0, st>>>((const float*)workspace, g.n_splits, m, Hp, g.HpQ, H, g.H_pad, dW);
+    dim3 rgrid((unsigned)ceil_div64((int64_t)Hp * m, 32), (unsigned)ceil_div64(H, 32));
+    cin_dw_reduce_tc_kernel<<<rgrid, 256, 0, st>>>((const float*)workspace, g.n_splits, m, Hp, g.HpQ, H, g.H_pad, dW);
     XDFM_LAUNCH_CHECK();
   }
   if (db != nullptr) {

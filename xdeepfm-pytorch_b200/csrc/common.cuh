@@ -1,5 +1,6 @@
 // Shared helpers for libxdfm_sm100a.so (sm_100a only).
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -46,6 +47,8 @@ static inline int xdfm_num_sms() {
   if (n == 0) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    const char* dbg = getenv("XDFM_DEBUG_SMS");       // profiling experiments only: size persistent grids for fewer SMs
+    if (dbg != nullptr && atoi(dbg) > 0 && atoi(dbg) < n) n = atoi(dbg);
   }
   return n;
 }

@@ -107,6 +107,7 @@ _SIGS = {
     "xdfm_cin_dx_set_debug": (None, [c_int]),
     "xdfm_cin_dx_set_groups": (None, [c_int]),
     "xdfm_cin_dw_set_jp": (None, [c_int]),
+    "xdfm_cin_dw_set_pack": (None, [c_int]),
     "xdfm_cin_dx_set_pair": (None, [c_int]),
     "xdfm_opt_tick_hist": (c_int, [_P, POINTER(OptCfg), _P, c_int64, c_int64, _P]),
     "xdfm_rows_catchup": (c_int, [POINTER(OptCfg), _P, _P, c_int64, POINTER(_P), POINTER(_P), POINTER(_P), _P, POINTER(c_int64), c_int, c_int,
