@@ -7,7 +7,11 @@ One "step" = one full training step (fused gather -> CIN -> DNN -> head -> BCE -
 fused Adam incl. the reference's dense-table L2/Adam semantics) over one batch of synthetic Criteo-shaped input.
 Prints ONE JSON line on rank 0 (see the task contract): `value` = device-resident throughput, `e2e` = the same step
 through the public `train_on_batch` API with pinned-host inputs (H2D + D2H inside the timed region), `roofline` for the
-dominant kernel (timed live with CUDA events), `cpu_baseline` = the CPU oracle port on this box's host cores.
+dominant kernel (timed live with CUDA events; `frac_incl_layout` counts the layout kernels that only serve it), `hbm_kernels`
+(embedding gather / sorted segmented scatter-add at the cfg5 shape against the measured HBM peak), `fit_e2e` / `predict_e2e`
+(the reference's own entry points `model.fit` / `model.predict` on host arrays), `cpu_baseline` = the unmodified reference
+(oracle/_ref, shipped by oracle/build_ref.py) on this box's host cores; at N > 1 `dp_parity` (N GPUs == 1 GPU on the same global
+batches, checked BEFORE timing; non-zero exit on mismatch) and `extra_workloads` (cfg4 = BASELINE configs[3]; cfg5 at N = 8).
 """
 import argparse
 import json
@@ -246,13 +250,21 @@ def run_reference_arm(args, w):
         return
     spec = make_spec(w, args.ref_vocab_cap)
     sample_batch = args.ref_batch
-    r = cpu_reference_steps(spec, sample_batch, max(1, args.steps), max(1, min(args.warmup, 1)))
-    sample = "%d-sample batches (of the %d-sample workload batch), vocab capped at %s rows/field, Adam, %d timed steps" % (
-        sample_batch, w["batch"], args.ref_vocab_cap, max(1, args.steps))
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    r = cpu_reference_steps(spec, sample_batch, steps, warmup)
+    sample = "%d-sample batches (of the %d-sample workload batch), vocab capped at %s rows/field, Adam, %d warm-up + %d timed steps" % (
+        sample_batch, w["batch"], args.ref_vocab_cap, warmup, steps)
+    cfg = workload_config(args, w)
+    # what THIS arm ran (the bounded CPU sample of the workload), next to the workload it samples
+    cfg["reference_arm"] = {"batch": sample_batch, "vocab_cap_rows_per_field": args.ref_vocab_cap,
+                            "total_rows": int(sum(spec.vocab_sizes)), "dtype": "f32", "device": "cpu", "threads": r["cores"],
+                            "implementation": "unmodified reference (oracle/_ref or /root/reference)" if r["kind"] == "reference"
+                            else "oracle port (reference tree not found)",
+                            "processes": 1}
     line = {"impl": "reference", "metric": "train samples/sec (Criteo-shape xDeepFM)", "value": r["samples_per_s"],
-            "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, w),
+            "config": cfg,
             "cpu_baseline": {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"], "sample": sample},
             "e2e": {"value": r["samples_per_s"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -279,6 +291,456 @@ def workload_config(args, w):
                             sum(w["vocab"]) * (w["D"] + 1) * 4 * 3 / 1e9)}
 
 
+# ------------------------------------------------------------------------------------------------
+# product arm
+# ------------------------------------------------------------------------------------------------
+class Env:
+    """Process-wide state of one bench run: rank / world / device, barrier + max-over-ranks helpers."""
+
+    def __init__(self):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = "cuda:%d" % self.local_rank
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device(self.dev))
+            self.dist = dist
+
+    def sync_all(self):
+        torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(self, vals):
+        if self.dist is None:
+            return list(vals)
+        t = torch.tensor(list(vals), dtype=torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
+
+def set_precision(model, cin_impl):
+    model.cin.precision = cin_impl
+    if hasattr(model, "dnn"):
+        model.dnn.precision = "bf16" if cin_impl == "bf16" else "fp32"      # tcgen05 dense layers in the bf16 configuration
+    if getattr(model, "sfg_decoder", None) is not None:
+        model.sfg_decoder.precision = "bf16" if cin_impl == "bf16" else "fp32"
+
+
+def build_workload_model(env, args, w, spec):
+    B = w["batch"]
+    if w.get("deferred"):
+        if env.world < 2:
+            raise SystemExit("workload keeps its tables row-sharded over the GPUs of the run: launch with --gpus >= 2 (torchrun)")
+        from deepctr.inputs import deferred_tables
+        with deferred_tables():
+            model = build_product_model(spec, env.dev)
+    else:
+        model = build_product_model(spec, env.dev)
+    # reference initialisation (init_std=1e-4 embeddings, default-init CIN) is what a user trains from
+    if env.world > 1:
+        # hybrid parallel: tables row-sharded over NVLink peer memory, dense part data-parallel (deepctr/distributed.py)
+        model.distribute(max_batch=B)
+    model.compile("adam", "binary_crossentropy")
+    set_precision(model, args.cin_impl)
+    model.optim.lazy_tables = not args.dense_table_pass
+    if w.get("sparse_update"):
+        model.optim.sparse_embedding_update = True
+    return model
+
+
+def release_model(model):
+    """Free a workload's device memory before the next one (row-sharded tables are cudaMalloc'ed peer buffers)."""
+    ctx = getattr(model, "_dist", None)
+    if ctx is not None:
+        # every rank unmaps its peers' buffers BEFORE any owner frees one (cudaFree of a region another process still has open is
+        # undefined behaviour): barrier, close the mappings, barrier, then drop the owners
+        torch.cuda.synchronize()
+        ctx.barrier(ctx.sharded.device)
+        torch.cuda.synchronize()
+        for buf in (ctx.sharded.tables, ctx.sharded.exchange):
+            if buf is not None:
+                buf.close()
+        torch.cuda.synchronize()
+        ctx.barrier(ctx.sharded.device)
+        torch.cuda.synchronize()
+    model._graphs.clear()
+    del model
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
+def run_workload(env, args, name, steps, want_profile, want_e2e=True):
+    """Warm up, (optionally) time every operator on eager launches, then time `steps` graph-replayed steps device-resident and
+    end to end.  Returns a dict of raw measurements (rank-local except the max-over-ranks times)."""
+    from deepctr import _native, ops
+    w = WORKLOADS[name]
+    spec = WorkloadSpec(w)
+    B = w["batch"]
+    model = build_workload_model(env, args, w, spec)
+    n_pool = 4
+    host = [(i.pin_memory(), d.pin_memory(), y.pin_memory()) for i, d, y in synth_batches(spec, B, n_pool, seed=2025 + env.rank)]
+    devb = [(i.to(env.dev), d.to(env.dev), y.to(env.dev)) for i, d, y in host]
+    # xDeepFM Pro sizes its positive-rows-only SFG pass from the labels' host copy (a count, no device sync); other models ignore it
+    hostl = [y for _, _, y in host] if w.get("variant") == "pro" else [None] * n_pool
+    accum = torch.zeros(1, dtype=torch.float64, device=env.dev)
+    model.train()
+    out = {"workload": name, "B": B, "spec": spec, "w": w}
+    # ---- warm-up, eager launches
+    graph_wanted = model.use_cuda_graph
+    model.use_cuda_graph = False
+    for i in range(max(args.warmup, 3)):
+        model.train_step(*devb[i % n_pool], accum, host_labels=hostl[i % n_pool])
+    env.sync_all()
+    if want_profile:
+        # ---- per-kernel-group device times (CUDA events around every operator; eager launches, same step, same data).  The pass
+        # runs for >= 2 s so that the clocks it sees are those of a long run; they are sampled and decide the roofline denominator
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(3):
+            model.train_step(*devb[i % n_pool], accum, host_labels=hostl[i % n_pool])
+        e1.record()
+        env.sync_all()
+        est = max(e0.elapsed_time(e1) / 3, 0.05)
+        prof_steps = int(min(2000, max(20, min(steps, 20), args.profile_seconds * 1e3 / est)))
+        sampler = ClockSampler(env.local_rank)
+        if env.rank == 0:
+            sampler.start()
+        ops.TIMERS = {}
+        l0 = _native.lib().xdfm_launch_count()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for i in range(prof_steps):
+            model.train_step(*devb[i % n_pool], accum, host_labels=hostl[i % n_pool])
+        p1.record()
+        env.sync_all()
+        sampler.stop_flag = True
+        out["prof_ms"], out["prof_steps"] = p0.elapsed_time(p1), prof_steps
+        out["launches_per_step"] = (_native.lib().xdfm_launch_count() - l0) // prof_steps
+        out["timers"] = ops.timer_totals()
+        out["prof_clocks"] = sampler.summary()
+        ops.TIMERS = None
+    # ---- the step captures itself into a CUDA graph on the third call with the same shapes
+    model.use_cuda_graph = graph_wanted
+    for i in range(3 * n_pool):          # every distinct step shape (Pro: positive-row bucket) is seen three times -> captured
+        model.train_step(*devb[i % n_pool], accum, host_labels=hostl[i % n_pool])
+    model.optim.flush()
+    env.sync_all()
+    out["graphed"] = bool(model._graphs)
+    # ---- timed: device-resident inputs
+    sampler = ClockSampler(env.local_rank)
+    if env.rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    env.sync_all()
+    e0.record()
+    t_host0 = time.perf_counter()
+    for i in range(steps):
+        model.train_step(*devb[i % n_pool], accum, host_labels=hostl[i % n_pool])
+    model.optim.flush()      # lazy dense-table semantics: every postponed row update is replayed INSIDE the timed region
+    out["host_enqueue_ms"] = 1e3 * (time.perf_counter() - t_host0) / steps      # Python + launch time per step (no sync inside)
+    e1.record()
+    env.sync_all()
+    ms = e0.elapsed_time(e1)
+    ms_e2e = float("nan")
+    if want_e2e:
+        # ---- timed: end-to-end through the public API with pinned host inputs
+        for i in range(n_pool):
+            model.train_on_batch(*host[i % n_pool])
+        env.sync_all()
+        t0 = time.perf_counter()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        for i in range(steps):
+            model.train_on_batch(*host[i % n_pool])
+        model.optim.flush()
+        e3.record()
+        env.sync_all()
+        ms_e2e = max(e2.elapsed_time(e3), 1e3 * (time.perf_counter() - t0))
+    sampler.stop_flag = True
+    out["clocks"] = sampler.summary()
+    out["ms"], out["ms_e2e"] = env.max_over_ranks([ms, ms_e2e])
+    out["steps"] = steps
+    out["h2d"] = sum(t.numel() * t.element_size() for t in host[0])
+    out["model"] = model
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# N GPUs == 1 GPU, checked on the hardware of the run before anything is timed
+# ------------------------------------------------------------------------------------------------
+def seeded_parameters(model, seed):
+    """O(0.1..1) parameters (embeddings std 0.5, matrices 1/sqrt(fan_in)) so that every branch of the model matters for the check
+    (the reference's init_std = 1e-4 makes the CIN / DNN contributions ~1e-8).  Identical on every rank."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, v in model.state_dict().items():
+        shp = tuple(v.shape)
+        fan_in = shp[1] if len(shp) > 1 else max(shp[0], 1)
+        if "embedding_dict" in k and not k.startswith("linear_model."):
+            std = 0.5
+        elif k.startswith("linear_model.") or k.endswith(".bias"):
+            std = 0.1
+        else:
+            std = 1.0 / max(fan_in, 1) ** 0.5
+        t = torch.randn(shp, generator=g) * std
+        if "layer_norm" in k and k.endswith("weight"):
+            t = 1.0 + 0.1 * t
+        sd[k] = t.to(v.dtype)
+    return sd
+
+
+PARITY_WORKLOADS = {
+    "xdeepfm": dict(m=8, nd=3, D=16, cin=(48, 32), dnn=(64, 48), vocab=[50, 7, 3000, 3, 29, 400, 1000, 12]),
+    "pro": dict(m=6, nd=2, D=16, cin=(32, 32), dnn=(48, 32), vocab=[40, 9, 500, 3, 31, 200], variant="pro"),
+}
+
+
+def run_dp_parity(env, args, variant, steps=4, per_rank=256):
+    """K steps of the hybrid-parallel model on N GPUs (each rank its slice of every global batch) and the same global batches on
+    rank 0 alone; both in the benchmarked precision.  Semantics that must hold (reference: basemodel.py:206-209, 254: per-GPU batch,
+    SUM not mean; basemodel_sfg.py:316-349 for xDeepFM Pro): per-step losses, every dense parameter, every table row.
+    Dense weight gradients are sums over rows whose fp32 association differs between the splits, and Adam normalises: tolerance
+    1e-2 of each tensor's movement (tables: same), losses 1e-5 relative."""
+    from deepctr.distributed import rank_slice
+    w = dict(PARITY_WORKLOADS[variant], batch=per_rank)
+    spec = WorkloadSpec(w)
+    gb = per_rank * env.world
+    batches = synth_batches(spec, gb, steps, seed=4242)         # same on every rank
+    model = build_product_model(spec, env.dev)
+    params = seeded_parameters(model, 31)
+    model.load_state_dict(params, strict=True)
+    model.distribute(max_batch=per_rank)
+    model.compile("adam", "binary_crossentropy")
+    set_precision(model, args.cin_impl)
+    model.train()
+    accum = torch.zeros(1, dtype=torch.float64, device=env.dev)
+    losses = []
+    for ids, dense, y in batches:
+        a, b = rank_slice(0, gb, env.rank, env.world)
+        accum.zero_()
+        model.train_step(ids[a:b].to(env.dev), dense[a:b].to(env.dev), y[a:b].to(env.dev), accum, host_labels=y[a:b])
+        t = accum.clone()
+        env.dist.all_reduce(t)
+        losses.append(t.item())
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}          # collective: tables re-assembled from the shards
+    release_model(model)
+    res = None
+    if env.rank == 0:
+        ref = build_product_model(spec, env.dev)
+        ref.load_state_dict(params, strict=True)
+        ref.compile("adam", "binary_crossentropy")
+        set_precision(ref, args.cin_impl)
+        ref.train()
+        ref_losses = []
+        for ids, dense, y in batches:
+            accum.zero_()
+            ref.train_step(ids.to(env.dev), dense.to(env.dev), y.to(env.dev), accum, host_labels=y)
+            ref_losses.append(accum.item())
+        rsd = {k: v.detach().cpu() for k, v in ref.state_dict().items()}
+        rel_loss = max(abs(a - b) / abs(b) for a, b in zip(losses, ref_losses))
+        dense_rel, table_rel = 0.0, 0.0
+        for k in rsd:
+            moved = (rsd[k].double() - params[k].double()).norm().item()
+            err = (sd[k].double() - rsd[k].double()).norm().item()
+            rel = err / max(moved, 1e-12) if moved > 0 else (0.0 if err == 0 else float("inf"))
+            if "embedding_dict" in k:
+                table_rel = max(table_rel, rel)
+            else:
+                dense_rel = max(dense_rel, rel)
+        res = {"model": variant, "world": env.world, "steps": steps, "global_batch": gb, "precision": args.cin_impl,
+               "max_rel_loss": rel_loss, "max_rel_dense_param": dense_rel, "max_rel_table": table_rel,
+               "tables_equal": bool(table_rel <= 1e-2), "losses": losses, "losses_1gpu": ref_losses,
+               "tolerance": "losses 1e-5 relative; parameters / table rows 1e-2 of the tensor's movement over the steps (norm)",
+               "ok": bool(rel_loss <= 1e-5 and dense_rel <= 1e-2 and table_rel <= 1e-2)}
+        del ref
+        torch.cuda.empty_cache()
+    flag = torch.tensor([1.0 if (res is None or res["ok"]) else 0.0], device=env.dev)
+    env.dist.all_reduce(flag, op=env.dist.ReduceOp.MIN)
+    return res, bool(flag.item() > 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# HBM-bound kernels at the cfg5 shape (north_star: achieved GB/s of gather / scatter against the measured HBM peak)
+# ------------------------------------------------------------------------------------------------
+def measure_hbm_kernels(env, peaks, B=65536, D=64):
+    """Fused multi-table gather and the sorted segmented scatter-add at BASELINE configs[4]'s per-step shape (65 536 samples x 26
+    fields x 64 dims; tables capped at 2 M rows so that they fit one GPU -- 26 tables, 3.0 GB, far beyond L2), through the C ABI,
+    CUDA events, L2 flushed between launches (a 256 MB write)."""
+    from deepctr import _native as Nv
+    from deepctr import ops
+    L = Nv.lib()
+    dev = env.dev
+    rows = [min(v, 2000000) for v in CRITEO_VOCAB]
+    m = len(rows)
+    tables = [torch.randn(v, D, device=dev) for v in rows]
+    g = torch.Generator().manual_seed(0)
+    ids = torch.stack([torch.clamp((float(v) ** torch.rand(B, generator=g)).long() - 1, 0, v - 1) for v in rows], 1).to(torch.int32).to(dev)
+    plan = ops.SparsePlan(list(range(m)), rows, D)
+    out = torch.empty(B, m, D, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timeit(fn, reps=7):
+        ts = []
+        for r in range(reps + 2):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            if r >= 2:
+                ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[len(ts) // 2]
+
+    def gather():
+        Nv.check(L.xdfm_embed_gather(Nv.ptr_array(tables), None, plan._c_vocab, Nv.ptr(ids), B, m, D, Nv.ptr(out), None, 0, None, None,
+                                     Nv.stream_ptr()))
+    res = {}
+    ms = timeit(gather)
+    nbytes = B * m * (4 + 2 * D * 4)
+    res["embed_gather"] = {"achieved": nbytes / ms / 1e6, "peak": peaks["hbm"], "unit": "GB/s", "frac": nbytes / ms / 1e6 / peaks["hbm"],
+                           "ms": ms, "bytes": nbytes, "shape": "B=%d m=%d D=%d fp32, 26 tables <= 2M rows, log-uniform ids" % (B, m, D),
+                           "bytes_are": "id (4 B) + table row read + output row write per looked-up row"}
+    # backward: (a) keys -> radix sort -> run-length segments, (b) deterministic segmented reduce of the [B*m, D] gradient rows
+    n = B * m
+    demb = torch.randn(B, m, D, device=dev)
+    uniq = torch.empty(n, dtype=torch.int32, device=dev)
+    seg_off = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    pos = torch.empty(n, dtype=torch.int32, device=dev)
+    nseg = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = torch.empty(int(L.xdfm_embed_bwd_workspace_bytes(n)), dtype=torch.uint8, device=dev)
+    gsum = torch.empty(n, D, device=dev)
+
+    def segments():
+        Nv.check(L.xdfm_embed_bwd_segments(Nv.ptr(ids), B, m, plan._c_feat_off, plan._c_vocab, plan.row_off[-1], Nv.ptr(ws), ws.numel(),
+                                           Nv.ptr(uniq), Nv.ptr(seg_off), Nv.ptr(pos), Nv.ptr(nseg), Nv.stream_ptr()))
+
+    def reduce_():
+        Nv.check(L.xdfm_embed_bwd_reduce(Nv.ptr(demb), None, Nv.ptr(pos), Nv.ptr(seg_off), Nv.ptr(nseg), n, m, D, Nv.ptr(gsum), None,
+                                         Nv.stream_ptr()))
+    ms_seg = timeit(segments)
+    ms_red = timeit(reduce_)
+    u = int(nseg.item())
+    red_bytes = n * D * 4 + u * D * 4 + n * 4 + (u + 1) * 4
+    res["embed_scatter_reduce"] = {"achieved": red_bytes / ms_red / 1e6, "peak": peaks["hbm"], "unit": "GB/s",
+                                   "frac": red_bytes / ms_red / 1e6 / peaks["hbm"], "ms": ms_red, "bytes": red_bytes,
+                                   "unique_rows": u, "bytes_are": "gradient rows read (n*D*4) + unique-row sums written (u*D*4) + "
+                                   "sorted positions and segment offsets read"}
+    tot_bytes = red_bytes + n * 4
+    res["embed_scatter"] = {"achieved": tot_bytes / (ms_seg + ms_red) / 1e6, "peak": peaks["hbm"], "unit": "GB/s",
+                            "frac": tot_bytes / (ms_seg + ms_red) / 1e6 / peaks["hbm"], "ms": ms_seg + ms_red, "ms_sort_segments": ms_seg,
+                            "bytes": tot_bytes, "note": "whole backward of the lookup: make keys + cub radix sort (only the key bits in "
+                            "use) + run-length encode + scan, then the segmented reduce; the sort moves keys and positions several "
+                            "times, bytes counted are the algorithmic ones only"}
+    del tables, out, demb, gsum, flush
+    torch.cuda.empty_cache()
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's own entry points: model.fit / model.predict on host arrays
+# ------------------------------------------------------------------------------------------------
+def measure_fit_predict(env, args, w, n_rows=2 ** 21):
+    """samples/s through `model.fit(x, y, batch_size, epochs=1, shuffle=True, verbose=0)` and `model.predict(x, batch_size)` on
+    `n_rows` synthetic rows given as a dict of numpy arrays (xdftrain.py:444-458); the first epoch / call warms up (graph capture,
+    pinned staging), the second is timed by wall clock around the call (everything inside: host batching, H2D, D2H)."""
+    spec = WorkloadSpec(w)
+    model = build_product_model(spec, env.dev)
+    model.compile("adam", "binary_crossentropy")
+    set_precision(model, args.cin_impl)
+    model.optim.lazy_tables = not args.dense_table_pass
+    B = w["batch"]
+    g = np.random.default_rng(7)
+    x = {}
+    for name, V in zip(spec.sparse_names, spec.vocab_sizes):
+        x[name] = np.minimum((float(V) ** g.random(n_rows)).astype(np.int64) - 1, V - 1).clip(0).astype(np.int32)
+    for name in spec.dense_names:
+        x[name] = g.random(n_rows, dtype=np.float32)
+    y = (g.random(n_rows) < 0.25).astype(np.float32).reshape(-1, 1)
+    import contextlib
+    import io
+    res = {}
+    with contextlib.redirect_stdout(io.StringIO()):
+        model.fit(x, y, batch_size=B, epochs=1, verbose=0, shuffle=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        hist = model.fit(x, y, batch_size=B, epochs=1, verbose=0, shuffle=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    res["fit_e2e"] = {"value": n_rows / dt, "unit": "samples/s", "rows": n_rows, "batch_size": B, "seconds": dt, "epoch_loss": hist.history["loss"][0],
+                      "how": "wall clock around model.fit(dict of numpy arrays, y, batch_size, epochs=1, shuffle=True, verbose=0), second epoch"}
+    n_pred = n_rows // 2
+    xp = {k: v[:n_pred] for k, v in x.items()}
+    with contextlib.redirect_stdout(io.StringIO()):
+        model.predict(xp, batch_size=B)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pred = model.predict(xp, batch_size=B)
+        dt = time.perf_counter() - t0
+    res["predict_e2e"] = {"value": n_pred / dt, "unit": "samples/s", "rows": n_pred, "batch_size": B, "seconds": dt,
+                          "returns": "float64 [N, 1] numpy (as the reference)", "finite": bool(np.isfinite(pred).all()),
+                          "how": "wall clock around model.predict(dict of numpy arrays, batch_size), second call"}
+    release_model(model)
+    return res
+
+
+def load_cin_traffic():
+    """DRAM bytes of the CIN contraction launches of one step, from the committed ncu --set full summary (written by
+    tools/ncu_cin_traffic.py from an .ncu-rep of this repo's bench.py): (bytes, provenance) or (None, reason)."""
+    p = os.path.join(ROOT, "profiles", "r02_ncu_cin_traffic.json")
+    if not os.path.exists(p):
+        return None, "profiles/r02_ncu_cin_traffic.json not committed"
+    try:
+        d = json.load(open(p))
+        return float(d["dram_bytes_per_step"]), "dram__bytes_read.sum + dram__bytes_write.sum over the %d CIN contraction launches of one " \
+            "cfg2 step, ncu --set full, %s (csrc hash %s, captured %s)" % (d["launches_per_step"], os.path.relpath(p, ROOT), d.get("csrc_hash"), d.get("when"))
+    except Exception as e:      # pragma: no cover
+        return None, "unreadable %s: %s" % (p, e)
+
+
+def roofline_block(args, peaks, r):
+    """CIN contraction roofline from the operator timers of the profiling pass."""
+    spec, B = r["spec"], r["B"]
+    timers, prof_steps = r["timers"], r["prof_steps"]
+    cin_ms = sum(timers.get(k, (0.0, 0))[0] for k in ("cin_fwd", "cin_bwd"))
+    cin_calls = sum(timers.get(k, (0.0, 0))[1] for k in ("cin_fwd", "cin_bwd"))
+    layout_ms = timers.get("cin_layout", (0.0, 0))[0]
+    flops_step = 3.0 * cin_flops_per_sample(spec) * B
+    achieved = flops_step * prof_steps / (cin_ms / 1e3) / 1e12 if cin_ms > 0 else None
+    achieved_l = flops_step * prof_steps / ((cin_ms + layout_ms) / 1e3) / 1e12 if cin_ms > 0 else None
+    # denominator: the burst figure when the SM clock during the profiled pass sat at its maximum (the step does not draw the power
+    # of a pure GEMM loop, so it is NOT clock-limited the way the sustained measurement is); the sustained figure otherwise
+    clk = r.get("prof_clocks") or {}
+    at_max = bool(clk.get("sm_mhz") and clk.get("sm_max_mhz") and clk["sm_mhz"] >= 0.97 * clk["sm_max_mhz"])
+    peak = peaks["tf_burst"] if at_max else peaks["tf_sust"]
+    traffic, traffic_note = (load_cin_traffic() if (r["workload"] == "cfg2" and args.cin_impl == "bf16") else (None, "no capture for this workload"))
+    return {"bound": "tensor", "kernel": "CIN contraction (cin_fwd + cin_bwd launches, %d per step)" % (cin_calls // max(prof_steps, 1)),
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
+            "frac_incl_layout": (achieved_l / peak) if achieved_l else None,
+            "frac_vs_burst": (achieved / peaks["tf_burst"]) if achieved else None,
+            "frac_vs_sustained": (achieved / peaks["tf_sust"]) if achieved else None,
+            "frac_incl_layout_vs_burst": (achieved_l / peaks["tf_burst"]) if achieved_l else None,
+            "layout_note": "frac_incl_layout adds the cin_layout group (row / channel-major copies, dY, dX0 re-layout: kernels that exist "
+                           "only to feed the contraction) to the kernel time",
+            "traffic": traffic, "traffic_note": traffic_note,
+            "algorithmic_hbm_bytes": 0.62e9 if r["workload"] == "cfg2" else None,
+            "peak_source": "%s MEASURED_PEAKS.json bf16 %s: median SM clock of the %.1f s profiled pass %s MHz of %s max" % (
+                peaks["src"], "burst (clock at max)" if at_max else "sustained (clock below max)", r["prof_ms"] / 1e3,
+                clk.get("sm_mhz"), clk.get("sm_max_mhz")),
+            "profile_clocks": clk,
+            "share_of_step": (cin_ms / prof_steps) / (r["ms"] / r["steps"]) if r["ms"] > 0 else None,
+            "timed_how": "CUDA events around every operator over %d eager steps (%.2f s) before the timed region (%.3f ms/step incl. event "
+                         "overhead); share_of_step = that per-step kernel time / the timed region's ms_per_step (CUDA graph replay: %s)" % (
+                             prof_steps, r["prof_ms"] / 1e3, r["prof_ms"] / prof_steps, r["graphed"]),
+            "other_ms_per_step": {k: v[0] / prof_steps for k, v in timers.items()}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -290,6 +752,8 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=1024)
     ap.add_argument("--ref-vocab-cap", type=int, default=100000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip hbm_kernels / fit_e2e / predict_e2e / dp_parity / extra_workloads")
+    ap.add_argument("--profile-seconds", type=float, default=2.0, help="length of the eager operator-timing pass")
     ap.add_argument("--dense-table-pass", action="store_true",
                     help="stream every table row every step instead of the (bit-identical) lazy replay of untouched rows")
     args = ap.parse_args()
@@ -297,173 +761,108 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args, w)
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     # rank 0's stdout carries exactly ONE JSON line: everything else written to file descriptor 1 during the run (NCCL prints its
     # version banner there when the first communicator is created) is sent to stderr
     sys.stdout.flush()
     json_out = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
-    torch.cuda.set_device(local_rank)
-    dev = "cuda:%d" % local_rank
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device(dev))
-    from deepctr import _native, ops
+    env = Env()
+    rank, world = env.rank, env.world
     peaks = load_peaks()
-    spec = WorkloadSpec(w)
-    B = w["batch"]
-    if w.get("deferred"):
-        if world < 2:
-            raise SystemExit("workload %s keeps its tables row-sharded over the GPUs of the run: launch with --gpus >= 2 (torchrun)" % args.workload)
-        from deepctr.inputs import deferred_tables
-        with deferred_tables():
-            model = build_product_model(spec, dev)
-    else:
-        model = build_product_model(spec, dev)
-    # reference initialisation (init_std=1e-4 embeddings, default-init CIN) is what a user trains from
-    if world > 1:
-        # hybrid parallel: tables row-sharded over NVLink peer memory, dense part data-parallel (deepctr/distributed.py)
-        model.distribute(max_batch=B)
-    model.compile("adam", "binary_crossentropy")
-    model.cin.precision = args.cin_impl
-    if hasattr(model, "dnn"):
-        model.dnn.precision = "bf16" if args.cin_impl == "bf16" else "fp32"      # tcgen05 dense layers in the bf16 configuration
-    if getattr(model, "sfg_decoder", None) is not None:
-        model.sfg_decoder.precision = "bf16" if args.cin_impl == "bf16" else "fp32"
-    model.optim.lazy_tables = not args.dense_table_pass
-    if w.get("sparse_update"):
-        model.optim.sparse_embedding_update = True
-    n_pool = 4
-    host = [(i.pin_memory(), d.pin_memory(), y.pin_memory()) for i, d, y in synth_batches(spec, B, n_pool, seed=2025 + rank)]
-    devb = [(i.to(dev), d.to(dev), y.to(dev)) for i, d, y in host]
-    # xDeepFM Pro sizes its positive-rows-only SFG pass from the labels' host copy (a count, no device sync); other models ignore it
-    hostl = [y for _, _, y in host] if w.get("variant") == "pro" else [None] * n_pool
-    accum = torch.zeros(1, dtype=torch.float64, device=dev)
-    model.train()
+    extras = not args.no_extras
 
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
+    # ---- N GPUs == 1 GPU on the same global batches, before anything is timed
+    dp_parity = None
+    if world > 1 and extras:
+        dp_parity = []
+        for variant in ("xdeepfm", "pro"):
+            res, ok = run_dp_parity(env, args, variant)
+            if rank == 0:
+                dp_parity.append(res)
+                print("dp_parity %s: %s" % (variant, json.dumps(res)), file=sys.stderr)
+            if not ok:
+                if rank == 0:
+                    json_out.write(json.dumps({"error": "dp_parity failed", "dp_parity": dp_parity}) + "\n")
+                    json_out.flush()
+                env.dist.destroy_process_group()
+                sys.exit(3)
 
-    # ---- warm-up, eager launches
-    graph_wanted = model.use_cuda_graph
-    model.use_cuda_graph = False
-    for i in range(max(args.warmup, 3)):
-        model.train_step(*devb[i % n_pool], accum, host_labels=hostl[i % n_pool])
-    sync_all()
-    # ---- per-kernel-group device times (CUDA events around every operator; eager launches, same step, same data)
-    prof_steps = min(args.steps, 20)
-    ops.TIMERS = {}
-    l0 = _native.lib().xdfm_launch_count()
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record()
-    for i in range(prof_steps):
-        model.train_step(*devb[i % n_pool], accum, host_labels=hostl[i % n_pool])
-    p1.record()
-    sync_all()
-    prof_ms = p0.elapsed_time(p1)
-    launches_per_step = (_native.lib().xdfm_launch_count() - l0) // prof_steps
-    launches = launches_per_step * args.steps
-    timers = ops.timer_totals()
-    ops.TIMERS = None
-    # ---- the step captures itself into a CUDA graph on the third call with the same shapes
-    model.use_cuda_graph = graph_wanted
-    for i in range(3 * n_pool):          # every distinct step shape (Pro: positive-row bucket) is seen three times -> captured
-        model.train_step(*devb[i % n_pool], accum, host_labels=hostl[i % n_pool])
-    model.optim.flush()
-    sync_all()
-    graphed = bool(model._graphs)
-    # ---- timed: device-resident inputs
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    e0.record()
-    t_host0 = time.perf_counter()
-    for i in range(args.steps):
-        model.train_step(*devb[i % n_pool], accum, host_labels=hostl[i % n_pool])
-    model.optim.flush()      # lazy dense-table semantics: every postponed row update is replayed INSIDE the timed region
-    host_enqueue_ms = 1e3 * (time.perf_counter() - t_host0) / args.steps      # Python + launch time per step (no sync inside)
-    e1.record()
-    sync_all()
-    ms = e0.elapsed_time(e1)
-    # ---- timed: end-to-end through the public API with pinned host inputs
-    for i in range(n_pool):
-        model.train_on_batch(*host[i % n_pool])
-    sync_all()
-    t0 = time.perf_counter()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    for i in range(args.steps):
-        model.train_on_batch(*host[i % n_pool])
-    model.optim.flush()
-    e3.record()
-    sync_all()
-    ms_e2e = max(e2.elapsed_time(e3), 1e3 * (time.perf_counter() - t0))
-    sampler.stop_flag = True
-    if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = t.tolist()
+    r = run_workload(env, args, args.workload, args.steps, want_profile=True)
+    spec, B = r["spec"], r["B"]
+    release_model(r.pop("model"))
+
+    extra_workloads = None
+    if world > 1 and extras and args.workload == "cfg2":
+        extra_workloads = {}
+        names = ["cfg4"] + (["cfg5"] if world >= 8 else [])
+        for name in names:
+            x = run_workload(env, args, name, min(args.steps, 30), want_profile=False)
+            release_model(x.pop("model"))
+            if rank == 0:
+                extra_workloads[name] = {
+                    "metric": "train samples/sec", "value": x["B"] * world * x["steps"] / (x["ms"] / 1e3), "unit": "samples/s",
+                    "ms_per_step": x["ms"] / x["steps"], "e2e_value": x["B"] * world * x["steps"] / (x["ms_e2e"] / 1e3),
+                    "e2e_ms_per_step": x["ms_e2e"] / x["steps"], "steps": x["steps"], "graph_replay": x["graphed"],
+                    "config": workload_config(argparse.Namespace(**dict(vars(args), workload=name)), WORKLOADS[name]), "clocks": x["clocks"]}
     if rank != 0:
+        if env.dist is not None:
+            env.dist.barrier()
         return
+    ms, ms_e2e = r["ms"], r["ms_e2e"]
     value = B * world * args.steps / (ms / 1e3)
     e2e = B * world * args.steps / (ms_e2e / 1e3)
-    # ---- roofline of the dominant kernel group: the CIN contraction (fwd + bwd)
-    cin_ms = sum(timers.get(k, (0.0, 0))[0] for k in ("cin_fwd", "cin_bwd"))
-    cin_calls = sum(timers.get(k, (0.0, 0))[1] for k in ("cin_fwd", "cin_bwd"))
-    flops_step = 3.0 * cin_flops_per_sample(spec) * B
-    achieved = flops_step * prof_steps / (cin_ms / 1e3) / 1e12 if cin_ms > 0 else None
-    peak = peaks["tf_sust"]
-    roofline = {"bound": "tensor", "kernel": "CIN contraction (cin_fwd + cin_bwd launches, %d per step)" % (cin_calls // max(prof_steps, 1)),
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": 0.80e9 if args.workload == "cfg2" and args.cin_impl == "bf16" else None,
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the 9 CIN contraction launches of one step, bytes, from "
-                                "profiles/r01c_ncu_full_cfg2.md (ncu --set full); algorithmic HBM bytes of the group ~0.62e9",
-                "peak_source": "%s MEASURED_PEAKS.json bf16 sustained (kernel timed inside a long step)" % peaks["src"],
-                "share_of_step": (cin_ms / prof_steps) / (ms / args.steps) if ms > 0 else None,
-                "timed_how": "CUDA events around every operator over %d eager steps before the timed region (%.3f ms/step incl. event "
-                             "overhead); share_of_step = that per-step kernel time / the timed region's ms_per_step (CUDA graph "
-                             "replay: %s)" % (prof_steps, prof_ms / prof_steps, graphed),
-                "other_ms_per_step": {k: v[0] / prof_steps for k, v in timers.items()}}
-    # secondary (HBM-bound) kernels, timed live in the same run: algorithmic bytes / CUDA-event time
+    roofline = roofline_block(args, peaks, r)
+    timers = r["timers"]
+    # secondary (HBM-bound) kernels: inside the step (tiny launches at this batch) and at the cfg5 shape (what the roofline is for)
     hbm = {}
     if "embed_gather" in timers and timers["embed_gather"][0] > 0:
         gb = B * spec.m * (4 + 2 * spec.embedding_dim * 4) * timers["embed_gather"][1]
         a = gb / (timers["embed_gather"][0] / 1e3) / 1e9
-        hbm["embed_gather"] = {"achieved": a, "peak": peaks["hbm"], "unit": "GB/s", "frac": a / peaks["hbm"],
-                               "note": "id + row read + row write per looked-up row; 15 MB per launch at this batch (latency-bound: see "
-                                       "profiles/ for the 450 MB/launch cfg5-shape measurement)"}
+        hbm["embed_gather_in_step"] = {"achieved": a, "peak": peaks["hbm"], "unit": "GB/s", "frac": a / peaks["hbm"],
+                                       "note": "id + row read + row write per looked-up row; %.0f MB per launch at this batch: latency-"
+                                               "bound, see the cfg5-shape entries" % (gb / timers["embed_gather"][1] / 1e6)}
+    if world == 1 and extras:
+        try:
+            hbm.update(measure_hbm_kernels(env, peaks))
+        except Exception as e:      # pragma: no cover
+            hbm["error"] = "cfg5-shape kernel measurement failed: %s" % e
     roofline["hbm_kernels"] = hbm
-    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    launches_per_step = r["launches_per_step"]
     line = {"metric": "train samples/sec (Criteo-shape xDeepFM)", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.cin_impl == "fp32" else "bf16", "data": "synthetic",
-            "config": workload_config(args, w), "clocks": sampler.summary(),
-            "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+            "config": workload_config(args, w), "clocks": r["clocks"],
+            "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": 8,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "gpu_launches_note": "%d kernels of libxdfm_sm100a.so per step (counted on eager steps) x %d "
-            "steps; in the timed region they run as nodes of a replayed CUDA graph: %s" % (launches_per_step, args.steps, graphed),
-            "host_enqueue_ms_per_step": host_enqueue_ms, "roofline": roofline}
+            "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_note": "%d kernels of libxdfm_sm100a.so per step (counted on "
+            "eager steps) x %d steps; in the timed region they run as nodes of a replayed CUDA graph: %s" % (
+                launches_per_step, args.steps, r["graphed"]),
+            "host_enqueue_ms_per_step": r["host_enqueue_ms"], "roofline": roofline}
+    if dp_parity is not None:
+        line["dp_parity"] = dp_parity
+    if extra_workloads is not None:
+        line["extra_workloads"] = extra_workloads
+    if world == 1 and extras and args.workload in ("cfg2", "cfg1"):
+        try:
+            line.update(measure_fit_predict(env, args, w))
+        except Exception as e:      # pragma: no cover
+            line["fit_e2e"] = {"value": None, "error": str(e)}
     if not args.no_cpu_baseline and world == 1:
         # bounded CPU sample (~10 s of host work on the box's cores) in a separate process (the reference package shares the name
         # `deepctr` with the product)
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "40" if args.workload in ("cfg1", "cfg2") else "10", "--warmup", "1",
-                                "--workload", args.workload, "--ref-batch", str(args.ref_batch),
-                                "--ref-vocab-cap", str(args.ref_vocab_cap)], capture_output=True, text=True, timeout=600)
-            ref = json.loads(r.stdout.strip().splitlines()[-1])
+            rr = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "40" if args.workload in ("cfg1", "cfg2") else "10", "--warmup", "3",
+                                 "--workload", args.workload, "--ref-batch", str(args.ref_batch),
+                                 "--ref-vocab-cap", str(args.ref_vocab_cap)], capture_output=True, text=True, timeout=600)
+            ref = json.loads(rr.stdout.strip().splitlines()[-1])
             line["cpu_baseline"] = ref["cpu_baseline"]
         except Exception as e:  # pragma: no cover
             line["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": "failed: %s" % e}
     json_out.write(json.dumps(line) + "\n")
     json_out.flush()
+    if env.dist is not None:
+        env.dist.barrier()
 
 
 if __name__ == "__main__":

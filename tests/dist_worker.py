@@ -21,16 +21,21 @@ from oracle import xdeepfm_oracle as O  # noqa: E402
 from tests.helpers import assert_close, build_product_model  # noqa: E402
 
 
-def spec_for_test():
+def spec_for_test(variant="xdeepfm"):
+    if variant == "pro":
+        # xDeepFM Pro (SFG decoder, label-aware attention): BASELINE configs[3] is its data-parallel run
+        return O.ModelSpec(sparse_names=["C%d" % i for i in range(1, 7)], vocab_sizes=[50, 7, 1000, 3, 29, 400], embedding_dim=16,
+                           dense_names=["I1", "I2", "I3"], cin_layer_size=(32, 16), dnn_hidden_units=(64, 32), l2_reg_linear=1e-4,
+                           l2_reg_embedding=1e-4, l2_reg_dnn=1e-4, l2_reg_cin=1e-4, variant="pro", sfg_hidden_units=(32, 16))
     return O.ModelSpec(sparse_names=["C%d" % i for i in range(1, 7)], vocab_sizes=[50, 7, 1000, 3, 29, 400], embedding_dim=16,
                        dense_names=["I1", "I2", "I3"], cin_layer_size=(32, 16), dnn_hidden_units=(64, 32), l2_reg_linear=1e-4,
                        l2_reg_embedding=1e-4, l2_reg_dnn=1e-4, l2_reg_cin=1e-4)
 
 
-def run(rank, world, optimizer="adam", steps=6, per_rank=48, fit_check=True):
+def run(rank, world, optimizer="adam", steps=6, per_rank=48, fit_check=True, variant="xdeepfm"):
     from deepctr.distributed import rank_slice
     dev = "cuda:%d" % torch.cuda.current_device()
-    spec = spec_for_test()
+    spec = spec_for_test(variant)
     params = O.make_params(spec, seed=11)
     gb = per_rank * world
     batches = [O.make_inputs(spec, gb, seed=100 + s, zipf=(s % 2 == 0)) for s in range(steps)]
@@ -96,7 +101,7 @@ def run(rank, world, optimizer="adam", steps=6, per_rank=48, fit_check=True):
     if fit_check:
         hist = ref.fit(xd, yf.numpy().reshape(-1, 1), batch_size=per_rank * world, epochs=2, verbose=0, shuffle=False)
         assert np.allclose(fit_loss, hist.history["loss"], rtol=1e-4), (fit_loss, hist.history["loss"])
-    print("dist parity ok: world=%d optimizer=%s losses=%s" % (world, optimizer, ["%.4f" % l for l in losses]), flush=True)
+    print("dist parity ok: %s world=%d optimizer=%s losses=%s" % (variant, world, optimizer, ["%.4f" % l for l in losses]), flush=True)
 
 
 def run_deferred(rank, world):
@@ -136,6 +141,8 @@ def spawn_entry(rank, world, init_file, optimizer):
     try:
         if optimizer == "deferred":
             run_deferred(rank, world)
+        elif optimizer.startswith("pro:"):
+            run(rank, world, optimizer[4:], variant="pro")
         else:
             run(rank, world, optimizer)
     finally:
@@ -150,6 +157,8 @@ if __name__ == "__main__":
         for opt in (sys.argv[1:] or ["adam", "sgd"]):
             if opt == "deferred":
                 run_deferred(rank, world)
+            elif opt.startswith("pro:"):
+                run(rank, world, opt[4:], variant="pro")
             else:
                 run(rank, world, opt)
     finally:

@@ -117,7 +117,11 @@ def test_distribute_world_size_1_equals_plain_model(optimizer):
     _run_in_subprocess(1, optimizer)
 
 
+def test_pro_distribute_world_size_1_equals_plain_model():
+    _run_in_subprocess(1, "pro:adam")
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-@pytest.mark.parametrize("optimizer", ["adam", "adagrad"])
+@pytest.mark.parametrize("optimizer", ["adam", "adagrad", "pro:adam"])
 def test_two_gpus_equal_one_gpu(optimizer):
     _run_in_subprocess(2, optimizer)

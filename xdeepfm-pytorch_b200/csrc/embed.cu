@@ -318,14 +318,24 @@ __device__ __forceinline__ void seg_accumulate(const float* __restrict__ demb, c
   }
 }
 
-// Long segments (hot rows: a field with 3 distinct ids has ~B/3 entries per row) are found by the short pass and appended to a
-// per-device list; the long pass then walks that list (one block per long segment) instead of scanning all ~1e5 segment offsets
-// from every block -- the scan alone cost 130 us per table set at BASELINE config 2 (ncu, round 1).  The list order depends on
-// scheduling, the sums do not (every segment is reduced by exactly one block in a fixed order).
-#define SEG_LONG_LIST 8192
-__device__ int g_seg_long_count;
-__device__ int g_seg_long_list[SEG_LONG_LIST];
+// Long segments (hot rows: a field with 3 distinct ids has ~B/3 entries per row) are found by the short pass and cut into CHUNKS
+// of SEG_CHUNK entries that are appended to a per-device work list; the long pass reduces one chunk per block into a partial row,
+// and the block that finishes a segment's last outstanding chunk adds the partials in chunk order.  One block per WHOLE segment
+// (round 1) left the step waiting for the longest segment: at B = 65 536, D = 64 a 40 000-entry segment took 1.7 ms on one block
+// while the other 147 SMs idled (4 % of the HBM peak for the whole reduce).  The list order depends on scheduling, the sums do
+// not: every chunk is reduced in a fixed order, and the chunks of a segment are combined in increasing chunk index.
+#define SEG_CHUNK 512
+#define SEG_ITEMS_MAX 16384
+#define SEG_PART_FLOATS (1 << 20)
+__device__ int g_seg_item_count;
+__device__ int4 g_seg_items[SEG_ITEMS_MAX];          // (segment, chunk, chunks of the segment, first item of the segment)
+__device__ int g_seg_done[SEG_ITEMS_MAX];            // per segment (indexed by its first item): chunks finished
+__device__ float g_seg_part[SEG_PART_FLOATS];        // [item][D] partial rows
+__device__ float g_seg_part_lin[SEG_ITEMS_MAX];
+// launches whose chunk count could exceed the static work list fall back to one block per whole segment, found by scanning
 
+// long_pass: 0 short segments + chunk list of the long ones | 3 reduce the listed chunks | legacy: -1 short only (no list),
+// 2 one block per long segment found by scanning every segment
 template <int VEC>
 __global__ void __launch_bounds__(256) seg_reduce_kernel(const float* __restrict__ demb, const float* __restrict__ dlin,
                                                          const int32_t* __restrict__ sorted_pos,
@@ -340,13 +350,21 @@ __global__ void __launch_bounds__(256) seg_reduce_kernel(const float* __restrict
   const int sub = lane % lpr;           // which VEC piece of the row (valid if sub*VEC < D)
   const bool active = sub * VEC < D;
   __shared__ float sh[8][32 * 4 + 8];
-  if (long_pass <= 0) {                    // 0: short segments + list of the long ones; -1: short segments only (scanning fallback)
+  __shared__ int sh_last;
+  if (long_pass <= 0) {
     int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t s = warp; s < nseg; s += nwarps) {
       int beg = seg_offsets[s], end = seg_offsets[s + 1];
       if (end - beg > SEG_LONG) {          // handled by the long pass
-        if (long_pass == 0 && lane == 0) g_seg_long_list[atomicAdd(&g_seg_long_count, 1)] = (int)s;
+        if (long_pass == 0) {
+          const int nch = (end - beg + SEG_CHUNK - 1) / SEG_CHUNK;
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&g_seg_item_count, nch);
+          base = __shfl_sync(0xffffffffu, base, 0);
+          for (int c = lane; c < nch; c += 32) g_seg_items[base + c] = make_int4((int)s, c, nch, base);
+          if (lane == 0) g_seg_done[base] = 0;
+        }
         continue;
       }
       float acc[VEC];
@@ -368,14 +386,19 @@ __global__ void __launch_bounds__(256) seg_reduce_kernel(const float* __restrict
       }
     }
   } else {
-    // long segments: one block per segment (grid-stride), 8 warps x S slots
+    // long segments: one block per chunk (mode 3) or per whole segment (mode 2), grid-stride; 8 warps x S slots
     const int w = threadIdx.x >> 5;
-    const bool listed = long_pass == 1;    // 1: walk the list left by the short pass; 2: scan every segment (n_keys beyond the list)
-    const int64_t n_iter = listed ? g_seg_long_count : nseg;
+    const bool chunked = long_pass == 3;
+    const int64_t n_iter = chunked ? g_seg_item_count : nseg;
     for (int64_t it = blockIdx.x; it < n_iter; it += gridDim.x) {
-      const int64_t s = listed ? g_seg_long_list[it] : it;
+      int4 item = chunked ? g_seg_items[it] : make_int4((int)it, 0, 1, 0);
+      const int64_t s = item.x;
       int beg = seg_offsets[s], end = seg_offsets[s + 1];
       if (end - beg <= SEG_LONG) continue;
+      if (chunked) {
+        beg += item.y * SEG_CHUNK;
+        end = min(end, beg + SEG_CHUNK);
+      }
       float acc[VEC];
 #pragma unroll
       for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
@@ -393,19 +416,44 @@ __global__ void __launch_bounds__(256) seg_reduce_kernel(const float* __restrict
         if (sub == 0) sh[w][32 * 4] = accl;
       }
       __syncthreads();
+      // the chunk's (or the whole segment's) sum: warps combined in warp order
+      float* out_row = chunked ? g_seg_part + (int64_t)it * D : (gsum != nullptr ? gsum + s * (int64_t)D : nullptr);
+      float* out_lin = chunked ? g_seg_part_lin + it : (gsum_lin != nullptr ? gsum_lin + s : nullptr);
       if (w == 0 && slot == 0) {
-        if (active && gsum != nullptr) {
+        if (active && out_row != nullptr && (chunked ? demb != nullptr : true)) {
 #pragma unroll
           for (int i = 0; i < VEC; ++i) {
             float t = 0.f;
             for (int ww = 0; ww < 8; ++ww) t += sh[ww][sub * VEC + i];
-            gsum[s * (int64_t)D + sub * VEC + i] = t;
+            out_row[sub * VEC + i] = t;
           }
         }
-        if (sub == 0 && gsum_lin != nullptr) {
+        if (sub == 0 && out_lin != nullptr) {
           float t = 0.f;
           for (int ww = 0; ww < 8; ++ww) t += sh[ww][32 * 4];
-          gsum_lin[s] = t;
+          *out_lin = t;
+        }
+      }
+      if (chunked) {
+        // last chunk of the segment to finish adds the partial rows in chunk order (fixed order whoever is last)
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) sh_last = (atomicAdd(&g_seg_done[item.w], 1) == item.z - 1) ? 1 : 0;
+        __syncthreads();
+        if (sh_last) {
+          __threadfence();
+          if (gsum != nullptr && demb != nullptr) {
+            for (int c0 = threadIdx.x; c0 < D; c0 += blockDim.x) {
+              float t = 0.f;
+              for (int c = 0; c < item.z; ++c) t += __ldcg(g_seg_part + (int64_t)(item.w + c) * D + c0);
+              gsum[s * (int64_t)D + c0] = t;
+            }
+          }
+          if (gsum_lin != nullptr && threadIdx.x == 0) {
+            float t = 0.f;
+            for (int c = 0; c < item.z; ++c) t += __ldcg(g_seg_part_lin + item.w + c);
+            gsum_lin[s] = t;
+          }
         }
       }
     }
@@ -427,14 +475,16 @@ extern "C" int xdfm_embed_bwd_reduce(const float* demb, const float* dlin, const
     return XDFM_ERR_UNSUPPORTED;
   }
   int blocks_short = (int)min((int64_t)xdfm_num_sms() * 8, ceil_div64(n_keys, 8));
-  int blocks_long = xdfm_num_sms() * 2;
-  const bool listed = n_keys / SEG_LONG < SEG_LONG_LIST;      // at most n_keys / SEG_LONG long segments can exist
-  if (listed) {
+  // chunks of all long segments: at most n_keys / SEG_CHUNK full ones + one partial per long segment (<= n_keys / SEG_LONG of those)
+  const int64_t item_bound = n_keys / SEG_CHUNK + n_keys / SEG_LONG + 1;
+  const bool chunked = item_bound <= SEG_ITEMS_MAX && item_bound * D <= SEG_PART_FLOATS;
+  int blocks_long = chunked ? (int)min((int64_t)xdfm_num_sms() * 8, item_bound) : xdfm_num_sms() * 2;
+  if (chunked) {
     void* cnt = nullptr;
-    XDFM_CUDA(cudaGetSymbolAddress(&cnt, g_seg_long_count));
+    XDFM_CUDA(cudaGetSymbolAddress(&cnt, g_seg_item_count));
     XDFM_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int), st));
   }
-  const int mode_short = listed ? 0 : -1, mode_long = listed ? 1 : 2;
+  const int mode_short = chunked ? 0 : -1, mode_long = chunked ? 3 : 2;
 #define LAUNCH_SEG(V)                                                                                                    \
   seg_reduce_kernel<V><<<max(blocks_short, 1), 256, 0, st>>>(demb, dlin, sorted_pos, seg_offsets, num_segments, m, D, lpr, gsum, \
                                                              gsum_lin, mode_short);                                      \

@@ -588,6 +588,75 @@ class BaseModel(nn.Module):
             ids_t, dense_t = ids_t.pin_memory(), dense_t.pin_memory()
         return ids_t, dense_t
 
+    # Device-staged epochs: when the whole input fits comfortably in HBM the feature arrays go to the device ONCE
+    # per fit() / predict() call, column by column (no [N, m] host matrix, no pinned staging copy), ids are range-checked there, and
+    # every batch is a device-side gather (shuffle) or slice.  Larger inputs keep the pinned double-buffered host feeder.
+    STAGE_FRACTION = 0.25          # of the currently free device memory
+
+    def _can_stage(self, n):
+        if os.environ.get("XDFM_DEVICE_STAGING", "1") == "0" or torch.device(self.device).type != "cuda":
+            return False
+        need = n * (len(self._all_sparse_cols) * 4 + len(self._all_dense_cols) * 4 + 8) * 2      # arrays + one conversion temporary
+        free, _ = torch.cuda.mem_get_info(torch.device(self.device))
+        return need <= self.STAGE_FRACTION * free
+
+    def _device_arrays(self, x):
+        """list / dict of per-feature arrays -> device (ids int32 [N, m_all], dense float32 [N, nd_all]); same column layout, id
+        truncation (== .long()) and IndexError behaviour as _host_arrays."""
+        x = self._as_list(x)
+        names = list(self.feature_index.keys())
+        by_name = dict(zip(names, x))
+        n = x[0].shape[0] if x else 0
+        dev = torch.device(self.device)
+        ids = torch.empty((n, len(self._all_sparse_cols)), dtype=torch.int32, device=dev)
+        dense = torch.empty((n, len(self._all_dense_cols)), dtype=torch.float32, device=dev)
+        checks = []            # (feature name, vocabulary size, device [2] = (min, max))
+
+        def put_ids(j, arr, width, fc):
+            a = np.asarray(arr).reshape(n, -1)
+            if width == 1:
+                a = a[:, :1]
+            elif a.shape[1] != width:
+                raise ValueError("feature '%s': expected %d positions per sample, got %d" % (fc.name, width, a.shape[1]))
+            t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+            if t.is_floating_point():
+                t = t.long()                                   # truncation == .long() (basemodel.py:368-370)
+            if n and fc is not None:
+                checks.append((fc.name, fc.vocabulary_size, torch.stack([t.min(), t.max()]).long()))
+            ids[:, j:j + width] = t
+            return j + width
+
+        j = 0
+        for fc in self._all_sparse:
+            j = put_ids(j, by_name[fc.name], 1, fc)
+        for fc in self._all_varlen:
+            j = put_ids(j, by_name[fc.name], fc.maxlen, fc)
+        for name in self._len_names:
+            j = put_ids(j, by_name[name], 1, None)
+        j = 0
+        for fc in self._all_dense:
+            a = np.asarray(by_name[fc.name]).reshape(n, -1)
+            dense[:, j:j + a.shape[1]] = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+            j += a.shape[1]
+        if checks:
+            mm = torch.stack([c[2] for c in checks]).cpu()     # one sync for all features
+            for (name, vocab, _), (lo, hi) in zip(checks, mm.tolist()):
+                if lo < 0 or hi >= vocab:
+                    raise IndexError("feature '%s': id out of range [0, %d)" % (name, vocab))
+        return ids, dense
+
+    def _device_batches(self, ids, dense, y, batch_size, order=None):
+        """Batches of device-staged arrays: slices, or gathers through the (device copy of the) epoch permutation."""
+        n = ids.shape[0] if order is None else order.shape[0]
+        steps = (n - 1) // batch_size + 1 if n > 0 else 0
+        for i in range(steps):
+            lo, hi = i * batch_size, min(n, (i + 1) * batch_size)
+            if order is None:
+                yield ids[lo:hi], dense[lo:hi], None if y is None else y[lo:hi]
+            else:
+                idx = order[lo:hi]
+                yield ids.index_select(0, idx), dense.index_select(0, idx), None if y is None else y.index_select(0, idx)
+
     def _dist_local_order(self, order, sample_num, batch_size):
         """Row indices this rank trains on, in step order: its slice of every global batch (identical permutation on all ranks)."""
         from ..distributed import rank_slice
@@ -688,8 +757,6 @@ class BaseModel(nn.Module):
         opt = self.optim
         if not isinstance(opt, FusedOptimizer) or self._graph_failed or ops.TIMERS is not None:
             return None
-        if self._dist is not None and type(self)._train_step_inner is not BaseModel._train_step_inner:
-            return None                      # subclasses with their own step body (xDeepFM Pro) stay eager under distribution
         if opt._lazy_active() and opt.steps + 2 - opt._hist_base >= opt._hist_cap:
             return None                      # the history window is about to be rebased: take the eager path for that step
         key = self._graph_key(ids, dense, y)
@@ -796,6 +863,7 @@ class BaseModel(nn.Module):
             self._dist.ensure_capacity(ids.shape[0] * self._dist.sharded.m)
             self._dist.sharded.stash = {}
             if ids.shape[0] == 0:           # this rank has no rows in the last partial batch: take part in the collectives only
+                self._empty_step_collectives()
                 opt.step(apply_l2=True)
                 return None
         for ts in opt.table_sets:
@@ -823,6 +891,9 @@ class BaseModel(nn.Module):
         if pred_log is not None:
             pred_log[pred_off:pred_off + yv.shape[0]] = y_pred.reshape(-1)
         return y_pred
+
+    def _empty_step_collectives(self):
+        """Hook: collectives a subclass issues inside its step body (a rank without rows must still take part)."""
 
     def _epoch_begin(self):
         """Hook for subclasses with extra device-side accumulators (xDeepFM Pro)."""
@@ -891,11 +962,14 @@ class BaseModel(nn.Module):
         if torch.device(self.device).type != "cuda":
             raise RuntimeError("fit(): the xdeepfm-b200 path needs device='cuda:N' (sm_100a); no CPU fallback")
 
-        ids, dense = self._host_arrays(x)
+        staged = self._dist is None and self._can_stage(x[0].shape[0] if x else 0)
+        ids, dense = self._device_arrays(x) if staged else self._host_arrays(x)
         y_t = torch.from_numpy(np.ascontiguousarray(np.asarray(y, dtype=np.float32)).reshape(ids.shape[0], -1))
         if y_t.shape[1] == 1:
             y_t = y_t.reshape(-1)
-        y_t = y_t.pin_memory()
+        y_dev = y_t.to(torch.device(self.device)) if staged else None      # labels stay on the host too (xDeepFM Pro counts positives there)
+        if not staged:
+            y_t = y_t.pin_memory()
         sample_num = ids.shape[0]
         steps_per_epoch = (sample_num - 1) // batch_size + 1
         ctx = self._dist
@@ -943,7 +1017,9 @@ class BaseModel(nn.Module):
             # before the epoch loop; the validation predict() leaves it in eval mode, so from the second epoch on dropout -- and
             # the SFG term of xDeepFM Pro, which is gated on self.training (xdeepfm_pro.py:265) -- are off when validation data
             # is given.  Kept for result parity (tests/golden/fit_pro_small_adam.npz: reference History['sfg_loss'] = [0.41, 0.0]).
-            for ids_b, dense_b, y_b in self._batches(ids, dense, y_t, batch_size, order):
+            feed = self._device_batches(ids, dense, y_dev, batch_size, None if order is None else order.to(dev)) if staged else \
+                self._batches(ids, dense, y_t, batch_size, order)
+            for ids_b, dense_b, y_b in feed:
                 nb = ids_b.shape[0]
                 if fused:
                     if ctx is None:
@@ -1020,12 +1096,15 @@ class BaseModel(nn.Module):
         if torch.device(self.device).type != "cuda":
             raise RuntimeError("predict(): the xdeepfm-b200 path needs device='cuda:N' (sm_100a); no CPU fallback")
         self.eval()
-        ids, dense = self._host_arrays(x)
+        x = self._as_list(x)
+        staged = self._can_stage(x[0].shape[0] if x else 0)
+        ids, dense = self._device_arrays(x) if staged else self._host_arrays(x)
         n = ids.shape[0]
         out = torch.empty((n, 1), dtype=torch.float32, device=torch.device(self.device))
         off = 0
         with torch.no_grad():
-            for ids_b, dense_b, _ in self._batches(ids, dense, None, batch_size, None):
+            feed = self._device_batches(ids, dense, None, batch_size) if staged else self._batches(ids, dense, None, batch_size, None)
+            for ids_b, dense_b, _ in feed:
                 yb = self.forward_ids(ids_b, dense_b)
                 out[off:off + yb.shape[0]] = yb.reshape(-1, 1)
                 off += yb.shape[0]

@@ -66,11 +66,16 @@ class BaseModelSFG(BaseModel):
     def _graph_key(self, ids, dense, y):
         return super()._graph_key(ids, dense, y) + (self._sfg_rows_cap(ids.shape[0]) if self.use_sfg else None,)
 
-    def train_step(self, *args, **kwargs):
+    def train_step(self, ids, dense, y, *args, **kwargs):
+        if self._sfg_in_step_collective():
+            # data parallel: the global positive count is all-reduced HERE, before the (possibly CUDA-graph replayed) step body,
+            # into a static device scalar the body multiplies its row weights with -- no collective inside the captured region
+            self._set_global_sfg_scale(y)
         try:
-            return super().train_step(*args, **kwargs)
+            return super().train_step(ids, dense, y, *args, **kwargs)
         finally:
             self._npos_hint = None           # a hint describes exactly one batch (eager, captured or replayed)
+            self._sfg_scale_ready = False
 
     # ---- SFG loss on the split (ids, dense) feed ------------------------------------------------------
     def sfg_loss_ids(self, ids_all, dense_all, emb, labels):
@@ -82,6 +87,8 @@ class BaseModelSFG(BaseModel):
         flat = emb.reshape(emb.shape[0], -1)
         dec_in = torch.cat([flat, dd], dim=-1) if dd.shape[1] > 0 else flat
         row_w = ops.sfg_row_weights(labels, self.sfg_positive_only)
+        if self._dist is not None and self._dist.world > 1:
+            row_w = row_w * self._global_row_weight_scale(labels)
         B = flat.shape[0]
         cap = self._sfg_rows_cap(B)
         if cap < B:
@@ -100,6 +107,37 @@ class BaseModelSFG(BaseModel):
             pred = ops.linear_act(h, dec.dense_head.weight, dec.dense_head.bias, precision=dec.precision)
             total = total + fn.dense_weight * ops.MaskedMSE.apply(pred, dd, row_w)
         return total.reshape(())
+
+    # ---- data parallel: the SFG normaliser is a property of the GLOBAL batch ---------------------------------
+    # The reference divides the masked reconstruction losses by the number of label-1 rows of the batch it was handed -- with
+    # `gpus=[...]` that is the whole G * batch_size batch on one device (basemodel_sfg.py:279-282 scales batch_size, :316 calls
+    # self.forward_with_sfg, not the DataParallel wrapper).  One process per GPU sees only its slice, so the local weights
+    # mask / (n_local + 1e-8) are rescaled to mask / (n_global + 1e-8) with ONE all-reduce of the count (8 bytes); no host sync.
+    def _sfg_in_step_collective(self):
+        return self.use_sfg and self.sfg_decoder is not None and self.training and self._dist is not None and self._dist.world > 1
+
+    def _set_global_sfg_scale(self, labels):
+        dev = torch.device(self.device)
+        if getattr(self, "_sfg_scale_buf", None) is None or self._sfg_scale_buf.device != dev:
+            self._sfg_scale_buf = torch.ones(1, dtype=torch.float32, device=dev)
+        self._sfg_scale_ready = False
+        self._sfg_scale_buf.copy_(self._global_row_weight_scale(labels.to(dev)).reshape(1))
+        self._sfg_scale_ready = True
+
+    def _global_row_weight_scale(self, labels):
+        if getattr(self, "_sfg_scale_ready", False):
+            return self._sfg_scale_buf           # set by train_step() for this batch
+        y = labels.reshape(-1)
+        local = ((y == 1).sum() if self.sfg_positive_only else torch.full((), y.shape[0], device=y.device)).to(torch.float64)
+        glob = local.clone().reshape(1)
+        self._dist.all_reduce_sum(glob)
+        eps = 1e-8 if self.sfg_positive_only else 0.0
+        return ((local + eps) / (glob[0] + eps)).to(torch.float32)
+
+    def _empty_step_collectives(self):
+        if self._sfg_in_step_collective() and not getattr(self, "_sfg_scale_ready", False):
+            zero = torch.zeros(1, dtype=torch.float64, device=torch.device(self.device))
+            self._dist.all_reduce_sum(zero)          # this rank has no rows in the last partial batch: 0 positives of 0 rows
 
     def compute_sfg_loss(self, X, sparse_embedding_list, dense_value_list, labels):
         """Reference-shaped entry (basemodel_sfg.py:420-476)."""
@@ -167,5 +205,9 @@ class BaseModelSFG(BaseModel):
         (basemodel_sfg.py:344, 369-371)."""
         if not self.use_sfg:
             return 0.0, {}
-        s = 0.0 if self._sfg_accum is None else float(self._sfg_accum.item())
+        acc = self._sfg_accum
+        if self._dist is not None and self._dist.world > 1:
+            acc = torch.zeros(1, dtype=torch.float64, device=torch.device(self.device)) if acc is None else acc.clone()
+            self._dist.all_reduce_sum(acc)           # every rank accumulated its share of the globally normalised loss
+        s = 0.0 if acc is None else float(acc.item())
         return self.sfg_weight * s, {"sfg_loss": s / sample_num}
