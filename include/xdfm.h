@@ -246,6 +246,16 @@ int xdfm_mhsa_bwd(const float* q, const float* k, const float* v, const float* o
 /* diagnostic switch: 1 (default) = four query / key rows per thread and shared-memory load when head_dim is exactly 2 or 4;
  * 0 = one row per thread */
 void xdfm_mhsa_set_row_blocked(int v);
+/* the same attention core with dropout on the probabilities (nn.Dropout(attn_probs), deepctr/layers/cin_attention.py:54, 86):
+ * keep mask = counter-based hash of (*seed_dev, sample, head, query, key) >= p * 2^32, recomputed by the backward (pass the same p
+ * and a seed buffer holding the same value); kept probabilities are scaled by 1 / (1 - p).  seed_dev: device uint64 [1], read by the
+ * kernel (so a CUDA-graph replay sees the value the host-side counter kernel left there).  xdfm_mhsa_dropout_mask materialises the
+ * mask [B, heads, L, L] uint8 for tests. */
+int xdfm_mhsa_fwd_dropout(const float* q, const float* k, const float* v, int64_t B, int L, int E, int heads, float p, const void* seed_dev,
+                          float* o, float* lse, void* stream);
+int xdfm_mhsa_bwd_dropout(const float* q, const float* k, const float* v, const float* o, const float* lse, const float* dout, int64_t B,
+                          int L, int E, int heads, float p, const void* seed_dev, float* dq, float* dk, float* dv, void* stream);
+int xdfm_mhsa_dropout_mask(int64_t B, int L, int heads, float p, const void* seed_dev, unsigned char* mask, void* stream);
 int xdfm_add_ln_fwd(const float* a, const float* r, const float* gamma, const float* beta, int64_t rows, int E, float eps, int normalize,
                     float* y, float* mean, float* rstd, void* stream);
 int xdfm_add_ln_bwd_blocks(int64_t rows);

@@ -378,12 +378,23 @@ def seqpool_cases():
     print("seqpool_cases", len(out), "arrays")
 
 
-def varlen_model_case(name, B, seed):
-    """One reference xDeepFM train step (no optimizer) with multi-value features in the linear, CIN and DNN parts."""
+def varlen_model_case(name, B, seed, variant="xdeepfm"):
+    """One reference train step (no optimizer) with multi-value features in the linear, CIN and DNN parts: xDeepFM, the attention
+    variants (`variant` = attn / attn_v2) or xDeepFMPro without SFG (the reference's SFG decoder does not accept multi-value
+    columns: its input width is sized from the SparseFeat columns only and the forward fails with a shape error)."""
     from deepctr.inputs import VarLenSparseFeat
     cols = columns_from_desc(VARLEN_COLUMNS, SparseFeat, DenseFeat, VarLenSparseFeat)
-    model = xDeepFM(cols, cols, dnn_hidden_units=(32, 16), cin_layer_size=(16, 8), l2_reg_linear=1e-3, l2_reg_embedding=1e-3,
-                    l2_reg_dnn=1e-3, l2_reg_cin=1e-3, device="cpu")
+    common = dict(dnn_hidden_units=(32, 16), cin_layer_size=(16, 8), l2_reg_linear=1e-3, l2_reg_embedding=1e-3, l2_reg_dnn=1e-3,
+                  l2_reg_cin=1e-3, device="cpu")
+    if variant == "attn":
+        model = xDeepFMAttention(cols, cols, cin_num_heads=4, **common)
+    elif variant == "attn_v2":
+        model = xDeepFMAttentionV2(cols, cols, cin_num_heads=2, cin_num_attn_layers=2, **common)
+    elif variant == "pro_nosfg":
+        from deepctr.xdeepfm_pro import xDeepFMPro
+        model = xDeepFMPro(cols, cols, use_sfg=False, use_autodis=False, **common)
+    else:
+        model = xDeepFM(cols, cols, **common)
     params = varlen_params(model, seed)
     model.load_state_dict(params, strict=True)
     X, y = varlen_inputs(VARLEN_COLUMNS, model.feature_index, B, seed)
@@ -396,7 +407,7 @@ def varlen_model_case(name, B, seed):
     total.backward()
     out = {"X": X.numpy(), "y": y.numpy(), "y_pred": y_pred.detach().numpy(), "loss": loss.detach().numpy(),
            "reg_loss": reg.detach().numpy(), "total": total.detach().numpy(), "columns_json": np.array(json.dumps(VARLEN_COLUMNS)),
-           "feature_names": np.array(json.dumps(list(model.feature_index.keys())))}
+           "feature_names": np.array(json.dumps(list(model.feature_index.keys()))), "variant": np.array(variant)}
     for k, p in model.named_parameters():
         out["grad::" + k] = (p.grad if p.grad is not None else torch.zeros_like(p)).numpy()
     model.eval()
@@ -449,6 +460,14 @@ def main_varlen():
     seqpool_cases()
     varlen_model_case("xdeepfm_varlen", B=48, seed=51)
     varlen_fit_case("fit_varlen_adam", N=96, batch_size=32, epochs=2, seed=52, lr=1e-2)
+    main_varlen_variants()
+
+
+def main_varlen_variants():
+    """Multi-value features in the other model classes (`python -m oracle.make_golden varlen_variants`)."""
+    varlen_model_case("attn_varlen", B=40, seed=53, variant="attn")
+    varlen_model_case("attn_v2_varlen", B=40, seed=54, variant="attn_v2")
+    varlen_model_case("pro_nosfg_varlen", B=40, seed=55, variant="pro_nosfg")
 
 
 if __name__ == "__main__":
@@ -458,6 +477,10 @@ if __name__ == "__main__":
         main_autodis()
     elif len(sys.argv) > 1 and sys.argv[1] == "varlen":
         main_varlen()
+    elif len(sys.argv) > 1 and sys.argv[1] == "varlen_variants":
+        os.makedirs(GOLD, exist_ok=True)
+        torch.set_num_threads(4)
+        main_varlen_variants()
     elif len(sys.argv) > 1 and sys.argv[1] == "cfg2":
         main_cfg2()
     else:

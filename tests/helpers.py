@@ -109,8 +109,16 @@ def product_columns(desc):
     return cols
 
 
-def build_varlen_product_model(desc, device="cuda:0"):
-    from deepctr.models import xDeepFM
+def build_varlen_product_model(desc, device="cuda:0", variant="xdeepfm"):
+    from deepctr.models import xDeepFM, xDeepFMAttention, xDeepFMAttentionV2
     cols = product_columns(desc)
-    return xDeepFM(cols, cols, dnn_hidden_units=(32, 16), cin_layer_size=(16, 8), l2_reg_linear=1e-3, l2_reg_embedding=1e-3,
-                   l2_reg_dnn=1e-3, l2_reg_cin=1e-3, device=device)
+    common = dict(dnn_hidden_units=(32, 16), cin_layer_size=(16, 8), l2_reg_linear=1e-3, l2_reg_embedding=1e-3, l2_reg_dnn=1e-3,
+                  l2_reg_cin=1e-3, device=device)
+    if variant == "attn":
+        return xDeepFMAttention(cols, cols, cin_num_heads=4, **common)
+    if variant == "attn_v2":
+        return xDeepFMAttentionV2(cols, cols, cin_num_heads=2, cin_num_attn_layers=2, **common)
+    if variant == "pro_nosfg":
+        from deepctr.xdeepfm_pro import xDeepFMPro
+        return xDeepFMPro(cols, cols, use_sfg=False, use_autodis=False, **common)
+    return xDeepFM(cols, cols, **common)

@@ -205,3 +205,75 @@ def test_small_linear_partial_outputs_and_limits():
         ops.SmallLinear.apply(x.detach(), None, 0, wide)
     y = ops.linear_act(x.detach(), wide)                       # falls through to the SGEMM path
     _close(y, x.detach().double().cpu() @ wide.double().cpu().t(), "wide layer")
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# attention dropout (reference: nn.Dropout on the probabilities, cin_attention.py:54, 86)
+# ---------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,L,E,heads,p", [(3, 37, 8, 4, 0.25), (2, 64, 16, 4, 0.5), (2, 21, 10, 2, 0.1), (1, 256, 16, 4, 0.3)])
+def test_mhsa_core_with_dropout_matches_torch_under_the_same_mask(B, L, E, heads, p):
+    """The fused core recomputes the keep mask from (seed, sample, head, query, key); xdfm_mhsa_dropout_mask materialises the same
+    mask, with which plain torch reproduces forward and backward: o = (mask / (1 - p) * softmax(q k^T / sqrt(hd))) v."""
+    from deepctr import _native as Nv
+    from deepctr import ops
+    g = torch.Generator().manual_seed(B * 1000 + L)
+    q, k, v = (torch.randn(B, L, E, generator=g) for _ in range(3))
+    dout = torch.randn(B, L, E, generator=g)
+    ops.reset_dropout_state()
+    st = ops.dropout_state(torch.device(DEV))
+    seed = st.clone()
+    mask = torch.empty((B, heads, L, L), dtype=torch.uint8, device=DEV)
+    Nv.check(Nv.lib().xdfm_mhsa_dropout_mask(B, L, heads, p, Nv.ptr(seed), Nv.ptr(mask), Nv.stream_ptr()))
+    keep = mask.double().cpu()
+    frac = keep.mean().item()
+    n = keep.numel()
+    assert abs(frac - (1 - p)) < 5 * (p * (1 - p) / n) ** 0.5 + 1e-3, "kept fraction %.4f, expected %.4f" % (frac, 1 - p)
+    qd, kd, vd = (t.to(DEV).requires_grad_(True) for t in (q, k, v))
+    o = ops.MHSACore.apply(qd, kd, vd, heads, p)
+    assert int(st.item()) != int(seed.item()), "the counter must advance"
+    o.backward(dout.to(DEV))
+    hd = E // heads
+    qr, kr, vr = (t.double().requires_grad_(True) for t in (q, k, v))
+    qh, kh, vh = (t.view(B, L, heads, hd).transpose(1, 2) for t in (qr, kr, vr))
+    probs = torch.softmax(qh @ kh.transpose(-2, -1) / hd ** 0.5, dim=-1) * keep / (1 - p)
+    ref = (probs @ vh).transpose(1, 2).reshape(B, L, E)
+    ref.backward(dout.double())
+    assert_close(o, ref, 2e-5, 2e-5 * ref.abs().max().item(), "o")
+    for name, got, want in (("dq", qd.grad, qr.grad), ("dk", kd.grad, kr.grad), ("dv", vd.grad, vr.grad)):
+        assert_close(got, want, 2e-4, 2e-5 * want.abs().max().item(), name)
+    # a second call draws a different mask; eval-style p = 0 is the plain kernel
+    o2 = ops.MHSACore.apply(qd, kd, vd, heads, p)
+    assert not torch.equal(o2, o)
+
+
+def test_attention_model_trains_with_attn_dropout_and_is_deterministic_in_eval():
+    """xDeepFMAttention(cin_attn_dropout > 0): training steps run (the reference applies nn.Dropout there; this build raised before),
+    the loss decreases, eval-mode predictions are dropout-free and reproducible, CUDA-graph replayed steps keep drawing new masks."""
+    from deepctr import ops
+    from deepctr.inputs import DenseFeat, SparseFeat
+    from deepctr.models import xDeepFMAttention
+    g = torch.Generator().manual_seed(3)
+    vocab = [30, 11, 200, 7, 50]
+    cols = [SparseFeat("C%d" % i, v, 8) for i, v in enumerate(vocab)] + [DenseFeat("I0", 1), DenseFeat("I1", 1)]
+    model = xDeepFMAttention(cols, cols, dnn_hidden_units=(32, 16), cin_layer_size=(16, 8), cin_num_heads=4, cin_attn_dropout=0.2,
+                             device=DEV, init_std=0.05)
+    assert model.cin.mhsa.dropout_rate == 0.2
+    model.compile("adam", "binary_crossentropy")
+    B = 64
+    ids = torch.stack([torch.randint(0, v, (B,), generator=g) for v in vocab], 1).to(torch.int32).to(DEV)
+    dense = torch.rand(B, 2, generator=g).to(DEV)
+    y = ((ids[:, 0] % 2 == 0) ^ (dense[:, 0] > 0.5)).float()
+    model.train()
+    losses, seeds = [], []
+    for _ in range(12):
+        accum = torch.zeros(1, dtype=torch.float64, device=DEV)
+        model.train_step(ids, dense, y, accum)
+        losses.append(accum.item())
+        seeds.append(int(ops.dropout_state(torch.device(DEV)).item()))
+    assert model._graphs, "the dropout step is CUDA-graph capturable (the seed lives on the device)"
+    assert len(set(seeds)) == len(seeds), "every step (replayed ones included) advances the dropout counter"
+    assert losses[-1] < losses[0]
+    model.eval()
+    with torch.no_grad():
+        a, b = model.forward_ids(ids, dense), model.forward_ids(ids, dense)
+    assert torch.equal(a, b)

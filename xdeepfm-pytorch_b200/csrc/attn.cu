@@ -55,12 +55,37 @@ __device__ __forceinline__ void load_head(float (&dst)[HDM], const float* __rest
   }
 }
 
-// HDM = compile-time bound of head_dim; EXACT = (head_dim == HDM)
-template <int HDM, bool EXACT>
+// Dropout on the attention probabilities (reference: nn.Dropout(attn_probs), cin_attention.py:54, 86).  The probabilities never
+// leave the SM, so the keep mask is a counter-based hash of (seed, sample, head, query, key) that the forward and both phases of the
+// backward recompute: no mask tensor, no RNG state.  32-bit avalanche mixers (murmur3 / splitmix finalizers) over the 64-bit
+// element index and the 64-bit seed; keep iff hash >= p * 2^32.  (Bit-wise parity with torch's Philox stream is not a goal:
+// SURVEY.md section 7, hard part 8.)
+struct DropCfg {
+  const unsigned long long* seed;     // device [1]
+  unsigned int threshold;             // p * 2^32 (p < 1)
+  float inv_keep;                     // 1 / (1 - p)
+};
+
+__device__ __forceinline__ unsigned int mix32(unsigned int x) {
+  x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+  return x;
+}
+
+__device__ __forceinline__ bool drop_keep(unsigned long long seed, unsigned long long row_index, int j, unsigned int threshold) {
+  // row_index = ((b * nh + h) * L + l): one 64-bit value per (sample, head, query); j = key
+  const unsigned int a = mix32((unsigned int)row_index ^ (unsigned int)seed);
+  const unsigned int c = mix32((unsigned int)(row_index >> 32) + (unsigned int)(seed >> 32) * 0x9e3779b9u + a);
+  return mix32(c ^ ((unsigned int)j * 0x9e3779b1u + 0x7f4a7c15u)) >= threshold;
+}
+
+// HDM = compile-time bound of head_dim; EXACT = (head_dim == HDM); DROP = dropout on the probabilities
+template <int HDM, bool EXACT, bool DROP>
 __global__ void __launch_bounds__(ATT_THREADS) mhsa_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                                const float* __restrict__ v, int L, int E, int nh, int hd,
-                                                               float scale_log2e, float* __restrict__ o, float* __restrict__ lse) {
+                                                               float scale_log2e, float* __restrict__ o, float* __restrict__ lse,
+                                                               DropCfg drop) {
   extern __shared__ __align__(16) float sm_att[];
+  const unsigned long long seed = DROP ? *drop.seed : 0ull;
   float* sK = sm_att;
   float* sV = sm_att + (size_t)L * E;
   const int64_t b = blockIdx.x;
@@ -79,6 +104,7 @@ __global__ void __launch_bounds__(ATT_THREADS) mhsa_fwd_kernel(const float* __re
       float mx = -CUDART_INF_F, s = 0.f;
       const float* kr = sK + h * hd;
       const float* vr = sV + h * hd;
+      const unsigned long long rix = ((unsigned long long)b * nh + h) * L + l;
       for (int j = 0; j < L; ++j, kr += E, vr += E) {
         float kk[HDM], vv[HDM];
         load_head<HDM, EXACT>(kk, kr, hd);
@@ -94,11 +120,12 @@ __global__ void __launch_bounds__(ATT_THREADS) mhsa_fwd_kernel(const float* __re
           mx = d;
         }
         const float p = fast_exp2(d - mx);
-        s += p;
+        s += p;                                   // the softmax denominator sees every key; dropped keys only leave the numerator
+        const float pk = (!DROP || drop_keep(seed, rix, j, drop.threshold)) ? p : 0.f;
 #pragma unroll
-        for (int i = 0; i < HDM; ++i) acc[i] = fmaf(p, vv[i], acc[i]);
+        for (int i = 0; i < HDM; ++i) acc[i] = fmaf(pk, vv[i], acc[i]);
       }
-      const float inv = 1.f / s;
+      const float inv = (DROP ? drop.inv_keep : 1.f) / s;
 #pragma unroll
       for (int i = 0; i < HDM; ++i)
         if (i < hd) o[base + (size_t)l * E + h * hd + i] = acc[i] * inv;
@@ -107,13 +134,16 @@ __global__ void __launch_bounds__(ATT_THREADS) mhsa_fwd_kernel(const float* __re
   }
 }
 
-template <int HDM, bool EXACT>
+template <int HDM, bool EXACT, bool DROP>
 __global__ void __launch_bounds__(ATT_THREADS) mhsa_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                                const float* __restrict__ v, const float* __restrict__ o,
                                                                const float* __restrict__ lse, const float* __restrict__ dout, int L, int E,
                                                                int nh, int hd, float scale, float* __restrict__ dq, float* __restrict__ dk,
-                                                               float* __restrict__ dv) {
+                                                               float* __restrict__ dv, DropCfg drop) {
   extern __shared__ __align__(16) float sm_att[];
+  const unsigned long long seed = DROP ? *drop.seed : 0ull;
+  // with P~ = keep / (1 - p) * P:  o = P~ V,  dP = keep / (1 - p) * (dO . v),  D = sum_j P dP = dO . o (unchanged),
+  // dS = P * (dP - D),  dV_j = sum_l P~_lj dO_l
   float* sA = sm_att;                          // phase A: K      phase B: Q
   float* sB = sm_att + (size_t)L * E;          // phase A: V      phase B: dO
   float* sLse = sB + (size_t)L * E;            // [nh][L]
@@ -145,6 +175,7 @@ __global__ void __launch_bounds__(ATT_THREADS) mhsa_bwd_kernel(const float* __re
       const float ls = sLse[h * L + l], Dl = sD[h * L + l];
       const float* kr = sA + h * hd;
       const float* vr = sB + h * hd;
+      const unsigned long long rix = ((unsigned long long)b * nh + h) * L + l;
       for (int j = 0; j < L; ++j, kr += E, vr += E) {
         float kk[HDM], vv[HDM];
         load_head<HDM, EXACT>(kk, kr, hd);
@@ -152,6 +183,7 @@ __global__ void __launch_bounds__(ATT_THREADS) mhsa_bwd_kernel(const float* __re
         float d = 0.f, dp = 0.f;
 #pragma unroll
         for (int i = 0; i < HDM; ++i) { d = fmaf(qv[i], kk[i], d); dp = fmaf(dov[i], vv[i], dp); }
+        if (DROP) dp = drop_keep(seed, rix, j, drop.threshold) ? dp * drop.inv_keep : 0.f;
         const float ds = fast_exp2(d - ls) * (dp - Dl);
 #pragma unroll
         for (int i = 0; i < HDM; ++i) acc[i] = fmaf(ds, kk[i], acc[i]);
@@ -188,9 +220,15 @@ __global__ void __launch_bounds__(ATT_THREADS) mhsa_bwd_kernel(const float* __re
 #pragma unroll
         for (int i = 0; i < HDM; ++i) { d = fmaf(qq[i], kv[i], d); dp = fmaf(dd[i], vv[i], dp); }
         const float p = fast_exp2(d - lsr[l]);
+        float pk = p;
+        if (DROP) {
+          const bool keep = drop_keep(seed, ((unsigned long long)b * nh + h) * L + l, j, drop.threshold);
+          dp = keep ? dp * drop.inv_keep : 0.f;
+          pk = keep ? p * drop.inv_keep : 0.f;
+        }
         const float ds = p * (dp - Dr[l]);
 #pragma unroll
-        for (int i = 0; i < HDM; ++i) { dvv[i] = fmaf(p, dd[i], dvv[i]); dkv[i] = fmaf(ds, qq[i], dkv[i]); }
+        for (int i = 0; i < HDM; ++i) { dvv[i] = fmaf(pk, dd[i], dvv[i]); dkv[i] = fmaf(ds, qq[i], dkv[i]); }
       }
 #pragma unroll
       for (int i = 0; i < HDM; ++i)
@@ -431,8 +469,21 @@ static int mhsa_check(int64_t B, int L, int E, int nh, size_t smem_floats, const
   return XDFM_OK;
 }
 
-extern "C" int xdfm_mhsa_fwd(const float* q, const float* k, const float* v, int64_t B, int L, int E, int heads, float* o, float* lse,
-                             void* stream) {
+static int make_drop_cfg(float p, const void* seed_dev, DropCfg* cfg, const char* what) {
+  XDFM_CHECK_ARG(p >= 0.f && p < 1.f, "%s: dropout p=%g must be in [0, 1)", what, (double)p);
+  XDFM_CHECK_ARG(p == 0.f || seed_dev != nullptr, "%s: dropout needs a device seed", what);
+  cfg->seed = (const unsigned long long*)seed_dev;
+  cfg->threshold = (unsigned int)std::min(4294967295.0, (double)p * 4294967296.0);
+  cfg->inv_keep = 1.f / (1.f - p);
+  return XDFM_OK;
+}
+
+static int mhsa_fwd_impl(const float* q, const float* k, const float* v, int64_t B, int L, int E, int heads, float p, const void* seed_dev,
+                         float* o, float* lse, void* stream) {
+  DropCfg drop;
+  int rc0 = make_drop_cfg(p, seed_dev, &drop, "mhsa_fwd");
+  if (rc0) return rc0;
+  const bool use_drop = p > 0.f;
   const size_t smem = (size_t)2 * L * E;
   int rc = mhsa_check(B, L, E, heads, smem, "mhsa_fwd");
   if (rc) return rc;
@@ -440,14 +491,15 @@ extern "C" int xdfm_mhsa_fwd(const float* q, const float* k, const float* v, int
   const int hd = E / heads;
   const float scale_log2e = 1.4426950408889634f / sqrtf((float)hd);
   cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH_FWD_(HDM, EX)                                                                                                \
+#define LAUNCH_FWD_(HDM, EX, DR)                                                                                            \
   do {                                                                                                                      \
-    XDFM_CUDA(cudaFuncSetAttribute(mhsa_fwd_kernel<HDM, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem * 4))); \
-    mhsa_fwd_kernel<HDM, EX><<<(unsigned)B, ATT_THREADS, smem * 4, st>>>(q, k, v, L, E, heads, hd, scale_log2e, o, lse);    \
+    XDFM_CUDA(cudaFuncSetAttribute(mhsa_fwd_kernel<HDM, EX, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem * 4))); \
+    mhsa_fwd_kernel<HDM, EX, DR><<<(unsigned)B, ATT_THREADS, smem * 4, st>>>(q, k, v, L, E, heads, hd, scale_log2e, o, lse, drop); \
   } while (0)
 #define LAUNCH_FWD(HDM)                                                                                                     \
   do {                                                                                                                      \
-    if (hd == HDM) LAUNCH_FWD_(HDM, true); else LAUNCH_FWD_(HDM, false);                                                    \
+    if (use_drop) { if (hd == HDM) LAUNCH_FWD_(HDM, true, true); else LAUNCH_FWD_(HDM, false, true); }                      \
+    else { if (hd == HDM) LAUNCH_FWD_(HDM, true, false); else LAUNCH_FWD_(HDM, false, false); }                             \
   } while (0)
 #define LAUNCH_FWD_RB(HDM)                                                                                                  \
   do {                                                                                                                      \
@@ -455,7 +507,8 @@ extern "C" int xdfm_mhsa_fwd(const float* q, const float* k, const float* v, int
     mhsa_fwd_rb_kernel<HDM><<<(unsigned)B, ATT_THREADS, smem * 4, st>>>(q, k, v, L, E, heads, scale_log2e, o, lse);          \
   } while (0)
   // wider heads need 4 x 4 x head_dim registers per thread in the backward (8: 177, 16: spills): one row per thread there
-  const bool rb = g_mhsa_row_blocked && ((hd == 2 && E % 2 == 0) || (hd == 4 && E % 4 == 0));
+  // (dropout runs on the one-row-per-thread kernels: the hash per (query, key) pair dominates there anyway)
+  const bool rb = !use_drop && g_mhsa_row_blocked && ((hd == 2 && E % 2 == 0) || (hd == 4 && E % 4 == 0));
   if (rb && hd == 2) LAUNCH_FWD_RB(2); else if (rb && hd == 4) LAUNCH_FWD_RB(4);
   else if (hd <= 2) LAUNCH_FWD(2); else if (hd <= 4) LAUNCH_FWD(4); else if (hd <= 8) LAUNCH_FWD(8); else if (hd <= 16) LAUNCH_FWD(16);
   else LAUNCH_FWD(32);
@@ -466,8 +519,22 @@ extern "C" int xdfm_mhsa_fwd(const float* q, const float* k, const float* v, int
   return XDFM_OK;
 }
 
-extern "C" int xdfm_mhsa_bwd(const float* q, const float* k, const float* v, const float* o, const float* lse, const float* dout,
-                             int64_t B, int L, int E, int heads, float* dq, float* dk, float* dv, void* stream) {
+extern "C" int xdfm_mhsa_fwd(const float* q, const float* k, const float* v, int64_t B, int L, int E, int heads, float* o, float* lse,
+                             void* stream) {
+  return mhsa_fwd_impl(q, k, v, B, L, E, heads, 0.f, nullptr, o, lse, stream);
+}
+
+extern "C" int xdfm_mhsa_fwd_dropout(const float* q, const float* k, const float* v, int64_t B, int L, int E, int heads, float p,
+                                     const void* seed_dev, float* o, float* lse, void* stream) {
+  return mhsa_fwd_impl(q, k, v, B, L, E, heads, p, seed_dev, o, lse, stream);
+}
+
+static int mhsa_bwd_impl(const float* q, const float* k, const float* v, const float* o, const float* lse, const float* dout,
+                         int64_t B, int L, int E, int heads, float p, const void* seed_dev, float* dq, float* dk, float* dv, void* stream) {
+  DropCfg drop;
+  int rc0 = make_drop_cfg(p, seed_dev, &drop, "mhsa_bwd");
+  if (rc0) return rc0;
+  const bool use_drop = p > 0.f;
   const size_t smem = (size_t)2 * L * E + (size_t)2 * L * heads;
   int rc = mhsa_check(B, L, E, heads, smem, "mhsa_bwd");
   if (rc) return rc;
@@ -475,27 +542,61 @@ extern "C" int xdfm_mhsa_bwd(const float* q, const float* k, const float* v, con
   const int hd = E / heads;
   const float scale = 1.f / sqrtf((float)hd);
   cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH_BWD_(HDM, EX)                                                                                                \
+#define LAUNCH_BWD_(HDM, EX, DR)                                                                                            \
   do {                                                                                                                      \
-    XDFM_CUDA(cudaFuncSetAttribute(mhsa_bwd_kernel<HDM, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem * 4))); \
-    mhsa_bwd_kernel<HDM, EX><<<(unsigned)B, ATT_THREADS, smem * 4, st>>>(q, k, v, o, lse, dout, L, E, heads, hd, scale, dq, dk, dv); \
+    XDFM_CUDA(cudaFuncSetAttribute(mhsa_bwd_kernel<HDM, EX, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem * 4))); \
+    mhsa_bwd_kernel<HDM, EX, DR><<<(unsigned)B, ATT_THREADS, smem * 4, st>>>(q, k, v, o, lse, dout, L, E, heads, hd, scale, dq, dk, dv, drop); \
   } while (0)
 #define LAUNCH_BWD(HDM)                                                                                                     \
   do {                                                                                                                      \
-    if (hd == HDM) LAUNCH_BWD_(HDM, true); else LAUNCH_BWD_(HDM, false);                                                    \
+    if (use_drop) { if (hd == HDM) LAUNCH_BWD_(HDM, true, true); else LAUNCH_BWD_(HDM, false, true); }                      \
+    else { if (hd == HDM) LAUNCH_BWD_(HDM, true, false); else LAUNCH_BWD_(HDM, false, false); }                             \
   } while (0)
 #define LAUNCH_BWD_RB(HDM)                                                                                                  \
   do {                                                                                                                      \
     XDFM_CUDA(cudaFuncSetAttribute(mhsa_bwd_rb_kernel<HDM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem * 4)));  \
     mhsa_bwd_rb_kernel<HDM><<<(unsigned)B, ATT_THREADS, smem * 4, st>>>(q, k, v, o, lse, dout, L, E, heads, scale, dq, dk, dv); \
   } while (0)
-  const bool rb = g_mhsa_row_blocked && ((hd == 2 && E % 2 == 0) || (hd == 4 && E % 4 == 0));
+  const bool rb = !use_drop && g_mhsa_row_blocked && ((hd == 2 && E % 2 == 0) || (hd == 4 && E % 4 == 0));
   if (rb && hd == 2) LAUNCH_BWD_RB(2); else if (rb && hd == 4) LAUNCH_BWD_RB(4);
   else if (hd <= 2) LAUNCH_BWD(2); else if (hd <= 4) LAUNCH_BWD(4); else if (hd <= 8) LAUNCH_BWD(8); else if (hd <= 16) LAUNCH_BWD(16);
   else LAUNCH_BWD(32);
 #undef LAUNCH_BWD_RB
 #undef LAUNCH_BWD
 #undef LAUNCH_BWD_
+  XDFM_LAUNCH_CHECK();
+  return XDFM_OK;
+}
+
+extern "C" int xdfm_mhsa_bwd(const float* q, const float* k, const float* v, const float* o, const float* lse, const float* dout,
+                             int64_t B, int L, int E, int heads, float* dq, float* dk, float* dv, void* stream) {
+  return mhsa_bwd_impl(q, k, v, o, lse, dout, B, L, E, heads, 0.f, nullptr, dq, dk, dv, stream);
+}
+
+extern "C" int xdfm_mhsa_bwd_dropout(const float* q, const float* k, const float* v, const float* o, const float* lse, const float* dout,
+                                     int64_t B, int L, int E, int heads, float p, const void* seed_dev, float* dq, float* dk, float* dv,
+                                     void* stream) {
+  return mhsa_bwd_impl(q, k, v, o, lse, dout, B, L, E, heads, p, seed_dev, dq, dk, dv, stream);
+}
+
+// the keep mask the dropout kernels recompute, materialised (tests / debugging): mask [B, heads, L, L] uint8
+__global__ void mhsa_dropout_mask_kernel(int64_t total, int L, int nh, DropCfg drop, unsigned char* __restrict__ mask) {
+  const unsigned long long seed = *drop.seed;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % L);
+    mask[i] = drop_keep(seed, (unsigned long long)(i / L), j, drop.threshold) ? 1 : 0;
+  }
+}
+
+extern "C" int xdfm_mhsa_dropout_mask(int64_t B, int L, int heads, float p, const void* seed_dev, unsigned char* mask, void* stream) {
+  DropCfg drop;
+  int rc = make_drop_cfg(p, seed_dev, &drop, "mhsa_dropout_mask");
+  if (rc) return rc;
+  XDFM_CHECK_ARG(seed_dev != nullptr, "mhsa_dropout_mask: needs a device seed");
+  const int64_t total = B * heads * (int64_t)L * L;
+  if (total == 0) return XDFM_OK;
+  int blocks = (int)std::min<int64_t>((int64_t)xdfm_num_sms() * 8, ceil_div64(total, 256));
+  mhsa_dropout_mask_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(total, L, heads, drop, mask);
   XDFM_LAUNCH_CHECK();
   return XDFM_OK;
 }

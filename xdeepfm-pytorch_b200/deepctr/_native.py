@@ -86,6 +86,9 @@ _SIGS = {
     "xdfm_small_linear_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, c_int, _P, _P, _P, _P]),
     "xdfm_small_linear_set_staged": (None, [c_int]),
     "xdfm_mhsa_set_row_blocked": (None, [c_int]),
+    "xdfm_mhsa_fwd_dropout": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, ctypes.c_float, _P, _P, _P, _P]),
+    "xdfm_mhsa_bwd_dropout": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, ctypes.c_float, _P, _P, _P, _P, _P]),
+    "xdfm_mhsa_dropout_mask": (c_int, [c_int64, c_int, c_int, ctypes.c_float, _P, _P, _P]),
     "xdfm_small_linear_bwd_dx": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P]),
     "xdfm_small_linear_bwd_dw_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int]),
     "xdfm_small_linear_bwd_dw": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),

@@ -45,11 +45,13 @@ class MultiHeadSelfAttention(nn.Module):
         self.to(device)
 
     def forward(self, x):
-        if self.dropout_rate > 0 and self.training:
-            raise NotImplementedError("attention dropout > 0 is not fused (the probabilities never leave the SM); the reference "
-                                      "default and its run scripts use 0.0")
         q, k, v = ops.linear_multi(x, [self.W_q.weight, self.W_k.weight, self.W_v.weight], precision=self.precision)
-        o = ops.MHSACore.apply(q, k, v, self.num_heads)
+        # dropout on the probabilities (cin_attention.py:54, 86) happens inside the fused core: the keep mask is a counter-based hash
+        # the backward recomputes; active in training mode only, like nn.Dropout
+        p = float(self.dropout_rate) if (self.training and self.dropout_rate > 0) else 0.0
+        if p >= 1.0:
+            return ops.linear_act(torch.zeros_like(x), self.W_o.weight, precision=self.precision) + 0.0 * (q + k + v)
+        o = ops.MHSACore.apply(q, k, v, self.num_heads, p)
         return ops.linear_act(o, self.W_o.weight, precision=self.precision)
 
 

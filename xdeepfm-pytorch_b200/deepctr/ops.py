@@ -810,21 +810,54 @@ def bce_sum(y_pred, labels, loss_accum=None, scale=1.0, want_grad=True):
 # ------------------------------------------------------------------------------------------------
 # field self-attention block over the CIN feature maps (deepctr/layers/cin_attention.py)
 # ------------------------------------------------------------------------------------------------
+_DROPOUT_STATE = {}
+
+
+def dropout_state(device):
+    """Device-resident uint64 counter [1] feeding the in-kernel dropout hashes (one per device).  Seeded from torch's CUDA generator
+    on first use (torch.manual_seed makes runs reproducible); every consumer clones the current value and then advances the
+    counter with a device-side add, so the sequence survives CUDA-graph replay (a host-drawn seed would be baked into the graph)."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    st = _DROPOUT_STATE.get(key)
+    if st is None:
+        base = int(torch.randint(0, 2 ** 62, (1,), device=device).item())
+        st = _DROPOUT_STATE[key] = torch.tensor([base], dtype=torch.int64, device=device)
+    return st
+
+
+def reset_dropout_state(seed=None):
+    """Forget the per-device dropout counters (the next use re-seeds from torch's generator) or set them to `seed`."""
+    if seed is None:
+        _DROPOUT_STATE.clear()
+    else:
+        for st in _DROPOUT_STATE.values():
+            st.fill_(int(seed))
+
+
 class MHSACore(torch.autograd.Function):
-    """o = softmax(q k^T / sqrt(head_dim)) v per head; q, k, v [B, L, E].  Scores never leave the SM; the backward recomputes
-    the probabilities from the saved log-sum-exp (reference: cin_attention.py:73-95 materialises [B, h, L, L] twice)."""
+    """o = dropout(softmax(q k^T / sqrt(head_dim))) v per head; q, k, v [B, L, E].  Scores never leave the SM; the backward
+    recomputes the probabilities from the saved log-sum-exp -- and, with dropout, the keep mask from the saved seed (reference:
+    cin_attention.py:73-95 materialises [B, h, L, L] scores, probabilities and the dropout mask)."""
 
     @staticmethod
-    def forward(ctx, q, k, v, heads):
+    def forward(ctx, q, k, v, heads, dropout_p=0.0):
         require_cuda(q, "MHSACore")
         q, k, v = _f32c(q), _f32c(k), _f32c(v)
         B, L, E = q.shape
         o = torch.empty_like(q)
         lse = torch.empty((B, heads, L), dtype=torch.float32, device=q.device)
+        seed = None
         with timed("mhsa"):
-            N.check(N.lib().xdfm_mhsa_fwd(N.ptr(q), N.ptr(k), N.ptr(v), B, L, E, heads, N.ptr(o), N.ptr(lse), N.stream_ptr()))
+            if dropout_p > 0.0:
+                st = dropout_state(q.device)
+                seed = st.clone()
+                st.add_(0x9E3779B97F4A7C15 & (2 ** 62 - 1))      # next call: a different stream
+                N.check(N.lib().xdfm_mhsa_fwd_dropout(N.ptr(q), N.ptr(k), N.ptr(v), B, L, E, heads, float(dropout_p), N.ptr(seed), N.ptr(o),
+                                                      N.ptr(lse), N.stream_ptr()))
+            else:
+                N.check(N.lib().xdfm_mhsa_fwd(N.ptr(q), N.ptr(k), N.ptr(v), B, L, E, heads, N.ptr(o), N.ptr(lse), N.stream_ptr()))
         ctx.save_for_backward(q, k, v, o, lse)
-        ctx.heads = heads
+        ctx.heads, ctx.dropout_p, ctx.seed = heads, float(dropout_p), seed
         return o
 
     @staticmethod
@@ -834,9 +867,13 @@ class MHSACore(torch.autograd.Function):
         do = _f32c(do)
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
         with timed("mhsa"):
-            N.check(N.lib().xdfm_mhsa_bwd(N.ptr(q), N.ptr(k), N.ptr(v), N.ptr(o), N.ptr(lse), N.ptr(do), B, L, E, ctx.heads, N.ptr(dq),
-                                          N.ptr(dk), N.ptr(dv), N.stream_ptr()))
-        return dq, dk, dv, None
+            if ctx.dropout_p > 0.0:
+                N.check(N.lib().xdfm_mhsa_bwd_dropout(N.ptr(q), N.ptr(k), N.ptr(v), N.ptr(o), N.ptr(lse), N.ptr(do), B, L, E, ctx.heads,
+                                                      ctx.dropout_p, N.ptr(ctx.seed), N.ptr(dq), N.ptr(dk), N.ptr(dv), N.stream_ptr()))
+            else:
+                N.check(N.lib().xdfm_mhsa_bwd(N.ptr(q), N.ptr(k), N.ptr(v), N.ptr(o), N.ptr(lse), N.ptr(do), B, L, E, ctx.heads, N.ptr(dq),
+                                              N.ptr(dk), N.ptr(dv), N.stream_ptr()))
+        return dq, dk, dv, None, None
 
 
 class AddLayerNorm(torch.autograd.Function):

@@ -17,8 +17,11 @@ class BaseModelSFG(BaseModel):
                  sfg_dropout=0.1, sfg_positive_only=True, sfg_use_label_attention=True):
         super().__init__(linear_feature_columns, dnn_feature_columns, l2_reg_linear=l2_reg_linear,
                          l2_reg_embedding=l2_reg_embedding, init_std=init_std, seed=seed, task=task, device=device, gpus=gpus)
-        if self._all_varlen:
-            raise NotImplementedError("xDeepFMPro: VarLenSparseFeat columns are not wired into the SFG step of this build")
+        if self._all_varlen and use_sfg:
+            # the reference's SFG decoder is sized from the SparseFeat columns only (sfg_decoder.py:52-77) and its forward_with_sfg
+            # fails with a shape error once a pooled sequence embedding joins the list (probed); without SFG the model is fine
+            raise NotImplementedError("xDeepFMPro(use_sfg=True) with VarLenSparseFeat columns: the reference's SFG decoder does not "
+                                      "accept multi-value columns either (its input width ignores them); pass use_sfg=False")
         self.use_sfg, self.sfg_weight, self.sfg_positive_only = use_sfg, sfg_weight, sfg_positive_only
         self.sparse_feature_columns = [fc for fc in dnn_feature_columns if isinstance(fc, SparseFeat)] if dnn_feature_columns else []
         self.dense_feature_columns = [fc for fc in dnn_feature_columns if isinstance(fc, DenseFeat)] if dnn_feature_columns else []
