@@ -124,6 +124,11 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
         if (it + 1 < p.n_iters && tile_of(it + 1) < p.n_tiles) load_x(tile_of(it + 1));
         for (int j = 0; j < p.m; ++j) {
           if (!first_pass) mbar_wait(&bars->w_empty[ws], wphase);
+          if (p.debug & 8) {                      // experiment: no weight stream at all (only the barrier hand-offs remain)
+            mbar_arrive(&bars->w_full[ws]);
+            if (++ws == (uint32_t)p.ns) { ws = 0; wphase ^= 1; first_pass = false; }
+            continue;
+          }
           mbar_arrive_expect_tx(&bars->w_full[ws], w_slot_bytes);
           for (int c = 0; c < p.n_full; ++c) {
             uint8_t* dst = sW + (size_t)ws * full_stride + (size_t)c * w_box_bytes + (size_t)wr0 * 128;
@@ -381,13 +386,13 @@ cin_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
       }
       staged = pipe;
       // ---- tile outputs
-      if (valid) {
+      if (valid && !(p.debug & 16)) {
         float* o = p.dxk + row * p.HpQ + half * HALF;
 #pragma unroll
         for (int i = 0; i < HALF; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(dxk[i], dxk[i + 1], dxk[i + 2], dxk[i + 3]);
       }
       asm volatile("bar.sync 1, %0;" ::"n"(128 * NG) : "memory");     // all groups' dX0 partials are in shared memory
-      if (valid) {
+      if (valid && !(p.debug & 16)) {
         // dx0 row += the groups' partials (summed in group order): 128-bit accesses, all loads of a pass in flight before the first
         // add (the scalar load -> add -> store chain this replaces cost one L2 round trip per field at every tile end); the
         // channel groups split the row's float4s
@@ -770,6 +775,9 @@ static int cin_dx_geom(int m, int Hp, int H, int D, CinDxGeom* g) {
   g->slot = slot;
   int ns = (int)std::min<size_t>((227 * 1024 - fixed) / slot, DX_MAX_NS * 1);
   ns = std::min(ns, DX_MAX_NS);
+  if (const char* e = getenv("XDFM_DEBUG_DX_NS")) {         // profiling experiments only: shallower W'' ring
+    if (atoi(e) >= 2) ns = std::min(ns, atoi(e));
+  }
   if (ns < 2) {
     xdfm_set_error("cin_bwd_dx_tc: shared memory too small");
     return XDFM_ERR_UNSUPPORTED;
