@@ -192,26 +192,29 @@ int xdfm_cin_dy_rows_cols(const void* yt, int64_t B, int D, int H, int Hs, int H
                           const float* dmaps, int fm_total, int col_off, const float* dnext, int64_t dnext_pitch, int n_next, int act,
                           void* dyt, void* dyT, void* stream);
 int xdfm_from_rows_f32(const float* xt, int64_t B, int C, int D, int CP, float* x, int accumulate, void* stream);
+/* x [B, C, D] fp32 = extra[r, c] (NULL = none; row pitch extra_pitch) + the sum of the n_planes planes parts [n_planes, B*D, CP],
+ * r = b * D + d: the CIN's dX^0 in the reference layout from the dX kernels' planes and layer 0's dXk */
+int xdfm_cin_dx0_finish(const float* parts, int n_planes, const float* extra, int64_t extra_pitch, int64_t B, int C, int D, int CP, float* x,
+                        void* stream);
 int xdfm_add_rows_f32(float* a, int64_t pitch_a, const float* b, int64_t pitch_b, int64_t R, int C, void* stream);
 
 /* CIN backward w.r.t. activations on the tensor cores: dyt [B*D, Hs] bf16 (act'(y) * upstream), x0t / xkt as in the forward,
  * wt = bf16 scratch [xdfm_cin_bwd_dx_tc_wt_elems]; dxk [B*D, HpQ] fp32 (overwritten, HpQ = Hp rounded up to 16),
- * dx0 [B*D, mP] fp32 (accumulated +=). */
+ * dx0 [2, B*D, mP] fp32 (overwritten): this layer's dX^0 as two planes, one per half of the X^{k-1} channels; the layers' planes are
+ * summed (and brought back to [B, m, D]) by xdfm_cin_dx0_finish.  (Replaces the dZ / einsum-backward part of torch autograd over
+ * deepctr/layers/interaction.py:218-224.) */
 int64_t xdfm_cin_bwd_dx_tc_wt_elems(int m, int Hp, int H, int D);
-/* diagnostic bit mask for profiling experiments (0 = production): 1 skip the epilogue contraction, 2 skip TMEM loads, 4 skip MMAs */
+/* diagnostic bit mask for profiling experiments (0 = production; cfg2 layer shapes only): 1 skip the contraction FMAs, 2 TMEM loads,
+ * 4 MMAs, 8 the weight stream, 16 tile outputs, 32 dY staging copies, 64 X^{k-1} loads; 256 = clock stamps follow one row warp */
 void xdfm_cin_dx_set_debug(int v);
-/* row warps per TMEM lane quarter in the dX kernel: 2 (default) or 4 (twice the resident warps, half the registers each; measured
- * slower in round 1) */
-void xdfm_cin_dx_set_groups(int v);
 /* experiment switch of xdfm_cin_bwd_dw_tc: 0 = automatic fields per CTA (default), 1 = one field per CTA (deeper A ring in TMEM);
  * call before xdfm_cin_bwd_dw_tc_workspace_bytes / xdfm_cin_bwd_dw_tc of a step (both read it) */
 void xdfm_cin_dw_set_jp(int v);
 /* lane packing of xdfm_cin_bwd_dw_tc for narrow X^{k-1} (HpQ <= 64: 2 or 4 fields share the 128 TMEM lanes of one accumulator):
  * 1 = on (default), 0 = one field per accumulator (A/B tests); same calling rule as xdfm_cin_dw_set_jp */
 void xdfm_cin_dw_set_pack(int enabled);
-/* 1: dX kernel that contracts two 128-row tiles per streamed W'' field when shared memory allows; 0 (default): single-tile kernel
- * (the pair variant halves the weight stream but measured the same time in round 1: profiles/r01_cin_findings.md) */
-void xdfm_cin_dx_set_pair(int v);
+/* profiling only: device buffer of 4 * 64 * 8 int64 clock stamps written by CTA 0 of the following dX launches (NULL = off) */
+void xdfm_cin_dx_set_trace(void* buf);
 int xdfm_cin_bwd_dx_tc(const void* dyt, const void* x0t, const void* xkt, int64_t xk_pitch, const float* W, void* wt, int64_t B, int m,
                        int Hp, int H, int D, float* dxk, float* dx0, void* stream);
 
@@ -365,6 +368,10 @@ int xdfm_shard_pull_segments(const void* const* peer_keys, const void* const* pe
 /* ---- tcgen05 self-test (diagnostic): D[128,N] = A[128,K] * B[N,K]^T, bf16 in / fp32 out, one CTA.
  * mode 0: A via TMA + shared-memory descriptor (SS); mode 1: A stored to TMEM by the threads (TS, the CIN operand path). */
 int xdfm_tc_selftest_gemm(const void* A, const void* Bm, int N, int K, int mode, float* out, void* stream);
+/* profiling only: SM-cycle latencies of the hand-off primitives (idle tcgen05.commit, mbarrier arrive, 13 MMAs + commit, their issue
+ * time, try_wait on a completed phase, tcgen05.ld + wait, round trips by arrive / by commit against one lane and against eight
+ * warps) into out[16] (device int64) */
+int xdfm_tc_latency_probe(long long* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -37,6 +37,22 @@ def test_tcgen05_selftest_gemm_k_tail_in_32_byte_swizzle(N, K):
     assert_close(out, ref, 1e-5, 1e-4, "selftest mode 2")
 
 
+@pytest.mark.parametrize("N,K", [(64, 64), (128, 128), (208, 64), (208, 128), (16, 16), (256, 256), (112, 48)])
+def test_tcgen05_selftest_gemm_mn_major_b(N, K):
+    """Mode 3: B handed over transposed ([K, N] row-major) and read MN-major by the tensor core -- how the weight-gradient kernels
+    consume row-layout activations without a transposed copy."""
+    from deepctr import _native as Nv
+    g = torch.Generator().manual_seed(N + K)
+    A = torch.randn(128, K, generator=g).to(torch.bfloat16).to(DEV)
+    B = torch.randn(N, K, generator=g).to(torch.bfloat16)
+    Bt = B.t().contiguous().to(DEV)
+    out = torch.full((128, N), float("nan"), device=DEV)
+    Nv.check(Nv.lib().xdfm_tc_selftest_gemm(Nv.ptr(A), Nv.ptr(Bt), N, K, 3, Nv.ptr(out), Nv.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = A.float().double().cpu() @ B.float().double().t()
+    assert_close(out, ref, 1e-5, 1e-4, "selftest mode 3")
+
+
 def to_rows(x, CP):
     """[B, C, D] fp32 (device) -> row layout [B*D, CP] bf16 via the library."""
     from deepctr import _native as Nv
@@ -171,6 +187,10 @@ DX_CASES = [
     (2500, 26, 16, 200, 100),     # 313 tiles on 148 CTAs: 2-3 tiles per CTA, the next tile's dY is staged while the current one drains
     (1250, 22, 32, 256, 128),     # same with the widest A tile (16 granules per row warp, 22 fields)
     (5000, 5, 8, 64, 32),         # fewer fields than granules: several tiles per CTA, each staged at its start
+    (2500, 26, 16, 200, 26),      # narrow layer, several tiles per CTA: three fields per MMA group, the last group holds two
+    (1300, 39, 16, 128, 64),      # two fields per group, odd field count
+    (3000, 3, 16, 32, 3),         # fewer fields than a group could hold
+    (2100, 7, 16, 64, 7),         # one group holds every field
 ]
 
 
@@ -195,8 +215,7 @@ def test_cin_tc_backward_dx_matches_emulation(case, cluster):
     wt = torch.empty(L.xdfm_cin_bwd_dx_tc_wt_elems(m, Hp, H, D), dtype=torch.bfloat16, device=DEV)
     HpQ, mP = r16(Hp), r8(m)
     dxk = torch.full((B * D, HpQ), float("nan"), device=DEV)
-    dx0_init = torch.randn(B * D, mP, generator=g)
-    dx0 = dx0_init.to(DEV).clone()
+    dx0 = torch.full((2, B * D, mP), float("nan"), device=DEV)      # two planes (one per channel half), overwritten
     L.xdfm_cin_tc_set_cluster(cluster)
     try:
         Nv.check(L.xdfm_cin_bwd_dx_tc(Nv.ptr(dyt), Nv.ptr(x0t), Nv.ptr(xkt), xkt.shape[1], Nv.ptr(Wd), Nv.ptr(wt), B, m, Hp, H, D,
@@ -209,31 +228,16 @@ def test_cin_tc_backward_dx_matches_emulation(case, cluster):
     ref_dxk = torch.einsum("bijd,bjd->bid", dz, bf(x0))
     ref_dx0 = torch.einsum("bijd,bid->bjd", dz, bf(xk_full[:, :Hp]))
     got_dxk = dxk.view(B, D, HpQ)[:, :, :Hp].permute(0, 2, 1)
-    got_dx0 = (dx0.cpu() - dx0_init).view(B, D, mP)[:, :, :m].permute(0, 2, 1)
+    got_dx0 = dx0.sum(0).cpu().view(B, D, mP)[:, :, :m].permute(0, 2, 1)
+    # the planes and layer-0 rows through xdfm_cin_dx0_finish: the reference layout [B, m, D]
+    fin = torch.full((B, m, D), float("nan"), device=DEV)
+    extra = torch.randn(B * D, HpQ, generator=g).to(DEV)
+    if HpQ >= m:
+        Nv.check(L.xdfm_cin_dx0_finish(Nv.ptr(dx0), 2, Nv.ptr(extra), HpQ, B, m, D, mP, Nv.ptr(fin), Nv.stream_ptr()))
+        want = dx0.sum(0).view(B, D, mP)[:, :, :m].permute(0, 2, 1) + extra.view(B, D, HpQ)[:, :, :m].permute(0, 2, 1)
+        assert_close(fin, want, 1e-6, 1e-6, "dx0 finish")
     assert_close(got_dxk, ref_dxk, 1e-3, 1e-3 * ref_dxk.abs().max().item(), "dxk")
     assert_close(got_dx0, ref_dx0, 1e-3, 1e-3 * ref_dx0.abs().max().item(), "dx0")
-
-
-@pytest.mark.parametrize("case", [(19, 26, 16, 200, 100), (2500, 26, 16, 200, 26), (33, 26, 8, 128, 128), (2500, 12, 16, 40, 20)], ids=str)
-def test_cin_tc_backward_dx_four_row_warps_per_quarter(case):
-    """The dX kernel's optional warp layout with 4 row warps per TMEM lane quarter (the default is 2)."""
-    from deepctr import _native as Nv
-    Nv.lib().xdfm_cin_dx_set_groups(4)
-    try:
-        test_cin_tc_backward_dx_matches_emulation(case, 2)
-    finally:
-        Nv.lib().xdfm_cin_dx_set_groups(2)
-
-
-@pytest.mark.parametrize("case", [(19, 26, 16, 200, 100), (2500, 26, 16, 200, 26), (700, 22, 32, 64, 22)], ids=str)
-def test_cin_tc_backward_dx_tile_pair_kernel_matches(case):
-    """The optional tile-pair dX kernel (xdfm_cin_dx_set_pair(1)): two 128-row tiles per streamed weight field."""
-    from deepctr import _native as Nv
-    Nv.lib().xdfm_cin_dx_set_pair(1)
-    try:
-        test_cin_tc_backward_dx_matches_emulation(case, 2)
-    finally:
-        Nv.lib().xdfm_cin_dx_set_pair(0)
 
 
 def test_cin_dy_rows():

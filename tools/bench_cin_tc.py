@@ -72,12 +72,10 @@ def time_dx(B, m, D, H, Hp, cluster=2, reps=5):
     wt = torch.empty(L.xdfm_cin_bwd_dx_tc_wt_elems(m, Hp, H, D), dtype=torch.bfloat16, device=DEV)
     HpQ = (Hp + 15) // 16 * 16
     dxk = torch.empty(R, HpQ, device=DEV)
-    dx0 = torch.zeros(R, r8(m), device=DEV)
+    dx0 = torch.zeros(2, R, r8(m), device=DEV)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
-    for dbg in (4, 2):
+    for dbg in (0,):
         L.xdfm_cin_dx_set_debug(0)
-        L.xdfm_cin_dx_set_groups(2)
-        L.xdfm_cin_dx_set_groups(dbg)
         ts = []
         for r in range(reps + 2):
             flush.zero_()
@@ -90,9 +88,8 @@ def time_dx(B, m, D, H, Hp, cluster=2, reps=5):
             if r >= 2:
                 ts.append(e0.elapsed_time(e1))
         ms = sorted(ts)[len(ts) // 2]
-        print("dX B=%d m=%d D=%d H=%d Hp=%d %s: %.3f ms  %.1f TFLOP/s" % (B, m, D, H, Hp, "%d row warps per lane quarter" % dbg, ms,
+        print("dX B=%d m=%d D=%d H=%d Hp=%d %s: %.3f ms  %.1f TFLOP/s" % (B, m, D, H, Hp, "", ms,
                                                                          2.0 * R * H * Hp * m / ms / 1e9), flush=True)
-    L.xdfm_cin_dx_set_groups(2)
 
 
 if __name__ == "__main__" and os.environ.get("BENCH_DX"):

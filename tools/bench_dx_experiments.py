@@ -27,7 +27,7 @@ def child():
         wt = torch.empty(L.xdfm_cin_bwd_dx_tc_wt_elems(m, Hp, H, D), dtype=torch.bfloat16, device=DEV)
         HpQ = (Hp + 15) // 16 * 16
         dxk = torch.empty(R, HpQ, device=DEV)
-        dx0 = torch.zeros(R, r8(m), device=DEV)
+        dx0 = torch.zeros(2, R, r8(m), device=DEV)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
         L.xdfm_cin_dx_set_debug(dbg)
         L.xdfm_cin_tc_set_cluster(cl)
@@ -47,6 +47,45 @@ def child():
         print("dX Hp=%d debug=%2d cluster=%d ns<=%s: %.3f ms" % (Hp, dbg, cl, os.environ.get("XDFM_DEBUG_DX_NS", "-"), sorted(ts)[len(ts) // 2]),
               flush=True)
 
+    if os.environ.get("DX_SHAPES"):
+        # cfg2 / cfg4 / cfg5-like layer shapes
+        for (B, m, D, H, Hp) in ((8192, 26, 16, 200, 100), (8192, 26, 16, 200, 26), (8192, 22, 32, 256, 128), (8192, 22, 32, 256, 22),
+                                 (4096, 26, 64, 200, 100), (4096, 26, 64, 200, 26), (8192, 39, 16, 128, 64), (8192, 10, 16, 96, 48)):
+            print("B=%d m=%d D=%d H=%d" % (B, m, D, H), end=" ")
+            run_dx(B, m, D, H, Hp, 0, 2)
+        return
+    if os.environ.get("DX_TRACE"):
+        # clock stamps of CTA 0's hand-offs: where does a field's round trip go?
+        tr = torch.zeros(4 * 64 * 8, dtype=torch.int64, device=DEV)
+        for Hp, dbg in ((100, 0), (100, 256), (100, 127), (100, 127 + 256), (26, 0)):
+            tr.zero_()
+            L.xdfm_cin_dx_set_trace(Nv.ptr(tr))
+            run_dx(8192, 26, 16, 200, Hp, dbg, int(os.environ.get("DX_CLUSTER", "2")), reps=1)
+            L.xdfm_cin_dx_set_trace(None)
+            t = tr.cpu().view(4, 64, 8)
+            t0 = int(t[0, 0, 0])
+            print("Hp=%d debug=%d: rows = tile.group; columns = mma:acc_empty mma:w_full mma:committed row:acc_full row:arrived row:consumed "
+                  "tma:w_empty row11:arrived (cycles since the first stamp)" % (Hp, dbg))
+            for it in range(2):
+                for g in range(26):
+                    if int(t[it, g, 2]) == 0 or (it == 1 and g > 3) or (it == 0 and 5 < g < 14):
+                        continue
+                    print("%d.%02d " % (it, g) + " ".join("%7d" % (int(v) - t0 if int(v) else -1) for v in t[it, g]))
+        return
+    if os.environ.get("DX_SKEL"):
+        # which part of the skeleton of the version-2 kernel costs what (wide and narrow cfg2 layers)
+        for Hp in (100, 26):
+            for dbg in (0, 7, 7 + 8, 7 + 16, 7 + 32, 7 + 64, 7 + 8 + 16 + 32 + 64, 8, 16, 32, 64):
+                run_dx(8192, 26, 16, 200, Hp, dbg, int(os.environ.get("DX_CLUSTER", "2")))
+        for m in (6, 13, 26, 52):
+            for dbg in (0, 7, 127):
+                print("m=%d" % m, end=" ")
+                run_dx(8192, m, 16, 200, 100, dbg, 2)
+        for B in (1184, 8192, 16384):
+            for dbg in (0, 7, 127):
+                print("B=%d" % B, end=" ")
+                run_dx(B, 26, 16, 200, 100, dbg, 2)
+        return
     if os.environ.get("DX_FIELDS"):
         # per-tile fixed cost vs per-field cost: same rows, different field counts
         for m in (6, 13, 26, 52):
@@ -71,7 +110,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         child()
     else:
-        for ns in ("", "2", "3"):
+        for ns in (("",) if os.environ.get("DX_SHAPES") else ("",) if os.environ.get("DX_TRACE") else ("", "2") if os.environ.get("DX_SKEL") else ("", "2", "3")):
             env = dict(os.environ)
             if ns:
                 env["XDFM_DEBUG_DX_NS"] = ns

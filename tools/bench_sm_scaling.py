@@ -30,7 +30,7 @@ def child():
         wt = torch.empty(L.xdfm_cin_bwd_dx_tc_wt_elems(m, Hp, H, D), dtype=torch.bfloat16, device=DEV)
         HpQ = (Hp + 15) // 16 * 16
         dxk = torch.empty(R, HpQ, device=DEV)
-        dx0 = torch.zeros(R, r8(m), device=DEV)
+        dx0 = torch.zeros(2, R, r8(m), device=DEV)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
         L.xdfm_cin_dx_set_debug(dbg)
         L.xdfm_cin_tc_set_cluster(cl)

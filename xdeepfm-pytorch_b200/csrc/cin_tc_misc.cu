@@ -97,6 +97,54 @@ extern "C" int xdfm_add_rows_f32(float* a, int64_t pitch_a, const float* b, int6
   return XDFM_OK;
 }
 
+// dX0 of the whole CIN in the reference layout: x[b, c, d] = extra[r, c] + sum over the n_planes planes of parts[plane][r, c],
+// r = b * D + d.  parts = the dX kernels' per-layer, per-channel-half dX0 planes ([n_planes, R, CP] fp32, summed in plane order:
+// deterministic); extra = layer 0's dXk rows (X^{k-1} is X^0 itself there), pitch extra_pitch.  One block per sample-group keeps
+// both the row-layout reads and the [B, C, D] writes coalesced through a shared-memory transpose.
+__global__ void __launch_bounds__(256) cin_dx0_finish_kernel(const float* __restrict__ parts, int n_planes, const float* __restrict__ extra,
+                                                             int64_t extra_pitch, int64_t B, int C, int D, int CP, float* __restrict__ x) {
+  extern __shared__ float sh[];                        // [rows_per_block][CP + 1]
+  const int64_t R = B * (int64_t)D;
+  const int spb = max(1, 256 / D);                     // samples per block pass
+  const int rows = spb * D;
+  const int pitch = CP + 1;
+  for (int64_t b0 = (int64_t)blockIdx.x * spb; b0 < B; b0 += (int64_t)gridDim.x * spb) {
+    const int64_t r0 = b0 * D;
+    const int nrows = (int)min((int64_t)rows, R - r0);
+    for (int e = threadIdx.x; e < nrows * CP; e += blockDim.x) {
+      const int rr = e / CP, c = e - rr * CP;
+      float v = 0.f;
+      if (c < C) {
+        v = extra != nullptr ? extra[(r0 + rr) * extra_pitch + c] : 0.f;
+        for (int pl = 0; pl < n_planes; ++pl) v += parts[((int64_t)pl * R + r0 + rr) * CP + c];
+      }
+      sh[rr * pitch + c] = v;
+    }
+    __syncthreads();
+    const int nsamp = nrows / D;
+    for (int e = threadIdx.x; e < nsamp * C * D; e += blockDim.x) {
+      const int d = e % D;
+      const int sc = e / D;
+      const int c = sc % C, sidx = sc / C;
+      x[((b0 + sidx) * C + c) * (int64_t)D + d] = sh[(sidx * D + d) * pitch + c];
+    }
+    __syncthreads();
+  }
+}
+
+extern "C" int xdfm_cin_dx0_finish(const float* parts, int n_planes, const float* extra, int64_t extra_pitch, int64_t B, int C, int D, int CP,
+                                   float* x, void* stream) {
+  XDFM_CHECK_ARG(D >= 1 && D <= 256 && CP >= C && n_planes >= 0, "cin_dx0_finish: bad shape D=%d C=%d CP=%d planes=%d", D, C, CP, n_planes);
+  if (B == 0) return XDFM_OK;
+  const int spb = std::max(1, 256 / D);
+  const size_t sm = (size_t)spb * D * (CP + 1) * sizeof(float);
+  int blocks = (int)std::min<int64_t>((int64_t)xdfm_num_sms() * 8, ceil_div64(B, spb));
+  if (sm > 48 * 1024) XDFM_CUDA(cudaFuncSetAttribute(cin_dx0_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  cin_dx0_finish_kernel<<<blocks, 256, sm, (cudaStream_t)stream>>>(parts, n_planes, extra, extra_pitch, B, C, D, CP, x);
+  XDFM_LAUNCH_CHECK();
+  return XDFM_OK;
+}
+
 // Fused form of cin_dy_rows + rows_to_cols: one pass over y / upstream gradients produces dY in BOTH layouts the backward needs --
 // row layout dyt [R, Hs] (A operand of the dX kernel) and channel-major dyT [H_pad, R] (B operand of the dW kernel) -- through a
 // 64 x 64 shared-memory tile.  Channels >= H are written as zeros in both.

@@ -153,6 +153,20 @@ __device__ __forceinline__ uint64_t make_desc_k_sw32(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major operand tile (the MN index is the contiguous one): [K rows x 64 elements] SWIZZLE_128B boxes as TMA writes them from a
+// row-major [K, MN] matrix; 8 K-rows = 1024 B (stride byte offset), the next 64 MN elements `chunk_stride` bytes further (leading
+// byte offset).  One UMMA_K step of bf16 (16 K-rows) advances the start address by 2048 B.  (cute make_umma_desc<Major::MN>, B128:
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units.)  Needs a_major / b_major = 1 in the instruction descriptor.
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t chunk_stride) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);          // start address
+  d |= (uint64_t)((chunk_stride >> 4) & 0x3FFF) << 16; // leading byte offset: next 64-element chunk along MN
+  d |= (uint64_t)(1024 >> 4) << 32;                    // stride byte offset: next 8 rows along K
+  d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                              // layout type SWIZZLE_128B
+  return d;
+}
+
 // tcgen05.st 32x32b: thread (lane l of warp w) writes N consecutive 32-bit columns of TMEM lane 32*(w%4)+l
 __device__ __forceinline__ void tmem_st_x4(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3])

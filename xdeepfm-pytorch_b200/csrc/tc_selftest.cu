@@ -1,6 +1,9 @@
 // Minimal tcgen05 self-test: one CTA computes D[128, N] = A[128, K] * B[N, K]^T (bf16 in, fp32 out) with
 //   mode 0: A from shared memory (TMA, SWIZZLE_128B, K-major)        -- tcgen05.mma  SS
 //   mode 1: A written into TMEM by the threads (tcgen05.st, packed)  -- tcgen05.mma  TS
+//   mode 2: as 1, K tail of B in SWIZZLE_32B boxes
+//   mode 3: as 1, B given TRANSPOSED ([K, N] row-major, N contiguous) and consumed MN-major: [K rows x 64 columns] SWIZZLE_128B
+//           boxes, descriptor LBO = box stride, SBO = 8 K-rows (the layout the dW kernels read row-major activations in)
 // It exercises exactly the primitives the CIN kernels are built from (TMEM alloc, TMA swizzle vs. UMMA descriptor,
 // A-in-TMEM layout, commit/mbarrier, tcgen05.ld) so that a descriptor/layout mistake shows up in a 40-line kernel.
 #include "tc_common.cuh"
@@ -57,9 +60,9 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const __grid_constant_
   __shared__ uint64_t bar_tma, bar_mma;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nchunk = K / 64;
-  const int ntail = (K % 64) / 16;                     // mode 2 only: 16-wide K steps past the last full chunk, SWIZZLE_32B boxes
-  uint8_t* sB = smem;                                  // nchunk x [N rows x 128 B]
+  const int nchunk = mode == 3 ? (N + 63) / 64 : K / 64;      // mode 3: chunks run along N
+  const int ntail = mode == 3 ? 0 : (K % 64) / 16;                     // mode 2 only: 16-wide K steps past the last full chunk, SWIZZLE_32B boxes
+  uint8_t* sB = smem;                                  // nchunk x [N rows x 128 B]   (mode 3: nchunk x [K rows x 128 B])
   uint8_t* sBt = smem + (size_t)nchunk * N * 128;      // ntail x [N rows x 32 B]
   uint8_t* sA = sBt + (size_t)ntail * N * 32;          // nchunk x [128 rows x 128 B]  (mode 0)
   sA = (uint8_t*)(((uintptr_t)sA + 1023) & ~(uintptr_t)1023);
@@ -76,8 +79,10 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const __grid_constant_
   const uint32_t acc_col = 0, a_col = 256;
   if (tid == 0) {
     uint32_t bytes = (uint32_t)nchunk * N * 128 + (uint32_t)ntail * N * 32 + (mode == 0 ? (uint32_t)nchunk * 128 * 128 : 0u);
+    if (mode == 3) bytes = (uint32_t)nchunk * K * 128;
     mbar_arrive_expect_tx(&bar_tma, bytes);
-    for (int c = 0; c < nchunk; ++c) {
+    for (int c = 0; c < nchunk && mode == 3; ++c) tma_load_2d(sB + (size_t)c * K * 128, &tmB, c * 64, 0, &bar_tma);
+    for (int c = 0; c < nchunk && mode != 3; ++c) {
       tma_load_2d(sB + (size_t)c * N * 128, &tmB, c * 64, 0, &bar_tma);
       if (mode == 0) tma_load_2d(sA + (size_t)c * 128 * 128, &tmA, c * 64, 0, &bar_tma);
     }
@@ -102,8 +107,10 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const __grid_constant_
   if (tid == 0) {
     mbar_wait(&bar_tma, 0);
     fence_after_sync();
-    const uint32_t idesc = make_idesc_bf16(128, N);
-    for (int ks = 0; ks < K / 16; ++ks) {
+    const uint32_t idesc = make_idesc_bf16(128, N, 0, mode == 3 ? 1 : 0);
+    for (int ks = 0; ks < K / 16 && mode == 3; ++ks)
+      umma_ts(tmem_base + acc_col, tmem_base + a_col + ks * 8, make_desc_mn_sw128(smem_u32(sB) + ks * 2048, (uint32_t)K * 128), idesc, ks > 0);
+    for (int ks = 0; ks < K / 16 && mode != 3; ++ks) {
       int c = ks / 4, o = (ks % 4) * 32;
       uint64_t bdesc = c < nchunk ? make_desc_k_sw128(smem_u32(sB + (size_t)c * N * 128) + o)
                                   : make_desc_k_sw32(smem_u32(sBt + (size_t)(ks - nchunk * 4) * N * 32));
@@ -138,8 +145,19 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const __grid_constant_
 // A [128, K] bf16 row-major, Bm [N, K] bf16 row-major (both device), out [128, N] fp32; N % 16 == 0, N <= 256, K <= 256;
 // modes 0 / 1: K % 64 == 0; mode 2 (A in TMEM, K tail of B in SWIZZLE_32B boxes): K % 16 == 0
 extern "C" int xdfm_tc_selftest_gemm(const void* A, const void* Bm, int N, int K, int mode, float* out, void* stream) {
-  XDFM_CHECK_ARG(N % 16 == 0 && N >= 16 && N <= 256 && K >= 16 && K <= 256 && (mode == 2 ? K % 16 == 0 : (K % 64 == 0)),
+  XDFM_CHECK_ARG(N % 16 == 0 && N >= 16 && N <= 256 && K >= 16 && K <= 256 && (mode >= 2 ? K % 16 == 0 : (K % 64 == 0)),
                  "tc_selftest: bad N=%d K=%d mode=%d", N, K, mode);
+  if (mode == 3) {
+    // Bm is [K, N] row-major (row pitch N elements, N % 8 == 0): boxes of [K rows x 64 columns], columns past N read as zeros
+    CUtensorMap tmT;
+    int rc3 = xdfm_make_tmap_bf16(&tmT, Bm, (uint64_t)K, (uint64_t)N, (uint64_t)N * 2, (uint32_t)K, 64, 1);
+    if (rc3) return rc3;
+    size_t sm3 = (size_t)((N + 63) / 64) * K * 128 + 2048;
+    XDFM_CUDA(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+    tc_selftest_kernel<<<1, 128, sm3, (cudaStream_t)stream>>>(tmT, tmT, tmT, (const __nv_bfloat16*)A, N, K, mode, out);
+    XDFM_LAUNCH_CHECK();
+    return XDFM_OK;
+  }
   CUtensorMap tmA, tmB, tmBt;
   int rc = xdfm_make_tmap_bf16_sw128(&tmA, A, 128, K, (uint64_t)K * 2, 128);
   if (rc) return rc;
@@ -150,6 +168,138 @@ extern "C" int xdfm_tc_selftest_gemm(const void* A, const void* Bm, int N, int K
   size_t sm = (size_t)(K / 64) * N * 128 + (size_t)((K % 64) / 16) * N * 32 + (size_t)(K / 64) * 128 * 128 + 2048;
   XDFM_CUDA(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   tc_selftest_kernel<<<1, 128, sm, (cudaStream_t)stream>>>(tmA, tmB, tmBt, (const __nv_bfloat16*)A, N, K, mode, out);
+  XDFM_LAUNCH_CHECK();
+  return XDFM_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Latency probe (profiling only): how long do the hand-off primitives of the CIN kernels take on this chip?  One CTA, 320 threads:
+// thread 0 issues, warps 2..9 are the "other side".  out[i] in SM cycles (clock64):
+//   0  tcgen05.commit with nothing in flight -> own mbarrier wait returns
+//   1  mbarrier.arrive (own thread) -> own wait returns
+//   2  13 x tcgen05.mma (M128 N112 K16, TS) + commit -> wait returns
+//   3  the same 13 MMAs, issue only (time the issuing thread is held)
+//   4  try_wait on an already completed phase
+//   5  tcgen05.ld 32x32b.x16 + wait::ld
+//   6  round trip: thread 0 arrives on A, lane 0 of warp 2 waits on A and arrives on B, thread 0 waits on B
+//   7  the same with tcgen05.commit on thread 0's side
+//   8  the same with TWO commits per trip (the second barrier is the one waited on)
+//   9  round trip by arrive against EIGHT full warps (all 256 lanes wait on A, lane 0 of each arrives on B, count 8)
+//  10  the same by commit
+//  11  the same by two commits, the whole of warp 0 (32 lanes) waiting on B like the MMA warp does
+//  12  as 11 plus the eight warps run tcgen05.fence / wait::ld / __syncwarp / a shared-memory store around the arrive (the skeleton of
+//      the dX row warps)
+__global__ void __launch_bounds__(320) tc_latency_probe_kernel(long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar[4 + 3 * 7];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float scratch[320];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 112 * 128 / 4; i += 320) reinterpret_cast<uint32_t*>(smem)[i] = 0u;       // one SWIZZLE_128B B chunk of zeros
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1);
+    for (int md = 0; md < 7; ++md) {
+      mbar_init(&bar[4 + 3 * md], 1);
+      mbar_init(&bar[5 + 3 * md], md >= 3 ? 8 : 1);
+      mbar_init(&bar[6 + 3 * md], 1);
+    }
+    fence_barrier_init();
+  }
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tb = tmem_base_s;
+  const int REPS = 16;
+  if (tid == 0) {
+    uint32_t ph = 0;
+    long long t0, acc;
+    acc = 0;
+    for (int r = 0; r < REPS; ++r) { t0 = clock64(); umma_commit(&bar[0]); mbar_wait(&bar[0], ph); acc += clock64() - t0; ph ^= 1; }
+    out[0] = acc / REPS;
+    acc = 0;
+    for (int r = 0; r < REPS; ++r) { t0 = clock64(); mbar_arrive(&bar[0]); mbar_wait(&bar[0], ph); acc += clock64() - t0; ph ^= 1; }
+    out[1] = acc / REPS;
+    const uint32_t idesc = make_idesc_bf16(128, 112);
+    const uint64_t bdesc = make_desc_k_sw128(smem_u32(smem));
+    long long acc_issue = 0;
+    acc = 0;
+    for (int r = 0; r < REPS; ++r) {
+      t0 = clock64();
+      for (int ks = 0; ks < 13; ++ks) umma_ts(tb + 256, tb + (ks & 3) * 8, bdesc + (uint64_t)((ks & 3) * 2), idesc, ks > 0);
+      long long t1 = clock64();
+      umma_commit(&bar[0]);
+      mbar_wait(&bar[0], ph);
+      acc += clock64() - t0;
+      acc_issue += t1 - t0;
+      ph ^= 1;
+    }
+    out[2] = acc / REPS;
+    out[3] = acc_issue / REPS;
+    acc = 0;
+    for (int r = 0; r < REPS; ++r) { t0 = clock64(); mbar_wait(&bar[0], ph ^ 1); acc += clock64() - t0; }
+    out[4] = acc / REPS;
+  }
+  __syncwarp();
+  if (warp == 0) {
+    long long t0 = clock64();
+    uint32_t v[16];
+    for (int r = 0; r < REPS; ++r) {
+      tmem_ld_x16(tb + 256, v);
+      tmem_wait_ld();
+      asm volatile("" ::"r"(v[0]), "r"(v[15]));
+    }
+    if (tid == 0) out[5] = (clock64() - t0) / REPS;
+  }
+  __syncthreads();
+  // round trips: thread 0 (or the whole of warp 0) against one lane / eight warps
+  for (int mode = 0; mode < 7; ++mode) {
+    const bool many = mode >= 3;                 // eight full warps answer
+    const int ncommit = (mode == 1 || mode == 4) ? 1 : ((mode == 2 || mode >= 5) ? 2 : 0);
+    const bool warp0_waits = mode >= 5;
+    const bool dress = mode == 6;
+    uint64_t* bA = &bar[4 + 3 * mode];
+    uint64_t* bB = &bar[5 + 3 * mode];
+    uint64_t* bC = &bar[6 + 3 * mode];
+    __syncthreads();
+    if (warp == 0) {
+      long long t0 = clock64();
+      for (int r = 0; r < REPS; ++r) {
+        if (tid == 0) {
+          if (ncommit == 0) mbar_arrive(bA);
+          if (ncommit == 2) umma_commit(bC);
+          if (ncommit >= 1) umma_commit(bA);
+        }
+        __syncwarp();
+        if (warp0_waits || tid == 0) mbar_wait(bB, r & 1);
+        if (warp0_waits) fence_after_sync();
+        __syncwarp();
+      }
+      if (tid == 0) out[6 + mode] = (clock64() - t0) / REPS;
+    } else if (warp >= 2 && (many || (warp == 2 && lane == 0))) {
+      for (int r = 0; r < REPS; ++r) {
+        mbar_wait(bA, r & 1);
+        if (dress) {
+          fence_after_sync();
+          tmem_wait_ld();
+          scratch[tid] = (float)r;
+          fence_before_sync();
+        }
+        if (many) __syncwarp();
+        if (lane == 0) mbar_arrive(bB);
+      }
+    }
+  }
+  __syncthreads();
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
+extern "C" int xdfm_tc_latency_probe(long long* out, void* stream) {
+  tc_latency_probe_kernel<<<1, 320, 112 * 128, (cudaStream_t)stream>>>(out);
   XDFM_LAUNCH_CHECK();
   return XDFM_OK;
 }

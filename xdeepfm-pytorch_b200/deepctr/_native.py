@@ -66,6 +66,7 @@ _SIGS = {
     "xdfm_cin_bwd_dw_tc_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int, c_int]),
     "xdfm_cin_bwd_dw_tc": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, c_int64, _P]),
     "xdfm_tc_selftest_gemm": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
+    "xdfm_tc_latency_probe": (c_int, [_P, _P]),
     "xdfm_ipc_alloc": (c_int, [c_int64, POINTER(_P)]),
     "xdfm_ipc_free": (c_int, [_P]),
     "xdfm_ipc_export": (c_int, [_P, _P]),
@@ -108,10 +109,10 @@ _SIGS = {
     "xdfm_cvt_bf16": (c_int, [_P, c_int, c_int, c_int64, c_int, _P, c_int64, _P]),
     "xdfm_set_rows_opt_dense_version": (None, [c_int]),
     "xdfm_cin_dx_set_debug": (None, [c_int]),
-    "xdfm_cin_dx_set_groups": (None, [c_int]),
     "xdfm_cin_dw_set_jp": (None, [c_int]),
     "xdfm_cin_dw_set_pack": (None, [c_int]),
-    "xdfm_cin_dx_set_pair": (None, [c_int]),
+    "xdfm_cin_dx0_finish": (c_int, [_P, c_int, _P, c_int64, c_int64, c_int, c_int, c_int, _P, _P]),
+    "xdfm_cin_dx_set_trace": (None, [_P]),
     "xdfm_opt_tick_hist": (c_int, [_P, POINTER(OptCfg), _P, c_int64, c_int64, _P]),
     "xdfm_rows_catchup": (c_int, [POINTER(OptCfg), _P, _P, c_int64, POINTER(_P), POINTER(_P), POINTER(_P), _P, POINTER(c_int64), c_int, c_int,
                                   _P, _P, c_int64, _P, _P]),

@@ -475,7 +475,8 @@ class CINFunctionTC(torch.autograd.Function):
         x0T = torch.empty((mP, R), dtype=torch.bfloat16, device=dev)
         with timed("cin_layout"):
             N.check(L.xdfm_rows_to_cols_bf16(N.ptr(x0t), mP, R, m, mP, N.ptr(x0T), st))
-        dx0_rows = torch.zeros((R, mP), dtype=torch.float32, device=dev)
+        n_layers = len(cfg.layer_size)
+        dx0_parts = torch.empty((n_layers, 2, R, mP), dtype=torch.float32, device=dev)   # per layer: one dX0 plane per channel half
         grads = [None] * len(wb)
         dnext, dnext_pitch = None, 0
         for k in range(len(cfg.layer_size) - 1, -1, -1):
@@ -508,14 +509,14 @@ class CINFunctionTC(torch.autograd.Function):
             dxk = torch.empty((R, HpQ), dtype=torch.float32, device=dev)
             with timed("cin_bwd"):
                 N.check(L.xdfm_cin_bwd_dx_tc(N.ptr(dyt), N.ptr(x0t), N.ptr(xkt), xkt.shape[1], N.ptr(W), N.ptr(wt), B, m, Hp, H, D,
-                                             N.ptr(dxk), N.ptr(dx0_rows), st))
+                                             N.ptr(dxk), N.ptr(dx0_parts[k]), st))
             grads[2 * k] = dW.view(wb[2 * k].shape)
             grads[2 * k + 1] = db
             dnext, dnext_pitch = dxk, HpQ
         dx0 = torch.empty((B, m, D), dtype=torch.float32, device=dev)
         with timed("cin_layout"):
-            N.check(L.xdfm_add_rows_f32(N.ptr(dx0_rows), mP, N.ptr(dnext), dnext_pitch, R, m, st))   # layer 0: X^{k-1} is X^0 itself
-            N.check(L.xdfm_from_rows_f32(N.ptr(dx0_rows), B, m, D, mP, N.ptr(dx0), 0, st))
+            # every layer's planes + layer 0's dXk (X^{k-1} is X^0 itself there), back in the reference layout
+            N.check(L.xdfm_cin_dx0_finish(N.ptr(dx0_parts), 2 * n_layers, N.ptr(dnext), dnext_pitch, B, m, D, mP, N.ptr(dx0), st))
         return (None, dx0) + tuple(grads)
 
 
