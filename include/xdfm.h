@@ -213,7 +213,7 @@ void xdfm_cin_dw_set_jp(int v);
 /* lane packing of xdfm_cin_bwd_dw_tc for narrow X^{k-1} (HpQ <= 64: 2 or 4 fields share the 128 TMEM lanes of one accumulator):
  * 1 = on (default), 0 = one field per accumulator (A/B tests); same calling rule as xdfm_cin_dw_set_jp */
 void xdfm_cin_dw_set_pack(int enabled);
-/* profiling only: device buffer of 4 * 64 * 8 int64 clock stamps written by CTA 0 of the following dX launches (NULL = off) */
+/* profiling only: device buffer of 2 * 32 * 16 int64 clock stamps written by CTA 0 of the following dX launches (NULL = off) */
 void xdfm_cin_dx_set_trace(void* buf);
 int xdfm_cin_bwd_dx_tc(const void* dyt, const void* x0t, const void* xkt, int64_t xk_pitch, const float* W, void* wt, int64_t B, int m,
                        int Hp, int H, int D, float* dxk, float* dx0, void* stream);
@@ -371,7 +371,7 @@ int xdfm_tc_selftest_gemm(const void* A, const void* Bm, int N, int K, int mode,
 /* profiling only: SM-cycle latencies of the hand-off primitives (idle tcgen05.commit, mbarrier arrive, 13 MMAs + commit, their issue
  * time, try_wait on a completed phase, tcgen05.ld + wait, round trips by arrive / by commit against one lane and against eight
  * warps) into out[16] (device int64) */
-int xdfm_tc_latency_probe(long long* out, void* stream);
+int xdfm_tc_latency_probe(long long* out, int setmaxnreg, void* stream);
 
 #ifdef __cplusplus
 }

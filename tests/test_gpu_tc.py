@@ -232,7 +232,7 @@ def test_cin_tc_backward_dx_matches_emulation(case, cluster):
     # the planes and layer-0 rows through xdfm_cin_dx0_finish: the reference layout [B, m, D]
     fin = torch.full((B, m, D), float("nan"), device=DEV)
     extra = torch.randn(B * D, HpQ, generator=g).to(DEV)
-    if HpQ >= m:
+    if HpQ >= mP:
         Nv.check(L.xdfm_cin_dx0_finish(Nv.ptr(dx0), 2, Nv.ptr(extra), HpQ, B, m, D, mP, Nv.ptr(fin), Nv.stream_ptr()))
         want = dx0.sum(0).view(B, D, mP)[:, :, :m].permute(0, 2, 1) + extra.view(B, D, HpQ)[:, :, :m].permute(0, 2, 1)
         assert_close(fin, want, 1e-6, 1e-6, "dx0 finish")

@@ -47,30 +47,35 @@ def child():
         print("dX Hp=%d debug=%2d cluster=%d ns<=%s: %.3f ms" % (Hp, dbg, cl, os.environ.get("XDFM_DEBUG_DX_NS", "-"), sorted(ts)[len(ts) // 2]),
               flush=True)
 
+    if os.environ.get("DX_PACE"):
+        for dbg in (1024, 1024 + 2048, 1024 + 4096):
+            run_dx(8192, 26, 16, 200, 100, dbg, 2)
+            run_dx(8192, 26, 16, 200, 26, dbg, 2)
+        return
     if os.environ.get("DX_SHAPES"):
         # cfg2 / cfg4 / cfg5-like layer shapes
         for (B, m, D, H, Hp) in ((8192, 26, 16, 200, 100), (8192, 26, 16, 200, 26), (8192, 22, 32, 256, 128), (8192, 22, 32, 256, 22),
                                  (4096, 26, 64, 200, 100), (4096, 26, 64, 200, 26), (8192, 39, 16, 128, 64), (8192, 10, 16, 96, 48)):
             print("B=%d m=%d D=%d H=%d" % (B, m, D, H), end=" ")
-            run_dx(B, m, D, H, Hp, 0, 2)
+            run_dx(B, m, D, H, Hp, 0, int(os.environ.get("DX_CLUSTER", "2")))
         return
     if os.environ.get("DX_TRACE"):
         # clock stamps of CTA 0's hand-offs: where does a field's round trip go?
-        tr = torch.zeros(4 * 64 * 8, dtype=torch.int64, device=DEV)
-        for Hp, dbg in ((100, 0), (100, 256), (100, 127), (100, 127 + 256), (26, 0)):
+        tr = torch.zeros(2 * 32 * 16, dtype=torch.int64, device=DEV)
+        for Hp, dbg in ((100, 1024), (100, 1024 + 3), (100, 1024 + 3 + 8), (100, 1024 + 8), (100, 1024 + 16 + 64)):
             tr.zero_()
             L.xdfm_cin_dx_set_trace(Nv.ptr(tr))
             run_dx(8192, 26, 16, 200, Hp, dbg, int(os.environ.get("DX_CLUSTER", "2")), reps=1)
             L.xdfm_cin_dx_set_trace(None)
-            t = tr.cpu().view(4, 64, 8)
+            t = tr.cpu().view(2, 32, 16)
             t0 = int(t[0, 0, 0])
-            print("Hp=%d debug=%d: rows = tile.group; columns = mma:acc_empty mma:w_full mma:committed row:acc_full row:arrived row:consumed "
-                  "tma:w_empty row11:arrived (cycles since the first stamp)" % (Hp, dbg))
+            print("Hp=%d debug=%d: rows = tile.group; columns = mma:acc_empty mma:w_full mma:committed tma:w_empty row4:acc_full | "
+                  "arrive of row warps 4..11 (cycles since the first stamp)" % (Hp, dbg))
             for it in range(2):
                 for g in range(26):
-                    if int(t[it, g, 2]) == 0 or (it == 1 and g > 3) or (it == 0 and 5 < g < 14):
+                    if int(t[it, g, 2]) == 0 or (it == 1 and g > 1) or (it == 0 and (g < 16 or g > 22)):
                         continue
-                    print("%d.%02d " % (it, g) + " ".join("%7d" % (int(v) - t0 if int(v) else -1) for v in t[it, g]))
+                    print("%d.%02d " % (it, g) + " ".join("%7d" % ((int(v) - t0) % (1 << 32) if int(v) else -1) for v in t[it, g]))
         return
     if os.environ.get("DX_SKEL"):
         # which part of the skeleton of the version-2 kernel costs what (wide and narrow cfg2 layers)
@@ -110,7 +115,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         child()
     else:
-        for ns in (("",) if os.environ.get("DX_SHAPES") else ("",) if os.environ.get("DX_TRACE") else ("", "2") if os.environ.get("DX_SKEL") else ("", "2", "3")):
+        for ns in (("",) if os.environ.get("DX_SHAPES") or os.environ.get("DX_PACE") else ("",) if os.environ.get("DX_TRACE") else ("", "2") if os.environ.get("DX_SKEL") else ("", "2", "3")):
             env = dict(os.environ)
             if ns:
                 env["XDFM_DEBUG_DX_NS"] = ns

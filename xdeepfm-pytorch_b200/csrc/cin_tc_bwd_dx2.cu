@@ -22,8 +22,8 @@
 //   * narrow layers (HpQ <= 64) contract FPG = 128 / HpQ consecutive fields with ONE MMA group (N = FPG * HpQ, the weight rows of
 //     consecutive fields are consecutive rows of W'') and one barrier hand-off instead of one per field.
 //
-// Warps (384 threads): 0 = W'' stream (TMA, multicast across the cluster), 1 = MMA issuer + TMEM alloc, 2 = per-tile loads (X^0 rows,
-// dY boxes), 3 = idle, 4..11 = row warps (TMEM lane quarter = warp & 3, channel half = (warp - 4) >> 2).
+// Warps (384 threads): 0 = W'' stream (TMA, multicast across the cluster), 1 and 3 = MMA issuers (field groups in turn; 1 also
+// allocates TMEM), 2 = per-tile loads (X^0 rows, dY boxes), 4..11 = row warps (TMEM lane quarter = warp & 3, channel half = (warp - 4) >> 2).
 // TMEM columns: [0,128) / [128,256) dY of the current / next tile (A operand, TS-mode MMA), [256,384) / [384,512) two accumulators.
 #include "tc_common.cuh"
 #include "../../include/xdfm.h"
@@ -59,16 +59,25 @@ __device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
   return d;
 }
 
-#define DX2_TRACE_TILES 4
-#define DX2_TRACE_GROUPS 64
+#define DX2_TRACE_TILES 2
+#define DX2_TRACE_GROUPS 32
+// stamps go to shared memory (a global store per stamp slows the stamping warp by several hundred cycles per field and the
+// whole hand-off chain follows the slowest warp); CTA 0 copies them out at the end
+__device__ __forceinline__ void dx2_stamp_s(uint32_t* strace, const CinDxParams& p, int it, int g, int ev) {
+  if (p.trace != nullptr && it < DX2_TRACE_TILES && g < DX2_TRACE_GROUPS) {
+    uint32_t c;
+    asm volatile("mov.u32 %0, %%clock;" : "=r"(c));
+    strace[(it * DX2_TRACE_GROUPS + g) * 16 + ev] = c;
+  }
+}
 __device__ __forceinline__ void dx2_stamp(const CinDxParams& p, int it, int g, int ev) {
   if (p.trace != nullptr && !(p.debug & 256) && blockIdx.x == 0 && it < DX2_TRACE_TILES && g < DX2_TRACE_GROUPS)
-    p.trace[((size_t)it * DX2_TRACE_GROUPS + g) * 8 + ev] = clock64();
+    p.trace[((size_t)it * DX2_TRACE_GROUPS + g) * 16 + ev] = clock64();
 }
 // debug bit 256: the eight stamps follow ONE row warp (warp 4) through a field (NBF == 2 shapes) instead of the hand-offs
 __device__ __forceinline__ void dx2_stamp_row(const CinDxParams& p, int it, int j, int ev) {
   if (p.trace != nullptr && (p.debug & 256) && blockIdx.x == 0 && threadIdx.x == 128 && it < DX2_TRACE_TILES && j < DX2_TRACE_GROUPS)
-    p.trace[((size_t)it * DX2_TRACE_GROUPS + j) * 8 + ev] = clock64();
+    p.trace[((size_t)it * DX2_TRACE_GROUPS + j) * 16 + ev] = clock64();
 }
 
 template <int BS>
@@ -104,20 +113,39 @@ __device__ __forceinline__ void tmem_ld_fence(uint32_t (&v)[BS]) {
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0, ok;
   do {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+    // suspend-time hint: the thread sleeps in hardware until the phase completes (or 20 us pass) instead of coming back to poll
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok)
-                 : "r"(bar), "r"(parity)
+                 : "r"(bar), "r"(parity), "r"(20000u)
                  : "memory");
     if (!ok && ++spins > (1u << 26)) __trap();
   } while (!ok);
+}
+// producer-side wait: the W'' / dY / X^0 producers are whole fields ahead of their consumers, so they can afford to sleep between
+// polls -- a polling warp takes issue slots from the two row warps on its scheduler (clock stamps, r02q: the row warps next to the
+// W'' producer handed their accumulators back ~1000 cycles per field later than those next to an idle warp)
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* barp, uint32_t parity) {
+  const uint32_t bar = smem_u32(barp);
+  uint32_t spins = 0, ok;
+  for (;;) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity), "r"(20000u)
+                 : "memory");
+    if (ok) break;
+    if (++spins > (1u << 26)) __trap();
+  }
 }
 // every lane polls (measured: one polling lane + __syncwarp is slower, 0.302 vs 0.220 ms on the cfg2 wide layer)
 __device__ __forceinline__ void mbar_wait_w(uint32_t bar, uint32_t parity, bool lead) {
   (void)lead;
   mbar_wait_a(bar, parity);
 }
+// "this buffer may be overwritten": the arriving thread only READ the buffer and those reads have completed (their values were
+// used; TMEM loads: tcgen05.wait::ld + fence), so the arrive needs no release ordering.  The default (release) form also waits for
+// every other memory operation the thread has in flight -- a prefetched global load or the tile's output stores, a microsecond each.
 __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.relaxed.cta.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
 }
 
 // NQ = HpQ / 16.  Each row warp drains HALF = HpQ / 2 channels of every field in NBF batches of BS columns.
@@ -131,6 +159,7 @@ cin_bwd_dx_tc2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   constexpr int NBF = HALF > 32 ? 2 : 1;           // batches per field
   constexpr int BS = HALF / NBF;                   // columns per batch (multiple of 4)
   static_assert(BS * NBF == HALF && BS % 4 == 0, "dZ batch split");
+  constexpr bool LOAD_ALL = HALF <= 32;            // the whole field half in one batch (measured at HALF = 56: spills, 0.198 vs 0.192 ms)
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NG = p.fpg * HpQ;                                                // accumulator columns / weight rows of a field group
@@ -147,6 +176,10 @@ cin_bwd_dx_tc2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   const int dpitch = p.m | 1;                                                 // odd pitch: a warp's 32 rows hit 32 different banks
   float* sDx0 = reinterpret_cast<float*>(sX0 + 2 * (size_t)x0_tile);          // [2 halves][128][dpitch] fp32: each thread's own dX0 row
   CinDx2Bars* bars = reinterpret_cast<CinDx2Bars*>(sDx0 + ((2 * 128 * dpitch + 1) & ~1));
+  uint32_t* strace = reinterpret_cast<uint32_t*>(bars + 1);                   // DBG builds only: DX2_TRACE_TILES x GROUPS x 16 stamps
+  if constexpr (DBG) {
+    for (int i = threadIdx.x; i < DX2_TRACE_TILES * DX2_TRACE_GROUPS * 16; i += blockDim.x) strace[i] = 0u;
+  }
 
   const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
   const uint16_t cmask = (uint16_t)((1u << csize) - 1);
@@ -154,7 +187,7 @@ cin_bwd_dx_tc2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   if (threadIdx.x == 0) {
     for (int i = 0; i < DX_MAX_NS; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], csize); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars->a_full[i], 8);    mbar_init(&bars->a_empty[i], 1);
+      mbar_init(&bars->a_full[i], 8);    mbar_init(&bars->a_empty[i], 2);
       mbar_init(&bars->acc_full[i], 1);  mbar_init(&bars->acc_empty[i], 8);
       mbar_init(&bars->x_full[i], 1);    mbar_init(&bars->x_empty[i], 8);
       mbar_init(&bars->dy_full[i], 1);   mbar_init(&bars->dy_empty[i], 8);
@@ -183,9 +216,9 @@ cin_bwd_dx_tc2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         bool first_pass = true;
         for (int it = 0; it < p.n_iters; ++it) {
           for (int g = 0; g < n_groups; ++g) {
-            if (!first_pass) mbar_wait(&bars->w_empty[ws], wphase);
+            if (!first_pass) mbar_wait_sleep(&bars->w_empty[ws], wphase);
             if constexpr (DBG) {
-              dx2_stamp(p, it, g, 6);
+              dx2_stamp_s(strace, p, it, g, 3);
               if (p.debug & 8) {                      // experiment: no weight stream (barrier hand-offs only)
                 mbar_arrive(&bars->w_full[ws]);
                 if (++ws == (uint32_t)p.ns) { ws = 0; wphase ^= 1; first_pass = false; }
@@ -207,8 +240,13 @@ cin_bwd_dx_tc2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
           }
         }
       }
-    } else if (warp == 1) {
-      // =============================== MMA issuer (warp-uniform loop, elected lane issues) ===============================
+    } else if (warp == 1 || warp == 3) {
+      // =============================== MMA issuers (warp-uniform loops, elected lane issues) ===============================
+      // TWO issuing warps take the field groups in turn.  One issuer alone is busy ~1500 cycles per field (clock stamps, r02q: two
+      // barrier waits ~450, 13 MMAs held by the tensor queue ~650, two commits ~350) for ~730 cycles of tensor work; with two, one
+      // warp's waits and commits run while the other warp's MMAs execute.  A group's MMAs all come from one thread (in order, own
+      // accumulator), tcgen05.commit tracks the issuing thread's MMAs, so nothing else changes.
+      const uint32_t which = (uint32_t)(warp >> 1);                       // warp 1 -> groups with even running index, warp 3 -> odd
       const uint32_t idesc = make_idesc_bf16(128, NG);
       const uint64_t bdesc0 = make_desc_k_sw128(smem_u32(sW));
       const uint64_t tdesc0 = make_desc_k_sw32(smem_u32(sWt));
@@ -216,53 +254,58 @@ cin_bwd_dx_tc2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
       const uint32_t tslot_desc_step = tail_stride >> 4;
       const uint32_t box_desc_step = w_box_bytes >> 4;
       const uint32_t tail_desc_step = w_tail_bytes >> 4;
-      uint32_t ws = 0, wphase = 0;
-      uint64_t bdesc = bdesc0, tdesc = tdesc0;
-      uint32_t gc = 0;            // field groups issued so far (accumulator = gc & 1)
+      uint32_t ws = 0, wphase = 0;      // ring slot / phase of the group under the cursor (every group, whoever issues it)
+      uint32_t G = 0;                   // running index of the group under the cursor
+      uint32_t gc = 0;                  // active groups before the cursor (accumulator = gc & 1)
       int at = 0;
       const int ksteps = p.n_full * 4;
       for (int it = 0; it < p.n_iters; ++it) {
         const bool active = tile_of(it) < p.n_tiles;
         const uint32_t abuf = (uint32_t)(at & 1);
         const uint32_t a_addr0 = tmem_base + abuf * 128;
-        if (active) {
-          mbar_wait_w(smem_u32(&bars->a_full[abuf]), (at >> 1) & 1, lane == 0);
-          fence_after_sync();
-        }
-        for (int g = 0; g < n_groups; ++g) {
-          const uint32_t ab = gc & 1;
-          if (active && gc >= 2) {
-            mbar_wait_w(smem_u32(&bars->acc_empty[ab]), ((gc >> 1) - 1) & 1, lane == 0);
-            fence_after_sync();
-          }
-          if constexpr (DBG) { if (lane == 0) dx2_stamp(p, it, g, 0); }
-          mbar_wait_w(smem_u32(&bars->w_full[ws]), wphase, lane == 0);
-          fence_after_sync();
-          if constexpr (DBG) { if (lane == 0) dx2_stamp(p, it, g, 1); }
-          if (elect_one()) {
-            if (active && !(DBG && (p.debug & 4))) {
-              const uint32_t d_addr = tmem_base + DX2_ACC_COL0 + ab * 128;
-              uint64_t bd = bdesc;
-              for (int ks = 0; ks < ksteps; ks += 4, bd += box_desc_step) {
-#pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4)
-                  umma_ts(d_addr, a_addr0 + (uint32_t)(ks + k4) * 8, bd + (uint64_t)(k4 * 2), idesc, (ks + k4) > 0 ? 1u : 0u);
-              }
-              for (int t = 0; t < p.tail_ks; ++t)
-                umma_ts(d_addr, a_addr0 + (uint32_t)(ksteps + t) * 8, tdesc + (uint64_t)t * tail_desc_step, idesc, (ksteps + t) > 0 ? 1u : 0u);
+        bool a_ready = false;
+        for (int g = 0; g < n_groups; ++g, ++G) {
+          if ((G & 1) == which) {
+            const uint32_t ab = gc & 1;
+            if (active && !a_ready) {
+              mbar_wait_w(smem_u32(&bars->a_full[abuf]), (at >> 1) & 1, lane == 0);
+              fence_after_sync();
+              a_ready = true;
             }
-            if (csize > 1) umma_commit_mcast(&bars->w_empty[ws], cmask);
-            else umma_commit(&bars->w_empty[ws]);
-            if (active) umma_commit(&bars->acc_full[ab]);
+            if (active && gc >= 2) {
+              mbar_wait_w(smem_u32(&bars->acc_empty[ab]), ((gc >> 1) - 1) & 1, lane == 0);
+              fence_after_sync();
+            }
+            if constexpr (DBG) { if (lane == 0) dx2_stamp_s(strace, p, it, g, 0); }
+            mbar_wait_w(smem_u32(&bars->w_full[ws]), wphase, lane == 0);
+            fence_after_sync();
+            if constexpr (DBG) { if (lane == 0) dx2_stamp_s(strace, p, it, g, 1); }
+            if (elect_one()) {
+              if (active && !(DBG && (p.debug & 4))) {
+                const uint32_t d_addr = tmem_base + DX2_ACC_COL0 + ab * 128;
+                uint64_t bd = bdesc0 + (uint64_t)ws * slot_desc_step;
+                const uint64_t td = tdesc0 + (uint64_t)ws * tslot_desc_step;
+                for (int ks = 0; ks < ksteps; ks += 4, bd += box_desc_step) {
+#pragma unroll
+                  for (int k4 = 0; k4 < 4; ++k4)
+                    umma_ts(d_addr, a_addr0 + (uint32_t)(ks + k4) * 8, bd + (uint64_t)(k4 * 2), idesc, (ks + k4) > 0 ? 1u : 0u);
+                }
+                for (int t = 0; t < p.tail_ks; ++t)
+                  umma_ts(d_addr, a_addr0 + (uint32_t)(ksteps + t) * 8, td + (uint64_t)t * tail_desc_step, idesc, (ksteps + t) > 0 ? 1u : 0u);
+              }
+              if (csize > 1) umma_commit_mcast(&bars->w_empty[ws], cmask);
+              else umma_commit(&bars->w_empty[ws]);
+              if (active) umma_commit(&bars->acc_full[ab]);
+            }
+            __syncwarp();
+            if constexpr (DBG) { if (lane == 0) dx2_stamp_s(strace, p, it, g, 2); }
           }
-          __syncwarp();
-          if constexpr (DBG) { if (lane == 0) dx2_stamp(p, it, g, 2); }
-          if (++ws == (uint32_t)p.ns) { ws = 0; wphase ^= 1; bdesc = bdesc0; tdesc = tdesc0; }
-          else { bdesc += slot_desc_step; tdesc += tslot_desc_step; }
+          if (++ws == (uint32_t)p.ns) { ws = 0; wphase ^= 1; }
           if (active) ++gc;
         }
         if (active) {
-          if (elect_one()) umma_commit(&bars->a_empty[abuf]);   // all MMAs reading this tile's dY have been issued and will complete
+          // every MMA of this thread that reads the tile's dY has been issued and will complete (the other issuer commits too)
+          if (elect_one()) umma_commit(&bars->a_empty[abuf]);
           __syncwarp();
           ++at;
         }
@@ -276,7 +319,7 @@ cin_bwd_dx_tc2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
           const int64_t tile = tile_of(it);
           if (tile >= p.n_tiles) break;
           const uint32_t buf = xit & 1;
-          if (xit >= 2) mbar_wait(&bars->x_empty[buf], ((xit >> 1) - 1) & 1);
+          if (xit >= 2) mbar_wait_sleep(&bars->x_empty[buf], ((xit >> 1) - 1) & 1);
           const int64_t r0 = tile * 128;
           const uint32_t nrows = (uint32_t)min((int64_t)128, p.R - r0);
           mbar_arrive_expect_tx(&bars->x_full[buf], nrows * (uint32_t)(p.mP * 2));
@@ -284,7 +327,7 @@ cin_bwd_dx_tc2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
           ++xit;
           for (int c = 0; c < p.n_hchunks; ++c, ++dyc) {
             const uint32_t slot = dyc & 1;
-            if (dyc >= 2) mbar_wait(&bars->dy_empty[slot], ((dyc >> 1) - 1) & 1);
+            if (dyc >= 2) mbar_wait_sleep(&bars->dy_empty[slot], ((dyc >> 1) - 1) & 1);
             mbar_arrive_expect_tx(&bars->dy_full[slot], DX2_DY_BOX);
             tma_load_2d(sDY + (size_t)slot * DX2_DY_BOX, &tmDy, c * 64, (int)r0, &bars->dy_full[slot]);   // rows / columns past the end: zeros
           }
@@ -369,7 +412,7 @@ cin_bwd_dx_tc2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
       const int64_t nrow = tile_of(it + 1) * 128 + rl;
       int sc = has_next ? 0 : n_boxes;               // boxes of the next tile staged so far
       if (has_next && at >= 1) {                     // the other A buffer was read by the previous tile's MMAs: long complete
-        mbar_wait(&bars->a_empty[nbuf], (((at + 1) >> 1) - 1) & 1);
+        mbar_wait_a(smem_u32(&bars->a_empty[nbuf]), (((at + 1) >> 1) - 1) & 1);
         fence_after_sync();
       }
       const int stage_from = max(1, m / 2 - 2);      // the next tile's boxes move during the middle fields of this tile
@@ -382,7 +425,7 @@ cin_bwd_dx_tc2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         xkf[v4 * 2 + 0] = pack2(xraw[v4].x << 16, xraw[v4].x & 0xffff0000u);
         xkf[v4 * 2 + 1] = pack2(xraw[v4].y << 16, xraw[v4].y & 0xffff0000u);
       }
-      mbar_wait(&bars->x_full[buf], (at >> 1) & 1);
+      mbar_wait_a(smem_u32(&bars->x_full[buf]), (at >> 1) & 1);
       uint32_t x0a = smem_u32(sX0) + (uint32_t)buf * x0_tile + (uint32_t)(rl * p.mP * 2);   // &x0[r, j] (bf16), advanced per field
       uint32_t pla = plane0;                                                                 // &dX0 partial [r, j], advanced per field
       uint64_t dxk[HALF / 2];
@@ -397,7 +440,6 @@ cin_bwd_dx_tc2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         const uint32_t ab = gc & 1;
         mbar_wait_a(bar_acc_full + ab * 8, (gc >> 1) & 1);
         fence_after_sync();
-        if constexpr (DBG) { if (warp == 4 && lead) dx2_stamp(p, it, j0 / fpg, 3); }
         const int nf = min(fpg, m - j0);
         uint32_t taddr = acc_taddr + ab * 128;
         for (int f = 0; f < nf; ++f, taddr += HpQ) {
@@ -406,6 +448,32 @@ cin_bwd_dx_tc2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
           asm volatile("ld.shared.u16 %0, [%1];" : "=r"(xb) : "r"(x0a));        // next field's x0 (one past the row's end at the last field: in bounds)
           const uint64_t x0p = pack2(xcur, xcur);
           uint64_t dacc[2] = {0ull, 0ull};
+          if constexpr (LOAD_ALL) {
+            // the whole field half in registers first: the accumulator goes back to the tensor core before the first FMA (the
+            // hand-off chain MMA -> rows -> MMA sets the pace; FMAs inside it cost a field time each)
+            uint32_t v[HALF];
+            if (DBG && (p.debug & 2)) {
+#pragma unroll
+              for (int i = 0; i < HALF; ++i) v[i] = 0u;
+            } else {
+              tmem_ld_batch<HALF>(taddr, v);
+            }
+            tmem_ld_fence<HALF>(v);
+            if (f == nf - 1) {
+              fence_before_sync();
+              __syncwarp();
+              if (lead) mbar_arrive_a(bar_acc_empty + ab * 8);
+              if constexpr (DBG) { if (lead) dx2_stamp_s(strace, p, it, j0 / fpg, 4 + warp); }
+            }
+            if (!(DBG && (p.debug & 1))) {
+#pragma unroll
+              for (int i = 0; i < HALF; i += 2) {
+                const uint64_t z = pack2(v[i], v[i + 1]);
+                dxk[i / 2] = ffma2(z, x0p, dxk[i / 2]);
+                dacc[(i / 2) & 1] = ffma2(z, xkf[i / 2], dacc[(i / 2) & 1]);
+              }
+            }
+          } else {
 #pragma unroll
           for (int nb = 0; nb < NBF; ++nb) {
             uint32_t v[BS];
@@ -420,7 +488,7 @@ cin_bwd_dx_tc2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
               fence_before_sync();
               __syncwarp();
               if (lead) mbar_arrive_a(bar_acc_empty + ab * 8);
-              if constexpr (DBG) { if (lead && (warp == 4 || warp == 11)) dx2_stamp(p, it, j0 / fpg, warp == 4 ? 4 : 7); }
+              if constexpr (DBG) { if (lead) dx2_stamp_s(strace, p, it, j0 / fpg, 4 + warp); }
             }
             if (!(DBG && (p.debug & 1))) {
 #pragma unroll
@@ -432,6 +500,7 @@ cin_bwd_dx_tc2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
               }
             }
           }
+          }
           float a0, a1, b0, b1;
           unpack2(dacc[0], a0, a1);
           unpack2(dacc[1], b0, b1);
@@ -439,7 +508,6 @@ cin_bwd_dx_tc2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
           asm volatile("st.shared.f32 [%0], %1;" ::"r"(pla), "f"((a0 + a1) + (b0 + b1)) : "memory");
           pla += 4;
         }
-        if constexpr (DBG) { if (warp == 4 && lead) dx2_stamp(p, it, j0 / fpg, 5); }
         ++gc;
         const int jn = j0 + nf;                      // fields drained so far
         if (sc < n_boxes && jn > stage_from) {       // one dY box of the next tile per group
@@ -476,12 +544,16 @@ cin_bwd_dx_tc2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         }
       }
       __syncwarp();
-      if (lead) mbar_arrive(&bars->x_empty[buf]);
+      if (lead) mbar_arrive_a(smem_u32(&bars->x_empty[buf]));
       ++at;
     }
   }
   fence_before_sync();
   __syncthreads();
+  if constexpr (DBG) {
+    if (p.trace != nullptr && blockIdx.x == 0)
+      for (int i = threadIdx.x; i < DX2_TRACE_TILES * DX2_TRACE_GROUPS * 16; i += blockDim.x) p.trace[i] = (long long)strace[i];
+  }
   if (csize > 1) cluster_sync_all();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
@@ -539,7 +611,7 @@ static int launch_dx2(const CUtensorMap& tmW, const CUtensorMap& tmWt, const CUt
 }
 
 long long* g_cin_dx_trace = nullptr;
-// profiling only: device buffer of DX2_TRACE_TILES * DX2_TRACE_GROUPS * 8 int64 that CTA 0 of the next dX launches stamps (nullptr = off)
+// profiling only: device buffer of DX2_TRACE_TILES * DX2_TRACE_GROUPS * 16 int64 that CTA 0 of the next dX launches stamps (nullptr = off)
 extern "C" void xdfm_cin_dx_set_trace(void* buf) { g_cin_dx_trace = (long long*)buf; }
 
 // called by xdfm_cin_bwd_dx_tc (cin_tc_bwd_dx.cu) after W'' has been written to `wt`; p carries the shape, the operands and the tile schedule
@@ -558,9 +630,12 @@ int cin_dx2_launch(const void* wt, int HC, CinDxParams p, int fpg, int ns, size_
   p.trace = g_cin_dx_trace;
   blocks = std::max(blocks / cluster * cluster, cluster);
   p.n_iters = (int)ceil_div64(p.n_tiles, blocks);
-  if (p.debug != 0 || p.trace != nullptr) {       // profiling builds of the two cfg2 shapes only
-    if (p.HpQ == 112) return launch_dx2<7, true>(tmW, tmWt, tmDy, p, smem, blocks, cluster, st);
-    if (p.HpQ == 32) return launch_dx2<2, true>(tmW, tmWt, tmDy, p, smem, blocks, cluster, st);
+  if (p.debug != 0 || p.trace != nullptr) {       // profiling builds of the two cfg2 shapes only (+ 4 KB of stamps in shared memory)
+    const size_t smem_dbg = smem + DX2_TRACE_TILES * DX2_TRACE_GROUPS * 16 * 4;
+    if (smem_dbg <= 227 * 1024) {
+      if (p.HpQ == 112) return launch_dx2<7, true>(tmW, tmWt, tmDy, p, smem_dbg, blocks, cluster, st);
+      if (p.HpQ == 32) return launch_dx2<2, true>(tmW, tmWt, tmDy, p, smem_dbg, blocks, cluster, st);
+    }
     p.debug = 0;
   }
   switch (p.HpQ / 16) {

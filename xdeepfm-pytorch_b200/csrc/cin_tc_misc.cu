@@ -103,22 +103,34 @@ extern "C" int xdfm_add_rows_f32(float* a, int64_t pitch_a, const float* b, int6
 // both the row-layout reads and the [B, C, D] writes coalesced through a shared-memory transpose.
 __global__ void __launch_bounds__(256) cin_dx0_finish_kernel(const float* __restrict__ parts, int n_planes, const float* __restrict__ extra,
                                                              int64_t extra_pitch, int64_t B, int C, int D, int CP, float* __restrict__ x) {
-  extern __shared__ float sh[];                        // [rows_per_block][CP + 1]
+  extern __shared__ float sh[];                        // [rows of a pass][CP + 1]
   const int64_t R = B * (int64_t)D;
   const int spb = max(1, 256 / D);                     // samples per block pass
   const int rows = spb * D;
   const int pitch = CP + 1;
+  const int v4_per_row = CP / 4;
   for (int64_t b0 = (int64_t)blockIdx.x * spb; b0 < B; b0 += (int64_t)gridDim.x * spb) {
     const int64_t r0 = b0 * D;
     const int nrows = (int)min((int64_t)rows, R - r0);
-    for (int e = threadIdx.x; e < nrows * CP; e += blockDim.x) {
-      const int rr = e / CP, c = e - rr * CP;
-      float v = 0.f;
-      if (c < C) {
-        v = extra != nullptr ? extra[(r0 + rr) * extra_pitch + c] : 0.f;
-        for (int pl = 0; pl < n_planes; ++pl) v += parts[((int64_t)pl * R + r0 + rr) * CP + c];
+    // 128-bit reads of every plane (rows of a pass are contiguous in each plane); all loads of an element group before the adds
+    for (int e = threadIdx.x; e < nrows * v4_per_row; e += blockDim.x) {
+      const int rr = e / v4_per_row, c4 = e - rr * v4_per_row;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (extra != nullptr) v = *reinterpret_cast<const float4*>(extra + (r0 + rr) * extra_pitch + c4 * 4);
+      const float4* src = reinterpret_cast<const float4*>(parts + (r0 + rr) * CP) + c4;
+      const int64_t plane_v4 = R * (int64_t)CP / 4;
+      int pl = 0;
+      for (; pl + 2 <= n_planes; pl += 2) {
+        const float4 a = src[(int64_t)pl * plane_v4], bq = src[(int64_t)(pl + 1) * plane_v4];
+        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+        v.x += bq.x; v.y += bq.y; v.z += bq.z; v.w += bq.w;
       }
-      sh[rr * pitch + c] = v;
+      if (pl < n_planes) {
+        const float4 a = src[(int64_t)pl * plane_v4];
+        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+      }
+      float* d = sh + rr * pitch + c4 * 4;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
     }
     __syncthreads();
     const int nsamp = nrows / D;
@@ -134,11 +146,15 @@ __global__ void __launch_bounds__(256) cin_dx0_finish_kernel(const float* __rest
 
 extern "C" int xdfm_cin_dx0_finish(const float* parts, int n_planes, const float* extra, int64_t extra_pitch, int64_t B, int C, int D, int CP,
                                    float* x, void* stream) {
-  XDFM_CHECK_ARG(D >= 1 && D <= 256 && CP >= C && n_planes >= 0, "cin_dx0_finish: bad shape D=%d C=%d CP=%d planes=%d", D, C, CP, n_planes);
+  XDFM_CHECK_ARG(D >= 1 && D <= 256 && CP >= C && CP % 4 == 0 && n_planes >= 0, "cin_dx0_finish: bad shape D=%d C=%d CP=%d planes=%d", D, C, CP,
+                 n_planes);
+  XDFM_CHECK_ARG(extra == nullptr || (extra_pitch >= CP && extra_pitch % 4 == 0 && (uintptr_t)extra % 16 == 0),
+                 "cin_dx0_finish: extra rows need a pitch >= CP, a multiple of 4, 16-byte aligned");
+  XDFM_CHECK_ARG((uintptr_t)parts % 16 == 0, "cin_dx0_finish: planes must be 16-byte aligned");
   if (B == 0) return XDFM_OK;
   const int spb = std::max(1, 256 / D);
   const size_t sm = (size_t)spb * D * (CP + 1) * sizeof(float);
-  int blocks = (int)std::min<int64_t>((int64_t)xdfm_num_sms() * 8, ceil_div64(B, spb));
+  int blocks = (int)std::min<int64_t>((int64_t)xdfm_num_sms() * 6, ceil_div64(B, spb));
   if (sm > 48 * 1024) XDFM_CUDA(cudaFuncSetAttribute(cin_dx0_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   cin_dx0_finish_kernel<<<blocks, 256, sm, (cudaStream_t)stream>>>(parts, n_planes, extra, extra_pitch, B, C, D, CP, x);
   XDFM_LAUNCH_CHECK();

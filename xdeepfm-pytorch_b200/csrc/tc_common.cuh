@@ -4,6 +4,10 @@
 #include "common.cuh"
 #include <cuda.h>
 
+#ifndef XDFM_TRYWAIT_HINT_NS
+#define XDFM_TRYWAIT_HINT_NS 20000u
+#endif
+
 namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -21,12 +25,15 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+// The suspend-time hint (ns) lets the thread sleep in hardware until the phase completes instead of coming back to poll after the
+// default (short) time limit: a polling warp takes issue slots and shared-memory cycles from the warps on its scheduler (clock stamps
+// in the dX kernel, round 2: the row warps next to a polling producer warp ran ~1000 cycles per field behind the others).
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
-      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(XDFM_TRYWAIT_HINT_NS)
       : "memory");
   return ok != 0;
 }

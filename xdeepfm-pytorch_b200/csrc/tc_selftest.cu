@@ -190,13 +190,13 @@ extern "C" int xdfm_tc_selftest_gemm(const void* A, const void* Bm, int N, int K
 //  11  the same by two commits, the whole of warp 0 (32 lanes) waiting on B like the MMA warp does
 //  12  as 11 plus the eight warps run tcgen05.fence / wait::ld / __syncwarp / a shared-memory store around the arrive (the skeleton of
 //      the dX row warps)
-__global__ void __launch_bounds__(320) tc_latency_probe_kernel(long long* out) {
+__global__ void __launch_bounds__(384, 1) tc_latency_probe_kernel(long long* out, int setmax) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar[4 + 3 * 7];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float scratch[320];
+  __shared__ float scratch[384];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < 112 * 128 / 4; i += 320) reinterpret_cast<uint32_t*>(smem)[i] = 0u;       // one SWIZZLE_128B B chunk of zeros
+  for (int i = tid; i < 112 * 128 / 4; i += 384) reinterpret_cast<uint32_t*>(smem)[i] = 0u;       // one SWIZZLE_128B B chunk of zeros
   if (warp == 0) tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1);
@@ -213,6 +213,10 @@ __global__ void __launch_bounds__(320) tc_latency_probe_kernel(long long* out) {
   fence_after_sync();
   const uint32_t tb = tmem_base_s;
   const int REPS = 16;
+  if (setmax) {                                   // the register hand-over of the CIN kernels: does it change the hand-off latencies?
+    if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+  }
   if (tid == 0) {
     uint32_t ph = 0;
     long long t0, acc;
@@ -278,7 +282,7 @@ __global__ void __launch_bounds__(320) tc_latency_probe_kernel(long long* out) {
         __syncwarp();
       }
       if (tid == 0) out[6 + mode] = (clock64() - t0) / REPS;
-    } else if (warp >= 2 && (many || (warp == 2 && lane == 0))) {
+    } else if (warp >= 4 && (many || (warp == 4 && lane == 0))) {
       for (int r = 0; r < REPS; ++r) {
         mbar_wait(bA, r & 1);
         if (dress) {
@@ -293,13 +297,55 @@ __global__ void __launch_bounds__(320) tc_latency_probe_kernel(long long* out) {
     }
   }
   __syncthreads();
+  // 13 / 14: the 13 MMAs + commit -> wait of test 2 while the eight other warps keep reading ANOTHER accumulator region out of TMEM
+  // (13: tcgen05.ld x16 x 7 + wait::ld in a loop, the dX drain's traffic; 14: the same loop with the loads replaced by FMAs)
+  __shared__ volatile int stop_flag;
+  for (int mode = 0; mode < 2; ++mode) {
+    if (tid == 0) stop_flag = 0;
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, 112);
+      const uint64_t bdesc = make_desc_k_sw128(smem_u32(smem));
+      uint32_t ph = 0;
+      long long acc = 0;
+      for (int r = 0; r < REPS; ++r) {
+        long long t0 = clock64();
+        for (int ks = 0; ks < 13; ++ks) umma_ts(tb + 256, tb + (ks & 3) * 8, bdesc + (uint64_t)((ks & 3) * 2), idesc, ks > 0);
+        umma_commit(&bar[3]);
+        mbar_wait(&bar[3], ph);
+        acc += clock64() - t0;
+        ph ^= 1;
+      }
+      out[13 + mode] = acc / REPS;
+      stop_flag = 1;
+    } else if (warp >= 4) {
+      const uint32_t taddr = tb + 384 + ((uint32_t)((warp & 3) * 32) << 16);
+      float accf = 0.f;
+      while (!stop_flag) {
+        uint32_t v[16];
+        if (mode == 0) {
+#pragma unroll
+          for (int c = 0; c < 7; ++c) {
+            tmem_ld_x16(taddr + c * 16, v);
+            tmem_wait_ld();
+            accf += __uint_as_float(v[0]) + __uint_as_float(v[15]);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 112; ++c) accf = fmaf(accf, 1.0001f, 0.5f);
+        }
+      }
+      scratch[tid] = accf;
+    }
+    __syncthreads();
+  }
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tb, 512);
 }
 
-extern "C" int xdfm_tc_latency_probe(long long* out, void* stream) {
-  tc_latency_probe_kernel<<<1, 320, 112 * 128, (cudaStream_t)stream>>>(out);
+extern "C" int xdfm_tc_latency_probe(long long* out, int setmaxnreg, void* stream) {
+  tc_latency_probe_kernel<<<1, 384, 112 * 128, (cudaStream_t)stream>>>(out, setmaxnreg);
   XDFM_LAUNCH_CHECK();
   return XDFM_OK;
 }

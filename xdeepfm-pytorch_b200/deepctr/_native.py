@@ -66,7 +66,7 @@ _SIGS = {
     "xdfm_cin_bwd_dw_tc_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int, c_int]),
     "xdfm_cin_bwd_dw_tc": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, c_int64, _P]),
     "xdfm_tc_selftest_gemm": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
-    "xdfm_tc_latency_probe": (c_int, [_P, _P]),
+    "xdfm_tc_latency_probe": (c_int, [_P, c_int, _P]),
     "xdfm_ipc_alloc": (c_int, [c_int64, POINTER(_P)]),
     "xdfm_ipc_free": (c_int, [_P]),
     "xdfm_ipc_export": (c_int, [_P, _P]),
