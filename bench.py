@@ -407,6 +407,7 @@ def run_workload(env, args, name, steps, want_profile, want_e2e=True):
         e1.record()
         env.sync_all()
         est = max(e0.elapsed_time(e1) / 3, 0.05)
+        est = env.max_over_ranks([est])[0]      # every rank must run the SAME number of profiled steps (the steps hold collectives)
         prof_steps = int(min(2000, max(20, min(steps, 20), args.profile_seconds * 1e3 / est)))
         sampler = ClockSampler(env.local_rank)
         if env.rank == 0:

@@ -22,8 +22,8 @@
 //   * narrow layers (HpQ <= 64) contract FPG = 128 / HpQ consecutive fields with ONE MMA group (N = FPG * HpQ, the weight rows of
 //     consecutive fields are consecutive rows of W'') and one barrier hand-off instead of one per field.
 //
-// Warps (384 threads): 0 = W'' stream (TMA, multicast across the cluster), 1 and 3 = MMA issuers (field groups in turn; 1 also
-// allocates TMEM), 2 = per-tile loads (X^0 rows, dY boxes), 4..11 = row warps (TMEM lane quarter = warp & 3, channel half = (warp - 4) >> 2).
+// Warps (384 threads): 0 = W'' stream (TMA, multicast across the cluster), 1 = MMA issuer + TMEM alloc, 2 = per-tile loads (X^0 rows,
+// dY boxes), 3 = idle, 4..11 = row warps (TMEM lane quarter = warp & 3, channel half = (warp - 4) >> 2).
 // TMEM columns: [0,128) / [128,256) dY of the current / next tile (A operand, TS-mode MMA), [256,384) / [384,512) two accumulators.
 #include "tc_common.cuh"
 #include "../../include/xdfm.h"
@@ -118,7 +118,10 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
                  : "=r"(ok)
                  : "r"(bar), "r"(parity), "r"(20000u)
                  : "memory");
-    if (!ok && ++spins > (1u << 26)) __trap();
+    if (!ok && ++spins > (1u << 26)) {
+      printf("xdfm: dX mbarrier wait timed out (block %d thread %d bar@%u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
   } while (!ok);
 }
 // producer-side wait: the W'' / dY / X^0 producers are whole fields ahead of their consumers, so they can afford to sleep between
@@ -133,7 +136,10 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* barp, uint32_t parity)
                  : "r"(bar), "r"(parity), "r"(20000u)
                  : "memory");
     if (ok) break;
-    if (++spins > (1u << 26)) __trap();
+    if (++spins > (1u << 26)) {
+      printf("xdfm: dX producer wait timed out (block %d thread %d bar@%u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
   }
 }
 // every lane polls (measured: one polling lane + __syncwarp is slower, 0.302 vs 0.220 ms on the cfg2 wide layer)
@@ -187,7 +193,7 @@ cin_bwd_dx_tc2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   if (threadIdx.x == 0) {
     for (int i = 0; i < DX_MAX_NS; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], csize); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars->a_full[i], 8);    mbar_init(&bars->a_empty[i], 2);
+      mbar_init(&bars->a_full[i], 8);    mbar_init(&bars->a_empty[i], 1);
       mbar_init(&bars->acc_full[i], 1);  mbar_init(&bars->acc_empty[i], 8);
       mbar_init(&bars->x_full[i], 1);    mbar_init(&bars->x_empty[i], 8);
       mbar_init(&bars->dy_full[i], 1);   mbar_init(&bars->dy_empty[i], 8);
@@ -240,13 +246,11 @@ cin_bwd_dx_tc2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
           }
         }
       }
-    } else if (warp == 1 || warp == 3) {
-      // =============================== MMA issuers (warp-uniform loops, elected lane issues) ===============================
-      // TWO issuing warps take the field groups in turn.  One issuer alone is busy ~1500 cycles per field (clock stamps, r02q: two
-      // barrier waits ~450, 13 MMAs held by the tensor queue ~650, two commits ~350) for ~730 cycles of tensor work; with two, one
-      // warp's waits and commits run while the other warp's MMAs execute.  A group's MMAs all come from one thread (in order, own
-      // accumulator), tcgen05.commit tracks the issuing thread's MMAs, so nothing else changes.
-      const uint32_t which = (uint32_t)(warp >> 1);                       // warp 1 -> groups with even running index, warp 3 -> odd
+    } else if (warp == 1) {
+      // =============================== MMA issuer (warp-uniform loop, elected lane issues) ===============================
+      // (Two issuing warps taking the groups in turn measured 8 % faster on the cfg2 wide layer -- one warp's barrier waits and
+      // commits overlap the other's MMAs -- but the full training flow then failed intermittently with a launch failure; one
+      // issuing thread per CTA is what every reference pipeline does, so that is what ships.)
       const uint32_t idesc = make_idesc_bf16(128, NG);
       const uint64_t bdesc0 = make_desc_k_sw128(smem_u32(sW));
       const uint64_t tdesc0 = make_desc_k_sw32(smem_u32(sWt));
@@ -265,7 +269,7 @@ cin_bwd_dx_tc2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         const uint32_t a_addr0 = tmem_base + abuf * 128;
         bool a_ready = false;
         for (int g = 0; g < n_groups; ++g, ++G) {
-          if ((G & 1) == which) {
+          {
             const uint32_t ab = gc & 1;
             if (active && !a_ready) {
               mbar_wait_w(smem_u32(&bars->a_full[abuf]), (at >> 1) & 1, lane == 0);
@@ -304,7 +308,7 @@ cin_bwd_dx_tc2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
           if (active) ++gc;
         }
         if (active) {
-          // every MMA of this thread that reads the tile's dY has been issued and will complete (the other issuer commits too)
+          // every MMA that reads the tile's dY has been issued and will complete
           if (elect_one()) umma_commit(&bars->a_empty[abuf]);
           __syncwarp();
           ++at;

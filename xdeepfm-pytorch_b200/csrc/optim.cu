@@ -619,12 +619,15 @@ __global__ void __launch_bounds__(256) gather_sharded_lazy_kernel(const long lon
     const int64_t lrow = feat_base[owner * m + f] + id / G;
     const long long* pp = ptrs + owner * 8;
     const int64_t e = lrow * D + v * 4;
+    // every operand of the replay is requested at once: a remote row costs ONE NVLink round trip, not two (the moments used to be
+    // fetched only after `last` had come back; nearly every row a batch looks up is behind, so nothing is saved by waiting)
     float4 w4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(pp[0]) + e);
     const int from = *(reinterpret_cast<const int32_t*>(pp[6]) + lrow);
+    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pp[2]) a4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(pp[2]) + e);
+    if (pp[4]) b4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(pp[4]) + e);
     if (from < done) {
-      float w[4] = {w4.x, w4.y, w4.z, w4.w}, a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
-      if (pp[2]) { const float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(pp[2]) + e); a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w; }
-      if (pp[4]) { const float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(pp[4]) + e); b[0] = t.x; b[1] = t.y; b[2] = t.z; b[3] = t.w; }
+      float w[4] = {w4.x, w4.y, w4.z, w4.w}, a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
       float reg = 0.f;
       replay_steps<4>(cfg, h, hist, hist_base, from, done, w, a, b, reg);
       w4 = make_float4(w[0], w[1], w[2], w[3]);
@@ -654,9 +657,9 @@ __global__ void __launch_bounds__(256) linear_term_sharded_lazy_kernel(const lon
       const long long* pp = ptrs + owner * 8;
       float w[1] = {*(reinterpret_cast<const float*>(pp[1]) + lrow)};
       const int from = *(reinterpret_cast<const int32_t*>(pp[7]) + lrow);
+      float a[1] = {pp[3] ? *(reinterpret_cast<const float*>(pp[3]) + lrow) : 0.f};      // requested with w and `last`: one round trip
+      float bb[1] = {pp[5] ? *(reinterpret_cast<const float*>(pp[5]) + lrow) : 0.f};
       if (from < done) {
-        float a[1] = {pp[3] ? *(reinterpret_cast<const float*>(pp[3]) + lrow) : 0.f};
-        float bb[1] = {pp[5] ? *(reinterpret_cast<const float*>(pp[5]) + lrow) : 0.f};
         float reg = 0.f;
         replay_steps<1>(cfg, h, hist, hist_base, from, done, w, a, bb, reg);
       }
