@@ -217,6 +217,12 @@ void xdfm_cin_dw_set_pack(int enabled);
 void xdfm_cin_dx_set_trace(void* buf);
 int xdfm_cin_bwd_dx_tc(const void* dyt, const void* x0t, const void* xkt, int64_t xk_pitch, const float* W, void* wt, int64_t B, int m,
                        int Hp, int H, int D, float* dxk, float* dx0, void* stream);
+/* As xdfm_cin_bwd_dx_tc, optionally writing the dY rows of the layer BELOW instead of dxk: when dy_prev != NULL,
+ * dy_prev[r, i] = act'(xkt[r, i]) * dXk[r, i] for i < HpQ (bf16, row pitch dy_pitch >= HpQ, multiple of 8) and dxk may be NULL.  Valid
+ * when the layer below feeds only this layer through those channels (split_half: its first Hp channels); act = XDFM_ACT_RELU / NONE.
+ * The layer below then calls xdfm_cin_dy_rows_cols with dnext = NULL and dnext_pitch = -1 ("hidden half already in dyt"). */
+int xdfm_cin_bwd_dx_tc_dy(const void* dyt, const void* x0t, const void* xkt, int64_t xk_pitch, const float* W, void* wt, int64_t B, int m,
+                          int Hp, int H, int D, float* dxk, float* dx0, void* dy_prev, int64_t dy_pitch, int act, void* stream);
 
 /* CIN weight gradient on the tensor cores.  Operands are CHANNEL-MAJOR bf16 copies (xdfm_rows_to_cols_bf16: rows [R, pitch]
  * -> [CP, R], rows >= C zero): dyT [H_pad, R], xkT [HpQ, R], x0T [mP, R] with H_pad/HpQ = H/Hp rounded up to 16, mP = m rounded

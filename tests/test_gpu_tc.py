@@ -240,6 +240,60 @@ def test_cin_tc_backward_dx_matches_emulation(case, cluster):
     assert_close(got_dx0, ref_dx0, 1e-3, 1e-3 * ref_dx0.abs().max().item(), "dx0")
 
 
+@pytest.mark.parametrize("act", [0, 1])
+@pytest.mark.parametrize("case", [(300, 26, 16, 200, 100), (2500, 12, 16, 40, 20), (33, 22, 32, 256, 128)], ids=str)
+def test_cin_tc_backward_dx_writes_the_dy_rows_of_the_layer_below(case, act):
+    """xdfm_cin_bwd_dx_tc_dy: instead of fp32 dXk the kernel writes act'(X^{k-1}) * dXk as bf16 into the hidden-half channels of the
+    dY rows of the layer below (what cin_dy_rows_cols would have computed from dXk), and xdfm_cin_dy_rows_cols (dnext = NULL,
+    pitch -1) completes the direct-connect channels around it."""
+    from deepctr import _native as Nv
+    L = Nv.lib()
+    B, m, D, H, Hp = case
+    g = torch.Generator().manual_seed(sum(case) + 7)
+    r8 = lambda v: (v + 7) // 8 * 8
+    r16 = lambda v: (v + 15) // 16 * 16
+    Hprev = 2 * Hp                                      # the layer below: split_half, hidden half = its first Hp channels
+    x0 = torch.randn(B, m, D, generator=g) * 0.5
+    yprev = torch.randn(B, Hprev, D, generator=g) * 0.5
+    W = torch.randn(H, Hp * m, generator=g) / (Hp * m) ** 0.5
+    dy = torch.randn(B, H, D, generator=g)
+    x0t, xkt, dyt = to_rows(x0.to(DEV), r8(m)), to_rows(yprev.to(DEV), r8(Hprev)), to_rows(dy.to(DEV), r8(H))
+    Wd = W.to(DEV)
+    wt = torch.empty(L.xdfm_cin_bwd_dx_tc_wt_elems(m, Hp, H, D), dtype=torch.bfloat16, device=DEV)
+    HpQ, mP, Hsp = r16(Hp), r8(m), r8(Hprev)
+    R = B * D
+    dxk = torch.empty((R, HpQ), device=DEV)
+    dx0a = torch.empty((2, R, mP), device=DEV)
+    dx0b = torch.empty((2, R, mP), device=DEV)
+    dy_prev = torch.full((R, Hsp), 7.0, dtype=torch.bfloat16, device=DEV)
+    Nv.check(L.xdfm_cin_bwd_dx_tc(Nv.ptr(dyt), Nv.ptr(x0t), Nv.ptr(xkt), Hsp, Nv.ptr(Wd), Nv.ptr(wt), B, m, Hp, H, D, Nv.ptr(dxk),
+                                  Nv.ptr(dx0a), Nv.stream_ptr()))
+    Nv.check(L.xdfm_cin_bwd_dx_tc_dy(Nv.ptr(dyt), Nv.ptr(x0t), Nv.ptr(xkt), Hsp, Nv.ptr(Wd), Nv.ptr(wt), B, m, Hp, H, D, None,
+                                     Nv.ptr(dx0b), Nv.ptr(dy_prev), Hsp, act, Nv.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(dx0a, dx0b)
+    want = dxk[:, :Hp]
+    if act == 1:
+        want = torch.where(xkt[:, :Hp].float() > 0, want, torch.zeros_like(want))
+    assert torch.equal(dy_prev[:, :Hp], want.to(torch.bfloat16))
+    assert bool((dy_prev[:, HpQ:] == 7.0).all())                          # nothing past HpQ is touched
+    # the dY kernel of the layer below, two ways: from fp32 dXk, and around the rows the dX kernel wrote
+    Hpad = r16(Hprev)
+    fm, col_off, db = Hprev - Hp + 5, 3, Hp
+    dpooled = torch.randn(B, fm, generator=g).to(DEV)
+    out = []
+    for ready in (False, True):
+        d_rows = dy_prev.clone() if ready else torch.empty((R, Hsp), dtype=torch.bfloat16, device=DEV)
+        d_cols = torch.empty((Hpad, R), dtype=torch.bfloat16, device=DEV)
+        Nv.check(L.xdfm_cin_dy_rows_cols(Nv.ptr(xkt), B, D, Hprev, Hsp, Hpad, db, Nv.ptr(dpooled), None, fm, col_off,
+                                         None if ready else Nv.ptr(dxk), -1 if ready else HpQ, Hp, act, Nv.ptr(d_rows), Nv.ptr(d_cols),
+                                         Nv.stream_ptr()))
+        out.append((d_rows, d_cols))
+    torch.cuda.synchronize()
+    assert torch.equal(out[0][0][:, :Hprev], out[1][0][:, :Hprev])
+    assert torch.equal(out[0][1][:Hprev], out[1][1][:Hprev])
+
+
 def test_cin_dy_rows():
     from deepctr import _native as Nv
     L = Nv.lib()

@@ -69,8 +69,21 @@ extern "C" void xdfm_cin_dx_set_debug(int v) { g_cin_dx_debug = v; }
 
 // dyt [B*D, Hs] bf16; x0t [B*D, mP] bf16; xkt rows (pitch xk_pitch) bf16; W fp32 [H, Hp*m]; wt = bf16 scratch
 // [xdfm_cin_bwd_dx_tc_wt_elems]; dxk [B*D, HpQ] fp32 out (HpQ = Hp rounded up to 16); dx0 [2, B*D, mP] fp32 out (two planes).
+extern "C" int xdfm_cin_bwd_dx_tc_dy(const void* dyt, const void* x0t, const void* xkt, int64_t xk_pitch, const float* W, void* wt,
+                                     int64_t B, int m, int Hp, int H, int D, float* dxk, float* dx0, void* dy_prev, int64_t dy_pitch,
+                                     int act, void* stream);
+
 extern "C" int xdfm_cin_bwd_dx_tc(const void* dyt, const void* x0t, const void* xkt, int64_t xk_pitch, const float* W, void* wt,
                                   int64_t B, int m, int Hp, int H, int D, float* dxk, float* dx0, void* stream) {
+  return xdfm_cin_bwd_dx_tc_dy(dyt, x0t, xkt, xk_pitch, W, wt, B, m, Hp, H, D, dxk, dx0, nullptr, 0, XDFM_ACT_NONE, stream);
+}
+
+// As xdfm_cin_bwd_dx_tc; when dy_prev != NULL the kernel writes the dY rows of the layer below instead of dxk (dxk may be NULL):
+// dy_prev[r, i] = act'(xkt[r, i]) * dXk[r, i] for i < HpQ, bf16, row pitch dy_pitch (>= HpQ, multiple of 8) -- valid when the layer
+// below feeds ONLY this layer through those channels (split_half: channels [0, Hp) are the hidden half); act = XDFM_ACT_RELU / NONE.
+extern "C" int xdfm_cin_bwd_dx_tc_dy(const void* dyt, const void* x0t, const void* xkt, int64_t xk_pitch, const float* W, void* wt,
+                                     int64_t B, int m, int Hp, int H, int D, float* dxk, float* dx0, void* dy_prev, int64_t dy_pitch,
+                                     int act, void* stream) {
   CinDxGeom g;
   int rc = cin_dx_geom(m, Hp, H, D, &g);
   if (rc) return rc;
@@ -78,6 +91,10 @@ extern "C" int xdfm_cin_bwd_dx_tc(const void* dyt, const void* x0t, const void* 
   XDFM_CHECK_ARG(((uintptr_t)dyt % 16 == 0) && ((uintptr_t)x0t % 16 == 0) && ((uintptr_t)xkt % 16 == 0) && xk_pitch % 8 == 0 &&
                      ((uintptr_t)dxk % 16 == 0) && ((uintptr_t)dx0 % 16 == 0),
                  "cin_bwd_dx_tc: operands must be 16-byte aligned and xk_pitch a multiple of 8");
+  XDFM_CHECK_ARG(dy_prev != nullptr || dxk != nullptr, "cin_bwd_dx_tc: neither dxk nor dy_prev given");
+  XDFM_CHECK_ARG(dy_prev == nullptr || (((uintptr_t)dy_prev % 16 == 0) && dy_pitch % 8 == 0 && dy_pitch >= g.HpQ &&
+                                         (act == XDFM_ACT_RELU || act == XDFM_ACT_NONE)),
+                 "cin_bwd_dx_tc: dy_prev must be 16-byte aligned with a pitch >= HpQ (multiple of 8) and a ReLU / linear activation");
   cudaStream_t st = (cudaStream_t)stream;
   {
     int64_t total = (int64_t)m * g.HpQ * g.HC;
@@ -90,6 +107,7 @@ extern "C" int xdfm_cin_bwd_dx_tc(const void* dyt, const void* x0t, const void* 
   CinDxParams p = {};
   p.n_full = g.n_full; p.tail_ks = g.tail_ks;
   p.dyt = (const __nv_bfloat16*)dyt; p.x0t = (const __nv_bfloat16*)x0t; p.xkt = (const __nv_bfloat16*)xkt; p.dxk = dxk; p.dx0 = dx0;
+  p.dyp = (__nv_bfloat16*)dy_prev; p.dy_pitch = dy_pitch; p.dy_relu = act == XDFM_ACT_RELU ? 1 : 0;
   p.R = R; p.xk_pitch = xk_pitch; p.m = m; p.mP = g.mP; p.Hp = Hp; p.HpQ = g.HpQ; p.H = H; p.H_pad = g.H_pad; p.Hs = g.Hs;
   p.n_tiles = ceil_div64(R, 128); p.n_hchunks = g.n_hchunks; p.debug = g_cin_dx_debug;
   const int blocks = (int)std::min<int64_t>(p.n_tiles, (int64_t)xdfm_num_sms());

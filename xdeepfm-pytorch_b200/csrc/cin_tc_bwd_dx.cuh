@@ -9,7 +9,10 @@ struct CinDxParams {
   const __nv_bfloat16* dyt;   // [R, Hs]
   const __nv_bfloat16* x0t;   // [R, mP]
   const __nv_bfloat16* xkt;   // rows with pitch xk_pitch, first Hp channels used
-  float* dxk;                 // [R, HpQ] fp32 (overwritten)
+  float* dxk;                 // [R, HpQ] fp32 (overwritten); unused when dyp is set
+  __nv_bfloat16* dyp;         // optional: dY of the layer BELOW, channels [0, HpQ) of rows with pitch dy_pitch = act'(X^{k-1}) * dXk (bf16)
+  int64_t dy_pitch;
+  int dy_relu;                // act' = (X^{k-1} > 0) (ReLU) or 1 (linear)
   float* dx0;                 // [2, R, mP] fp32 (overwritten): one plane per half of the X^{k-1} channels
   int64_t R, xk_pitch;
   int m, mP, Hp, HpQ, H, H_pad, Hs;

@@ -529,6 +529,28 @@ cin_bwd_dx_tc2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
       }
       // ---- tile outputs: plain stores, nothing the next tile has to wait for
       if (valid && !(DBG && (p.debug & 16))) {
+        if (p.dyp != nullptr) {
+          // the layer below needs dY = act'(y) * dXk and y is this layer's X^{k-1}, which sits in registers: write its dY rows (bf16,
+          // hidden-half channels) instead of fp32 dXk -- half the bytes, and the fp32 round trip through the dY kernel is gone
+          uint4* o = reinterpret_cast<uint4*>(p.dyp + row * p.dy_pitch + half * HALF);
+#pragma unroll
+          for (int i8 = 0; i8 < HALF / 8; ++i8) {
+            uint32_t w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float g0, g1, y0, y1;
+              unpack2(dxk[i8 * 4 + u], g0, g1);
+              unpack2(xkf[i8 * 4 + u], y0, y1);
+              if (p.dy_relu) {
+                g0 = y0 > 0.f ? g0 : 0.f;
+                g1 = y1 > 0.f ? g1 : 0.f;
+              }
+              const __nv_bfloat162 t = __floats2bfloat162_rn(g0, g1);
+              w[u] = *reinterpret_cast<const uint32_t*>(&t);
+            }
+            o[i8] = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        } else {
         float* o = p.dxk + row * p.HpQ + half * HALF;
 #pragma unroll
         for (int i = 0; i < HALF / 2; i += 2) {
@@ -536,6 +558,7 @@ cin_bwd_dx_tc2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
           unpack2(dxk[i], f.x, f.y);
           unpack2(dxk[i + 1], f.z, f.w);
           *reinterpret_cast<float4*>(o + 2 * i) = f;
+        }
         }
         // this thread's dX0 partials (its own shared-memory row) -> plane `half` of dx0
         const float* myplane = sDx0 + (size_t)(half * 128 + rl) * dpitch;

@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(256) cin_dy_rows_cols_kernel(const __nv_bfloat
   __shared__ __align__(16) __nv_bfloat16 tile[64][72];       // 144-byte rows: 16-byte aligned granules
   const int64_t r0 = (int64_t)blockIdx.x * 64;
   const int c0 = blockIdx.y * 64;
+  const bool hidden_ready = dnext == nullptr && dnext_pitch < 0;
   {
     const int rr = threadIdx.x >> 2, cg = (threadIdx.x & 3) * 16;
     const int64_t r = r0 + rr;
@@ -190,6 +191,11 @@ __global__ void __launch_bounds__(256) cin_dy_rows_cols_kernel(const __nv_bfloat
         float dn[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) dn[i] = 0.f;
+        // dnext_pitch < 0: the hidden-half channels [0, n_next) of dyt were already written by the dX kernel of the layer above
+        // (xdfm_cin_bwd_dx_tc_dy); they are taken over as they are, the direct-connect channels are computed as usual
+        uint4 old8 = make_uint4(0u, 0u, 0u, 0u);
+        if (hidden_ready && h0 < n_next) old8 = *reinterpret_cast<const uint4*>(dyt + r * Hs + h0);
+        const __nv_bfloat16* oldb = reinterpret_cast<const __nv_bfloat16*>(&old8);
         if (dnext != nullptr && h0 < n_next) {
           const float* dsrc = dnext + r * dnext_pitch + h0;
           if (h0 + 8 <= n_next && (dnext_pitch & 3) == 0) {
@@ -227,6 +233,7 @@ __global__ void __launch_bounds__(256) cin_dy_rows_cols_kernel(const __nv_bfloat
             }
             v += dn[i];
             if (act == XDFM_ACT_RELU && !(__bfloat162float(yb[i]) > 0.f)) v = 0.f;
+            if (hidden_ready && h < n_next) v = __bfloat162float(oldb[i]);       // exact: re-rounded to the same bf16 below
           }
           g[i] = v;
         }
@@ -237,7 +244,7 @@ __global__ void __launch_bounds__(256) cin_dy_rows_cols_kernel(const __nv_bfloat
       o.x = *reinterpret_cast<uint32_t*>(&t0); o.y = *reinterpret_cast<uint32_t*>(&t1);
       o.z = *reinterpret_cast<uint32_t*>(&t2); o.w = *reinterpret_cast<uint32_t*>(&t3);
       *reinterpret_cast<uint4*>(&tile[rr][cg + g8 * 8]) = o;
-      if (r < R && h0 < Hs) *reinterpret_cast<uint4*>(dyt + r * Hs + h0) = o;
+      if (r < R && h0 < Hs && !(hidden_ready && h0 + 8 <= n_next)) *reinterpret_cast<uint4*>(dyt + r * Hs + h0) = o;
     }
   }
   __syncthreads();

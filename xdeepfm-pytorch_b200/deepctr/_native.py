@@ -62,6 +62,7 @@ _SIGS = {
     "xdfm_add_rows_f32": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, _P]),
     "xdfm_cin_bwd_dx_tc_wt_elems": (c_int64, [c_int, c_int, c_int, c_int]),
     "xdfm_cin_bwd_dx_tc": (c_int, [_P, _P, _P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "xdfm_cin_bwd_dx_tc_dy": (c_int, [_P, _P, _P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, c_int64, c_int, _P]),
     "xdfm_rows_to_cols_bf16": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, _P]),
     "xdfm_cin_bwd_dw_tc_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int, c_int]),
     "xdfm_cin_bwd_dw_tc": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, c_int64, _P]),

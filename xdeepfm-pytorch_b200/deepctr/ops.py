@@ -479,19 +479,22 @@ class CINFunctionTC(torch.autograd.Function):
         dx0_parts = torch.empty((n_layers, 2, R, mP), dtype=torch.float32, device=dev)   # per layer: one dX0 plane per channel half
         grads = [None] * len(wb)
         dnext, dnext_pitch = None, 0
+        dyt_ready = None        # dY rows of the layer about to be processed whose hidden half the dX kernel above has already written
         for k in range(len(cfg.layer_size) - 1, -1, -1):
             H, Hp = cfg.layer_size[k], cfg.Hp[k]
             Hs, H_pad, HpQ = _r8(H), _r16(H), _r16(Hp)
             yt = yts[k]
             xkt = x0t if k == 0 else yts[k - 1]
-            dyt = torch.empty_like(yt)
+            dyt = torch.empty_like(yt) if dyt_ready is None else dyt_ready
             dyT = torch.empty((H_pad, R), dtype=torch.bfloat16, device=dev)
             reuse_x0T = k == 0 and HpQ == mP        # layer 0: X^{k-1} is X^0 itself and the channel-major copy already exists
             xkT = x0T if reuse_x0T else torch.empty((HpQ, R), dtype=torch.bfloat16, device=dev)
             with timed("cin_layout"):
+                # (dnext = None with pitch -1: the hidden half of dyt is already there)
                 N.check(L.xdfm_cin_dy_rows_cols(N.ptr(yt), B, D, H, Hs, H_pad, cfg.direct_begin[k], N.ptr(dout) if cfg.pool else None,
-                                                None if cfg.pool else N.ptr(dout), cfg.fm, cfg.col_off[k], N.ptr(dnext), dnext_pitch,
-                                                cfg.n_next[k], cfg.act, N.ptr(dyt), N.ptr(dyT), st))
+                                                None if cfg.pool else N.ptr(dout), cfg.fm, cfg.col_off[k], N.ptr(dnext),
+                                                -1 if dyt_ready is not None else dnext_pitch, cfg.n_next[k], cfg.act, N.ptr(dyt),
+                                                N.ptr(dyT), st))
                 if not reuse_x0T:
                     N.check(L.xdfm_rows_to_cols_bf16(N.ptr(xkt), xkt.shape[1], R, Hp, HpQ, N.ptr(xkT), st))
             W = _f32c(wb[2 * k]).view(H, -1)
@@ -506,10 +509,22 @@ class CINFunctionTC(torch.autograd.Function):
                                              ws.numel(), st))
             nwt = L.xdfm_cin_bwd_dx_tc_wt_elems(m, Hp, H, D)
             wt = workspace("cin_wt", nwt * 2, dev)
-            dxk = torch.empty((R, HpQ), dtype=torch.float32, device=dev)
-            with timed("cin_bwd"):
-                N.check(L.xdfm_cin_bwd_dx_tc(N.ptr(dyt), N.ptr(x0t), N.ptr(xkt), xkt.shape[1], N.ptr(W), N.ptr(wt), B, m, Hp, H, D,
-                                             N.ptr(dxk), N.ptr(dx0_parts[k]), st))
+            # the layer below gets its dY rows straight from this layer's dX kernel when its hidden half feeds only this layer
+            # (split_half: channels [0, Hp) of y_{k-1}; direct-connect channels start at or after Hp) and the rows are wide enough
+            fuse_dy = (k > 0 and cfg.n_next[k - 1] == Hp and cfg.direct_begin[k - 1] >= Hp and HpQ <= _r8(cfg.layer_size[k - 1])
+                       and cfg.act in (N.ACT["relu"], N.ACT["linear"]))
+            if fuse_dy:
+                dyt_ready = torch.empty_like(yts[k - 1])
+                dxk = None
+                with timed("cin_bwd"):
+                    N.check(L.xdfm_cin_bwd_dx_tc_dy(N.ptr(dyt), N.ptr(x0t), N.ptr(xkt), xkt.shape[1], N.ptr(W), N.ptr(wt), B, m, Hp, H, D,
+                                                    None, N.ptr(dx0_parts[k]), N.ptr(dyt_ready), dyt_ready.shape[1], cfg.act, st))
+            else:
+                dyt_ready = None
+                dxk = torch.empty((R, HpQ), dtype=torch.float32, device=dev)
+                with timed("cin_bwd"):
+                    N.check(L.xdfm_cin_bwd_dx_tc(N.ptr(dyt), N.ptr(x0t), N.ptr(xkt), xkt.shape[1], N.ptr(W), N.ptr(wt), B, m, Hp, H, D,
+                                                 N.ptr(dxk), N.ptr(dx0_parts[k]), st))
             grads[2 * k] = dW.view(wb[2 * k].shape)
             grads[2 * k + 1] = db
             dnext, dnext_pitch = dxk, HpQ
