@@ -241,6 +241,13 @@ int64_t xdfm_gemm_tc_workspace_bytes(int M, int N, int K);
 int xdfm_gemm_tc(int M, int N, int K, const void* A, int64_t lda, const void* Bm, int64_t ldb, float* C, int ldc, const float* bias,
                  int act, void* workspace, int64_t workspace_bytes, void* stream);
 int xdfm_cvt_bf16(const float* src, int R, int C, int64_t ld, int transpose, void* dst, int64_t dst_pitch, void* stream);
+/* One pass for every bf16 operand of a dense layer's tensor-core GEMMs: g = src * act'(y) (y = NULL: g = src; fp32 [R, C], row pitch
+ * ld for both), dst [R, dst_pitch] = bf16(g), dstT [C, dstT_pitch] = bf16(g)^T, colsum[c] = sum_r g[r, c] (fixed order; needs a
+ * workspace of xdfm_cvt_bf16_both_workspace_bytes).  dst / dstT / colsum may each be NULL; pitches are multiples of 8, padding is zero.
+ * Replaces torch autograd's ReLU-backward + the bias gradient sum of deepctr/layers/core.py:DNN together with the operand copies. */
+int64_t xdfm_cvt_bf16_both_workspace_bytes(int R, int C);
+int xdfm_cvt_bf16_both(const float* src, const float* y, int act, int R, int C, int64_t ld, void* dst, int64_t dst_pitch, void* dstT,
+                       int64_t dstT_pitch, float* colsum, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- field self-attention block over the CIN feature maps (deepctr/layers/cin_attention.py).
  * q/k/v/o/dout [B, L, E] fp32 (E = heads * head_dim, head_dim <= 32); lse [B, heads, L] = log2-sum-exp2 of the scaled scores.

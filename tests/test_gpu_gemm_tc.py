@@ -58,3 +58,39 @@ def test_linear_act_bf16_forward_backward(B, K, Nn, act):
     tol = 2e-2          # stated bf16 tolerance (operands rounded to 8 mantissa bits), relative to each tensor's scale
     for got, want, what in ((out, ref, "y"), (xg.grad, xd.grad, "dx"), (Wg.grad, Wd.grad, "dW"), (bg.grad, bd.grad, "db")):
         assert_close(got, want, tol, tol * want.abs().max().item(), what)
+
+
+@pytest.mark.parametrize("act", ["linear", "relu", "tanh", "sigmoid"])
+@pytest.mark.parametrize("R,C", [(8192, 400), (100, 37), (64, 64), (1, 8), (333, 429), (4096, 1)])
+def test_cvt_bf16_both_one_pass_for_every_operand(R, C, act):
+    """xdfm_cvt_bf16_both: g = dy * act'(y) in one pass -> bf16 rows, bf16 transposed copy, fp32 column sums (the bias gradient);
+    compared with the separate act_bwd / cvt_bf16 / wcolsum results it replaces."""
+    from deepctr import ops, _native as Nv
+    g = torch.Generator().manual_seed(R * 7 + C)
+    dy = torch.randn(R, C, generator=g).to(DEV)
+    y = torch.randn(R, C, generator=g).to(DEV)
+    if act == "sigmoid":
+        y = torch.sigmoid(y)
+    a = Nv.ACT[act]
+    rows, cols, colsum = ops.cvt_bf16_both(dy, True, True, y=None if a == 0 else y, act=a, want_colsum=True)
+    torch.cuda.synchronize()
+    if act == "linear":
+        want = dy
+    elif act == "relu":
+        want = torch.where(y > 0, dy, torch.zeros_like(dy))
+    elif act == "tanh":
+        want = dy * (1 - y * y)
+    else:
+        want = dy * y * (1 - y)
+    C8, R8 = (C + 7) // 8 * 8, (R + 7) // 8 * 8
+    assert rows.shape == (R, C8) and cols.shape == (C, R8)
+    if act in ("linear", "relu"):          # the same fp32 value rounded once: bit-exact
+        assert torch.equal(rows[:, :C], want.to(torch.bfloat16))
+    else:                                  # the kernel may contract dy * (1 - y * y) differently: one bf16 ulp
+        assert_close(rows[:, :C].float(), want, 2.0 ** -7, 1e-30, "rows")
+    assert torch.equal(cols[:, :R], rows[:, :C].t())          # both copies hold the same bf16 values
+    assert bool((rows[:, C:] == 0).all()) and bool((cols[:, R:] == 0).all())
+    assert_close(colsum, want.double().sum(0), 1e-5, 1e-5 * max(1.0, float(want.abs().sum(0).max())), "colsum")
+    # no outputs requested individually
+    r2, c2, s2 = ops.cvt_bf16_both(dy, True, False)
+    assert c2 is None and s2 is None and torch.equal(r2[:, :C], dy.to(torch.bfloat16))

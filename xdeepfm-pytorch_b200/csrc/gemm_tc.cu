@@ -270,3 +270,138 @@ extern "C" int xdfm_cvt_bf16(const float* src, int R, int C, int64_t ld, int tra
   XDFM_LAUNCH_CHECK();
   return XDFM_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// One pass that produces every bf16 operand a dense layer's tensor-core GEMMs need from an fp32 matrix:
+//     g[r, c]   = src[r, c] * act'(y[r, c])          (y = NULL or act = NONE: g = src)
+//     dst [R, dst_pitch]   = bf16(g)                  (row-major: A operand of  g . W)
+//     dstT[C, dstT_pitch]  = bf16(g)^T                (A operand of  g^T . x)
+//     colsum[c]            = sum_r g[r, c]            (fp32, fixed order: per 64-row tile, then over the tiles -- the bias gradient)
+// Any of dst / dstT / colsum may be NULL.  Replaces act_bwd + cvt_bf16 + cvt_bf16(transpose) + wcolsum (four passes over the
+// matrix, five launches) in the backward of a dense layer, and cvt_bf16 + cvt_bf16(transpose) in its forward.  64 x 64 tiles
+// through shared memory: both outputs are written in 16- / 32-byte runs.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cvt_bf16_both_kernel(const float* __restrict__ src, const float* __restrict__ y, int act, int R, int C,
+                                                            int64_t ld, __nv_bfloat16* __restrict__ dst, int64_t dpitch,
+                                                            __nv_bfloat16* __restrict__ dstT, int64_t tpitch, float* __restrict__ part) {
+  __shared__ float tile[64][65];
+  __shared__ float psum[4][64];
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  {
+    // 16 threads per row (one float4 each: 256 contiguous bytes), 16 rows per pass
+    const int c4 = (threadIdx.x & 15) * 4;
+    const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
+                     (y == nullptr || (reinterpret_cast<uintptr_t>(y) & 15) == 0);
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+      const int rr = (threadIdx.x >> 4) + pass * 16;
+      const int r = r0 + rr, c = c0 + c4;
+      float g[4] = {0.f, 0.f, 0.f, 0.f}, yv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (r < R && c < C) {
+        if (vec && c + 4 <= C) {
+          const float4 t = *reinterpret_cast<const float4*>(src + (int64_t)r * ld + c);
+          g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
+          if (y != nullptr) {
+            const float4 u = *reinterpret_cast<const float4*>(y + (int64_t)r * ld + c);
+            yv[0] = u.x; yv[1] = u.y; yv[2] = u.z; yv[3] = u.w;
+          }
+        } else {
+          for (int i = 0; i < 4; ++i)
+            if (c + i < C) {
+              g[i] = src[(int64_t)r * ld + c + i];
+              if (y != nullptr) yv[i] = y[(int64_t)r * ld + c + i];
+            }
+        }
+        if (y != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (act == XDFM_ACT_RELU) g[i] = yv[i] > 0.f ? g[i] : 0.f;
+            else if (act == XDFM_ACT_TANH) g[i] = g[i] * (1.f - yv[i] * yv[i]);
+            else if (act == XDFM_ACT_SIGMOID) g[i] = g[i] * yv[i] * (1.f - yv[i]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tile[rr][c4 + i] = g[i];
+      if (dst != nullptr && r < R && c < dpitch) {       // pitch is a multiple of 8: the four columns never straddle it
+        const __nv_bfloat162 t0 = __floats2bfloat162_rn(g[0], g[1]), t1 = __floats2bfloat162_rn(g[2], g[3]);
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&t0);
+        o.y = *reinterpret_cast<const uint32_t*>(&t1);
+        *reinterpret_cast<uint2*>(dst + (int64_t)r * dpitch + c) = o;
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const int cc = threadIdx.x & 63, rg = (threadIdx.x >> 6) * 16;
+    const int c = c0 + cc;
+    float s = 0.f;
+    __align__(16) __nv_bfloat16 col[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float v = tile[rg + i][cc];
+      s += v;
+      col[i] = __float2bfloat16(v);
+    }
+    psum[threadIdx.x >> 6][cc] = s;
+    if (dstT != nullptr && c < C) {
+      const int r = r0 + rg;
+      __nv_bfloat16* d = dstT + (int64_t)c * tpitch + r;
+      if (r + 16 <= tpitch && (tpitch & 7) == 0 && ((reinterpret_cast<uintptr_t>(dstT) & 15) == 0)) {
+        *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(&col[0]);
+        *reinterpret_cast<uint4*>(d + 8) = *reinterpret_cast<const uint4*>(&col[8]);
+      } else {
+        for (int i = 0; i < 16; ++i)
+          if (r + i < tpitch) d[i] = col[i];
+      }
+    }
+  }
+  if (part != nullptr) {
+    __syncthreads();
+    if (threadIdx.x < 64 && c0 + threadIdx.x < C)
+      part[(int64_t)blockIdx.x * C + c0 + threadIdx.x] =
+          (psum[0][threadIdx.x] + psum[1][threadIdx.x]) + (psum[2][threadIdx.x] + psum[3][threadIdx.x]);
+  }
+}
+
+__global__ void colsum_tiles_kernel(const float* __restrict__ part, int n_tiles, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int t = 0;
+  for (; t + 4 <= n_tiles; t += 4) {
+    a0 += part[(int64_t)t * C + c];
+    a1 += part[(int64_t)(t + 1) * C + c];
+    a2 += part[(int64_t)(t + 2) * C + c];
+    a3 += part[(int64_t)(t + 3) * C + c];
+  }
+  for (; t < n_tiles; ++t) a0 += part[(int64_t)t * C + c];
+  out[c] = (a0 + a1) + (a2 + a3);
+}
+
+extern "C" int64_t xdfm_cvt_bf16_both_workspace_bytes(int R, int C) { return (int64_t)((R + 63) / 64) * C * 4; }
+
+extern "C" int xdfm_cvt_bf16_both(const float* src, const float* y, int act, int R, int C, int64_t ld, void* dst, int64_t dst_pitch,
+                                  void* dstT, int64_t dstT_pitch, float* colsum, void* workspace, int64_t workspace_bytes, void* stream) {
+  XDFM_CHECK_ARG(R >= 0 && C >= 1 && ld >= C, "cvt_bf16_both: bad shape R=%d C=%d ld=%lld", R, C, (long long)ld);
+  XDFM_CHECK_ARG(dst == nullptr || (dst_pitch % 8 == 0 && dst_pitch >= C), "cvt_bf16_both: dst_pitch=%lld", (long long)dst_pitch);
+  XDFM_CHECK_ARG(dstT == nullptr || (dstT_pitch % 8 == 0 && dstT_pitch >= R), "cvt_bf16_both: dstT_pitch=%lld", (long long)dstT_pitch);
+  XDFM_CHECK_ARG(colsum == nullptr || (workspace != nullptr && workspace_bytes >= xdfm_cvt_bf16_both_workspace_bytes(R, C)),
+                 "cvt_bf16_both: workspace too small for the column sums");
+  if (R == 0) return XDFM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  // the tile grid covers the padding of both outputs (zeros)
+  const int64_t cover_r = std::max<int64_t>(R, dstT != nullptr ? dstT_pitch : 0);
+  const int64_t cover_c = std::max<int64_t>(C, dst != nullptr ? dst_pitch : 0);
+  dim3 grid((unsigned)ceil_div64(cover_r, 64), (unsigned)ceil_div64(cover_c, 64));
+  cvt_bf16_both_kernel<<<grid, 256, 0, st>>>(src, y, act, R, C, ld, (__nv_bfloat16*)dst, dst_pitch, (__nv_bfloat16*)dstT, dstT_pitch,
+                                             colsum != nullptr ? (float*)workspace : nullptr);
+  XDFM_LAUNCH_CHECK();
+  if (colsum != nullptr) {
+    colsum_tiles_kernel<<<(unsigned)ceil_div64(C, 128), 128, 0, st>>>((const float*)workspace, (R + 63) / 64, C, colsum);
+    XDFM_LAUNCH_CHECK();
+  }
+  return XDFM_OK;
+}

@@ -625,8 +625,29 @@ def gemm_tc(A, Bm, M, Nn, K, bias=None, act=0):
     return C
 
 
+def cvt_bf16_both(src, want_rows=True, want_cols=True, y=None, act=0, want_colsum=False):
+    """One pass over fp32 [R, C]: g = src * act'(y) -> (bf16 [R, C8] or None, bf16 [C, R8] or None, fp32 column sums [C] or None)."""
+    R, C = src.shape
+    require_cuda(src, "cvt_bf16_both")
+    src = _f32c(src)
+    dev = src.device
+    L = N.lib()
+    rows = torch.empty((R, _r8(C)), dtype=torch.bfloat16, device=dev) if want_rows else None
+    cols = torch.empty((C, _r8(R)), dtype=torch.bfloat16, device=dev) if want_cols else None
+    colsum = torch.empty(C, dtype=torch.float32, device=dev) if want_colsum else None
+    ws = workspace("cvt_both", L.xdfm_cvt_bf16_both_workspace_bytes(R, C), dev) if want_colsum else None
+    N.check(L.xdfm_cvt_bf16_both(N.ptr(src), N.ptr(y), int(act), R, C, C, N.ptr(rows), 0 if rows is None else rows.shape[1], N.ptr(cols),
+                                 0 if cols is None else cols.shape[1], N.ptr(colsum), N.ptr(ws), 0 if ws is None else ws.numel(),
+                                 N.stream_ptr()))
+    return rows, cols, colsum
+
+
 class LinearActTC(torch.autograd.Function):
-    """y = act(x @ W.T + b) with bf16 operands on the tensor cores (fp32 accumulate, fp32 activations in HBM)."""
+    """y = act(x @ W.T + b) with bf16 operands on the tensor cores (fp32 accumulate, fp32 activations in HBM).
+
+    Every bf16 operand comes out of ONE pass over its fp32 source (xdfm_cvt_bf16_both): the forward converts x and W once for both
+    GEMM orientations (row-major for this GEMM, transposed for the backward's), the backward folds act'(y), both copies of dY and
+    the bias gradient into one pass."""
 
     @staticmethod
     def forward(ctx, x, W, b, act):
@@ -636,38 +657,28 @@ class LinearActTC(torch.autograd.Function):
         W = _f32c(W)
         Bn, K = x2.shape
         Nn = W.shape[0]
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         with timed("gemm_cvt"):
-            xb, wb = cvt_bf16(x2), cvt_bf16(W)
+            xb, xT, _ = cvt_bf16_both(x2, True, need_dw)                 # [Bn, K8], [K, Bn8] (for dW = dY^T . x)
+            wb, wT, _ = cvt_bf16_both(W, True, need_dx)                  # [Nn, K8], [K, Nn8] (for dX = dY . W)
         y = gemm_tc(xb, wb, Bn, Nn, K, None if b is None else _f32c(b), act)
-        ctx.save_for_backward(x2, W, y)
-        ctx.act, ctx.has_bias, ctx.shp = act, b is not None, shp
+        ctx.save_for_backward(xT, wT, y if act != 0 else None)
+        ctx.act, ctx.has_bias, ctx.shp, ctx.dims = act, b is not None, shp, (Bn, K, Nn)
         return y.view(*shp[:-1], Nn)
 
     @staticmethod
     def backward(ctx, dy):
-        x2, W, y = ctx.saved_tensors
-        Bn, K = x2.shape
-        Nn = W.shape[0]
+        xT, wT, y = ctx.saved_tensors
+        Bn, K, Nn = ctx.dims
         dy = _f32c(dy).reshape(Bn, Nn)
-        L = N.lib()
-        if ctx.act != 0:
-            dym = torch.empty_like(dy)
-            N.check(L.xdfm_act_bwd(N.ptr(dy), N.ptr(y), N.ptr(dym), dy.numel(), ctx.act, N.stream_ptr()))
-        else:
-            dym = dy
-        dx = dW = db = None
-        if ctx.needs_input_grad[0]:
-            with timed("gemm_cvt"):
-                dyb, wT = cvt_bf16(dym), cvt_bf16(W, transpose=True)             # [Bn, Nn], [K, Nn]
+        need_dx, need_dw, need_db = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        with timed("gemm_cvt"):
+            dyb, dyT, db = cvt_bf16_both(dy, need_dx, need_dw, y=y, act=ctx.act, want_colsum=need_db)
+        dx = dW = None
+        if need_dx:
             dx = gemm_tc(dyb, wT, Bn, K, Nn).view(ctx.shp)
-        if ctx.needs_input_grad[1]:
-            with timed("gemm_cvt"):
-                dyT, xT = cvt_bf16(dym, transpose=True), cvt_bf16(x2, transpose=True)   # [Nn, Bn], [K, Bn]
+        if need_dw:
             dW = gemm_tc(dyT, xT, Nn, K, Bn)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = torch.empty(Nn, dtype=torch.float32, device=dy.device)
-            ws = workspace("wcolsum", L.xdfm_wcolsum_workspace_bytes(Nn), dy.device)
-            N.check(L.xdfm_wcolsum(N.ptr(dym), Bn, Nn, Nn, None, N.ptr(db), 0, N.ptr(ws), ws.numel(), N.stream_ptr()))
         return dx, dW, db, None
 
 
