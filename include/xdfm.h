@@ -191,6 +191,12 @@ int xdfm_cin_dy_rows(const void* yt, int64_t B, int D, int H, int Hs, int direct
 int xdfm_cin_dy_rows_cols(const void* yt, int64_t B, int D, int H, int Hs, int H_pad, int direct_begin, const float* dpooled,
                           const float* dmaps, int fm_total, int col_off, const float* dnext, int64_t dnext_pitch, int n_next, int act,
                           void* dyt, void* dyT, void* stream);
+/* As xdfm_cin_dy_rows_cols; db != NULL also returns the layer's bias gradient db[h] = sum_r dY[r, h] (per-tile partial sums in
+ * `workspace`, xdfm_cin_dy_db_workspace_bytes; fixed order) -- torch autograd's Conv1d bias gradient (interaction.py:224). */
+int64_t xdfm_cin_dy_db_workspace_bytes(int64_t B, int D, int H_pad);
+int xdfm_cin_dy_rows_cols_db(const void* yt, int64_t B, int D, int H, int Hs, int H_pad, int direct_begin, const float* dpooled,
+                             const float* dmaps, int fm_total, int col_off, const float* dnext, int64_t dnext_pitch, int n_next, int act,
+                             void* dyt, void* dyT, float* db, void* workspace, int64_t workspace_bytes, void* stream);
 int xdfm_from_rows_f32(const float* xt, int64_t B, int C, int D, int CP, float* x, int accumulate, void* stream);
 /* x [B, C, D] fp32 = extra[r, c] (NULL = none; row pitch extra_pitch) + the sum of the n_planes planes parts [n_planes, B*D, CP],
  * r = b * D + d: the CIN's dX^0 in the reference layout from the dX kernels' planes and layer 0's dXk */

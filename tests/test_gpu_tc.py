@@ -292,6 +292,17 @@ def test_cin_tc_backward_dx_writes_the_dy_rows_of_the_layer_below(case, act):
     torch.cuda.synchronize()
     assert torch.equal(out[0][0][:, :Hprev], out[1][0][:, :Hprev])
     assert torch.equal(out[0][1][:Hprev], out[1][1][:Hprev])
+    # the same kernel also returns the bias gradient: column sums of the bf16 dY it wrote
+    d_rows = dy_prev.clone()
+    d_cols = torch.empty((Hpad, R), dtype=torch.bfloat16, device=DEV)
+    dbias = torch.full((Hprev,), float("nan"), device=DEV)
+    ws = torch.empty(L.xdfm_cin_dy_db_workspace_bytes(B, D, Hpad), dtype=torch.uint8, device=DEV)
+    Nv.check(L.xdfm_cin_dy_rows_cols_db(Nv.ptr(xkt), B, D, Hprev, Hsp, Hpad, db, Nv.ptr(dpooled), None, fm, col_off, None, -1, Hp, act,
+                                        Nv.ptr(d_rows), Nv.ptr(d_cols), Nv.ptr(dbias), Nv.ptr(ws), ws.numel(), Nv.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(d_cols[:Hprev], out[1][1][:Hprev])
+    want_db = d_cols[:Hprev].double().sum(1)
+    assert_close(dbias, want_db, 1e-5, 1e-5 * float(d_cols[:Hprev].double().abs().sum(1).max()), "db")
 
 
 def test_cin_dy_rows():

@@ -168,8 +168,9 @@ __global__ void __launch_bounds__(256) cin_dy_rows_cols_kernel(const __nv_bfloat
                                                                int hdb, const float* __restrict__ dpooled, const float* __restrict__ dmaps,
                                                                int fm_total, int col_off, const float* __restrict__ dnext,
                                                                int64_t dnext_pitch, int n_next, int act, __nv_bfloat16* __restrict__ dyt,
-                                                               __nv_bfloat16* __restrict__ dyT) {
+                                                               __nv_bfloat16* __restrict__ dyT, float* __restrict__ part) {
   __shared__ __align__(16) __nv_bfloat16 tile[64][72];       // 144-byte rows: 16-byte aligned granules
+  __shared__ float psum[4][64];                              // bias gradient: column sums of this tile's four 16-row groups
   const int64_t r0 = (int64_t)blockIdx.x * 64;
   const int c0 = blockIdx.y * 64;
   const bool hidden_ready = dnext == nullptr && dnext_pitch < 0;
@@ -256,6 +257,12 @@ __global__ void __launch_bounds__(256) cin_dy_rows_cols_kernel(const __nv_bfloat
       __align__(16) __nv_bfloat16 col[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) col[i] = tile[rg + i][cc];
+      if (part != nullptr) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sacc += __bfloat162float(col[i]);       // rows past R hold zeros
+        psum[threadIdx.x >> 6][cc] = sacc;
+      }
       const int64_t r = r0 + rg;
       __nv_bfloat16* dst = dyT + (int64_t)c * R + r;
       if (r + 16 <= R && ((R & 7) == 0)) {
@@ -267,19 +274,75 @@ __global__ void __launch_bounds__(256) cin_dy_rows_cols_kernel(const __nv_bfloat
       }
     }
   }
+  if (part != nullptr) {
+    __syncthreads();
+    const int c = c0 + (int)threadIdx.x;
+    if (threadIdx.x < 64 && c < H_pad)
+      part[(int64_t)blockIdx.x * H_pad + c] = (psum[0][threadIdx.x] + psum[1][threadIdx.x]) + (psum[2][threadIdx.x] + psum[3][threadIdx.x]);
+  }
 }
+
+// db[h] = sum over the row tiles of the per-tile column sums: 8 channels x 128 tile strides per block; every thread has its (up to)
+// 16 loads in flight at once per pass, adds them in a fixed order, then the 128 strides are added as a tree in shared memory
+__global__ void __launch_bounds__(1024) cin_db_tiles_kernel(const float* __restrict__ part, int64_t n_tiles, int H_pad, int H,
+                                                             float* __restrict__ db) {
+  __shared__ float red[128][9];
+  const int hx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  const int h = blockIdx.x * 8 + hx;
+  float acc = 0.f;
+  if (h < H) {
+    for (int64_t t0 = ty; t0 < n_tiles; t0 += 128 * 16) {
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int64_t t = t0 + (int64_t)i * 128;
+        v[i] = t < n_tiles ? part[t * H_pad + h] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) acc += (v[i] + v[i + 1]) + (v[i + 2] + v[i + 3]);
+    }
+  }
+  red[ty][hx] = acc;
+  __syncthreads();
+  for (int s = 64; s > 0; s >>= 1) {
+    if (ty < s) red[ty][hx] += red[ty + s][hx];
+    __syncthreads();
+  }
+  if (ty == 0 && h < H) db[h] = red[0][hx];
+}
+
+extern "C" int64_t xdfm_cin_dy_db_workspace_bytes(int64_t B, int D, int H_pad) { return ceil_div64(B * (int64_t)D, 64) * H_pad * 4; }
+
+extern "C" int xdfm_cin_dy_rows_cols_db(const void* yt, int64_t B, int D, int H, int Hs, int H_pad, int direct_begin, const float* dpooled,
+                                        const float* dmaps, int fm_total, int col_off, const float* dnext, int64_t dnext_pitch, int n_next,
+                                        int act, void* dyt, void* dyT, float* db, void* workspace, int64_t workspace_bytes, void* stream);
 
 extern "C" int xdfm_cin_dy_rows_cols(const void* yt, int64_t B, int D, int H, int Hs, int H_pad, int direct_begin, const float* dpooled,
                                      const float* dmaps, int fm_total, int col_off, const float* dnext, int64_t dnext_pitch, int n_next,
                                      int act, void* dyt, void* dyT, void* stream) {
+  return xdfm_cin_dy_rows_cols_db(yt, B, D, H, Hs, H_pad, direct_begin, dpooled, dmaps, fm_total, col_off, dnext, dnext_pitch, n_next, act,
+                                  dyt, dyT, nullptr, nullptr, 0, stream);
+}
+
+// As xdfm_cin_dy_rows_cols; db != NULL also produces the layer's bias gradient db[h] = sum_r dY[r, h] (of the bf16 values, fixed
+// order) from per-tile partial sums in `workspace` (xdfm_cin_dy_db_workspace_bytes) -- the separate pass over dyT is gone.
+extern "C" int xdfm_cin_dy_rows_cols_db(const void* yt, int64_t B, int D, int H, int Hs, int H_pad, int direct_begin, const float* dpooled,
+                                     const float* dmaps, int fm_total, int col_off, const float* dnext, int64_t dnext_pitch, int n_next,
+                                        int act, void* dyt, void* dyT, float* db, void* workspace, int64_t workspace_bytes, void* stream) {
   XDFM_CHECK_ARG(Hs % 8 == 0 && Hs >= H && H_pad >= Hs, "cin_dy_rows_cols: Hs=%d (multiple of 8, >= H=%d), H_pad=%d >= Hs", Hs, H, H_pad);
+  XDFM_CHECK_ARG(db == nullptr || (workspace != nullptr && workspace_bytes >= xdfm_cin_dy_db_workspace_bytes(B, D, H_pad)),
+                 "cin_dy_rows_cols: workspace too small for the bias gradient");
   XDFM_CHECK_ARG(act == XDFM_ACT_RELU || act == XDFM_ACT_NONE, "cin_dy_rows_cols: activation %d not supported on the bf16 path", act);
   const int64_t R = B * (int64_t)D;
   if (R == 0) return XDFM_OK;
   dim3 grid((unsigned)ceil_div64(R, 64), (unsigned)ceil_div64(H_pad, 64));
   cin_dy_rows_cols_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)yt, R, D, H, Hs, H_pad, direct_begin, dpooled, dmaps,
                                                                   fm_total, col_off, dnext, dnext_pitch, n_next, act, (__nv_bfloat16*)dyt,
-                                                                  (__nv_bfloat16*)dyT);
+                                                                  (__nv_bfloat16*)dyT, db != nullptr ? (float*)workspace : nullptr);
   XDFM_LAUNCH_CHECK();
+  if (db != nullptr) {
+    cin_db_tiles_kernel<<<(unsigned)ceil_div64(H, 8), 1024, 0, (cudaStream_t)stream>>>((const float*)workspace, ceil_div64(R, 64), H_pad, H, db);
+    XDFM_LAUNCH_CHECK();
+  }
   return XDFM_OK;
 }

@@ -58,6 +58,9 @@ _SIGS = {
     "xdfm_cin_dy_rows": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, _P, c_int64, c_int, c_int, _P, _P]),
     "xdfm_cin_dy_rows_cols": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, _P, c_int64, c_int, c_int, _P, _P,
                                       _P]),
+    "xdfm_cin_dy_db_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
+    "xdfm_cin_dy_rows_cols_db": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, _P, c_int64, c_int, c_int, _P, _P,
+                                         _P, _P, c_int64, _P]),
     "xdfm_from_rows_f32": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, c_int, _P]),
     "xdfm_add_rows_f32": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, _P]),
     "xdfm_cin_bwd_dx_tc_wt_elems": (c_int64, [c_int, c_int, c_int, c_int]),

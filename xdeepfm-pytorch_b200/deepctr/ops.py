@@ -491,22 +491,23 @@ class CINFunctionTC(torch.autograd.Function):
             xkT = x0T if reuse_x0T else torch.empty((HpQ, R), dtype=torch.bfloat16, device=dev)
             with timed("cin_layout"):
                 # (dnext = None with pitch -1: the hidden half of dyt is already there)
-                N.check(L.xdfm_cin_dy_rows_cols(N.ptr(yt), B, D, H, Hs, H_pad, cfg.direct_begin[k], N.ptr(dout) if cfg.pool else None,
-                                                None if cfg.pool else N.ptr(dout), cfg.fm, cfg.col_off[k], N.ptr(dnext),
-                                                -1 if dyt_ready is not None else dnext_pitch, cfg.n_next[k], cfg.act, N.ptr(dyt),
-                                                N.ptr(dyT), st))
+                db = torch.empty(H, dtype=torch.float32, device=dev)
+                dbws = workspace("cin_db_part", L.xdfm_cin_dy_db_workspace_bytes(B, D, H_pad), dev)
+                N.check(L.xdfm_cin_dy_rows_cols_db(N.ptr(yt), B, D, H, Hs, H_pad, cfg.direct_begin[k], N.ptr(dout) if cfg.pool else None,
+                                                   None if cfg.pool else N.ptr(dout), cfg.fm, cfg.col_off[k], N.ptr(dnext),
+                                                   -1 if dyt_ready is not None else dnext_pitch, cfg.n_next[k], cfg.act, N.ptr(dyt),
+                                                   N.ptr(dyT), N.ptr(db), N.ptr(dbws), dbws.numel(), st))
                 if not reuse_x0T:
                     N.check(L.xdfm_rows_to_cols_bf16(N.ptr(xkt), xkt.shape[1], R, Hp, HpQ, N.ptr(xkT), st))
             W = _f32c(wb[2 * k]).view(H, -1)
             dW = torch.empty_like(W)
-            db = torch.empty(H, dtype=torch.float32, device=dev)
             nb = L.xdfm_cin_bwd_dw_tc_workspace_bytes(B, m, Hp, H, D)
             if nb < 0:
                 raise RuntimeError("libxdfm: " + L.xdfm_last_error().decode())
             ws = workspace("cin_dw_part", nb, dev)
             with timed("cin_bwd"):
-                N.check(L.xdfm_cin_bwd_dw_tc(N.ptr(dyT), N.ptr(xkT), N.ptr(x0T), B, m, Hp, H, D, N.ptr(dW), N.ptr(db), N.ptr(ws),
-                                             ws.numel(), st))
+                N.check(L.xdfm_cin_bwd_dw_tc(N.ptr(dyT), N.ptr(xkT), N.ptr(x0T), B, m, Hp, H, D, N.ptr(dW), None, N.ptr(ws),
+                                             ws.numel(), st))            # (db came out of the dY kernel)
             nwt = L.xdfm_cin_bwd_dx_tc_wt_elems(m, Hp, H, D)
             wt = workspace("cin_wt", nwt * 2, dev)
             # the layer below gets its dY rows straight from this layer's dX kernel when its hidden half feeds only this layer
