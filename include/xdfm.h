@@ -116,6 +116,13 @@ int xdfm_head_fwd(const float* lin, const float* cin_out, const float* w_cin, in
                   const float* bias, int64_t B, int binary, float* y_pred, void* stream);
 int xdfm_head_bwd(const float* dy_pred, const float* y_pred, int64_t B, int binary, const float* w_cin, int fm, const float* w_dnn,
                   int hd, float* dlogit, float* d_cin_out, float* d_dnn_out, void* stream);
+/* Backward of the head in one pass (autograd of xdeepfm.py:88-105): dlogit, d_cin_out, d_dnn_out as xdfm_head_bwd, plus
+ * d_w [fm + hd + 1] = (d_w_cin = sum_b dlogit[b] * cin_out[b,:] | d_w_dnn | d_bias = sum_b dlogit[b]); fixed summation order.
+ * cin_out / dnn_out NULL = that branch is absent (fm / hd count as 0). */
+int64_t xdfm_head_bwd_fused_workspace_bytes(int64_t B, int fm, int hd);
+int xdfm_head_bwd_fused(const float* dy_pred, const float* y_pred, int64_t B, int binary, const float* cin_out, const float* w_cin, int fm,
+                        const float* dnn_out, const float* w_dnn, int hd, float* dlogit, float* d_cin_out, float* d_dnn_out, float* d_w,
+                        void* workspace, int64_t workspace_bytes, void* stream);
 /* F.binary_cross_entropy(y_pred, y, reduction='sum') (basemodel.py:254): *loss_sum += loss; dy_pred = scale * dL/dy_pred */
 int xdfm_bce_sum(const float* y_pred, const float* labels, int64_t B, float scale, float* per_sample, float* dy_pred,
                  double* loss_sum, void* stream);
@@ -159,6 +166,18 @@ int xdfm_embed_gather_sharded_lazy(const void* ptrs_dev, const int64_t* feat_bas
                                    int m, int D, int G, const xdfm_opt_cfg* cfg_emb, const xdfm_opt_cfg* cfg_lin, const float* opt_dev,
                                    const float* hist, int64_t hist_base, float* out_emb, const float* dense, int nd, const float* dense_w,
                                    float* out_lin, void* stream);
+
+/* Row-sharded lookup through the batch's DISTINCT rows (replaces the nn.DataParallel replica lookup of basemodel.py:206-209, 354-380 at
+ * G > 1): uniq_keys / seg_offsets / sorted_pos / num_segments are xdfm_shard_segments' outputs for this batch (the backward reuses them);
+ * every distinct row crosses NVLink once into u_emb [nseg, D] / u_lin [nseg] (either may be NULL), replayed when stale (hist != NULL:
+ * lazy tables; hist == NULL: tables are current, cfg_* / opt_dev ignored); inv [n] = segment of lookup q = b*m + f, n = B*m.
+ * xdfm_embed_expand_unique then writes out_emb [B, m, D] = u_emb[inv] and out_lin [B] = sum_f u_lin[inv[b, f]] + dense[b,:] . dense_w. */
+int xdfm_embed_fetch_unique_sharded(const void* ptrs_dev, int G, uint32_t key_stride, int D, const uint32_t* uniq_keys,
+                                    const int32_t* seg_offsets, const int32_t* sorted_pos, const int32_t* num_segments, int64_t n,
+                                    const xdfm_opt_cfg* cfg_emb, const xdfm_opt_cfg* cfg_lin, const float* opt_dev, const float* hist,
+                                    int64_t hist_base, float* u_emb, float* u_lin, int32_t* inv, void* stream);
+int xdfm_embed_expand_unique(const float* u_emb, const float* u_lin, const int32_t* inv, int64_t B, int m, int D, float* out_emb,
+                             const float* dense, int nd, const float* dense_w, float* out_lin, void* stream);
 
 /* diagnostic: 1 = first version of the dense-table streaming pass, 2 = unrolled / streaming-hint version (default) */
 void xdfm_set_rows_opt_dense_version(int v);

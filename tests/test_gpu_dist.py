@@ -53,6 +53,56 @@ def test_sharded_gather_is_bit_exact(G):
     assert out.shape == (0, len(table_of), Dm)
 
 
+@pytest.mark.parametrize("G", [1, 3])
+def test_lookup_through_distinct_rows_equals_the_direct_lookup(G):
+    """The default forward fetches every DISTINCT row of the batch once and expands locally; it must return the bits of the direct
+    per-lookup kernels, serve the embedding and the first-order call of one forward from one fetch, notice a changed batch or
+    changed tables, and hand its segments to the backward."""
+    rows, table_of, Dm, B = [50, 7, 1000, 3, 4000], [0, 1, 2, 3, 4, 2], 16, 513
+    m = len(table_of)
+    ranks, full_emb, full_lin = _make_ranks(G, rows, table_of, Dm, B * m)
+    sh = ranks[G - 1]
+    g = torch.Generator().manual_seed(5)
+
+    def batch():
+        cols = [torch.clamp((rows[t] ** torch.rand(B, generator=g)).long() - 1, 0, rows[t] - 1) for t in table_of]
+        return torch.stack(cols, 1).to(torch.int32).to(DEV)
+
+    ids = batch()
+    dense, w = torch.rand(B, 3, generator=g).to(DEV), torch.randn(3, 1, generator=g).to(DEV)
+    sh.unique_lookup = False
+    out0, _ = sh.gather(ids, want_emb=True)
+    _, lin0 = sh.gather(ids, want_emb=False, dense=dense, dense_w=w, want_lin=True)
+    sh.unique_lookup = True
+    out1, _ = sh.gather(ids, want_emb=True)
+    assert sh._uniq == {"emb"}
+    _, lin1 = sh.gather(ids, want_emb=False, dense=dense, dense_w=w, want_lin=True)
+    assert sh._uniq == {"emb", "lin"}                      # second call of the forward: expanded from the same fetch
+    assert torch.equal(out0, out1) and torch.equal(lin0, lin1)
+    nseg = int(sh.nseg.item())
+    assert nseg == sum(int(ids[:, [f for f, t in enumerate(table_of) if t == tt]].unique().numel()) for tt in range(len(rows)))
+    # the backward takes the forward's segments over (no second sort) and gives the sums of the direct design
+    demb, dlin = torch.randn(B, m, Dm, generator=g).to(DEV), torch.randn(B, generator=g).to(DEV)
+    sh.stash = {"ids": ids, "demb": demb, "dlin": dlin}
+    assert sh._segments_current(ids)
+    sh.reduce_local()
+    keys1, gs1, gl1 = sh.x_keys[:nseg].clone(), sh.x_gsum[:nseg].clone(), sh.x_gsum_lin[:nseg].clone()
+    sh.unique_lookup = False
+    sh.stash = {"ids": ids, "demb": demb, "dlin": dlin}
+    sh.reduce_local()
+    assert torch.equal(keys1, sh.x_keys[:nseg]) and torch.equal(gs1, sh.x_gsum[:nseg]) and torch.equal(gl1, sh.x_gsum_lin[:nseg])
+    # a rewritten table row and a batch changed in place are both seen by the next forward
+    sh.unique_lookup = True
+    sh.gather(ids, want_emb=True)
+    sh.emb.mul_(2.0)
+    sh.tables_changed()
+    ids.copy_(batch())
+    out2, _ = sh.gather(ids, want_emb=True)
+    sh.unique_lookup = False
+    out3, _ = sh.gather(ids, want_emb=True)
+    assert torch.equal(out2, out3)
+
+
 @pytest.mark.parametrize("G,zipf", [(1, False), (2, True), (4, True)])
 def test_sharded_backward_exchange_matches_scatter_add_and_is_deterministic(G, zipf):
     rows, table_of, Dm, B = [50, 7, 1000, 3, 29], [0, 1, 2, 3, 4, 2], 8, 257

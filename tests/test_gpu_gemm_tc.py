@@ -94,3 +94,37 @@ def test_cvt_bf16_both_one_pass_for_every_operand(R, C, act):
     # no outputs requested individually
     r2, c2, s2 = ops.cvt_bf16_both(dy, True, False)
     assert c2 is None and s2 is None and torch.equal(r2[:, :C], dy.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("B,fm,hd,binary", [(8192, 400, 400, 1), (37, 5, 0, 1), (100, 0, 33, 0), (16, 300, 7, 1), (1, 1, 1, 1)])
+def test_head_backward_in_one_pass(B, fm, hd, binary):
+    """xdfm_head_bwd_fused == xdfm_head_bwd + the three weighted column sums (autograd of xdeepfm.py:88-105), against float64."""
+    from deepctr import _native as Nv
+    L = Nv.lib()
+    g = torch.Generator().manual_seed(B + fm + hd)
+    dy = torch.randn(B, generator=g).to(DEV)
+    y = torch.rand(B, generator=g).to(DEV)
+    cin = torch.randn(B, fm, generator=g).to(DEV) if fm else None
+    dnn = torch.randn(B, hd, generator=g).to(DEV) if hd else None
+    wc = torch.randn(fm, generator=g).to(DEV) if fm else None
+    wd = torch.randn(hd, generator=g).to(DEV) if hd else None
+    dlogit = torch.full((B,), float("nan"), device=DEV)
+    d_cin = torch.full((B, fm), float("nan"), device=DEV) if fm else None
+    d_dnn = torch.full((B, hd), float("nan"), device=DEV) if hd else None
+    d_w = torch.full((fm + hd + 1,), float("nan"), device=DEV)
+    ws = torch.empty(L.xdfm_head_bwd_fused_workspace_bytes(B, fm, hd), dtype=torch.uint8, device=DEV)
+    for _ in range(2):
+        Nv.check(L.xdfm_head_bwd_fused(Nv.ptr(dy), Nv.ptr(y), B, binary, Nv.ptr(cin), Nv.ptr(wc), fm, Nv.ptr(dnn), Nv.ptr(wd), hd,
+                                       Nv.ptr(dlogit), Nv.ptr(d_cin), Nv.ptr(d_dnn), Nv.ptr(d_w), Nv.ptr(ws), ws.numel(), Nv.stream_ptr()))
+        torch.cuda.synchronize()
+        first = d_w.clone() if _ == 0 else first
+    assert torch.equal(first, d_w)                      # fixed summation order: bit-reproducible
+    gl = dy.double() * (y.double() * (1 - y.double())) if binary else dy.double()
+    assert_close(dlogit, gl, 1e-6, 1e-7, "dlogit")
+    if fm:
+        assert_close(d_cin, gl[:, None] * wc.double()[None, :], 1e-6, 1e-7, "d_cin")
+        assert_close(d_w[:fm], (gl[:, None] * cin.double()).sum(0), 1e-5, 1e-5 * (B ** 0.5), "d_w_cin")
+    if hd:
+        assert_close(d_dnn, gl[:, None] * wd.double()[None, :], 1e-6, 1e-7, "d_dnn")
+        assert_close(d_w[fm:fm + hd], (gl[:, None] * dnn.double()).sum(0), 1e-5, 1e-5 * (B ** 0.5), "d_w_dnn")
+    assert_close(d_w[fm + hd:], gl.sum().reshape(1), 1e-5, 1e-5 * (B ** 0.5), "d_bias")

@@ -282,35 +282,6 @@ __global__ void __launch_bounds__(256) cin_dy_rows_cols_kernel(const __nv_bfloat
   }
 }
 
-// db[h] = sum over the row tiles of the per-tile column sums: 8 channels x 128 tile strides per block; every thread has its (up to)
-// 16 loads in flight at once per pass, adds them in a fixed order, then the 128 strides are added as a tree in shared memory
-__global__ void __launch_bounds__(1024) cin_db_tiles_kernel(const float* __restrict__ part, int64_t n_tiles, int H_pad, int H,
-                                                             float* __restrict__ db) {
-  __shared__ float red[128][9];
-  const int hx = threadIdx.x & 7, ty = threadIdx.x >> 3;
-  const int h = blockIdx.x * 8 + hx;
-  float acc = 0.f;
-  if (h < H) {
-    for (int64_t t0 = ty; t0 < n_tiles; t0 += 128 * 16) {
-      float v[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int64_t t = t0 + (int64_t)i * 128;
-        v[i] = t < n_tiles ? part[t * H_pad + h] : 0.f;
-      }
-#pragma unroll
-      for (int i = 0; i < 16; i += 4) acc += (v[i] + v[i + 1]) + (v[i + 2] + v[i + 3]);
-    }
-  }
-  red[ty][hx] = acc;
-  __syncthreads();
-  for (int s = 64; s > 0; s >>= 1) {
-    if (ty < s) red[ty][hx] += red[ty + s][hx];
-    __syncthreads();
-  }
-  if (ty == 0 && h < H) db[h] = red[0][hx];
-}
-
 extern "C" int64_t xdfm_cin_dy_db_workspace_bytes(int64_t B, int D, int H_pad) { return ceil_div64(B * (int64_t)D, 64) * H_pad * 4; }
 
 extern "C" int xdfm_cin_dy_rows_cols_db(const void* yt, int64_t B, int D, int H, int Hs, int H_pad, int direct_begin, const float* dpooled,
@@ -341,7 +312,7 @@ extern "C" int xdfm_cin_dy_rows_cols_db(const void* yt, int64_t B, int D, int H,
                                                                   (__nv_bfloat16*)dyT, db != nullptr ? (float*)workspace : nullptr);
   XDFM_LAUNCH_CHECK();
   if (db != nullptr) {
-    cin_db_tiles_kernel<<<(unsigned)ceil_div64(H, 8), 1024, 0, (cudaStream_t)stream>>>((const float*)workspace, ceil_div64(R, 64), H_pad, H, db);
+    XDFM_TILE_COLSUM((const float*)workspace, ceil_div64(R, 64), (int64_t)H_pad, H, db, 0, (cudaStream_t)stream);   // fixed order
     XDFM_LAUNCH_CHECK();
   }
   return XDFM_OK;

@@ -61,6 +61,38 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// out[c] (+)= sum over the n_tiles rows of part[t * pitch + c]: second stage of every deterministic column sum in the library.
+// 8 columns x 128 tile strides per block of 1024 threads; a thread has up to 16 loads in flight per pass and adds them in a fixed
+// order, the 128 strides are then added as a tree in shared memory -- the result depends only on (n_tiles, values).
+static __global__ void __launch_bounds__(1024) xdfm_tile_colsum_kernel(const float* __restrict__ part, int64_t n_tiles, int64_t pitch, int C,
+                                                                        float* __restrict__ out, int accumulate) {
+  __shared__ float red[128][9];
+  const int cx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + cx;
+  float acc = 0.f;
+  if (c < C) {
+    for (int64_t t0 = ty; t0 < n_tiles; t0 += 128 * 16) {
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int64_t t = t0 + (int64_t)i * 128;
+        v[i] = t < n_tiles ? part[t * pitch + c] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) acc += (v[i] + v[i + 1]) + (v[i + 2] + v[i + 3]);
+    }
+  }
+  red[ty][cx] = acc;
+  __syncthreads();
+  for (int s = 64; s > 0; s >>= 1) {
+    if (ty < s) red[ty][cx] += red[ty + s][cx];
+    __syncthreads();
+  }
+  if (ty == 0 && c < C) out[c] = accumulate ? out[c] + red[0][cx] : red[0][cx];
+}
+#define XDFM_TILE_COLSUM(part, n_tiles, pitch, C, out, accumulate, st) \
+  xdfm_tile_colsum_kernel<<<(unsigned)(((C) + 7) / 8), 1024, 0, (st)>>>((part), (n_tiles), (pitch), (C), (out), (accumulate))
+
 // 128-bit streaming loads/stores (read-only path, do not pollute L1)
 __device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
   float4 r;

@@ -196,14 +196,6 @@ __global__ void wcolsum_stage1(const float* __restrict__ X, int64_t B, int K, in
   for (; b < b1; ++b) a0 += (s ? s[b] : 1.f) * X[b * ld + k];
   part[(int64_t)c * K + k] = (a0 + a1) + (a2 + a3);
 }
-__global__ void wcolsum_stage2(const float* __restrict__ part, int K, float* __restrict__ out, int accumulate) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= K) return;
-  float acc = 0.f;
-  for (int c = 0; c < WCS_CHUNKS; ++c) acc += part[(int64_t)c * K + k];
-  out[k] = accumulate ? out[k] + acc : acc;
-}
-
 extern "C" int64_t xdfm_wcolsum_workspace_bytes(int K) { return (int64_t)WCS_CHUNKS * K * 4; }
 
 extern "C" int xdfm_wcolsum(const float* X, int64_t B, int K, int ld, const float* s, float* out, int accumulate, void* workspace,
@@ -214,7 +206,7 @@ extern "C" int xdfm_wcolsum(const float* X, int64_t B, int K, int ld, const floa
   dim3 g1((unsigned)ceil_div64(K, 128), WCS_CHUNKS);
   wcolsum_stage1<<<g1, 128, 0, st>>>(X, B, K, ld, s, (float*)workspace);
   XDFM_LAUNCH_CHECK();
-  wcolsum_stage2<<<(unsigned)ceil_div64(K, 128), 128, 0, st>>>((const float*)workspace, K, out, accumulate);
+  XDFM_TILE_COLSUM((const float*)workspace, (int64_t)WCS_CHUNKS, (int64_t)K, K, out, accumulate, st);
   XDFM_LAUNCH_CHECK();
   return XDFM_OK;
 }
@@ -281,6 +273,89 @@ extern "C" int xdfm_head_bwd(const float* dy_pred, const float* y_pred, int64_t 
   int blocks = (int)min((int64_t)xdfm_num_sms() * 8, ceil_div64(total, 256));
   head_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dy_pred, y_pred, B, binary, w_cin, fm, w_dnn, hd, dlogit, d_cin_out,
                                                             d_dnn_out);
+  XDFM_LAUNCH_CHECK();
+  return XDFM_OK;
+}
+
+// Fused backward of the head: one pass over the saved CIN / DNN outputs gives dlogit, d_cin_out, d_dnn_out AND the per-chunk partial
+// sums of d_w_cin = sum_b dlogit[b] * cin_out[b, :], d_w_dnn, d_bias = sum_b dlogit[b] (xdfm_head_bwd + three xdfm_wcolsum = 7 launches
+// before).  Block = 16 samples; thread = a column of [cin_out | dnn_out]; part [n_chunks, fm + hd + 1]; fixed order throughout.
+#define HEAD_ROWS 16
+__global__ void __launch_bounds__(256) head_bwd_fused_kernel(const float* __restrict__ dy_pred, const float* __restrict__ y_pred, int64_t B,
+                                                             int binary, const float* __restrict__ cin_out, const float* __restrict__ w_cin,
+                                                             int fm, const float* __restrict__ dnn_out, const float* __restrict__ w_dnn, int hd,
+                                                             float* __restrict__ dlogit, float* __restrict__ d_cin_out,
+                                                             float* __restrict__ d_dnn_out, float* __restrict__ part) {
+  __shared__ float sg[HEAD_ROWS];
+  const int64_t b0 = (int64_t)blockIdx.x * HEAD_ROWS;
+  const int W = fm + hd;
+  if (threadIdx.x < HEAD_ROWS) {
+    const int64_t b = b0 + threadIdx.x;
+    float g = 0.f;
+    if (b < B) {
+      g = dy_pred[b];
+      if (binary) { const float p = y_pred[b]; g = g * (p * (1.f - p)); }
+      dlogit[b] = g;
+    }
+    sg[threadIdx.x] = g;                       // rows past B contribute zeros
+  }
+  __syncthreads();
+  float* prow = part + (int64_t)blockIdx.x * (W + 1);
+  if (threadIdx.x == 0) {
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < HEAD_ROWS; ++i) a += sg[i];
+    prow[W] = a;
+  }
+  const int nrow = (int)min((int64_t)HEAD_ROWS, B - b0);
+  for (int c = threadIdx.x; c < W; c += blockDim.x) {
+    const bool in_cin = c < fm;
+    const int cc = in_cin ? c : c - fm;
+    const int ld = in_cin ? fm : hd;
+    const float* src = (in_cin ? cin_out : dnn_out) + b0 * ld + cc;
+    float* dst = (in_cin ? d_cin_out : d_dnn_out) + b0 * ld + cc;
+    const float w = in_cin ? w_cin[cc] : w_dnn[cc];
+    float v[HEAD_ROWS];
+#pragma unroll
+    for (int i = 0; i < HEAD_ROWS; ++i) v[i] = i < nrow ? src[(int64_t)i * ld] : 0.f;
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < HEAD_ROWS; i += 2) {
+      a0 = fmaf(sg[i], v[i], a0);
+      a1 = fmaf(sg[i + 1], v[i + 1], a1);
+    }
+#pragma unroll
+    for (int i = 0; i < HEAD_ROWS; ++i)
+      if (i < nrow) dst[(int64_t)i * ld] = sg[i] * w;
+    prow[c] = a0 + a1;
+  }
+}
+
+extern "C" int64_t xdfm_head_bwd_fused_workspace_bytes(int64_t B, int fm, int hd) {
+  return ceil_div64(B, HEAD_ROWS) * (int64_t)(fm + hd + 1) * 4;
+}
+
+// d_w [fm + hd + 1] = (d_w_cin | d_w_dnn | d_bias).  cin_out / dnn_out may be NULL (then fm / hd count as 0).
+extern "C" int xdfm_head_bwd_fused(const float* dy_pred, const float* y_pred, int64_t B, int binary, const float* cin_out, const float* w_cin,
+                                   int fm, const float* dnn_out, const float* w_dnn, int hd, float* dlogit, float* d_cin_out,
+                                   float* d_dnn_out, float* d_w, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (cin_out == nullptr) fm = 0;
+  if (dnn_out == nullptr) hd = 0;
+  XDFM_CHECK_ARG(fm == 0 || (w_cin != nullptr && d_cin_out != nullptr), "head_bwd_fused: w_cin / d_cin_out missing");
+  XDFM_CHECK_ARG(hd == 0 || (w_dnn != nullptr && d_dnn_out != nullptr), "head_bwd_fused: w_dnn / d_dnn_out missing");
+  XDFM_CHECK_ARG(d_w != nullptr && dlogit != nullptr, "head_bwd_fused: d_w / dlogit missing");
+  XDFM_CHECK_ARG(workspace != nullptr && workspace_bytes >= xdfm_head_bwd_fused_workspace_bytes(B, fm, hd), "head_bwd_fused: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int W = fm + hd;
+  if (B == 0) {
+    XDFM_CUDA(cudaMemsetAsync(d_w, 0, (size_t)(W + 1) * 4, st));
+    return XDFM_OK;
+  }
+  const int64_t n_chunks = ceil_div64(B, HEAD_ROWS);
+  head_bwd_fused_kernel<<<(unsigned)n_chunks, 256, 0, st>>>(dy_pred, y_pred, B, binary, cin_out, w_cin, fm, dnn_out, w_dnn, hd, dlogit,
+                                                          d_cin_out, d_dnn_out, (float*)workspace);
+  XDFM_LAUNCH_CHECK();
+  XDFM_TILE_COLSUM((const float*)workspace, n_chunks, (int64_t)(W + 1), W + 1, d_w, 0, st);
   XDFM_LAUNCH_CHECK();
   return XDFM_OK;
 }

@@ -366,21 +366,6 @@ __global__ void __launch_bounds__(256) cvt_bf16_both_kernel(const float* __restr
   }
 }
 
-__global__ void colsum_tiles_kernel(const float* __restrict__ part, int n_tiles, int C, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int t = 0;
-  for (; t + 4 <= n_tiles; t += 4) {
-    a0 += part[(int64_t)t * C + c];
-    a1 += part[(int64_t)(t + 1) * C + c];
-    a2 += part[(int64_t)(t + 2) * C + c];
-    a3 += part[(int64_t)(t + 3) * C + c];
-  }
-  for (; t < n_tiles; ++t) a0 += part[(int64_t)t * C + c];
-  out[c] = (a0 + a1) + (a2 + a3);
-}
-
 extern "C" int64_t xdfm_cvt_bf16_both_workspace_bytes(int R, int C) { return (int64_t)((R + 63) / 64) * C * 4; }
 
 extern "C" int xdfm_cvt_bf16_both(const float* src, const float* y, int act, int R, int C, int64_t ld, void* dst, int64_t dst_pitch,
@@ -400,7 +385,7 @@ extern "C" int xdfm_cvt_bf16_both(const float* src, const float* y, int act, int
                                              colsum != nullptr ? (float*)workspace : nullptr);
   XDFM_LAUNCH_CHECK();
   if (colsum != nullptr) {
-    colsum_tiles_kernel<<<(unsigned)ceil_div64(C, 128), 128, 0, st>>>((const float*)workspace, (R + 63) / 64, C, colsum);
+    XDFM_TILE_COLSUM((const float*)workspace, (int64_t)((R + 63) / 64), (int64_t)C, C, colsum, 0, st);
     XDFM_LAUNCH_CHECK();
   }
   return XDFM_OK;

@@ -9,6 +9,8 @@
 // g = scatter_add(row grads) + 2*l2*w, so the pass is a pure HBM stream: 4 B read + 4 B write per state
 // element (Adam: w, m, v -> 24 B/element).  Rows touched by the batch are updated by the sparse kernel
 // (which also marks them in a bitmap); the dense kernel streams all tables and skips marked rows.
+#include <cstring>
+
 #include "common.cuh"
 #include "../../include/xdfm.h"
 
@@ -672,6 +674,176 @@ __global__ void __launch_bounds__(256) linear_term_sharded_lazy_kernel(const lon
     accd = warp_sum(accd);
     if (lane == 0) out_lin[b] = acc + accd;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row-sharded lookup through the batch's UNIQUE rows.  A Criteo-shaped batch looks most rows up many times (cfg2: 213 k lookups,
+// 54 k distinct rows), and a remote row costs four small NVLink reads (w, both moments, `last`): the direct kernels above are bound
+// by the request rate of the links, not by bytes.  Here every distinct row crosses NVLink once -- keys, segments and sorted positions
+// are the ones the backward needs anyway (xdfm_shard_segments, now run before the lookup) -- is replayed if stale, and lands in a
+// compact local buffer; the per-sample tensors are expanded from it with local loads.
+//   uniq_keys[s] = owner * key_stride + local row;  inv[q] = segment of lookup q = b * m + f
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fetch_unique_emb_kernel(const long long* __restrict__ ptrs, const uint32_t* __restrict__ uniq_keys,
+                                                               const int32_t* __restrict__ num_segments, uint32_t S, int D, xdfm_opt_cfg cfg,
+                                                               const float* __restrict__ d, const float4* __restrict__ hist,
+                                                               long long hist_base, float* __restrict__ u_emb) {
+  const bool lazy = hist != nullptr;
+  OptScalars h = lazy ? load_scalars(cfg, d) : OptScalars();
+  const int done = lazy ? __float_as_int(d[0]) : 0;
+  const int vpr = D >> 2;
+  const int64_t total = (int64_t)(*num_segments) * vpr;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = i / vpr;
+    const int v = (int)(i - s * vpr);
+    const uint32_t key = __ldg(uniq_keys + s);
+    const int owner = (int)(key / S);
+    const int64_t lrow = key - (uint32_t)owner * S;
+    const long long* pp = ptrs + owner * 8;
+    const int64_t e = lrow * D + v * 4;
+    float4 w4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(pp[0]) + e);
+    if (lazy) {
+      // every operand of the replay is requested at once: one NVLink round trip per remote row
+      const int from = *(reinterpret_cast<const int32_t*>(pp[6]) + lrow);
+      float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pp[2]) a4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(pp[2]) + e);
+      if (pp[4]) b4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(pp[4]) + e);
+      if (from < done) {
+        float w[4] = {w4.x, w4.y, w4.z, w4.w}, a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+        float reg = 0.f;
+        replay_steps<4>(cfg, h, hist, hist_base, from, done, w, a, b, reg);
+        w4 = make_float4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    reinterpret_cast<float4*>(u_emb)[i] = w4;
+  }
+}
+
+__global__ void __launch_bounds__(256) fetch_unique_lin_kernel(const long long* __restrict__ ptrs, const uint32_t* __restrict__ uniq_keys,
+                                                               const int32_t* __restrict__ num_segments, uint32_t S, xdfm_opt_cfg cfg,
+                                                               const float* __restrict__ d, const float4* __restrict__ hist,
+                                                               long long hist_base, float* __restrict__ u_lin) {
+  const bool lazy = hist != nullptr;
+  OptScalars h = lazy ? load_scalars(cfg, d) : OptScalars();
+  const int done = lazy ? __float_as_int(d[0]) : 0;
+  const int nseg = *num_segments;
+  for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < nseg; s += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t key = __ldg(uniq_keys + s);
+    const int owner = (int)(key / S);
+    const int64_t lrow = key - (uint32_t)owner * S;
+    const long long* pp = ptrs + owner * 8;
+    float w[1] = {*(reinterpret_cast<const float*>(pp[1]) + lrow)};
+    if (lazy) {
+      const int from = *(reinterpret_cast<const int32_t*>(pp[7]) + lrow);
+      float a[1] = {pp[3] ? *(reinterpret_cast<const float*>(pp[3]) + lrow) : 0.f};
+      float bb[1] = {pp[5] ? *(reinterpret_cast<const float*>(pp[5]) + lrow) : 0.f};
+      if (from < done) {
+        float reg = 0.f;
+        replay_steps<1>(cfg, h, hist, hist_base, from, done, w, a, bb, reg);
+      }
+    }
+    u_lin[s] = w[0];
+  }
+}
+
+// inv[sorted_pos[p]] = the segment that holds sorted position p (binary search in seg_offsets[0 .. nseg])
+__global__ void __launch_bounds__(256) segment_of_lookup_kernel(const int32_t* __restrict__ seg_offsets, const int32_t* __restrict__ sorted_pos,
+                                                                const int32_t* __restrict__ num_segments, int64_t n, int32_t* __restrict__ inv) {
+  const int nseg = *num_segments;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    int lo = 0, hi = nseg;                          // last s with seg_offsets[s] <= p
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if ((int64_t)__ldg(seg_offsets + mid) <= p) lo = mid; else hi = mid;
+    }
+    inv[sorted_pos[p]] = lo;
+  }
+}
+
+__global__ void __launch_bounds__(256) expand_unique_emb_kernel(const float4* __restrict__ u_emb, const int32_t* __restrict__ inv, int64_t n,
+                                                                int vpr, float4* __restrict__ out) {
+  const int64_t total = n * vpr;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t q = i / vpr;
+    const int v = (int)(i - q * vpr);
+    out[i] = u_emb[(int64_t)__ldg(inv + q) * vpr + v];
+  }
+}
+
+// same lane / field assignment and summation order as linear_term_sharded(_lazy)_kernel: bit-identical first-order term
+__global__ void __launch_bounds__(256) expand_unique_lin_kernel(const float* __restrict__ u_lin, const int32_t* __restrict__ inv, int64_t B, int m,
+                                                                const float* __restrict__ dense, int nd, const float* __restrict__ dense_w,
+                                                                float* __restrict__ out_lin) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t b = warp; b < B; b += nwarps) {
+    float acc = 0.f;
+    for (int f = lane; f < m; f += 32) acc += u_lin[__ldg(inv + b * m + f)];
+    float accd = 0.f;
+    if (dense_w != nullptr)
+      for (int j = lane; j < nd; j += 32) accd += __ldg(dense + b * nd + j) * __ldg(dense_w + j);
+    acc = warp_sum(acc);
+    accd = warp_sum(accd);
+    if (lane == 0) out_lin[b] = acc + accd;
+  }
+}
+
+// Distinct rows of the batch -> u_emb [nseg, D], u_lin [nseg] (stale rows replayed when hist != NULL; cfg_* / opt_dev may be NULL
+// otherwise), and inv [n].  n = B * m = number of lookups (capacity of every per-lookup / per-segment array).
+extern "C" int xdfm_embed_fetch_unique_sharded(const void* ptrs_dev, int G, uint32_t key_stride, int D, const uint32_t* uniq_keys,
+                                               const int32_t* seg_offsets, const int32_t* sorted_pos, const int32_t* num_segments, int64_t n,
+                                               const xdfm_opt_cfg* cfg_emb, const xdfm_opt_cfg* cfg_lin, const float* opt_dev, const float* hist,
+                                               int64_t hist_base, float* u_emb, float* u_lin, int32_t* inv, void* stream) {
+  XDFM_CHECK_ARG(G >= 1 && G <= 16 && key_stride > 0, "embed_fetch_unique_sharded: G=%d key_stride=%u", G, key_stride);
+  XDFM_CHECK_ARG(ptrs_dev != nullptr && uniq_keys != nullptr && seg_offsets != nullptr && sorted_pos != nullptr && num_segments != nullptr &&
+                     inv != nullptr, "embed_fetch_unique_sharded: null argument");
+  XDFM_CHECK_ARG(hist == nullptr || (opt_dev != nullptr && cfg_emb != nullptr && cfg_lin != nullptr),
+                 "embed_fetch_unique_sharded: lazy tables need cfg_emb, cfg_lin and opt_dev");
+  XDFM_CHECK_ARG(u_emb == nullptr || (D >= 4 && D % 4 == 0), "embed_fetch_unique_sharded: D=%d must be a multiple of 4", D);
+  if (n == 0) return XDFM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  xdfm_opt_cfg none;
+  memset(&none, 0, sizeof(none));
+  if (u_emb != nullptr) {
+    int blocks = (int)min((int64_t)xdfm_num_sms() * 8, ceil_div64(n * (D / 4), 256));
+    fetch_unique_emb_kernel<<<max(blocks, 1), 256, 0, st>>>((const long long*)ptrs_dev, uniq_keys, num_segments, key_stride, D,
+                                                            hist ? *cfg_emb : none, opt_dev, (const float4*)hist, (long long)hist_base, u_emb);
+    XDFM_LAUNCH_CHECK();
+  }
+  if (u_lin != nullptr) {
+    int blocks = (int)min((int64_t)xdfm_num_sms() * 8, ceil_div64(n, 256));
+    fetch_unique_lin_kernel<<<max(blocks, 1), 256, 0, st>>>((const long long*)ptrs_dev, uniq_keys, num_segments, key_stride,
+                                                            hist ? *cfg_lin : none, opt_dev, (const float4*)hist, (long long)hist_base, u_lin);
+    XDFM_LAUNCH_CHECK();
+  }
+  int blocks = (int)min((int64_t)xdfm_num_sms() * 8, ceil_div64(n, 256));
+  segment_of_lookup_kernel<<<max(blocks, 1), 256, 0, st>>>(seg_offsets, sorted_pos, num_segments, n, inv);
+  XDFM_LAUNCH_CHECK();
+  return XDFM_OK;
+}
+
+// out_emb [B, m, D] = u_emb[inv] and / or out_lin [B] = sum_f u_lin[inv[b, f]] + dense[b, :] . dense_w (either output may be NULL)
+extern "C" int xdfm_embed_expand_unique(const float* u_emb, const float* u_lin, const int32_t* inv, int64_t B, int m, int D, float* out_emb,
+                                        const float* dense, int nd, const float* dense_w, float* out_lin, void* stream) {
+  XDFM_CHECK_ARG(m >= 1 && m <= XDFM_MAX_FIELDS && inv != nullptr, "embed_expand_unique: m=%d", m);
+  if (B == 0) return XDFM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_emb != nullptr) {
+    XDFM_CHECK_ARG(u_emb != nullptr && D >= 4 && D % 4 == 0 && (uintptr_t)out_emb % 16 == 0 && (uintptr_t)u_emb % 16 == 0,
+                   "embed_expand_unique: D=%d must be a multiple of 4 and the buffers 16-byte aligned", D);
+    const int64_t total = B * (int64_t)m * (D / 4);
+    int blocks = (int)min((int64_t)xdfm_num_sms() * 16, ceil_div64(total, 256));
+    expand_unique_emb_kernel<<<max(blocks, 1), 256, 0, st>>>((const float4*)u_emb, inv, B * (int64_t)m, D / 4, (float4*)out_emb);
+    XDFM_LAUNCH_CHECK();
+  }
+  if (out_lin != nullptr) {
+    XDFM_CHECK_ARG(u_lin != nullptr, "embed_expand_unique: u_lin is null");
+    int blocks = (int)min((int64_t)xdfm_num_sms() * 8, ceil_div64(B, 8));
+    expand_unique_lin_kernel<<<max(blocks, 1), 256, 0, st>>>(u_lin, inv, B, m, dense, nd, nd > 0 ? dense_w : nullptr, out_lin);
+    XDFM_LAUNCH_CHECK();
+  }
+  return XDFM_OK;
 }
 
 extern "C" int xdfm_embed_gather_sharded_lazy(const void* ptrs_dev, const int64_t* feat_base_dev, const int32_t* vocab, const int32_t* ids,

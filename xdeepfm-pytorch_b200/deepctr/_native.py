@@ -48,6 +48,8 @@ _SIGS = {
     "xdfm_wcolsum": (c_int, [_P, c_int64, c_int, c_int, _P, _P, c_int, _P, c_int64, _P]),
     "xdfm_head_fwd": (c_int, [_P, _P, _P, c_int, _P, _P, c_int, _P, c_int64, c_int, _P, _P]),
     "xdfm_head_bwd": (c_int, [_P, _P, c_int64, c_int, _P, c_int, _P, c_int, _P, _P, _P, _P]),
+    "xdfm_head_bwd_fused_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
+    "xdfm_head_bwd_fused": (c_int, [_P, _P, c_int64, c_int, _P, _P, c_int, _P, _P, c_int, _P, _P, _P, _P, _P, c_int64, _P]),
     "xdfm_bce_sum": (c_int, [_P, _P, c_int64, c_float, _P, _P, _P, _P]),
     "xdfm_to_rows_bf16": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P]),
     "xdfm_cin_tc_set_cluster": (None, [c_int]),
@@ -127,6 +129,9 @@ _SIGS = {
                                 _P]),
     "xdfm_embed_gather_sharded_lazy": (c_int, [_P, _P, POINTER(c_int32), _P, c_int64, c_int, c_int, c_int, POINTER(OptCfg), POINTER(OptCfg), _P, _P,
                                                c_int64, _P, _P, c_int, _P, _P, _P]),
+    "xdfm_embed_fetch_unique_sharded": (c_int, [_P, c_int, c_uint32, c_int, _P, _P, _P, _P, c_int64, POINTER(OptCfg), POINTER(OptCfg), _P, _P,
+                                                c_int64, _P, _P, _P, _P]),
+    "xdfm_embed_expand_unique": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, _P, c_int, _P, _P, _P]),
     "xdfm_opt_tick": (c_int, [_P, POINTER(OptCfg), _P]),
     "xdfm_flat_opt": (c_int, [POINTER(OptCfg), _P, c_int64, _P, _P, _P, _P, _P, c_float, _P, _P]),
     "xdfm_rows_opt": (c_int, [POINTER(OptCfg), _P, POINTER(_P), POINTER(_P), POINTER(_P), POINTER(c_int64), c_int, c_int, _P, _P, _P,

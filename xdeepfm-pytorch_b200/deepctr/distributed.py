@@ -22,6 +22,7 @@ Usage (every rank):
 The integer routing functions at the top are pure Python so that the CPU test-suite (gloo, world_size 2) covers them.
 """
 import ctypes
+import os
 
 import torch
 
@@ -220,6 +221,9 @@ class ShardedSparse:
         self._peer_tables = None
         self._peer_x = None
         self.stash = {}
+        # XDFM_SHARD_UNIQUE=0: every lookup reads its row from the owner (the first design; kept for batches beyond the exchange capacity)
+        self.unique_lookup = os.environ.get("XDFM_SHARD_UNIQUE", "1") != "0"
+        self._seg_key = self._uniq = None
         self.anchor = torch.zeros(1, device=self.device, requires_grad=True)
         # optimizer state (allocated by FusedOptimizer.prepare)
         self.s1 = self.s2 = self.s1_lin = self.s2_lin = None
@@ -261,6 +265,11 @@ class ShardedSparse:
         self.p_gsum = torch.empty((n_cap, self.D), dtype=torch.float32, device=dev)
         self.p_gsum_lin = torch.empty(n_cap, dtype=torch.float32, device=dev)
         self.ws = torch.empty(int(N.lib().xdfm_shard_workspace_bytes(n_cap)), dtype=torch.uint8, device=dev)
+        # lookup through the batch's distinct rows: compact rows fetched over NVLink + the segment of every lookup
+        self.u_emb = torch.empty((self.cap, self.D), dtype=torch.float32, device=dev)
+        self.u_lin = torch.empty(self.cap, dtype=torch.float32, device=dev)
+        self.inv = torch.empty(self.cap, dtype=torch.int32, device=dev)
+        self._seg_key = self._uniq = None
 
     def export(self):
         """Picklable description of this rank's exported buffers (all_gather_object it, then connect())."""
@@ -337,6 +346,47 @@ class ShardedSparse:
         self.last_lin.fill_(int(steps))
 
     # ---- forward ------------------------------------------------------------------------------------
+    def _segments_of(self, ids):
+        """Sort this batch's keys owner-major and run-length encode them: (x_keys, x_ranges) in the exchange buffer, (seg_off, pos,
+        nseg) next to it.  Run once per batch, before the lookup; the backward (reduce_local) reuses the result."""
+        B, m = ids.shape
+        with ops.timed("embed_segments"):
+            N.check(N.lib().xdfm_shard_segments(N.ptr(ids), B, m, self.G, self.S, N.ptr(self.feat_base), self._c_vocab, N.ptr(self.ws),
+                                                self.ws.numel(), N.ptr(self.x_keys), N.ptr(self.seg_off), N.ptr(self.pos), N.ptr(self.nseg),
+                                                N.ptr(self.x_ranges), N.stream_ptr()))
+        self._seg_key = (ids, ids._version)           # strong reference: the address cannot be recycled while cached
+        self._uniq = None
+
+    def _segments_current(self, ids):
+        k = self._seg_key
+        return k is not None and k[0] is ids and k[1] == ids._version
+
+    def tables_changed(self):
+        """Rows were rewritten (optimizer step, catch-up, flush, load): fetched copies of them are stale."""
+        self._uniq = None
+
+    def _gather_unique(self, ids, out, lin, dense, dense_w, nd):
+        """Every DISTINCT row of the batch crosses NVLink once (replayed if stale) into (u_emb, u_lin); the per-sample tensors are
+        expanded from them locally.  One fetch serves the embedding lookup and the first-order term of the same forward."""
+        B, m = ids.shape
+        L = N.lib()
+        st = N.stream_ptr()
+        need = ([] if out is None else ["emb"]) + ([] if lin is None else ["lin"])
+        if self._uniq is None or not self._segments_current(ids) or any(p in self._uniq for p in need):
+            self._segments_of(ids)
+            lz = self.lazy
+            with ops.timed("embed_gather"):
+                N.check(L.xdfm_embed_fetch_unique_sharded(
+                    N.ptr(self.peer_ptrs), self.G, self.S, self.D, N.ptr(self.x_keys), N.ptr(self.seg_off), N.ptr(self.pos), N.ptr(self.nseg),
+                    B * m, lz["cfg_emb"] if lz else None, lz["cfg_lin"] if lz else None, N.ptr(lz["opt_dev"]) if lz else None,
+                    N.ptr(lz["hist"]) if lz else None, lz["hist_base"] if lz else 0, N.ptr(self.u_emb), N.ptr(self.u_lin), N.ptr(self.inv), st))
+            self._uniq = set()
+        with ops.timed("embed_gather"):
+            N.check(L.xdfm_embed_expand_unique(N.ptr(self.u_emb), N.ptr(self.u_lin), N.ptr(self.inv), B, m, self.D, N.ptr(out),
+                                               N.ptr(dense) if nd > 0 else None, nd, N.ptr(dense_w) if nd > 0 else None, N.ptr(lin), st))
+        self._uniq.update(need)
+        return out, lin
+
     def gather(self, ids, want_emb=True, dense=None, dense_w=None, want_lin=False):
         B, m = ids.shape
         assert m == self.m
@@ -344,6 +394,8 @@ class ShardedSparse:
         out = torch.empty((B, m, self.D), dtype=torch.float32, device=dev) if want_emb else None
         lin = torch.empty((B,), dtype=torch.float32, device=dev) if want_lin else None
         nd = 0 if dense is None or dense_w is None else dense.shape[1]
+        if self.unique_lookup and self.exchange is not None and 0 < B * m <= self.cap and self.peer_ptrs is not None:
+            return self._gather_unique(ids, out, lin, dense, dense_w, nd)
         if self.lazy is not None:
             lz = self.lazy
             with ops.timed("embed_gather"):
@@ -376,10 +428,10 @@ class ShardedSparse:
         if n > self.cap:
             raise RuntimeError("row-sharded tables: batch of %d keys exceeds the exchange capacity %d; call "
                                "model.distribute(max_batch=...) with the largest per-GPU batch" % (n, self.cap))
+        if not self._segments_current(ids):             # (the unique-row lookup of the forward already sorted this batch)
+            self._segments_of(ids)
+        self._seg_key = None                             # one forward, one backward
         with ops.timed("embed_scatter"):
-            N.check(L.xdfm_shard_segments(N.ptr(ids), B, m, self.G, self.S, N.ptr(self.feat_base), self._c_vocab, N.ptr(self.ws),
-                                          self.ws.numel(), N.ptr(self.x_keys), N.ptr(self.seg_off), N.ptr(self.pos), N.ptr(self.nseg),
-                                          N.ptr(self.x_ranges), st))
             demb, dlin = self.stash.get("demb"), self.stash.get("dlin")
             if demb is None:
                 self.x_gsum[:n].zero_()
@@ -408,6 +460,7 @@ class ShardedSparse:
     def catch_up_pulled(self, cfg_emb, cfg_lin, opt_dev, hist, hist_base, reg_out):
         """Lazy semantics, owner side: the rows about to be updated (p_uniq) are replayed up to the completed-step count first.
         Must run BEFORE the step counter is advanced."""
+        self.tables_changed()
         L = N.lib()
         st = N.stream_ptr()
         n_cap = self.cap * self.G
@@ -425,6 +478,7 @@ class ShardedSparse:
                                                    N.stream_ptr()))
 
     def flush_rows(self, cfg_emb, cfg_lin, opt_dev, hist, hist_base, reg_out):
+        self.tables_changed()
         L = N.lib()
         st = N.stream_ptr()
         if self.local_rows == 0:
@@ -437,6 +491,7 @@ class ShardedSparse:
                                           N.ptr(last), self._row_off, 1, width, N.ptr(reg_out), st))
 
     def apply_optimizer(self, cfg_emb, cfg_lin, opt_dev, grad_scale, dense_pass, reg_out):
+        self.tables_changed()
         L = N.lib()
         st = N.stream_ptr()
         n_cap = self.cap * self.G

@@ -802,21 +802,15 @@ class LogitHead(torch.autograd.Function):
         dlogit = torch.empty(B, dtype=torch.float32, device=dev)
         d_cin = torch.empty_like(cin_c) if cin_c is not None else None
         d_dnn = torch.empty_like(dnn_c) if dnn_c is not None else None
-        N.check(L.xdfm_head_bwd(N.ptr(dy), N.ptr(y), B, binary, N.ptr(wc), fm, N.ptr(wd), hd, N.ptr(dlogit), N.ptr(d_cin),
-                                N.ptr(d_dnn), N.stream_ptr()))
-        ws = workspace("wcolsum", L.xdfm_wcolsum_workspace_bytes(max(fm, hd, 1)), dev)
-        d_wc = d_wd = d_bias = None
-        if cin_c is not None:
-            d_wc = torch.empty(fm, dtype=torch.float32, device=dev)
-            N.check(L.xdfm_wcolsum(N.ptr(cin_c), B, fm, fm, N.ptr(dlogit), N.ptr(d_wc), 0, N.ptr(ws), ws.numel(), N.stream_ptr()))
-            d_wc = d_wc.view(wc_shape)
-        if dnn_c is not None:
-            d_wd = torch.empty(hd, dtype=torch.float32, device=dev)
-            N.check(L.xdfm_wcolsum(N.ptr(dnn_c), B, hd, hd, N.ptr(dlogit), N.ptr(d_wd), 0, N.ptr(ws), ws.numel(), N.stream_ptr()))
-            d_wd = d_wd.view(wd_shape)
-        if has_bias:
-            d_bias = torch.empty(1, dtype=torch.float32, device=dev)
-            N.check(L.xdfm_wcolsum(N.ptr(dlogit), B, 1, 1, None, N.ptr(d_bias), 0, N.ptr(ws), ws.numel(), N.stream_ptr()))
+        # one pass: dlogit, the two output gradients and (d_w_cin | d_w_dnn | d_bias) as slices of one buffer
+        fm_, hd_ = (fm if cin_c is not None else 0), (hd if dnn_c is not None else 0)
+        d_w = torch.empty(fm_ + hd_ + 1, dtype=torch.float32, device=dev)
+        ws = workspace("head_bwd", L.xdfm_head_bwd_fused_workspace_bytes(B, fm_, hd_), dev)
+        N.check(L.xdfm_head_bwd_fused(N.ptr(dy), N.ptr(y), B, binary, N.ptr(cin_c), N.ptr(wc), fm_, N.ptr(dnn_c), N.ptr(wd), hd_,
+                                      N.ptr(dlogit), N.ptr(d_cin), N.ptr(d_dnn), N.ptr(d_w), N.ptr(ws), ws.numel(), N.stream_ptr()))
+        d_wc = d_w[:fm_].view(wc_shape) if cin_c is not None else None
+        d_wd = d_w[fm_:fm_ + hd_].view(wd_shape) if dnn_c is not None else None
+        d_bias = d_w[fm_ + hd_:] if has_bias else None
         d_lin = dlogit.view(lin_shape) if lin_shape is not None else None
         return d_lin, d_cin, d_wc, d_dnn, d_wd, d_bias, None
 
