@@ -11,7 +11,7 @@ dominant kernel (timed live with CUDA events; `frac_incl_layout` counts the layo
 (embedding gather / sorted segmented scatter-add at the cfg5 shape against the measured HBM peak), `fit_e2e` / `predict_e2e`
 (the reference's own entry points `model.fit` / `model.predict` on host arrays), `cpu_baseline` = the unmodified reference
 (oracle/_ref, shipped by oracle/build_ref.py) on this box's host cores; at N > 1 `dp_parity` (N GPUs == 1 GPU on the same global
-batches, checked BEFORE timing; non-zero exit on mismatch) and `extra_workloads` (cfg4 = BASELINE configs[3]; cfg5 at N = 8).
+batches, checked BEFORE timing; non-zero exit on mismatch) and `extra_workloads` (N = 1: cfg3, cfg4; N > 1: cfg4 = BASELINE configs[3] data-parallel; cfg5 at N = 8).
 """
 import argparse
 import json
@@ -793,9 +793,10 @@ def main():
     release_model(r.pop("model"))
 
     extra_workloads = None
-    if world > 1 and extras and args.workload == "cfg2":
+    if extras and args.workload == "cfg2":
         extra_workloads = {}
-        names = ["cfg4"] + (["cfg5"] if world >= 8 else [])
+        # one GPU: the attention variant (cfg3) and xDeepFM Pro (cfg4 = BASELINE configs[3]); N > 1: cfg4 data-parallel, cfg5 at N = 8
+        names = ["cfg3", "cfg4"] if world == 1 else ["cfg4"] + (["cfg5"] if world >= 8 else [])
         for name in names:
             x = run_workload(env, args, name, min(args.steps, 30), want_profile=False)
             release_model(x.pop("model"))

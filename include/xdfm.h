@@ -178,6 +178,9 @@ int xdfm_embed_fetch_unique_sharded(const void* ptrs_dev, int G, uint32_t key_st
                                     int64_t hist_base, float* u_emb, float* u_lin, int32_t* inv, void* stream);
 int xdfm_embed_expand_unique(const float* u_emb, const float* u_lin, const int32_t* inv, int64_t B, int m, int D, float* out_emb,
                              const float* dense, int nd, const float* dense_w, float* out_lin, void* stream);
+/* out [n] = u_lin[inv]: the first-order row of every lookup, un-summed (multi-value features are pooled per field first,
+ * basemodel.py:63-92 with inputs.py:141-155) */
+int xdfm_embed_expand_unique_lin_rows(const float* u_lin, const int32_t* inv, int64_t n, float* out, void* stream);
 
 /* diagnostic: 1 = first version of the dense-table streaming pass, 2 = unrolled / streaming-hint version (default) */
 void xdfm_set_rows_opt_dense_version(int v);

@@ -32,15 +32,36 @@ def spec_for_test(variant="xdeepfm"):
                        l2_reg_embedding=1e-4, l2_reg_dnn=1e-4, l2_reg_cin=1e-4)
 
 
+def _setup(variant, dev):
+    """(model builder, initial state_dict, make_inputs(n, seed, zipf) -> (X float [n, columns], y [n]))."""
+    if variant == "varlen":
+        # multi-value features (VarLenSparseFeat: mean / max / sum pooling, id-0 masks and length columns) over row-sharded tables:
+        # rows drawn with replacement from the reference-generated fixture, weights = the fixture's
+        from tests.helpers import build_varlen_product_model, load_varlen_case
+        desc, _, params, z = load_varlen_case("xdeepfm_varlen")
+        Xz, yz = torch.from_numpy(z["X"]).float(), torch.from_numpy(z["y"]).float()
+
+        def make_inputs(n, seed, zipf=False):
+            idx = torch.randint(0, Xz.shape[0], (n,), generator=torch.Generator().manual_seed(seed))
+            return Xz[idx].clone(), yz[idx].clone()
+
+        return (lambda: build_varlen_product_model(desc, dev)), params, make_inputs
+    spec = spec_for_test(variant)
+    return (lambda: build_product_model(spec, dev)), O.make_params(spec, seed=11), (lambda n, seed, zipf=False: O.make_inputs(spec, n, seed=seed, zipf=zipf))
+
+
+def _as_dict(model, X):
+    return {n: (X[:, a:b].numpy().copy() if b - a > 1 else X[:, a].numpy().copy()) for n, (a, b) in model.feature_index.items()}
+
+
 def run(rank, world, optimizer="adam", steps=6, per_rank=48, fit_check=True, variant="xdeepfm"):
     from deepctr.distributed import rank_slice
     dev = "cuda:%d" % torch.cuda.current_device()
-    spec = spec_for_test(variant)
-    params = O.make_params(spec, seed=11)
+    build, params, make_inputs = _setup(variant, dev)
     gb = per_rank * world
-    batches = [O.make_inputs(spec, gb, seed=100 + s, zipf=(s % 2 == 0)) for s in range(steps)]
+    batches = [make_inputs(gb, 100 + s, zipf=(s % 2 == 0)) for s in range(steps)]
 
-    model = build_product_model(spec, dev)
+    model = build()
     model.load_state_dict(params, strict=True)
     model.distribute(max_batch=per_rank)
     model.compile(optimizer, "binary_crossentropy")
@@ -58,7 +79,7 @@ def run(rank, world, optimizer="adam", steps=6, per_rank=48, fit_check=True, var
     reg = model.optim.pop_reg_loss()
     sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}          # collective
     model.eval()
-    Xe, _ = O.make_inputs(spec, 64, seed=999)
+    Xe, _ = make_inputs(64, 999)
     with torch.no_grad():
         pred = model(Xe.to(dev)).cpu()
 
@@ -70,14 +91,13 @@ def run(rank, world, optimizer="adam", steps=6, per_rank=48, fit_check=True, var
 
     if fit_check:
         # fit(): every rank passes the same arrays; the epoch loss must equal the single-GPU value at batch = world * bs
-        Xf, yf = O.make_inputs(spec, 5 * gb + 7, seed=77)
-        names = list(model.feature_index.keys())
-        xd = {n: Xf[:, i].numpy().copy() for i, n in enumerate(names)}
+        Xf, yf = make_inputs(5 * gb + 7, 77)
+        xd = _as_dict(model, Xf)
         hist = model.fit(xd, yf.numpy().reshape(-1, 1), batch_size=per_rank, epochs=2, verbose=0, shuffle=False)
         fit_loss = list(hist.history["loss"])
     if rank != 0:
         return
-    ref = build_product_model(spec, dev)
+    ref = build()
     ref.load_state_dict(params, strict=True)
     ref.compile(optimizer, "binary_crossentropy")
     ref.train()
@@ -141,8 +161,8 @@ def spawn_entry(rank, world, init_file, optimizer):
     try:
         if optimizer == "deferred":
             run_deferred(rank, world)
-        elif optimizer.startswith("pro:"):
-            run(rank, world, optimizer[4:], variant="pro")
+        elif ":" in optimizer:
+            run(rank, world, optimizer.split(":")[1], variant=optimizer.split(":")[0])
         else:
             run(rank, world, optimizer)
     finally:
@@ -157,8 +177,8 @@ if __name__ == "__main__":
         for opt in (sys.argv[1:] or ["adam", "sgd"]):
             if opt == "deferred":
                 run_deferred(rank, world)
-            elif opt.startswith("pro:"):
-                run(rank, world, opt[4:], variant="pro")
+            elif ":" in opt:
+                run(rank, world, opt.split(":")[1], variant=opt.split(":")[0])
             else:
                 run(rank, world, opt)
     finally:

@@ -171,7 +171,12 @@ def test_pro_distribute_world_size_1_equals_plain_model():
     _run_in_subprocess(1, "pro:adam")
 
 
+def test_multi_value_features_distribute_world_size_1_equals_plain_model():
+    """VarLenSparseFeat columns over row-sharded tables: slots looked up through the batch's distinct rows, pooled per field."""
+    _run_in_subprocess(1, "varlen:adam")
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-@pytest.mark.parametrize("optimizer", ["adam", "adagrad", "pro:adam"])
+@pytest.mark.parametrize("optimizer", ["adam", "adagrad", "pro:adam", "varlen:adam"])
 def test_two_gpus_equal_one_gpu(optimizer):
     _run_in_subprocess(2, optimizer)

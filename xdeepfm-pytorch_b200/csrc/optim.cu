@@ -823,6 +823,21 @@ extern "C" int xdfm_embed_fetch_unique_sharded(const void* ptrs_dev, int G, uint
   return XDFM_OK;
 }
 
+// first-order rows of every lookup, un-summed: out [n] = u_lin[inv] (models with multi-value features pool them per field first)
+__global__ void __launch_bounds__(256) expand_unique_rows1_kernel(const float* __restrict__ u_lin, const int32_t* __restrict__ inv, int64_t n,
+                                                                  float* __restrict__ out) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) out[q] = u_lin[__ldg(inv + q)];
+}
+
+extern "C" int xdfm_embed_expand_unique_lin_rows(const float* u_lin, const int32_t* inv, int64_t n, float* out, void* stream) {
+  XDFM_CHECK_ARG(n == 0 || (u_lin != nullptr && inv != nullptr && out != nullptr), "embed_expand_unique_lin_rows: null argument");
+  if (n == 0) return XDFM_OK;
+  int blocks = (int)min((int64_t)xdfm_num_sms() * 8, ceil_div64(n, 256));
+  expand_unique_rows1_kernel<<<max(blocks, 1), 256, 0, (cudaStream_t)stream>>>(u_lin, inv, n, out);
+  XDFM_LAUNCH_CHECK();
+  return XDFM_OK;
+}
+
 // out_emb [B, m, D] = u_emb[inv] and / or out_lin [B] = sum_f u_lin[inv[b, f]] + dense[b, :] . dense_w (either output may be NULL)
 extern "C" int xdfm_embed_expand_unique(const float* u_emb, const float* u_lin, const int32_t* inv, int64_t B, int m, int D, float* out_emb,
                                         const float* dense, int nd, const float* dense_w, float* out_lin, void* stream) {

@@ -132,6 +132,7 @@ _SIGS = {
     "xdfm_embed_fetch_unique_sharded": (c_int, [_P, c_int, c_uint32, c_int, _P, _P, _P, _P, c_int64, POINTER(OptCfg), POINTER(OptCfg), _P, _P,
                                                 c_int64, _P, _P, _P, _P]),
     "xdfm_embed_expand_unique": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, _P, c_int, _P, _P, _P]),
+    "xdfm_embed_expand_unique_lin_rows": (c_int, [_P, _P, c_int64, _P, _P]),
     "xdfm_opt_tick": (c_int, [_P, POINTER(OptCfg), _P]),
     "xdfm_flat_opt": (c_int, [POINTER(OptCfg), _P, c_int64, _P, _P, _P, _P, _P, c_float, _P, _P]),
     "xdfm_rows_opt": (c_int, [POINTER(OptCfg), _P, POINTER(_P), POINTER(_P), POINTER(_P), POINTER(c_int64), c_int, c_int, _P, _P, _P,

@@ -365,13 +365,13 @@ class ShardedSparse:
         """Rows were rewritten (optimizer step, catch-up, flush, load): fetched copies of them are stale."""
         self._uniq = None
 
-    def _gather_unique(self, ids, out, lin, dense, dense_w, nd):
+    def _gather_unique(self, ids, out, lin, dense, dense_w, nd, lin_rows=None):
         """Every DISTINCT row of the batch crosses NVLink once (replayed if stale) into (u_emb, u_lin); the per-sample tensors are
         expanded from them locally.  One fetch serves the embedding lookup and the first-order term of the same forward."""
         B, m = ids.shape
         L = N.lib()
         st = N.stream_ptr()
-        need = ([] if out is None else ["emb"]) + ([] if lin is None else ["lin"])
+        need = ([] if out is None else ["emb"]) + ([] if lin is None and lin_rows is None else ["lin"])
         if self._uniq is None or not self._segments_current(ids) or any(p in self._uniq for p in need):
             self._segments_of(ids)
             lz = self.lazy
@@ -382,10 +382,33 @@ class ShardedSparse:
                     N.ptr(lz["hist"]) if lz else None, lz["hist_base"] if lz else 0, N.ptr(self.u_emb), N.ptr(self.u_lin), N.ptr(self.inv), st))
             self._uniq = set()
         with ops.timed("embed_gather"):
-            N.check(L.xdfm_embed_expand_unique(N.ptr(self.u_emb), N.ptr(self.u_lin), N.ptr(self.inv), B, m, self.D, N.ptr(out),
-                                               N.ptr(dense) if nd > 0 else None, nd, N.ptr(dense_w) if nd > 0 else None, N.ptr(lin), st))
+            if out is not None or lin is not None:
+                N.check(L.xdfm_embed_expand_unique(N.ptr(self.u_emb), N.ptr(self.u_lin), N.ptr(self.inv), B, m, self.D, N.ptr(out),
+                                                   N.ptr(dense) if nd > 0 else None, nd, N.ptr(dense_w) if nd > 0 else None, N.ptr(lin), st))
+            if lin_rows is not None:
+                N.check(L.xdfm_embed_expand_unique_lin_rows(N.ptr(self.u_lin), N.ptr(self.inv), B * m, N.ptr(lin_rows), st))
         self._uniq.update(need)
         return out, lin
+
+    def gather_lin_rows(self, ids):
+        """[B, m, 1] first-order row of every lookup, un-summed (models with multi-value features pool them per field).  Always
+        through the distinct rows of the batch; batches beyond the exchange capacity are looked up in slices."""
+        B, m = ids.shape
+        assert m == self.m
+        rows = torch.empty((B, m, 1), dtype=torch.float32, device=ids.device)
+        if B == 0:
+            return rows
+        if self.exchange is None or self.peer_ptrs is None:
+            raise RuntimeError("row-sharded tables are not connected yet (distribute() wires them)")
+        step = max(self.cap // m, 1)
+        if step * m > self.cap:
+            raise RuntimeError("row-sharded tables: exchange capacity %d is below one sample's %d lookups" % (self.cap, m))
+        if B <= step:
+            self._gather_unique(ids, None, None, None, None, 0, lin_rows=rows)
+        else:
+            for a in range(0, B, step):
+                self._gather_unique(ids[a:a + step], None, None, None, None, 0, lin_rows=rows[a:a + step])
+        return rows
 
     def gather(self, ids, want_emb=True, dense=None, dense_w=None, want_lin=False):
         B, m = ids.shape
@@ -432,14 +455,19 @@ class ShardedSparse:
             self._segments_of(ids)
         self._seg_key = None                             # one forward, one backward
         with ops.timed("embed_scatter"):
-            demb, dlin = self.stash.get("demb"), self.stash.get("dlin")
+            demb, dlin, dlin_rows = self.stash.get("demb"), self.stash.get("dlin"), self.stash.get("dlin_rows")
             if demb is None:
                 self.x_gsum[:n].zero_()
-            if dlin is None:
+            if dlin is None and dlin_rows is None:
                 self.x_gsum_lin[:n].zero_()
-            N.check(L.xdfm_embed_bwd_reduce(N.ptr(demb), N.ptr(dlin), N.ptr(self.pos), N.ptr(self.seg_off), N.ptr(self.nseg), n, m,
-                                            self.D, N.ptr(self.x_gsum) if demb is not None else None,
-                                            N.ptr(self.x_gsum_lin) if dlin is not None else None, st))
+            if demb is not None or dlin is not None:
+                N.check(L.xdfm_embed_bwd_reduce(N.ptr(demb), N.ptr(dlin), N.ptr(self.pos), N.ptr(self.seg_off), N.ptr(self.nseg), n, m,
+                                                self.D, N.ptr(self.x_gsum) if demb is not None else None,
+                                                N.ptr(self.x_gsum_lin) if dlin is not None else None, st))
+            if dlin_rows is not None:
+                # one gradient per LOOKUP (multi-value features: pooled first-order rows), reduced like a width-1 embedding
+                N.check(L.xdfm_embed_bwd_reduce(N.ptr(dlin_rows), None, N.ptr(self.pos), N.ptr(self.seg_off), N.ptr(self.nseg), n, m, 1,
+                                                N.ptr(self.x_gsum_lin), None, st))
         self.stash = {}
 
     # ---- backward, owner side -----------------------------------------------------------------------
@@ -553,6 +581,23 @@ class ShardedLinearTerm(torch.autograd.Function):
         return None, None, None, d_dense_w, None
 
 
+class ShardedLinearRows(torch.autograd.Function):
+    """[B, m, 1] first-order rows of the row-sharded [V,1] tables, one per lookup (the model pools the positions of multi-value
+    features per field before summing: basemodel.py:63-92 with inputs.py:141-155)."""
+
+    @staticmethod
+    def forward(ctx, sh, ids, anchor):
+        ops.require_cuda(ids, "ShardedLinearRows")
+        ctx.sh, ctx.ids = sh, ids
+        return sh.gather_lin_rows(ids)
+
+    @staticmethod
+    def backward(ctx, dout):
+        ctx.sh.stash["ids"] = ctx.ids
+        ctx.sh.stash["dlin_rows"] = ops._f32c(dout).reshape(-1)
+        return None, None, None
+
+
 # ------------------------------------------------------------------------------------------------
 # process-group context of a distributed model
 # ------------------------------------------------------------------------------------------------
@@ -609,9 +654,9 @@ def attach(model, group=None, max_batch=None):
     if dev.type != "cuda":
         raise RuntimeError("distribute(): the xdeepfm-b200 path needs device='cuda:N'; no CPU fallback")
     ctx = DistContext(group)
-    lin_names = [fc.name for fc in model.linear_model.sparse_feature_columns]
-    dnn_names = [fc.name for fc in model._dnn_sparse]
-    if lin_names != dnn_names or model._dnn_sparse_sel is not None or model._lin_sparse_sel is not None or not dnn_names:
+    lin_names = [fc.name for fc in list(model.linear_model.sparse_feature_columns) + list(model.linear_model.varlen_sparse_feature_columns)]
+    dnn_names = [fc.name for fc in list(model._dnn_sparse) + list(model._dnn_varlen)]
+    if lin_names != dnn_names or model._dnn_sparse_sel != model._lin_sparse_sel or not dnn_names:
         raise NotImplementedError("distribute(): the linear and the deep part must use the same sparse feature columns "
                                   "(as every xdftrain*.py script builds them)")
     emb_plan, lin_plan = model._emb_plan, model.linear_model._plan

@@ -279,7 +279,16 @@ class BaseModel(nn.Module):
         idx = cache.get(key)
         if idx is None:
             idx = cache[key] = torch.tensor(list(sel), dtype=torch.int64, device=t.device)
-        return torch.index_select(t, 1, idx)
+        # the deep and the first-order part usually select the same columns of the same batch: one tensor for both (the row-sharded
+        # lookup recognises a batch by tensor identity and then fetches its distinct rows once).  The memo holds `t`, so its
+        # address cannot be recycled while it is remembered; an in-place write bumps _version.
+        slot = ("last", t.dtype)
+        memo = cache.get(slot)
+        if memo is not None and memo[0] is t and memo[1] == t._version and memo[2] == key[0]:
+            return memo[3]
+        out = torch.index_select(t, 1, idx)
+        cache[slot] = (t, t._version, key[0], out)
+        return out
 
     # ------------------------------------------------------------------------------------------
     # inputs
@@ -296,7 +305,10 @@ class BaseModel(nn.Module):
         if self._dist is not None:
             from ..distributed import ShardedGather
             sh = self._dist.sharded
-            return ShardedGather.apply(sh, ids, sh.anchor)
+            emb = ShardedGather.apply(sh, ids, sh.anchor)
+            if self._emb_bag is not None:   # multi-value features: one slot per sequence position, pooled per field
+                emb = ops.BagPool.apply(self._emb_bag, emb, ids, self._lens(ids_all))
+            return emb
         self._tables_current(self._emb_plan, ids)
         tables = [emb.weight for emb in self.embedding_dict.values()]
         emb = ops.SparseGather.apply(self._emb_plan, self._seg_cache, ids, *tables)
@@ -312,9 +324,16 @@ class BaseModel(nn.Module):
         ids = self._select(ids_all, self._lin_sparse_sel)
         dense = self._select(dense_all, self._lin_dense_sel)
         if self._dist is not None:
-            from ..distributed import ShardedLinearTerm
+            from ..distributed import ShardedLinearRows, ShardedLinearTerm
             sh = self._dist.sharded
             has_w = len(self.linear_model.dense_feature_columns) > 0
+            if self.linear_model._bag is not None:
+                # multi-value features: per-lookup rows, pooled per field under the sequence mask, summed over the fields
+                rows = ShardedLinearRows.apply(sh, ids, sh.anchor)
+                logit = ops.BagPool.apply(self.linear_model._bag, rows, ids, self._lens(ids_all)).sum(dim=1)
+                if has_w:
+                    logit = logit + ops.linear_act(dense, self.linear_model.weight.t().contiguous(), None, None)
+                return logit
             return ShardedLinearTerm.apply(sh, ids, dense if has_w else None, self.linear_model.weight if has_w else None, sh.anchor)
         self._tables_current(self.linear_model._plan, ids)
         return self.linear_model.forward_ids(ids, dense, cache=self._seg_cache, lens=self._lens(ids_all))
@@ -462,8 +481,6 @@ class BaseModel(nn.Module):
         from .. import distributed
         if self._dist is not None:
             raise RuntimeError("distribute() was already called on this model")
-        if self._all_varlen:
-            raise NotImplementedError("distribute(): VarLenSparseFeat columns are looked up on one GPU only in this build")
         distributed.attach(self, group, max_batch)
         if self._optimizer_spec is not None:
             self.optim = self._get_optim(self._optimizer_spec)     # re-bind the optimizer to the sharded tables
