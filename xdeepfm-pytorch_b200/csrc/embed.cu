@@ -274,6 +274,7 @@ extern "C" int xdfm_embed_bwd_segments(const int32_t* ids, int64_t B, int m, con
 // entries in increasing e, then slots are combined by a fixed xor-shuffle tree (and a fixed smem order
 // across warps).  The summation order depends only on (len, D), never on scheduling -> bit-reproducible.
 #define SEG_LONG 256
+#define SEG_TINY 16
 
 template <int VEC>
 __device__ __forceinline__ void vec_add(float* a, const float* b) {
@@ -337,7 +338,7 @@ __device__ float g_seg_part_lin[SEG_ITEMS_MAX];
 // long_pass: 0 short segments + chunk list of the long ones | 3 reduce the listed chunks | legacy: -1 short only (no list),
 // 2 one block per long segment found by scanning every segment
 template <int VEC>
-__global__ void __launch_bounds__(256) seg_reduce_kernel(const float* __restrict__ demb, const float* __restrict__ dlin,
+__global__ void __launch_bounds__(256, 4) seg_reduce_kernel(const float* __restrict__ demb, const float* __restrict__ dlin,
                                                          const int32_t* __restrict__ sorted_pos,
                                                          const int32_t* __restrict__ seg_offsets,
                                                          const int32_t* __restrict__ num_segments, int m, int D, int lpr,
@@ -352,37 +353,89 @@ __global__ void __launch_bounds__(256) seg_reduce_kernel(const float* __restrict
   __shared__ float sh[8][32 * 4 + 8];
   __shared__ int sh_last;
   if (long_pass <= 0) {
+    // S segments per warp at a time.  TINY segments (<= SEG_TINY entries: nearly all of them in a Criteo-shaped batch, where the
+    // average row is looked up 4 times) are summed by ONE slot group each -- S independent (offsets -> positions -> rows) chains per
+    // warp instead of one, up to four rows in flight per group -- in entry order.  The others take the whole warp, one after another
+    // (entries dealt round-robin to the S slots, fixed shuffle tree), or go to the long pass.
     int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t s = warp; s < nseg; s += nwarps) {
-      int beg = seg_offsets[s], end = seg_offsets[s + 1];
-      if (end - beg > SEG_LONG) {          // handled by the long pass
-        if (long_pass == 0) {
-          const int nch = (end - beg + SEG_CHUNK - 1) / SEG_CHUNK;
-          int base = 0;
-          if (lane == 0) base = atomicAdd(&g_seg_item_count, nch);
-          base = __shfl_sync(0xffffffffu, base, 0);
-          for (int c = lane; c < nch; c += 32) g_seg_items[base + c] = make_int4((int)s, c, nch, base);
-          if (lane == 0) g_seg_done[base] = 0;
+    // (a warp's S segments are nwarps apart: sorted keys put the medium-length segments of a low-cardinality table next to each
+    // other, and a warp that drew eight of them in a row worked through them alone while the others had finished)
+    for (int64_t s0 = warp; s0 < nseg; s0 += nwarps * S) {
+      const int64_t sg = s0 + (int64_t)slot * nwarps;
+      int beg = 0, end = 0;
+      if (sg < nseg) {
+        beg = seg_offsets[sg];
+        end = seg_offsets[sg + 1];
+      }
+      const int len = end - beg;
+      if (len > 0 && len <= SEG_TINY) {
+        float acc[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+        float accl = 0.f;
+        for (int e = beg; e < end; e += 4) {
+          int p[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) p[u] = e + u < end ? __ldg(sorted_pos + e + u) : -1;
+          V v[4];
+          float l[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            l[u] = 0.f;
+            if (p[u] >= 0) {
+              if (active && demb != nullptr) v[u] = __ldg(reinterpret_cast<const V*>(demb + (int64_t)p[u] * D) + sub);
+              if (sub == 0 && dlin != nullptr) l[u] = __ldg(dlin + p[u] / m);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (p[u] >= 0) {
+              if (active && demb != nullptr) vec_add<VEC>(acc, reinterpret_cast<const float*>(&v[u]));
+              accl += l[u];
+            }
+          }
         }
-        continue;
-      }
-      float acc[VEC];
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
-      float accl = 0.f;
-      seg_accumulate<VEC>(demb, dlin, sorted_pos, beg + slot, end, S, m, D, sub, active, acc, accl);
-      for (int o = lpr; o < 32; o <<= 1) {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
-        accl += __shfl_xor_sync(0xffffffffu, accl, o);
-      }
-      if (slot == 0) {
         if (active && gsum != nullptr) {
 #pragma unroll
-          for (int i = 0; i < VEC; ++i) gsum[s * (int64_t)D + sub * VEC + i] = acc[i];
+          for (int i = 0; i < VEC; ++i) gsum[sg * (int64_t)D + sub * VEC + i] = acc[i];
         }
-        if (sub == 0 && gsum_lin != nullptr) gsum_lin[s] = accl;
+        if (sub == 0 && gsum_lin != nullptr) gsum_lin[sg] = accl;
+      }
+      unsigned pending = __ballot_sync(0xffffffffu, len > SEG_TINY && sub == 0);
+      while (pending) {
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1;
+        const int64_t s = s0 + (int64_t)(src / lpr) * nwarps;
+        const int wb = __shfl_sync(0xffffffffu, beg, src), we = __shfl_sync(0xffffffffu, end, src);
+        if (we - wb > SEG_LONG) {          // handled by the long pass
+          if (long_pass == 0) {
+            const int nch = (we - wb + SEG_CHUNK - 1) / SEG_CHUNK;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&g_seg_item_count, nch);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            for (int c = lane; c < nch; c += 32) g_seg_items[base + c] = make_int4((int)s, c, nch, base);
+            if (lane == 0) g_seg_done[base] = 0;
+          }
+          continue;
+        }
+        float acc[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+        float accl = 0.f;
+        seg_accumulate<VEC>(demb, dlin, sorted_pos, wb + slot, we, S, m, D, sub, active, acc, accl);
+        for (int o = lpr; o < 32; o <<= 1) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+          accl += __shfl_xor_sync(0xffffffffu, accl, o);
+        }
+        if (slot == 0) {
+          if (active && gsum != nullptr) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) gsum[s * (int64_t)D + sub * VEC + i] = acc[i];
+          }
+          if (sub == 0 && gsum_lin != nullptr) gsum_lin[s] = accl;
+        }
       }
     }
   } else {
