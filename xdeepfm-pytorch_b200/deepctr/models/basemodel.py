@@ -1071,13 +1071,22 @@ class BaseModel(nn.Module):
             epoch_logs["loss"] = (total_loss_epoch + extra_total) / sample_num
             epoch_logs.update(extra_logs)
             if want_metrics:
-                pred_host = pred_log.cpu().numpy().astype("float64")
-                y_host = y_t.numpy() if order is None else y_t[order].numpy()
+                # per-step metrics of the epoch from the device-resident prediction log: float64 on the device (metrics_device.py);
+                # metric functions it does not know, or steps sklearn would reject, go through the host exactly like the reference
+                from ..metrics_device import step_metrics
+                y_epoch = y_t if order is None else y_t[order]
+                dev_vals = step_metrics(self, self.metrics, pred_log, y_epoch.to(dev), batch_size) if n_local > 0 else None
+                if dev_vals is None:
+                    pred_host = pred_log.cpu().numpy().astype("float64")
+                    y_host = y_epoch.numpy()
                 for name, fn in self.metrics.items():
-                    vals = []
-                    for s in range(local_steps):
-                        lo, hi = s * batch_size, min(n_local, (s + 1) * batch_size)
-                        vals.append(fn(y_host[lo:hi], pred_host[lo:hi]))
+                    if dev_vals is not None:
+                        vals = dev_vals[name].cpu().numpy().tolist()
+                    else:
+                        vals = []
+                        for s in range(local_steps):
+                            lo, hi = s * batch_size, min(n_local, (s + 1) * batch_size)
+                            vals.append(fn(y_host[lo:hi], pred_host[lo:hi]))
                     if ctx is not None:
                         # per-step metrics of the LOCAL sub-batches, averaged over all ranks' steps
                         t = torch.tensor([float(np.sum(vals)), float(len(vals))], dtype=torch.float64, device=dev)
