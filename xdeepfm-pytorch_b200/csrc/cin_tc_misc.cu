@@ -175,77 +175,94 @@ __global__ void __launch_bounds__(256) cin_dy_rows_cols_kernel(const __nv_bfloat
   const int c0 = blockIdx.y * 64;
   const bool hidden_ready = dnext == nullptr && dnext_pitch < 0;
   {
+    // One thread = one row x two granules of 8 channels.  A granule is (A) entirely inside the hidden half the dX kernel of the layer
+    // above already wrote: copied as it is; (B) entirely direct-connect with a pooled upstream gradient: 2 x 128-bit loads under
+    // the activation mask; (C) anything else (the granule that straddles the split, un-pooled maps, fp32 dnext, ragged tails): per
+    // element.  (The per-element form for every granule cost 225 instructions per granule and made the kernel issue-bound.)
     const int rr = threadIdx.x >> 2, cg = (threadIdx.x & 3) * 16;
     const int64_t r = r0 + rr;
-    const int64_t b = r / D;
-    const int d = (int)(r - b * D);
+    const bool row_ok = r < R;
+    const uint32_t b32 = row_ok ? (uint32_t)r / (uint32_t)D : 0u;          // R < 2^32: checked by the host
+    const int64_t b = (int64_t)b32;
+    const int d = (int)((uint32_t)r - b32 * (uint32_t)D);
+    const __nv_bfloat16* yrow = yt + r * Hs;
+    __nv_bfloat16* drow = dyt + r * Hs;
+    const int hid_end = hidden_ready ? n_next : 0;
+    const bool pooled_fast = dpooled != nullptr && dmaps == nullptr && (reinterpret_cast<uintptr_t>(dpooled) & 15) == 0;
 #pragma unroll
     for (int g8 = 0; g8 < 2; ++g8) {
       const int h0 = c0 + cg + g8 * 8;
-      float g[8];
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      bool store = false;
+      if (row_ok && h0 < Hs) {
+        const int64_t pidx = b * fm_total + col_off + (h0 - hdb);
+        if (h0 + 8 <= hid_end) {
+          o = *reinterpret_cast<const uint4*>(drow + h0);                                  // (A)
+        } else if (pooled_fast && h0 >= hdb && h0 >= n_next && h0 + 8 <= H && (pidx & 3) == 0) {
+          const uint4 yv = *reinterpret_cast<const uint4*>(yrow + h0);                     // (B)
+          const float4 p0 = *reinterpret_cast<const float4*>(dpooled + pidx), p1 = *reinterpret_cast<const float4*>(dpooled + pidx + 4);
+          float g[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+          if (act == XDFM_ACT_RELU) {
+            const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) g[i] = 0.f;
-      if (r < R && h0 < Hs) {
-        const uint4 yv = *reinterpret_cast<const uint4*>(yt + r * Hs + h0);
-        const __nv_bfloat16* yb = reinterpret_cast<const __nv_bfloat16*>(&yv);
-        // next layer's input gradient for these 8 channels: two 128-bit loads when the whole granule lies inside it
-        float dn[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) dn[i] = 0.f;
-        // dnext_pitch < 0: the hidden-half channels [0, n_next) of dyt were already written by the dX kernel of the layer above
-        // (xdfm_cin_bwd_dx_tc_dy); they are taken over as they are, the direct-connect channels are computed as usual
-        uint4 old8 = make_uint4(0u, 0u, 0u, 0u);
-        if (hidden_ready && h0 < n_next) old8 = *reinterpret_cast<const uint4*>(dyt + r * Hs + h0);
-        const __nv_bfloat16* oldb = reinterpret_cast<const __nv_bfloat16*>(&old8);
-        if (dnext != nullptr && h0 < n_next) {
-          const float* dsrc = dnext + r * dnext_pitch + h0;
-          if (h0 + 8 <= n_next && (dnext_pitch & 3) == 0) {
-            const float4 a = *reinterpret_cast<const float4*>(dsrc), c = *reinterpret_cast<const float4*>(dsrc + 4);
-            dn[0] = a.x; dn[1] = a.y; dn[2] = a.z; dn[3] = a.w; dn[4] = c.x; dn[5] = c.y; dn[6] = c.z; dn[7] = c.w;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (h0 + i < n_next) dn[i] = dsrc[i];
-          }
-        }
-        // pooled-output gradient of these 8 channels (direct-connect range h >= hdb): two 128-bit loads when aligned
-        float dpv[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) dpv[i] = 0.f;
-        if (dpooled != nullptr && h0 + 8 > hdb) {
-          const int64_t pidx = b * fm_total + col_off + (h0 - hdb);
-          if (h0 >= hdb && h0 + 8 <= H && (pidx & 3) == 0 && (reinterpret_cast<uintptr_t>(dpooled) & 15) == 0) {
-            const float4 a = *reinterpret_cast<const float4*>(dpooled + pidx), c = *reinterpret_cast<const float4*>(dpooled + pidx + 4);
-            dpv[0] = a.x; dpv[1] = a.y; dpv[2] = a.z; dpv[3] = a.w; dpv[4] = c.x; dpv[5] = c.y; dpv[6] = c.z; dpv[7] = c.w;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (h0 + i >= hdb && h0 + i < H) dpv[i] = dpooled[pidx + i];
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int h = h0 + i;
-          float v = 0.f;
-          if (h < H) {
-            if (h >= hdb) {
-              v += dpv[i];
-              if (dmaps) v += dmaps[(b * fm_total + col_off + (h - hdb)) * (int64_t)D + d];
+            for (int i = 0; i < 4; ++i) {
+              if (!(__uint_as_float(yw[i] << 16) > 0.f)) g[2 * i] = 0.f;                   // bf16 -> fp32 is a 16-bit shift
+              if (!(__uint_as_float(yw[i] & 0xffff0000u) > 0.f)) g[2 * i + 1] = 0.f;
             }
-            v += dn[i];
-            if (act == XDFM_ACT_RELU && !(__bfloat162float(yb[i]) > 0.f)) v = 0.f;
-            if (hidden_ready && h < n_next) v = __bfloat162float(oldb[i]);       // exact: re-rounded to the same bf16 below
           }
-          g[i] = v;
+          __nv_bfloat162 t0 = __floats2bfloat162_rn(g[0], g[1]), t1 = __floats2bfloat162_rn(g[2], g[3]);
+          __nv_bfloat162 t2 = __floats2bfloat162_rn(g[4], g[5]), t3 = __floats2bfloat162_rn(g[6], g[7]);
+          o.x = *reinterpret_cast<uint32_t*>(&t0); o.y = *reinterpret_cast<uint32_t*>(&t1);
+          o.z = *reinterpret_cast<uint32_t*>(&t2); o.w = *reinterpret_cast<uint32_t*>(&t3);
+          store = true;
+        } else {
+          float g[8];                                                                      // (C)
+          const uint4 yv = *reinterpret_cast<const uint4*>(yrow + h0);
+          const __nv_bfloat16* yb = reinterpret_cast<const __nv_bfloat16*>(&yv);
+          // next layer's input gradient for these 8 channels: two 128-bit loads when the whole granule lies inside it
+          float dn[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dn[i] = 0.f;
+          // dnext_pitch < 0: the hidden-half channels [0, n_next) of dyt were already written by the dX kernel of the layer above
+          // (xdfm_cin_bwd_dx_tc_dy); they are taken over as they are, the direct-connect channels are computed as usual
+          uint4 old8 = make_uint4(0u, 0u, 0u, 0u);
+          if (hidden_ready && h0 < n_next) old8 = *reinterpret_cast<const uint4*>(drow + h0);
+          const __nv_bfloat16* oldb = reinterpret_cast<const __nv_bfloat16*>(&old8);
+          if (dnext != nullptr && h0 < n_next) {
+            const float* dsrc = dnext + r * dnext_pitch + h0;
+            if (h0 + 8 <= n_next && (dnext_pitch & 3) == 0) {
+              const float4 a = *reinterpret_cast<const float4*>(dsrc), c = *reinterpret_cast<const float4*>(dsrc + 4);
+              dn[0] = a.x; dn[1] = a.y; dn[2] = a.z; dn[3] = a.w; dn[4] = c.x; dn[5] = c.y; dn[6] = c.z; dn[7] = c.w;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (h0 + i < n_next) dn[i] = dsrc[i];
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int h = h0 + i;
+            float v = 0.f;
+            if (h < H) {
+              if (h >= hdb) {
+                if (dpooled) v += dpooled[pidx + i];
+                if (dmaps) v += dmaps[(pidx + i) * (int64_t)D + d];
+              }
+              v += dn[i];
+              if (act == XDFM_ACT_RELU && !(__bfloat162float(yb[i]) > 0.f)) v = 0.f;
+              if (hidden_ready && h < n_next) v = __bfloat162float(oldb[i]);       // exact: re-rounded to the same bf16 below
+            }
+            g[i] = v;
+          }
+          __nv_bfloat162 t0 = __floats2bfloat162_rn(g[0], g[1]), t1 = __floats2bfloat162_rn(g[2], g[3]);
+          __nv_bfloat162 t2 = __floats2bfloat162_rn(g[4], g[5]), t3 = __floats2bfloat162_rn(g[6], g[7]);
+          o.x = *reinterpret_cast<uint32_t*>(&t0); o.y = *reinterpret_cast<uint32_t*>(&t1);
+          o.z = *reinterpret_cast<uint32_t*>(&t2); o.w = *reinterpret_cast<uint32_t*>(&t3);
+          store = true;
         }
       }
-      uint4 o;
-      __nv_bfloat162 t0 = __floats2bfloat162_rn(g[0], g[1]), t1 = __floats2bfloat162_rn(g[2], g[3]);
-      __nv_bfloat162 t2 = __floats2bfloat162_rn(g[4], g[5]), t3 = __floats2bfloat162_rn(g[6], g[7]);
-      o.x = *reinterpret_cast<uint32_t*>(&t0); o.y = *reinterpret_cast<uint32_t*>(&t1);
-      o.z = *reinterpret_cast<uint32_t*>(&t2); o.w = *reinterpret_cast<uint32_t*>(&t3);
       *reinterpret_cast<uint4*>(&tile[rr][cg + g8 * 8]) = o;
-      if (r < R && h0 < Hs && !(hidden_ready && h0 + 8 <= n_next)) *reinterpret_cast<uint4*>(dyt + r * Hs + h0) = o;
+      if (store) *reinterpret_cast<uint4*>(drow + h0) = o;
     }
   }
   __syncthreads();
@@ -306,6 +323,7 @@ extern "C" int xdfm_cin_dy_rows_cols_db(const void* yt, int64_t B, int D, int H,
   XDFM_CHECK_ARG(act == XDFM_ACT_RELU || act == XDFM_ACT_NONE, "cin_dy_rows_cols: activation %d not supported on the bf16 path", act);
   const int64_t R = B * (int64_t)D;
   if (R == 0) return XDFM_OK;
+  XDFM_CHECK_ARG(R < ((int64_t)1 << 32), "cin_dy_rows_cols: B * D = %lld rows exceed the 32-bit row arithmetic of the kernel", (long long)R);
   dim3 grid((unsigned)ceil_div64(R, 64), (unsigned)ceil_div64(H_pad, 64));
   cin_dy_rows_cols_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)yt, R, D, H, Hs, H_pad, direct_begin, dpooled, dmaps,
                                                                   fm_total, col_off, dnext, dnext_pitch, n_next, act, (__nv_bfloat16*)dyt,
