@@ -128,3 +128,30 @@ def test_head_backward_in_one_pass(B, fm, hd, binary):
         assert_close(d_dnn, gl[:, None] * wd.double()[None, :], 1e-6, 1e-7, "d_dnn")
         assert_close(d_w[fm:fm + hd], (gl[:, None] * dnn.double()).sum(0), 1e-5, 1e-5 * (B ** 0.5), "d_w_dnn")
     assert_close(d_w[fm + hd:], gl.sum().reshape(1), 1e-5, 1e-5 * (B ** 0.5), "d_bias")
+
+
+def test_parameter_gradients_written_in_place_equal_autograd_accumulation():
+    """ops.direct_param_grads (fused training step): the first gradient of a parameter in a backward pass is written straight into
+    its zeroed p.grad view, later uses of the same parameter are accumulated by autograd -- same bits as the plain path."""
+    g = torch.Generator().manual_seed(3)
+    W = torch.nn.Parameter(torch.randn(24, 40, generator=g).to(DEV))
+    b = torch.nn.Parameter(torch.randn(24, generator=g).to(DEV))
+    x1, x2 = torch.randn(64, 40, generator=g).to(DEV), torch.randn(32, 40, generator=g).to(DEV)
+    W.grad, b.grad = torch.zeros_like(W), torch.zeros_like(b)
+    ptrs = (W.grad.data_ptr(), b.grad.data_ptr())
+
+    def run(direct):
+        W.grad.zero_()
+        b.grad.zero_()
+        ops.direct_param_grads(direct)
+        try:
+            out = ops.LinearActTC.apply(x1, W, b, 1).sum() + ops.LinearActTC.apply(x2, W, b, 1).square().sum()
+            out.backward()
+        finally:
+            ops.direct_param_grads(False)
+        assert (W.grad.data_ptr(), b.grad.data_ptr()) == ptrs
+        return W.grad.clone(), b.grad.clone()
+
+    plain, direct = run(False), run(True)
+    assert float(plain[0].abs().max()) > 0 and float(plain[1].abs().max()) > 0
+    assert torch.equal(plain[0], direct[0]) and torch.equal(plain[1], direct[1])

@@ -886,9 +886,11 @@ class BaseModel(nn.Module):
         for ts in opt.table_sets:
             ts.plan.sparse_grad = True      # backward leaves (unique rows, segment sums) for the fused optimizer
         self._in_train_step = True
+        ops.direct_param_grads(True)        # p.grad views were just zeroed: the hot layers write their gradients in place
         try:
             return self._train_step_inner(opt, ids, dense, y, loss_accum, pred_log, pred_off)
         finally:
+            ops.direct_param_grads(False)
             self._in_train_step = False
             for ts in opt.table_sets:
                 ts.plan.sparse_grad = False

@@ -491,7 +491,7 @@ class CINFunctionTC(torch.autograd.Function):
             xkT = x0T if reuse_x0T else torch.empty((HpQ, R), dtype=torch.bfloat16, device=dev)
             with timed("cin_layout"):
                 # (dnext = None with pitch -1: the hidden half of dyt is already there)
-                db = torch.empty(H, dtype=torch.float32, device=dev)
+                db, db_ret = _grad_dst(wb[2 * k + 1], (H,))
                 dbws = workspace("cin_db_part", L.xdfm_cin_dy_db_workspace_bytes(B, D, H_pad), dev)
                 N.check(L.xdfm_cin_dy_rows_cols_db(N.ptr(yt), B, D, H, Hs, H_pad, cfg.direct_begin[k], N.ptr(dout) if cfg.pool else None,
                                                    None if cfg.pool else N.ptr(dout), cfg.fm, cfg.col_off[k], N.ptr(dnext),
@@ -500,7 +500,7 @@ class CINFunctionTC(torch.autograd.Function):
                 if not reuse_x0T:
                     N.check(L.xdfm_rows_to_cols_bf16(N.ptr(xkt), xkt.shape[1], R, Hp, HpQ, N.ptr(xkT), st))
             W = _f32c(wb[2 * k]).view(H, -1)
-            dW = torch.empty_like(W)
+            dW, dW_ret = _grad_dst(wb[2 * k], W.shape)
             nb = L.xdfm_cin_bwd_dw_tc_workspace_bytes(B, m, Hp, H, D)
             if nb < 0:
                 raise RuntimeError("libxdfm: " + L.xdfm_last_error().decode())
@@ -526,14 +526,42 @@ class CINFunctionTC(torch.autograd.Function):
                 with timed("cin_bwd"):
                     N.check(L.xdfm_cin_bwd_dx_tc(N.ptr(dyt), N.ptr(x0t), N.ptr(xkt), xkt.shape[1], N.ptr(W), N.ptr(wt), B, m, Hp, H, D,
                                                  N.ptr(dxk), N.ptr(dx0_parts[k]), st))
-            grads[2 * k] = dW.view(wb[2 * k].shape)
-            grads[2 * k + 1] = db
+            grads[2 * k] = dW_ret
+            grads[2 * k + 1] = db_ret
             dnext, dnext_pitch = dxk, HpQ
         dx0 = torch.empty((B, m, D), dtype=torch.float32, device=dev)
         with timed("cin_layout"):
             # every layer's planes + layer 0's dXk (X^{k-1} is X^0 itself there), back in the reference layout
             N.check(L.xdfm_cin_dx0_finish(N.ptr(dx0_parts), 2 * n_layers, N.ptr(dnext), dnext_pitch, B, m, D, mP, N.ptr(dx0), st))
         return (None, dx0) + tuple(grads)
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter gradients written in place (fused training step only)
+# ------------------------------------------------------------------------------------------------
+_DIRECT = {"on": False, "done": set()}
+
+
+def direct_param_grads(on):
+    """The fused training step zeroes one flat gradient buffer and binds every dense p.grad to a view of it.  While this is on, the
+    backward kernels of the hot layers write a parameter's gradient straight into that view and hand autograd None, so no
+    `p.grad += g` launch follows (one small add per parameter per step before).  Only the FIRST gradient of a parameter in a
+    backward pass goes in place -- the view is still zero then; a parameter used twice gets its later contributions accumulated
+    by autograd as usual."""
+    _DIRECT["on"] = bool(on)
+    _DIRECT["done"].clear()
+
+
+def _grad_dst(param, shape=None):
+    """-> (tensor the kernel writes d(param) into, value to return to autograd for it)."""
+    shape = tuple(param.shape) if shape is None else tuple(shape)
+    g = param.grad if (_DIRECT["on"] and isinstance(param, torch.nn.Parameter) and param.is_leaf) else None
+    if g is not None and g.dtype == torch.float32 and g.is_cuda and g.is_contiguous() and g.shape == param.shape and \
+            id(param) not in _DIRECT["done"]:
+        _DIRECT["done"].add(id(param))
+        return g.view(shape), None
+    t = torch.empty(shape, dtype=torch.float32, device=param.device)
+    return t, t.view(param.shape)
 
 
 def cin_apply(cfg, x0, *wb):
@@ -614,10 +642,10 @@ def cvt_bf16(src, transpose=False):
     return dst
 
 
-def gemm_tc(A, Bm, M, Nn, K, bias=None, act=0):
+def gemm_tc(A, Bm, M, Nn, K, bias=None, act=0, out=None):
     """fp32 [M, Nn] = act(A[M, K] . Bm[Nn, K]^T + bias) on tcgen05; A / Bm bf16 K-major (from cvt_bf16)."""
     L = N.lib()
-    C = torch.empty((M, Nn), dtype=torch.float32, device=A.device)
+    C = torch.empty((M, Nn), dtype=torch.float32, device=A.device) if out is None else out
     nb = L.xdfm_gemm_tc_workspace_bytes(M, Nn, K)
     ws = workspace("gemm_tc", nb, A.device)
     with timed("gemm"):
@@ -626,7 +654,7 @@ def gemm_tc(A, Bm, M, Nn, K, bias=None, act=0):
     return C
 
 
-def cvt_bf16_both(src, want_rows=True, want_cols=True, y=None, act=0, want_colsum=False):
+def cvt_bf16_both(src, want_rows=True, want_cols=True, y=None, act=0, want_colsum=False, colsum_out=None):
     """One pass over fp32 [R, C]: g = src * act'(y) -> (bf16 [R, C8] or None, bf16 [C, R8] or None, fp32 column sums [C] or None)."""
     R, C = src.shape
     require_cuda(src, "cvt_bf16_both")
@@ -635,7 +663,7 @@ def cvt_bf16_both(src, want_rows=True, want_cols=True, y=None, act=0, want_colsu
     L = N.lib()
     rows = torch.empty((R, _r8(C)), dtype=torch.bfloat16, device=dev) if want_rows else None
     cols = torch.empty((C, _r8(R)), dtype=torch.bfloat16, device=dev) if want_cols else None
-    colsum = torch.empty(C, dtype=torch.float32, device=dev) if want_colsum else None
+    colsum = (torch.empty(C, dtype=torch.float32, device=dev) if colsum_out is None else colsum_out) if want_colsum else None
     ws = workspace("cvt_both", L.xdfm_cvt_bf16_both_workspace_bytes(R, C), dev) if want_colsum else None
     N.check(L.xdfm_cvt_bf16_both(N.ptr(src), N.ptr(y), int(act), R, C, C, N.ptr(rows), 0 if rows is None else rows.shape[1], N.ptr(cols),
                                  0 if cols is None else cols.shape[1], N.ptr(colsum), N.ptr(ws), 0 if ws is None else ws.numel(),
@@ -655,6 +683,7 @@ class LinearActTC(torch.autograd.Function):
         require_cuda(x, "LinearActTC")
         shp = x.shape
         x2 = _f32c(x).reshape(-1, shp[-1])
+        W_in = W
         W = _f32c(W)
         Bn, K = x2.shape
         Nn = W.shape[0]
@@ -665,6 +694,7 @@ class LinearActTC(torch.autograd.Function):
         y = gemm_tc(xb, wb, Bn, Nn, K, None if b is None else _f32c(b), act)
         ctx.save_for_backward(xT, wT, y if act != 0 else None)
         ctx.act, ctx.has_bias, ctx.shp, ctx.dims = act, b is not None, shp, (Bn, K, Nn)
+        ctx.params = (W_in, b)                  # the leaves themselves: their gradients may be written in place (direct_param_grads)
         return y.view(*shp[:-1], Nn)
 
     @staticmethod
@@ -673,14 +703,19 @@ class LinearActTC(torch.autograd.Function):
         Bn, K, Nn = ctx.dims
         dy = _f32c(dy).reshape(Bn, Nn)
         need_dx, need_dw, need_db = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        W_in, b_in = ctx.params
+        db_dst = db_ret = None
+        if need_db:
+            db_dst, db_ret = _grad_dst(b_in, (Nn,))
         with timed("gemm_cvt"):
-            dyb, dyT, db = cvt_bf16_both(dy, need_dx, need_dw, y=y, act=ctx.act, want_colsum=need_db)
-        dx = dW = None
+            dyb, dyT, _ = cvt_bf16_both(dy, need_dx, need_dw, y=y, act=ctx.act, want_colsum=need_db, colsum_out=db_dst)
+        dx = dW_ret = None
         if need_dx:
             dx = gemm_tc(dyb, wT, Bn, K, Nn).view(ctx.shp)
         if need_dw:
-            dW = gemm_tc(dyT, xT, Nn, K, Bn)
-        return dx, dW, db, None
+            dW, dW_ret = _grad_dst(W_in, (Nn, K))
+            gemm_tc(dyT, xT, Nn, K, Bn, out=dW)
+        return dx, dW_ret, db_ret, None
 
 
 SMALL_LINEAR_MAX = 32
