@@ -182,6 +182,8 @@ int xdfm_embed_expand_unique(const float* u_emb, const float* u_lin, const int32
  * basemodel.py:63-92 with inputs.py:141-155) */
 int xdfm_embed_expand_unique_lin_rows(const float* u_lin, const int32_t* inv, int64_t n, float* out, void* stream);
 
+/* diagnostic: 0 = the lazy replay uses scalar arithmetic everywhere (default 1: packed fp32 pairs for 4-wide Adam pieces; same bits) */
+int xdfm_set_replay_packed(int on);
 /* diagnostic: 1 = first version of the dense-table streaming pass, 2 = unrolled / streaming-hint version (default) */
 void xdfm_set_rows_opt_dense_version(int v);
 

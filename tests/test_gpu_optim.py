@@ -120,3 +120,44 @@ def test_lazy_replay_is_bit_identical_to_the_dense_pass(kind, hist_cap):
     for a, b in zip(dense_r[0] + dense_r[1] + dense_r[2], lazy_r[0] + lazy_r[1] + lazy_r[2]):
         assert torch.equal(a, b)
     assert abs(dense_r[3] - lazy_r[3]) <= 1e-6 * abs(dense_r[3])      # same terms, different summation order (float atomics)
+
+
+def test_packed_replay_is_bit_identical_to_the_scalar_replay():
+    """The lazy replay of 4-wide Adam pieces runs on packed fp32 pairs (fma / mul .f32x2); the diagnostic switch turns it off.
+    Tables and both moments must not differ in a single bit (this caught ptxas contracting mul.rn.f32x2 + sub.rn.f32x2 into FFMA2)."""
+    from deepctr import _native as N, ops
+    from deepctr.optim import FusedOptimizer, TableSet
+    L = N.lib()
+
+    def run(packed):
+        N.check(L.xdfm_set_replay_packed(int(packed)))
+        g = torch.Generator().manual_seed(11)
+        vocab, D, B = [300, 9, 2000], 8, 64
+        tabs = [torch.nn.Parameter(torch.randn(v, D, generator=g).to(DEV)) for v in vocab]
+        w = torch.nn.Parameter(torch.ones(3, device=DEV))
+        plan = ops.SparsePlan([0, 1, 2], vocab, D)
+        plan.sparse_grad = True
+        opt = FusedOptimizer("adam", [("w", w)], [TableSet(plan, tabs, 1e-3)], {})
+        opt.lazy_tables = True
+        cache = ops.SegmentCache()
+        for s in range(9):
+            ids = torch.stack([torch.clamp((float(v) ** torch.rand(B, generator=g)).long() - 1, 0, v - 1) for v in vocab], 1)
+            ids = ids.to(torch.int32).to(DEV)
+            dout = torch.randn(B, 3, D, generator=g).to(DEV)
+            opt.zero_grad()
+            opt.prepare()
+            cache.clear()
+            opt.catch_up(plan, cache, ids)
+            out = ops.SparseGather.apply(plan, cache, ids, *tabs)
+            torch.autograd.backward([out], [dout])
+            opt.step(apply_l2=True)
+        opt.flush()
+        ts = opt.table_sets[0]
+        return [p.detach().clone() for p in tabs] + [t.clone() for t in ts.s1] + [t.clone() for t in ts.s2]
+
+    try:
+        scalar, packed = run(0), run(1)
+    finally:
+        N.check(L.xdfm_set_replay_packed(1))
+    for a, b in zip(scalar, packed):
+        assert torch.equal(a, b)

@@ -59,9 +59,17 @@ __device__ __forceinline__ OptScalars load_scalars(const xdfm_opt_cfg& c, const 
 // kernel and the lazy replay produce bit-identical results wherever the same update is computed.  Square roots and quotients use
 // the SFU approximations (sqrt.approx / rcp-based division, <= 2 ulp): the lazy replay of postponed rows is pure ALU work and two
 // IEEE divisions per element and step would triple its cost; the parity tests against torch.optim hold at 1e-4 of the update.
+// (.ftz forms: ONE MUFU instruction for the square root, MUFU.RCP + FMUL for the quotient; without .ftz each carries a
+// subnormal-range check and rescaling, ~4 extra instructions, i.e. half of the replay's issue slots.  Subnormal inputs are flushed:
+// that only concerns second moments below 1e-38, where sqrt(v) + eps == eps either way.)
 __device__ __forceinline__ float fast_sqrt(float x) {
   float r;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_div(float a, float b) {
+  float r;
+  asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
   return r;
 }
 __device__ __forceinline__ void opt_apply(const OptScalars& h, float& w, float g, float& s1, float& s2) {
@@ -73,19 +81,19 @@ __device__ __forceinline__ void opt_apply(const OptScalars& h, float& w, float g
       s1 = __fmaf_rn(h.one_minus_b1, __fsub_rn(g, s1), s1);                      // exp_avg.lerp_(grad, 1-beta1)
       s2 = __fmaf_rn(h.one_minus_b2, __fmul_rn(g, g), __fmul_rn(s2, h.b2));      // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1-beta2)
       const float denom = __fmaf_rn(fast_sqrt(s2), h.bc2_sqrt, h.eps);           // sqrt(v) / sqrt(bias_correction2) + eps
-      w = __fsub_rn(w, __fmul_rn(h.step_size, __fdividef(s1, denom)));           // param.addcdiv_(exp_avg, denom, value=-step_size)
+      w = __fsub_rn(w, __fmul_rn(h.step_size, fast_div(s1, denom)));           // param.addcdiv_(exp_avg, denom, value=-step_size)
       break;
     }
     case XDFM_OPT_ADAGRAD: {
       s1 = __fmaf_rn(g, g, s1);                                                  // state_sum.addcmul_(grad, grad, value=1)
       const float stdv = __fadd_rn(fast_sqrt(s1), h.eps);
-      w = __fsub_rn(w, __fmul_rn(h.clr, __fdividef(g, stdv)));
+      w = __fsub_rn(w, __fmul_rn(h.clr, fast_div(g, stdv)));
       break;
     }
     case XDFM_OPT_RMSPROP: {
       s1 = __fmaf_rn(h.one_minus_alpha, __fmul_rn(g, g), __fmul_rn(s1, h.alpha));   // square_avg.mul_(alpha).addcmul_(g, g, 1-alpha)
       const float avg = __fadd_rn(fast_sqrt(s1), h.eps);
-      w = __fsub_rn(w, __fmul_rn(h.lr, __fdividef(g, avg)));
+      w = __fsub_rn(w, __fmul_rn(h.lr, fast_div(g, avg)));
       break;
     }
   }
@@ -410,10 +418,84 @@ extern "C" int xdfm_opt_tick_hist(float* opt_dev, const xdfm_opt_cfg* cfg, float
   return XDFM_OK;
 }
 
+// diagnostic switch (tests): 0 = scalar replay everywhere
+__device__ int g_replay_packed = 1;
+extern "C" int xdfm_set_replay_packed(int on) {
+  XDFM_CUDA(cudaMemcpyToSymbol(g_replay_packed, &on, sizeof(int)));
+  return XDFM_OK;
+}
+
+// Packed fp32 pairs (Blackwell fma / mul / add / sub .f32x2): each lane is the IEEE round-to-nearest result of the scalar intrinsic,
+// so a replay written with them agrees bit for bit with opt_apply -- at half the issue slots.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk2(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpk2(f32x2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) {
+  f32x2_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// a - b as fma(b, -1, a): exact product, one rounding == sub.rn.  (ptxas contracts `mul.rn.f32x2` followed by `sub.rn.f32x2` into
+// one FFMA2 -- the explicit .rn does not protect the packed forms the way it protects the scalar ones -- which changed 2 % of the
+// replayed weights by an ulp or more against the scalar kernels.  A product cannot be folded into an FMA's operand.)
+__device__ __forceinline__ f32x2_t sub2(f32x2_t a, f32x2_t b) {
+  const f32x2_t neg1 = 0xbf800000bf800000ull;                       // (-1.f, -1.f)
+  return fma2(b, neg1, a);
+}
+
+// Adam replay of a 4-element piece.  The replay of postponed rows is pure ALU work (every element of every table, every step the
+// row was not looked up): ~20 issue slots per element and step in the scalar form, next to two MUFU operations (sqrt.approx, the
+// reciprocal of the quotient) that cannot be avoided.  Here the multiply / add work runs on packed pairs; same bits as opt_apply.
+__device__ __forceinline__ void replay_adam4(const xdfm_opt_cfg& cfg, const OptScalars& h, const float4* __restrict__ hist, long long hist_base,
+                                             int from, int to, float* w, float* a, float* b, float& reg) {
+  const float c2 = __fmul_rn(2.f, cfg.l2);
+  const f32x2_t c2l2 = pk2(c2, c2), l2p = pk2(cfg.l2, cfg.l2);
+  const f32x2_t omb1 = pk2(h.one_minus_b1, h.one_minus_b1), omb2 = pk2(h.one_minus_b2, h.one_minus_b2), b2p = pk2(h.b2, h.b2);
+  const f32x2_t epsp = pk2(h.eps, h.eps);
+  f32x2_t W[2] = {pk2(w[0], w[1]), pk2(w[2], w[3])}, A[2] = {pk2(a[0], a[1]), pk2(a[2], a[3])}, Bv[2] = {pk2(b[0], b[1]), pk2(b[2], b[3])};
+  f32x2_t regp = pk2(0.f, 0.f);
+  for (int s = from + 1; s <= to; ++s) {
+    const float4 hs = __ldg(hist + ((long long)s - hist_base));
+    const f32x2_t ss = pk2(hs.x, hs.x), bc = pk2(hs.y, hs.y);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      regp = fma2(l2p, mul2(W[p], W[p]), regp);
+      const f32x2_t g = mul2(c2l2, W[p]);                                     // l2_grad
+      A[p] = fma2(omb1, sub2(g, A[p]), A[p]);                                 // exp_avg.lerp_(grad, 1-beta1)
+      Bv[p] = fma2(omb2, mul2(g, g), mul2(Bv[p], b2p));                       // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1-beta2)
+      float v0, v1, m0, m1, d0, d1;
+      unpk2(Bv[p], v0, v1);
+      const f32x2_t denom = fma2(pk2(fast_sqrt(v0), fast_sqrt(v1)), bc, epsp);   // sqrt(v) / sqrt(bias_correction2) + eps
+      unpk2(denom, d0, d1);
+      unpk2(A[p], m0, m1);
+      W[p] = sub2(W[p], mul2(ss, pk2(fast_div(m0, d0), fast_div(m1, d1))));   // param.addcdiv_(exp_avg, denom, value=-step_size)
+    }
+  }
+  unpk2(W[0], w[0], w[1]); unpk2(W[1], w[2], w[3]);
+  unpk2(A[0], a[0], a[1]); unpk2(A[1], a[2], a[3]);
+  unpk2(Bv[0], b[0], b[1]); unpk2(Bv[1], b[2], b[3]);
+  float r0, r1;
+  unpk2(regp, r0, r1);
+  reg += r0 + r1;
+}
+
 // replay steps (from, to] of an untouched row piece: g = 2*l2*w at every step, exactly as rows_opt_dense does
 template <int VEC>
 __device__ __forceinline__ void replay_steps(const xdfm_opt_cfg& cfg, OptScalars h, const float4* __restrict__ hist, long long hist_base,
                                              int from, int to, float* w, float* a, float* b, float& reg) {
+  if (VEC == 4 && cfg.kind == XDFM_OPT_ADAM && g_replay_packed) {
+    replay_adam4(cfg, h, hist, hist_base, from, to, w, a, b, reg);
+    return;
+  }
   for (int s = from + 1; s <= to; ++s) {
     const float4 hs = __ldg(hist + ((long long)s - hist_base));
     h.step_size = hs.x;

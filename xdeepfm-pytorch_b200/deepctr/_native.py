@@ -116,6 +116,7 @@ _SIGS = {
     "xdfm_cvt_bf16_both_workspace_bytes": (c_int64, [c_int, c_int]),
     "xdfm_cvt_bf16_both": (c_int, [_P, _P, c_int, c_int, c_int, c_int64, _P, c_int64, _P, c_int64, _P, _P, c_int64, _P]),
     "xdfm_set_rows_opt_dense_version": (None, [c_int]),
+    "xdfm_set_replay_packed": (c_int, [c_int]),
     "xdfm_cin_dx_set_debug": (None, [c_int]),
     "xdfm_cin_dw_set_jp": (None, [c_int]),
     "xdfm_cin_dw_set_pack": (None, [c_int]),
