@@ -170,7 +170,7 @@ int xdfm_embed_gather_sharded_lazy(const void* ptrs_dev, const int64_t* feat_bas
 /* Row-sharded lookup through the batch's DISTINCT rows (replaces the nn.DataParallel replica lookup of basemodel.py:206-209, 354-380 at
  * G > 1): uniq_keys / seg_offsets / sorted_pos / num_segments are xdfm_shard_segments' outputs for this batch (the backward reuses them);
  * every distinct row crosses NVLink once into u_emb [nseg, D] / u_lin [nseg] (either may be NULL), replayed when stale (hist != NULL:
- * lazy tables; hist == NULL: tables are current, cfg_* / opt_dev ignored); inv [n] = segment of lookup q = b*m + f, n = B*m.
+ * lazy tables; hist == NULL: tables are current, cfg_* / opt_dev ignored); inv [n] = segment of lookup q = b*m + f, n = B*m (NULL = skip).
  * xdfm_embed_expand_unique then writes out_emb [B, m, D] = u_emb[inv] and out_lin [B] = sum_f u_lin[inv[b, f]] + dense[b,:] . dense_w. */
 int xdfm_embed_fetch_unique_sharded(const void* ptrs_dev, int G, uint32_t key_stride, int D, const uint32_t* uniq_keys,
                                     const int32_t* seg_offsets, const int32_t* sorted_pos, const int32_t* num_segments, int64_t n,

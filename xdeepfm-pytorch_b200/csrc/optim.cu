@@ -878,8 +878,8 @@ extern "C" int xdfm_embed_fetch_unique_sharded(const void* ptrs_dev, int G, uint
                                                const xdfm_opt_cfg* cfg_emb, const xdfm_opt_cfg* cfg_lin, const float* opt_dev, const float* hist,
                                                int64_t hist_base, float* u_emb, float* u_lin, int32_t* inv, void* stream) {
   XDFM_CHECK_ARG(G >= 1 && G <= 16 && key_stride > 0, "embed_fetch_unique_sharded: G=%d key_stride=%u", G, key_stride);
-  XDFM_CHECK_ARG(ptrs_dev != nullptr && uniq_keys != nullptr && seg_offsets != nullptr && sorted_pos != nullptr && num_segments != nullptr &&
-                     inv != nullptr, "embed_fetch_unique_sharded: null argument");
+  XDFM_CHECK_ARG(ptrs_dev != nullptr && uniq_keys != nullptr && seg_offsets != nullptr && sorted_pos != nullptr && num_segments != nullptr,
+                 "embed_fetch_unique_sharded: null argument");
   XDFM_CHECK_ARG(hist == nullptr || (opt_dev != nullptr && cfg_emb != nullptr && cfg_lin != nullptr),
                  "embed_fetch_unique_sharded: lazy tables need cfg_emb, cfg_lin and opt_dev");
   XDFM_CHECK_ARG(u_emb == nullptr || (D >= 4 && D % 4 == 0), "embed_fetch_unique_sharded: D=%d must be a multiple of 4", D);
@@ -899,9 +899,11 @@ extern "C" int xdfm_embed_fetch_unique_sharded(const void* ptrs_dev, int G, uint
                                                             hist ? *cfg_lin : none, opt_dev, (const float4*)hist, (long long)hist_base, u_lin);
     XDFM_LAUNCH_CHECK();
   }
-  int blocks = (int)min((int64_t)xdfm_num_sms() * 8, ceil_div64(n, 256));
-  segment_of_lookup_kernel<<<max(blocks, 1), 256, 0, st>>>(seg_offsets, sorted_pos, num_segments, n, inv);
-  XDFM_LAUNCH_CHECK();
+  if (inv != nullptr) {
+    int blocks = (int)min((int64_t)xdfm_num_sms() * 8, ceil_div64(n, 256));
+    segment_of_lookup_kernel<<<max(blocks, 1), 256, 0, st>>>(seg_offsets, sorted_pos, num_segments, n, inv);
+    XDFM_LAUNCH_CHECK();
+  }
   return XDFM_OK;
 }
 

@@ -375,13 +375,23 @@ class ShardedSparse:
         if self._uniq is None or not self._segments_current(ids) or any(p in self._uniq for p in need):
             self._segments_of(ids)
             lz = self.lazy
-            with ops.timed("embed_gather"):
+            def fetch(u_emb, u_lin, inv):
                 N.check(L.xdfm_embed_fetch_unique_sharded(
                     N.ptr(self.peer_ptrs), self.G, self.S, self.D, N.ptr(self.x_keys), N.ptr(self.seg_off), N.ptr(self.pos), N.ptr(self.nseg),
                     B * m, lz["cfg_emb"] if lz else None, lz["cfg_lin"] if lz else None, N.ptr(lz["opt_dev"]) if lz else None,
-                    N.ptr(lz["hist"]) if lz else None, lz["hist_base"] if lz else 0, N.ptr(self.u_emb), N.ptr(self.u_lin), N.ptr(self.inv), st))
+                    N.ptr(lz["hist"]) if lz else None, lz["hist_base"] if lz else 0, N.ptr(u_emb), N.ptr(u_lin), N.ptr(inv), st))
+
+            if ops.TIMERS is not None:          # operator-timing pass: the three kernels one by one
+                with ops.timed("embed_gather"):
+                    fetch(self.u_emb, None, None)
+                with ops.timed("embed_gather_lin"):
+                    fetch(None, self.u_lin, None)
+                with ops.timed("embed_expand"):
+                    fetch(None, None, self.inv)
+            else:
+                fetch(self.u_emb, self.u_lin, self.inv)
             self._uniq = set()
-        with ops.timed("embed_gather"):
+        with ops.timed("embed_expand"):
             if out is not None or lin is not None:
                 N.check(L.xdfm_embed_expand_unique(N.ptr(self.u_emb), N.ptr(self.u_lin), N.ptr(self.inv), B, m, self.D, N.ptr(out),
                                                    N.ptr(dense) if nd > 0 else None, nd, N.ptr(dense_w) if nd > 0 else None, N.ptr(lin), st))
@@ -477,7 +487,7 @@ class ShardedSparse:
         L = N.lib()
         st = N.stream_ptr()
         n_cap = self.cap * self.G
-        with ops.timed("embed_scatter"):
+        with ops.timed("embed_pull"):
             N.check(L.xdfm_shard_pull_segments(self._c_peer_keys, self._c_peer_gsum, self._c_peer_gsum_lin, self._c_peer_ranges, self.G,
                                                self.rank, self.S, self.D, n_cap, N.ptr(self.ws), self.ws.numel(), N.ptr(self.p_rows),
                                                N.ptr(self.p_rows_lin), N.ptr(self.p_uniq), N.ptr(self.p_seg_off), N.ptr(self.p_pos),
