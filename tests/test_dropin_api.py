@@ -98,3 +98,27 @@ def test_varlen_feature_column_surface_matches_the_reference():
     assert {k: tuple(t.weight.shape) for k, t in lin.items()} == {"item": (30, 1), "tags": (9, 1)}
     with pytest.raises(TypeError):
         build_input_features([type("Other", (), {"name": "x"})()])               # inputs.py:121-122
+
+
+def test_column_selection_is_shared_between_the_deep_and_the_first_order_part():
+    """Host logic: BaseModel._select hands both parts ONE tensor for the same columns of the same batch (the row-sharded lookup
+    recognises a batch by tensor identity and fetches its distinct rows once), and forgets it when the batch is rewritten in place
+    or another batch arrives."""
+    spec = O.ModelSpec(sparse_names=["C1", "C2", "C3"], vocab_sizes=[5, 7, 9], embedding_dim=4, dense_names=["I1"],
+                       cin_layer_size=(8, 4), dnn_hidden_units=(8,))
+    model = build_product_model(spec, "cpu")
+    ids = torch.arange(12, dtype=torch.int32).reshape(4, 3)
+    assert model._select(ids, None) is ids
+    a = model._select(ids, [0, 2])
+    assert model._select(ids, [0, 2]) is a and a.tolist() == [[0, 2], [3, 5], [6, 8], [9, 11]]
+    assert model._select(ids, [1]) is not a
+    b = model._select(ids, [0, 2])                       # a different selection in between: recomputed, same values
+    assert torch.equal(a, b)
+    ids.add_(1)                                          # in-place write bumps the version
+    c = model._select(ids, [0, 2])
+    assert c is not b and c.tolist() == [[1, 3], [4, 6], [7, 9], [10, 12]]
+    other = ids.clone()
+    assert model._select(other, [0, 2]) is not c
+    dense = torch.rand(4, 2)
+    d = model._select(dense, [1])
+    assert model._select(ids, [0, 2]).dtype == torch.int32 and model._select(dense, [1]) is d      # one memo per dtype
