@@ -555,7 +555,7 @@ def direct_param_grads(on):
 def _grad_dst(param, shape=None):
     """-> (tensor the kernel writes d(param) into, value to return to autograd for it)."""
     shape = tuple(param.shape) if shape is None else tuple(shape)
-    g = param.grad if (_DIRECT["on"] and isinstance(param, torch.nn.Parameter) and param.is_leaf) else None
+    g = param.grad if (_DIRECT["on"] and isinstance(param, torch.nn.Parameter) and param.is_leaf and param.requires_grad) else None
     if g is not None and g.dtype == torch.float32 and g.is_cuda and g.is_contiguous() and g.shape == param.shape and \
             id(param) not in _DIRECT["done"]:
         _DIRECT["done"].add(id(param))
